@@ -1,0 +1,391 @@
+"""CPU oracle for the FSRNet face-hallucination path.  TEST INFRASTRUCTURE ONLY.
+
+This file is a plain-PyTorch (CPU, fp32) restatement of the reference algorithm.  It is imported only by
+``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py``;
+the product package never imports it.
+
+Parity pin: the reference ships no tests or golden vectors, so the pin is live execution of
+the reference's own modules.  ``oracle/make_golden.py`` (run in the build container, where ``/root/reference``
+exists) checks every function here against the imported reference modules and writes ``tests/golden/*.npz``;
+``tests/test_oracle_golden.py`` re-checks this file against those fixtures on any box.
+
+Everything is written against a flat ``state_dict`` (name -> tensor) so the same weights can be loaded into the
+reference modules, this oracle and the CUDA drop-in modules.
+
+Reference sites restated (all paths relative to /root/reference):
+  _Residual_Block            model/FSRnet.py:75-98
+  BasicBlock (hourglass)     model/FSRnet.py:105-135
+  Hourglass                  model/FSRnet.py:176-215
+  Course_SR_Network          model/FSRnet.py:308-340
+  Fine_SR_Encoder            model/FSRnet.py:342-379
+  Prior_Estimation_Network   model/FSRnet.py:381-426
+  Fine_SR_Decoder            model/FSRnet.py:428-459
+  OverallNetwork             model/FSRnet.py:488-508 with the runnable wiring of :538-541
+  weights_init               FSR_main.py:38-58
+  MSELossFunc                loss/loss.py:7-15
+  MSELoss_Landmark           loss/loss.py:17-32
+  CrossEntropyLoss2d         loss/loss.py:34-62
+  loss composition           FSR_main.py:233-234
+"""
+import math
+from collections import OrderedDict
+
+import torch
+import torch.nn.functional as F
+
+EPS = 1e-5  # nn.InstanceNorm2d default
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# parameter inventory (state_dict order of the reference OverallNetwork: 202 keys)
+# ----------------------------------------------------------------------------------------------------------------
+def _res_block_keys(prefix, c, cin=None):
+    cin = c if cin is None else cin
+    return [
+        (prefix + "conv1.weight", (c, cin, 3, 3)),
+        (prefix + "in1.weight", (c,)), (prefix + "in1.bias", (c,)),
+        (prefix + "relu.weight", (c,)),
+        (prefix + "conv2.weight", (c, c, 3, 3)),
+        (prefix + "in2.weight", (c,)), (prefix + "in2.bias", (c,)),
+        (prefix + "relu_out.weight", (c,)),
+    ]
+
+
+def fsrnet_param_shapes():
+    """Ordered (name, shape) list, identical to ``OverallNetwork().state_dict()`` of the reference."""
+    ks = []
+    p = "_coarse_sr_network."
+    ks += [(p + "conv_input.weight", (64, 3, 3, 3)), (p + "conv_input.bias", (64,)), (p + "relu.weight", (64,))]
+    for b in range(3):
+        ks += _res_block_keys(p + "residual.%d." % b, 64)
+    ks += [(p + "conv_mid.weight", (3, 64, 3, 3)), (p + "conv_mid.bias", (3,)),
+           (p + "bn_mid.weight", (64,)), (p + "bn_mid.bias", (64,)),
+           (p + "bn_end.weight", (3,)), (p + "bn_end.bias", (3,))]
+    p = "_prior_estimation_network."
+    ks += [(p + "conv.weight", (128, 3, 7, 7)), (p + "conv.bias", (128,)),
+           (p + "bn.weight", (128,)), (p + "bn.bias", (128,)), (p + "relu.weight", (128,))]
+    for b in range(3):
+        ks += _res_block_keys(p + "residual.%d." % b, 128)
+    for b in range(3):
+        ks += _res_block_keys(p + "residual_next.%d." % b, 128)
+    for d in range(2):
+        for s in range(4 if d == 0 else 3):
+            for b in range(2):
+                q = p + "hg.hg.%d.%d.%d." % (d, s, b)
+                ks += [(q + "conv1.weight", (128, 128, 3, 3)), (q + "relu.weight", (128,)),
+                       (q + "conv2.weight", (128, 128, 3, 3))]
+    ks += [(p + "fc.weight", (11, 128, 1, 1)), (p + "fc.bias", (11,)),
+           (p + "fc_landmark.weight", (97, 128, 1, 1)), (p + "fc_landmark.bias", (97,))]
+    p = "_fine_sr_encoder."
+    ks += [(p + "conv_input.weight", (64, 3, 7, 7)), (p + "conv_input.bias", (64,)), (p + "relu.weight", (64,))]
+    for b in range(3):
+        ks += _res_block_keys(p + "residual.%d." % b, 64)
+    ks += [(p + "conv_mid.weight", (3, 64, 3, 3)), (p + "conv_mid.bias", (3,)),
+           (p + "bn_mid.weight", (64,)), (p + "bn_mid.bias", (64,)),
+           (p + "bn_end.weight", (3,)), (p + "bn_end.bias", (3,)),
+           (p + "conv_end.weight", (64, 64, 3, 3)), (p + "conv_end.bias", (64,))]
+    p = "_fine_sr_decoder."
+    ks += [(p + "conv_input.weight", (64, 192, 3, 3)), (p + "conv_input.bias", (64,)), (p + "relu.weight", (64,)),
+           (p + "bn_mid.weight", (64,)), (p + "bn_mid.bias", (64,)),
+           (p + "deconv.weight", (64, 64, 7, 7)), (p + "deconv.bias", (64,))]
+    for b in range(3):
+        ks += _res_block_keys(p + "residual.%d." % b, 64)
+    ks += [(p + "conv_out.weight", (3, 64, 3, 3)), (p + "conv_out.bias", (3,)),
+           (p + "instance_norm.weight", (3,)), (p + "instance_norm.bias", (3,))]
+    return ks
+
+
+# Parameters that never influence the oracle-wiring outputs (888 789 dead parameters).
+def fsrnet_dead_param(name):
+    return (".bn_end." in name or ".residual_next." in name or name.startswith("_fine_sr_encoder.conv_mid")
+            or ".instance_norm." in name)
+
+
+# Conv biases that feed straight into an InstanceNorm: the mean subtraction cancels them, so their gradient is
+# mathematically zero and the reference only produces rounding noise there (compare with an absolute tolerance).
+FSRNET_NULL_GRAD = ("_coarse_sr_network.conv_input.bias", "_prior_estimation_network.conv.bias",
+                    "_fine_sr_encoder.conv_input.bias", "_fine_sr_encoder.conv_end.bias",
+                    "_fine_sr_decoder.conv_input.bias", "_fine_sr_decoder.deconv.bias")
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# seeded initialisation: reproduces ``torch.manual_seed(s); OverallNetwork(); apply(weights_init)`` draw for draw
+# ----------------------------------------------------------------------------------------------------------------
+def _default_conv_init(shape, bias):
+    """nn.Conv2d / nn.ConvTranspose2d ``reset_parameters`` (torch 2.x): consumes the global RNG identically."""
+    w = torch.empty(shape)
+    torch.nn.init.kaiming_uniform_(w, a=math.sqrt(5))
+    b = None
+    if bias:
+        fan_in = shape[1] * shape[2] * shape[3]
+        bound = 1.0 / math.sqrt(fan_in)
+        b = torch.empty(shape[0])
+        torch.nn.init.uniform_(b, -bound, bound)
+    return w, b
+
+
+def build_fsrnet_state_dict(seed=1234, xavier=True):
+    """Weights as produced by the reference start-up code (FSR_main.py:128,131 with weights_init :38-58).
+
+    Constructor order matters because every Conv2d draws from the global generator when it is built:
+    Course_SR_Network (:308-322), Prior_Estimation_Network (:381-392), Fine_SR_Encoder (super().__init__ first,
+    then its own members, :342-351), Fine_SR_Decoder (:428-441).  ``weights_init`` afterwards re-draws every
+    nn.Conv2d weight with xavier_uniform_ in ``modules()`` order and zeroes conv biases; ConvTranspose2d is not an
+    nn.Conv2d instance and keeps its default init.
+    """
+    torch.manual_seed(seed)
+    sd = OrderedDict((k, None) for k, _ in fsrnet_param_shapes())
+    shapes = dict(fsrnet_param_shapes())
+
+    def conv(name, bias):
+        w, b = _default_conv_init(shapes[name + ".weight"], bias)
+        sd[name + ".weight"] = w
+        if bias:
+            sd[name + ".bias"] = b
+
+    def const(name, v):
+        sd[name] = torch.full(shapes[name], v)
+
+    def res_block(prefix):
+        conv(prefix + "conv1", False)
+        const(prefix + "in1.weight", 1.0); const(prefix + "in1.bias", 0.0); const(prefix + "relu.weight", 0.25)
+        conv(prefix + "conv2", False)
+        const(prefix + "in2.weight", 1.0); const(prefix + "in2.bias", 0.0); const(prefix + "relu_out.weight", 0.25)
+
+    def coarse_like(p, k_in):
+        # members in the order Course_SR_Network.__init__ builds them
+        if k_in == 3:
+            conv(p + "conv_input", True)
+        else:  # encoder: the inherited ctor first builds the 3x3 input conv, later replaced
+            _default_conv_init((64, 3, 3, 3), True)
+        const(p + "relu.weight", 0.25)
+        for b in range(3):
+            res_block(p + "residual.%d." % b)
+        conv(p + "conv_mid", True)
+        const(p + "bn_mid.weight", 1.0); const(p + "bn_mid.bias", 0.0)
+        const(p + "bn_end.weight", 1.0); const(p + "bn_end.bias", 0.0)
+
+    # --- OverallNetwork.__init__ (:491-494): coarse, prior, encoder, decoder ---
+    coarse_like("_coarse_sr_network.", 3)
+
+    p = "_prior_estimation_network."
+    conv(p + "conv", True)
+    const(p + "bn.weight", 1.0); const(p + "bn.bias", 0.0); const(p + "relu.weight", 0.25)
+    for b in range(3):
+        res_block(p + "residual.%d." % b)
+    for b in range(3):
+        res_block(p + "residual_next.%d." % b)
+    for d in range(2):
+        for s in range(4 if d == 0 else 3):
+            for b in range(2):
+                q = p + "hg.hg.%d.%d.%d." % (d, s, b)
+                conv(q + "conv1", False); const(q + "relu.weight", 0.25); conv(q + "conv2", False)
+    conv(p + "fc", True)
+    conv(p + "fc_landmark", True)
+
+    p = "_fine_sr_encoder."
+    coarse_like(p, 7)                        # super().__init__()
+    conv(p + "conv_input", True)             # 7x7 stride-4 stem replaces the inherited one
+    const(p + "relu.weight", 0.25)
+    const(p + "bn_mid.weight", 1.0); const(p + "bn_mid.bias", 0.0)
+    for b in range(3):
+        res_block(p + "residual.%d." % b)    # replaces the inherited residual stack
+    conv(p + "conv_end", True)
+
+    p = "_fine_sr_decoder."
+    conv(p + "conv_input", True)
+    const(p + "relu.weight", 0.25)
+    const(p + "bn_mid.weight", 1.0); const(p + "bn_mid.bias", 0.0)
+    w, b = _default_conv_init((64, 64, 7, 7), True)    # ConvTranspose2d weight is (in, out, kh, kw)
+    sd[p + "deconv.weight"], sd[p + "deconv.bias"] = w, b
+    for b_ in range(3):
+        res_block(p + "residual.%d." % b_)
+    conv(p + "conv_out", True)
+    const(p + "instance_norm.weight", 1.0); const(p + "instance_norm.bias", 0.0)
+
+    if xavier:
+        # ``model.apply(weights_init)`` (FSR_main.py:131) calls weights_init on every sub-module in post-order, and
+        # weights_init itself walks ``m.modules()`` (:45): every Conv2d is therefore re-drawn once per ancestor.
+        # The final values come from the root's pass, but every earlier draw advances the generator, so the
+        # whole recursion is replayed over the module tree (lists = containers, strings = Conv2d weights).
+        def blocks(prefix, names=("residual",)):
+            return [[[prefix + "%s.%d.conv1.weight" % (n, b), prefix + "%s.%d.conv2.weight" % (n, b)]
+                     for b in range(3)] for n in names]
+        pc, pp, pe, pd = ("_coarse_sr_network.", "_prior_estimation_network.", "_fine_sr_encoder.",
+                          "_fine_sr_decoder.")
+        hg = [[[[pp + "hg.hg.%d.%d.%d.conv1.weight" % (d, s_, b), pp + "hg.hg.%d.%d.%d.conv2.weight" % (d, s_, b)]
+                for b in range(2)] for s_ in range(4 if d == 0 else 3)] for d in range(2)]
+        tree = [
+            [pc + "conv_input.weight"] + blocks(pc) + [pc + "conv_mid.weight"],
+            [pp + "conv.weight"] + blocks(pp, ("residual", "residual_next")) + [[hg]]
+            + [pp + "fc.weight", pp + "fc_landmark.weight"],
+            [pe + "conv_input.weight"] + blocks(pe) + [pe + "conv_mid.weight", pe + "conv_end.weight"],
+            [pd + "conv_input.weight"] + blocks(pd) + [pd + "conv_out.weight"],
+        ]
+
+        def convs(node):
+            if isinstance(node, str):
+                return [node]
+            return [c for ch in node for c in convs(ch)]
+
+        def draw(k):
+            torch.nn.init.xavier_uniform_(sd[k])
+            bk = k[:-6] + "bias"
+            if bk in sd:
+                sd[bk].zero_()
+
+        def apply(node):
+            if not isinstance(node, str):
+                for ch in node:
+                    apply(ch)
+            for k in convs(node):
+                draw(k)
+        apply(tree)
+    assert all(v is not None for v in sd.values())
+    return sd
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# forward restatement
+# ----------------------------------------------------------------------------------------------------------------
+def _inorm(x, w=None, b=None):
+    # InstanceNorm2d: per-(n,c) biased variance over H*W, eps 1e-5, no running stats (train == eval)
+    mu = x.mean(dim=(2, 3), keepdim=True)
+    var = ((x - mu) ** 2).mean(dim=(2, 3), keepdim=True)
+    y = (x - mu) / torch.sqrt(var + EPS)
+    if w is not None:
+        y = y * w.view(1, -1, 1, 1) + b.view(1, -1, 1, 1)
+    return y
+
+
+def _prelu(x, a):
+    a = a.view(1, -1, 1, 1)
+    return torch.clamp(x, min=0) + a * torch.clamp(x, max=0)
+
+
+def _res_block(sd, p, x):
+    y = F.conv2d(x, sd[p + "conv1.weight"], None, 1, 1)
+    y = _prelu(_inorm(y, sd[p + "in1.weight"], sd[p + "in1.bias"]), sd[p + "relu.weight"])
+    y = F.conv2d(y, sd[p + "conv2.weight"], None, 1, 1)
+    y = _inorm(y, sd[p + "in2.weight"], sd[p + "in2.bias"]) + x
+    return _prelu(y, sd[p + "relu_out.weight"])
+
+
+def _res_stack(sd, p, x, times):
+    for _ in range(times):
+        for b in range(3):
+            x = _res_block(sd, p + "residual.%d." % b, x)
+    return x
+
+
+def _hg_block(sd, p, x):
+    y = F.conv2d(x, sd[p + "conv1.weight"], None, 1, 1)
+    y = _prelu(_inorm(y), sd[p + "relu.weight"])
+    y = F.conv2d(y, sd[p + "conv2.weight"], None, 1, 1)
+    return _prelu(_inorm(y) + x, sd[p + "relu.weight"])
+
+
+def _hg_seq(sd, p, d, s, x):
+    for b in range(2):
+        x = _hg_block(sd, p + "hg.hg.%d.%d.%d." % (d, s, b), x)
+    return x
+
+
+def _hourglass(sd, p, n, x):
+    up1 = _hg_seq(sd, p, n - 1, 0, x)
+    low1 = _hg_seq(sd, p, n - 1, 1, F.max_pool2d(x, 2, 2))
+    low2 = _hourglass(sd, p, n - 1, low1) if n > 1 else _hg_seq(sd, p, 0, 3, low1)
+    low3 = _hg_seq(sd, p, n - 1, 2, low2)
+    return up1 + F.interpolate(low3, scale_factor=2)      # default mode: nearest
+
+
+def coarse_forward(sd, x, p="_coarse_sr_network."):
+    y = F.conv2d(x, sd[p + "conv_input.weight"], sd[p + "conv_input.bias"], 1, 1)
+    y = _prelu(_inorm(y, sd[p + "bn_mid.weight"], sd[p + "bn_mid.bias"]), sd[p + "relu.weight"])
+    y = _res_stack(sd, p, y, 3)
+    feat = _inorm(y, sd[p + "bn_mid.weight"], sd[p + "bn_mid.bias"])
+    return feat, F.conv2d(feat, sd[p + "conv_mid.weight"], sd[p + "conv_mid.bias"], 1, 1)
+
+
+def encoder_forward(sd, x, p="_fine_sr_encoder."):
+    y = F.conv2d(x, sd[p + "conv_input.weight"], sd[p + "conv_input.bias"], 4, 3)
+    y = _prelu(_inorm(y, sd[p + "bn_mid.weight"], sd[p + "bn_mid.bias"]), sd[p + "relu.weight"])
+    y = _res_stack(sd, p, y, 3)
+    y = F.conv2d(y, sd[p + "conv_end.weight"], sd[p + "conv_end.bias"], 1, 1)
+    return _prelu(_inorm(y, sd[p + "bn_mid.weight"], sd[p + "bn_mid.bias"]), sd[p + "relu.weight"])
+
+
+def prior_forward(sd, x, p="_prior_estimation_network."):
+    y = F.conv2d(x, sd[p + "conv.weight"], sd[p + "conv.bias"], 4, 3)
+    y = _prelu(_inorm(y, sd[p + "bn.weight"], sd[p + "bn.bias"]), sd[p + "relu.weight"])
+    y = _res_stack(sd, p, y, 1)
+    y = _hourglass(sd, p, 2, y)
+    parsing = F.conv2d(y, sd[p + "fc.weight"], sd[p + "fc.bias"])
+    landmark = F.conv2d(y, sd[p + "fc_landmark.weight"], sd[p + "fc_landmark.bias"])
+    return y, landmark, parsing
+
+
+def decoder_forward(sd, x, p="_fine_sr_decoder."):
+    y = F.conv2d(x, sd[p + "conv_input.weight"], sd[p + "conv_input.bias"], 1, 1)
+    y = _prelu(_inorm(y, sd[p + "bn_mid.weight"], sd[p + "bn_mid.bias"]), sd[p + "relu.weight"])
+    y = F.conv_transpose2d(y, sd[p + "deconv.weight"], sd[p + "deconv.bias"], 4, 2, 1)
+    y = _prelu(_inorm(y, sd[p + "bn_mid.weight"], sd[p + "bn_mid.bias"]), sd[p + "relu.weight"])
+    y = _res_stack(sd, p, y, 3)
+    y = _inorm(y, sd[p + "bn_mid.weight"], sd[p + "bn_mid.bias"])
+    return F.conv2d(y, sd[p + "conv_out.weight"], sd[p + "conv_out.bias"], 1, 1)
+
+
+def fsrnet_forward(sd, x):
+    """OverallNetwork.forward with encoder / prior net fed by the 3-channel coarse image."""
+    _, coarse = coarse_forward(sd, x)
+    enc = encoder_forward(sd, coarse)
+    pe, landmark, parsing = prior_forward(sd, coarse)
+    out = decoder_forward(sd, torch.cat((pe, enc), 1))
+    return coarse, out, landmark, parsing
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# losses
+# ----------------------------------------------------------------------------------------------------------------
+def mse97(x, t):
+    return ((x.float() - t.float()) ** 2).mean() * 97.0
+
+
+def landmark_loss(x, t):
+    s = x.sum(dim=1)
+    return ((s.float() - t.float()) ** 2).mean() * 97.0
+
+
+def ce2d(logits, target):
+    return F.nll_loss(F.log_softmax(logits, 1), torch.squeeze(target))
+
+
+def fsrnet_loss(outputs, hr, heatmap, labels, train_batch=None, w_pix=5.0):
+    coarse, out, landmark, parsing = outputs
+    b = hr.shape[0] if train_batch is None else train_batch
+    parts = (mse97(out, hr), mse97(coarse, hr), landmark_loss(landmark, heatmap), ce2d(parsing, labels))
+    total = (w_pix * parts[0] + w_pix * parts[1] + parts[2] + parts[3]) / (2.0 * b)
+    return total, parts
+
+
+def synthetic_batch(batch, size=128, seed=4321):
+    """SURVEY.md 8d / Appendix E draw order: x, hr, labels, heat-map from one seeded generator."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(batch, 3, size, size, generator=g)
+    hr = torch.randn(batch, 3, size, size, generator=g)
+    lbl = torch.randint(0, 11, (batch, 1, size // 4, size // 4), generator=g)
+    hm = torch.rand(batch, size // 4, size // 4, generator=g)
+    return x, hr, lbl, hm
+
+
+def fsrnet_loss_and_grads(sd, x, hr, hm, lbl, train_batch=None):
+    """One forward+backward; returns (outputs, total, parts, {name: grad}) - used as the parity oracle."""
+    leaves = OrderedDict((k, v.detach().clone().requires_grad_(True)) for k, v in sd.items())
+    outs = fsrnet_forward(leaves, x)
+    total, parts = fsrnet_loss(outs, hr, hm, lbl, train_batch)
+    names = [k for k in leaves if not fsrnet_dead_param(k)]
+    grads = torch.autograd.grad(total, [leaves[k] for k in names], allow_unused=True)
+    gd = OrderedDict((k, None) for k in leaves)
+    for k, g in zip(names, grads):
+        gd[k] = g
+    return [o.detach() for o in outs], total.detach(), [p.detach() for p in parts], gd

@@ -1,0 +1,148 @@
+"""Pins the oracle restatements against the live reference and writes tests/golden/*.npz.
+
+Run in the build container only (needs /root/reference and Pillow):  python -m oracle.make_golden
+Every fixture is produced by the REFERENCE's own code (modules loaded by file path); the oracle
+restatement is asserted against it before anything is written.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+from oracle import bicubic_oracle as BO      # noqa: E402
+from oracle import eval_oracle as EO         # noqa: E402
+from oracle import fsrnet_oracle as FO       # noqa: E402
+from oracle import ref_loader as R           # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def ref_fsrnet(seed):
+    F = R.load("model/FSRnet.py")
+    torch.manual_seed(seed)
+    net = F.OverallNetwork()
+    net.apply(R.reference_weights_init)
+    net.train()
+    return net
+
+
+def ref_loss(outs, hr, hm, lbl, batch):
+    L = R.load("loss/loss.py")
+    parts = (L.MSELossFunc()(outs[1], hr), L.MSELossFunc()(outs[0], hr), L.MSELoss_Landmark()(outs[2], hm),
+             L.CrossEntropyLoss2d()(outs[3], lbl))
+    return (5. * parts[0] + 5. * parts[1] + parts[2] + parts[3]) / (2.0 * batch), parts
+
+
+def golden_fsrnet():
+    net = ref_fsrnet(1234)
+    ref_sd = net.state_dict()
+    sd = FO.build_fsrnet_state_dict(1234)
+    assert list(sd) == list(ref_sd) and all(torch.equal(sd[k], ref_sd[k]) for k in sd), "seeded init differs"
+    np.savez_compressed(os.path.join(OUT, "fsrnet_init_checksums.npz"),
+                        names=np.array(list(sd)), sums=np.array([v.double().sum().item() for v in sd.values()]),
+                        abssums=np.array([v.double().abs().sum().item() for v in sd.values()]))
+    for tag, b, size in (("small", 2, 64), ("kat128", 4, 128)):
+        x, hr, lbl, hm = FO.synthetic_batch(b, size)
+        net.zero_grad()
+        outs = R.reference_fsrnet_forward(net, x)
+        total, parts = ref_loss(outs, hr, hm, lbl, b)
+        total.backward()
+        o_outs, o_total, o_parts, gd = FO.fsrnet_loss_and_grads(ref_sd, x, hr, hm, lbl)
+        for a, c in zip(outs, o_outs):
+            assert torch.allclose(a, c, rtol=1e-4, atol=1e-4), (a - c).abs().max()
+        assert abs(total.item() - o_total.item()) <= 1e-5 * abs(total.item())
+        names, gnorm, small = [], [], {}
+        for k, p in net.named_parameters():
+            if p.grad is None:
+                assert FO.fsrnet_dead_param(k), k
+                continue
+            g = p.grad
+            if k not in FO.FSRNET_NULL_GRAD:
+                rel = ((g - gd[k]).norm() / (g.norm() + 1e-30)).item()
+                assert rel < 2e-2, (k, rel)
+            names.append(k); gnorm.append(g.norm().item())
+            if g.numel() <= 192:
+                small["grad:" + k] = g.numpy()
+        d = dict(total=total.item(), parts=np.array([p.item() for p in parts]),
+                 grad_names=np.array(names), grad_norms=np.array(gnorm),
+                 global_grad_norm=float(np.sqrt(np.sum(np.square(gnorm)))))
+        if tag == "small":
+            d.update(coarse=outs[0].detach().numpy(), out=outs[1].detach().numpy(),
+                     landmark=outs[2].detach().numpy(), parsing=outs[3].detach().numpy())
+            d.update(small)
+            for k in ("_coarse_sr_network.residual.0.conv1.weight", "_fine_sr_decoder.deconv.weight",
+                      "_prior_estimation_network.hg.hg.0.0.0.conv1.weight", "_fine_sr_encoder.conv_input.weight",
+                      "_fine_sr_decoder.conv_out.weight", "_prior_estimation_network.fc_landmark.weight"):
+                d["grad:" + k] = dict(net.named_parameters())[k].grad.numpy()
+        else:
+            d.update(out_mean=outs[1].mean().item(), out_std=outs[1].std().item(), coarse_mean=outs[0].mean().item())
+        np.savez_compressed(os.path.join(OUT, "fsrnet_%s.npz" % tag), **d)
+        print("fsrnet", tag, "total", total.item(), [p.item() for p in parts])
+
+
+def golden_losses():
+    L = R.load("loss/loss.py")
+    g = torch.Generator().manual_seed(7)
+    a = torch.randn(3, 3, 16, 16, generator=g); t = torch.randn(3, 3, 16, 16, generator=g)
+    lm = torch.randn(3, 97, 8, 8, generator=g); hm = torch.rand(3, 8, 8, generator=g)
+    lg = torch.randn(3, 11, 8, 8, generator=g); lb = torch.randint(0, 11, (3, 1, 8, 8), generator=g)
+    v = [L.MSELossFunc()(a, t), L.MSELoss_Landmark()(lm, hm), L.CrossEntropyLoss2d()(lg, lb)]
+    o = [FO.mse97(a, t), FO.landmark_loss(lm, hm), FO.ce2d(lg, lb)]
+    for x, y in zip(v, o):
+        assert torch.allclose(x, y, rtol=1e-6), (x, y)
+    np.savez_compressed(os.path.join(OUT, "losses.npz"), a=a.numpy(), t=t.numpy(), lm=lm.numpy(), hm=hm.numpy(),
+                        lg=lg.numpy(), lb=lb.numpy(), values=np.array([x.item() for x in v]))
+    print("losses", [x.item() for x in v])
+
+
+def golden_bicubic():
+    from PIL import Image
+    import PIL
+    rng = np.random.default_rng(20261018)
+    d = {"pillow_version": np.array(PIL.__version__)}
+    for s, o, n in ((16, 128, 4), (28, 224, 2), (16, 64, 1), (20, 50, 1)):
+        src = rng.integers(0, 256, (n, s, s, 3), dtype=np.uint8)
+        src[0, :, : s // 2] = 255 * (np.arange(s)[:, None, None] % 2)       # hard edges: exercises the clip
+        dst = np.stack([np.asarray(Image.fromarray(a).resize((o, o), Image.BICUBIC)) for a in src])
+        assert np.array_equal(dst, BO.bicubic_u8(src, o, o)), (s, o)
+        d["src_%d_%d" % (s, o)] = src; d["dst_%d_%d" % (s, o)] = dst
+    np.savez_compressed(os.path.join(OUT, "bicubic.npz"), **d)
+    print("bicubic ok")
+
+
+def golden_eval():
+    E = R.load("utils/eval.py")
+    U = R.load("utils/utils.py")
+    rng = np.random.RandomState(11)
+    scores = rng.standard_normal((64, 200)).astype(np.float32)
+    target = rng.randint(0, 200, 64)
+    top1 = E.accuracy(torch.from_numpy(scores), torch.from_numpy(target), topk=(1,))[0].item()
+    res = U.accuracy(torch.from_numpy(scores).contiguous(), torch.from_numpy(target), topk=(1,))
+    assert abs(EO.accuracy(scores, target, (1,))[0] - top1) < 1e-5 and abs(res[0].item() - top1) < 1e-5
+    # make some probes hits so the percentage is non-trivial
+    for i in range(0, 64, 3):
+        scores[i, target[i]] = 10.0
+    top1 = E.accuracy(torch.from_numpy(scores), torch.from_numpy(target), topk=(1,))[0].item()
+    o15 = EO.accuracy(scores, target, (1, 5))
+    assert abs(o15[0] - top1) < 1e-5
+    ref_top5_idx = torch.from_numpy(scores).topk(5, 1, True, True)[1].numpy()
+    assert np.array_equal(ref_top5_idx, EO.topk_indices(scores, 5))
+    e1 = rng.standard_normal((300, 32)).astype(np.float32); e2 = e1 + 0.8 * rng.standard_normal((300, 32)).astype(np.float32)
+    e2[150:] = rng.standard_normal((150, 32)).astype(np.float32)
+    same = np.arange(300) < 150
+    dist = np.sum(np.square(e1 - e2), 1)
+    thr = np.arange(0, 120, 3).astype(np.float64)
+    ca = np.array([U.calculate_accuracy(t, dist, same) for t in thr])
+    assert np.allclose(ca, np.array([EO.calculate_accuracy(t, dist, same) for t in thr]))
+    np.savez_compressed(os.path.join(OUT, "eval.npz"), scores=scores, target=target, top1=top1, top5_idx=ref_top5_idx,
+                        top15=np.array(o15), e1=e1, e2=e2, same=same, thr=thr, calc_acc=ca)
+    print("eval ok", top1, o15)
+
+
+if __name__ == "__main__":
+    assert R.available(), "reference tree not present"
+    os.makedirs(OUT, exist_ok=True)
+    golden_losses(); golden_bicubic(); golden_eval(); golden_fsrnet()
