@@ -1,0 +1,128 @@
+// C-ABI convolution entry points: shape validation + engine dispatch (tcgen05 implicit GEMM or CUDA-core direct).
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "common.cuh"
+#include "crfr.h"
+#include "internal.h"
+
+// ---- error string / counters -------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+unsigned long long g_crfr_launches = 0;
+
+void crfr_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char* crfr_last_error(void) { return g_err; }
+extern "C" int crfr_version(void) { return 100; }
+extern "C" unsigned long long crfr_launch_count(void) { return g_crfr_launches; }
+
+static int check_desc(const crfr_conv_desc* d, const char* who) {
+  CRFR_CHECK_ARG(d, "%s: null descriptor", who);
+  CRFR_CHECK_ARG(d->n > 0 && d->h > 0 && d->w > 0 && d->cin > 0 && d->cout > 0 && d->k > 0 && d->stride > 0 &&
+                     d->pad >= 0 && d->oh > 0 && d->ow > 0,
+                 "%s: non-positive dimension", who);
+  CRFR_CHECK_ARG(d->in_ld >= d->cin && d->out_ld >= d->cout, "%s: ld smaller than channel count", who);
+  if (!d->transposed) {
+    CRFR_CHECK_ARG(d->oh == (d->h + 2 * d->pad - d->k) / d->stride + 1 &&
+                       d->ow == (d->w + 2 * d->pad - d->k) / d->stride + 1,
+                   "%s: output size %dx%d inconsistent with Conv2d geometry", who, d->oh, d->ow);
+  } else {
+    int lo_h = (d->h - 1) * d->stride - 2 * d->pad + d->k, lo_w = (d->w - 1) * d->stride - 2 * d->pad + d->k;
+    CRFR_CHECK_ARG(d->oh >= lo_h && d->oh < lo_h + d->stride && d->ow >= lo_w && d->ow < lo_w + d->stride,
+                   "%s: output size %dx%d inconsistent with ConvTranspose2d geometry", who, d->oh, d->ow);
+  }
+  return CRFR_OK;
+}
+
+extern "C" size_t crfr_conv_workspace_bytes(const crfr_conv_desc* d) {
+  if (!d) return 0;
+  size_t norm = crfr_norm_ws_bytes(d->n, d->oh * d->ow, d->cout);
+  size_t tc = crfr_tc_workspace_bytes(d);
+  return (norm > tc ? norm : tc) + 1024;
+}
+
+extern "C" int crfr_conv_engine_supported(int engine, int op, int h, int w, int cin, int cout, int k, int stride,
+                                          int pad) {
+  if (engine == CRFR_ENGINE_DIRECT) return 1;
+  return crfr_tc_supported(op, h, w, cin, cout, k, stride, pad);
+}
+
+extern "C" int crfr_conv_fwd(int engine, const crfr_conv_desc* d, const void* x, const void* w_packed, int cin_pad,
+                             const float* bias, void* y, float* y_nchw, float* stats, float eps, void* ws,
+                             size_t ws_bytes, void* stream) {
+  CRFR_TRY(check_desc(d, "conv_fwd"));
+  CRFR_CHECK_ARG(x && w_packed && (y || y_nchw), "conv_fwd: null pointer");
+  CRFR_CHECK_ARG(cin_pad >= d->cin && d->in_ld >= cin_pad, "conv_fwd: cin_pad %d vs cin %d / in_ld %d", cin_pad,
+                 d->cin, d->in_ld);
+  CRFR_CHECK_ARG(!stats || y, "conv_fwd: statistics need the bf16 output");
+  cudaStream_t st = (cudaStream_t)stream;
+  bool tc = false;
+  if (engine != CRFR_ENGINE_DIRECT && !d->transposed && y && !y_nchw && cin_pad == d->cin &&
+      crfr_tc_supported(0, d->h, d->w, d->cin, d->cout, d->k, d->stride, d->pad)) {
+    tc = true;
+  }
+  if (engine == CRFR_ENGINE_TCGEN05 && !tc) {
+    crfr_set_error("conv_fwd: shape not supported by the tcgen05 engine");
+    return CRFR_EUNSUPPORTED;
+  }
+  if (tc) return crfr_tc_conv(d, 0, x, w_packed, bias, y, stats, eps, ws, ws_bytes, st);
+  if (!d->transposed)
+    CRFR_TRY(crfr_direct_gather(1, d->n, d->h, d->w, d->oh, d->ow, d->k, d->stride, d->pad, x, d->in_ld, w_packed,
+                                d->cout, cin_pad, bias, y, d->out_ld, y_nchw, st));
+  else
+    CRFR_TRY(crfr_direct_gather(0, d->n, d->oh, d->ow, d->h, d->w, d->k, d->stride, d->pad, x, d->in_ld, w_packed,
+                                d->cout, cin_pad, bias, y, d->out_ld, y_nchw, st));
+  if (stats) CRFR_TRY(crfr_norm_stats(y, d->n, d->oh * d->ow, d->cout, d->out_ld, eps, stats, ws, ws_bytes, stream));
+  return CRFR_OK;
+}
+
+extern "C" int crfr_conv_dgrad(int engine, const crfr_conv_desc* d, const void* dy, const void* w_packed_t,
+                               int cout_pad, void* dx, void* ws, size_t ws_bytes, void* stream) {
+  CRFR_TRY(check_desc(d, "conv_dgrad"));
+  CRFR_CHECK_ARG(dy && w_packed_t && dx, "conv_dgrad: null pointer");
+  CRFR_CHECK_ARG(cout_pad >= d->cout && d->out_ld >= cout_pad, "conv_dgrad: cout_pad %d vs cout %d / out_ld %d",
+                 cout_pad, d->cout, d->out_ld);
+  cudaStream_t st = (cudaStream_t)stream;
+  bool tc = engine != CRFR_ENGINE_DIRECT && !d->transposed && cout_pad == d->cout &&
+            crfr_tc_supported(1, d->h, d->w, d->cin, d->cout, d->k, d->stride, d->pad);
+  if (engine == CRFR_ENGINE_TCGEN05 && !tc) {
+    crfr_set_error("conv_dgrad: shape not supported by the tcgen05 engine");
+    return CRFR_EUNSUPPORTED;
+  }
+  if (tc) return crfr_tc_conv(d, 1, dy, w_packed_t, nullptr, dx, nullptr, 0.f, ws, ws_bytes, st);
+  if (!d->transposed)
+    return crfr_direct_gather(0, d->n, d->h, d->w, d->oh, d->ow, d->k, d->stride, d->pad, dy, d->out_ld, w_packed_t,
+                              d->cin, cout_pad, nullptr, dx, d->in_ld, nullptr, st);
+  return crfr_direct_gather(1, d->n, d->oh, d->ow, d->h, d->w, d->k, d->stride, d->pad, dy, d->out_ld, w_packed_t,
+                            d->cin, cout_pad, nullptr, dx, d->in_ld, nullptr, st);
+}
+
+extern "C" int crfr_conv_wgrad(int engine, const crfr_conv_desc* d, const void* x, const void* dy, float* dw,
+                               float* dbias, void* ws, size_t ws_bytes, void* stream) {
+  CRFR_TRY(check_desc(d, "conv_wgrad"));
+  CRFR_CHECK_ARG(x && dy && (dw || dbias), "conv_wgrad: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dw) {
+    bool tc = engine != CRFR_ENGINE_DIRECT && !d->transposed &&
+              crfr_tc_supported(2, d->h, d->w, d->cin, d->cout, d->k, d->stride, d->pad);
+    if (engine == CRFR_ENGINE_TCGEN05 && !tc) {
+      crfr_set_error("conv_wgrad: shape not supported by the tcgen05 engine");
+      return CRFR_EUNSUPPORTED;
+    }
+    if (tc) {
+      CRFR_TRY(crfr_tc_wgrad(d, x, dy, dw, ws, ws_bytes, st));
+    } else if (!d->transposed) {
+      CRFR_TRY(crfr_direct_wgrad(d->n, d->h, d->w, d->oh, d->ow, d->k, d->stride, d->pad, dy, d->out_ld, d->cout, x,
+                                 d->in_ld, d->cin, dw, st));
+    } else {
+      CRFR_TRY(crfr_direct_wgrad(d->n, d->oh, d->ow, d->h, d->w, d->k, d->stride, d->pad, x, d->in_ld, d->cin, dy,
+                                 d->out_ld, d->cout, dw, st));
+    }
+  }
+  if (dbias) CRFR_TRY(crfr_colsum(dy, d->out_ld, d->cout, (long long)d->n * d->oh * d->ow, dbias, st));
+  return CRFR_OK;
+}

@@ -1,0 +1,610 @@
+// Native FSRNet network program: the whole OverallNetwork forward / backward / train step is sequenced here in C++
+// (no per-layer Python), on one stream, over a caller-provided workspace arena.
+//
+// The forward pass records a tape of fused ops (conv [+ InstanceNorm statistics], normalise+PReLU(+residual),
+// max-pool, nearest-up+add, concat-by-view); the backward pass replays the tape in reverse.  A tensor that feeds
+// several consumers gets one gradient "slot" per consumer; the producer's backward sums them on the fly
+// (norm_act_bwd reads two) or with one add_n launch.  Because the arena is a deterministic bump allocator, the
+// backward entry point rebuilds the tape with a dry run of the forward (no launches) and finds every saved
+// activation at the same offset.
+//
+// ref: model/FSRnet.py:75-98 (_Residual_Block), :105-135 (BasicBlock), :176-215 (Hourglass), :308-340 (coarse),
+//      :342-379 (encoder), :381-426 (prior), :428-459 (decoder), :488-508 + :538-541 (OverallNetwork wiring),
+//      FSR_main.py:233-234 (loss composition).
+#include <vector>
+
+#include "common.cuh"
+#include "crfr.h"
+#include "internal.h"
+
+// dst[ci][coff + r] = w[r][ci]  (transposed 1x1 weights into a column range of a wider matrix)
+int crfr_pack_weight_cols(const float* w, void* dst, int cin, int rows, int ld, int coff, cudaStream_t st);
+
+namespace {
+
+constexpr float kEps = 1e-5f;
+
+// ---- parameter table (state_dict order, 202 entries) ---------------------------------------------
+enum { RB_CONV1 = 0, RB_IN1_W, RB_IN1_B, RB_RELU, RB_CONV2, RB_IN2_W, RB_IN2_B, RB_RELU_OUT };
+enum {
+  C_CONV_IN_W = 0, C_CONV_IN_B = 1, C_RELU = 2, C_RES = 3, C_CONV_MID_W = 27, C_CONV_MID_B = 28, C_BN_MID_W = 29,
+  C_BN_MID_B = 30,
+  P_CONV_W = 33, P_CONV_B = 34, P_BN_W = 35, P_BN_B = 36, P_RELU = 37, P_RES = 38, P_HG = 86, P_FC_W = 128,
+  P_FC_B = 129, P_FCL_W = 130, P_FCL_B = 131,
+  E_CONV_IN_W = 132, E_CONV_IN_B = 133, E_RELU = 134, E_RES = 135, E_BN_MID_W = 161, E_BN_MID_B = 162,
+  E_CONV_END_W = 165, E_CONV_END_B = 166,
+  D_CONV_IN_W = 167, D_CONV_IN_B = 168, D_RELU = 169, D_BN_MID_W = 170, D_BN_MID_B = 171, D_DECONV_W = 172,
+  D_DECONV_B = 173, D_RES = 174, D_CONV_OUT_W = 198, D_CONV_OUT_B = 199
+};
+inline int hg_param(int d, int s, int b, int which) { return P_HG + (d == 0 ? 0 : 24) + ((s * 2 + b) * 3) + which; }
+
+struct Tensor {
+  bf16* p = nullptr;
+  int n = 0, h = 0, w = 0, c = 0, ld = 0;
+  int id = -1;
+};
+
+struct Slot {
+  bf16* p;
+  int ld;
+};
+
+enum OpKind { OP_CONV, OP_NORM, OP_POOL, OP_UPADD, OP_CAT, OP_HEADS, OP_IMGCONV };
+
+struct Op {
+  OpKind kind;
+  Tensor a, b, out;        // inputs / output
+  crfr_conv_desc cd;       // OP_CONV / OP_IMGCONV
+  int w_idx = -1, b_idx = -1, g_idx = -1, beta_idx = -1, alpha_idx = -1;
+  int cin_pad = 0;
+  float* stats = nullptr;  // OP_NORM
+  bool has_res = false;
+  bool x_needs_grad = true;
+};
+
+struct Net {
+  int engine;
+  const float* const* params;
+  float* const* grads;
+  const crfr_fsrnet_io* io;
+  cudaStream_t st;
+  uint8_t* ws;
+  size_t ws_bytes, off = 0;
+  bool exec;        // false: dry run (allocate + record only)
+  bool training;
+  int err = CRFR_OK;
+  std::vector<Op> tape;
+  std::vector<std::vector<Slot>> slots;
+  void* packed_fwd[CRFR_FSRNET_NPARAMS];
+  void* packed_bwd[CRFR_FSRNET_NPARAMS];
+  void* scratch = nullptr;
+  size_t scratch_bytes = 0;
+  // fixed buffers
+  Tensor x4, coarse4, cat;
+  // output gradients (bf16): NHWC4 images and the combined 112-wide heads buffer
+  bf16* d_coarse4 = nullptr;
+  bf16* d_out4 = nullptr;
+  bf16* d_heads = nullptr;
+
+  void* alloc(size_t bytes) {
+    size_t a = (off + 1023) & ~(size_t)1023;
+    if (a + bytes > ws_bytes) {
+      if (err == CRFR_OK) {
+        crfr_set_error("fsrnet: workspace too small (%zu needed so far, %zu given)", a + bytes, ws_bytes);
+        err = CRFR_EWORKSPACE;
+      }
+      off = a + bytes;  // keep counting so the dry run reports the total
+      return ws;        // harmless pointer, nothing executes after an error
+    }
+    off = a + bytes;
+    return ws + a;
+  }
+  bool ok() const { return err == CRFR_OK; }
+  bool run() const { return exec && err == CRFR_OK; }
+  void check(int rc) {
+    if (rc != CRFR_OK && err == CRFR_OK) err = rc;
+  }
+  Tensor new_tensor(int n, int h, int w, int c) {
+    Tensor t;
+    t.n = n; t.h = h; t.w = w; t.c = c; t.ld = c;
+    t.p = (bf16*)alloc((size_t)n * h * w * c * sizeof(bf16));
+    t.id = (int)slots.size();
+    slots.emplace_back();
+    return t;
+  }
+  Tensor view(const Tensor& base, int coff, int c) {
+    Tensor t = base;
+    t.p = base.p + coff;
+    t.c = c;
+    t.id = (int)slots.size();
+    slots.emplace_back();
+    return t;
+  }
+
+  // ---- weight packing (once per call and per direction) ----
+  void* pack(int idx, int cout, int cin, int k, int cin_pad, bool transposed_conv, bool for_dgrad) {
+    void** cache = for_dgrad ? packed_bwd : packed_fwd;
+    if (cache[idx]) return cache[idx];
+    const int T = k * k;
+    int R, S, s_pad;
+    long long rs, ss;
+    if (!transposed_conv) {           // Conv2d weight [cout][cin][k][k]
+      if (!for_dgrad) { R = cout; S = cin; rs = (long long)cin * T; ss = T; }
+      else            { R = cin; S = cout; rs = T; ss = (long long)cin * T; }
+    } else {                          // ConvTranspose2d weight [cin][cout][k][k]
+      if (!for_dgrad) { R = cout; S = cin; rs = T; ss = (long long)cout * T; }
+      else            { R = cin; S = cout; rs = (long long)cout * T; ss = T; }
+    }
+    s_pad = for_dgrad ? ((S + 7) / 8) * 8 : cin_pad;
+    if (for_dgrad && S < 8) s_pad = 4;
+    void* dst = alloc((size_t)T * R * s_pad * sizeof(bf16));
+    if (run()) check(crfr_pack_weight(params[idx], dst, T, R, S, s_pad, rs, ss, 1, st));
+    cache[idx] = dst;
+    return dst;
+  }
+
+  // ---- forward ops ----
+  Tensor conv(const Tensor& x, int w_idx, int b_idx, int cout, int k, int stride, int pad, bool transposed,
+              float** stats_out, const Tensor* out_view = nullptr, bool x_needs_grad = true) {
+    Op op;
+    op.kind = OP_CONV;
+    crfr_conv_desc& d = op.cd;
+    d.n = x.n; d.h = x.h; d.w = x.w; d.cin = x.c; d.cout = cout; d.k = k; d.stride = stride; d.pad = pad;
+    d.transposed = transposed ? 1 : 0;
+    if (!transposed) {
+      d.oh = (x.h + 2 * pad - k) / stride + 1;
+      d.ow = (x.w + 2 * pad - k) / stride + 1;
+    } else {
+      d.oh = x.h * stride;  // k=7, s=4, p=2, output_padding=1 -> exactly 4x
+      d.ow = x.w * stride;
+    }
+    Tensor y = out_view ? *out_view : new_tensor(x.n, d.oh, d.ow, cout);
+    d.in_ld = x.ld; d.out_ld = y.ld;
+    op.cin_pad = x.c < 8 ? 4 : x.c;
+    void* wp = pack(w_idx, cout, x.c, k, op.cin_pad, transposed, false);
+    float* stats = nullptr;
+    if (stats_out) {
+      stats = (float*)alloc((size_t)x.n * cout * 2 * sizeof(float));
+      *stats_out = stats;
+    }
+    if (run())
+      check(crfr_conv_fwd(engine, &d, x.p, wp, op.cin_pad, b_idx >= 0 ? params[b_idx] : nullptr, y.p, nullptr, stats,
+                          kEps, scratch, scratch_bytes, st));
+    op.a = x; op.out = y; op.w_idx = w_idx; op.b_idx = b_idx; op.x_needs_grad = x_needs_grad;
+    tape.push_back(op);
+    return y;
+  }
+
+  float* stats_of(const Tensor& y) {
+    float* stats = (float*)alloc((size_t)y.n * y.c * 2 * sizeof(float));
+    if (run()) check(crfr_norm_stats(y.p, y.n, y.h * y.w, y.c, y.ld, kEps, stats, scratch, scratch_bytes, st));
+    return stats;
+  }
+
+  Tensor norm_act(const Tensor& y, float* stats, int g_idx, int beta_idx, int alpha_idx, const Tensor* res,
+                  const Tensor* out_view = nullptr) {
+    Tensor out = out_view ? *out_view : new_tensor(y.n, y.h, y.w, y.c);
+    if (run())
+      check(crfr_norm_act_fwd(y.p, y.ld, stats, g_idx >= 0 ? params[g_idx] : nullptr,
+                              beta_idx >= 0 ? params[beta_idx] : nullptr, alpha_idx >= 0 ? params[alpha_idx] : nullptr,
+                              0, res ? res->p : nullptr, res ? res->ld : 8, out.p, out.ld, y.n, y.h * y.w, y.c, st));
+    Op op;
+    op.kind = OP_NORM;
+    op.a = y; op.out = out; op.stats = stats; op.g_idx = g_idx; op.beta_idx = beta_idx; op.alpha_idx = alpha_idx;
+    op.has_res = res != nullptr;
+    if (res) op.b = *res;
+    tape.push_back(op);
+    return out;
+  }
+
+  Tensor maxpool(const Tensor& x) {
+    Tensor out = new_tensor(x.n, x.h / 2, x.w / 2, x.c);
+    if (run()) check(crfr_maxpool2_fwd(x.p, x.ld, out.p, out.ld, x.n, x.h, x.w, x.c, st));
+    Op op;
+    op.kind = OP_POOL; op.a = x; op.out = out;
+    tape.push_back(op);
+    return out;
+  }
+
+  Tensor upadd(const Tensor& up, const Tensor& low, const Tensor* out_view = nullptr) {
+    Tensor out = out_view ? *out_view : new_tensor(up.n, up.h, up.w, up.c);
+    if (run()) check(crfr_upnearest2_add_fwd(up.p, up.ld, low.p, low.ld, out.p, out.ld, low.n, low.h, low.w, low.c, st));
+    Op op;
+    op.kind = OP_UPADD; op.a = up; op.b = low; op.out = out;
+    tape.push_back(op);
+    return out;
+  }
+
+  // ---- network pieces ----
+  Tensor res_block(const Tensor& x, int base) {   // _Residual_Block, FSRnet.py:75-98
+    float* s1; float* s2;
+    Tensor y1 = conv(x, base + RB_CONV1, -1, x.c, 3, 1, 1, false, &s1);
+    Tensor a1 = norm_act(y1, s1, base + RB_IN1_W, base + RB_IN1_B, base + RB_RELU, nullptr);
+    Tensor y2 = conv(a1, base + RB_CONV2, -1, x.c, 3, 1, 1, false, &s2);
+    return norm_act(y2, s2, base + RB_IN2_W, base + RB_IN2_B, base + RB_RELU_OUT, &x);
+  }
+  Tensor res_stack(Tensor x, int base, int times) {
+    for (int t = 0; t < times; ++t)
+      for (int b = 0; b < 3; ++b) x = res_block(x, base + 8 * b);
+    return x;
+  }
+  Tensor hg_block(const Tensor& x, int d, int s, int b) {  // BasicBlock :105-135
+    float* s1; float* s2;
+    Tensor y1 = conv(x, hg_param(d, s, b, 0), -1, 128, 3, 1, 1, false, &s1);
+    Tensor a1 = norm_act(y1, s1, -1, -1, hg_param(d, s, b, 1), nullptr);
+    Tensor y2 = conv(a1, hg_param(d, s, b, 2), -1, 128, 3, 1, 1, false, &s2);
+    return norm_act(y2, s2, -1, -1, hg_param(d, s, b, 1), &x);
+  }
+  Tensor hg_seq(const Tensor& x, int d, int s) { return hg_block(hg_block(x, d, s, 0), d, s, 1); }
+  Tensor hourglass(int n, const Tensor& x, const Tensor* out_view) {  // Hourglass._hour_glass_forward :200-212
+    Tensor up1 = hg_seq(x, n - 1, 0);
+    Tensor low1 = hg_seq(maxpool(x), n - 1, 1);
+    Tensor low2 = n > 1 ? hourglass(n - 1, low1, nullptr) : hg_seq(low1, 0, 3);
+    Tensor low3 = hg_seq(low2, n - 1, 2);
+    return upadd(up1, low3, out_view);
+  }
+
+  // 64 -> 3 output convolution: fp32 NCHW result for the caller (+ optional bf16 NHWC4 copy for the stems)
+  void img_conv(const Tensor& x, int w_idx, int b_idx, float* y_nchw, Tensor* y4) {
+    Op op;
+    op.kind = OP_IMGCONV;
+    crfr_conv_desc& d = op.cd;
+    d.n = x.n; d.h = x.h; d.w = x.w; d.cin = x.c; d.cout = 3; d.k = 3; d.stride = 1; d.pad = 1; d.oh = x.h; d.ow = x.w;
+    d.in_ld = x.ld; d.out_ld = 4; d.transposed = 0;
+    op.cin_pad = x.c;
+    void* wp = pack(w_idx, 3, x.c, 3, x.c, false, false);
+    if (run()) {
+      if (y4) check(cudaMemsetAsync(y4->p, 0, (size_t)x.n * x.h * x.w * 4 * sizeof(bf16), st) == cudaSuccess ? CRFR_OK : CRFR_ECUDA);
+      check(crfr_conv_fwd(CRFR_ENGINE_DIRECT, &d, x.p, wp, x.c, params[b_idx], y4 ? y4->p : nullptr, y_nchw, nullptr,
+                          kEps, scratch, scratch_bytes, st));
+    }
+    op.a = x; op.w_idx = w_idx; op.b_idx = b_idx;
+    if (y4) op.out = *y4;
+    tape.push_back(op);
+  }
+
+  void heads(const Tensor& x) {   // fc (11) and fc_landmark (97): 1x1 convs with fp32 NCHW outputs
+    const int idx[2][2] = {{P_FC_W, P_FC_B}, {P_FCL_W, P_FCL_B}};
+    const int couts[2] = {11, 97};
+    float* outs[2] = {io->parsing, io->landmark};
+    for (int i = 0; i < 2; ++i) {
+      crfr_conv_desc d;
+      d.n = x.n; d.h = x.h; d.w = x.w; d.cin = x.c; d.cout = couts[i]; d.k = 1; d.stride = 1; d.pad = 0;
+      d.oh = x.h; d.ow = x.w; d.in_ld = x.ld; d.out_ld = couts[i]; d.transposed = 0;
+      void* wp = pack(idx[i][0], couts[i], x.c, 1, x.c, false, false);
+      if (run())
+        check(crfr_conv_fwd(CRFR_ENGINE_DIRECT, &d, x.p, wp, x.c, params[idx[i][1]], nullptr, outs[i], nullptr, kEps,
+                            scratch, scratch_bytes, st));
+    }
+    Op op;
+    op.kind = OP_HEADS; op.a = x;
+    tape.push_back(op);
+  }
+
+  void forward() {
+    const int B = io->batch, S = io->size;
+    for (int i = 0; i < CRFR_FSRNET_NPARAMS; ++i) packed_fwd[i] = packed_bwd[i] = nullptr;
+    // shared scratch: norm partials / wgrad accumulators of the largest layer
+    scratch_bytes = crfr_norm_ws_bytes(B, S * S, 128) + sizeof(float) * 9 * 192 * 128 + 4096;
+    scratch = alloc(scratch_bytes);
+    x4 = new_tensor(B, S, S, 4);
+    x4.c = 3;
+    if (run()) check(crfr_nchw_f32_to_nhwc_bf16(io->x, x4.p, B, 3, S, S, 4, 4, st));
+
+    // ---- coarse SR network (:328-340) ----
+    float* s0;
+    Tensor y = conv(x4, C_CONV_IN_W, C_CONV_IN_B, 64, 3, 1, 1, false, &s0, nullptr, false);
+    Tensor a = norm_act(y, s0, C_BN_MID_W, C_BN_MID_B, C_RELU, nullptr);
+    a = res_stack(a, C_RES, 3);
+    Tensor feat = norm_act(a, stats_of(a), C_BN_MID_W, C_BN_MID_B, -1, nullptr);
+    coarse4 = new_tensor(B, S, S, 4);
+    coarse4.c = 3;
+    img_conv(feat, C_CONV_MID_W, C_CONV_MID_B, io->coarse, &coarse4);
+
+    const int Q = S / 4;
+    cat = new_tensor(B, Q, Q, 192);
+    Tensor pe_view = view(cat, 0, 128), enc_view = view(cat, 128, 64);
+
+    // ---- fine SR encoder (:359-379) ----
+    float* se;
+    Tensor ye = conv(coarse4, E_CONV_IN_W, E_CONV_IN_B, 64, 7, 4, 3, false, &se);
+    Tensor ae = norm_act(ye, se, E_BN_MID_W, E_BN_MID_B, E_RELU, nullptr);
+    ae = res_stack(ae, E_RES, 3);
+    float* se2;
+    Tensor ye2 = conv(ae, E_CONV_END_W, E_CONV_END_B, 64, 3, 1, 1, false, &se2);
+    norm_act(ye2, se2, E_BN_MID_W, E_BN_MID_B, E_RELU, nullptr, &enc_view);
+
+    // ---- prior estimation network (:408-426) ----
+    float* sp;
+    Tensor yp = conv(coarse4, P_CONV_W, P_CONV_B, 128, 7, 4, 3, false, &sp);
+    Tensor ap = norm_act(yp, sp, P_BN_W, P_BN_B, P_RELU, nullptr);
+    ap = res_stack(ap, P_RES, 1);
+    Tensor pe = hourglass(2, ap, &pe_view);
+    heads(pe);
+
+    // ---- fine SR decoder (:448-459) on cat(prior, encoder) (:505) ----
+    Op cop;
+    cop.kind = OP_CAT; cop.a = pe_view; cop.b = enc_view; cop.out = cat;
+    tape.push_back(cop);
+    float* sd;
+    Tensor yd = conv(cat, D_CONV_IN_W, D_CONV_IN_B, 64, 3, 1, 1, false, &sd);
+    Tensor ad = norm_act(yd, sd, D_BN_MID_W, D_BN_MID_B, D_RELU, nullptr);
+    float* sd2;
+    Tensor yd2 = conv(ad, D_DECONV_W, D_DECONV_B, 64, 7, 4, 2, true, &sd2);
+    Tensor ad2 = norm_act(yd2, sd2, D_BN_MID_W, D_BN_MID_B, D_RELU, nullptr);
+    ad2 = res_stack(ad2, D_RES, 3);
+    Tensor fd = norm_act(ad2, stats_of(ad2), D_BN_MID_W, D_BN_MID_B, -1, nullptr);
+    img_conv(fd, D_CONV_OUT_W, D_CONV_OUT_B, io->out, nullptr);
+  }
+
+  // ---- backward helpers ----
+  float* grad(int idx) { return (grads && idx >= 0) ? grads[idx] : nullptr; }
+  void add_slot(const Tensor& t, bf16* p, int ld) { slots[t.id].push_back({p, ld}); }
+  // reduce the slots of t to at most `max_slots`
+  void squash(const Tensor& t, size_t max_slots) {
+    std::vector<Slot>& s = slots[t.id];
+    while (s.size() > max_slots) {
+      const bool three = s.size() >= 3;
+      const int cc = t.c < 8 ? 4 : t.c;
+      bf16* out = (bf16*)alloc((size_t)t.n * t.h * t.w * cc * sizeof(bf16));
+      size_t k = s.size();
+      Slot a = s[k - 1], b = s[k - 2], c = three ? s[k - 3] : Slot{nullptr, cc};
+      if (run()) check(crfr_add_n(a.p, a.ld, b.p, b.ld, c.p, c.ld, out, cc, (long long)t.n * t.h * t.w, cc, st));
+      s.resize(k - (three ? 3 : 2));
+      s.push_back({out, cc});
+    }
+  }
+  bool has_grad(const Tensor& t) const { return t.id >= 0 && !slots[t.id].empty(); }
+
+  void backward() {
+    for (int i = (int)tape.size() - 1; i >= 0 && ok(); --i) {
+      Op& op = tape[i];
+      switch (op.kind) {
+        case OP_NORM: {
+          if (!has_grad(op.out)) break;
+          squash(op.out, 2);
+          std::vector<Slot>& s = slots[op.out.id];
+          const Tensor& y = op.a;
+          const size_t bytes = (size_t)y.n * y.h * y.w * y.c * sizeof(bf16);
+          bf16* dz = (bf16*)alloc(bytes);
+          bf16* dy = (bf16*)alloc(bytes);
+          if (run()) check(crfr_norm_act_bwd(s[0].p, s[0].ld, s.size() > 1 ? s[1].p : nullptr, s.size() > 1 ? s[1].ld : 8, y.p, y.ld,
+                                  op.stats, op.g_idx >= 0 ? params[op.g_idx] : nullptr,
+                                  op.beta_idx >= 0 ? params[op.beta_idx] : nullptr,
+                                  op.alpha_idx >= 0 ? params[op.alpha_idx] : nullptr, 0,
+                                  op.has_res ? op.b.p : nullptr, op.has_res ? op.b.ld : 8, dz, y.c, dy, y.c,
+                                  grad(op.g_idx), grad(op.beta_idx), grad(op.alpha_idx), y.n, y.h * y.w, y.c, scratch,
+                                  scratch_bytes, st));
+          add_slot(y, dy, y.c);
+          if (op.has_res) add_slot(op.b, dz, y.c);
+          break;
+        }
+        case OP_CONV: {
+          if (!has_grad(op.out)) break;
+          squash(op.out, 1);
+          Slot dy = slots[op.out.id][0];
+          crfr_conv_desc d = op.cd;
+          d.out_ld = dy.ld;
+          if (run()) check(crfr_conv_wgrad(engine, &d, op.a.p, dy.p, grad(op.w_idx), grad(op.b_idx), scratch, scratch_bytes, st));
+          if (op.x_needs_grad) {
+            const Tensor& x = op.a;
+            const int xc = x.c < 8 ? 4 : x.c;
+            bf16* dx = (bf16*)alloc((size_t)x.n * x.h * x.w * xc * sizeof(bf16));
+            crfr_conv_desc dd = d;
+            dd.in_ld = xc;
+            void* wt = pack(op.w_idx, d.cout, d.cin, d.k, 0, d.transposed != 0, true);
+            const int cout_pad = d.cout;
+            if (run()) check(crfr_conv_dgrad(engine, &dd, dy.p, wt, cout_pad, dx, scratch, scratch_bytes, st));
+            add_slot(x, dx, xc);
+          }
+          break;
+        }
+        case OP_POOL: {
+          if (!has_grad(op.out)) break;
+          squash(op.out, 1);
+          Slot g = slots[op.out.id][0];
+          const Tensor& x = op.a;
+          bf16* dx = (bf16*)alloc((size_t)x.n * x.h * x.w * x.c * sizeof(bf16));
+          if (run()) check(crfr_maxpool2_bwd(x.p, x.ld, g.p, g.ld, dx, x.c, x.n, x.h, x.w, x.c, st));
+          add_slot(x, dx, x.c);
+          break;
+        }
+        case OP_UPADD: {
+          if (!has_grad(op.out)) break;
+          squash(op.out, 1);
+          Slot g = slots[op.out.id][0];
+          const Tensor& low = op.b;
+          bf16* dlow = (bf16*)alloc((size_t)low.n * low.h * low.w * low.c * sizeof(bf16));
+          if (run()) check(crfr_upnearest2_bwd(g.p, g.ld, dlow, low.c, low.n, low.h, low.w, low.c, st));
+          add_slot(op.a, g.p, g.ld);
+          add_slot(low, dlow, low.c);
+          break;
+        }
+        case OP_CAT: {
+          if (!has_grad(op.out)) break;
+          squash(op.out, 1);
+          Slot g = slots[op.out.id][0];
+          add_slot(op.a, g.p, g.ld);
+          add_slot(op.b, g.p + op.a.c, g.ld);
+          break;
+        }
+        case OP_HEADS: {
+          if (!d_heads) break;
+          const Tensor& x = op.a;
+          // combined [.., 112] gradient buffer: parsing channels 0..10, landmark 11..107, zero padding 108..111
+          const int idx[2][2] = {{P_FC_W, P_FC_B}, {P_FCL_W, P_FCL_B}};
+          const int couts[2] = {11, 97}, coff[2] = {0, 11};
+          for (int k = 0; k < 2; ++k) {
+            crfr_conv_desc d;
+            d.n = x.n; d.h = x.h; d.w = x.w; d.cin = x.c; d.cout = couts[k]; d.k = 1; d.stride = 1; d.pad = 0;
+            d.oh = x.h; d.ow = x.w; d.in_ld = x.ld; d.out_ld = 112; d.transposed = 0;
+            if (run()) check(crfr_conv_wgrad(CRFR_ENGINE_DIRECT, &d, x.p, d_heads + coff[k], grad(idx[k][0]), grad(idx[k][1]),
+                                  scratch, scratch_bytes, st));
+          }
+          // one combined dgrad: weights [1][128][112] = rows of fc then fc_landmark, zero padded
+          bf16* wt = (bf16*)alloc((size_t)128 * 112 * sizeof(bf16));
+          if (run()) check(cudaMemsetAsync(wt, 0, (size_t)128 * 112 * sizeof(bf16), st) == cudaSuccess ? CRFR_OK : CRFR_ECUDA);
+          if (run()) check(crfr_pack_weight_cols(params[P_FC_W], wt, 128, 11, 112, 0, st));
+          if (run()) check(crfr_pack_weight_cols(params[P_FCL_W], wt, 128, 97, 112, 11, st));
+          crfr_conv_desc d;
+          d.n = x.n; d.h = x.h; d.w = x.w; d.cin = x.c; d.cout = 112; d.k = 1; d.stride = 1; d.pad = 0;
+          d.oh = x.h; d.ow = x.w; d.in_ld = x.c; d.out_ld = 112; d.transposed = 0;
+          bf16* dx = (bf16*)alloc((size_t)x.n * x.h * x.w * x.c * sizeof(bf16));
+          if (run()) check(crfr_conv_dgrad(CRFR_ENGINE_DIRECT, &d, d_heads, wt, 112, dx, scratch, scratch_bytes, st));
+          add_slot(x, dx, x.c);
+          break;
+        }
+        case OP_IMGCONV: {
+          // gradient of the 3-channel image: explicit (loss / caller) + consumers' slots if it fed the stems
+          const bool is_coarse = op.out.p != nullptr;
+          bf16* g = is_coarse ? d_coarse4 : d_out4;
+          if (is_coarse && has_grad(op.out)) {
+            if (g) add_slot(op.out, g, 4);
+            squash(op.out, 1);
+            g = slots[op.out.id][0].p;
+          }
+          if (!g) break;
+          crfr_conv_desc d = op.cd;
+          d.out_ld = 4;
+          if (run()) check(crfr_conv_wgrad(CRFR_ENGINE_DIRECT, &d, op.a.p, g, grad(op.w_idx), grad(op.b_idx), scratch,
+                                scratch_bytes, st));
+          const Tensor& x = op.a;
+          bf16* dx = (bf16*)alloc((size_t)x.n * x.h * x.w * x.c * sizeof(bf16));
+          void* wt = pack(op.w_idx, 3, x.c, 3, 0, false, true);
+          crfr_conv_desc dd = d;
+          dd.in_ld = x.c;
+          if (run()) check(crfr_conv_dgrad(CRFR_ENGINE_DIRECT, &dd, g, wt, 4, dx, scratch, scratch_bytes, st));
+          add_slot(x, dx, x.c);
+          break;
+        }
+      }
+    }
+  }
+};
+
+__global__ void pack_cols_kernel(const float* __restrict__ w, bf16* __restrict__ dst, int cin, int rows, int ld,
+                                 int coff) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;  // over rows*cin; w is [rows][cin]
+  if (i >= rows * cin) return;
+  int r = i / cin, ci = i - r * cin;
+  dst[(long long)ci * ld + coff + r] = __float2bfloat16_rn(w[i]);
+}
+
+__global__ void total_loss_kernel(float* losses, float w_pix, float inv_div) {
+  losses[0] = (w_pix * losses[1] + w_pix * losses[2] + losses[3] + losses[4]) * inv_div;
+}
+
+void init_net(Net& net, int engine, const float* const* params, float* const* grads, const crfr_fsrnet_io* io,
+              void* ws, size_t ws_bytes, cudaStream_t st, bool exec, bool training) {
+  net.engine = engine; net.params = params; net.grads = grads; net.io = io; net.st = st;
+  net.ws = (uint8_t*)ws; net.ws_bytes = ws_bytes; net.exec = exec; net.training = training;
+}
+
+int check_io(const crfr_fsrnet_io* io, const char* who) {
+  CRFR_CHECK_ARG(io && io->batch > 0 && io->size >= 32 && io->size % 16 == 0, "%s: batch/size invalid (size must be a multiple of 16, >= 32)", who);
+  CRFR_CHECK_ARG(io->x && io->coarse && io->out && io->landmark && io->parsing, "%s: null tensor pointer", who);
+  return CRFR_OK;
+}
+
+}  // namespace
+
+int crfr_pack_weight_cols(const float* w, void* dst, int cin, int rows, int ld, int coff, cudaStream_t st) {
+  pack_cols_kernel<<<crfr_cdiv(rows * cin, 256), 256, 0, st>>>(w, (bf16*)dst, cin, rows, ld, coff);
+  CRFR_COUNT_LAUNCH();
+  CRFR_LAUNCH_CHECK();
+  return CRFR_OK;
+}
+
+namespace {
+
+// allocate the output-gradient buffers right after the forward region (same order in sizing and execution)
+void alloc_out_grads(Net& net, bool coarse, bool out, bool heads) {
+  const int B = net.io->batch, S = net.io->size, Q = S / 4;
+  net.d_coarse4 = coarse ? (bf16*)net.alloc((size_t)B * S * S * 4 * sizeof(bf16)) : nullptr;
+  net.d_out4 = out ? (bf16*)net.alloc((size_t)B * S * S * 4 * sizeof(bf16)) : nullptr;
+  net.d_heads = heads ? (bf16*)net.alloc((size_t)B * Q * Q * 112 * sizeof(bf16)) : nullptr;
+}
+
+}  // namespace
+
+extern "C" size_t crfr_fsrnet_workspace_bytes(int batch, int size, int training) {
+  if (batch <= 0 || size < 32 || size % 16) return 0;
+  crfr_fsrnet_io io = {};
+  io.batch = batch; io.size = size;
+  Net net;
+  init_net(net, CRFR_ENGINE_AUTO, nullptr, nullptr, &io, nullptr, ~(size_t)0 >> 2, nullptr, false, training != 0);
+  net.forward();
+  if (training) {
+    alloc_out_grads(net, true, true, true);
+    net.backward();
+  }
+  return net.off + 65536;
+}
+
+extern "C" int crfr_fsrnet_forward(int engine, const float* const* host_params, const crfr_fsrnet_io* io,
+                                   int training, void* ws, size_t ws_bytes, void* stream) {
+  CRFR_TRY(check_io(io, "fsrnet_forward"));
+  CRFR_CHECK_ARG(host_params && ws, "fsrnet_forward: null pointer");
+  Net net;
+  init_net(net, engine, host_params, nullptr, io, ws, ws_bytes, (cudaStream_t)stream, true, training != 0);
+  net.forward();
+  return net.err;
+}
+
+extern "C" int crfr_fsrnet_backward(int engine, const float* const* host_params, float* const* host_grads,
+                                    const crfr_fsrnet_io* io, const float* d_coarse, const float* d_out,
+                                    const float* d_landmark, const float* d_parsing, void* ws, size_t ws_bytes,
+                                    void* stream) {
+  CRFR_TRY(check_io(io, "fsrnet_backward"));
+  CRFR_CHECK_ARG(host_params && host_grads && ws, "fsrnet_backward: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  Net net;
+  init_net(net, engine, host_params, host_grads, io, ws, ws_bytes, st, false, true);
+  net.forward();  // dry run: rebuild the tape and the saved-activation offsets
+  if (!net.ok()) return net.err;
+  net.exec = true;
+  const int B = io->batch, S = io->size, Q = S / 4;
+  alloc_out_grads(net, d_coarse != nullptr, d_out != nullptr, d_landmark || d_parsing);
+  if (!net.ok()) return net.err;
+  if (d_coarse) CRFR_TRY(crfr_nchw_f32_to_nhwc_bf16(d_coarse, net.d_coarse4, B, 3, S, S, 4, 4, stream));
+  if (d_out) CRFR_TRY(crfr_nchw_f32_to_nhwc_bf16(d_out, net.d_out4, B, 3, S, S, 4, 4, stream));
+  if (net.d_heads) {
+    CRFR_CUDA(cudaMemsetAsync(net.d_heads, 0, (size_t)B * Q * Q * 112 * sizeof(bf16), st));
+    if (d_parsing) CRFR_TRY(crfr_nchw_f32_to_nhwc_bf16(d_parsing, net.d_heads, B, 11, Q, Q, 112, 11, stream));
+    if (d_landmark) CRFR_TRY(crfr_nchw_f32_to_nhwc_bf16(d_landmark, net.d_heads + 11, B, 97, Q, Q, 112, 97, stream));
+  }
+  net.backward();
+  return net.err;
+}
+
+extern "C" int crfr_fsrnet_train_step(int engine, const float* const* host_params, float* const* host_grads,
+                                      const crfr_fsrnet_io* io, float* losses, void* ws, size_t ws_bytes,
+                                      void* stream) {
+  CRFR_TRY(check_io(io, "fsrnet_train_step"));
+  CRFR_CHECK_ARG(host_params && host_grads && ws && losses, "fsrnet_train_step: null pointer");
+  CRFR_CHECK_ARG(io->hr && io->heatmap && io->labels && io->loss_div > 0.f, "fsrnet_train_step: missing targets");
+  cudaStream_t st = (cudaStream_t)stream;
+  Net net;
+  init_net(net, engine, host_params, host_grads, io, ws, ws_bytes, st, true, true);
+  net.forward();
+  if (!net.ok()) return net.err;
+  const int B = io->batch, S = io->size, Q = S / 4;
+  alloc_out_grads(net, true, true, true);
+  if (!net.ok()) return net.err;
+  // FSR_main.py:233-234: (w*mse(sr,hr) + w*mse(coarse,hr) + landmark + ce) / (2*train_batch)
+  const float inv = 1.f / io->loss_div;
+  CRFR_TRY(crfr_loss_mse97(io->out, io->hr, B, 3, S * S, io->w_pix * inv, losses + 1, net.d_out4, 4, net.scratch,
+                           net.scratch_bytes, stream));
+  CRFR_TRY(crfr_loss_mse97(io->coarse, io->hr, B, 3, S * S, io->w_pix * inv, losses + 2, net.d_coarse4, 4,
+                           net.scratch, net.scratch_bytes, stream));
+  CRFR_CUDA(cudaMemsetAsync(net.d_heads, 0, (size_t)B * Q * Q * 112 * sizeof(bf16), st));
+  CRFR_TRY(crfr_loss_landmark(io->landmark, io->heatmap, B, 97, Q * Q, inv, losses + 3, net.d_heads, 112, 11,
+                              net.scratch, net.scratch_bytes, stream));
+  CRFR_TRY(crfr_loss_ce2d(io->parsing, io->labels, B, 11, Q * Q, inv, losses + 4, net.d_heads, 112, 0, net.scratch,
+                          net.scratch_bytes, stream));
+  total_loss_kernel<<<1, 1, 0, st>>>(losses, io->w_pix, inv);
+  CRFR_COUNT_LAUNCH();
+  CRFR_LAUNCH_CHECK();
+  net.backward();
+  return net.err;
+}

@@ -1,0 +1,27 @@
+// Internal (non-ABI) entry points shared between translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+#include "crfr.h"
+
+// norm_act.cu
+size_t crfr_norm_ws_bytes(int n, int hw, int c);
+int crfr_norm_finalize(const float* partial, int n, int chunks, int hw, int c, float eps, float* stats,
+                       cudaStream_t st);
+
+// direct_conv.cu
+int crfr_direct_gather(int down, int n, int bh, int bw, int sh, int sw, int k, int stride, int pad, const void* src,
+                       int src_ld, const void* w, int R, int s_pad, const float* bias, void* y, int y_ld,
+                       float* y_nchw, cudaStream_t st);
+int crfr_direct_wgrad(int n, int bh, int bw, int sh, int sw, int k, int stride, int pad, const void* small,
+                      int small_ld, int A, const void* big, int big_ld, int B, float* G, cudaStream_t st);
+int crfr_colsum(const void* t, int ld, int c, long long npix, float* out, cudaStream_t st);
+
+// tc_conv.cu (tcgen05 engine).  op: 0 = forward, 1 = dgrad, 2 = wgrad
+int crfr_tc_supported(int op, int h, int w, int cin, int cout, int k, int stride, int pad);
+size_t crfr_tc_workspace_bytes(const crfr_conv_desc* d);
+int crfr_tc_conv(const crfr_conv_desc* d, int dgrad, const void* src, const void* w_packed, const float* bias,
+                 void* dst, float* stats, float eps, void* ws, size_t ws_bytes, cudaStream_t st);
+int crfr_tc_wgrad(const crfr_conv_desc* d, const void* x, const void* dy, float* dw, void* ws, size_t ws_bytes,
+                  cudaStream_t st);

@@ -1,0 +1,77 @@
+// Layout conversions at the nn.Module boundary and weight packing.
+#include "common.cuh"
+#include "crfr.h"
+
+namespace {
+
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long npix, int hw,
+                                    int c, int ld, int c_zero_to) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  long long n = i / hw;
+  int p = (int)(i - n * hw);
+  const float* s = src + n * (long long)c * hw + p;
+  bf16* d = dst + i * ld;
+  for (int ch = 0; ch < c; ++ch) d[ch] = __float2bfloat16_rn(s[(long long)ch * hw]);
+  for (int ch = c; ch < c_zero_to; ++ch) d[ch] = __float2bfloat16_rn(0.f);
+}
+
+__global__ void nhwc_to_nchw_kernel(const bf16* __restrict__ src, float* __restrict__ dst, long long npix, int hw,
+                                    int c, int ld) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  long long n = i / hw;
+  int p = (int)(i - n * hw);
+  const bf16* s = src + i * ld;
+  float* d = dst + n * (long long)c * hw + p;
+  for (int ch = 0; ch < c; ++ch) d[(long long)ch * hw] = __bfloat162float(s[ch]);
+}
+
+__global__ void pack_weight_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int T, int R, int S,
+                                   int s_pad, long long rs, long long ss, long long ts) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)T * R * s_pad;
+  if (i >= total) return;
+  int s = (int)(i % s_pad);
+  long long q = i / s_pad;
+  int r = (int)(q % R);
+  int t = (int)(q / R);
+  float v = (s < S) ? src[r * rs + s * ss + t * ts] : 0.f;
+  dst[i] = __float2bfloat16_rn(v);
+}
+
+}  // namespace
+
+extern "C" int crfr_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int n, int c, int h, int w, int dst_ld,
+                                          int c_zero_to, void* stream) {
+  CRFR_CHECK_ARG(src && dst && n > 0 && c > 0 && h > 0 && w > 0, "nchw_to_nhwc: bad argument");
+  CRFR_CHECK_ARG(dst_ld >= c && c_zero_to <= dst_ld, "nchw_to_nhwc: ld %d < c %d", dst_ld, c);
+  long long npix = (long long)n * h * w;
+  nchw_to_nhwc_kernel<<<crfr_cdiv(npix, 256), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, npix, h * w, c,
+                                                                              dst_ld, c_zero_to);
+  CRFR_COUNT_LAUNCH();
+  CRFR_LAUNCH_CHECK();
+  return CRFR_OK;
+}
+
+extern "C" int crfr_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int n, int c, int h, int w, int src_ld,
+                                          void* stream) {
+  CRFR_CHECK_ARG(src && dst && n > 0 && c > 0 && h > 0 && w > 0 && src_ld >= c, "nhwc_to_nchw: bad argument");
+  long long npix = (long long)n * h * w;
+  nhwc_to_nchw_kernel<<<crfr_cdiv(npix, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)src, dst, npix, h * w, c,
+                                                                              src_ld);
+  CRFR_COUNT_LAUNCH();
+  CRFR_LAUNCH_CHECK();
+  return CRFR_OK;
+}
+
+extern "C" int crfr_pack_weight(const float* src, void* dst, int T, int R, int S, int s_pad, long long r_stride,
+                                long long s_stride, long long t_stride, void* stream) {
+  CRFR_CHECK_ARG(src && dst && T > 0 && R > 0 && S > 0 && s_pad >= S, "pack_weight: bad argument");
+  long long total = (long long)T * R * s_pad;
+  pack_weight_kernel<<<crfr_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, T, R, S, s_pad,
+                                                                              r_stride, s_stride, t_stride);
+  CRFR_COUNT_LAUNCH();
+  CRFR_LAUNCH_CHECK();
+  return CRFR_OK;
+}

@@ -1,0 +1,207 @@
+// Fused loss forward+backward kernels (HBM-bound, one pass over the prediction and target, deterministic
+// two-stage reductions: per-block partials in the workspace, fixed-order finalisation in double).
+// ref: loss/loss.py:7-15 (MSELossFunc), :17-32 (MSELoss_Landmark), :34-62 (CrossEntropyLoss2d),
+//      distill_main.py:63,68-70 (nn.MSELoss residual-KD terms).
+#include "common.cuh"
+#include "crfr.h"
+
+namespace {
+
+constexpr int kT = 256;
+
+__device__ __forceinline__ void block_partial(float v, float* partial) {
+  __shared__ float sm[kT / 32];
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < kT / 32; ++i) s += sm[i];
+    partial[blockIdx.x] = s;
+  }
+}
+
+__global__ void finalize_kernel(const float* __restrict__ partial, int nblocks, double scale, float* __restrict__ loss) {
+  __shared__ double sm[kT];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < nblocks; i += kT) s += (double)partial[i];
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = kT / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) loss[0] = (float)(sm[0] * scale);
+}
+
+__global__ void __launch_bounds__(kT)
+mse97_kernel(const float* __restrict__ x, const float* __restrict__ t, long long npix, int hw, int c, float gcoef,
+             bf16* __restrict__ dx, int dx_ld, float* __restrict__ partial) {
+  long long i = (long long)blockIdx.x * kT + threadIdx.x;
+  float acc = 0.f;
+  if (i < npix) {
+    long long n = i / hw;
+    int p = (int)(i - n * hw);
+    const float* xs = x + n * (long long)c * hw + p;
+    const float* ts = t + n * (long long)c * hw + p;
+    for (int ch = 0; ch < c; ++ch) {
+      float d = xs[(long long)ch * hw] - ts[(long long)ch * hw];
+      acc += d * d;
+      if (dx) dx[i * dx_ld + ch] = __float2bfloat16_rn(gcoef * d);
+    }
+    if (dx)
+      for (int ch = c; ch < dx_ld; ++ch) dx[i * dx_ld + ch] = __float2bfloat16_rn(0.f);
+  }
+  block_partial(acc, partial);
+}
+
+__global__ void __launch_bounds__(kT)
+landmark_kernel(const float* __restrict__ x, const float* __restrict__ t, long long npix, int hw, int c, float gcoef,
+                bf16* __restrict__ dx, int dx_ld, int coff, float* __restrict__ partial) {
+  long long i = (long long)blockIdx.x * kT + threadIdx.x;
+  float acc = 0.f;
+  if (i < npix) {
+    long long n = i / hw;
+    int p = (int)(i - n * hw);
+    const float* xs = x + n * (long long)c * hw + p;
+    float s = 0.f;
+    for (int ch = 0; ch < c; ++ch) s += xs[(long long)ch * hw];
+    float d = s - t[i];
+    acc = d * d;
+    if (dx) {
+      bf16 g = __float2bfloat16_rn(gcoef * d);
+      for (int ch = 0; ch < c; ++ch) dx[i * dx_ld + coff + ch] = g;
+    }
+  }
+  block_partial(acc, partial);
+}
+
+__global__ void __launch_bounds__(kT)
+ce2d_kernel(const float* __restrict__ x, const long long* __restrict__ target, long long npix, int hw, int c,
+            float gcoef, bf16* __restrict__ dx, int dx_ld, int coff, float* __restrict__ partial) {
+  long long i = (long long)blockIdx.x * kT + threadIdx.x;
+  float acc = 0.f;
+  if (i < npix) {
+    long long n = i / hw;
+    int p = (int)(i - n * hw);
+    const float* xs = x + n * (long long)c * hw + p;
+    float m = -INFINITY;
+    for (int ch = 0; ch < c; ++ch) m = fmaxf(m, xs[(long long)ch * hw]);
+    float se = 0.f;
+    for (int ch = 0; ch < c; ++ch) se += expf(xs[(long long)ch * hw] - m);
+    float lse = m + logf(se);
+    int tg = (int)target[i];
+    acc = lse - xs[(long long)tg * hw];
+    if (dx)
+      for (int ch = 0; ch < c; ++ch) {
+        float sm = expf(xs[(long long)ch * hw] - lse);
+        dx[i * dx_ld + coff + ch] = __float2bfloat16_rn(gcoef * (sm - (ch == tg ? 1.f : 0.f)));
+      }
+  }
+  block_partial(acc, partial);
+}
+
+template <typename T> __device__ __forceinline__ float ldf(const T* p, long long i);
+template <> __device__ __forceinline__ float ldf<float>(const float* p, long long i) { return p[i]; }
+template <> __device__ __forceinline__ float ldf<bf16>(const bf16* p, long long i) { return __bfloat162float(p[i]); }
+__device__ __forceinline__ void stf(float* p, long long i, float v) { p[i] = v; }
+__device__ __forceinline__ void stf(bf16* p, long long i, float v) { p[i] = __float2bfloat16_rn(v); }
+
+template <typename T>
+__global__ void __launch_bounds__(kT)
+kd_kernel(const T* __restrict__ t, const T* __restrict__ s, const T* __restrict__ a, long long numel, float gcoef,
+          T* __restrict__ dt, T* __restrict__ ds, T* __restrict__ da, float* __restrict__ partial) {
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < numel; i += (long long)gridDim.x * kT) {
+    float r = ldf(t, i) - (s ? ldf(s, i) : 0.f) - ldf(a, i);
+    acc += r * r;
+    float g = gcoef * r;
+    if (dt) stf(dt, i, g);
+    if (ds) stf(ds, i, -g);
+    if (da) stf(da, i, -g);
+  }
+  block_partial(acc, partial);
+}
+
+int check_ws(const char* who, void* ws, size_t ws_bytes, int blocks) {
+  if (!ws || ws_bytes < sizeof(float) * (size_t)blocks) {
+    crfr_set_error("%s: workspace %zu < %zu", who, ws_bytes, sizeof(float) * (size_t)blocks);
+    return CRFR_EWORKSPACE;
+  }
+  return CRFR_OK;
+}
+
+}  // namespace
+
+extern "C" int crfr_loss_mse97(const float* x, const float* t, int n, int c, int hw, float gscale, float* loss,
+                               void* dx, int dx_ld, void* ws, size_t ws_bytes, void* stream) {
+  CRFR_CHECK_ARG(x && t && loss && n > 0 && c > 0 && hw > 0 && (!dx || dx_ld >= c), "loss_mse97: bad argument");
+  long long npix = (long long)n * hw;
+  int blocks = crfr_cdiv(npix, kT);
+  CRFR_TRY(check_ws("loss_mse97", ws, ws_bytes, blocks));
+  double numel = (double)npix * c;
+  cudaStream_t st = (cudaStream_t)stream;
+  mse97_kernel<<<blocks, kT, 0, st>>>(x, t, npix, hw, c, (float)(gscale * 2.0 * 97.0 / numel), (bf16*)dx, dx_ld,
+                                      (float*)ws);
+  CRFR_COUNT_LAUNCH();
+  finalize_kernel<<<1, kT, 0, st>>>((const float*)ws, blocks, 97.0 / numel, loss);
+  CRFR_COUNT_LAUNCH();
+  CRFR_LAUNCH_CHECK();
+  return CRFR_OK;
+}
+
+extern "C" int crfr_loss_landmark(const float* x, const float* t, int n, int c, int hw, float gscale, float* loss,
+                                  void* dx, int dx_ld, int dx_coff, void* ws, size_t ws_bytes, void* stream) {
+  CRFR_CHECK_ARG(x && t && loss && n > 0 && c > 0 && hw > 0 && (!dx || dx_ld >= dx_coff + c),
+                 "loss_landmark: bad argument");
+  long long npix = (long long)n * hw;
+  int blocks = crfr_cdiv(npix, kT);
+  CRFR_TRY(check_ws("loss_landmark", ws, ws_bytes, blocks));
+  cudaStream_t st = (cudaStream_t)stream;
+  landmark_kernel<<<blocks, kT, 0, st>>>(x, t, npix, hw, c, (float)(gscale * 2.0 * 97.0 / (double)npix), (bf16*)dx,
+                                         dx_ld, dx_coff, (float*)ws);
+  CRFR_COUNT_LAUNCH();
+  finalize_kernel<<<1, kT, 0, st>>>((const float*)ws, blocks, 97.0 / (double)npix, loss);
+  CRFR_COUNT_LAUNCH();
+  CRFR_LAUNCH_CHECK();
+  return CRFR_OK;
+}
+
+extern "C" int crfr_loss_ce2d(const float* logits, const long long* target, int n, int c, int hw, float gscale,
+                              float* loss, void* dx, int dx_ld, int dx_coff, void* ws, size_t ws_bytes,
+                              void* stream) {
+  CRFR_CHECK_ARG(logits && target && loss && n > 0 && c > 0 && hw > 0 && (!dx || dx_ld >= dx_coff + c),
+                 "loss_ce2d: bad argument");
+  long long npix = (long long)n * hw;
+  int blocks = crfr_cdiv(npix, kT);
+  CRFR_TRY(check_ws("loss_ce2d", ws, ws_bytes, blocks));
+  cudaStream_t st = (cudaStream_t)stream;
+  ce2d_kernel<<<blocks, kT, 0, st>>>(logits, target, npix, hw, c, (float)(gscale / (double)npix), (bf16*)dx, dx_ld,
+                                     dx_coff, (float*)ws);
+  CRFR_COUNT_LAUNCH();
+  finalize_kernel<<<1, kT, 0, st>>>((const float*)ws, blocks, 1.0 / (double)npix, loss);
+  CRFR_COUNT_LAUNCH();
+  CRFR_LAUNCH_CHECK();
+  return CRFR_OK;
+}
+
+extern "C" int crfr_loss_kd(const void* t, const void* s, const void* a, long long numel, int is_f32, float gscale,
+                            float* loss, void* dt, void* ds, void* da, void* ws, size_t ws_bytes, void* stream) {
+  CRFR_CHECK_ARG(t && a && loss && numel > 0, "loss_kd: bad argument");
+  int blocks = (int)((numel + kT - 1) / kT);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  CRFR_TRY(check_ws("loss_kd", ws, ws_bytes, blocks));
+  cudaStream_t st = (cudaStream_t)stream;
+  float gcoef = (float)(gscale * 2.0 / (double)numel);
+  if (is_f32)
+    kd_kernel<float><<<blocks, kT, 0, st>>>((const float*)t, (const float*)s, (const float*)a, numel, gcoef,
+                                            (float*)dt, (float*)ds, (float*)da, (float*)ws);
+  else
+    kd_kernel<bf16><<<blocks, kT, 0, st>>>((const bf16*)t, (const bf16*)s, (const bf16*)a, numel, gcoef, (bf16*)dt,
+                                           (bf16*)ds, (bf16*)da, (float*)ws);
+  CRFR_COUNT_LAUNCH();
+  finalize_kernel<<<1, kT, 0, st>>>((const float*)ws, blocks, 1.0 / (double)numel, loss);
+  CRFR_COUNT_LAUNCH();
+  CRFR_LAUNCH_CHECK();
+  return CRFR_OK;
+}

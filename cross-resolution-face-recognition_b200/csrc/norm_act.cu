@@ -1,0 +1,364 @@
+// InstanceNorm / BatchNorm statistics and the fused normalise + affine + residual + PReLU/ReLU pass, forward and
+// backward.  HBM-bound: every pass reads/writes 16-byte (8 x bf16) vectors, one channel-group per thread, so a
+// warp touches whole 128-byte lines of the NHWC rows.  Reductions are deterministic: per-chunk partials in a
+// workspace, fixed-order finalisation (no float atomics).
+//
+// ref: nn.InstanceNorm2d + nn.PReLU + torch.add in _Residual_Block (model/FSRnet.py:75-98) and BasicBlock
+//      (:105-135); nn.BatchNorm2d + ReLU in model/resnet.py:18-47 (groups: n = 1, hw = N*H*W).
+#include "common.cuh"
+#include "crfr.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+struct ChunkPlan {
+  int chunks;      // partials per image
+  int chunk_pix;   // pixels per chunk
+};
+
+inline ChunkPlan plan_chunks(int n, int hw) {
+  // aim for >= ~4 CTAs per SM overall, chunks of at least 256 pixels
+  int want = (148 * 8 + n - 1) / n;
+  int maxc = (hw + 255) / 256;
+  int chunks = want < 1 ? 1 : want;
+  if (chunks > maxc) chunks = maxc;
+  if (chunks < 1) chunks = 1;
+  if (chunks > 2048) chunks = 2048;
+  int chunk_pix = (hw + chunks - 1) / chunks;
+  chunks = (hw + chunk_pix - 1) / chunk_pix;
+  return {chunks, chunk_pix};
+}
+
+// Reduce K per-thread 8-vectors across the pixel lanes of the CTA and store [K][C] at dst.
+template <int K>
+__device__ __forceinline__ void cta_reduce_store(float (&acc)[K][8], float* smem, int cg, int lane, int lanes, int c,
+                                                 float* dst) {
+  // smem layout [K][lanes][C]
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) smem[(k * lanes + lane) * c + cg * 8 + j] = acc[k][j];
+  __syncthreads();
+  for (int i = threadIdx.x; i < K * c; i += kThreads) {
+    int k = i / c, ch = i - k * c;
+    float s = 0.f;
+    for (int l = 0; l < lanes; ++l) s += smem[(k * lanes + l) * c + ch];
+    dst[k * c + ch] = s;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+stats_partial_kernel(const bf16* __restrict__ y, int ld, int hw, int c, int chunk_pix, float* __restrict__ partial) {
+  extern __shared__ float smem[];
+  const int groups = c >> 3, lanes = kThreads / groups;
+  const int cg = threadIdx.x % groups, lane = threadIdx.x / groups;
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const int p0 = chunk * chunk_pix, p1 = min(hw, p0 + chunk_pix);
+  const bf16* base = y + ((long long)n * hw) * ld + cg * 8;
+  float acc[2][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
+  for (int p = p0 + lane; p < p1; p += lanes) {
+    bf16x8 v = *reinterpret_cast<const bf16x8*>(base + (long long)p * ld);
+    float f[8];
+    unpack8(v, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      acc[0][j] += f[j];
+      acc[1][j] += f[j] * f[j];
+    }
+  }
+  cta_reduce_store<2>(acc, smem, cg, lane, lanes, c, partial + ((long long)n * gridDim.x + chunk) * 2 * c);
+}
+
+__global__ void stats_finalize_kernel(const float* __restrict__ partial, int chunks, int c, int total, float inv_hw,
+                                      float eps, float* __restrict__ stats) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;  // (n, ch)
+  if (i >= total) return;
+  int n = i / c, ch = i - n * c;
+  const float* p = partial + (long long)n * chunks * 2 * c;
+  float s = 0.f, q = 0.f;
+  for (int k = 0; k < chunks; ++k) {
+    s += p[(k * 2 + 0) * c + ch];
+    q += p[(k * 2 + 1) * c + ch];
+  }
+  float mean = s * inv_hw;
+  float var = fmaxf(q * inv_hw - mean * mean, 0.f);
+  stats[2 * i] = mean;
+  stats[2 * i + 1] = rsqrtf(var + eps);
+}
+
+__global__ void __launch_bounds__(kThreads)
+norm_act_fwd_kernel(const bf16* __restrict__ y, int y_ld, const float* __restrict__ stats,
+                    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ alpha,
+                    int relu, const bf16* __restrict__ res, int res_ld, bf16* __restrict__ out, int out_ld, int hw,
+                    int c, int chunk_pix) {
+  const int groups = c >> 3, lanes = kThreads / groups;
+  const int cg = threadIdx.x % groups, lane = threadIdx.x / groups;
+  const int n = blockIdx.y;
+  const int p0 = blockIdx.x * chunk_pix, p1 = min(hw, p0 + chunk_pix);
+  float sc[8], sh[8], al[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    int ch = cg * 8 + j;
+    float mean = stats[2 * (n * c + ch)], rstd = stats[2 * (n * c + ch) + 1];
+    float g = gamma ? gamma[ch] : 1.f, b = beta ? beta[ch] : 0.f;
+    sc[j] = g * rstd;
+    sh[j] = b - mean * sc[j];
+    al[j] = relu ? 0.f : (alpha ? alpha[ch] : 1.f);
+  }
+  const long long pix0 = (long long)n * hw;
+  for (int p = p0 + lane; p < p1; p += lanes) {
+    float f[8], r[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(y + (pix0 + p) * y_ld + cg * 8), f);
+    if (res) unpack8(*reinterpret_cast<const bf16x8*>(res + (pix0 + p) * res_ld + cg * 8), r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float z = fmaf(f[j], sc[j], sh[j]);
+      if (res) z += r[j];
+      f[j] = z > 0.f ? z : z * al[j];
+    }
+    *reinterpret_cast<bf16x8*>(out + (pix0 + p) * out_ld + cg * 8) = pack8(f);
+  }
+}
+
+// backward pass 1: dz = dout * act'(z) (stored, bf16), partial sums of dz, dz*xhat, dout*min(z,0)
+__global__ void __launch_bounds__(kThreads)
+norm_act_bwd_reduce_kernel(const bf16* __restrict__ da, int da_ld, const bf16* __restrict__ db, int db_ld,
+                           const bf16* __restrict__ y, int y_ld, const float* __restrict__ stats,
+                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                           const float* __restrict__ alpha, int relu, const bf16* __restrict__ res, int res_ld,
+                           bf16* __restrict__ dz, int dz_ld, int hw, int c, int chunk_pix,
+                           float* __restrict__ partial) {
+  extern __shared__ float smem[];
+  const int groups = c >> 3, lanes = kThreads / groups;
+  const int cg = threadIdx.x % groups, lane = threadIdx.x / groups;
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const int p0 = chunk * chunk_pix, p1 = min(hw, p0 + chunk_pix);
+  const bool act = relu || alpha;
+  float mu[8], rs[8], sc[8], sh[8], al[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    int ch = cg * 8 + j;
+    mu[j] = stats[2 * (n * c + ch)];
+    rs[j] = stats[2 * (n * c + ch) + 1];
+    float g = gamma ? gamma[ch] : 1.f, b = beta ? beta[ch] : 0.f;
+    sc[j] = g * rs[j];
+    sh[j] = b - mu[j] * sc[j];
+    al[j] = relu ? 0.f : (alpha ? alpha[ch] : 1.f);
+  }
+  float acc[3][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = acc[2][j] = 0.f;
+  const long long pix0 = (long long)n * hw;
+  for (int p = p0 + lane; p < p1; p += lanes) {
+    float g[8], f[8], r[8], g2[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(da + (pix0 + p) * da_ld + cg * 8), g);
+    if (db) {
+      unpack8(*reinterpret_cast<const bf16x8*>(db + (pix0 + p) * db_ld + cg * 8), g2);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] += g2[j];
+    }
+    unpack8(*reinterpret_cast<const bf16x8*>(y + (pix0 + p) * y_ld + cg * 8), f);
+    if (act && res) unpack8(*reinterpret_cast<const bf16x8*>(res + (pix0 + p) * res_ld + cg * 8), r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float d = g[j];
+      if (act) {
+        float z = fmaf(f[j], sc[j], sh[j]);
+        if (res) z += r[j];
+        if (!(z > 0.f)) {
+          acc[2][j] += d * z;
+          d *= al[j];
+        }
+      }
+      d = bf16_round(d);
+      g[j] = d;
+      acc[0][j] += d;
+      acc[1][j] += d * (f[j] - mu[j]) * rs[j];
+    }
+    *reinterpret_cast<bf16x8*>(dz + (pix0 + p) * dz_ld + cg * 8) = pack8(g);
+  }
+  cta_reduce_store<3>(acc, smem, cg, lane, lanes, c, partial + ((long long)n * gridDim.x + chunk) * 3 * c);
+}
+
+// per (n, ch): fold the chunk partials -> bstats[n][ch] = (mean dz, mean dz*xhat); tot[n][3][c]
+__global__ void bwd_fold_kernel(const float* __restrict__ partial, int chunks, int c, int total, float inv_hw,
+                                float* __restrict__ bstats, float* __restrict__ tot) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int n = i / c, ch = i - n * c;
+  const float* p = partial + (long long)n * chunks * 3 * c;
+  float s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  for (int k = 0; k < chunks; ++k) {
+    s1 += p[(k * 3 + 0) * c + ch];
+    s2 += p[(k * 3 + 1) * c + ch];
+    s3 += p[(k * 3 + 2) * c + ch];
+  }
+  bstats[2 * i] = s1 * inv_hw;
+  bstats[2 * i + 1] = s2 * inv_hw;
+  tot[(n * 3 + 0) * c + ch] = s1;
+  tot[(n * 3 + 1) * c + ch] = s2;
+  tot[(n * 3 + 2) * c + ch] = s3;
+}
+
+// per channel: sum tot over n in fixed order and accumulate into the parameter gradients
+__global__ void bwd_param_kernel(const float* __restrict__ tot, int n, int c, float* __restrict__ dgamma,
+                                 float* __restrict__ dbeta, float* __restrict__ dalpha) {
+  __shared__ float sm[8][3][32];
+  int cl = threadIdx.x & 31, lane = threadIdx.x >> 5;  // 32 channels x 8 n-lanes
+  int ch = blockIdx.x * 32 + cl;
+  float s[3] = {0.f, 0.f, 0.f};
+  if (ch < c)
+    for (int i = lane; i < n; i += 8)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) s[k] += tot[(i * 3 + k) * c + ch];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) sm[lane][k][cl] = s[k];
+  __syncthreads();
+  if (lane == 0 && ch < c) {
+    float t[3] = {0.f, 0.f, 0.f};
+    for (int l = 0; l < 8; ++l)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) t[k] += sm[l][k][cl];
+    if (dbeta) dbeta[ch] += t[0];
+    if (dgamma) dgamma[ch] += t[1];
+    if (dalpha) dalpha[ch] += t[2];
+  }
+}
+
+// backward pass 2: dy = gamma * rstd * (dz - mean(dz) - xhat * mean(dz * xhat))
+__global__ void __launch_bounds__(kThreads)
+norm_act_bwd_apply_kernel(const bf16* __restrict__ dz, int dz_ld, const bf16* __restrict__ y, int y_ld,
+                          const float* __restrict__ stats, const float* __restrict__ bstats,
+                          const float* __restrict__ gamma, bf16* __restrict__ dy, int dy_ld, int hw, int c,
+                          int chunk_pix) {
+  const int groups = c >> 3, lanes = kThreads / groups;
+  const int cg = threadIdx.x % groups, lane = threadIdx.x / groups;
+  const int n = blockIdx.y;
+  const int p0 = blockIdx.x * chunk_pix, p1 = min(hw, p0 + chunk_pix);
+  float mu[8], rs[8], gr[8], m1[8], m2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    int ch = cg * 8 + j;
+    mu[j] = stats[2 * (n * c + ch)];
+    rs[j] = stats[2 * (n * c + ch) + 1];
+    gr[j] = (gamma ? gamma[ch] : 1.f) * rs[j];
+    m1[j] = bstats[2 * (n * c + ch)];
+    m2[j] = bstats[2 * (n * c + ch) + 1];
+  }
+  const long long pix0 = (long long)n * hw;
+  for (int p = p0 + lane; p < p1; p += lanes) {
+    float d[8], f[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(dz + (pix0 + p) * dz_ld + cg * 8), d);
+    unpack8(*reinterpret_cast<const bf16x8*>(y + (pix0 + p) * y_ld + cg * 8), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float xh = (f[j] - mu[j]) * rs[j];
+      d[j] = gr[j] * (d[j] - m1[j] - xh * m2[j]);
+    }
+    *reinterpret_cast<bf16x8*>(dy + (pix0 + p) * dy_ld + cg * 8) = pack8(d);
+  }
+}
+
+inline bool channels_ok(int c) { return c >= 8 && c <= 2048 && (c & 7) == 0 && (kThreads % (c >> 3)) == 0; }
+
+}  // namespace
+
+size_t crfr_norm_ws_bytes(int n, int hw, int c) {
+  ChunkPlan pl = plan_chunks(n, hw);
+  // partials [n][chunks][3][c] + bstats [n][c][2] + tot [n][3][c]
+  return sizeof(float) * ((size_t)n * pl.chunks * 3 * c + (size_t)n * c * 2 + (size_t)n * 3 * c) + 256;
+}
+
+// Finalise (mean, rstd) from partials laid out [n][chunks][2][c]; shared with the conv epilogue statistics.
+int crfr_norm_finalize(const float* partial, int n, int chunks, int hw, int c, float eps, float* stats,
+                       cudaStream_t st) {
+  int total = n * c;
+  stats_finalize_kernel<<<crfr_cdiv(total, 256), 256, 0, st>>>(partial, chunks, c, total, 1.f / (float)hw, eps,
+                                                               stats);
+  CRFR_COUNT_LAUNCH();
+  CRFR_LAUNCH_CHECK();
+  return CRFR_OK;
+}
+
+extern "C" int crfr_norm_stats(const void* y, int n, int hw, int c, int ld, float eps, float* stats, void* ws,
+                               size_t ws_bytes, void* stream) {
+  CRFR_CHECK_ARG(y && stats && n > 0 && hw > 0, "norm_stats: bad argument");
+  CRFR_CHECK_ARG(channels_ok(c) && ld >= c && (ld & 7) == 0, "norm_stats: unsupported channels %d (ld %d)", c, ld);
+  ChunkPlan pl = plan_chunks(n, hw);
+  size_t need = sizeof(float) * (size_t)n * pl.chunks * 2 * c;
+  if (!ws || ws_bytes < need) {
+    crfr_set_error("norm_stats: workspace %zu < %zu", ws_bytes, need);
+    return CRFR_EWORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  int lanes = kThreads / (c >> 3);
+  size_t smem = sizeof(float) * 2 * lanes * c;
+  stats_partial_kernel<<<dim3(pl.chunks, n), kThreads, smem, st>>>((const bf16*)y, ld, hw, c, pl.chunk_pix,
+                                                                   (float*)ws);
+  CRFR_COUNT_LAUNCH();
+  CRFR_LAUNCH_CHECK();
+  return crfr_norm_finalize((const float*)ws, n, pl.chunks, hw, c, eps, stats, st);
+}
+
+extern "C" int crfr_norm_act_fwd(const void* y, int y_ld, const float* stats, const float* gamma, const float* beta,
+                                 const float* alpha, int relu, const void* res, int res_ld, void* out, int out_ld,
+                                 int n, int hw, int c, void* stream) {
+  CRFR_CHECK_ARG(y && stats && out && n > 0 && hw > 0, "norm_act_fwd: bad argument");
+  CRFR_CHECK_ARG(channels_ok(c) && y_ld >= c && out_ld >= c && ((y_ld | out_ld | res_ld) & 7) == 0,
+                 "norm_act_fwd: unsupported channels %d", c);
+  ChunkPlan pl = plan_chunks(n, hw);
+  norm_act_fwd_kernel<<<dim3(pl.chunks, n), kThreads, 0, (cudaStream_t)stream>>>(
+      (const bf16*)y, y_ld, stats, gamma, beta, alpha, relu, (const bf16*)res, res_ld, (bf16*)out, out_ld, hw, c,
+      pl.chunk_pix);
+  CRFR_COUNT_LAUNCH();
+  CRFR_LAUNCH_CHECK();
+  return CRFR_OK;
+}
+
+extern "C" int crfr_norm_act_bwd(const void* dout_a, int da_ld, const void* dout_b, int db_ld, const void* y,
+                                 int y_ld, const float* stats, const float* gamma, const float* beta,
+                                 const float* alpha, int relu, const void* res, int res_ld, void* dz, int dz_ld,
+                                 void* dy, int dy_ld, float* dgamma, float* dbeta, float* dalpha, int n, int hw,
+                                 int c, void* ws, size_t ws_bytes, void* stream) {
+  CRFR_CHECK_ARG(dout_a && y && stats && dz && dy && n > 0 && hw > 0, "norm_act_bwd: bad argument");
+  CRFR_CHECK_ARG(channels_ok(c) && ((da_ld | db_ld | y_ld | res_ld | dz_ld | dy_ld) & 7) == 0,
+                 "norm_act_bwd: unsupported channels %d", c);
+  ChunkPlan pl = plan_chunks(n, hw);
+  size_t need = crfr_norm_ws_bytes(n, hw, c);
+  if (!ws || ws_bytes < need) {
+    crfr_set_error("norm_act_bwd: workspace %zu < %zu", ws_bytes, need);
+    return CRFR_EWORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  float* partial = (float*)ws;
+  float* bstats = partial + (size_t)n * pl.chunks * 3 * c;
+  float* tot = bstats + (size_t)n * c * 2;
+  int lanes = kThreads / (c >> 3);
+  size_t smem = sizeof(float) * 3 * lanes * c;
+  if (smem > 48 * 1024) {
+    CRFR_CUDA(cudaFuncSetAttribute(norm_act_bwd_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  norm_act_bwd_reduce_kernel<<<dim3(pl.chunks, n), kThreads, smem, st>>>(
+      (const bf16*)dout_a, da_ld, (const bf16*)dout_b, db_ld, (const bf16*)y, y_ld, stats, gamma, beta, alpha, relu,
+      (const bf16*)res, res_ld, (bf16*)dz, dz_ld, hw, c, pl.chunk_pix, partial);
+  CRFR_COUNT_LAUNCH();
+  CRFR_LAUNCH_CHECK();
+  int total = n * c;
+  bwd_fold_kernel<<<crfr_cdiv(total, 256), 256, 0, st>>>(partial, pl.chunks, c, total, 1.f / (float)hw, bstats, tot);
+  CRFR_COUNT_LAUNCH();
+  CRFR_LAUNCH_CHECK();
+  if (dgamma || dbeta || dalpha) {
+    bwd_param_kernel<<<crfr_cdiv(c, 32), 256, 0, st>>>(tot, n, c, dgamma, dbeta, dalpha);
+    CRFR_COUNT_LAUNCH();
+    CRFR_LAUNCH_CHECK();
+  }
+  norm_act_bwd_apply_kernel<<<dim3(pl.chunks, n), kThreads, 0, st>>>((const bf16*)dz, dz_ld, (const bf16*)y, y_ld,
+                                                                     stats, bstats, gamma, (bf16*)dy, dy_ld, hw, c,
+                                                                     pl.chunk_pix);
+  CRFR_COUNT_LAUNCH();
+  CRFR_LAUNCH_CHECK();
+  return CRFR_OK;
+}

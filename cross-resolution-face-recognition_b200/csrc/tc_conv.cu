@@ -1,0 +1,515 @@
+// tcgen05 / TMEM implicit-GEMM convolution engine for sm_100a, fed by TMA.
+//
+// Forward / dgrad (3x3, stride 1, pad 1, channels in multiples of 64), NHWC bf16:
+//   one CTA computes a tile of 128 output pixels x N output channels.  The 128 pixels are a TMA box
+//   (64 channels x bw x bh x bn) of the NHWC activation tensor, so the im2col gather of tap (ky,kx) is just the
+//   same box shifted by (kx-1, ky-1); out-of-bounds elements are zero-filled by the TMA unit (= the padding).
+//   K loop = taps x (Cin/64): per step one 16 KB activation tile (A, K-major, SWIZZLE_128B) and one N x 64 weight
+//   tile (B, K-major) land in a 3-4 stage smem ring (mbarrier full/empty), one elected thread issues 4
+//   tcgen05.mma (M=128, N, K=16) per step into a TMEM accumulator, and 4 epilogue warps drain TMEM with
+//   tcgen05.ld, add the bias, round to bf16 and store NHWC rows.
+//   dgrad is the same kernel on dY with flipped tap offsets and [tap][cin][cout] weights.
+// Wgrad: D[(kx,ci)][co] = sum_pixels X[p + tap][ci] * dY[p][co]: both operands are MN-major views of the same
+//   NHWC tiles (pixels are the K dimension); two kx taps are stacked in M=128 through the leading-byte-offset of
+//   the smem descriptor; fp32 partial results are reduced into a [tap][cin][cout] scratch with vector atomics.
+//
+// ref: the nn.Conv2d sites of model/FSRnet.py (:79,85,110,114,351,387,411,432) that carry 99 % of the FLOPs.
+#include <cudaTypedefs.h>
+
+#include "common.cuh"
+#include "crfr.h"
+#include "internal.h"
+#include "sm100.cuh"
+
+using namespace sm100;
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// host: tensor-map encoding through the driver entry point (no link-time dependency on libcuda)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// NHWC bf16 activation view [n][h][w][c] with per-pixel stride ld; box = (64, bw, bh, bn), SWIZZLE_128B
+int make_act_map(CUtensorMap* m, const void* ptr, int n, int h, int w, int c, int ld, int bw, int bh, int bn) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    crfr_set_error("cuTensorMapEncodeTiled entry point not available");
+    return CRFR_ECUDA;
+  }
+  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)w * ld * 2, (cuuint64_t)h * w * ld * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    crfr_set_error("cuTensorMapEncodeTiled(activation n=%d h=%d w=%d c=%d ld=%d box=%dx%dx%d) failed: %d", n, h, w, c,
+                   ld, bw, bh, bn, (int)r);
+    return CRFR_ECUDA;
+  }
+  return CRFR_OK;
+}
+
+// packed weights [rows][kdim] bf16 (kdim contiguous); box = (64, box_rows)
+int make_weight_map(CUtensorMap* m, const void* ptr, long long rows, int kdim, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    crfr_set_error("cuTensorMapEncodeTiled entry point not available");
+    return CRFR_ECUDA;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)kdim, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)kdim * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    crfr_set_error("cuTensorMapEncodeTiled(weights rows=%lld k=%d) failed: %d", rows, kdim, (int)r);
+    return CRFR_ECUDA;
+  }
+  return CRFR_OK;
+}
+
+struct Tiling {
+  int bw, bh, bn, tiles_x, tiles_y, tiles_n, rows;  // rows = bw*bh*bn <= 128
+};
+
+bool make_tiling(int n, int h, int w, Tiling* t) {
+  if (w >= 128) {
+    t->bw = 128; t->bh = 1; t->bn = 1;
+  } else {
+    t->bw = w;
+    t->bh = 128 / w;
+    if (t->bh > h) t->bh = h;
+    if (t->bh < 1) return false;
+    t->bn = 128 / (t->bw * t->bh);
+    if (t->bn < 1) t->bn = 1;
+    if (t->bn > 256) return false;
+  }
+  t->rows = t->bw * t->bh * t->bn;
+  t->tiles_x = (w + t->bw - 1) / t->bw;
+  t->tiles_y = (h + t->bh - 1) / t->bh;
+  t->tiles_n = (n + t->bn - 1) / t->bn;
+  return t->rows <= 128 && t->rows >= 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward / dgrad kernel
+// ------------------------------------------------------------------------------------------------
+struct ConvParams {
+  int n, h, w;
+  int kchunks, ksize, ntaps, pad, sign;
+  int bw, bh, bn, tiles_x, tiles_y, rows;
+  int out_ld;
+  bf16* out;
+  const float* bias;
+};
+
+constexpr int kConvThreads = 192;  // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
+constexpr int kATileBytes = 128 * 128;
+
+template <int N>
+struct ConvCfg {
+  static constexpr int kBTileBytes = N * 128;
+  static constexpr int kStageBytes = kATileBytes + kBTileBytes;
+  static constexpr int kStages = (N <= 64) ? 4 : 3;
+  static constexpr int kTmemCols = (N <= 32) ? 32 : (N <= 64) ? 64 : (N <= 128) ? 128 : 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int N>
+__global__ void __launch_bounds__(kConvThreads, 1)
+tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvParams p) {
+  using Cfg = ConvCfg<N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = (uint64_t*)(base + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty = full + Cfg::kStages;
+  uint64_t* tmem_full = empty + Cfg::kStages;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+  }
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  int t = blockIdx.x;
+  const int tx = t % p.tiles_x; t /= p.tiles_x;
+  const int ty = t % p.tiles_y; t /= p.tiles_y;
+  const int x0 = tx * p.bw, y0 = ty * p.bh, n0 = t * p.bn;
+  const int iters = p.ntaps * p.kchunks;
+  const uint32_t a_bytes = (uint32_t)p.rows * 128u;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % Cfg::kStages;
+        mbar_wait(&empty[s], ((it / Cfg::kStages) & 1) ^ 1);
+        mbar_expect_tx(&full[s], a_bytes + Cfg::kBTileBytes);
+        const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
+        const int ky = tap / p.ksize, kx = tap - ky * p.ksize;
+        uint8_t* sa = base + s * Cfg::kStageBytes;
+        tma_load_4d(sa, &tmA, &full[s], kc * 64, x0 + p.sign * (kx - p.pad), y0 + p.sign * (ky - p.pad), n0);
+        tma_load_2d(sa + kATileBytes, &tmB, &full[s], kc * 64, tap * N);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
+      for (int it = 0; it < iters; ++it) {
+        const int s = it % Cfg::kStages;
+        mbar_wait(&full[s], (it / Cfg::kStages) & 1);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(base + s * Cfg::kStageBytes);
+        const uint32_t b_addr = a_addr + kATileBytes;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t da = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+          const uint64_t db = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+          umma_bf16(tmem, da, db, idesc, (uint32_t)((it | k) != 0));
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(tmem_full);
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int iw = r % p.bw;
+    const int rr = r / p.bw;
+    const int ih = rr % p.bh, in = rr / p.bh;
+    const int x = x0 + iw, y = y0 + ih, n = n0 + in;
+    const bool valid = r < p.rows && x < p.w && y < p.h && n < p.n;
+    bf16* dst = p.out + (((long long)n * p.h + y) * p.w + x) * p.out_ld;
+#pragma unroll
+    for (int c0 = 0; c0 < N; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c0, v);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          float f[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j + e]) + (p.bias ? p.bias[c0 + j + e] : 0.f);
+          *reinterpret_cast<bf16x8*>(dst + c0 + j) = pack8(f);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem);
+  }
+}
+
+template <int N>
+int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, int tiles, cudaStream_t st) {
+  using Cfg = ConvCfg<N>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    CRFR_CUDA(cudaFuncSetAttribute(tc_conv_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  tc_conv_kernel<N><<<tiles, kConvThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
+  CRFR_COUNT_LAUNCH();
+  CRFR_LAUNCH_CHECK();
+  return CRFR_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// wgrad kernel
+// ------------------------------------------------------------------------------------------------
+struct WgradParams {
+  int n, h, w;
+  int bw, bh, bn, tiles_x, tiles_y, total_tiles;
+  int cin, cout;
+  float* G;  // [9][cin][cout] fp32, pre-zeroed
+};
+
+constexpr int kTile16K = 128 * 128;
+
+template <int N>
+struct WgCfg {
+  static constexpr int kDyTiles = N / 64;
+  static constexpr int kStageBytes = (3 + kDyTiles) * kTile16K;
+  static constexpr int kStages = (N <= 64) ? 3 : 2;
+  static constexpr int kTmemCols = (2 * N <= 128) ? 128 : 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int N>
+__global__ void __launch_bounds__(kConvThreads, 1)
+tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY, WgradParams p) {
+  using Cfg = WgCfg<N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = (uint64_t*)(base + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty = full + Cfg::kStages;
+  uint64_t* tmem_full = empty + Cfg::kStages;
+  uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+    prefetch_tmap(&tmX);
+    prefetch_tmap(&tmDY);
+  }
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  const int ky = blockIdx.y, kc = blockIdx.z;
+  const int first = blockIdx.x, step = gridDim.x;
+  const int my_tiles = first < p.total_tiles ? (p.total_tiles - first + step - 1) / step : 0;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < my_tiles; ++i) {
+        const int s = i % Cfg::kStages;
+        mbar_wait(&empty[s], ((i / Cfg::kStages) & 1) ^ 1);
+        mbar_expect_tx(&full[s], Cfg::kStageBytes);
+        int t = first + i * step;
+        const int tx = t % p.tiles_x; t /= p.tiles_x;
+        const int ty = t % p.tiles_y; t /= p.tiles_y;
+        const int x0 = tx * p.bw, y0 = ty * p.bh, n0 = t * p.bn;
+        uint8_t* sb = base + s * Cfg::kStageBytes;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx)
+          tma_load_4d(sb + kx * kTile16K, &tmX, &full[s], kc * 64, x0 + kx - 1, y0 + ky - 1, n0);
+#pragma unroll
+        for (int j = 0; j < Cfg::kDyTiles; ++j)
+          tma_load_4d(sb + (3 + j) * kTile16K, &tmDY, &full[s], j * 64, x0, y0, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, N, 1, 1);
+      for (int i = 0; i < my_tiles; ++i) {
+        const int s = i % Cfg::kStages;
+        mbar_wait(&full[s], (i / Cfg::kStages) & 1);
+        tc_fence_after();
+        const uint32_t sb = smem_u32(base + s * Cfg::kStageBytes);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {  // 8 x 16 pixels
+          const uint64_t a01 = make_smem_desc_sw128(sb + k * 2048, kTile16K, 1024);
+          const uint64_t a2x = make_smem_desc_sw128(sb + 2 * kTile16K + k * 2048, kTile16K, 1024);
+          const uint64_t db = make_smem_desc_sw128(sb + 3 * kTile16K + k * 2048, kTile16K, 1024);
+          const uint32_t acc = (uint32_t)((i | k) != 0);
+          umma_bf16(tmem, a01, db, idesc, acc);
+          umma_bf16(tmem + N, a2x, db, idesc, acc);
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(tmem_full);
+    }
+  } else if (my_tiles > 0) {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int ci = kc * 64 + (r & 63);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int kx = half == 0 ? (r >> 6) : 2;
+      const bool live = half == 0 || r < 64;   // warp-uniform (32-row granularity)
+      float* dst = p.G + ((long long)(ky * 3 + kx) * p.cin + ci) * p.cout;
+#pragma unroll
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + half * N + c0, v);
+        tmem_ld_wait();
+        if (live) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            red_add_v4(dst + c0 + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                       __uint_as_float(v[j + 3]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem);
+  }
+}
+
+// dW[co][ci][t] += G[t][ci][co]
+__global__ void wgrad_unpack_kernel(const float* __restrict__ G, float* __restrict__ dw, int cin, int cout, int T) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)cout * cin * T;
+  if (i >= total) return;
+  int t = (int)(i % T);
+  long long q = i / T;
+  int ci = (int)(q % cin);
+  int co = (int)(q / cin);
+  dw[i] += G[((long long)t * cin + ci) * cout + co];
+}
+
+template <int N>
+int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmDY, const WgradParams& p, int splits, cudaStream_t st) {
+  using Cfg = WgCfg<N>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    CRFR_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  tc_wgrad_kernel<N><<<dim3(splits, 3, p.cin / 64), kConvThreads, Cfg::kSmemBytes, st>>>(tmX, tmDY, p);
+  CRFR_COUNT_LAUNCH();
+  CRFR_LAUNCH_CHECK();
+  return CRFR_OK;
+}
+
+bool spatial_ok(int h, int w, bool exact128) {
+  Tiling t;
+  if (!make_tiling(1, h, w, &t)) return false;
+  if (w > 128 && (w % 128) != 0 && exact128) return false;
+  if (exact128) {
+    // wgrad sums over all 128 rows of a tile: rows must be real pixels or TMA zero fill
+    if (t.bw * t.bh * t.bn != 128) return false;
+  }
+  return true;
+}
+
+}  // namespace
+
+int crfr_tc_supported(int op, int h, int w, int cin, int cout, int k, int stride, int pad) {
+  if (k != 3 || stride != 1 || pad != 1) return 0;
+  if (cin % 64 || cout % 64) return 0;
+  const int nout = (op == 1) ? cin : cout;  // GEMM N
+  if (op == 2) {
+    if (cout != 64 && cout != 128) return 0;
+    return spatial_ok(h, w, true) ? 1 : 0;
+  }
+  if (nout != 64 && nout != 128 && nout != 192 && nout != 256) return 0;
+  return spatial_ok(h, w, false) ? 1 : 0;
+}
+
+size_t crfr_tc_workspace_bytes(const crfr_conv_desc* d) {
+  return sizeof(float) * (size_t)d->k * d->k * d->cin * d->cout + 256;  // wgrad scratch
+}
+
+int crfr_tc_conv(const crfr_conv_desc* d, int dgrad, const void* src, const void* w_packed, const float* bias,
+                 void* dst, float* stats, float eps, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const int ksrc = dgrad ? d->cout : d->cin;    // GEMM K per tap
+  const int nout = dgrad ? d->cin : d->cout;    // GEMM N
+  const int src_ld = dgrad ? d->out_ld : d->in_ld;
+  const int dst_ld = dgrad ? d->in_ld : d->out_ld;
+  CRFR_CHECK_ARG(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0 && ((uintptr_t)w_packed & 15) == 0 &&
+                     (src_ld & 7) == 0 && (dst_ld & 7) == 0,
+                 "tc_conv: pointers must be 16B aligned and ld a multiple of 8");
+  Tiling t;
+  if (!make_tiling(d->n, d->h, d->w, &t)) {
+    crfr_set_error("tc_conv: unsupported spatial size %dx%d", d->h, d->w);
+    return CRFR_EUNSUPPORTED;
+  }
+  CUtensorMap tmA, tmB;
+  CRFR_TRY(make_act_map(&tmA, src, d->n, d->h, d->w, ksrc, src_ld, t.bw, t.bh, t.bn));
+  const int T = d->k * d->k;
+  CRFR_TRY(make_weight_map(&tmB, w_packed, (long long)T * nout, ksrc, nout));
+  ConvParams p;
+  p.n = d->n; p.h = d->h; p.w = d->w;
+  p.kchunks = ksrc / 64; p.ksize = d->k; p.ntaps = T; p.pad = d->pad; p.sign = dgrad ? -1 : 1;
+  p.bw = t.bw; p.bh = t.bh; p.bn = t.bn; p.tiles_x = t.tiles_x; p.tiles_y = t.tiles_y; p.rows = t.rows;
+  p.out_ld = dst_ld; p.out = (bf16*)dst; p.bias = bias;
+  const int tiles = t.tiles_x * t.tiles_y * t.tiles_n;
+  switch (nout) {
+    case 64: CRFR_TRY(launch_conv<64>(tmA, tmB, p, tiles, st)); break;
+    case 128: CRFR_TRY(launch_conv<128>(tmA, tmB, p, tiles, st)); break;
+    case 192: CRFR_TRY(launch_conv<192>(tmA, tmB, p, tiles, st)); break;
+    case 256: CRFR_TRY(launch_conv<256>(tmA, tmB, p, tiles, st)); break;
+    default:
+      crfr_set_error("tc_conv: unsupported output channel count %d", nout);
+      return CRFR_EUNSUPPORTED;
+  }
+  if (stats && !dgrad)
+    CRFR_TRY(crfr_norm_stats(dst, d->n, d->oh * d->ow, d->cout, d->out_ld, eps, stats, ws, ws_bytes, (void*)st));
+  return CRFR_OK;
+}
+
+int crfr_tc_wgrad(const crfr_conv_desc* d, const void* x, const void* dy, float* dw, void* ws, size_t ws_bytes,
+                  cudaStream_t st) {
+  CRFR_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0 && (d->in_ld & 7) == 0 && (d->out_ld & 7) == 0,
+                 "tc_wgrad: pointers must be 16B aligned and ld a multiple of 8");
+  const size_t need = sizeof(float) * (size_t)9 * d->cin * d->cout;
+  if (!ws || ws_bytes < need) {
+    crfr_set_error("tc_wgrad: workspace %zu < %zu", ws_bytes, need);
+    return CRFR_EWORKSPACE;
+  }
+  Tiling t;
+  if (!make_tiling(d->n, d->h, d->w, &t) || t.bw * t.bh * t.bn != 128) {
+    crfr_set_error("tc_wgrad: unsupported spatial size %dx%d", d->h, d->w);
+    return CRFR_EUNSUPPORTED;
+  }
+  CUtensorMap tmX, tmDY;
+  CRFR_TRY(make_act_map(&tmX, x, d->n, d->h, d->w, d->cin, d->in_ld, t.bw, t.bh, t.bn));
+  CRFR_TRY(make_act_map(&tmDY, dy, d->n, d->h, d->w, d->cout, d->out_ld, t.bw, t.bh, t.bn));
+  CRFR_CUDA(cudaMemsetAsync(ws, 0, need, st));
+  WgradParams p;
+  p.n = d->n; p.h = d->h; p.w = d->w;
+  p.bw = t.bw; p.bh = t.bh; p.bn = t.bn; p.tiles_x = t.tiles_x; p.tiles_y = t.tiles_y;
+  p.total_tiles = t.tiles_x * t.tiles_y * t.tiles_n;
+  p.cin = d->cin; p.cout = d->cout; p.G = (float*)ws;
+  int ctas_per_split = 3 * (d->cin / 64);
+  int splits = (148 * 2 + ctas_per_split - 1) / ctas_per_split;
+  if (splits > p.total_tiles) splits = p.total_tiles;
+  if (splits < 1) splits = 1;
+  if (d->cout == 64) CRFR_TRY(launch_wgrad<64>(tmX, tmDY, p, splits, st));
+  else if (d->cout == 128) CRFR_TRY(launch_wgrad<128>(tmX, tmDY, p, splits, st));
+  else {
+    crfr_set_error("tc_wgrad: unsupported cout %d", d->cout);
+    return CRFR_EUNSUPPORTED;
+  }
+  long long total = (long long)d->cout * d->cin * 9;
+  wgrad_unpack_kernel<<<crfr_cdiv(total, 256), 256, 0, st>>>((const float*)ws, dw, d->cin, d->cout, 9);
+  CRFR_COUNT_LAUNCH();
+  CRFR_LAUNCH_CHECK();
+  return CRFR_OK;
+}

@@ -1,0 +1,59 @@
+"""Drop-in for the matcher part of the reference's utils/utils.py plus the cosine identification entry point."""
+import numpy as np
+import torch
+
+from .. import ops
+
+
+def l2_norm(x, axis=1):
+    """ref: DISTILLATION/model/model_irse.py:16-20.  Returns unit-norm bf16 rows (the matcher's operand format)."""
+    assert axis == 1
+    return ops.l2norm_bf16(x)
+
+
+def calculate_accuracy(threshold, dist, actual_issame):
+    """ref: utils/utils.py:14-24.  dist / actual_issame may be numpy arrays or tensors; counting runs on the GPU."""
+    d = torch.as_tensor(np.asarray(dist) if not torch.is_tensor(dist) else dist).float().cuda()
+    s = torch.as_tensor(np.asarray(actual_issame) if not torch.is_tensor(actual_issame) else actual_issame).cuda()
+    tp, fp, tn, fn = (int(v) for v in ops.verify_counts(d, s, float(threshold)).tolist())
+    tpr = 0 if (tp + fn == 0) else float(tp) / float(tp + fn)
+    fpr = 0 if (fp + tn == 0) else float(fp) / float(fp + tn)
+    acc = float(tp + tn) / d.numel()
+    return tpr, fpr, acc
+
+
+def calculate_roc(thresholds, embeddings1, embeddings2, actual_issame, nrof_folds=10, seed=0):
+    """ref: utils/utils.py:26-87 with the K-fold shuffle seeded (the reference's is not) and the dead margin_list
+    work dropped.  Pair distances and every threshold count run on the GPU."""
+    e1 = torch.as_tensor(embeddings1).float().cuda()
+    e2 = torch.as_tensor(embeddings2).float().cuda()
+    same = torch.as_tensor(np.asarray(actual_issame)).cuda()
+    dist, _ = ops.pair_verify(e1, e2, 0.0)
+    n = dist.numel()
+    idx = np.arange(n)
+    np.random.RandomState(seed).shuffle(idx)
+    sizes = np.full(nrof_folds, n // nrof_folds, int)
+    sizes[: n % nrof_folds] += 1
+    nt = len(thresholds)
+    tprs = np.zeros((nrof_folds, nt)); fprs = np.zeros((nrof_folds, nt))
+    accuracy = np.zeros(nrof_folds); best = np.zeros(nrof_folds)
+    cur = 0
+    for f, sz in enumerate(sizes):
+        test = np.sort(idx[cur:cur + sz]); cur += sz
+        mask = np.ones(n, bool); mask[test] = False
+        tr = torch.from_numpy(np.nonzero(mask)[0]).cuda(); te = torch.from_numpy(test).cuda()
+        d_tr, s_tr, d_te, s_te = dist[tr], same[tr], dist[te], same[te]
+        acc_train = np.array([calculate_accuracy(t, d_tr, s_tr)[2] for t in thresholds])
+        bi = int(np.argmax(acc_train)); best[f] = thresholds[bi]
+        for ti, t in enumerate(thresholds):
+            tprs[f, ti], fprs[f, ti], _ = calculate_accuracy(t, d_te, s_te)
+        accuracy[f] = calculate_accuracy(thresholds[bi], d_te, s_te)[2]
+    return tprs.mean(0), fprs.mean(0), accuracy.mean(), best
+
+
+def cosine_identify(probes, gallery, k=5, normalized=False):
+    """1:N identification: top-k gallery indices by cosine similarity without materialising the score matrix.
+    probes [P, D], gallery [G, D] (fp32 embeddings, or unit-norm bf16 when ``normalized``)."""
+    p = probes if normalized else l2_norm(probes)
+    g = gallery if normalized else l2_norm(gallery)
+    return ops.cosine_topk(p, g, k)

@@ -1,0 +1,196 @@
+/* crfr.h - C-ABI of the B200-native hot path of HyoKong/Cross-Resolution-Face-Recognition.
+ *
+ * The reference has no FFI: its operator API is torch.nn.Module.__call__ + state_dict.  Every entry
+ * point below replaces the ATen/cuDNN (or Pillow / numpy) call sequence behind one reference site, cited as
+ * "ref:" (paths relative to the reference root).  The Python host mirror (package crfr_b200) binds these with
+ * ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless named host_*;
+ *   - the caller owns all memory (inputs, outputs, workspace); the library never allocates device memory and
+ *     keeps no pointer past return;
+ *   - every call only enqueues work on `stream` (a cudaStream_t passed as void*) and returns immediately;
+ *   - return value: 0 = ok, non-zero = error code; message via crfr_last_error() (thread-local);
+ *   - activations are NHWC bf16 with an explicit per-pixel stride `ld` (elements) so that a tensor can be a channel
+ *     slice of a wider buffer (this is how torch.cat at model/FSRnet.py:505 is eliminated);
+ *   - parameters and parameter gradients are fp32 in the reference's own layouts (OIHW etc.); gradients are
+ *     ACCUMULATED (+=) because the reference shares one module across several call sites (FSRnet.py:331-333).
+ */
+#ifndef CRFR_H_
+#define CRFR_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CRFR_ENGINE_AUTO 0
+#define CRFR_ENGINE_DIRECT 1   /* CUDA-core direct kernels (edge shapes, cross-check) */
+#define CRFR_ENGINE_TCGEN05 2  /* tcgen05/TMEM implicit GEMM fed by TMA */
+
+const char* crfr_last_error(void);
+int crfr_version(void);
+/* number of kernel launches issued by this library in this process (bench.py reports it as gpu_launches) */
+unsigned long long crfr_launch_count(void);
+/* 1 if the engine can run the shape (h,w,cin,cout,k,stride,pad), else 0 */
+int crfr_conv_engine_supported(int engine, int op, int h, int w, int cin, int cout, int k, int stride, int pad);
+
+/* ---------------------------------------------------------------- layout ---------------------------------- */
+/* ref: the NCHW fp32 tensors at the nn.Module boundary (model/FSRnet.py:497, model/resnet.py:208) */
+int crfr_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int n, int c, int h, int w, int dst_ld, int c_zero_to,
+                               void* stream);
+int crfr_nhwc_bf16_to_nchw_f32(const void* src, float* dst, int n, int c, int h, int w, int src_ld, void* stream);
+/* dst[t][r][s] (bf16, s padded with zeros up to s_pad) = src[r*r_stride + s*s_stride + t*t_stride] (fp32) */
+int crfr_pack_weight(const float* src, void* dst, int T, int R, int S, int s_pad, long long r_stride,
+                     long long s_stride, long long t_stride, void* stream);
+
+/* ---------------------------------------------------------------- convolutions ---------------------------- */
+typedef struct crfr_conv_desc {
+  int n, h, w;        /* input batch / spatial size            */
+  int cin, cout;      /* logical channel counts                */
+  int k, stride, pad; /* square kernel                         */
+  int oh, ow;         /* output spatial size                   */
+  int in_ld, out_ld;  /* per-pixel strides of x and y (elems)  */
+  int transposed;     /* 0: Conv2d, 1: ConvTranspose2d         */
+} crfr_conv_desc;
+
+/* ref: nn.Conv2d / nn.ConvTranspose2d forward at model/FSRnet.py:79,85,110,114,312,318,345,351,384,391,392,432,436,439
+ *      and model/resnet.py:23-26,158,196.
+ * x: NHWC bf16.  w_packed: bf16 [k*k][cout][cin_pad] made by crfr_pack_weight.  bias: fp32 [cout] or NULL.
+ * y: NHWC bf16 or NULL.  y_nchw: fp32 NCHW [n][cout][oh][ow] or NULL.
+ * stats: fp32 [n][cout][2] = (mean, rstd) of y over (oh,ow) per (n, channel) - the InstanceNorm statistics
+ *        (FSRnet.py:81) computed from the stored (bf16-rounded) values; NULL to skip. */
+int crfr_conv_fwd(int engine, const crfr_conv_desc* d, const void* x, const void* w_packed, int cin_pad,
+                  const float* bias, void* y, float* y_nchw, float* stats, float eps, void* ws, size_t ws_bytes,
+                  void* stream);
+/* dx = gradient w.r.t. x.  w_packed_t: bf16 [k*k][cin][cout_pad].  dx: NHWC bf16 with stride d->in_ld. */
+int crfr_conv_dgrad(int engine, const crfr_conv_desc* d, const void* dy, const void* w_packed_t, int cout_pad,
+                    void* dx, void* ws, size_t ws_bytes, void* stream);
+/* dw (fp32, reference layout: Conv2d [cout][cin][k][k], ConvTranspose2d [cin][cout][k][k]) += ...; dbias += sum dy */
+int crfr_conv_wgrad(int engine, const crfr_conv_desc* d, const void* x, const void* dy, float* dw, float* dbias,
+                    void* ws, size_t ws_bytes, void* stream);
+size_t crfr_conv_workspace_bytes(const crfr_conv_desc* d);
+
+/* ---------------------------------------------------------------- normalisation + activation -------------- */
+/* ref: nn.InstanceNorm2d (FSRnet.py:81,87,112,115,319,347,385,434), nn.PReLU (:84,88,113,314,346,386,433),
+ *      residual add (:96,132); with groups==1 over the whole batch it is train-mode nn.BatchNorm2d + ReLU
+ *      (model/resnet.py:24-28).
+ * stats[n][c][2] (mean, rstd) over hw pixels of image n. */
+int crfr_norm_stats(const void* y, int n, int hw, int c, int ld, float eps, float* stats, void* ws, size_t ws_bytes,
+                    void* stream);
+/* out = act(gamma*(y-mean)*rstd + beta + res); gamma/beta NULL = non-affine; alpha NULL = no activation;
+ * alpha_is_relu != 0 -> ReLU (alpha ignored). res NULL = no residual. */
+int crfr_norm_act_fwd(const void* y, int y_ld, const float* stats, const float* gamma, const float* beta,
+                      const float* alpha, int relu, const void* res, int res_ld, void* out, int out_ld, int n,
+                      int hw, int c, void* stream);
+/* dout = dout_a (+ dout_b).  Outputs: dz (grad wrt pre-activation, == grad wrt res), dy (grad wrt conv output),
+ * dgamma/dbeta/dalpha fp32 [c] accumulated (NULL to skip). */
+int crfr_norm_act_bwd(const void* dout_a, int da_ld, const void* dout_b, int db_ld, const void* y, int y_ld,
+                      const float* stats, const float* gamma, const float* beta, const float* alpha, int relu,
+                      const void* res, int res_ld, void* dz, int dz_ld, void* dy, int dy_ld, float* dgamma,
+                      float* dbeta, float* dalpha, int n, int hw, int c, void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------- hourglass resampling --------------------- */
+/* ref: F.max_pool2d(x,2,2) FSRnet.py:202 ; F.interpolate(scale_factor=2)+add :210-211 */
+int crfr_maxpool2_fwd(const void* x, int x_ld, void* out, int out_ld, int n, int h, int w, int c, void* stream);
+int crfr_maxpool2_bwd(const void* x, int x_ld, const void* dout, int dout_ld, void* dx, int dx_ld, int n, int h,
+                      int w, int c, void* stream);
+int crfr_upnearest2_add_fwd(const void* up, int up_ld, const void* low, int low_ld, void* out, int out_ld, int n,
+                            int h, int w, int c, void* stream); /* h,w: size of `low`; out is 2h x 2w */
+int crfr_upnearest2_bwd(const void* dout, int dout_ld, void* dlow, int dlow_ld, int n, int h, int w, int c,
+                        void* stream);
+/* out = a + b (+ c) elementwise on NHWC bf16 views */
+int crfr_add_n(const void* a, int a_ld, const void* b, int b_ld, const void* c3, int c_ld, void* out, int out_ld,
+               long long pixels, int c, void* stream);
+
+/* ---------------------------------------------------------------- losses ---------------------------------- */
+/* ref: MSELossFunc loss/loss.py:7-15.  x,t fp32 NCHW [n][c][hw]; loss[0] = mean((x-t)^2)*97;
+ * dx (NHWC bf16, stride dx_ld, may be NULL) = gscale * dloss/dx. */
+int crfr_loss_mse97(const float* x, const float* t, int n, int c, int hw, float gscale, float* loss, void* dx,
+                    int dx_ld, void* ws, size_t ws_bytes, void* stream);
+/* ref: MSELoss_Landmark loss/loss.py:17-32.  x fp32 NCHW [n][c][hw], t fp32 [n][hw]. dx written at channel
+ * offset dx_coff of an NHWC bf16 buffer. */
+int crfr_loss_landmark(const float* x, const float* t, int n, int c, int hw, float gscale, float* loss, void* dx,
+                       int dx_ld, int dx_coff, void* ws, size_t ws_bytes, void* stream);
+/* ref: CrossEntropyLoss2d loss/loss.py:34-62.  logits fp32 NCHW [n][c][hw], target int64 [n][hw]. */
+int crfr_loss_ce2d(const float* logits, const long long* target, int n, int c, int hw, float gscale, float* loss,
+                   void* dx, int dx_ld, int dx_coff, void* ws, size_t ws_bytes, void* stream);
+/* ref: nn.MSELoss over (t - s) vs a, distill_main.py:63,68-70.  All NHWC bf16 or all fp32 flat (is_f32).
+ * loss = mean(((t - s) - a)^2) with s NULL meaning 0.  Gradients (scaled by gscale) are optional. */
+int crfr_loss_kd(const void* t, const void* s, const void* a, long long numel, int is_f32, float gscale,
+                 float* loss, void* dt, void* ds, void* da, void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------- optimiser ------------------------------- */
+/* ref: torch.optim.RMSprop(lr, alpha=.99, eps=1e-8, weight_decay=1e-5) FSR_main.py:185, distill_main.py:222-225.
+ * g is multiplied by gscale first (1/world_size after the all-reduce). */
+int crfr_rmsprop_step(float* p, const float* g, float* sq, long long n, float lr, float alpha, float eps,
+                      float weight_decay, float gscale, void* stream);
+
+/* ---------------------------------------------------------------- bicubic --------------------------------- */
+/* ref: PIL Image.resize(BICUBIC) at bicubic_interpolation.py:188, SUPER_RESOLUTION/FHN_loader.py:66.
+ * src u8 NHWC [n][ih][iw][c] -> dst u8 NHWC [n][oh][ow][c] (bit-exact with Pillow's 8-bit path) and/or
+ * dst_f32 NCHW normalised (x/255-0.5)/0.5 (helen_loader.py:53-58).  Coefficient tables are built on the host
+ * (double precision, exactly as Pillow) by crfr_bicubic_tables into host_tab, then copied by the caller. */
+int crfr_bicubic_table_size(int in_size, int out_size);                   /* number of int32 entries */
+int crfr_bicubic_tables(int in_size, int out_size, int32_t* host_tab);    /* [out][2+ksize]: xmin, count, kk[] */
+int crfr_bicubic_u8(const uint8_t* src, int n, int ih, int iw, int c, const int32_t* tab_h, const int32_t* tab_w,
+                    int oh, int ow, uint8_t* tmp, uint8_t* dst, float* dst_f32, void* stream);
+
+/* ---------------------------------------------------------------- matcher --------------------------------- */
+/* ref: l2_norm DISTILLATION/model/model_irse.py:16-20 ; accuracy()/topk utils/eval.py:6-19 ; threshold decision
+ * utils/utils.py:14-24.  rows of x (fp32 [rows][dim]) -> unit-norm bf16. */
+int crfr_l2norm_bf16(const float* x, void* out, long long rows, int dim, void* stream);
+/* probes bf16 [p][dim], gallery bf16 [g][dim] (both unit norm).  Writes top-k (k<=8) scores fp32 [p][k] and global
+ * indices int32 [p][k] (+ index_base), sorted descending, ties -> lowest index. */
+int crfr_cosine_topk(int engine, const void* probes, const void* gallery, int p, long long g, int dim, int k,
+                     int index_base, float* top_val, int* top_idx, void* ws, size_t ws_bytes, void* stream);
+size_t crfr_cosine_topk_workspace_bytes(int p, long long g, int dim, int k);
+/* merges `parts` per-shard top-k lists ([parts][p][k]) into one (gallery-sharded multi-GPU path) */
+int crfr_topk_merge(const float* vals, const int* idx, int parts, int p, int k, float* out_val, int* out_idx,
+                    void* stream);
+/* ref: output.topk(maxk, 1, True, True) on a materialised score matrix (utils/eval.py:11): scores fp32 [p][g],
+ * k <= 8, sorted descending, ties -> lowest index. */
+int crfr_topk_rows(const float* scores, int p, long long g, int k, float* out_val, int* out_idx, void* stream);
+/* ref: calculate_accuracy utils/utils.py:14-24: counts[4] = tp, fp, tn, fn of (dist < thr) vs issame (u8) */
+int crfr_verify_counts(const float* dist, const uint8_t* issame, long long n, float thr, unsigned long long* counts,
+                       void* stream);
+/* verification: same[i] = (sum((e1-e2)^2) < thr) for fp32 pairs; also writes dist */
+int crfr_pair_verify(const float* e1, const float* e2, long long pairs, int dim, float thr, float* dist,
+                     uint8_t* same, void* stream);
+
+/* ---------------------------------------------------------------- FSRNet network program ------------------ */
+#define CRFR_FSRNET_NPARAMS 202
+typedef struct crfr_fsrnet_io {
+  int batch, size;          /* size = H = W of the (already upsampled) network input, multiple of 16 */
+  const float* x;           /* [B,3,H,W] fp32 NCHW */
+  float* coarse;            /* [B,3,H,W]      (out) */
+  float* out;               /* [B,3,H,W]      (out) */
+  float* landmark;          /* [B,97,H/4,W/4] (out) */
+  float* parsing;           /* [B,11,H/4,W/4] (out) */
+  /* training targets (crfr_fsrnet_train_step only) */
+  const float* hr;          /* [B,3,H,W] */
+  const float* heatmap;     /* [B,H/4,W/4] */
+  const long long* labels;  /* [B,1,H/4,W/4] int64 */
+  float loss_div;           /* the 2*train_batch of FSR_main.py:234 (global batch under data parallelism) */
+  float w_pix;              /* 5.0 at FSR_main.py:233 (7.0 at :319) */
+} crfr_fsrnet_io;
+
+/* ref: OverallNetwork.forward model/FSRnet.py:497-508 with the runnable wiring of :538-541.
+ * params: 202 fp32 device pointers in state_dict order.  engine selects the conv engine for eligible layers. */
+size_t crfr_fsrnet_workspace_bytes(int batch, int size, int training);
+int crfr_fsrnet_forward(int engine, const float* const* host_params, const crfr_fsrnet_io* io, int training,
+                        void* ws, size_t ws_bytes, void* stream);
+/* grads w.r.t. the four outputs (fp32 NCHW, any may be NULL) -> accumulates into host_grads[202] (NULL entries skipped) */
+int crfr_fsrnet_backward(int engine, const float* const* host_params, float* const* host_grads,
+                         const crfr_fsrnet_io* io, const float* d_coarse, const float* d_out,
+                         const float* d_landmark, const float* d_parsing, void* ws, size_t ws_bytes, void* stream);
+/* forward + losses (FSR_main.py:233-234) + backward in one call.  losses: device fp32[5] =
+ * (total, L_sr, L_coarse, L_landmark, L_ce). */
+int crfr_fsrnet_train_step(int engine, const float* const* host_params, float* const* host_grads,
+                           const crfr_fsrnet_io* io, float* losses, void* ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CRFR_H_ */

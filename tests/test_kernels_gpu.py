@@ -1,0 +1,315 @@
+"""Per-kernel parity on the GPU: every C-ABI family against a plain fp32 PyTorch (CPU) statement of the same op on
+identical bf16-representable inputs.  Tolerances: outputs stored as bf16 carry one rounding (2^-9 relative per
+element) -> norm-wise 5e-3; fp32 results (weight gradients, losses) -> 1e-4 (north_star tolerance)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.util import bf16_round, max_abs, nhwc_from, rel_err, to_nchw
+
+pytestmark = pytest.mark.gpu
+
+BF16_TOL = 5e-3
+F32_TOL = 1e-4
+
+
+def _ops():
+    from crfr_b200 import ops
+    return ops
+
+
+def _L():
+    from crfr_b200 import _lib
+    return _lib
+
+
+# (cin, cout, k, stride, pad, h) - the edge layers of FSRNet that stay on the CUDA-core engine, plus a 64->64 case
+DIRECT_SHAPES = [
+    (3, 64, 3, 1, 1, 32),      # coarse conv_input  (FSRnet.py:312)
+    (64, 3, 3, 1, 1, 32),      # conv_mid / conv_out (:318, :439)
+    (3, 64, 7, 4, 3, 64),      # encoder stem       (:345)
+    (3, 128, 7, 4, 3, 32),     # prior stem         (:384)
+    (128, 11, 1, 1, 0, 16),    # fc                 (:391)
+    (128, 97, 1, 1, 0, 16),    # fc_landmark        (:392)
+    (64, 64, 3, 1, 1, 16),     # residual conv on the direct engine (cross-check path)
+    (192, 64, 3, 1, 1, 8),     # decoder conv_input (:432)
+]
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,pad,h", DIRECT_SHAPES)
+def test_direct_conv_fwd_dgrad_wgrad(cuda, cin, cout, k, stride, pad, h):
+    ops, L = _ops(), _L()
+    g = torch.Generator().manual_seed(cin * 1000 + cout)
+    n = 2
+    x = bf16_round(torch.randn(n, cin, h, h, generator=g))
+    w = bf16_round(torch.randn(cout, cin, k, k, generator=g) * 0.1)
+    b = torch.randn(cout, generator=g)
+    xr = x.clone().requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    br = b.clone().requires_grad_(True)
+    y_ref = F.conv2d(xr, wr, br, stride, pad)
+    dy = bf16_round(torch.randn(y_ref.shape, generator=g))
+    y_ref.backward(dy)
+
+    in_ld = 4 if cin < 8 else cin
+    out_ld = 4 if cout < 8 else (cout + 7) // 8 * 8
+    xg = nhwc_from(x, in_ld)
+    wp = ops.pack_conv_weight(w.cuda())
+    y, _, _ = ops.conv_fwd(xg, wp, cin, cout, k, stride, pad, bias=b.cuda(), engine=L.ENGINE_DIRECT)
+    assert rel_err(to_nchw(y, cout), y_ref) < BF16_TOL
+    _, yn, _ = ops.conv_fwd(xg, wp, cin, cout, k, stride, pad, bias=b.cuda(), engine=L.ENGINE_DIRECT, nchw_out=True)
+    assert rel_err(yn, y_ref) < F32_TOL
+
+    dyg = nhwc_from(dy, out_ld)
+    wt = ops.pack_conv_weight(w.cuda(), for_dgrad=True)
+    dx = ops.conv_dgrad(dyg, wt, (n, h, h, in_ld), cin, cout, k, stride, pad, engine=L.ENGINE_DIRECT)
+    assert rel_err(to_nchw(dx, cin), xr.grad) < BF16_TOL
+    if in_ld > cin:
+        assert float(dx[..., cin:].float().abs().max()) == 0.0     # channel padding stays zero
+    dw, db = ops.conv_wgrad(xg, dyg, cin, cout, k, stride, pad, engine=L.ENGINE_DIRECT, want_bias=True)
+    assert rel_err(dw, wr.grad) < F32_TOL
+    assert rel_err(db, br.grad) < F32_TOL
+
+
+def test_direct_deconv(cuda):
+    """ConvTranspose2d 7x7 s4 p2 op1 64->64 (FSRnet.py:436)."""
+    ops, L = _ops(), _L()
+    g = torch.Generator().manual_seed(7)
+    n, c, h = 2, 64, 8
+    x = bf16_round(torch.randn(n, c, h, h, generator=g))
+    w = bf16_round(torch.randn(c, c, 7, 7, generator=g) * 0.05)
+    b = torch.randn(c, generator=g)
+    xr, wr, br = (t.clone().requires_grad_(True) for t in (x, w, b))
+    y_ref = F.conv_transpose2d(xr, wr, br, 4, 2, 1)
+    dy = bf16_round(torch.randn(y_ref.shape, generator=g))
+    y_ref.backward(dy)
+    xg = nhwc_from(x)
+    wp = ops.pack_conv_weight(w.cuda(), transposed=True)
+    y, _, st = ops.conv_fwd(xg, wp, c, c, 7, 4, 2, bias=b.cuda(), engine=L.ENGINE_DIRECT, transposed=True,
+                            out_hw=(4 * h, 4 * h), want_stats=True)
+    assert rel_err(to_nchw(y), y_ref) < BF16_TOL
+    yb = to_nchw(y)
+    assert max_abs(st[..., 0], yb.mean((2, 3))) < 1e-4
+    assert rel_err(st[..., 1], 1.0 / torch.sqrt(yb.var((2, 3), unbiased=False) + 1e-5)) < 1e-4
+    dyg = nhwc_from(dy)
+    wt = ops.pack_conv_weight(w.cuda(), for_dgrad=True, transposed=True)
+    dx = ops.conv_dgrad(dyg, wt, (n, h, h, c), c, c, 7, 4, 2, engine=L.ENGINE_DIRECT, transposed=True)
+    assert rel_err(to_nchw(dx), xr.grad) < BF16_TOL
+    dw, db = ops.conv_wgrad(xg, dyg, c, c, 7, 4, 2, engine=L.ENGINE_DIRECT, transposed=True, want_bias=True)
+    assert rel_err(dw, wr.grad) < F32_TOL
+    assert rel_err(db, br.grad) < F32_TOL
+
+
+def _prelu(x, a):
+    return torch.clamp(x, min=0) + a.view(1, -1, 1, 1) * torch.clamp(x, max=0)
+
+
+@pytest.mark.parametrize("c,h,affine,act,res", [(64, 32, True, True, True), (128, 8, False, True, True),
+                                                 (64, 16, True, False, False), (128, 16, True, True, False)])
+def test_instance_norm_prelu_add(cuda, c, h, affine, act, res):
+    """IN + PReLU + residual forward/backward (FSRnet.py:75-98, 105-135)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(c + h)
+    n = 3
+    y = bf16_round(torch.randn(n, c, h, h, generator=g) * 2 + 0.5)
+    r = bf16_round(torch.randn(n, c, h, h, generator=g)) if res else None
+    gamma = (torch.rand(c, generator=g) + 0.5) if affine else None
+    beta = torch.randn(c, generator=g) if affine else None
+    alpha = (torch.rand(c, generator=g) * 0.5) if act else None
+    leaves = [t.clone().requires_grad_(True) if t is not None else None for t in (y, r, gamma, beta, alpha)]
+    yr, rr, gr, br, ar = leaves
+    z = F.instance_norm(yr, weight=gr, bias=br, eps=1e-5)
+    if res:
+        z = z + rr
+    out_ref = _prelu(z, ar) if act else z
+    dout = bf16_round(torch.randn(out_ref.shape, generator=g))
+    dout2 = bf16_round(torch.randn(out_ref.shape, generator=g))
+    out_ref.backward(dout + dout2)
+
+    cu = lambda t: None if t is None else t.cuda()
+    yg = nhwc_from(y)
+    stats = ops.norm_stats(yg)
+    assert max_abs(stats[..., 0], y.mean((2, 3))) < 1e-4
+    out = ops.norm_act_fwd(yg, stats, cu(gamma), cu(beta), cu(alpha), res=None if r is None else nhwc_from(r))
+    assert rel_err(to_nchw(out), out_ref) < BF16_TOL
+    dz, dy, dg, db, da = ops.norm_act_bwd(nhwc_from(dout), yg, stats, cu(gamma), cu(beta), cu(alpha),
+                                          res=None if r is None else nhwc_from(r), dout_b=nhwc_from(dout2))
+    assert rel_err(to_nchw(dy), yr.grad) < 2e-2          # two bf16 roundings (dz, dy) on a cancelling expression
+    if res:
+        assert rel_err(to_nchw(dz), rr.grad) < BF16_TOL
+    if affine:
+        assert rel_err(dg, gr.grad) < 1e-2 and rel_err(db, br.grad) < 1e-2
+    if act:
+        assert rel_err(da, ar.grad) < 1e-2
+
+
+def test_batch_norm_relu_mode(cuda):
+    """The same kernels with one statistic group over the whole batch = train-mode BatchNorm2d + ReLU (resnet.py:24-28)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(5)
+    n, c, h = 4, 64, 14
+    y = bf16_round(torch.randn(n, c, h, h, generator=g) * 1.5 - 0.3)
+    gamma, beta = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g)
+    yr, gr, br = (t.clone().requires_grad_(True) for t in (y, gamma, beta))
+    out_ref = F.relu(F.batch_norm(yr, None, None, gr, br, True, 0.1, 1e-5))
+    dout = bf16_round(torch.randn(out_ref.shape, generator=g))
+    out_ref.backward(dout)
+    yg = nhwc_from(y)
+    stats = ops.norm_stats(yg, groups_as_batch=True)
+    out = ops.norm_act_fwd(yg, stats, gamma.cuda(), beta.cuda(), relu=True, batch_norm=True)
+    assert rel_err(to_nchw(out), out_ref) < BF16_TOL
+    dz, dy, dg, db, _ = ops.norm_act_bwd(nhwc_from(dout), yg, stats, gamma.cuda(), beta.cuda(), relu=True, batch_norm=True)
+    assert rel_err(to_nchw(dy), yr.grad) < 2e-2
+    assert rel_err(dg, gr.grad) < 1e-2 and rel_err(db, br.grad) < 1e-2
+
+
+def test_pool_upsample_add(cuda):
+    ops = _ops()
+    g = torch.Generator().manual_seed(9)
+    n, c, h = 2, 128, 16
+    x = bf16_round(torch.randn(n, c, h, h, generator=g))
+    xr = x.clone().requires_grad_(True)
+    p_ref = F.max_pool2d(xr, 2, 2)
+    dp = bf16_round(torch.randn(p_ref.shape, generator=g))
+    p_ref.backward(dp)
+    xg = nhwc_from(x)
+    assert max_abs(to_nchw(ops.maxpool2_fwd(xg)), p_ref) == 0.0
+    assert max_abs(to_nchw(ops.maxpool2_bwd(xg, nhwc_from(dp))), xr.grad) == 0.0
+    low = bf16_round(torch.randn(n, c, h // 2, h // 2, generator=g))
+    lr_ = low.clone().requires_grad_(True)
+    u_ref = x + F.interpolate(lr_, scale_factor=2)
+    du = bf16_round(torch.randn(u_ref.shape, generator=g))
+    u_ref.backward(du)
+    assert rel_err(to_nchw(ops.upnearest2_add_fwd(xg, nhwc_from(low))), u_ref) < BF16_TOL
+    assert rel_err(to_nchw(ops.upnearest2_bwd(nhwc_from(du))), lr_.grad) < BF16_TOL
+    a3 = ops.add_n(xg, nhwc_from(du), nhwc_from(x))
+    assert rel_err(to_nchw(a3), x + du + x) < BF16_TOL
+
+
+def test_losses_against_golden_and_torch(cuda, golden_dir):
+    import os
+    ops = _ops()
+    gd = np.load(os.path.join(golden_dir, "losses.npz"))
+    a, t, lm, hm, lg, lb = (torch.from_numpy(gd[k]) for k in ("a", "t", "lm", "hm", "lg", "lb"))
+    ar, lmr, lgr = (v.clone().requires_grad_(True) for v in (a, lm, lg))
+    l1 = ((ar - t) ** 2).mean() * 97.0
+    l2 = ((lmr.sum(1) - hm) ** 2).mean() * 97.0
+    l3 = F.nll_loss(F.log_softmax(lgr, 1), lb.squeeze())
+    (0.7 * l1 + 0.3 * l2 + 1.3 * l3).backward()
+    loss, dx = ops.loss_mse97(a.cuda(), t.cuda(), 0.7)
+    assert abs(loss.item() - gd["values"][0]) < F32_TOL * abs(gd["values"][0])
+    assert rel_err(to_nchw(dx, 3), ar.grad) < BF16_TOL and float(dx[..., 3].float().abs().max()) == 0.0
+    n, _, h, w = lm.shape
+    buf = torch.zeros((n, h, w, 112), dtype=torch.bfloat16, device="cuda")
+    loss = ops.loss_landmark(lm.cuda(), hm.cuda(), 0.3, buf, 11)
+    assert abs(loss.item() - gd["values"][1]) < F32_TOL * abs(gd["values"][1])
+    loss = ops.loss_ce2d(lg.cuda(), lb.cuda(), 1.3, buf, 0)
+    assert abs(loss.item() - gd["values"][2]) < F32_TOL * abs(gd["values"][2])
+    assert rel_err(to_nchw(buf[..., 11:108]), lmr.grad) < BF16_TOL
+    assert rel_err(to_nchw(buf[..., :11]), lgr.grad) < BF16_TOL
+    assert float(buf[..., 108:].float().abs().max()) == 0.0
+
+
+def test_loss_modules_dropin(cuda):
+    """MSELossFunc / MSELoss_Landmark / CrossEntropyLoss2d keep the reference call signature and autograd behaviour."""
+    from crfr_b200.loss import CrossEntropyLoss2d, MSELoss_Landmark, MSELossFunc
+    from oracle import fsrnet_oracle as FO
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 3, 32, 32, generator=g); t = torch.randn(2, 3, 32, 32, generator=g)
+    lm = torch.randn(2, 97, 8, 8, generator=g); hm = torch.rand(2, 8, 8, generator=g)
+    lg = torch.randn(2, 11, 8, 8, generator=g); lb = torch.randint(0, 11, (2, 1, 8, 8), generator=g)
+    refs = []
+    for fn, (p, q) in ((FO.mse97, (x, t)), (FO.landmark_loss, (lm, hm)), (FO.ce2d, (lg, lb))):
+        pr = p.clone().requires_grad_(True)
+        v = fn(pr, q)
+        (2.0 * v).backward()
+        refs.append((v.item(), pr.grad))
+    for mod, (p, q), (v_ref, g_ref) in zip((MSELossFunc(), MSELoss_Landmark(), CrossEntropyLoss2d()),
+                                           ((x, t), (lm, hm), (lg, lb)), refs):
+        pc = p.cuda().requires_grad_(True)
+        v = mod(pc, q.cuda())
+        (2.0 * v).backward()
+        assert abs(v.item() - v_ref) < F32_TOL * abs(v_ref)
+        assert rel_err(pc.grad, g_ref) < BF16_TOL
+
+
+def test_kd_loss(cuda):
+    """distill_main.py:63,68-70: MSE(s, t) and MSE(t - s, a), fp32 embeddings and bf16 stage maps."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(21)
+    for dtype, shape in ((torch.float32, (16, 512)), (torch.bfloat16, (4, 14, 14, 256))):
+        t, s, a = (bf16_round(torch.randn(shape, generator=g)) for _ in range(3))
+        sr, ar = s.clone().requires_grad_(True), a.clone().requires_grad_(True)
+        ref = F.mse_loss(t - sr, ar)
+        ref.backward()
+        loss, (dt, ds, da) = ops.loss_kd(t.to(dtype).cuda(), s.to(dtype).cuda(), a.to(dtype).cuda())
+        assert abs(loss.item() - ref.item()) < F32_TOL * abs(ref.item())
+        tol = F32_TOL if dtype == torch.float32 else BF16_TOL
+        assert rel_err(ds.float(), sr.grad) < tol and rel_err(da.float(), ar.grad) < tol
+        # student term: MSE(s_emb, t_emb) == mean(((t) - 0) - s)^2 with s := NULL slot
+        loss2, _ = ops.loss_kd(t.to(dtype).cuda(), None, s.to(dtype).cuda(), want=(False, False, True))
+        assert abs(loss2.item() - F.mse_loss(s, t).item()) < F32_TOL * F.mse_loss(s, t).item()
+
+
+def test_rmsprop_matches_torch(cuda):
+    """torch.optim.RMSprop(lr, alpha=.99, eps=1e-8, weight_decay=1e-5) as at FSR_main.py:185."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(17)
+    p0 = torch.randn(10007, generator=g)
+    p_ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.RMSprop([p_ref], lr=1e-3, alpha=0.99, weight_decay=1e-5)
+    p = p0.clone().cuda()
+    p = torch.cat([p, torch.zeros(1, device="cuda")])[:10007]      # keep 16B alignment explicit
+    sq = torch.zeros_like(p)
+    for _ in range(3):
+        gr = torch.randn(10007, generator=g)
+        p_ref.grad = gr.clone()
+        opt.step()
+        ops.rmsprop_step(p, (gr * 2).cuda(), sq, 1e-3, 0.99, 1e-8, 1e-5, gscale=0.5)
+    assert rel_err(p, p_ref) < 1e-6
+
+
+def test_bicubic_bit_exact(cuda, golden_dir):
+    import os
+    ops = _ops()
+    gd = np.load(os.path.join(golden_dir, "bicubic.npz"))
+    from oracle import bicubic_oracle as BO
+    for key in gd.files:
+        if not key.startswith("src_"):
+            continue
+        _, s, o = key.split("_")
+        src, dst = gd[key], gd["dst_%s_%s" % (s, o)]
+        got, f32 = ops.bicubic_u8(torch.from_numpy(src).cuda(), int(o), int(o), want_f32=True)
+        assert np.array_equal(got.cpu().numpy(), dst), key
+        assert np.array_equal(f32.cpu().numpy(), BO.normalise_to_input(dst)), key
+    # BASELINE size: a batch of 128 faces 16 -> 128, checked against the numpy oracle
+    rng = np.random.default_rng(1)
+    src = rng.integers(0, 256, (128, 16, 16, 3), dtype=np.uint8)
+    got, _ = ops.bicubic_u8(torch.from_numpy(src).cuda(), 128, 128)
+    assert np.array_equal(got.cpu().numpy(), BO.bicubic_u8(src, 128, 128))
+
+
+def test_eval_dropins(cuda, golden_dir):
+    import os
+    from crfr_b200.utils import accuracy, calculate_accuracy, calculate_roc
+    from oracle import eval_oracle as EO
+    gd = np.load(os.path.join(golden_dir, "eval.npz"))
+    sc, tg = torch.from_numpy(gd["scores"]).cuda(), torch.from_numpy(gd["target"]).cuda()
+    r = accuracy(sc, tg, topk=(1, 5))
+    assert abs(r[0].item() - gd["top1"]) < 1e-5 and abs(r[1].item() - gd["top15"][1]) < 1e-5
+    ops = _ops()
+    _, idx = ops.topk_rows(sc, 5)
+    assert np.array_equal(idx.cpu().numpy(), gd["top5_idx"])
+    # ties -> lowest index, k > number of distinct maxima
+    t = torch.tensor([[1.0, 3.0, 3.0, 3.0, 0.0], [5.0, 5.0, 5.0, 5.0, 5.0]], device="cuda")
+    assert ops.topk_rows(t, 3)[1].tolist() == [[1, 2, 3], [0, 1, 2]]
+    dist = EO.pair_sqdist(gd["e1"], gd["e2"])
+    for thr, ref in zip(gd["thr"], gd["calc_acc"]):
+        assert np.allclose(calculate_accuracy(thr, dist, gd["same"]), ref)
+    d_gpu, same = ops.pair_verify(torch.from_numpy(gd["e1"]).cuda(), torch.from_numpy(gd["e2"]).cuda(), 30.0)
+    assert rel_err(d_gpu, torch.from_numpy(dist)) < 1e-5
+    assert np.array_equal(same.cpu().numpy(), dist < 30.0)          # margins >> fp32 summation-order noise
+    tpr, fpr, acc, best = calculate_roc(gd["thr"], gd["e1"], gd["e2"], gd["same"], nrof_folds=10, seed=0)
+    o = EO.calculate_roc(gd["thr"], gd["e1"], gd["e2"], gd["same"], nrof_folds=10, seed=0)
+    assert np.allclose(tpr, o[0]) and np.allclose(fpr, o[1]) and abs(acc - o[2]) < 1e-12 and np.array_equal(best, o[3])

@@ -1,0 +1,166 @@
+"""tcgen05 / TMEM / TMA engine parity: implicit-GEMM conv forward, dgrad, wgrad and the fused cosine top-k matcher
+against fp32 PyTorch / the numpy oracle on identical bf16-representable inputs."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.util import bf16_round, nhwc_from, rel_err, to_nchw
+
+pytestmark = pytest.mark.gpu
+
+BF16_TOL = 5e-3
+F32_TOL = 1e-4
+
+# (n, cin, cout, h): every 3x3 s1 p1 shape of FSRNet at 128x128 input (and the small maps of a 64x64 input)
+TC_SHAPES = [
+    (2, 64, 64, 128),     # coarse / decoder residual convs (FSRnet.py:79,85) - 87 % of the MACs
+    (3, 64, 64, 32),      # encoder residual convs
+    (2, 128, 128, 32),    # prior residual convs, hourglass level 2
+    (3, 128, 128, 16),    # hourglass level 1
+    (5, 128, 128, 8),     # hourglass level 0 (two images per tile, ragged last tile)
+    (9, 128, 128, 4),     # 64x64-input hourglass floor (eight images per tile)
+    (2, 192, 64, 32),     # decoder conv_input on cat(prior, encoder)
+    (1, 64, 64, 64),      # two rows per tile
+]
+
+
+def _mk(n, cin, cout, h, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = bf16_round(torch.randn(n, cin, h, h, generator=g))
+    w = bf16_round(torch.randn(cout, cin, 3, 3, generator=g) * 0.05)
+    b = torch.randn(cout, generator=g)
+    dy = bf16_round(torch.randn(n, cout, h, h, generator=g))
+    return x, w, b, dy
+
+
+@pytest.mark.parametrize("n,cin,cout,h", TC_SHAPES)
+def test_tc_conv_fwd(cuda, n, cin, cout, h):
+    from crfr_b200 import _lib as L, ops
+    assert ops.engine_supported(L.ENGINE_TCGEN05, 0, h, h, cin, cout, 3, 1, 1)
+    x, w, b, _ = _mk(n, cin, cout, h, 11)
+    ref = F.conv2d(x, w, b, 1, 1)
+    y, _, st = ops.conv_fwd(nhwc_from(x), ops.pack_conv_weight(w.cuda()), cin, cout, 3, 1, 1, bias=b.cuda(),
+                            engine=L.ENGINE_TCGEN05, want_stats=True)
+    torch.cuda.synchronize()
+    assert rel_err(to_nchw(y), ref) < BF16_TOL
+    yb = to_nchw(y)
+    assert rel_err(st[..., 0], yb.mean((2, 3))) < 1e-3
+    assert rel_err(st[..., 1], 1.0 / torch.sqrt(yb.var((2, 3), unbiased=False) + 1e-5)) < 1e-3
+    # the CUDA-core engine computes the same thing (cross-check used at full size below)
+    y2, _, _ = ops.conv_fwd(nhwc_from(x), ops.pack_conv_weight(w.cuda()), cin, cout, 3, 1, 1, bias=b.cuda(),
+                            engine=L.ENGINE_DIRECT)
+    assert rel_err(y.float(), y2.float()) < BF16_TOL
+
+
+@pytest.mark.parametrize("n,cin,cout,h", TC_SHAPES)
+def test_tc_conv_dgrad(cuda, n, cin, cout, h):
+    from crfr_b200 import _lib as L, ops
+    assert ops.engine_supported(L.ENGINE_TCGEN05, 1, h, h, cin, cout, 3, 1, 1)
+    x, w, _, dy = _mk(n, cin, cout, h, 12)
+    xr = x.clone().requires_grad_(True)
+    F.conv2d(xr, w, None, 1, 1).backward(dy)
+    dx = ops.conv_dgrad(nhwc_from(dy), ops.pack_conv_weight(w.cuda(), for_dgrad=True), (n, h, h, cin), cin, cout, 3, 1, 1,
+                        engine=L.ENGINE_TCGEN05)
+    torch.cuda.synchronize()
+    assert rel_err(to_nchw(dx), xr.grad) < BF16_TOL
+
+
+@pytest.mark.parametrize("n,cin,cout,h", TC_SHAPES)
+def test_tc_conv_wgrad(cuda, n, cin, cout, h):
+    from crfr_b200 import _lib as L, ops
+    assert ops.engine_supported(L.ENGINE_TCGEN05, 2, h, h, cin, cout, 3, 1, 1)
+    x, w, _, dy = _mk(n, cin, cout, h, 13)
+    wr = w.clone().requires_grad_(True)
+    F.conv2d(x, wr, None, 1, 1).backward(dy)
+    dw, _ = ops.conv_wgrad(nhwc_from(x), nhwc_from(dy), cin, cout, 3, 1, 1, engine=L.ENGINE_TCGEN05)
+    torch.cuda.synchronize()
+    assert rel_err(dw, wr.grad) < F32_TOL
+
+
+def test_tc_conv_views_and_accumulation(cuda):
+    """Channel-slice views (ld > c, the concat-free decoder input) and += semantics of the weight gradient."""
+    from crfr_b200 import _lib as L, ops
+    n, h = 2, 32
+    x, w, b, dy = _mk(n, 64, 64, h, 14)
+    wide = torch.randn(n, h, h, 192).to(torch.bfloat16).cuda()
+    wide[..., 128:192] = nhwc_from(x)
+    view = wide[..., 128:]           # pointer offset 128, ld 192 (ops read shape[3] as ld -> build desc by hand)
+    import ctypes as C
+    d = L.ConvDesc(n, h, h, 64, 64, 3, 1, 1, h, h, 192, 64, 0)
+    y = torch.empty((n, h, h, 64), dtype=torch.bfloat16, device="cuda")
+    wp = ops.pack_conv_weight(w.cuda())
+    ws = ops.workspace(L.lib().crfr_conv_workspace_bytes(C.byref(d)))
+    L.call("crfr_conv_fwd", L.ENGINE_TCGEN05, C.byref(d), view.data_ptr(), wp.data_ptr(), 64, None, y.data_ptr(), None,
+           None, 1e-5, ws.data_ptr(), ws.numel(), ops.stream())
+    assert rel_err(to_nchw(y), F.conv2d(x, w, None, 1, 1)) < BF16_TOL
+    wr = w.clone().requires_grad_(True)
+    F.conv2d(x, wr, None, 1, 1).backward(dy)
+    dw = torch.ones((64, 64, 3, 3), dtype=torch.float32, device="cuda")
+    dyg = nhwc_from(dy)
+    for _ in range(2):
+        L.call("crfr_conv_wgrad", L.ENGINE_TCGEN05, C.byref(d), view.data_ptr(), dyg.data_ptr(), dw.data_ptr(), None,
+               ws.data_ptr(), ws.numel(), ops.stream())
+    assert rel_err(dw, 1.0 + 2.0 * wr.grad) < F32_TOL
+
+
+def test_tc_conv_full_size_against_direct_engine(cuda):
+    """BASELINE size (batch 16 of the 64ch 128x128 layer): the two engines agree, and the conv is linear."""
+    from crfr_b200 import _lib as L, ops
+    g = torch.Generator().manual_seed(15)
+    n, c, h = 16, 64, 128
+    x = torch.randn(n, h, h, c, generator=g).to(torch.bfloat16).cuda()
+    w = bf16_round(torch.randn(c, c, 3, 3, generator=g) * 0.05).cuda()
+    wp = ops.pack_conv_weight(w)
+    y_tc, _, _ = ops.conv_fwd(x, wp, c, c, 3, 1, 1, engine=L.ENGINE_TCGEN05)
+    y_d, _, _ = ops.conv_fwd(x, wp, c, c, 3, 1, 1, engine=L.ENGINE_DIRECT)
+    assert rel_err(y_tc.float(), y_d.float()) < BF16_TOL
+    y2, _, _ = ops.conv_fwd((x.float() * 2).to(torch.bfloat16), wp, c, c, 3, 1, 1, engine=L.ENGINE_TCGEN05)
+    assert rel_err(y2.float(), 2 * y_tc.float()) < BF16_TOL
+    dy = torch.randn(n, h, h, c, generator=g).to(torch.bfloat16).cuda()
+    dw_tc, _ = ops.conv_wgrad(x, dy, c, c, 3, 1, 1, engine=L.ENGINE_TCGEN05)
+    dw_d, _ = ops.conv_wgrad(x, dy, c, c, 3, 1, 1, engine=L.ENGINE_DIRECT)
+    assert rel_err(dw_tc, dw_d) < F32_TOL
+    dx_tc = ops.conv_dgrad(dy, ops.pack_conv_weight(w, for_dgrad=True), (n, h, h, c), c, c, 3, 1, 1, engine=L.ENGINE_TCGEN05)
+    dx_d = ops.conv_dgrad(dy, ops.pack_conv_weight(w, for_dgrad=True), (n, h, h, c), c, c, 3, 1, 1, engine=L.ENGINE_DIRECT)
+    assert rel_err(dx_tc.float(), dx_d.float()) < BF16_TOL
+
+
+@pytest.mark.parametrize("p,g,dim,k", [(64, 1000, 128, 5), (200, 5000, 512, 5), (130, 777, 512, 8), (1, 3, 64, 5)])
+def test_matcher_small_against_oracle(cuda, p, g, dim, k):
+    """Bit-exact top-k indices vs the fp32 oracle on bf16-rounded unit vectors (planted identities, tie-free)."""
+    from crfr_b200 import ops
+    from oracle import eval_oracle as EO
+    gal, pr, ids = EO.synthetic_gallery(g, p, dim=dim, seed=p + g)
+    gb = ops.l2norm_bf16(torch.from_numpy(gal).cuda())
+    pb = ops.l2norm_bf16(torch.from_numpy(pr).cuda())
+    val, idx = ops.cosine_topk(pb, gb, k)
+    torch.cuda.synchronize()
+    oval, oidx = EO.cosine_topk(pb.float().cpu().numpy(), gb.float().cpu().numpy(), min(k, g))
+    kk = min(k, g)
+    assert np.array_equal(idx.cpu().numpy()[:, :kk], oidx)
+    assert np.allclose(val.cpu().numpy()[:, :kk], oval, rtol=1e-5, atol=1e-5)
+    if g > k:
+        assert np.array_equal(idx.cpu().numpy()[:, 0], ids)
+    else:
+        assert (idx.cpu().numpy()[:, kk:] == -1).all()
+
+
+def test_matcher_ties_and_sharding(cuda):
+    """Duplicate gallery rows tie exactly -> lowest index first; gallery-sharded top-k merges to the unsharded one."""
+    from crfr_b200 import ops
+    from oracle import eval_oracle as EO
+    gal, pr, ids = EO.synthetic_gallery(4096, 96, dim=256, seed=3)
+    gal[2000:2010] = gal[5]            # ten exact duplicates of entry 5
+    gb = ops.l2norm_bf16(torch.from_numpy(gal).cuda())
+    pb = ops.l2norm_bf16(torch.from_numpy(gal[[5]] * 1.0).cuda())
+    val, idx = ops.cosine_topk(pb, gb, 5)
+    assert idx[0].tolist() == [5, 2000, 2001, 2002, 2003]
+    pb = ops.l2norm_bf16(torch.from_numpy(pr).cuda())
+    full_v, full_i = ops.cosine_topk(pb, gb, 5)
+    parts_v, parts_i = [], []
+    for s in range(4):
+        v, i = ops.cosine_topk(pb, gb[s * 1024:(s + 1) * 1024], 5, index_base=s * 1024)
+        parts_v.append(v); parts_i.append(i)
+    mv, mi = ops.topk_merge(torch.stack(parts_v), torch.stack(parts_i), 5)
+    assert torch.equal(mi, full_i) and torch.equal(mv, full_v)
