@@ -1,0 +1,261 @@
+#!/usr/bin/env python
+"""Benchmark of the FSRNet train step (BASELINE.json metric: FSRNet train imgs/sec @16->128).
+
+  python bench.py [--gpus N --steps K --warmup W]            our arm: native sm_100a hot path
+  python bench.py --impl reference [...]                     the reference algorithm on the host CPU cores (oracle port)
+
+A "step" is one pass of the hot path over one synthetic batch of `--batch` faces per GPU (config 2 of BASELINE.json:
+bf16, batch 128, 16x16 -> 128x128 with parsing-map and landmark priors): bicubic 8x upsample of the uint8 LR faces,
+coarse SR net, encoder, hourglass prior estimator, decoder, pixel + prior losses, full backward, bucketed NCCL
+gradient all-reduce (N > 1) and the RMSprop update.  One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_IMG_TRAIN = 149.9e9      # 3 x 24.983 GMAC x 2
+METRIC = "fsrnet_train_images_per_sec"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops", 1590.0), d.get("bf16_tflops_sustained", 1400.0), d.get("hbm_gbs", 6650.0), "measured"
+    return 1590.0, 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.rows.append(f)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def cpu_reference_step_rate(steps, warmup, batch=4, size=128):
+    """The reference algorithm (oracle port, fp32) on the host cores: forward + backward + RMSprop, config 1."""
+    import torch
+    from oracle import fsrnet_oracle as FO
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = FO.build_fsrnet_state_dict(1234)
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    live = [v for k, v in leaves.items() if not FO.fsrnet_dead_param(k)]
+    opt = torch.optim.RMSprop(live, lr=1e-3, alpha=0.99, weight_decay=1e-5)
+    x, hr, lbl, hm = FO.synthetic_batch(batch, size)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        outs = FO.fsrnet_forward(leaves, x)
+        total, _ = FO.fsrnet_loss(outs, hr, hm, lbl)
+        opt.zero_grad()
+        total.backward()
+        opt.step()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return batch * len(times) / sum(times), cores, sum(times) / len(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    value, cores, sec = cpu_reference_step_rate(max(1, args.steps), max(1, min(args.warmup, 2)))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "FSRNet train step 16->128 (128x128 input), reference algorithm on host CPU",
+                       "sample": "batch 4 per step (config 1 of BASELINE.json)"},
+            "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port",
+                             "sample": "oracle port of model/FSRnet.py + loss/loss.py, batch 4 x 128x128, fp32"},
+            "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def time_dominant_kernel(torch, ops, L, chunk):
+    """CUDA-event timing of the dominant kernel: the 3x3 64->64 implicit GEMM at 128x128 (87 % of the MACs)."""
+    g = torch.Generator(device="cuda").manual_seed(3)
+    c, h = 64, 128
+    xs = [torch.randn(chunk, h, h, c, generator=g, device="cuda").to(torch.bfloat16) for _ in range(4)]  # > L2 in total
+    w = ops.pack_conv_weight(torch.randn(c, c, 3, 3, generator=g, device="cuda") * 0.05)
+    for x in xs:
+        ops.conv_fwd(x, w, c, c, 3, 1, 1, engine=L.ENGINE_TCGEN05)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    import ctypes as C
+    d = ops.conv_desc(xs[0], c, c, 3, 1, 1)
+    y = torch.empty((chunk, h, h, c), dtype=torch.bfloat16, device="cuda")
+    ws = ops.workspace(L.lib().crfr_conv_workspace_bytes(C.byref(d)))
+    reps = 12
+    ev0.record()
+    for i in range(reps):
+        L.call("crfr_conv_fwd", L.ENGINE_TCGEN05, C.byref(d), xs[i % 4].data_ptr(), w.data_ptr(), c, None, y.data_ptr(),
+               None, None, 1e-5, ws.data_ptr(), ws.numel(), ops.stream())
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / reps
+    flops = 2.0 * chunk * h * h * c * c * 9
+    return flops / (ms * 1e-3) / 1e12, ms, flops
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import crfr_b200
+    crfr_b200.build()
+    from crfr_b200 import _lib as L, ops
+    from crfr_b200.model.FSRnet import OverallNetwork, weights_init
+    from crfr_b200.trainer import FSRNetTrainer
+
+    B, S, LR = args.batch, 128, 16
+    torch.manual_seed(1234)
+    net = OverallNetwork()
+    net.apply(weights_init)
+    net = net.to(dev).train()
+    trainer = FSRNetTrainer(net, lr=1e-3, chunk=args.chunk)
+
+    # synthetic data, a few distinct batches in pinned host memory
+    g = torch.Generator().manual_seed(4321 + rank)
+    nb = 2
+    host = []
+    for _ in range(nb):
+        host.append((torch.randint(0, 256, (B, LR, LR, 3), generator=g, dtype=torch.uint8).pin_memory(),
+                     torch.randn(B, 3, S, S, generator=g).pin_memory(),
+                     torch.rand(B, S // 4, S // 4, generator=g).pin_memory(),
+                     torch.randint(0, 11, (B, 1, S // 4, S // 4), generator=g).pin_memory()))
+    resident = [tuple(t.to(dev) for t in hb) for hb in host]
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
+
+    def step_resident(i):
+        lr_u8, hr, hm, lbl = resident[i % nb]
+        _, x = ops.bicubic_u8(lr_u8, S, S, want_f32=True)
+        return trainer.step(x, hr, hm, lbl)
+
+    def step_e2e(i):
+        hb = host[i % nb]
+        lr_u8, hr, hm, lbl = (t.to(dev, non_blocking=True) for t in hb)
+        _, x = ops.bicubic_u8(lr_u8, S, S, want_f32=True)
+        return float(trainer.step(x, hr, hm, lbl)[0].item())        # device -> host read of the loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        sampler = ClockSampler(local) if rank == 0 else None
+        if sampler:
+            sampler.start()
+        launches0 = L.lib().crfr_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        last = None
+        for i in range(steps):
+            last = fn(warmup + i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = L.lib().crfr_launch_count() - launches0
+        if sampler:
+            sampler.stop_flag = True
+            sampler.join(timeout=3)
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item(), launches, (sampler.summary() if sampler else None), last
+
+    ms, launches, clocks, last = timed(step_resident, args.steps, args.warmup)
+    loss_val = float(last[0].item())
+    ms_e2e, _, _, _ = timed(step_e2e, max(2, args.steps // 2), 1)
+    value = world * B * args.steps / (ms * 1e-3)
+    e2e = world * B * max(2, args.steps // 2) / (ms_e2e * 1e-3)
+
+    if rank == 0:
+        burst, sustained, hbm, how = measured_peaks()
+        k_tflops, k_ms, k_flops = time_dominant_kernel(torch, ops, L, args.chunk)
+        line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": "FSRNet train step bf16, batch %d per GPU, 16x16 -> 128x128, parsing + landmark "
+                                       "priors (BASELINE.json configs[1])" % B, "global_batch": B * world,
+                           "chunk": args.chunk, "parallelism": "dp%d" % world,
+                           "l2": "inputs + saved activations per chunk (GBs) exceed the 126 MB L2; no explicit flush"},
+                "clocks": clocks, "loss": loss_val,
+                "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+                "gpu_launches": int(launches),
+                "step_tensor_frac": {"achieved_tflops": value / world * FLOP_PER_IMG_TRAIN / 1e12,
+                                     "peak_tflops_sustained": sustained,
+                                     "frac": value / world * FLOP_PER_IMG_TRAIN / 1e12 / sustained, "peak": how},
+                "roofline": {"bound": "tensor", "kernel": "tc_conv_kernel<64> (3x3 64->64 @128x128, %d images)" % args.chunk,
+                             "achieved": k_tflops, "peak": burst, "unit": "TFLOP/s", "frac": k_tflops / burst,
+                             "traffic": None, "ms_per_launch": k_ms, "flops_per_launch": k_flops, "peak_source": how}}
+        if not args.no_cpu_baseline:
+            v, cores, sec = cpu_reference_step_rate(3, 1)
+            line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
+                                    "sample": "oracle port, 3 timed steps of batch 4 x 128x128 fp32 (%.2f s/step)" % sec}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=128)
+    ap.add_argument("--chunk", type=int, default=16)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -21,7 +21,7 @@ class ConvDesc(C.Structure):
 
 class FsrnetIO(C.Structure):
     _fields_ = [("batch", ci), ("size", ci), ("x", vp), ("coarse", vp), ("out", vp), ("landmark", vp), ("parsing", vp),
-                ("hr", vp), ("heatmap", vp), ("labels", vp), ("loss_div", cf), ("w_pix", cf)]
+                ("hr", vp), ("heatmap", vp), ("labels", vp), ("loss_div", cf), ("w_pix", cf), ("bucket_events", vp * 3)]
 
 
 # name -> (restype, argtypes); every symbol declared in include/crfr.h

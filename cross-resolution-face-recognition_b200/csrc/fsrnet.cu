@@ -81,6 +81,7 @@ struct Net {
   size_t scratch_bytes = 0;
   // fixed buffers
   Tensor x4, coarse4, cat;
+  int tape_enc_start = 0, tape_dec_start = 0;   // first tape index of the encoder / decoder sections
   // output gradients (bf16): NHWC4 images and the combined 112-wide heads buffer
   bf16* d_coarse4 = nullptr;
   bf16* d_out4 = nullptr;
@@ -306,6 +307,7 @@ struct Net {
     Tensor pe_view = view(cat, 0, 128), enc_view = view(cat, 128, 64);
 
     // ---- fine SR encoder (:359-379) ----
+    tape_enc_start = (int)tape.size();
     float* se;
     Tensor ye = conv(coarse4, E_CONV_IN_W, E_CONV_IN_B, 64, 7, 4, 3, false, &se);
     Tensor ae = norm_act(ye, se, E_BN_MID_W, E_BN_MID_B, E_RELU, nullptr);
@@ -323,6 +325,7 @@ struct Net {
     heads(pe);
 
     // ---- fine SR decoder (:448-459) on cat(prior, encoder) (:505) ----
+    tape_dec_start = (int)tape.size();
     Op cop;
     cop.kind = OP_CAT; cop.a = pe_view; cop.b = enc_view; cop.out = cat;
     tape.push_back(cop);
@@ -356,8 +359,15 @@ struct Net {
   }
   bool has_grad(const Tensor& t) const { return t.id >= 0 && !slots[t.id].empty(); }
 
+  void record_bucket(int k) {
+    if (run() && io->bucket_events[k])
+      check(cudaEventRecord((cudaEvent_t)io->bucket_events[k], st) == cudaSuccess ? CRFR_OK : CRFR_ECUDA);
+  }
+
   void backward() {
     for (int i = (int)tape.size() - 1; i >= 0 && ok(); --i) {
+      if (i == tape_dec_start - 1) record_bucket(0);   // every decoder op has run: its gradients are final
+      if (i == tape_enc_start - 1) record_bucket(1);   // prior + encoder done
       Op& op = tape[i];
       switch (op.kind) {
         case OP_NORM: {
@@ -479,6 +489,7 @@ struct Net {
         }
       }
     }
+    record_bucket(2);
   }
 };
 

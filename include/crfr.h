@@ -174,6 +174,10 @@ typedef struct crfr_fsrnet_io {
   const long long* labels;  /* [B,1,H/4,W/4] int64 */
   float loss_div;           /* the 2*train_batch of FSR_main.py:234 (global batch under data parallelism) */
   float w_pix;              /* 5.0 at FSR_main.py:233 (7.0 at :319) */
+  /* optional cudaEvent_t handles recorded on `stream` during backward when a gradient bucket is complete:
+   * [0] decoder (params 167..201), [1] prior + encoder (33..166), [2] coarse (0..32).  The data-parallel host
+   * loop starts each bucket's all-reduce on a side stream behind its event (overlap with the rest of backward). */
+  void* bucket_events[3];
 } crfr_fsrnet_io;
 
 /* ref: OverallNetwork.forward model/FSRnet.py:497-508 with the runnable wiring of :538-541.

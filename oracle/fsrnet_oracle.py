@@ -246,6 +246,59 @@ def build_fsrnet_state_dict(seed=1234, xavier=True):
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# storage-precision model
+# ----------------------------------------------------------------------------------------------------------------
+class _RoundFwd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.bfloat16).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+class _RoundBwd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(torch.float32)
+
+
+class Precision:
+    """Where the arithmetic is allowed to round.
+
+    ``Precision("fp32")`` is the reference's arithmetic (every hook is the identity).  ``Precision("bf16")`` states
+    the storage contract of the CUDA path (DESIGN.md "bf16 contract"): all accumulation, statistics, losses and
+    parameters stay fp32, but every tensor that is STORED between two kernels is a bf16 tensor -
+      q  : value rounded to bf16 when stored (network input, conv weights, conv outputs, activation outputs);
+      qg : gradient rounded to bf16 when stored (gradient w.r.t. a conv input / conv output / pre-activation /
+           upsampled branch / a tensor whose consumers' gradients are summed by an add kernel / loss gradients).
+    With the hooks at exactly the storage points of the CUDA program, this oracle predicts its results up to
+    fp32 summation order, which is what the 1e-2 bf16 tolerance of the parity tests is measured against.
+    """
+
+    def __init__(self, mode="fp32"):
+        assert mode in ("fp32", "bf16")
+        self.on = mode == "bf16"
+
+    def q(self, x):
+        return _RoundFwd.apply(x) if self.on else x
+
+    def qg(self, x):
+        return _RoundBwd.apply(x) if self.on else x
+
+    def qb(self, x):
+        return self.q(self.qg(x)) if self.on else x
+
+
+FP32 = Precision("fp32")
+
+
+# ----------------------------------------------------------------------------------------------------------------
 # forward restatement
 # ----------------------------------------------------------------------------------------------------------------
 def _inorm(x, w=None, b=None):
@@ -263,84 +316,102 @@ def _prelu(x, a):
     return torch.clamp(x, min=0) + a * torch.clamp(x, max=0)
 
 
-def _res_block(sd, p, x):
-    y = F.conv2d(x, sd[p + "conv1.weight"], None, 1, 1)
-    y = _prelu(_inorm(y, sd[p + "in1.weight"], sd[p + "in1.bias"]), sd[p + "relu.weight"])
-    y = F.conv2d(y, sd[p + "conv2.weight"], None, 1, 1)
-    y = _inorm(y, sd[p + "in2.weight"], sd[p + "in2.bias"]) + x
-    return _prelu(y, sd[p + "relu_out.weight"])
+def _conv(pr, x, w, b=None, stride=1, pad=0, store=True):
+    """Conv2d on a stored activation: bf16 weights, gradient w.r.t. the input stored, output stored (unless fp32)."""
+    y = F.conv2d(pr.qg(x), pr.q(w), b, stride, pad)
+    return pr.qb(y) if store else y
 
 
-def _res_stack(sd, p, x, times):
+def _norm_act(pr, y, w=None, b=None, alpha=None, res=None):
+    z = _inorm(y, w, b)
+    if res is not None:
+        z = z + res
+    z = pr.qg(z)                       # gradient w.r.t. the pre-activation (== gradient of the residual input)
+    return pr.q(_prelu(z, alpha) if alpha is not None else z)
+
+
+def _res_block(pr, sd, p, x):
+    y = _conv(pr, x, sd[p + "conv1.weight"], None, 1, 1)
+    y = _norm_act(pr, y, sd[p + "in1.weight"], sd[p + "in1.bias"], sd[p + "relu.weight"])
+    y = _conv(pr, y, sd[p + "conv2.weight"], None, 1, 1)
+    return _norm_act(pr, y, sd[p + "in2.weight"], sd[p + "in2.bias"], sd[p + "relu_out.weight"], res=x)
+
+
+def _res_stack(pr, sd, p, x, times):
     for _ in range(times):
         for b in range(3):
-            x = _res_block(sd, p + "residual.%d." % b, x)
+            x = _res_block(pr, sd, p + "residual.%d." % b, x)
     return x
 
 
-def _hg_block(sd, p, x):
-    y = F.conv2d(x, sd[p + "conv1.weight"], None, 1, 1)
-    y = _prelu(_inorm(y), sd[p + "relu.weight"])
-    y = F.conv2d(y, sd[p + "conv2.weight"], None, 1, 1)
-    return _prelu(_inorm(y) + x, sd[p + "relu.weight"])
+def _hg_block(pr, sd, p, x):
+    y = _conv(pr, x, sd[p + "conv1.weight"], None, 1, 1)
+    y = _norm_act(pr, y, alpha=sd[p + "relu.weight"])
+    y = _conv(pr, y, sd[p + "conv2.weight"], None, 1, 1)
+    return _norm_act(pr, y, alpha=sd[p + "relu.weight"], res=x)
 
 
-def _hg_seq(sd, p, d, s, x):
+def _hg_seq(pr, sd, p, d, s, x):
     for b in range(2):
-        x = _hg_block(sd, p + "hg.hg.%d.%d.%d." % (d, s, b), x)
+        x = _hg_block(pr, sd, p + "hg.hg.%d.%d.%d." % (d, s, b), x)
     return x
 
 
-def _hourglass(sd, p, n, x):
-    up1 = _hg_seq(sd, p, n - 1, 0, x)
-    low1 = _hg_seq(sd, p, n - 1, 1, F.max_pool2d(x, 2, 2))
-    low2 = _hourglass(sd, p, n - 1, low1) if n > 1 else _hg_seq(sd, p, 0, 3, low1)
-    low3 = _hg_seq(sd, p, n - 1, 2, low2)
-    return up1 + F.interpolate(low3, scale_factor=2)      # default mode: nearest
+def _hourglass(pr, sd, p, n, x):
+    x = pr.qg(x)                       # three consumers (block conv, its skip, the pool): their gradients are summed + stored
+    up1 = _hg_seq(pr, sd, p, n - 1, 0, x)
+    low1 = _hg_seq(pr, sd, p, n - 1, 1, F.max_pool2d(x, 2, 2))
+    low2 = _hourglass(pr, sd, p, n - 1, low1) if n > 1 else _hg_seq(pr, sd, p, 0, 3, low1)
+    low3 = _hg_seq(pr, sd, p, n - 1, 2, low2)
+    out = up1 + F.interpolate(pr.qg(low3), scale_factor=2)      # default mode: nearest
+    return pr.qb(out)
 
 
-def coarse_forward(sd, x, p="_coarse_sr_network."):
-    y = F.conv2d(x, sd[p + "conv_input.weight"], sd[p + "conv_input.bias"], 1, 1)
-    y = _prelu(_inorm(y, sd[p + "bn_mid.weight"], sd[p + "bn_mid.bias"]), sd[p + "relu.weight"])
-    y = _res_stack(sd, p, y, 3)
-    feat = _inorm(y, sd[p + "bn_mid.weight"], sd[p + "bn_mid.bias"])
-    return feat, F.conv2d(feat, sd[p + "conv_mid.weight"], sd[p + "conv_mid.bias"], 1, 1)
+def coarse_forward(sd, x, p="_coarse_sr_network.", pr=FP32):
+    y = _conv(pr, pr.q(x), sd[p + "conv_input.weight"], sd[p + "conv_input.bias"], 1, 1)
+    y = _norm_act(pr, y, sd[p + "bn_mid.weight"], sd[p + "bn_mid.bias"], sd[p + "relu.weight"])
+    y = _res_stack(pr, sd, p, y, 3)
+    feat = _norm_act(pr, y, sd[p + "bn_mid.weight"], sd[p + "bn_mid.bias"])
+    coarse = _conv(pr, feat, sd[p + "conv_mid.weight"], sd[p + "conv_mid.bias"], 1, 1, store=False)   # fp32 output
+    return feat, pr.qg(coarse)         # loss + two stems: summed gradient is stored
 
 
-def encoder_forward(sd, x, p="_fine_sr_encoder."):
-    y = F.conv2d(x, sd[p + "conv_input.weight"], sd[p + "conv_input.bias"], 4, 3)
-    y = _prelu(_inorm(y, sd[p + "bn_mid.weight"], sd[p + "bn_mid.bias"]), sd[p + "relu.weight"])
-    y = _res_stack(sd, p, y, 3)
-    y = F.conv2d(y, sd[p + "conv_end.weight"], sd[p + "conv_end.bias"], 1, 1)
-    return _prelu(_inorm(y, sd[p + "bn_mid.weight"], sd[p + "bn_mid.bias"]), sd[p + "relu.weight"])
+def encoder_forward(sd, x, p="_fine_sr_encoder.", pr=FP32):
+    y = _conv(pr, pr.q(x), sd[p + "conv_input.weight"], sd[p + "conv_input.bias"], 4, 3)
+    y = _norm_act(pr, y, sd[p + "bn_mid.weight"], sd[p + "bn_mid.bias"], sd[p + "relu.weight"])
+    y = _res_stack(pr, sd, p, y, 3)
+    y = _conv(pr, y, sd[p + "conv_end.weight"], sd[p + "conv_end.bias"], 1, 1)
+    return _norm_act(pr, y, sd[p + "bn_mid.weight"], sd[p + "bn_mid.bias"], sd[p + "relu.weight"])
 
 
-def prior_forward(sd, x, p="_prior_estimation_network."):
-    y = F.conv2d(x, sd[p + "conv.weight"], sd[p + "conv.bias"], 4, 3)
-    y = _prelu(_inorm(y, sd[p + "bn.weight"], sd[p + "bn.bias"]), sd[p + "relu.weight"])
-    y = _res_stack(sd, p, y, 1)
-    y = _hourglass(sd, p, 2, y)
-    parsing = F.conv2d(y, sd[p + "fc.weight"], sd[p + "fc.bias"])
-    landmark = F.conv2d(y, sd[p + "fc_landmark.weight"], sd[p + "fc_landmark.bias"])
-    return y, landmark, parsing
+def prior_forward(sd, x, p="_prior_estimation_network.", pr=FP32):
+    y = _conv(pr, pr.q(x), sd[p + "conv.weight"], sd[p + "conv.bias"], 4, 3)
+    y = _norm_act(pr, y, sd[p + "bn.weight"], sd[p + "bn.bias"], sd[p + "relu.weight"])
+    y = _res_stack(pr, sd, p, y, 1)
+    y = _hourglass(pr, sd, p, 2, y)
+    # the two 1x1 heads (:391-392) evaluated as one 108-channel conv: same arithmetic, one stored input gradient
+    w = torch.cat((sd[p + "fc.weight"], sd[p + "fc_landmark.weight"]), 0)
+    b = torch.cat((sd[p + "fc.bias"], sd[p + "fc_landmark.bias"]), 0)
+    heads = _conv(pr, y, w, b, store=False)
+    return y, heads[:, 11:], heads[:, :11]
 
 
-def decoder_forward(sd, x, p="_fine_sr_decoder."):
-    y = F.conv2d(x, sd[p + "conv_input.weight"], sd[p + "conv_input.bias"], 1, 1)
-    y = _prelu(_inorm(y, sd[p + "bn_mid.weight"], sd[p + "bn_mid.bias"]), sd[p + "relu.weight"])
-    y = F.conv_transpose2d(y, sd[p + "deconv.weight"], sd[p + "deconv.bias"], 4, 2, 1)
-    y = _prelu(_inorm(y, sd[p + "bn_mid.weight"], sd[p + "bn_mid.bias"]), sd[p + "relu.weight"])
-    y = _res_stack(sd, p, y, 3)
-    y = _inorm(y, sd[p + "bn_mid.weight"], sd[p + "bn_mid.bias"])
-    return F.conv2d(y, sd[p + "conv_out.weight"], sd[p + "conv_out.bias"], 1, 1)
+def decoder_forward(sd, x, p="_fine_sr_decoder.", pr=FP32):
+    y = _conv(pr, x, sd[p + "conv_input.weight"], sd[p + "conv_input.bias"], 1, 1)
+    y = _norm_act(pr, y, sd[p + "bn_mid.weight"], sd[p + "bn_mid.bias"], sd[p + "relu.weight"])
+    y = pr.qb(F.conv_transpose2d(pr.qg(y), pr.q(sd[p + "deconv.weight"]), sd[p + "deconv.bias"], 4, 2, 1))
+    y = _norm_act(pr, y, sd[p + "bn_mid.weight"], sd[p + "bn_mid.bias"], sd[p + "relu.weight"])
+    y = _res_stack(pr, sd, p, y, 3)
+    y = _norm_act(pr, y, sd[p + "bn_mid.weight"], sd[p + "bn_mid.bias"])
+    return _conv(pr, y, sd[p + "conv_out.weight"], sd[p + "conv_out.bias"], 1, 1, store=False)
 
 
-def fsrnet_forward(sd, x):
+def fsrnet_forward(sd, x, pr=FP32):
     """OverallNetwork.forward with encoder / prior net fed by the 3-channel coarse image."""
-    _, coarse = coarse_forward(sd, x)
-    enc = encoder_forward(sd, coarse)
-    pe, landmark, parsing = prior_forward(sd, coarse)
-    out = decoder_forward(sd, torch.cat((pe, enc), 1))
+    _, coarse = coarse_forward(sd, x, pr=pr)
+    enc = encoder_forward(sd, coarse, pr=pr)
+    pe, landmark, parsing = prior_forward(sd, coarse, pr=pr)
+    out = decoder_forward(sd, torch.cat((pe, enc), 1), pr=pr)
     return coarse, out, landmark, parsing
 
 
@@ -360,10 +431,11 @@ def ce2d(logits, target):
     return F.nll_loss(F.log_softmax(logits, 1), torch.squeeze(target))
 
 
-def fsrnet_loss(outputs, hr, heatmap, labels, train_batch=None, w_pix=5.0):
+def fsrnet_loss(outputs, hr, heatmap, labels, train_batch=None, w_pix=5.0, pr=FP32):
     coarse, out, landmark, parsing = outputs
     b = hr.shape[0] if train_batch is None else train_batch
-    parts = (mse97(out, hr), mse97(coarse, hr), landmark_loss(landmark, heatmap), ce2d(parsing, labels))
+    parts = (mse97(pr.qg(out), hr), mse97(pr.qg(coarse), hr), landmark_loss(pr.qg(landmark), heatmap),
+             ce2d(pr.qg(parsing), labels))
     total = (w_pix * parts[0] + w_pix * parts[1] + parts[2] + parts[3]) / (2.0 * b)
     return total, parts
 
@@ -378,11 +450,12 @@ def synthetic_batch(batch, size=128, seed=4321):
     return x, hr, lbl, hm
 
 
-def fsrnet_loss_and_grads(sd, x, hr, hm, lbl, train_batch=None):
+def fsrnet_loss_and_grads(sd, x, hr, hm, lbl, train_batch=None, precision="fp32"):
     """One forward+backward; returns (outputs, total, parts, {name: grad}) - used as the parity oracle."""
+    pr = Precision(precision)
     leaves = OrderedDict((k, v.detach().clone().requires_grad_(True)) for k, v in sd.items())
-    outs = fsrnet_forward(leaves, x)
-    total, parts = fsrnet_loss(outs, hr, hm, lbl, train_batch)
+    outs = fsrnet_forward(leaves, x, pr)
+    total, parts = fsrnet_loss(outs, hr, hm, lbl, train_batch, pr=pr)
     names = [k for k in leaves if not fsrnet_dead_param(k)]
     grads = torch.autograd.grad(total, [leaves[k] for k in names], allow_unused=True)
     gd = OrderedDict((k, None) for k in leaves)

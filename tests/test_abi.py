@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol(lib):
 def test_struct_layouts_match_header():
     from crfr_b200 import _lib
     assert C.sizeof(_lib.ConvDesc) == 13 * 4
-    assert C.sizeof(_lib.FsrnetIO) == 8 + 8 * 8 + 8      # 2 ints, 8 pointers, 2 floats
+    assert C.sizeof(_lib.FsrnetIO) == 8 + 8 * 8 + 8 + 3 * 8      # 2 ints, 8 pointers, 2 floats, 3 event handles
     assert _lib.FSRNET_NPARAMS == 202
 
 
