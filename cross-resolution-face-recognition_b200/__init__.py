@@ -8,5 +8,6 @@ from ._lib import ENGINE_AUTO, ENGINE_DIRECT, ENGINE_TCGEN05, lib  # noqa: F401
 
 
 def build(force=False):
-    from .build import build as _b
+    """Compiles csrc/*.cu for sm_100a and links libcrfr.so next to this package (no-op when up to date)."""
+    from .buildlib import build as _b
     return _b(force=force)
