@@ -40,15 +40,21 @@ static int check_desc(const crfr_conv_desc* d, const char* who) {
 
 extern "C" size_t crfr_conv_workspace_bytes(const crfr_conv_desc* d) {
   if (!d) return 0;
-  size_t norm = crfr_norm_ws_bytes(d->n, d->oh * d->ow, d->cout);
+  size_t norm = d->cout >= 8 ? crfr_norm_ws_bytes(d->n, d->oh * d->ow, d->cout) : 0;
   size_t tc = crfr_tc_workspace_bytes(d);
-  return (norm > tc ? norm : tc) + 1024;
+  size_t low = crfr_lowered_ws_bytes(d);
+  size_t m = norm > tc ? norm : tc;
+  return (m > low ? m : low) + 1024;
 }
 
 extern "C" int crfr_conv_engine_supported(int engine, int op, int h, int w, int cin, int cout, int k, int stride,
                                           int pad) {
   if (engine == CRFR_ENGINE_DIRECT) return 1;
-  return crfr_tc_supported(op, h, w, cin, cout, k, stride, pad);
+  if (crfr_tc_supported(op, h, w, cin, cout, k, stride, pad)) return 1;
+  crfr_conv_desc d = {1, h, w, cin, cout, k, stride, pad, (h + 2 * pad - k) / stride + 1, (w + 2 * pad - k) / stride + 1,
+                      cin < 8 ? 4 : cin, cout < 8 ? 4 : cout, 0};
+  const int r = crfr_lowered_recipe(&d);
+  return r != 0 && !(r == 1 && op == 1);
 }
 
 extern "C" int crfr_conv_fwd(int engine, const crfr_conv_desc* d, const void* x, const void* w_packed, int cin_pad,
@@ -60,6 +66,14 @@ extern "C" int crfr_conv_fwd(int engine, const crfr_conv_desc* d, const void* x,
                  d->cin, d->in_ld);
   CRFR_CHECK_ARG(!stats || y, "conv_fwd: statistics need the bf16 output");
   cudaStream_t st = (cudaStream_t)stream;
+  if (engine != CRFR_ENGINE_DIRECT) {
+    const int r = crfr_lowered_recipe(d);
+    if (r == 2 || (r != 0 && y && !y_nchw)) {
+      CRFR_TRY(crfr_lowered_fwd(d, x, w_packed, cin_pad, bias, y, y_nchw, ws, ws_bytes, st));
+      if (stats) CRFR_TRY(crfr_norm_stats(y, d->n, d->oh * d->ow, d->cout, d->out_ld, eps, stats, ws, ws_bytes, stream));
+      return CRFR_OK;
+    }
+  }
   bool tc = false;
   if (engine != CRFR_ENGINE_DIRECT && !d->transposed && y && !y_nchw && cin_pad == d->cin &&
       crfr_tc_supported(0, d->h, d->w, d->cin, d->cout, d->k, d->stride, d->pad)) {
@@ -87,6 +101,10 @@ extern "C" int crfr_conv_dgrad(int engine, const crfr_conv_desc* d, const void* 
   CRFR_CHECK_ARG(cout_pad >= d->cout && d->out_ld >= cout_pad, "conv_dgrad: cout_pad %d vs cout %d / out_ld %d",
                  cout_pad, d->cout, d->out_ld);
   cudaStream_t st = (cudaStream_t)stream;
+  if (engine != CRFR_ENGINE_DIRECT) {
+    const int r = crfr_lowered_recipe(d);
+    if (r >= 2) return crfr_lowered_dgrad(d, dy, w_packed_t, cout_pad, dx, ws, ws_bytes, st);
+  }
   bool tc = engine != CRFR_ENGINE_DIRECT && !d->transposed && cout_pad == d->cout &&
             crfr_tc_supported(1, d->h, d->w, d->cin, d->cout, d->k, d->stride, d->pad);
   if (engine == CRFR_ENGINE_TCGEN05 && !tc) {
@@ -106,7 +124,9 @@ extern "C" int crfr_conv_wgrad(int engine, const crfr_conv_desc* d, const void* 
   CRFR_TRY(check_desc(d, "conv_wgrad"));
   CRFR_CHECK_ARG(x && dy && (dw || dbias), "conv_wgrad: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  if (dw) {
+  if (dw && engine != CRFR_ENGINE_DIRECT && crfr_lowered_recipe(d) != 0) {
+    CRFR_TRY(crfr_lowered_wgrad(d, x, dy, dw, ws, ws_bytes, st));
+  } else if (dw) {
     bool tc = engine != CRFR_ENGINE_DIRECT && !d->transposed &&
               crfr_tc_supported(2, d->h, d->w, d->cin, d->cout, d->k, d->stride, d->pad);
     if (engine == CRFR_ENGINE_TCGEN05 && !tc) {

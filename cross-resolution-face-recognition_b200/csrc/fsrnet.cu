@@ -256,8 +256,8 @@ struct Net {
     void* wp = pack(w_idx, 3, x.c, 3, x.c, false, false);
     if (run()) {
       if (y4) check(cudaMemsetAsync(y4->p, 0, (size_t)x.n * x.h * x.w * 4 * sizeof(bf16), st) == cudaSuccess ? CRFR_OK : CRFR_ECUDA);
-      check(crfr_conv_fwd(CRFR_ENGINE_DIRECT, &d, x.p, wp, x.c, params[b_idx], y4 ? y4->p : nullptr, y_nchw, nullptr,
-                          kEps, scratch, scratch_bytes, st));
+      check(crfr_conv_fwd(engine, &d, x.p, wp, x.c, params[b_idx], y4 ? y4->p : nullptr, y_nchw, nullptr, kEps, scratch,
+                          scratch_bytes, st));
     }
     op.a = x; op.w_idx = w_idx; op.b_idx = b_idx;
     if (y4) op.out = *y4;
@@ -287,6 +287,17 @@ struct Net {
     for (int i = 0; i < CRFR_FSRNET_NPARAMS; ++i) packed_fwd[i] = packed_bwd[i] = nullptr;
     // shared scratch: norm partials / wgrad accumulators of the largest layer
     scratch_bytes = crfr_norm_ws_bytes(B, S * S, 128) + sizeof(float) * 9 * 192 * 128 + 4096;
+    {  // the lowered edge layers (lowered_conv.cu) stage their im2col / partial-product buffers here
+      const crfr_conv_desc shapes[4] = {
+          {B, S, S, 3, 64, 3, 1, 1, S, S, 4, 64, 0},            // coarse conv_input
+          {B, S, S, 64, 3, 3, 1, 1, S, S, 64, 4, 0},            // conv_mid / conv_out
+          {B, S, S, 3, 128, 7, 4, 3, S / 4, S / 4, 4, 128, 0},  // stems
+          {B, S / 4, S / 4, 64, 64, 7, 4, 2, S, S, 64, 64, 1}}; // deconv
+      for (const crfr_conv_desc& sd : shapes) {
+        size_t b = crfr_conv_workspace_bytes(&sd);
+        if (b > scratch_bytes) scratch_bytes = b;
+      }
+    }
     scratch = alloc(scratch_bytes);
     x4 = new_tensor(B, S, S, 4);
     x4.c = 3;
@@ -476,14 +487,14 @@ struct Net {
           if (!g) break;
           crfr_conv_desc d = op.cd;
           d.out_ld = 4;
-          if (run()) check(crfr_conv_wgrad(CRFR_ENGINE_DIRECT, &d, op.a.p, g, grad(op.w_idx), grad(op.b_idx), scratch,
+          if (run()) check(crfr_conv_wgrad(engine, &d, op.a.p, g, grad(op.w_idx), grad(op.b_idx), scratch,
                                 scratch_bytes, st));
           const Tensor& x = op.a;
           bf16* dx = (bf16*)alloc((size_t)x.n * x.h * x.w * x.c * sizeof(bf16));
           void* wt = pack(op.w_idx, 3, x.c, 3, 0, false, true);
           crfr_conv_desc dd = d;
           dd.in_ld = x.c;
-          if (run()) check(crfr_conv_dgrad(CRFR_ENGINE_DIRECT, &dd, g, wt, 4, dx, scratch, scratch_bytes, st));
+          if (run()) check(crfr_conv_dgrad(engine, &dd, g, wt, 4, dx, scratch, scratch_bytes, st));
           add_slot(x, dx, x.c);
           break;
         }

@@ -18,6 +18,24 @@ int crfr_direct_wgrad(int n, int bh, int bw, int sh, int sw, int k, int stride, 
                       int small_ld, int A, const void* big, int big_ld, int B, float* G, cudaStream_t st);
 int crfr_colsum(const void* t, int ld, int c, long long npix, float* out, cudaStream_t st);
 
+// tc_conv.cu: generic tcgen05 launchers used by the lowered (im2col) edge layers
+struct TcGemm {           // out[pixel][n] = bias[n] + sum_{tap,k} src[pixel + sign*(tap - pad)][k] * w[tap][n][k]
+  const void* src; int n, h, w, k_total, src_ld;
+  const void* wt;         // bf16 [ksize*ksize][n_total][k_total]
+  int ksize, pad, sign;
+  int n_total, tile_n;    // tile_n = 0: pick automatically
+  void* out; int out_ld, out_f32;
+  const float* bias;
+};
+int crfr_tc_gemm(const TcGemm& g, cudaStream_t st);
+struct TcWgrad {          // G[tap][ci][co] += sum_pixel x[pixel + tap - 1][ci] * dy[pixel][co]   (fp32, caller zeroes G)
+  const void* x; int n, h, w, cin, x_ld;
+  const void* dy; int cout, dy_ld;
+  int taps3x3;            // 1: 3x3 pad 1 (9 taps), 0: single tap
+  float* G;
+};
+int crfr_tc_wgrad_raw(const TcWgrad& g, cudaStream_t st);
+
 // tc_conv.cu (tcgen05 engine).  op: 0 = forward, 1 = dgrad, 2 = wgrad
 int crfr_tc_supported(int op, int h, int w, int cin, int cout, int k, int stride, int pad);
 size_t crfr_tc_workspace_bytes(const crfr_conv_desc* d);
@@ -25,3 +43,13 @@ int crfr_tc_conv(const crfr_conv_desc* d, int dgrad, const void* src, const void
                  void* dst, float* stats, float eps, void* ws, size_t ws_bytes, cudaStream_t st);
 int crfr_tc_wgrad(const crfr_conv_desc* d, const void* x, const void* dy, float* dw, void* ws, size_t ws_bytes,
                   cudaStream_t st);
+
+// lowered_conv.cu: edge layers as [gather kernel] + [tcgen05 GEMM]; recipe 0 = not applicable
+int crfr_lowered_recipe(const crfr_conv_desc* d);
+size_t crfr_lowered_ws_bytes(const crfr_conv_desc* d);
+int crfr_lowered_fwd(const crfr_conv_desc* d, const void* x, const void* w_packed, int cin_pad, const float* bias,
+                     void* y, float* y_nchw, void* ws, size_t ws_bytes, cudaStream_t st);
+int crfr_lowered_dgrad(const crfr_conv_desc* d, const void* dy, const void* w_packed_t, int cout_pad, void* dx, void* ws,
+                       size_t ws_bytes, cudaStream_t st);
+int crfr_lowered_wgrad(const crfr_conv_desc* d, const void* x, const void* dy, float* dw, void* ws, size_t ws_bytes,
+                       cudaStream_t st);

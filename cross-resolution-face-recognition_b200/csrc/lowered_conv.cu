@@ -1,0 +1,400 @@
+// Edge layers lowered onto the tcgen05 GEMM engine.
+//
+// The layers whose channel counts cannot fill a UMMA tile (3-channel images) or that are strided / transposed are
+// rewritten as [cheap HBM-bound gather kernel] + [plain tcgen05 GEMM over 64-channel K chunks]:
+//   R1  Conv2d 3x3 s1 p1, cin = 3 (coarse conv_input, FSRnet.py:312)   fwd, wgrad : im2col(27 -> 64 ch) . W
+//   R2  Conv2d 3x3 s1 p1, cout = 3 (conv_mid :318, conv_out :439)      fwd : x . W(27 -> 32 cols, fp32) then col2im
+//                                                                     dgrad, wgrad : im2col(dY) as the GEMM operand
+//   R3  Conv2d 7x7 s4 p3, cin = 3 (encoder / prior stems :345, :384)   fwd, wgrad : im2col(147 -> 192 ch) . W
+//                                                                     dgrad : dY . W (192 cols, fp32) then col2im
+//   R4  ConvTranspose2d 7x7 s4 p2 op1, 64 -> 64 (decoder :436)         fwd : x . W (49*64 cols, fp32) then col2im
+//                                                                     dgrad, wgrad : im2col(dOut) as the GEMM operand
+// Partial products that are summed by a col2im kernel stay fp32 until the single final rounding, so the arithmetic
+// contract is the same as the direct kernels': fp32 accumulation over all taps and channels, one bf16 rounding.
+#include "common.cuh"
+#include "crfr.h"
+#include "internal.h"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------------
+// gather kernels
+// ---------------------------------------------------------------------------------------------------------
+// P[o][tap*C + c] = x[o*stride + sign*(tap - pad)][c]   (zero outside the image, zero for k >= T*C); kpad % 8 == 0
+__global__ void im2col_small_kernel(const bf16* __restrict__ x, int x_ld, int C, int h, int w, int oh, int ow, int ks,
+                                    int stride, int pad, int sign, bf16* __restrict__ P, int kpad, long long total) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int groups = kpad >> 3;
+  const int g = (int)(i % groups);
+  long long o = i / groups;
+  const int ox = (int)(o % ow);
+  long long q = o / ow;
+  const int oy = (int)(q % oh);
+  const long long n = q / oh;
+  const int kmax = ks * ks * C;
+  float f[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = g * 8 + j;
+    float v = 0.f;
+    if (k < kmax) {
+      const int tap = k / C, c = k - tap * C;
+      const int ky = tap / ks, kx = tap - ky * ks;
+      const int y = oy * stride + sign * (ky - pad), xx = ox * stride + sign * (kx - pad);
+      if (y >= 0 && y < h && xx >= 0 && xx < w) v = __bfloat162float(x[((n * h + y) * w + xx) * x_ld + c]);
+    }
+    f[j] = v;
+  }
+  *reinterpret_cast<bf16x8*>(P + o * kpad + g * 8) = pack8(f);
+}
+
+// dst[P][c] = bias[c] + sum_{tap : t = P + sgn*(pad - tap), t % stride == 0, t/stride inside} src[t/stride][tap*C + c]
+// src fp32 [.., src_ld]; outputs: fp32 NCHW and/or bf16 NHWC (ld, zero channel padding)
+__global__ void col2im_small_kernel(const float* __restrict__ src, int src_ld, int C, int sh, int sw, int bh, int bw,
+                                    int ks, int stride, int pad, int sgn, const float* __restrict__ bias,
+                                    float* __restrict__ y_nchw, bf16* __restrict__ y, int y_ld, long long total) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int X = (int)(i % bw);
+  long long q = i / bw;
+  const int Y = (int)(q % bh);
+  const long long n = q / bh;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int c = 0; c < C; ++c) acc[c] = bias ? bias[c] : 0.f;
+  for (int ky = 0; ky < ks; ++ky) {
+    const int ty = Y + sgn * (pad - ky);
+    if (ty < 0 || ty % stride) continue;
+    const int sy = ty / stride;
+    if (sy >= sh) continue;
+    for (int kx = 0; kx < ks; ++kx) {
+      const int tx = X + sgn * (pad - kx);
+      if (tx < 0 || tx % stride) continue;
+      const int sx = tx / stride;
+      if (sx >= sw) continue;
+      const float* s = src + ((n * sh + sy) * sw + sx) * src_ld + (ky * ks + kx) * C;
+      for (int c = 0; c < C; ++c) acc[c] += s[c];
+    }
+  }
+  if (y_nchw)
+    for (int c = 0; c < C; ++c) y_nchw[(n * C + c) * ((long long)bh * bw) + (long long)Y * bw + X] = acc[c];
+  if (y)
+    for (int c = 0; c < y_ld; ++c) y[i * y_ld + c] = __float2bfloat16_rn(c < C ? acc[c] : 0.f);
+}
+
+// ConvTranspose col2im, 8 channels per thread: out[Y][X][co] = bias + sum_{valid taps} Z[(Y+pad-ky)/s][(X+pad-kx)/s][tap*C + co]
+__global__ void deconv_col2im_kernel(const float* __restrict__ Z, int C, int sh, int sw, int bh, int bw, int ks,
+                                     int stride, int pad, const float* __restrict__ bias, bf16* __restrict__ out,
+                                     int out_ld, long long total) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int groups = C >> 3;
+  const int g = (int)(i % groups);
+  long long p = i / groups;
+  const int X = (int)(p % bw);
+  long long q = p / bw;
+  const int Y = (int)(q % bh);
+  const long long n = q / bh;
+  const int zld = ks * ks * C;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = bias ? bias[g * 8 + j] : 0.f;
+  for (int ky = 0; ky < ks; ++ky) {
+    const int ty = Y + pad - ky;
+    if (ty < 0 || ty % stride) continue;
+    const int sy = ty / stride;
+    if (sy >= sh) continue;
+    for (int kx = 0; kx < ks; ++kx) {
+      const int tx = X + pad - kx;
+      if (tx < 0 || tx % stride) continue;
+      const int sx = tx / stride;
+      if (sx >= sw) continue;
+      const float4* s = reinterpret_cast<const float4*>(Z + ((n * sh + sy) * sw + sx) * zld + (ky * ks + kx) * C + g * 8);
+      const float4 a = s[0], b = s[1];
+      acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+      acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+    }
+  }
+  *reinterpret_cast<bf16x8*>(out + p * out_ld + g * 8) = pack8(acc);
+}
+
+// ConvTranspose im2col: dZ[i][tap*C + co] = dOut[i*s - pad + tap][co] (zero outside)
+__global__ void deconv_im2col_kernel(const bf16* __restrict__ dout, int dout_ld, int C, int sh, int sw, int bh, int bw,
+                                     int ks, int stride, int pad, bf16* __restrict__ dZ, long long total) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int groups = C >> 3;
+  const int g = (int)(i % groups);
+  long long r = i / groups;
+  const int T = ks * ks;
+  const int tap = (int)(r % T);
+  long long p = r / T;
+  const int sx = (int)(p % sw);
+  long long q = p / sw;
+  const int sy = (int)(q % sh);
+  const long long n = q / sh;
+  const int ky = tap / ks, kx = tap - ky * ks;
+  const int Y = sy * stride - pad + ky, X = sx * stride - pad + kx;
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (Y >= 0 && Y < bh && X >= 0 && X < bw)
+    v = *reinterpret_cast<const uint4*>(dout + ((n * bh + Y) * bw + X) * dout_ld + g * 8);
+  *reinterpret_cast<uint4*>(dZ + p * ((long long)T * C) + (long long)tap * C + g * 8) = v;
+}
+
+// dst[r][tap*S + s] = src[tap][r][s] for s < S (src: [T][R][s_pad] bf16), zero elsewhere; dst is [rows_pad][kpad]
+__global__ void repack_tapmajor_kernel(const bf16* __restrict__ src, int T, int R, int S, int s_pad, bf16* __restrict__ dst,
+                                       int rows_pad, int kpad) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows_pad * kpad) return;
+  const int k = i % kpad, r = i / kpad;
+  bf16 v = __float2bfloat16_rn(0.f);
+  if (r < R && k < T * S) {
+    const int tap = k / S, s = k - tap * S;
+    v = src[((long long)tap * R + r) * s_pad + s];
+  }
+  dst[i] = v;
+}
+
+// dw[(d0*D1 + d1)*T + tap] += G[k][n]
+//   mode 0: k = tap*D1 + d1, n = d0            (R1 / R3: d0 = co, d1 = c)
+//   mode 1: k = d1,          n = tap*D0 + d0   (R2: d0 = co, d1 = ci)
+//   mode 2: k = d0,          n = tap*D1 + d1   (R4: d0 = ci, d1 = co)
+__global__ void unpack_lowered_kernel(const float* __restrict__ G, int g_ld, float* __restrict__ dw, int D0, int D1, int T,
+                                      int mode) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)D0 * D1 * T) return;
+  const int tap = (int)(i % T);
+  long long r = i / T;
+  const int d1 = (int)(r % D1), d0 = (int)(r / D1);
+  int k, n;
+  if (mode == 0) { k = tap * D1 + d1; n = d0; }
+  else if (mode == 1) { k = d1; n = tap * D0 + d0; }
+  else { k = d0; n = tap * D1 + d1; }
+  dw[i] += G[(long long)k * g_ld + n];
+}
+
+struct Arena {
+  uint8_t* base;
+  size_t cap, off;
+  void* take(size_t bytes) {
+    size_t a = (off + 1023) & ~(size_t)1023;
+    if (a + bytes > cap) return nullptr;
+    off = a + bytes;
+    return base + a;
+  }
+};
+
+#define TAKE(ptr, type, arena, bytes)                                              \
+  type* ptr = (type*)(arena).take(bytes);                                          \
+  if (!ptr) {                                                                      \
+    crfr_set_error("lowered conv: workspace too small (%zu bytes given)", (arena).cap); \
+    return CRFR_EWORKSPACE;                                                        \
+  }
+
+#define LAUNCH(kernel, total, st, ...)                                              \
+  do {                                                                              \
+    kernel<<<crfr_cdiv((total), 256), 256, 0, (st)>>>(__VA_ARGS__);                 \
+    CRFR_COUNT_LAUNCH();                                                            \
+    CRFR_LAUNCH_CHECK();                                                            \
+  } while (0)
+
+inline int kpad_of(const crfr_conv_desc* d) { return ((d->k * d->k * 3 + 63) / 64) * 64; }   // 27 -> 64, 147 -> 192
+
+int tcgen05_spatial_ok(int h, int w) { return crfr_tc_supported(2, h, w, 64, 64, 3, 1, 1); }
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------
+// recipe selection
+// ---------------------------------------------------------------------------------------------------------
+int crfr_lowered_recipe(const crfr_conv_desc* d) {
+  if (!d->transposed) {
+    if (d->k == 3 && d->stride == 1 && d->pad == 1 && d->cin == 3 && d->in_ld == 4 && d->cout % 64 == 0 && d->cout <= 256 &&
+        tcgen05_spatial_ok(d->h, d->w))
+      return 1;
+    if (d->k == 3 && d->stride == 1 && d->pad == 1 && d->cout == 3 && d->cin == 64 && tcgen05_spatial_ok(d->h, d->w))
+      return 2;
+    if (d->k == 7 && d->stride == 4 && d->pad == 3 && d->cin == 3 && d->in_ld == 4 && (d->cout == 64 || d->cout == 128) &&
+        tcgen05_spatial_ok(d->oh, d->ow))
+      return 3;
+    return 0;
+  }
+  if (d->k == 7 && d->stride == 4 && d->pad == 2 && d->cin == 64 && d->cout == 64 && d->oh == 4 * d->h && d->ow == 4 * d->w &&
+      tcgen05_spatial_ok(d->h, d->w))
+    return 4;
+  return 0;
+}
+
+size_t crfr_lowered_ws_bytes(const crfr_conv_desc* d) {
+  const int r = crfr_lowered_recipe(d);
+  const size_t big = (size_t)d->n * d->h * d->w, small = (size_t)d->n * d->oh * d->ow;
+  size_t b = 0;
+  switch (r) {
+    case 1: b = big * 64 * 2 + (size_t)256 * 64 * 2 + (size_t)64 * 256 * 4; break;
+    case 2: b = big * 64 * 2 + big * 32 * 4 + (size_t)64 * 64 * 2 * 2 + (size_t)64 * 64 * 4; break;
+    case 3: b = small * 192 * 2 + small * 192 * 4 + (size_t)192 * 128 * 2 * 2 + (size_t)192 * 128 * 4; break;
+    case 4: {
+      const size_t zc = 49 * 64;
+      b = big * zc * 4 + (size_t)64 * zc * 2 + (size_t)64 * zc * 4;   // big = input (small) grid here
+      break;
+    }
+    default: return 0;
+  }
+  return b + 16 * 1024;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------------------
+int crfr_lowered_fwd(const crfr_conv_desc* d, const void* x, const void* w_packed, int cin_pad, const float* bias,
+                     void* y, float* y_nchw, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const int recipe = crfr_lowered_recipe(d);
+  Arena A{(uint8_t*)ws, ws_bytes, 0};
+  const int T = d->k * d->k;
+  if (recipe == 1 || recipe == 3) {
+    if (!y || y_nchw) {
+      crfr_set_error("lowered conv: recipe %d produces the bf16 NHWC output only", recipe);
+      return CRFR_EUNSUPPORTED;
+    }
+    const int kp = kpad_of(d);
+    const long long opix = (long long)d->n * d->oh * d->ow;
+    TAKE(P, bf16, A, (size_t)opix * kp * 2);
+    TAKE(Wg, bf16, A, (size_t)d->cout * kp * 2);
+    LAUNCH(im2col_small_kernel, opix * (kp / 8), st, (const bf16*)x, d->in_ld, 3, d->h, d->w, d->oh, d->ow, d->k, d->stride,
+           d->pad, 1, P, kp, opix * (kp / 8));
+    LAUNCH(repack_tapmajor_kernel, d->cout * kp, st, (const bf16*)w_packed, T, d->cout, 3, cin_pad, Wg, d->cout, kp);
+    TcGemm g{P, d->n, d->oh, d->ow, kp, kp, Wg, 1, 0, 1, d->cout, 0, y, d->out_ld, 0, bias};
+    return crfr_tc_gemm(g, st);
+  }
+  if (recipe == 2) {
+    const long long pix = (long long)d->n * d->h * d->w;
+    TAKE(Q, float, A, (size_t)pix * 32 * 4);
+    TAKE(Wq, bf16, A, (size_t)32 * 64 * 2);
+    CRFR_CUDA(cudaMemsetAsync(Wq, 0, (size_t)32 * 64 * 2, st));
+    CRFR_CUDA(cudaMemcpyAsync(Wq, w_packed, (size_t)27 * 64 * 2, cudaMemcpyDeviceToDevice, st));   // rows (tap, co)
+    TcGemm g{x, d->n, d->h, d->w, 64, d->in_ld, Wq, 1, 0, 1, 32, 32, Q, 32, 1, nullptr};
+    CRFR_TRY(crfr_tc_gemm(g, st));
+    // y[p] = bias + sum_tap Q[p + (tap - pad)][tap*3 + co]
+    LAUNCH(col2im_small_kernel, pix, st, Q, 32, 3, d->h, d->w, d->h, d->w, 3, 1, 1, -1, bias, y_nchw, (bf16*)y,
+           y ? d->out_ld : 0, pix);
+    return CRFR_OK;
+  }
+  if (recipe == 4) {
+    if (!y || y_nchw) {
+      crfr_set_error("lowered conv: the transposed recipe produces the bf16 NHWC output only");
+      return CRFR_EUNSUPPORTED;
+    }
+    const long long ipix = (long long)d->n * d->h * d->w, opix = (long long)d->n * d->oh * d->ow;
+    const int zc = T * 64;
+    TAKE(Z, float, A, (size_t)ipix * zc * 4);
+    // w_packed is [tap][co][ci]: exactly the [tap*64 + co][ci] GEMM weight
+    TcGemm g{x, d->n, d->h, d->w, 64, d->in_ld, w_packed, 1, 0, 1, zc, 224, Z, zc, 1, nullptr};
+    CRFR_TRY(crfr_tc_gemm(g, st));
+    LAUNCH(deconv_col2im_kernel, opix * 8, st, Z, 64, d->h, d->w, d->oh, d->ow, d->k, d->stride, d->pad, bias, (bf16*)y,
+           d->out_ld, opix * 8);
+    return CRFR_OK;
+  }
+  crfr_set_error("lowered conv: no recipe for this shape");
+  return CRFR_EUNSUPPORTED;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// dgrad (recipes 2, 3, 4)
+// ---------------------------------------------------------------------------------------------------------
+int crfr_lowered_dgrad(const crfr_conv_desc* d, const void* dy, const void* w_packed_t, int cout_pad, void* dx, void* ws,
+                       size_t ws_bytes, cudaStream_t st) {
+  const int recipe = crfr_lowered_recipe(d);
+  Arena A{(uint8_t*)ws, ws_bytes, 0};
+  const int T = d->k * d->k;
+  if (recipe == 2) {
+    // dX[q][ci] = sum_k R[q][k] Wd[ci][k],  R[q][tap*3+co] = dY[q - (tap - pad)][co],  Wd[ci][tap*3+co] = W[co][ci][tap]
+    const long long pix = (long long)d->n * d->h * d->w;
+    TAKE(R, bf16, A, (size_t)pix * 64 * 2);
+    TAKE(Wd, bf16, A, (size_t)64 * 64 * 2);
+    LAUNCH(im2col_small_kernel, pix * 8, st, (const bf16*)dy, d->out_ld, 3, d->h, d->w, d->h, d->w, 3, 1, 1, -1, R, 64,
+           pix * 8);
+    LAUNCH(repack_tapmajor_kernel, 64 * 64, st, (const bf16*)w_packed_t, T, 64, 3, cout_pad, Wd, 64, 64);
+    TcGemm g{R, d->n, d->h, d->w, 64, 64, Wd, 1, 0, 1, 64, 64, dx, d->in_ld, 0, nullptr};
+    return crfr_tc_gemm(g, st);
+  }
+  if (recipe == 3) {
+    // dP[o][tap*3+c] = sum_co dY[o][co] W[co][c][tap] (fp32), then dx[P][c] = sum over the taps that hit P
+    const int kp = kpad_of(d);   // 192
+    const long long opix = (long long)d->n * d->oh * d->ow, ipix = (long long)d->n * d->h * d->w;
+    TAKE(dP, float, A, (size_t)opix * kp * 4);
+    TAKE(Wd, bf16, A, (size_t)kp * d->cout * 2);
+    // w_packed_t is [tap][c(3)][cout_pad]: rows (tap, c) are the GEMM weight rows; pad to kp rows of cout
+    CRFR_CUDA(cudaMemsetAsync(Wd, 0, (size_t)kp * d->cout * 2, st));
+    CRFR_CHECK_ARG(cout_pad == d->cout, "lowered dgrad: cout_pad %d != cout %d", cout_pad, d->cout);
+    CRFR_CUDA(cudaMemcpyAsync(Wd, w_packed_t, (size_t)T * 3 * d->cout * 2, cudaMemcpyDeviceToDevice, st));
+    TcGemm g{dy, d->n, d->oh, d->ow, d->cout, d->out_ld, Wd, 1, 0, 1, kp, kp == 192 ? 192 : 0, dP, kp, 1, nullptr};
+    CRFR_TRY(crfr_tc_gemm(g, st));
+    LAUNCH(col2im_small_kernel, ipix, st, dP, kp, 3, d->oh, d->ow, d->h, d->w, d->k, d->stride, d->pad, 1, nullptr, nullptr,
+           (bf16*)dx, d->in_ld, ipix);
+    return CRFR_OK;
+  }
+  if (recipe == 4) {
+    // d_in[i][ci] = sum_{tap,co} dZ[i][tap*64+co] W[ci][co][tap]
+    const long long ipix = (long long)d->n * d->h * d->w;
+    const int zc = T * 64;
+    TAKE(dZ, bf16, A, (size_t)ipix * zc * 2);
+    TAKE(Wd, bf16, A, (size_t)64 * zc * 2);
+    LAUNCH(deconv_im2col_kernel, ipix * T * 8, st, (const bf16*)dy, d->out_ld, 64, d->h, d->w, d->oh, d->ow, d->k, d->stride,
+           d->pad, dZ, ipix * T * 8);
+    LAUNCH(repack_tapmajor_kernel, 64 * zc, st, (const bf16*)w_packed_t, T, 64, 64, cout_pad, Wd, 64, zc);
+    TcGemm g{dZ, d->n, d->h, d->w, zc, zc, Wd, 1, 0, 1, 64, 64, dx, d->in_ld, 0, nullptr};
+    return crfr_tc_gemm(g, st);
+  }
+  crfr_set_error("lowered dgrad: no recipe for this shape");
+  return CRFR_EUNSUPPORTED;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// wgrad (all recipes); dw is accumulated (+=)
+// ---------------------------------------------------------------------------------------------------------
+int crfr_lowered_wgrad(const crfr_conv_desc* d, const void* x, const void* dy, float* dw, void* ws, size_t ws_bytes,
+                       cudaStream_t st) {
+  const int recipe = crfr_lowered_recipe(d);
+  Arena A{(uint8_t*)ws, ws_bytes, 0};
+  const int T = d->k * d->k;
+  if (recipe == 1 || recipe == 3) {
+    const int kp = kpad_of(d);
+    const long long opix = (long long)d->n * d->oh * d->ow;
+    TAKE(P, bf16, A, (size_t)opix * kp * 2);
+    TAKE(G, float, A, (size_t)kp * d->cout * 4);
+    LAUNCH(im2col_small_kernel, opix * (kp / 8), st, (const bf16*)x, d->in_ld, 3, d->h, d->w, d->oh, d->ow, d->k, d->stride,
+           d->pad, 1, P, kp, opix * (kp / 8));
+    CRFR_CUDA(cudaMemsetAsync(G, 0, (size_t)kp * d->cout * 4, st));
+    TcWgrad g{P, d->n, d->oh, d->ow, kp, kp, dy, d->cout, d->out_ld, 0, G};
+    CRFR_TRY(crfr_tc_wgrad_raw(g, st));
+    LAUNCH(unpack_lowered_kernel, (long long)d->cout * 3 * T, st, G, d->cout, dw, d->cout, 3, T, 0);
+    return CRFR_OK;
+  }
+  if (recipe == 2) {
+    const long long pix = (long long)d->n * d->h * d->w;
+    TAKE(R, bf16, A, (size_t)pix * 64 * 2);
+    TAKE(G, float, A, (size_t)64 * 64 * 4);
+    LAUNCH(im2col_small_kernel, pix * 8, st, (const bf16*)dy, d->out_ld, 3, d->h, d->w, d->h, d->w, 3, 1, 1, -1, R, 64,
+           pix * 8);
+    CRFR_CUDA(cudaMemsetAsync(G, 0, (size_t)64 * 64 * 4, st));
+    TcWgrad g{x, d->n, d->h, d->w, 64, d->in_ld, R, 64, 64, 0, G};
+    CRFR_TRY(crfr_tc_wgrad_raw(g, st));
+    LAUNCH(unpack_lowered_kernel, (long long)3 * 64 * T, st, G, 64, dw, 3, 64, T, 1);
+    return CRFR_OK;
+  }
+  if (recipe == 4) {
+    const long long ipix = (long long)d->n * d->h * d->w;
+    const int zc = T * 64;
+    TAKE(dZ, bf16, A, (size_t)ipix * zc * 2);
+    TAKE(G, float, A, (size_t)64 * zc * 4);
+    LAUNCH(deconv_im2col_kernel, ipix * T * 8, st, (const bf16*)dy, d->out_ld, 64, d->h, d->w, d->oh, d->ow, d->k, d->stride,
+           d->pad, dZ, ipix * T * 8);
+    CRFR_CUDA(cudaMemsetAsync(G, 0, (size_t)64 * zc * 4, st));
+    TcWgrad g{x, d->n, d->h, d->w, 64, d->in_ld, dZ, zc, zc, 0, G};
+    CRFR_TRY(crfr_tc_wgrad_raw(g, st));
+    LAUNCH(unpack_lowered_kernel, (long long)64 * 64 * T, st, G, zc, dw, 64, 64, T, 2);
+    return CRFR_OK;
+  }
+  crfr_set_error("lowered wgrad: no recipe for this shape");
+  return CRFR_EUNSUPPORTED;
+}

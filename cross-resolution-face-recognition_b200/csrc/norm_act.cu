@@ -19,7 +19,7 @@ struct ChunkPlan {
 
 inline ChunkPlan plan_chunks(int n, int hw) {
   // aim for >= ~4 CTAs per SM overall, chunks of at least 256 pixels
-  int want = (148 * 8 + n - 1) / n;
+  int want = (148 * 4 + n - 1) / n;
   int maxc = (hw + 255) / 256;
   int chunks = want < 1 ? 1 : want;
   if (chunks > maxc) chunks = maxc;
@@ -72,21 +72,39 @@ stats_partial_kernel(const bf16* __restrict__ y, int ld, int hw, int c, int chun
   cta_reduce_store<2>(acc, smem, cg, lane, lanes, c, partial + ((long long)n * gridDim.x + chunk) * 2 * c);
 }
 
-__global__ void stats_finalize_kernel(const float* __restrict__ partial, int chunks, int c, int total, float inv_hw,
-                                      float eps, float* __restrict__ stats) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;  // (n, ch)
-  if (i >= total) return;
-  int n = i / c, ch = i - n * c;
+// one CTA per image: 256 threads = (256 / c) chunk lanes x c channels; deterministic two-level sum over the chunks
+__global__ void __launch_bounds__(kThreads)
+stats_finalize_kernel(const float* __restrict__ partial, int chunks, int c, float inv_hw, float eps,
+                      float* __restrict__ stats) {
+  __shared__ float sm[2][kThreads];
+  const int n = blockIdx.x;
   const float* p = partial + (long long)n * chunks * 2 * c;
-  float s = 0.f, q = 0.f;
-  for (int k = 0; k < chunks; ++k) {
-    s += p[(k * 2 + 0) * c + ch];
-    q += p[(k * 2 + 1) * c + ch];
+  for (int c0 = 0; c0 < c; c0 += kThreads) {
+    const int cw = min(c - c0, kThreads);          // channels handled in this pass
+    const int lanes = kThreads / cw;
+    const int ch = threadIdx.x % cw, lane = threadIdx.x / cw;
+    float s = 0.f, q = 0.f;
+    if (lane < lanes)
+      for (int k = lane; k < chunks; k += lanes) {
+        s += p[(k * 2 + 0) * c + c0 + ch];
+        q += p[(k * 2 + 1) * c + c0 + ch];
+      }
+    sm[0][threadIdx.x] = s;
+    sm[1][threadIdx.x] = q;
+    __syncthreads();
+    if (threadIdx.x < cw) {
+      float ts = 0.f, tq = 0.f;
+      for (int l = 0; l < lanes; ++l) {
+        ts += sm[0][l * cw + threadIdx.x];
+        tq += sm[1][l * cw + threadIdx.x];
+      }
+      const float mean = ts * inv_hw;
+      const float var = fmaxf(tq * inv_hw - mean * mean, 0.f);
+      stats[2 * (n * c + c0 + threadIdx.x)] = mean;
+      stats[2 * (n * c + c0 + threadIdx.x) + 1] = rsqrtf(var + eps);
+    }
+    __syncthreads();
   }
-  float mean = s * inv_hw;
-  float var = fmaxf(q * inv_hw - mean * mean, 0.f);
-  stats[2 * i] = mean;
-  stats[2 * i + 1] = rsqrtf(var + eps);
 }
 
 __global__ void __launch_bounds__(kThreads)
@@ -183,24 +201,38 @@ norm_act_bwd_reduce_kernel(const bf16* __restrict__ da, int da_ld, const bf16* _
   cta_reduce_store<3>(acc, smem, cg, lane, lanes, c, partial + ((long long)n * gridDim.x + chunk) * 3 * c);
 }
 
-// per (n, ch): fold the chunk partials -> bstats[n][ch] = (mean dz, mean dz*xhat); tot[n][3][c]
-__global__ void bwd_fold_kernel(const float* __restrict__ partial, int chunks, int c, int total, float inv_hw,
-                                float* __restrict__ bstats, float* __restrict__ tot) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  int n = i / c, ch = i - n * c;
+// one CTA per image: fold the chunk partials -> bstats[n][ch] = (mean dz, mean dz*xhat); tot[n][3][c]
+__global__ void __launch_bounds__(kThreads)
+bwd_fold_kernel(const float* __restrict__ partial, int chunks, int c, float inv_hw, float* __restrict__ bstats,
+                float* __restrict__ tot) {
+  __shared__ float sm[3][kThreads];
+  const int n = blockIdx.x;
   const float* p = partial + (long long)n * chunks * 3 * c;
-  float s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  for (int k = 0; k < chunks; ++k) {
-    s1 += p[(k * 3 + 0) * c + ch];
-    s2 += p[(k * 3 + 1) * c + ch];
-    s3 += p[(k * 3 + 2) * c + ch];
+  for (int c0 = 0; c0 < c; c0 += kThreads) {
+    const int cw = min(c - c0, kThreads);
+    const int lanes = kThreads / cw;
+    const int ch = threadIdx.x % cw, lane = threadIdx.x / cw;
+    float s[3] = {0.f, 0.f, 0.f};
+    if (lane < lanes)
+      for (int k = lane; k < chunks; k += lanes)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) s[j] += p[(k * 3 + j) * c + c0 + ch];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) sm[j][threadIdx.x] = s[j];
+    __syncthreads();
+    if (threadIdx.x < cw) {
+      float t[3] = {0.f, 0.f, 0.f};
+      for (int l = 0; l < lanes; ++l)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) t[j] += sm[j][l * cw + threadIdx.x];
+      const int i = n * c + c0 + threadIdx.x;
+      bstats[2 * i] = t[0] * inv_hw;
+      bstats[2 * i + 1] = t[1] * inv_hw;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) tot[(n * 3 + j) * c + c0 + threadIdx.x] = t[j];
+    }
+    __syncthreads();
   }
-  bstats[2 * i] = s1 * inv_hw;
-  bstats[2 * i + 1] = s2 * inv_hw;
-  tot[(n * 3 + 0) * c + ch] = s1;
-  tot[(n * 3 + 1) * c + ch] = s2;
-  tot[(n * 3 + 2) * c + ch] = s3;
 }
 
 // per channel: sum tot over n in fixed order and accumulate into the parameter gradients
@@ -275,9 +307,7 @@ size_t crfr_norm_ws_bytes(int n, int hw, int c) {
 // Finalise (mean, rstd) from partials laid out [n][chunks][2][c]; shared with the conv epilogue statistics.
 int crfr_norm_finalize(const float* partial, int n, int chunks, int hw, int c, float eps, float* stats,
                        cudaStream_t st) {
-  int total = n * c;
-  stats_finalize_kernel<<<crfr_cdiv(total, 256), 256, 0, st>>>(partial, chunks, c, total, 1.f / (float)hw, eps,
-                                                               stats);
+  stats_finalize_kernel<<<n, kThreads, 0, st>>>(partial, chunks, c, 1.f / (float)hw, eps, stats);
   CRFR_COUNT_LAUNCH();
   CRFR_LAUNCH_CHECK();
   return CRFR_OK;
@@ -346,8 +376,7 @@ extern "C" int crfr_norm_act_bwd(const void* dout_a, int da_ld, const void* dout
       (const bf16*)res, res_ld, (bf16*)dz, dz_ld, hw, c, pl.chunk_pix, partial);
   CRFR_COUNT_LAUNCH();
   CRFR_LAUNCH_CHECK();
-  int total = n * c;
-  bwd_fold_kernel<<<crfr_cdiv(total, 256), 256, 0, st>>>(partial, pl.chunks, c, total, 1.f / (float)hw, bstats, tot);
+  bwd_fold_kernel<<<n, kThreads, 0, st>>>(partial, pl.chunks, c, 1.f / (float)hw, bstats, tot);
   CRFR_COUNT_LAUNCH();
   CRFR_LAUNCH_CHECK();
   if (dgamma || dbeta || dalpha) {

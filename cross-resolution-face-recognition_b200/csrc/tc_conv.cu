@@ -118,8 +118,10 @@ struct ConvParams {
   int n, h, w;
   int kchunks, ksize, ntaps, pad, sign;
   int bw, bh, bn, tiles_x, tiles_y, rows;
+  int n_total;     // all output channels; this CTA computes columns [blockIdx.y * N, +N)
   int out_ld;
-  bf16* out;
+  int out_f32;     // 0: bf16 NHWC rows, 1: fp32 NHWC rows
+  void* out;
   const float* bias;
 };
 
@@ -133,6 +135,7 @@ struct ConvCfg {
   static constexpr int kStages = (N <= 64) ? 4 : 3;
   static constexpr int kTmemCols = (N <= 32) ? 32 : (N <= 64) ? 64 : (N <= 128) ? 128 : 256;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static_assert(N % 32 == 0 && N <= 256, "tile width");
 };
 
 template <int N>
@@ -169,6 +172,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int x0 = tx * p.bw, y0 = ty * p.bh, n0 = t * p.bn;
   const int iters = p.ntaps * p.kchunks;
   const uint32_t a_bytes = (uint32_t)p.rows * 128u;
+  const int ncol0 = blockIdx.y * N;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -180,7 +184,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int ky = tap / p.ksize, kx = tap - ky * p.ksize;
         uint8_t* sa = base + s * Cfg::kStageBytes;
         tma_load_4d(sa, &tmA, &full[s], kc * 64, x0 + p.sign * (kx - p.pad), y0 + p.sign * (ky - p.pad), n0);
-        tma_load_2d(sa + kATileBytes, &tmB, &full[s], kc * 64, tap * N);
+        tma_load_2d(sa + kATileBytes, &tmB, &full[s], kc * 64, tap * p.n_total + ncol0);
       }
     }
   } else if (warp == 1) {
@@ -212,7 +216,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int ih = rr % p.bh, in = rr / p.bh;
     const int x = x0 + iw, y = y0 + ih, n = n0 + in;
     const bool valid = r < p.rows && x < p.w && y < p.h && n < p.n;
-    bf16* dst = p.out + (((long long)n * p.h + y) * p.w + x) * p.out_ld;
+    const long long pix = ((long long)n * p.h + y) * p.w + x;
+    bf16* dst = (bf16*)p.out + pix * p.out_ld + ncol0;
+    float* dstf = (float*)p.out + pix * p.out_ld + ncol0;
+    const float* bias = p.bias ? p.bias + ncol0 : nullptr;
 #pragma unroll
     for (int c0 = 0; c0 < N; c0 += 32) {
       uint32_t v[32];
@@ -223,8 +230,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int j = 0; j < 32; j += 8) {
           float f[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j + e]) + (p.bias ? p.bias[c0 + j + e] : 0.f);
-          *reinterpret_cast<bf16x8*>(dst + c0 + j) = pack8(f);
+          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j + e]) + (bias ? bias[c0 + j + e] : 0.f);
+          if (p.out_f32) {
+            *reinterpret_cast<float4*>(dstf + c0 + j) = make_float4(f[0], f[1], f[2], f[3]);
+            *reinterpret_cast<float4*>(dstf + c0 + j + 4) = make_float4(f[4], f[5], f[6], f[7]);
+          } else {
+            *reinterpret_cast<bf16x8*>(dst + c0 + j) = pack8(f);
+          }
         }
       }
     }
@@ -245,7 +257,7 @@ int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams
     CRFR_CUDA(cudaFuncSetAttribute(tc_conv_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_done = true;
   }
-  tc_conv_kernel<N><<<tiles, kConvThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
+  tc_conv_kernel<N><<<dim3(tiles, p.n_total / N), kConvThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
   CRFR_COUNT_LAUNCH();
   CRFR_LAUNCH_CHECK();
   return CRFR_OK;
@@ -257,18 +269,21 @@ int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams
 struct WgradParams {
   int n, h, w;
   int bw, bh, bn, tiles_x, tiles_y, total_tiles;
-  int cin, cout;
-  float* G;  // [9][cin][cout] fp32, pre-zeroed
+  int cin, cout;   // cout = all dY channels; a CTA handles columns [ntile * N, +N)
+  float* G;        // [taps][cin][cout] fp32, pre-zeroed
 };
 
 constexpr int kTile16K = 128 * 128;
 
-template <int N>
+// TAPS = 3: one kernel row (ky) of a 3x3 conv per CTA, the three kx taps share the dY tile.  TAPS = 1: plain
+// [cin x cout] = X^T dY product (1x1 convs and the im2col-lowered edge layers).
+template <int N, int TAPS>
 struct WgCfg {
   static constexpr int kDyTiles = N / 64;
-  static constexpr int kStageBytes = (3 + kDyTiles) * kTile16K;
-  static constexpr int kStages = (N <= 64) ? 3 : 2;
-  static constexpr int kTmemCols = (2 * N <= 128) ? 128 : 256;
+  static constexpr int kStageBytes = (TAPS + kDyTiles) * kTile16K;
+  static constexpr int kStages = (kStageBytes <= 64 * 1024) ? 3 : 2;
+  static constexpr int kAccs = (TAPS + 1) / 2;                     // accumulators of M = 128 (two taps each)
+  static constexpr int kTmemCols = (kAccs * N <= 64) ? 64 : (kAccs * N <= 128) ? 128 : 256;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
 };
 
@@ -276,10 +291,10 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <int N>
+template <int N, int TAPS>
 __global__ void __launch_bounds__(kConvThreads, 1)
 tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY, WgradParams p) {
-  using Cfg = WgCfg<N>;
+  using Cfg = WgCfg<N, TAPS>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full = (uint64_t*)(base + Cfg::kStages * Cfg::kStageBytes);
@@ -304,7 +319,9 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  const int ky = blockIdx.y, kc = blockIdx.z;
+  // TAPS == 3: blockIdx.y = ky;  TAPS == 1: blockIdx.y = column tile of dY
+  const int ky = TAPS == 3 ? blockIdx.y : 0, kc = blockIdx.z;
+  const int ncol0 = TAPS == 3 ? 0 : blockIdx.y * N;
   const int first = blockIdx.x, step = gridDim.x;
   const int my_tiles = first < p.total_tiles ? (p.total_tiles - first + step - 1) / step : 0;
 
@@ -319,12 +336,16 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         const int ty = t % p.tiles_y; t /= p.tiles_y;
         const int x0 = tx * p.bw, y0 = ty * p.bh, n0 = t * p.bn;
         uint8_t* sb = base + s * Cfg::kStageBytes;
+        if (TAPS == 3) {
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx)
-          tma_load_4d(sb + kx * kTile16K, &tmX, &full[s], kc * 64, x0 + kx - 1, y0 + ky - 1, n0);
+          for (int kx = 0; kx < 3; ++kx)
+            tma_load_4d(sb + kx * kTile16K, &tmX, &full[s], kc * 64, x0 + kx - 1, y0 + ky - 1, n0);
+        } else {
+          tma_load_4d(sb, &tmX, &full[s], kc * 64, x0, y0, n0);
+        }
 #pragma unroll
         for (int j = 0; j < Cfg::kDyTiles; ++j)
-          tma_load_4d(sb + (3 + j) * kTile16K, &tmDY, &full[s], j * 64, x0, y0, n0);
+          tma_load_4d(sb + (TAPS + j) * kTile16K, &tmDY, &full[s], ncol0 + j * 64, x0, y0, n0);
       }
     }
   } else if (warp == 1) {
@@ -337,12 +358,16 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         const uint32_t sb = smem_u32(base + s * Cfg::kStageBytes);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {  // 8 x 16 pixels
+          // M = 128 = two 64-channel atoms LBO (= one 16 KB tile) apart: taps (0,1) in the first MMA; the second
+          // atom of the last MMA is whatever tile follows (rows 64..127 of that accumulator are never read)
           const uint64_t a01 = make_smem_desc_sw128(sb + k * 2048, kTile16K, 1024);
-          const uint64_t a2x = make_smem_desc_sw128(sb + 2 * kTile16K + k * 2048, kTile16K, 1024);
-          const uint64_t db = make_smem_desc_sw128(sb + 3 * kTile16K + k * 2048, kTile16K, 1024);
+          const uint64_t db = make_smem_desc_sw128(sb + TAPS * kTile16K + k * 2048, kTile16K, 1024);
           const uint32_t acc = (uint32_t)((i | k) != 0);
           umma_bf16(tmem, a01, db, idesc, acc);
-          umma_bf16(tmem + N, a2x, db, idesc, acc);
+          if (TAPS == 3) {
+            const uint64_t a2x = make_smem_desc_sw128(sb + 2 * kTile16K + k * 2048, kTile16K, 1024);
+            umma_bf16(tmem + N, a2x, db, idesc, acc);
+          }
         }
         umma_commit(&empty[s]);
       }
@@ -355,10 +380,10 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     tc_fence_after();
     const int ci = kc * 64 + (r & 63);
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
+    for (int half = 0; half < Cfg::kAccs; ++half) {
       const int kx = half == 0 ? (r >> 6) : 2;
-      const bool live = half == 0 || r < 64;   // warp-uniform (32-row granularity)
-      float* dst = p.G + ((long long)(ky * 3 + kx) * p.cin + ci) * p.cout;
+      const bool live = TAPS == 3 ? (half == 0 || r < 64) : (r < 64);   // warp-uniform (32-row granularity)
+      float* dst = p.G + ((long long)(TAPS == 3 ? ky * 3 + kx : 0) * p.cin + ci) * p.cout + ncol0;
 #pragma unroll
       for (int c0 = 0; c0 < N; c0 += 32) {
         uint32_t v[32];
@@ -393,15 +418,17 @@ __global__ void wgrad_unpack_kernel(const float* __restrict__ G, float* __restri
   dw[i] += G[((long long)t * cin + ci) * cout + co];
 }
 
-template <int N>
+template <int N, int TAPS>
 int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmDY, const WgradParams& p, int splits, cudaStream_t st) {
-  using Cfg = WgCfg<N>;
+  using Cfg = WgCfg<N, TAPS>;
   static bool attr_done = false;
   if (!attr_done) {
-    CRFR_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    CRFR_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<N, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   Cfg::kSmemBytes));
     attr_done = true;
   }
-  tc_wgrad_kernel<N><<<dim3(splits, 3, p.cin / 64), kConvThreads, Cfg::kSmemBytes, st>>>(tmX, tmDY, p);
+  const int gy = TAPS == 3 ? 3 : p.cout / N;
+  tc_wgrad_kernel<N, TAPS><<<dim3(splits, gy, p.cin / 64), kConvThreads, Cfg::kSmemBytes, st>>>(tmX, tmDY, p);
   CRFR_COUNT_LAUNCH();
   CRFR_LAUNCH_CHECK();
   return CRFR_OK;
@@ -418,7 +445,84 @@ bool spatial_ok(int h, int w, bool exact128) {
   return true;
 }
 
+int pick_tile_n(int n_total) {
+  const int cands[] = {256, 224, 192, 128, 96, 64, 32};
+  for (int c : cands)
+    if (n_total % c == 0) return c;
+  return 0;
+}
+
 }  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// generic launchers (internal.h)
+// ------------------------------------------------------------------------------------------------
+int crfr_tc_gemm(const TcGemm& g, cudaStream_t st) {
+  CRFR_CHECK_ARG(((uintptr_t)g.src & 15) == 0 && ((uintptr_t)g.out & 15) == 0 && ((uintptr_t)g.wt & 15) == 0 &&
+                     (g.src_ld & 7) == 0 && (g.out_ld & 3) == 0,
+                 "tc_gemm: pointers must be 16B aligned and ld a multiple of 8");
+  CRFR_CHECK_ARG(g.k_total % 64 == 0 && g.k_total > 0, "tc_gemm: K %d must be a multiple of 64", g.k_total);
+  const int tile_n = g.tile_n ? g.tile_n : pick_tile_n(g.n_total);
+  CRFR_CHECK_ARG(tile_n && g.n_total % tile_n == 0, "tc_gemm: N %d has no supported tile width", g.n_total);
+  Tiling t;
+  if (!make_tiling(g.n, g.h, g.w, &t)) {
+    crfr_set_error("tc_gemm: unsupported spatial size %dx%d", g.h, g.w);
+    return CRFR_EUNSUPPORTED;
+  }
+  CUtensorMap tmA, tmB;
+  CRFR_TRY(make_act_map(&tmA, g.src, g.n, g.h, g.w, g.k_total, g.src_ld, t.bw, t.bh, t.bn));
+  const int T = g.ksize * g.ksize;
+  CRFR_TRY(make_weight_map(&tmB, g.wt, (long long)T * g.n_total, g.k_total, tile_n));
+  ConvParams p;
+  p.n = g.n; p.h = g.h; p.w = g.w;
+  p.kchunks = g.k_total / 64; p.ksize = g.ksize; p.ntaps = T; p.pad = g.pad; p.sign = g.sign;
+  p.bw = t.bw; p.bh = t.bh; p.bn = t.bn; p.tiles_x = t.tiles_x; p.tiles_y = t.tiles_y; p.rows = t.rows;
+  p.n_total = g.n_total; p.out_ld = g.out_ld; p.out_f32 = g.out_f32; p.out = g.out; p.bias = g.bias;
+  const int tiles = t.tiles_x * t.tiles_y * t.tiles_n;
+  switch (tile_n) {
+    case 32: return launch_conv<32>(tmA, tmB, p, tiles, st);
+    case 64: return launch_conv<64>(tmA, tmB, p, tiles, st);
+    case 96: return launch_conv<96>(tmA, tmB, p, tiles, st);
+    case 128: return launch_conv<128>(tmA, tmB, p, tiles, st);
+    case 192: return launch_conv<192>(tmA, tmB, p, tiles, st);
+    case 224: return launch_conv<224>(tmA, tmB, p, tiles, st);
+    case 256: return launch_conv<256>(tmA, tmB, p, tiles, st);
+  }
+  crfr_set_error("tc_gemm: unsupported tile width %d", tile_n);
+  return CRFR_EUNSUPPORTED;
+}
+
+int crfr_tc_wgrad_raw(const TcWgrad& g, cudaStream_t st) {
+  CRFR_CHECK_ARG(((uintptr_t)g.x & 15) == 0 && ((uintptr_t)g.dy & 15) == 0 && (g.x_ld & 7) == 0 && (g.dy_ld & 7) == 0,
+                 "tc_wgrad: pointers must be 16B aligned and ld a multiple of 8");
+  CRFR_CHECK_ARG(g.cin % 64 == 0 && g.cout % 64 == 0, "tc_wgrad: channels must be multiples of 64");
+  Tiling t;
+  if (!make_tiling(g.n, g.h, g.w, &t) || t.bw * t.bh * t.bn != 128) {
+    crfr_set_error("tc_wgrad: unsupported spatial size %dx%d", g.h, g.w);
+    return CRFR_EUNSUPPORTED;
+  }
+  CUtensorMap tmX, tmDY;
+  CRFR_TRY(make_act_map(&tmX, g.x, g.n, g.h, g.w, g.cin, g.x_ld, t.bw, t.bh, t.bn));
+  CRFR_TRY(make_act_map(&tmDY, g.dy, g.n, g.h, g.w, g.cout, g.dy_ld, t.bw, t.bh, t.bn));
+  WgradParams p;
+  p.n = g.n; p.h = g.h; p.w = g.w;
+  p.bw = t.bw; p.bh = t.bh; p.bn = t.bn; p.tiles_x = t.tiles_x; p.tiles_y = t.tiles_y;
+  p.total_tiles = t.tiles_x * t.tiles_y * t.tiles_n;
+  p.cin = g.cin; p.cout = g.cout; p.G = g.G;
+  const int tile_n = (g.cout % 128 == 0) ? 128 : 64;
+  const int ctas_per_split = (g.taps3x3 ? 3 : g.cout / tile_n) * (g.cin / 64);
+  int splits = (148 * 2 + ctas_per_split - 1) / ctas_per_split;
+  if (splits > p.total_tiles) splits = p.total_tiles;
+  if (splits < 1) splits = 1;
+  if (g.taps3x3) {
+    if (g.cout == 64) return launch_wgrad<64, 3>(tmX, tmDY, p, splits, st);
+    if (g.cout == 128) return launch_wgrad<128, 3>(tmX, tmDY, p, splits, st);
+    crfr_set_error("tc_wgrad: 3x3 needs cout 64 or 128, got %d", g.cout);
+    return CRFR_EUNSUPPORTED;
+  }
+  if (tile_n == 128) return launch_wgrad<128, 1>(tmX, tmDY, p, splits, st);
+  return launch_wgrad<64, 1>(tmX, tmDY, p, splits, st);
+}
 
 int crfr_tc_supported(int op, int h, int w, int cin, int cout, int k, int stride, int pad) {
   if (k != 3 || stride != 1 || pad != 1) return 0;
@@ -438,37 +542,15 @@ size_t crfr_tc_workspace_bytes(const crfr_conv_desc* d) {
 
 int crfr_tc_conv(const crfr_conv_desc* d, int dgrad, const void* src, const void* w_packed, const float* bias,
                  void* dst, float* stats, float eps, void* ws, size_t ws_bytes, cudaStream_t st) {
-  const int ksrc = dgrad ? d->cout : d->cin;    // GEMM K per tap
-  const int nout = dgrad ? d->cin : d->cout;    // GEMM N
-  const int src_ld = dgrad ? d->out_ld : d->in_ld;
-  const int dst_ld = dgrad ? d->in_ld : d->out_ld;
-  CRFR_CHECK_ARG(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0 && ((uintptr_t)w_packed & 15) == 0 &&
-                     (src_ld & 7) == 0 && (dst_ld & 7) == 0,
-                 "tc_conv: pointers must be 16B aligned and ld a multiple of 8");
-  Tiling t;
-  if (!make_tiling(d->n, d->h, d->w, &t)) {
-    crfr_set_error("tc_conv: unsupported spatial size %dx%d", d->h, d->w);
-    return CRFR_EUNSUPPORTED;
-  }
-  CUtensorMap tmA, tmB;
-  CRFR_TRY(make_act_map(&tmA, src, d->n, d->h, d->w, ksrc, src_ld, t.bw, t.bh, t.bn));
-  const int T = d->k * d->k;
-  CRFR_TRY(make_weight_map(&tmB, w_packed, (long long)T * nout, ksrc, nout));
-  ConvParams p;
-  p.n = d->n; p.h = d->h; p.w = d->w;
-  p.kchunks = ksrc / 64; p.ksize = d->k; p.ntaps = T; p.pad = d->pad; p.sign = dgrad ? -1 : 1;
-  p.bw = t.bw; p.bh = t.bh; p.bn = t.bn; p.tiles_x = t.tiles_x; p.tiles_y = t.tiles_y; p.rows = t.rows;
-  p.out_ld = dst_ld; p.out = (bf16*)dst; p.bias = bias;
-  const int tiles = t.tiles_x * t.tiles_y * t.tiles_n;
-  switch (nout) {
-    case 64: CRFR_TRY(launch_conv<64>(tmA, tmB, p, tiles, st)); break;
-    case 128: CRFR_TRY(launch_conv<128>(tmA, tmB, p, tiles, st)); break;
-    case 192: CRFR_TRY(launch_conv<192>(tmA, tmB, p, tiles, st)); break;
-    case 256: CRFR_TRY(launch_conv<256>(tmA, tmB, p, tiles, st)); break;
-    default:
-      crfr_set_error("tc_conv: unsupported output channel count %d", nout);
-      return CRFR_EUNSUPPORTED;
-  }
+  TcGemm g;
+  g.src = src; g.n = d->n; g.h = d->h; g.w = d->w;
+  g.k_total = dgrad ? d->cout : d->cin;
+  g.src_ld = dgrad ? d->out_ld : d->in_ld;
+  g.wt = w_packed; g.ksize = d->k; g.pad = d->pad; g.sign = dgrad ? -1 : 1;
+  g.n_total = dgrad ? d->cin : d->cout;
+  g.tile_n = g.n_total;
+  g.out = dst; g.out_ld = dgrad ? d->in_ld : d->out_ld; g.out_f32 = 0; g.bias = bias;
+  CRFR_TRY(crfr_tc_gemm(g, st));
   if (stats && !dgrad)
     CRFR_TRY(crfr_norm_stats(dst, d->n, d->oh * d->ow, d->cout, d->out_ld, eps, stats, ws, ws_bytes, (void*)st));
   return CRFR_OK;
@@ -476,37 +558,16 @@ int crfr_tc_conv(const crfr_conv_desc* d, int dgrad, const void* src, const void
 
 int crfr_tc_wgrad(const crfr_conv_desc* d, const void* x, const void* dy, float* dw, void* ws, size_t ws_bytes,
                   cudaStream_t st) {
-  CRFR_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0 && (d->in_ld & 7) == 0 && (d->out_ld & 7) == 0,
-                 "tc_wgrad: pointers must be 16B aligned and ld a multiple of 8");
   const size_t need = sizeof(float) * (size_t)9 * d->cin * d->cout;
   if (!ws || ws_bytes < need) {
     crfr_set_error("tc_wgrad: workspace %zu < %zu", ws_bytes, need);
     return CRFR_EWORKSPACE;
   }
-  Tiling t;
-  if (!make_tiling(d->n, d->h, d->w, &t) || t.bw * t.bh * t.bn != 128) {
-    crfr_set_error("tc_wgrad: unsupported spatial size %dx%d", d->h, d->w);
-    return CRFR_EUNSUPPORTED;
-  }
-  CUtensorMap tmX, tmDY;
-  CRFR_TRY(make_act_map(&tmX, x, d->n, d->h, d->w, d->cin, d->in_ld, t.bw, t.bh, t.bn));
-  CRFR_TRY(make_act_map(&tmDY, dy, d->n, d->h, d->w, d->cout, d->out_ld, t.bw, t.bh, t.bn));
   CRFR_CUDA(cudaMemsetAsync(ws, 0, need, st));
-  WgradParams p;
-  p.n = d->n; p.h = d->h; p.w = d->w;
-  p.bw = t.bw; p.bh = t.bh; p.bn = t.bn; p.tiles_x = t.tiles_x; p.tiles_y = t.tiles_y;
-  p.total_tiles = t.tiles_x * t.tiles_y * t.tiles_n;
-  p.cin = d->cin; p.cout = d->cout; p.G = (float*)ws;
-  int ctas_per_split = 3 * (d->cin / 64);
-  int splits = (148 * 2 + ctas_per_split - 1) / ctas_per_split;
-  if (splits > p.total_tiles) splits = p.total_tiles;
-  if (splits < 1) splits = 1;
-  if (d->cout == 64) CRFR_TRY(launch_wgrad<64>(tmX, tmDY, p, splits, st));
-  else if (d->cout == 128) CRFR_TRY(launch_wgrad<128>(tmX, tmDY, p, splits, st));
-  else {
-    crfr_set_error("tc_wgrad: unsupported cout %d", d->cout);
-    return CRFR_EUNSUPPORTED;
-  }
+  TcWgrad g;
+  g.x = x; g.n = d->n; g.h = d->h; g.w = d->w; g.cin = d->cin; g.x_ld = d->in_ld;
+  g.dy = dy; g.cout = d->cout; g.dy_ld = d->out_ld; g.taps3x3 = 1; g.G = (float*)ws;
+  CRFR_TRY(crfr_tc_wgrad_raw(g, st));
   long long total = (long long)d->cout * d->cin * 9;
   wgrad_unpack_kernel<<<crfr_cdiv(total, 256), 256, 0, st>>>((const float*)ws, dw, d->cin, d->cout, 9);
   CRFR_COUNT_LAUNCH();

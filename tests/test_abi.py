@@ -70,8 +70,10 @@ def test_tcgen05_shape_support_table(lib):
     sup = lambda op, h, cin, cout, k=3, s=1, p=1: bool(lib.crfr_conv_engine_supported(_lib.ENGINE_TCGEN05, op, h, h, cin, cout, k, s, p))
     for op in (0, 1, 2):
         assert sup(op, 128, 64, 64) and sup(op, 32, 128, 128) and sup(op, 8, 128, 128) and sup(op, 32, 192, 64)
-    assert not sup(0, 128, 3, 64) and not sup(0, 128, 64, 3) and not sup(0, 128, 3, 64, 7, 4, 3)
-    assert not sup(0, 32, 128, 11, 1, 1, 0)
+    # edge layers ride the tensor cores through the lowered (im2col + GEMM) recipes
+    assert sup(0, 128, 3, 64) and sup(2, 128, 3, 64) and not sup(1, 128, 3, 64)
+    assert sup(0, 128, 64, 3) and sup(1, 128, 64, 3) and sup(0, 128, 3, 64, 7, 4, 3) and sup(1, 128, 3, 128, 7, 4, 3)
+    assert not sup(0, 32, 128, 11, 1, 1, 0) and sup(0, 100, 64, 64) and not sup(2, 100, 64, 64)
 
 
 def test_module_mirror_keeps_reference_interface():

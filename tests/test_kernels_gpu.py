@@ -37,9 +37,12 @@ DIRECT_SHAPES = [
 ]
 
 
+@pytest.mark.parametrize("engine", ["direct", "auto"])
 @pytest.mark.parametrize("cin,cout,k,stride,pad,h", DIRECT_SHAPES)
-def test_direct_conv_fwd_dgrad_wgrad(cuda, cin, cout, k, stride, pad, h):
+def test_edge_conv_fwd_dgrad_wgrad(cuda, cin, cout, k, stride, pad, h, engine):
+    """engine 'direct' = CUDA-core kernels; 'auto' = the lowered im2col + tcgen05 GEMM recipes where they apply."""
     ops, L = _ops(), _L()
+    ENG = L.ENGINE_DIRECT if engine == "direct" else L.ENGINE_AUTO
     g = torch.Generator().manual_seed(cin * 1000 + cout)
     n = 2
     x = bf16_round(torch.randn(n, cin, h, h, generator=g))
@@ -56,25 +59,27 @@ def test_direct_conv_fwd_dgrad_wgrad(cuda, cin, cout, k, stride, pad, h):
     out_ld = 4 if cout < 8 else (cout + 7) // 8 * 8
     xg = nhwc_from(x, in_ld)
     wp = ops.pack_conv_weight(w.cuda())
-    y, _, _ = ops.conv_fwd(xg, wp, cin, cout, k, stride, pad, bias=b.cuda(), engine=L.ENGINE_DIRECT)
+    y, _, _ = ops.conv_fwd(xg, wp, cin, cout, k, stride, pad, bias=b.cuda(), engine=ENG)
     assert rel_err(to_nchw(y, cout), y_ref) < BF16_TOL
-    _, yn, _ = ops.conv_fwd(xg, wp, cin, cout, k, stride, pad, bias=b.cuda(), engine=L.ENGINE_DIRECT, nchw_out=True)
+    _, yn, _ = ops.conv_fwd(xg, wp, cin, cout, k, stride, pad, bias=b.cuda(), engine=ENG, nchw_out=True)
     assert rel_err(yn, y_ref) < F32_TOL
 
     dyg = nhwc_from(dy, out_ld)
     wt = ops.pack_conv_weight(w.cuda(), for_dgrad=True)
-    dx = ops.conv_dgrad(dyg, wt, (n, h, h, in_ld), cin, cout, k, stride, pad, engine=L.ENGINE_DIRECT)
+    dx = ops.conv_dgrad(dyg, wt, (n, h, h, in_ld), cin, cout, k, stride, pad, engine=ENG)
     assert rel_err(to_nchw(dx, cin), xr.grad) < BF16_TOL
     if in_ld > cin:
         assert float(dx[..., cin:].float().abs().max()) == 0.0     # channel padding stays zero
-    dw, db = ops.conv_wgrad(xg, dyg, cin, cout, k, stride, pad, engine=L.ENGINE_DIRECT, want_bias=True)
+    dw, db = ops.conv_wgrad(xg, dyg, cin, cout, k, stride, pad, engine=ENG, want_bias=True)
     assert rel_err(dw, wr.grad) < F32_TOL
     assert rel_err(db, br.grad) < F32_TOL
 
 
-def test_direct_deconv(cuda):
+@pytest.mark.parametrize("engine", ["direct", "auto"])
+def test_deconv(cuda, engine):
     """ConvTranspose2d 7x7 s4 p2 op1 64->64 (FSRnet.py:436)."""
     ops, L = _ops(), _L()
+    ENG = L.ENGINE_DIRECT if engine == "direct" else L.ENGINE_AUTO
     g = torch.Generator().manual_seed(7)
     n, c, h = 2, 64, 8
     x = bf16_round(torch.randn(n, c, h, h, generator=g))
@@ -86,7 +91,7 @@ def test_direct_deconv(cuda):
     y_ref.backward(dy)
     xg = nhwc_from(x)
     wp = ops.pack_conv_weight(w.cuda(), transposed=True)
-    y, _, st = ops.conv_fwd(xg, wp, c, c, 7, 4, 2, bias=b.cuda(), engine=L.ENGINE_DIRECT, transposed=True,
+    y, _, st = ops.conv_fwd(xg, wp, c, c, 7, 4, 2, bias=b.cuda(), engine=ENG, transposed=True,
                             out_hw=(4 * h, 4 * h), want_stats=True)
     assert rel_err(to_nchw(y), y_ref) < BF16_TOL
     yb = to_nchw(y)
@@ -94,9 +99,9 @@ def test_direct_deconv(cuda):
     assert rel_err(st[..., 1], 1.0 / torch.sqrt(yb.var((2, 3), unbiased=False) + 1e-5)) < 1e-4
     dyg = nhwc_from(dy)
     wt = ops.pack_conv_weight(w.cuda(), for_dgrad=True, transposed=True)
-    dx = ops.conv_dgrad(dyg, wt, (n, h, h, c), c, c, 7, 4, 2, engine=L.ENGINE_DIRECT, transposed=True)
+    dx = ops.conv_dgrad(dyg, wt, (n, h, h, c), c, c, 7, 4, 2, engine=ENG, transposed=True)
     assert rel_err(to_nchw(dx), xr.grad) < BF16_TOL
-    dw, db = ops.conv_wgrad(xg, dyg, c, c, 7, 4, 2, engine=L.ENGINE_DIRECT, transposed=True, want_bias=True)
+    dw, db = ops.conv_wgrad(xg, dyg, c, c, 7, 4, 2, engine=ENG, transposed=True, want_bias=True)
     assert rel_err(dw, wr.grad) < F32_TOL
     assert rel_err(db, br.grad) < F32_TOL
 
