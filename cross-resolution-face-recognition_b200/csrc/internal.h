@@ -53,3 +53,8 @@ int crfr_lowered_dgrad(const crfr_conv_desc* d, const void* dy, const void* w_pa
                        size_t ws_bytes, cudaStream_t st);
 int crfr_lowered_wgrad(const crfr_conv_desc* d, const void* x, const void* dy, float* dw, void* ws, size_t ws_bytes,
                        cudaStream_t st);
+
+// rowconv.cu: persistent row-streaming kernel for 3x3 64->64 convolutions at width 128
+int crfr_rowconv_supported(int h, int w, int cin, int cout, int k, int stride, int pad);
+int crfr_rowconv(const void* src, int src_ld, int n, int h, const void* w_packed, int flip, const float* bias, void* dst,
+                 int dst_ld, cudaStream_t st);

@@ -133,40 +133,45 @@ cosine_topk_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
   const int kch = mp.kchunks;
 
   if (warp == 0) {
-    if (lane == 0) {
+    const bool leader = elect_one();
+    if (leader) {
       mbar_expect_tx(a_full, (uint32_t)kch * kTile);
       for (int kc = 0; kc < kch; ++kc) tma_load_2d(sA + kc * kTile, &tmP, a_full, kc * 64, ptile * 128);
-      int it = 0;
-      for (int b = 0; b < nblk; ++b)
-        for (int kc = 0; kc < kch; ++kc, ++it) {
-          const int s = it % kStages;
-          mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
+    }
+    int it = 0;
+    for (int b = 0; b < nblk; ++b)
+      for (int kc = 0; kc < kch; ++kc, ++it) {
+        const int s = it % kStages;
+        mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
+        if (leader) {
           mbar_expect_tx(&full[s], kTile);
           tma_load_2d(sB + s * kTile, &tmG, &full[s], kc * 64, (blk0 + b) * 128);
         }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, 128, 0, 0);
-      mbar_wait(a_full, 0);
-      int it = 0;
-      for (int b = 0; b < nblk; ++b) {
-        const int buf = b & 1;
-        mbar_wait(&acc_empty[buf], ((b >> 1) & 1) ^ 1);
-        tc_fence_after();
-        for (int kc = 0; kc < kch; ++kc, ++it) {
-          const int s = it % kStages;
-          mbar_wait(&full[s], (it / kStages) & 1);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(sA + kc * kTile), b_addr = smem_u32(sB + s * kTile);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem + buf * 128, make_smem_desc_sw128(a_addr + k * 32, 16, 1024),
-                      make_smem_desc_sw128(b_addr + k * 32, 16, 1024), idesc, (uint32_t)((kc | k) != 0));
-          umma_commit(&empty[s]);
-        }
-        umma_commit(&acc_full[buf]);
       }
+  } else if (warp == 1) {
+    const bool leader = elect_one();
+    const uint32_t idesc = make_idesc_bf16(128, 128, 0, 0);
+    const uint64_t adesc0 = make_smem_desc_sw128(smem_u32(sA), 16, 1024);
+    const uint64_t bdesc0 = make_smem_desc_sw128(smem_u32(sB), 16, 1024);
+    mbar_wait(a_full, 0);
+    int it = 0;
+    for (int b = 0; b < nblk; ++b) {
+      const int buf = b & 1;
+      mbar_wait(&acc_empty[buf], ((b >> 1) & 1) ^ 1);
+      tc_fence_after();
+      for (int kc = 0; kc < kch; ++kc, ++it) {
+        const int s = it % kStages;
+        mbar_wait(&full[s], (it / kStages) & 1);
+        tc_fence_after();
+        const uint64_t da = adesc0 + (uint64_t)((kc * kTile) >> 4), db = bdesc0 + (uint64_t)((s * kTile) >> 4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (leader) umma_bf16(tmem + buf * 128, da + 2 * k, db + 2 * k, idesc, (uint32_t)((kc | k) != 0));
+        if (leader) umma_commit(&empty[s]);
+        __syncwarp();
+      }
+      if (leader) umma_commit(&acc_full[buf]);
+      __syncwarp();
     }
   } else {
     const int q = warp & 3;

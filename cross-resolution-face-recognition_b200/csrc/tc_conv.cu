@@ -15,6 +15,7 @@
 //
 // ref: the nn.Conv2d sites of model/FSRnet.py (:79,85,110,114,351,387,411,432) that carry 99 % of the FLOPs.
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "crfr.h"
@@ -134,17 +135,21 @@ struct ConvCfg {
   static constexpr int kStageBytes = kATileBytes + kBTileBytes;
   static constexpr int kStages = (N <= 64) ? 4 : 3;
   static constexpr int kTmemCols = (N <= 32) ? 32 : (N <= 64) ? 64 : (N <= 128) ? 128 : 256;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kOutTiles = (N + 63) / 64;               // 64-channel sub-tiles staged for the TMA store
+  static constexpr int kOutBytes = kOutTiles * kATileBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static_assert(N % 32 == 0 && N <= 256, "tile width");
 };
 
 template <int N>
 __global__ void __launch_bounds__(kConvThreads, 1)
-tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, ConvParams p) {
+tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmY, ConvParams p) {
   using Cfg = ConvCfg<N>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* full = (uint64_t*)(base + Cfg::kStages * Cfg::kStageBytes);
+  uint8_t* sOut = base + Cfg::kStages * Cfg::kStageBytes;
+  uint64_t* full = (uint64_t*)(sOut + Cfg::kOutBytes);
   uint64_t* empty = full + Cfg::kStages;
   uint64_t* tmem_full = empty + Cfg::kStages;
   uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
@@ -175,37 +180,37 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int ncol0 = blockIdx.y * N;
 
   if (warp == 0) {
-    if (lane == 0) {
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % Cfg::kStages;
-        mbar_wait(&empty[s], ((it / Cfg::kStages) & 1) ^ 1);
+    const bool leader = elect_one();
+    for (int it = 0; it < iters; ++it) {
+      const int s = it % Cfg::kStages;
+      mbar_wait(&empty[s], ((it / Cfg::kStages) & 1) ^ 1);
+      const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
+      const int ky = tap / p.ksize, kx = tap - ky * p.ksize;
+      uint8_t* sa = base + s * Cfg::kStageBytes;
+      if (leader) {
         mbar_expect_tx(&full[s], a_bytes + Cfg::kBTileBytes);
-        const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
-        const int ky = tap / p.ksize, kx = tap - ky * p.ksize;
-        uint8_t* sa = base + s * Cfg::kStageBytes;
         tma_load_4d(sa, &tmA, &full[s], kc * 64, x0 + p.sign * (kx - p.pad), y0 + p.sign * (ky - p.pad), n0);
         tma_load_2d(sa + kATileBytes, &tmB, &full[s], kc * 64, tap * p.n_total + ncol0);
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
-      for (int it = 0; it < iters; ++it) {
-        const int s = it % Cfg::kStages;
-        mbar_wait(&full[s], (it / Cfg::kStages) & 1);
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(base + s * Cfg::kStageBytes);
-        const uint32_t b_addr = a_addr + kATileBytes;
+    const bool leader = elect_one();
+    const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
+    const uint64_t desc0 = make_smem_desc_sw128(smem_u32(base), 16, 1024);
+    for (int it = 0; it < iters; ++it) {
+      const int s = it % Cfg::kStages;
+      mbar_wait(&full[s], (it / Cfg::kStages) & 1);
+      tc_fence_after();
+      const uint64_t da = desc0 + (uint64_t)((s * Cfg::kStageBytes) >> 4);
+      const uint64_t db = da + (uint64_t)(kATileBytes >> 4);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t da = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
-          const uint64_t db = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-          umma_bf16(tmem, da, db, idesc, (uint32_t)((it | k) != 0));
-        }
-        umma_commit(&empty[s]);
-      }
-      umma_commit(tmem_full);
+      for (int k = 0; k < 4; ++k)
+        if (leader) umma_bf16(tmem, da + 2 * k, db + 2 * k, idesc, (uint32_t)((it | k) != 0));
+      if (leader) umma_commit(&empty[s]);
+      __syncwarp();
     }
+    if (leader) umma_commit(tmem_full);
+    __syncwarp();
   } else {
     const int q = warp & 3;
     const int r = q * 32 + lane;
@@ -217,7 +222,6 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int x = x0 + iw, y = y0 + ih, n = n0 + in;
     const bool valid = r < p.rows && x < p.w && y < p.h && n < p.n;
     const long long pix = ((long long)n * p.h + y) * p.w + x;
-    bf16* dst = (bf16*)p.out + pix * p.out_ld + ncol0;
     float* dstf = (float*)p.out + pix * p.out_ld + ncol0;
     const float* bias = p.bias ? p.bias + ncol0 : nullptr;
 #pragma unroll
@@ -225,19 +229,33 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t v[32];
       tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c0, v);
       tmem_ld_wait();
-      if (valid) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          float f[8];
+      for (int j = 0; j < 32; j += 8) {
+        float f[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j + e]) + (bias ? bias[c0 + j + e] : 0.f);
-          if (p.out_f32) {
+        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j + e]) + (bias ? bias[c0 + j + e] : 0.f);
+        if (p.out_f32) {
+          if (valid) {
             *reinterpret_cast<float4*>(dstf + c0 + j) = make_float4(f[0], f[1], f[2], f[3]);
             *reinterpret_cast<float4*>(dstf + c0 + j + 4) = make_float4(f[4], f[5], f[6], f[7]);
-          } else {
-            *reinterpret_cast<bf16x8*>(dst + c0 + j) = pack8(f);
           }
+        } else {
+          // stage the bf16 tile in the SWIZZLE_128B layout of the output tensor map: sub-tile (c / 64), row r
+          const int c = c0 + j;
+          uint8_t* srow = sOut + (c >> 6) * kATileBytes + r * 128;
+          *reinterpret_cast<bf16x8*>(srow + ((((c & 63) >> 3) ^ (r & 7)) << 4)) = pack8(f);
         }
+      }
+    }
+    if (!p.out_f32) {
+      fence_proxy_async();
+      named_bar_sync(1, 128);
+      if (warp == 2 && lane == 0) {   // one TMA store per 64-channel sub-tile; out-of-range pixels are clipped
+#pragma unroll
+        for (int t2 = 0; t2 < Cfg::kOutTiles; ++t2)
+          tma_store_4d(&tmY, sOut + t2 * kATileBytes, ncol0 + t2 * 64, x0, y0, n0);
+        tma_store_commit();
+        tma_store_wait_read<0>();
       }
     }
   }
@@ -250,14 +268,15 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 template <int N>
-int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, int tiles, cudaStream_t st) {
+int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const ConvParams& p, int tiles,
+                cudaStream_t st) {
   using Cfg = ConvCfg<N>;
   static bool attr_done = false;
   if (!attr_done) {
     CRFR_CUDA(cudaFuncSetAttribute(tc_conv_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_done = true;
   }
-  tc_conv_kernel<N><<<dim3(tiles, p.n_total / N), kConvThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
+  tc_conv_kernel<N><<<dim3(tiles, p.n_total / N), kConvThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, tmY, p);
   CRFR_COUNT_LAUNCH();
   CRFR_LAUNCH_CHECK();
   return CRFR_OK;
@@ -326,16 +345,17 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   const int my_tiles = first < p.total_tiles ? (p.total_tiles - first + step - 1) / step : 0;
 
   if (warp == 0) {
-    if (lane == 0) {
-      for (int i = 0; i < my_tiles; ++i) {
-        const int s = i % Cfg::kStages;
-        mbar_wait(&empty[s], ((i / Cfg::kStages) & 1) ^ 1);
+    const bool leader = elect_one();
+    for (int i = 0; i < my_tiles; ++i) {
+      const int s = i % Cfg::kStages;
+      mbar_wait(&empty[s], ((i / Cfg::kStages) & 1) ^ 1);
+      int t = first + i * step;
+      const int tx = t % p.tiles_x; t /= p.tiles_x;
+      const int ty = t % p.tiles_y; t /= p.tiles_y;
+      const int x0 = tx * p.bw, y0 = ty * p.bh, n0 = t * p.bn;
+      uint8_t* sb = base + s * Cfg::kStageBytes;
+      if (leader) {
         mbar_expect_tx(&full[s], Cfg::kStageBytes);
-        int t = first + i * step;
-        const int tx = t % p.tiles_x; t /= p.tiles_x;
-        const int ty = t % p.tiles_y; t /= p.tiles_y;
-        const int x0 = tx * p.bw, y0 = ty * p.bh, n0 = t * p.bn;
-        uint8_t* sb = base + s * Cfg::kStageBytes;
         if (TAPS == 3) {
 #pragma unroll
           for (int kx = 0; kx < 3; ++kx)
@@ -349,30 +369,30 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, N, 1, 1);
-      for (int i = 0; i < my_tiles; ++i) {
-        const int s = i % Cfg::kStages;
-        mbar_wait(&full[s], (i / Cfg::kStages) & 1);
-        tc_fence_after();
-        const uint32_t sb = smem_u32(base + s * Cfg::kStageBytes);
+    const bool leader = elect_one();
+    const uint32_t idesc = make_idesc_bf16(128, N, 1, 1);
+    // M = 128 = two 64-channel atoms LBO (= one 16 KB tile) apart: taps (0,1) in the first MMA; the second atom of
+    // the last MMA is whatever tile follows (rows 64..127 of that accumulator are never read)
+    const uint64_t desc0 = make_smem_desc_sw128(smem_u32(base), kTile16K, 1024);
+    for (int i = 0; i < my_tiles; ++i) {
+      const int s = i % Cfg::kStages;
+      mbar_wait(&full[s], (i / Cfg::kStages) & 1);
+      tc_fence_after();
+      const uint64_t a01 = desc0 + (uint64_t)((s * Cfg::kStageBytes) >> 4);
+      const uint64_t a2x = a01 + (uint64_t)((2 * kTile16K) >> 4);
+      const uint64_t db = a01 + (uint64_t)((TAPS * kTile16K) >> 4);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {  // 8 x 16 pixels
-          // M = 128 = two 64-channel atoms LBO (= one 16 KB tile) apart: taps (0,1) in the first MMA; the second
-          // atom of the last MMA is whatever tile follows (rows 64..127 of that accumulator are never read)
-          const uint64_t a01 = make_smem_desc_sw128(sb + k * 2048, kTile16K, 1024);
-          const uint64_t db = make_smem_desc_sw128(sb + TAPS * kTile16K + k * 2048, kTile16K, 1024);
-          const uint32_t acc = (uint32_t)((i | k) != 0);
-          umma_bf16(tmem, a01, db, idesc, acc);
-          if (TAPS == 3) {
-            const uint64_t a2x = make_smem_desc_sw128(sb + 2 * kTile16K + k * 2048, kTile16K, 1024);
-            umma_bf16(tmem + N, a2x, db, idesc, acc);
-          }
-        }
-        umma_commit(&empty[s]);
+      for (int k = 0; k < 8; ++k) {  // 8 x 16 pixels
+        const uint32_t acc = (uint32_t)((i | k) != 0);
+        if (leader) umma_bf16(tmem, a01 + k * (2048 >> 4), db + k * (2048 >> 4), idesc, acc);
+        if (TAPS == 3)
+          if (leader) umma_bf16(tmem + N, a2x + k * (2048 >> 4), db + k * (2048 >> 4), idesc, acc);
       }
-      umma_commit(tmem_full);
+      if (leader) umma_commit(&empty[s]);
+      __syncwarp();
     }
+    if (leader) umma_commit(tmem_full);
+    __syncwarp();
   } else if (my_tiles > 0) {
     const int q = warp & 3;
     const int r = q * 32 + lane;
@@ -469,8 +489,14 @@ int crfr_tc_gemm(const TcGemm& g, cudaStream_t st) {
     crfr_set_error("tc_gemm: unsupported spatial size %dx%d", g.h, g.w);
     return CRFR_EUNSUPPORTED;
   }
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmY;
   CRFR_TRY(make_act_map(&tmA, g.src, g.n, g.h, g.w, g.k_total, g.src_ld, t.bw, t.bh, t.bn));
+  if (!g.out_f32) {
+    CRFR_CHECK_ARG(tile_n % 64 == 0 && (g.out_ld & 7) == 0, "tc_gemm: bf16 output needs a tile width multiple of 64");
+    CRFR_TRY(make_act_map(&tmY, g.out, g.n, g.h, g.w, g.n_total, g.out_ld, t.bw, t.bh, t.bn));
+  } else {
+    tmY = tmA;   // unused by the fp32 epilogue
+  }
   const int T = g.ksize * g.ksize;
   CRFR_TRY(make_weight_map(&tmB, g.wt, (long long)T * g.n_total, g.k_total, tile_n));
   ConvParams p;
@@ -480,13 +506,13 @@ int crfr_tc_gemm(const TcGemm& g, cudaStream_t st) {
   p.n_total = g.n_total; p.out_ld = g.out_ld; p.out_f32 = g.out_f32; p.out = g.out; p.bias = g.bias;
   const int tiles = t.tiles_x * t.tiles_y * t.tiles_n;
   switch (tile_n) {
-    case 32: return launch_conv<32>(tmA, tmB, p, tiles, st);
-    case 64: return launch_conv<64>(tmA, tmB, p, tiles, st);
-    case 96: return launch_conv<96>(tmA, tmB, p, tiles, st);
-    case 128: return launch_conv<128>(tmA, tmB, p, tiles, st);
-    case 192: return launch_conv<192>(tmA, tmB, p, tiles, st);
-    case 224: return launch_conv<224>(tmA, tmB, p, tiles, st);
-    case 256: return launch_conv<256>(tmA, tmB, p, tiles, st);
+    case 32: return launch_conv<32>(tmA, tmB, tmY, p, tiles, st);
+    case 64: return launch_conv<64>(tmA, tmB, tmY, p, tiles, st);
+    case 96: return launch_conv<96>(tmA, tmB, tmY, p, tiles, st);
+    case 128: return launch_conv<128>(tmA, tmB, tmY, p, tiles, st);
+    case 192: return launch_conv<192>(tmA, tmB, tmY, p, tiles, st);
+    case 224: return launch_conv<224>(tmA, tmB, tmY, p, tiles, st);
+    case 256: return launch_conv<256>(tmA, tmB, tmY, p, tiles, st);
   }
   crfr_set_error("tc_gemm: unsupported tile width %d", tile_n);
   return CRFR_EUNSUPPORTED;
@@ -540,8 +566,24 @@ size_t crfr_tc_workspace_bytes(const crfr_conv_desc* d) {
   return sizeof(float) * (size_t)d->k * d->k * d->cin * d->cout + 256;  // wgrad scratch
 }
 
+static int rowconv_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CRFR_ROWCONV");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
+
 int crfr_tc_conv(const crfr_conv_desc* d, int dgrad, const void* src, const void* w_packed, const float* bias,
                  void* dst, float* stats, float eps, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (rowconv_enabled() && crfr_rowconv_supported(d->h, d->w, d->cin, d->cout, d->k, d->stride, d->pad)) {
+    CRFR_TRY(crfr_rowconv(src, dgrad ? d->out_ld : d->in_ld, d->n, d->h, w_packed, dgrad, bias, dst,
+                          dgrad ? d->in_ld : d->out_ld, st));
+    if (stats && !dgrad)
+      CRFR_TRY(crfr_norm_stats(dst, d->n, d->oh * d->ow, d->cout, d->out_ld, eps, stats, ws, ws_bytes, (void*)st));
+    return CRFR_OK;
+  }
   TcGemm g;
   g.src = src; g.n = d->n; g.h = d->h; g.w = d->w;
   g.k_total = dgrad ? d->cout : d->cin;
