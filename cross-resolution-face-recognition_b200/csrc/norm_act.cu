@@ -12,6 +12,14 @@ namespace {
 
 constexpr int kThreads = 256;
 
+__device__ __forceinline__ bf16x8 ld_stream(const bf16* p) {
+  uint4 u;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
+               : "l"(p));
+  return *reinterpret_cast<bf16x8*>(&u);
+}
+
 struct ChunkPlan {
   int chunks;      // partials per image
   int chunk_pix;   // pixels per chunk
@@ -59,14 +67,22 @@ stats_partial_kernel(const bf16* __restrict__ y, int ld, int hw, int c, int chun
   float acc[2][8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
-  for (int p = p0 + lane; p < p1; p += lanes) {
-    bf16x8 v = *reinterpret_cast<const bf16x8*>(base + (long long)p * ld);
-    float f[8];
-    unpack8(v, f);
+  for (int p = p0 + lane; p < p1; p += 4 * lanes) {
+    bf16x8 v[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      acc[0][j] += f[j];
-      acc[1][j] += f[j] * f[j];
+    for (int u = 0; u < 4; ++u)
+      if (p + u * lanes < p1) v[u] = ld_stream(base + (long long)(p + u * lanes) * ld);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (p + u * lanes < p1) {
+        float f[8];
+        unpack8(v[u], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[0][j] += f[j];
+          acc[1][j] += f[j] * f[j];
+        }
+      }
     }
   }
   cta_reduce_store<2>(acc, smem, cg, lane, lanes, c, partial + ((long long)n * gridDim.x + chunk) * 2 * c);
@@ -127,22 +143,37 @@ norm_act_fwd_kernel(const bf16* __restrict__ y, int y_ld, const float* __restric
     al[j] = relu ? 0.f : (alpha ? alpha[ch] : 1.f);
   }
   const long long pix0 = (long long)n * hw;
-  for (int p = p0 + lane; p < p1; p += lanes) {
-    float f[8], r[8];
-    unpack8(*reinterpret_cast<const bf16x8*>(y + (pix0 + p) * y_ld + cg * 8), f);
-    if (res) unpack8(*reinterpret_cast<const bf16x8*>(res + (pix0 + p) * res_ld + cg * 8), r);
+  for (int p = p0 + lane; p < p1; p += 4 * lanes) {
+    bf16x8 vy[4], vr[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float z = fmaf(f[j], sc[j], sh[j]);
-      if (res) z += r[j];
-      f[j] = z > 0.f ? z : z * al[j];
+    for (int u = 0; u < 4; ++u) {
+      const int pp = p + u * lanes;
+      if (pp < p1) {
+        vy[u] = ld_stream(y + (pix0 + pp) * y_ld + cg * 8);
+        if (res) vr[u] = ld_stream(res + (pix0 + pp) * res_ld + cg * 8);
+      }
     }
-    *reinterpret_cast<bf16x8*>(out + (pix0 + p) * out_ld + cg * 8) = pack8(f);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int pp = p + u * lanes;
+      if (pp < p1) {
+        float f[8], r[8];
+        unpack8(vy[u], f);
+        if (res) unpack8(vr[u], r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float z = fmaf(f[j], sc[j], sh[j]);
+          if (res) z += r[j];
+          f[j] = z > 0.f ? z : z * al[j];
+        }
+        *reinterpret_cast<bf16x8*>(out + (pix0 + pp) * out_ld + cg * 8) = pack8(f);
+      }
+    }
   }
 }
 
 // backward pass 1: dz = dout * act'(z) (stored, bf16), partial sums of dz, dz*xhat, dout*min(z,0)
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 norm_act_bwd_reduce_kernel(const bf16* __restrict__ da, int da_ld, const bf16* __restrict__ db, int db_ld,
                            const bf16* __restrict__ y, int y_ld, const float* __restrict__ stats,
                            const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -170,33 +201,50 @@ norm_act_bwd_reduce_kernel(const bf16* __restrict__ da, int da_ld, const bf16* _
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = acc[2][j] = 0.f;
   const long long pix0 = (long long)n * hw;
-  for (int p = p0 + lane; p < p1; p += lanes) {
-    float g[8], f[8], r[8], g2[8];
-    unpack8(*reinterpret_cast<const bf16x8*>(da + (pix0 + p) * da_ld + cg * 8), g);
-    if (db) {
-      unpack8(*reinterpret_cast<const bf16x8*>(db + (pix0 + p) * db_ld + cg * 8), g2);
+  for (int p = p0 + lane; p < p1; p += 2 * lanes) {
+    bf16x8 va[2], vb[2], vy[2], vr[2];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) g[j] += g2[j];
-    }
-    unpack8(*reinterpret_cast<const bf16x8*>(y + (pix0 + p) * y_ld + cg * 8), f);
-    if (act && res) unpack8(*reinterpret_cast<const bf16x8*>(res + (pix0 + p) * res_ld + cg * 8), r);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float d = g[j];
-      if (act) {
-        float z = fmaf(f[j], sc[j], sh[j]);
-        if (res) z += r[j];
-        if (!(z > 0.f)) {
-          acc[2][j] += d * z;
-          d *= al[j];
-        }
+    for (int u = 0; u < 2; ++u) {
+      const int pp = p + u * lanes;
+      if (pp < p1) {
+        va[u] = ld_stream(da + (pix0 + pp) * da_ld + cg * 8);
+        if (db) vb[u] = ld_stream(db + (pix0 + pp) * db_ld + cg * 8);
+        vy[u] = ld_stream(y + (pix0 + pp) * y_ld + cg * 8);
+        if (act && res) vr[u] = ld_stream(res + (pix0 + pp) * res_ld + cg * 8);
       }
-      d = bf16_round(d);
-      g[j] = d;
-      acc[0][j] += d;
-      acc[1][j] += d * (f[j] - mu[j]) * rs[j];
     }
-    *reinterpret_cast<bf16x8*>(dz + (pix0 + p) * dz_ld + cg * 8) = pack8(g);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int pp = p + u * lanes;
+      if (pp < p1) {
+        float g[8], f[8], r[8], g2[8];
+        unpack8(va[u], g);
+        if (db) {
+          unpack8(vb[u], g2);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g[j] += g2[j];
+        }
+        unpack8(vy[u], f);
+        if (act && res) unpack8(vr[u], r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float d = g[j];
+          if (act) {
+            float z = fmaf(f[j], sc[j], sh[j]);
+            if (res) z += r[j];
+            if (!(z > 0.f)) {
+              acc[2][j] += d * z;
+              d *= al[j];
+            }
+          }
+          d = bf16_round(d);
+          g[j] = d;
+          acc[0][j] += d;
+          acc[1][j] += d * (f[j] - mu[j]) * rs[j];
+        }
+        *reinterpret_cast<bf16x8*>(dz + (pix0 + pp) * dz_ld + cg * 8) = pack8(g);
+      }
+    }
   }
   cta_reduce_store<3>(acc, smem, cg, lane, lanes, c, partial + ((long long)n * gridDim.x + chunk) * 3 * c);
 }
@@ -235,37 +283,27 @@ bwd_fold_kernel(const float* __restrict__ partial, int chunks, int c, float inv_
   }
 }
 
-// per channel: sum tot over n in fixed order and accumulate into the parameter gradients
-__global__ void bwd_param_kernel(const float* __restrict__ tot, int n, int c, float* __restrict__ dgamma,
-                                 float* __restrict__ dbeta, float* __restrict__ dalpha) {
-  __shared__ float sm[8][3][32];
-  int cl = threadIdx.x & 31, lane = threadIdx.x >> 5;  // 32 channels x 8 n-lanes
-  int ch = blockIdx.x * 32 + cl;
-  float s[3] = {0.f, 0.f, 0.f};
-  if (ch < c)
-    for (int i = lane; i < n; i += 8)
-#pragma unroll
-      for (int k = 0; k < 3; ++k) s[k] += tot[(i * 3 + k) * c + ch];
-#pragma unroll
-  for (int k = 0; k < 3; ++k) sm[lane][k][cl] = s[k];
-  __syncthreads();
-  if (lane == 0 && ch < c) {
-    float t[3] = {0.f, 0.f, 0.f};
-    for (int l = 0; l < 8; ++l)
-#pragma unroll
-      for (int k = 0; k < 3; ++k) t[k] += sm[l][k][cl];
-    if (dbeta) dbeta[ch] += t[0];
-    if (dgamma) dgamma[ch] += t[1];
-    if (dalpha) dalpha[ch] += t[2];
-  }
-}
-
 // backward pass 2: dy = gamma * rstd * (dz - mean(dz) - xhat * mean(dz * xhat))
 __global__ void __launch_bounds__(kThreads)
 norm_act_bwd_apply_kernel(const bf16* __restrict__ dz, int dz_ld, const bf16* __restrict__ y, int y_ld,
                           const float* __restrict__ stats, const float* __restrict__ bstats,
                           const float* __restrict__ gamma, bf16* __restrict__ dy, int dy_ld, int hw, int c,
-                          int chunk_pix) {
+                          int chunk_pix, const float* __restrict__ tot, int nimg, float* __restrict__ dgamma,
+                          float* __restrict__ dbeta, float* __restrict__ dalpha) {
+  // CTA (0,0) also folds the per-image totals into the parameter gradients, in fixed order (deterministic)
+  if (blockIdx.x == 0 && blockIdx.y == 0 && (dgamma || dbeta || dalpha)) {
+    for (int ch = threadIdx.x; ch < c; ch += kThreads) {
+      float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+      for (int i = 0; i < nimg; ++i) {
+        t0 += tot[(i * 3 + 0) * c + ch];
+        t1 += tot[(i * 3 + 1) * c + ch];
+        t2 += tot[(i * 3 + 2) * c + ch];
+      }
+      if (dbeta) dbeta[ch] += t0;
+      if (dgamma) dgamma[ch] += t1;
+      if (dalpha) dalpha[ch] += t2;
+    }
+  }
   const int groups = c >> 3, lanes = kThreads / groups;
   const int cg = threadIdx.x % groups, lane = threadIdx.x / groups;
   const int n = blockIdx.y;
@@ -281,16 +319,31 @@ norm_act_bwd_apply_kernel(const bf16* __restrict__ dz, int dz_ld, const bf16* __
     m2[j] = bstats[2 * (n * c + ch) + 1];
   }
   const long long pix0 = (long long)n * hw;
-  for (int p = p0 + lane; p < p1; p += lanes) {
-    float d[8], f[8];
-    unpack8(*reinterpret_cast<const bf16x8*>(dz + (pix0 + p) * dz_ld + cg * 8), d);
-    unpack8(*reinterpret_cast<const bf16x8*>(y + (pix0 + p) * y_ld + cg * 8), f);
+  for (int p = p0 + lane; p < p1; p += 4 * lanes) {
+    bf16x8 vd[4], vy[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float xh = (f[j] - mu[j]) * rs[j];
-      d[j] = gr[j] * (d[j] - m1[j] - xh * m2[j]);
+    for (int u = 0; u < 4; ++u) {
+      const int pp = p + u * lanes;
+      if (pp < p1) {
+        vd[u] = ld_stream(dz + (pix0 + pp) * dz_ld + cg * 8);
+        vy[u] = ld_stream(y + (pix0 + pp) * y_ld + cg * 8);
+      }
     }
-    *reinterpret_cast<bf16x8*>(dy + (pix0 + p) * dy_ld + cg * 8) = pack8(d);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int pp = p + u * lanes;
+      if (pp < p1) {
+        float d[8], f[8];
+        unpack8(vd[u], d);
+        unpack8(vy[u], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float xh = (f[j] - mu[j]) * rs[j];
+          d[j] = gr[j] * (d[j] - m1[j] - xh * m2[j]);
+        }
+        *reinterpret_cast<bf16x8*>(dy + (pix0 + pp) * dy_ld + cg * 8) = pack8(d);
+      }
+    }
   }
 }
 
@@ -379,14 +432,9 @@ extern "C" int crfr_norm_act_bwd(const void* dout_a, int da_ld, const void* dout
   bwd_fold_kernel<<<n, kThreads, 0, st>>>(partial, pl.chunks, c, 1.f / (float)hw, bstats, tot);
   CRFR_COUNT_LAUNCH();
   CRFR_LAUNCH_CHECK();
-  if (dgamma || dbeta || dalpha) {
-    bwd_param_kernel<<<crfr_cdiv(c, 32), 256, 0, st>>>(tot, n, c, dgamma, dbeta, dalpha);
-    CRFR_COUNT_LAUNCH();
-    CRFR_LAUNCH_CHECK();
-  }
   norm_act_bwd_apply_kernel<<<dim3(pl.chunks, n), kThreads, 0, st>>>((const bf16*)dz, dz_ld, (const bf16*)y, y_ld,
                                                                      stats, bstats, gamma, (bf16*)dy, dy_ld, hw, c,
-                                                                     pl.chunk_pix);
+                                                                     pl.chunk_pix, tot, n, dgamma, dbeta, dalpha);
   CRFR_COUNT_LAUNCH();
   CRFR_LAUNCH_CHECK();
   return CRFR_OK;
