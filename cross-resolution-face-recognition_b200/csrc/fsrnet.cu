@@ -288,7 +288,8 @@ struct Net {
     // shared scratch: norm partials / wgrad accumulators of the largest layer
     scratch_bytes = crfr_norm_ws_bytes(B, S * S, 128) + sizeof(float) * 9 * 192 * 128 + 4096;
     {  // the lowered edge layers (lowered_conv.cu) stage their im2col / partial-product buffers here
-      const crfr_conv_desc shapes[4] = {
+      const crfr_conv_desc shapes[5] = {
+          {B, S, S, 64, 64, 3, 1, 1, S, S, 64, 64, 0},          // residual stacks (row-streaming kernels' scratch)
           {B, S, S, 3, 64, 3, 1, 1, S, S, 4, 64, 0},            // coarse conv_input
           {B, S, S, 64, 3, 3, 1, 1, S, S, 64, 4, 0},            // conv_mid / conv_out
           {B, S, S, 3, 128, 7, 4, 3, S / 4, S / 4, 4, 128, 0},  // stems

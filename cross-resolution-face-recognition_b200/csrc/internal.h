@@ -56,5 +56,11 @@ int crfr_lowered_wgrad(const crfr_conv_desc* d, const void* x, const void* dy, f
 
 // rowconv.cu: persistent row-streaming kernel for 3x3 64->64 convolutions at width 128
 int crfr_rowconv_supported(int h, int w, int cin, int cout, int k, int stride, int pad);
+size_t crfr_rowconv_ws_bytes(int n, int h);
+// rowwgrad.cu: persistent row-streaming weight gradient of the same shape (deterministic slab reduction)
+int crfr_rowwgrad_supported(int h, int w, int cin, int cout, int k, int stride, int pad);
+size_t crfr_rowwgrad_ws_bytes(int n, int h);
+int crfr_rowwgrad(const void* x, int x_ld, const void* dy, int dy_ld, int n, int h, float* dw, void* ws,
+                  size_t ws_bytes, cudaStream_t st);
 int crfr_rowconv(const void* src, int src_ld, int n, int h, const void* w_packed, int flip, const float* bias, void* dst,
-                 int dst_ld, cudaStream_t st);
+                 int dst_ld, float* stats, float eps, void* ws, size_t ws_bytes, cudaStream_t st);

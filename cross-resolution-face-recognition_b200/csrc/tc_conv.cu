@@ -563,7 +563,14 @@ int crfr_tc_supported(int op, int h, int w, int cin, int cout, int k, int stride
 }
 
 size_t crfr_tc_workspace_bytes(const crfr_conv_desc* d) {
-  return sizeof(float) * (size_t)d->k * d->k * d->cin * d->cout + 256;  // wgrad scratch
+  size_t wg = sizeof(float) * (size_t)d->k * d->k * d->cin * d->cout + 256;  // wgrad scratch
+  if (crfr_rowconv_supported(d->h, d->w, d->cin, d->cout, d->k, d->stride, d->pad)) {
+    const size_t rc = crfr_rowconv_ws_bytes(d->n, d->h);
+    if (rc > wg) wg = rc;
+    const size_t rw = crfr_rowwgrad_ws_bytes(d->n, d->h);
+    if (rw > wg) wg = rw;
+  }
+  return wg;
 }
 
 static int rowconv_enabled() {
@@ -578,11 +585,8 @@ static int rowconv_enabled() {
 int crfr_tc_conv(const crfr_conv_desc* d, int dgrad, const void* src, const void* w_packed, const float* bias,
                  void* dst, float* stats, float eps, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (rowconv_enabled() && crfr_rowconv_supported(d->h, d->w, d->cin, d->cout, d->k, d->stride, d->pad)) {
-    CRFR_TRY(crfr_rowconv(src, dgrad ? d->out_ld : d->in_ld, d->n, d->h, w_packed, dgrad, bias, dst,
-                          dgrad ? d->in_ld : d->out_ld, st));
-    if (stats && !dgrad)
-      CRFR_TRY(crfr_norm_stats(dst, d->n, d->oh * d->ow, d->cout, d->out_ld, eps, stats, ws, ws_bytes, (void*)st));
-    return CRFR_OK;
+    return crfr_rowconv(src, dgrad ? d->out_ld : d->in_ld, d->n, d->h, w_packed, dgrad, bias, dst,
+                        dgrad ? d->in_ld : d->out_ld, dgrad ? nullptr : stats, eps, ws, ws_bytes, st);
   }
   TcGemm g;
   g.src = src; g.n = d->n; g.h = d->h; g.w = d->w;
@@ -600,6 +604,8 @@ int crfr_tc_conv(const crfr_conv_desc* d, int dgrad, const void* src, const void
 
 int crfr_tc_wgrad(const crfr_conv_desc* d, const void* x, const void* dy, float* dw, void* ws, size_t ws_bytes,
                   cudaStream_t st) {
+  if (rowconv_enabled() && crfr_rowwgrad_supported(d->h, d->w, d->cin, d->cout, d->k, d->stride, d->pad))
+    return crfr_rowwgrad(x, d->in_ld, dy, d->out_ld, d->n, d->h, dw, ws, ws_bytes, st);
   const size_t need = sizeof(float) * (size_t)9 * d->cin * d->cout;
   if (!ws || ws_bytes < need) {
     crfr_set_error("tc_wgrad: workspace %zu < %zu", ws_bytes, need);

@@ -164,3 +164,35 @@ def test_matcher_ties_and_sharding(cuda):
         parts_v.append(v); parts_i.append(i)
     mv, mi = ops.topk_merge(torch.stack(parts_v), torch.stack(parts_i), 5)
     assert torch.equal(mi, full_i) and torch.equal(mv, full_v)
+
+
+@pytest.mark.parametrize("n,h", [(200, 2), (7, 50), (300, 1), (3, 128), (40, 16)])
+def test_rowconv_ragged_row_ranges(cuda, n, h):
+    """Row-streaming kernels (rowconv.cu / rowwgrad.cu, width 128, 64 -> 64): CTAs that own single rows, whole
+    images or several images; forward + fused InstanceNorm statistics, dgrad and wgrad against fp32 PyTorch."""
+    from crfr_b200 import _lib as L, ops
+    g = torch.Generator().manual_seed(100 + n)
+    c, w_ = 64, 128
+    x = bf16_round(torch.randn(n, c, h, w_, generator=g))
+    w = bf16_round(torch.randn(c, c, 3, 3, generator=g) * 0.05)
+    dy = bf16_round(torch.randn(n, c, h, w_, generator=g))
+    xr, wr = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    ref = F.conv2d(xr, wr, None, 1, 1)
+    ref.backward(dy)
+    y, _, st = ops.conv_fwd(nhwc_from(x), ops.pack_conv_weight(w.cuda()), c, c, 3, 1, 1, engine=L.ENGINE_TCGEN05,
+                            want_stats=True)
+    torch.cuda.synchronize()
+    assert rel_err(to_nchw(y), ref) < BF16_TOL
+    yb = to_nchw(y)
+    assert rel_err(st[..., 0], yb.mean((2, 3))) < 1e-3
+    assert rel_err(st[..., 1], 1.0 / torch.sqrt(yb.var((2, 3), unbiased=False) + 1e-5)) < 1e-3
+    dx = ops.conv_dgrad(nhwc_from(dy), ops.pack_conv_weight(w.cuda(), for_dgrad=True), (n, h, w_, c), c, c, 3, 1, 1,
+                        engine=L.ENGINE_TCGEN05)
+    assert rel_err(to_nchw(dx), xr.grad) < BF16_TOL
+    dw, _ = ops.conv_wgrad(nhwc_from(x), nhwc_from(dy), c, c, 3, 1, 1, engine=L.ENGINE_TCGEN05)
+    assert rel_err(dw, wr.grad) < F32_TOL
+    # run-to-run determinism of the reductions (fixed-order partials, no float atomics)
+    dw2, _ = ops.conv_wgrad(nhwc_from(x), nhwc_from(dy), c, c, 3, 1, 1, engine=L.ENGINE_TCGEN05)
+    _, _, st2 = ops.conv_fwd(nhwc_from(x), ops.pack_conv_weight(w.cuda()), c, c, 3, 1, 1, engine=L.ENGINE_TCGEN05,
+                             want_stats=True)
+    assert torch.equal(dw, dw2) and torch.equal(st, st2)

@@ -28,11 +28,16 @@ ws = torch.empty(L.lib().crfr_fsrnet_workspace_bytes(B, 128, 1), dtype=torch.uin
 losses = torch.zeros(5, device="cuda")
 pt, gt = M._ParamTable([p.detach() for p in params]), M._ParamTable(grads)
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+import time
+host = []
 ev[0].record()
 for i in range(reps):
+    t0 = time.perf_counter()
     L.call("crfr_fsrnet_train_step", L.ENGINE_AUTO, pt.arr, gt.arr, C.byref(io), losses.data_ptr(), ws.data_ptr(),
            ws.numel(), ops.stream())
+    host.append((time.perf_counter() - t0) * 1e3)
     ev[i + 1].record()
 torch.cuda.synchronize()
+print("host enqueue ms per chunk step:", host)
 print("losses", losses.tolist())
 print("ms per chunk step:", [ev[i].elapsed_time(ev[i + 1]) for i in range(reps)], "launches", L.lib().crfr_launch_count())
