@@ -37,6 +37,7 @@ SIGNATURES = {
     "crfr_conv_dgrad": (ci, [ci, C.POINTER(ConvDesc), vp, vp, ci, vp, vp, csz, vp]),
     "crfr_conv_wgrad": (ci, [ci, C.POINTER(ConvDesc), vp, vp, vp, vp, vp, csz, vp]),
     "crfr_conv_workspace_bytes": (csz, [C.POINTER(ConvDesc)]),
+    "crfr_norm_workspace_bytes": (csz, [ci, ci, ci]),
     "crfr_norm_stats": (ci, [vp, ci, ci, ci, ci, cf, vp, vp, csz, vp]),
     "crfr_norm_act_fwd": (ci, [vp, ci, vp, vp, vp, vp, ci, vp, ci, vp, ci, ci, ci, ci, vp]),
     "crfr_norm_act_bwd": (ci, [vp, ci, vp, ci, vp, ci, vp, vp, vp, vp, ci, vp, ci, vp, ci, vp, ci, vp, vp, vp, ci, ci,

@@ -20,33 +20,38 @@ namespace {
 // ---------------------------------------------------------------------------------------------------------
 // gather kernels
 // ---------------------------------------------------------------------------------------------------------
-// P[o][tap*C + c] = x[o*stride + sign*(tap - pad)][c]   (zero outside the image, zero for k >= T*C); kpad % 8 == 0
-__global__ void im2col_small_kernel(const bf16* __restrict__ x, int x_ld, int C, int h, int w, int oh, int ow, int ks,
-                                    int stride, int pad, int sign, bf16* __restrict__ P, int kpad, long long total) {
+// P[o][tap*3 + c] = x[o*stride + sign*(tap - pad)][c] for 3-channel images stored 4 bf16 per pixel (zero outside the
+// image and for k >= T*3); kpad % 8 == 0.  One thread writes one 16-byte group of a row, so a warp writes whole
+// 128-byte lines; the 8 values of a group come from at most 4 taps, each fetched as one 8-byte pixel.
+__global__ void im2col_small_kernel(const bf16* __restrict__ x, int h, int w, int oh, int ow, int ks, int stride, int pad,
+                                    int sign, bf16* __restrict__ P, int kpad, long long total) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int groups = kpad >> 3;
   const int g = (int)(i % groups);
   long long o = i / groups;
-  const int ox = (int)(o % ow);
-  long long q = o / ow;
-  const int oy = (int)(q % oh);
-  const long long n = q / oh;
-  const int kmax = ks * ks * C;
-  float f[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int k = g * 8 + j;
-    float v = 0.f;
-    if (k < kmax) {
-      const int tap = k / C, c = k - tap * C;
+  const int k0 = g * 8, kmax = ks * ks * 3;
+  uint32_t out[4] = {0u, 0u, 0u, 0u};
+  if (k0 < kmax) {
+    const int ox = (int)(o % ow);
+    long long q = o / ow;
+    const int oy = (int)(q % oh);
+    const long long n = q / oh;
+    const int t0 = k0 / 3, t1 = min((k0 + 7) / 3, ks * ks - 1);
+    for (int tap = t0; tap <= t1; ++tap) {
       const int ky = tap / ks, kx = tap - ky * ks;
       const int y = oy * stride + sign * (ky - pad), xx = ox * stride + sign * (kx - pad);
-      if (y >= 0 && y < h && xx >= 0 && xx < w) v = __bfloat162float(x[((n * h + y) * w + xx) * x_ld + c]);
+      uint2 v = make_uint2(0u, 0u);
+      if (y >= 0 && y < h && xx >= 0 && xx < w) v = *reinterpret_cast<const uint2*>(x + ((n * h + y) * w + xx) * 4);
+      const uint32_t ch[3] = {v.x & 0xffffu, v.x >> 16, v.y & 0xffffu};
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int j = tap * 3 + c - k0;
+        if (j >= 0 && j < 8) out[j >> 1] |= ch[c] << ((j & 1) * 16);
+      }
     }
-    f[j] = v;
   }
-  *reinterpret_cast<bf16x8*>(P + o * kpad + g * 8) = pack8(f);
+  *reinterpret_cast<uint4*>(P + o * kpad + g * 8) = make_uint4(out[0], out[1], out[2], out[3]);
 }
 
 // dst[P][c] = bias[c] + sum_{tap : t = P + sgn*(pad - tap), t % stride == 0, t/stride inside} src[t/stride][tap*C + c]
@@ -212,7 +217,8 @@ int crfr_lowered_recipe(const crfr_conv_desc* d) {
     if (d->k == 3 && d->stride == 1 && d->pad == 1 && d->cin == 3 && d->in_ld == 4 && d->cout % 64 == 0 && d->cout <= 256 &&
         tcgen05_spatial_ok(d->h, d->w))
       return 1;
-    if (d->k == 3 && d->stride == 1 && d->pad == 1 && d->cout == 3 && d->cin == 64 && tcgen05_spatial_ok(d->h, d->w))
+    if (d->k == 3 && d->stride == 1 && d->pad == 1 && d->cout == 3 && d->cin == 64 && d->out_ld == 4 &&
+        tcgen05_spatial_ok(d->h, d->w))
       return 2;
     if (d->k == 7 && d->stride == 4 && d->pad == 3 && d->cin == 3 && d->in_ld == 4 && (d->cout == 64 || d->cout == 128) &&
         tcgen05_spatial_ok(d->oh, d->ow))
@@ -260,7 +266,7 @@ int crfr_lowered_fwd(const crfr_conv_desc* d, const void* x, const void* w_packe
     const long long opix = (long long)d->n * d->oh * d->ow;
     TAKE(P, bf16, A, (size_t)opix * kp * 2);
     TAKE(Wg, bf16, A, (size_t)d->cout * kp * 2);
-    LAUNCH(im2col_small_kernel, opix * (kp / 8), st, (const bf16*)x, d->in_ld, 3, d->h, d->w, d->oh, d->ow, d->k, d->stride,
+    LAUNCH(im2col_small_kernel, opix * (kp / 8), st, (const bf16*)x, d->h, d->w, d->oh, d->ow, d->k, d->stride,
            d->pad, 1, P, kp, opix * (kp / 8));
     LAUNCH(repack_tapmajor_kernel, d->cout * kp, st, (const bf16*)w_packed, T, d->cout, 3, cin_pad, Wg, d->cout, kp);
     TcGemm g{P, d->n, d->oh, d->ow, kp, kp, Wg, 1, 0, 1, d->cout, 0, y, d->out_ld, 0, bias};
@@ -311,7 +317,7 @@ int crfr_lowered_dgrad(const crfr_conv_desc* d, const void* dy, const void* w_pa
     const long long pix = (long long)d->n * d->h * d->w;
     TAKE(R, bf16, A, (size_t)pix * 64 * 2);
     TAKE(Wd, bf16, A, (size_t)64 * 64 * 2);
-    LAUNCH(im2col_small_kernel, pix * 8, st, (const bf16*)dy, d->out_ld, 3, d->h, d->w, d->h, d->w, 3, 1, 1, -1, R, 64,
+    LAUNCH(im2col_small_kernel, pix * 8, st, (const bf16*)dy, d->h, d->w, d->h, d->w, 3, 1, 1, -1, R, 64,
            pix * 8);
     LAUNCH(repack_tapmajor_kernel, 64 * 64, st, (const bf16*)w_packed_t, T, 64, 3, cout_pad, Wd, 64, 64);
     TcGemm g{R, d->n, d->h, d->w, 64, 64, Wd, 1, 0, 1, 64, 64, dx, d->in_ld, 0, nullptr};
@@ -362,7 +368,7 @@ int crfr_lowered_wgrad(const crfr_conv_desc* d, const void* x, const void* dy, f
     const long long opix = (long long)d->n * d->oh * d->ow;
     TAKE(P, bf16, A, (size_t)opix * kp * 2);
     TAKE(G, float, A, (size_t)kp * d->cout * 4);
-    LAUNCH(im2col_small_kernel, opix * (kp / 8), st, (const bf16*)x, d->in_ld, 3, d->h, d->w, d->oh, d->ow, d->k, d->stride,
+    LAUNCH(im2col_small_kernel, opix * (kp / 8), st, (const bf16*)x, d->h, d->w, d->oh, d->ow, d->k, d->stride,
            d->pad, 1, P, kp, opix * (kp / 8));
     CRFR_CUDA(cudaMemsetAsync(G, 0, (size_t)kp * d->cout * 4, st));
     TcWgrad g{P, d->n, d->oh, d->ow, kp, kp, dy, d->cout, d->out_ld, 0, G};
@@ -374,7 +380,7 @@ int crfr_lowered_wgrad(const crfr_conv_desc* d, const void* x, const void* dy, f
     const long long pix = (long long)d->n * d->h * d->w;
     TAKE(R, bf16, A, (size_t)pix * 64 * 2);
     TAKE(G, float, A, (size_t)64 * 64 * 4);
-    LAUNCH(im2col_small_kernel, pix * 8, st, (const bf16*)dy, d->out_ld, 3, d->h, d->w, d->h, d->w, 3, 1, 1, -1, R, 64,
+    LAUNCH(im2col_small_kernel, pix * 8, st, (const bf16*)dy, d->h, d->w, d->h, d->w, 3, 1, 1, -1, R, 64,
            pix * 8);
     CRFR_CUDA(cudaMemsetAsync(G, 0, (size_t)64 * 64 * 4, st));
     TcWgrad g{x, d->n, d->h, d->w, 64, d->in_ld, R, 64, 64, 0, G};

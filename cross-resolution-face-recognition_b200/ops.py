@@ -140,8 +140,7 @@ def engine_supported(engine, op, h, w, cin, cout, k, stride, pad):
 
 # ---------------------------------------------------------------------------------------------- norm + act
 def _norm_ws(n, hw, c):
-    chunks = max(1, min((148 * 4 + n - 1) // n, (hw + 255) // 256, 2048))
-    return workspace(4 * (n * (chunks + 1) * 3 * c + n * c * 5) + (1 << 16))
+    return workspace(L.lib().crfr_norm_workspace_bytes(n, hw, c) + 1024)
 
 
 def norm_stats(y, c=None, eps=1e-5, groups_as_batch=False):

@@ -76,7 +76,9 @@ size_t crfr_conv_workspace_bytes(const crfr_conv_desc* d);
 /* ref: nn.InstanceNorm2d (FSRnet.py:81,87,112,115,319,347,385,434), nn.PReLU (:84,88,113,314,346,386,433),
  *      residual add (:96,132); with groups==1 over the whole batch it is train-mode nn.BatchNorm2d + ReLU
  *      (model/resnet.py:24-28).
- * stats[n][c][2] (mean, rstd) over hw pixels of image n. */
+ * stats[n][c][2] (mean, rstd) over hw pixels of image n.
+ * crfr_norm_workspace_bytes: scratch needed by crfr_norm_stats / crfr_norm_act_bwd for this shape. */
+size_t crfr_norm_workspace_bytes(int n, int hw, int c);
 int crfr_norm_stats(const void* y, int n, int hw, int c, int ld, float eps, float* stats, void* ws, size_t ws_bytes,
                     void* stream);
 /* out = act(gamma*(y-mean)*rstd + beta + res); gamma/beta NULL = non-affine; alpha NULL = no activation;
