@@ -24,6 +24,13 @@ class FsrnetIO(C.Structure):
                 ("hr", vp), ("heatmap", vp), ("labels", vp), ("loss_div", cf), ("w_pix", cf), ("bucket_events", vp * 3)]
 
 
+class ResnetIO(C.Structure):
+    _fields_ = [("batch", ci), ("size", ci), ("x", vp), ("emb", vp), ("feat", vp * 4), ("training", ci),
+                ("momentum", cf), ("eps", cf)]
+
+
+RESNET34_NPARAMS, RESNET34_NBN = 114, 38
+
 # name -> (restype, argtypes); every symbol declared in include/crfr.h
 SIGNATURES = {
     "crfr_last_error": (C.c_char_p, []),
@@ -66,6 +73,11 @@ SIGNATURES = {
     "crfr_fsrnet_forward": (ci, [ci, vp, C.POINTER(FsrnetIO), ci, vp, csz, vp]),
     "crfr_fsrnet_backward": (ci, [ci, vp, vp, C.POINTER(FsrnetIO), vp, vp, vp, vp, vp, csz, vp]),
     "crfr_fsrnet_train_step": (ci, [ci, vp, vp, C.POINTER(FsrnetIO), vp, vp, csz, vp]),
+    "crfr_bn_update_running": (ci, [vp, vp, vp, vp, ci, cll, cf, cf, vp]),
+    "crfr_bn_running_to_stats": (ci, [vp, vp, ci, cf, vp, vp]),
+    "crfr_resnet34_workspace_bytes": (csz, [ci, ci, ci]),
+    "crfr_resnet34_forward": (ci, [ci, vp, vp, C.POINTER(ResnetIO), vp, csz, vp]),
+    "crfr_resnet34_backward": (ci, [ci, vp, vp, C.POINTER(ResnetIO), vp, vp, vp, csz, vp]),
 }
 
 _lib = None

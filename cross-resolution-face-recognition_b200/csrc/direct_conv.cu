@@ -215,20 +215,23 @@ wgrad_kernel(Geo g, const bf16* __restrict__ small, int small_ld, int A, const b
 
 // out[c] += sum over pixels of t[pix][c]
 __global__ void __launch_bounds__(256)
-colsum_kernel(const bf16* __restrict__ t, int ld, int c, long long npix, int chunk_pix, float* __restrict__ out) {
+colsum_kernel(const bf16* __restrict__ t, int ld, int c_total, long long npix, int chunk_pix, float* __restrict__ out) {
   extern __shared__ float sm[];  // [lanes][c]
+  // blockIdx.y selects a block of up to 256 channels
+  const int coff = blockIdx.y * 256;
+  const int c = min(256, c_total - coff);
   const int lanes = 256 / c > 0 ? 256 / c : 1;
   const int ch = threadIdx.x % c, lane = threadIdx.x / c;
   float acc = 0.f;
   const long long p0 = (long long)blockIdx.x * chunk_pix, p1 = min(npix, p0 + (long long)chunk_pix);
   if (lane < lanes)
-    for (long long p = p0 + lane; p < p1; p += lanes) acc += __bfloat162float(t[p * ld + ch]);
+    for (long long p = p0 + lane; p < p1; p += lanes) acc += __bfloat162float(t[p * ld + coff + ch]);
   if (lane < lanes) sm[lane * c + ch] = acc;
   __syncthreads();
   if (threadIdx.x < c) {
     float s = 0.f;
     for (int l = 0; l < lanes; ++l) s += sm[l * c + threadIdx.x];
-    atomicAdd(&out[threadIdx.x], s);
+    atomicAdd(&out[coff + threadIdx.x], s);
   }
 }
 
@@ -298,16 +301,14 @@ int crfr_direct_wgrad(int n, int bh, int bw, int sh, int sw, int k, int stride, 
 }
 
 int crfr_colsum(const void* t, int ld, int c, long long npix, float* out, cudaStream_t st) {
-  if (c > 256) {
-    crfr_set_error("colsum: c %d > 256", c);
-    return CRFR_EUNSUPPORTED;
-  }
   long long chunks = npix / 512 < 1 ? 1 : npix / 512;
   if (chunks > 148 * 4) chunks = 148 * 4;
   int chunk_pix = (int)((npix + chunks - 1) / chunks);
   chunks = (npix + chunk_pix - 1) / chunk_pix;
-  int lanes = 256 / c > 0 ? 256 / c : 1;
-  colsum_kernel<<<(unsigned)chunks, 256, sizeof(float) * lanes * c, st>>>((const bf16*)t, ld, c, npix, chunk_pix, out);
+  const int cb = c < 256 ? c : 256;
+  const int lanes = 256 / cb > 0 ? 256 / cb : 1;
+  colsum_kernel<<<dim3((unsigned)chunks, (unsigned)((c + 255) / 256)), 256, sizeof(float) * lanes * cb, st>>>(
+      (const bf16*)t, ld, c, npix, chunk_pix, out);
   CRFR_COUNT_LAUNCH();
   CRFR_LAUNCH_CHECK();
   return CRFR_OK;

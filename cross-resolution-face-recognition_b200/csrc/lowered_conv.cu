@@ -5,10 +5,13 @@
 //   R1  Conv2d 3x3 s1 p1, cin = 3 (coarse conv_input, FSRnet.py:312)   fwd, wgrad : im2col(27 -> 64 ch) . W
 //   R2  Conv2d 3x3 s1 p1, cout = 3 (conv_mid :318, conv_out :439)      fwd : x . W(27 -> 32 cols, fp32) then col2im
 //                                                                     dgrad, wgrad : im2col(dY) as the GEMM operand
-//   R3  Conv2d 7x7 s4 p3, cin = 3 (encoder / prior stems :345, :384)   fwd, wgrad : im2col(147 -> 192 ch) . W
+//   R3  Conv2d 7x7 s4|s2 p3, cin = 3 (encoder / prior stems :345, :384; ResNet stem model/resnet.py:158)   fwd, wgrad : im2col(147 -> 192 ch) . W
 //                                                                     dgrad : dY . W (192 cols, fp32) then col2im
 //   R4  ConvTranspose2d 7x7 s4 p2 op1, 64 -> 64 (decoder :436)         fwd : x . W (49*64 cols, fp32) then col2im
 //                                                                     dgrad, wgrad : im2col(dOut) as the GEMM operand
+//   R5  Conv2d 3x3 s2 p1 / 1x1 s2 p0, channels % 64 == 0 (ResNet stage transitions and downsample branches,
+//       model/resnet.py:9-16, 193-200)                                 fwd, wgrad : im2col(T*cin) . W
+//                                                                     dgrad : dY . W (T*cin cols, fp32) then col2im
 // Partial products that are summed by a col2im kernel stay fp32 until the single final rounding, so the arithmetic
 // contract is the same as the direct kernels': fp32 accumulation over all taps and channels, one bf16 rounding.
 #include "common.cuh"
@@ -146,6 +149,62 @@ __global__ void deconv_im2col_kernel(const bf16* __restrict__ dout, int dout_ld,
   *reinterpret_cast<uint4*>(dZ + p * ((long long)T * C) + (long long)tap * C + g * 8) = v;
 }
 
+// Generic im2col for channel counts that are multiples of 8 (16-byte vectors):
+// P[o][tap*C + c] = x[o*stride + tap - pad][c], zero outside the image
+__global__ void im2col_vec_kernel(const bf16* __restrict__ x, int x_ld, int C, int h, int w, int oh, int ow, int ks,
+                                  int stride, int pad, bf16* __restrict__ P, long long total) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int groups = C >> 3, T = ks * ks;
+  const int g = (int)(i % groups);
+  long long r = i / groups;
+  const int tap = (int)(r % T);
+  long long o = r / T;
+  const int ox = (int)(o % ow);
+  long long q = o / ow;
+  const int oy = (int)(q % oh);
+  const long long n = q / oh;
+  const int ky = tap / ks, kx = tap - ky * ks;
+  const int y = oy * stride + ky - pad, xx = ox * stride + kx - pad;
+  uint4 v = make_uint4(0u, 0u, 0u, 0u);
+  if (y >= 0 && y < h && xx >= 0 && xx < w)
+    v = *reinterpret_cast<const uint4*>(x + ((n * h + y) * w + xx) * x_ld + g * 8);
+  *reinterpret_cast<uint4*>(P + o * ((long long)T * C) + (long long)tap * C + g * 8) = v;
+}
+
+// Its transpose: dx[p][c] = sum over the taps that reach input pixel p of dP[o][tap*C + c] (fp32 in, one rounding)
+__global__ void col2im_vec_kernel(const float* __restrict__ dP, int C, int oh, int ow, int h, int w, int ks, int stride,
+                                  int pad, bf16* __restrict__ dx, int dx_ld, long long total) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int groups = C >> 3;
+  const int g = (int)(i % groups);
+  long long p = i / groups;
+  const int X = (int)(p % w);
+  long long q = p / w;
+  const int Y = (int)(q % h);
+  const long long n = q / h;
+  const long long ld = (long long)ks * ks * C;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int ky = 0; ky < ks; ++ky) {
+    const int ty = Y + pad - ky;
+    if (ty < 0 || ty % stride) continue;
+    const int oy = ty / stride;
+    if (oy >= oh) continue;
+    for (int kx = 0; kx < ks; ++kx) {
+      const int tx = X + pad - kx;
+      if (tx < 0 || tx % stride) continue;
+      const int ox = tx / stride;
+      if (ox >= ow) continue;
+      const float4* s = reinterpret_cast<const float4*>(dP + ((n * oh + oy) * ow + ox) * ld + (ky * ks + kx) * C + g * 8);
+      const float4 a = s[0], b = s[1];
+      acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+      acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+    }
+  }
+  *reinterpret_cast<bf16x8*>(dx + p * dx_ld + g * 8) = pack8(acc);
+}
+
 // dst[r][tap*S + s] = src[tap][r][s] for s < S (src: [T][R][s_pad] bf16), zero elsewhere; dst is [rows_pad][kpad]
 __global__ void repack_tapmajor_kernel(const bf16* __restrict__ src, int T, int R, int S, int s_pad, bf16* __restrict__ dst,
                                        int rows_pad, int kpad) {
@@ -220,9 +279,12 @@ int crfr_lowered_recipe(const crfr_conv_desc* d) {
     if (d->k == 3 && d->stride == 1 && d->pad == 1 && d->cout == 3 && d->cin == 64 && d->out_ld == 4 &&
         tcgen05_spatial_ok(d->h, d->w))
       return 2;
-    if (d->k == 7 && d->stride == 4 && d->pad == 3 && d->cin == 3 && d->in_ld == 4 && (d->cout == 64 || d->cout == 128) &&
-        tcgen05_spatial_ok(d->oh, d->ow))
+    if (d->k == 7 && (d->stride == 4 || d->stride == 2) && d->pad == 3 && d->cin == 3 && d->in_ld == 4 &&
+        (d->cout == 64 || d->cout == 128) && tcgen05_spatial_ok(d->oh, d->ow))
       return 3;
+    if (d->stride == 2 && ((d->k == 3 && d->pad == 1) || (d->k == 1 && d->pad == 0)) && d->cin % 64 == 0 &&
+        d->cout % 64 == 0 && (d->in_ld & 7) == 0 && (d->out_ld & 7) == 0 && tcgen05_spatial_ok(d->oh, d->ow))
+      return 5;
     return 0;
   }
   if (d->k == 7 && d->stride == 4 && d->pad == 2 && d->cin == 64 && d->cout == 64 && d->oh == 4 * d->h && d->ow == 4 * d->w &&
@@ -242,6 +304,11 @@ size_t crfr_lowered_ws_bytes(const crfr_conv_desc* d) {
     case 4: {
       const size_t zc = 49 * 64;
       b = big * zc * 4 + (size_t)64 * zc * 2 + (size_t)64 * zc * 4;   // big = input (small) grid here
+      break;
+    }
+    case 5: {
+      const size_t kc = (size_t)d->k * d->k * d->cin;
+      b = small * kc * 2 + small * kc * 4 + (size_t)d->cout * kc * 2 + kc * d->cout * 4;
       break;
     }
     default: return 0;
@@ -270,6 +337,26 @@ int crfr_lowered_fwd(const crfr_conv_desc* d, const void* x, const void* w_packe
            d->pad, 1, P, kp, opix * (kp / 8));
     LAUNCH(repack_tapmajor_kernel, d->cout * kp, st, (const bf16*)w_packed, T, d->cout, 3, cin_pad, Wg, d->cout, kp);
     TcGemm g{P, d->n, d->oh, d->ow, kp, kp, Wg, 1, 0, 1, d->cout, 0, y, d->out_ld, 0, bias};
+    return crfr_tc_gemm(g, st);
+  }
+  if (recipe == 5) {
+    if (!y || y_nchw) {
+      crfr_set_error("lowered conv: recipe 5 produces the bf16 NHWC output only");
+      return CRFR_EUNSUPPORTED;
+    }
+    CRFR_CHECK_ARG(cin_pad == d->cin, "lowered conv: cin_pad %d != cin %d", cin_pad, d->cin);
+    const int kc = T * d->cin;
+    const long long opix = (long long)d->n * d->oh * d->ow;
+    TAKE(P, bf16, A, (size_t)opix * kc * 2);
+    LAUNCH(im2col_vec_kernel, opix * T * (d->cin / 8), st, (const bf16*)x, d->in_ld, d->cin, d->h, d->w, d->oh, d->ow, d->k,
+           d->stride, d->pad, P, opix * T * (d->cin / 8));
+    const void* wg = w_packed;   // [1][cout][cin] is already the GEMM weight for 1x1
+    if (T > 1) {
+      TAKE(Wg, bf16, A, (size_t)d->cout * kc * 2);
+      LAUNCH(repack_tapmajor_kernel, d->cout * kc, st, (const bf16*)w_packed, T, d->cout, d->cin, cin_pad, Wg, d->cout, kc);
+      wg = Wg;
+    }
+    TcGemm g{P, d->n, d->oh, d->ow, kc, kc, wg, 1, 0, 1, d->cout, 0, y, d->out_ld, 0, bias};
     return crfr_tc_gemm(g, st);
   }
   if (recipe == 2) {
@@ -339,6 +426,18 @@ int crfr_lowered_dgrad(const crfr_conv_desc* d, const void* dy, const void* w_pa
            (bf16*)dx, d->in_ld, ipix);
     return CRFR_OK;
   }
+  if (recipe == 5) {
+    // dP[o][tap*cin+ci] = sum_co dY[o][co] W[co][ci][tap] (fp32); w_packed_t [tap][ci][cout] is that GEMM weight
+    CRFR_CHECK_ARG(cout_pad == d->cout, "lowered dgrad: cout_pad %d != cout %d", cout_pad, d->cout);
+    const int kc = T * d->cin;
+    const long long opix = (long long)d->n * d->oh * d->ow, ipix = (long long)d->n * d->h * d->w;
+    TAKE(dP, float, A, (size_t)opix * kc * 4);
+    TcGemm g{dy, d->n, d->oh, d->ow, d->cout, d->out_ld, w_packed_t, 1, 0, 1, kc, 0, dP, kc, 1, nullptr};
+    CRFR_TRY(crfr_tc_gemm(g, st));
+    LAUNCH(col2im_vec_kernel, ipix * (d->cin / 8), st, dP, d->cin, d->oh, d->ow, d->h, d->w, d->k, d->stride, d->pad,
+           (bf16*)dx, d->in_ld, ipix * (d->cin / 8));
+    return CRFR_OK;
+  }
   if (recipe == 4) {
     // d_in[i][ci] = sum_{tap,co} dZ[i][tap*64+co] W[ci][co][tap]
     const long long ipix = (long long)d->n * d->h * d->w;
@@ -374,6 +473,19 @@ int crfr_lowered_wgrad(const crfr_conv_desc* d, const void* x, const void* dy, f
     TcWgrad g{P, d->n, d->oh, d->ow, kp, kp, dy, d->cout, d->out_ld, 0, G};
     CRFR_TRY(crfr_tc_wgrad_raw(g, st));
     LAUNCH(unpack_lowered_kernel, (long long)d->cout * 3 * T, st, G, d->cout, dw, d->cout, 3, T, 0);
+    return CRFR_OK;
+  }
+  if (recipe == 5) {
+    const int kc = T * d->cin;
+    const long long opix = (long long)d->n * d->oh * d->ow;
+    TAKE(P, bf16, A, (size_t)opix * kc * 2);
+    TAKE(G, float, A, (size_t)kc * d->cout * 4);
+    LAUNCH(im2col_vec_kernel, opix * T * (d->cin / 8), st, (const bf16*)x, d->in_ld, d->cin, d->h, d->w, d->oh, d->ow, d->k,
+           d->stride, d->pad, P, opix * T * (d->cin / 8));
+    CRFR_CUDA(cudaMemsetAsync(G, 0, (size_t)kc * d->cout * 4, st));
+    TcWgrad g{P, d->n, d->oh, d->ow, kc, kc, dy, d->cout, d->out_ld, 0, G};
+    CRFR_TRY(crfr_tc_wgrad_raw(g, st));
+    LAUNCH(unpack_lowered_kernel, (long long)d->cout * d->cin * T, st, G, d->cout, dw, d->cout, d->cin, T, 0);
     return CRFR_OK;
   }
   if (recipe == 2) {

@@ -364,6 +364,27 @@ norm_act_bwd_apply_kernel(const bf16* __restrict__ dz, int dz_ld, const bf16* __
   }
 }
 
+// BatchNorm buffer maintenance (one thread per channel)
+__global__ void bn_update_running_kernel(const float* __restrict__ stats, float* __restrict__ rmean,
+                                         float* __restrict__ rvar, long long* __restrict__ nbt, int c, float unbias,
+                                         float momentum, float eps) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch == 0 && nbt) *nbt += 1;
+  if (ch >= c) return;
+  const float mean = stats[2 * ch], rstd = stats[2 * ch + 1];
+  const float var = fmaxf(1.f / (rstd * rstd) - eps, 0.f);
+  rmean[ch] = (1.f - momentum) * rmean[ch] + momentum * mean;
+  rvar[ch] = (1.f - momentum) * rvar[ch] + momentum * var * unbias;
+}
+
+__global__ void bn_running_to_stats_kernel(const float* __restrict__ rmean, const float* __restrict__ rvar, int c,
+                                           float eps, float* __restrict__ stats) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  stats[2 * ch] = rmean[ch];
+  stats[2 * ch + 1] = rsqrtf(rvar[ch] + eps);
+}
+
 inline bool channels_ok(int c) { return c >= 8 && c <= 2048 && (c & 7) == 0 && (kThreads % (c >> 3)) == 0; }
 
 }  // namespace
@@ -378,6 +399,29 @@ size_t crfr_norm_ws_bytes(int n, int hw, int c) {
 int crfr_norm_finalize(const float* partial, int n, int chunks, int hw, int c, float eps, float* stats,
                        cudaStream_t st) {
   stats_finalize_kernel<<<n, kThreads, 0, st>>>(partial, chunks, c, 1.f / (float)hw, eps, stats);
+  CRFR_COUNT_LAUNCH();
+  CRFR_LAUNCH_CHECK();
+  return CRFR_OK;
+}
+
+extern "C" int crfr_bn_update_running(const float* stats, float* running_mean, float* running_var,
+                                      long long* num_batches_tracked, int c, long long count, float momentum,
+                                      float eps, void* stream) {
+  CRFR_CHECK_ARG(stats && running_mean && running_var && c > 0 && count > 0, "bn_update_running: bad argument");
+  const float unbias = count > 1 ? (float)((double)count / (double)(count - 1)) : 1.f;
+  bn_update_running_kernel<<<crfr_cdiv(c, 128), 128, 0, (cudaStream_t)stream>>>(stats, running_mean, running_var,
+                                                                               num_batches_tracked, c, unbias,
+                                                                               momentum, eps);
+  CRFR_COUNT_LAUNCH();
+  CRFR_LAUNCH_CHECK();
+  return CRFR_OK;
+}
+
+extern "C" int crfr_bn_running_to_stats(const float* running_mean, const float* running_var, int c, float eps,
+                                        float* stats, void* stream) {
+  CRFR_CHECK_ARG(stats && running_mean && running_var && c > 0, "bn_running_to_stats: bad argument");
+  bn_running_to_stats_kernel<<<crfr_cdiv(c, 128), 128, 0, (cudaStream_t)stream>>>(running_mean, running_var, c, eps,
+                                                                                 stats);
   CRFR_COUNT_LAUNCH();
   CRFR_LAUNCH_CHECK();
   return CRFR_OK;

@@ -1,0 +1,417 @@
+// Native ResNet_34 face-embedding network program (student / assistant / teacher of the residual knowledge
+// distillation step): the whole forward and backward are sequenced here in C++ on one stream over a caller-provided
+// workspace arena, exactly like fsrnet.cu - a tape of fused ops recorded by the forward and replayed in reverse.
+//
+// Layers: 7x7 s2 stem (lowered im2col + tcgen05 GEMM), 16 BasicBlocks of 3x3 convolutions on the tcgen05 implicit-GEMM
+// engine (stage transitions: 3x3 s2 and 1x1 s2 through the lowered recipe 5), train-mode BatchNorm (+ReLU, +residual)
+// as the n = 1 grouping of the fused normalise kernels with the running-statistics update, the 25088 -> 512 linear
+// head as a tcgen05 GEMM over the NHWC-flattened feature (weights re-ordered from the reference's NCHW flatten), and
+// BatchNorm1d on the embedding.
+//
+// ref: model/resnet.py:18-47 (BasicBlock), :152-225 (ResNet.__init__/_make_layer/forward), :231-236 (ResNet_34).
+#include <vector>
+
+#include "common.cuh"
+#include "crfr.h"
+#include "internal.h"
+
+namespace {
+
+struct Tensor {
+  bf16* p = nullptr;
+  int n = 0, h = 0, w = 0, c = 0, ld = 0;
+  int id = -1;
+};
+struct Slot {
+  bf16* p;
+  int ld;
+};
+enum OpKind { OP_CONV, OP_BN, OP_LINEAR };
+struct Op {
+  OpKind kind;
+  Tensor a, b, out;
+  crfr_conv_desc cd;
+  int w_idx = -1, b_idx = -1, g_idx = -1, beta_idx = -1;
+  int cin_pad = 0;
+  float* stats = nullptr;
+  bool relu = false, has_res = false, x_needs_grad = true;
+};
+
+constexpr int kFeat = 512, kEmb = 512;
+
+// W [o][c*HW + hw] (fp32, reference flatten order) -> Wp [o][hw*C + c] and WpT [hw*C + c][o] (bf16)
+__global__ void linear_pack_kernel(const float* __restrict__ w, bf16* __restrict__ wp, bf16* __restrict__ wpt, int O,
+                                   int C, int HW) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long K = (long long)C * HW;
+  if (i >= (long long)O * K) return;
+  const int o = (int)(i / K);
+  const long long k = i - (long long)o * K;       // hw*C + c
+  const int hw = (int)(k / C), c = (int)(k - (long long)hw * C);
+  const bf16 v = __float2bfloat16_rn(w[(long long)o * K + (long long)c * HW + hw]);
+  if (wp) wp[i] = v;
+  if (wpt) wpt[k * O + o] = v;
+}
+
+// dW [o][c*HW + hw] += G[hw*C + c][o]
+__global__ void linear_unpack_kernel(const float* __restrict__ G, float* __restrict__ dw, int O, int C, int HW) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long K = (long long)C * HW;
+  if (i >= (long long)O * K) return;
+  const int o = (int)(i / K);
+  const long long r = i - (long long)o * K;       // c*HW + hw
+  const int c = (int)(r / HW), hw = (int)(r - (long long)c * HW);
+  dw[i] += G[((long long)hw * C + c) * O + o];
+}
+
+struct Net {
+  int engine;
+  const float* const* params;
+  float* const* grads;
+  void* const* buffers;
+  const crfr_resnet_io* io;
+  cudaStream_t st;
+  uint8_t* ws;
+  size_t ws_bytes, off = 0;
+  bool exec;
+  int err = CRFR_OK;
+  std::vector<Op> tape;
+  std::vector<std::vector<Slot>> slots;
+  void* scratch = nullptr;
+  size_t scratch_bytes = 0;
+  Tensor feat[4], emb;
+  bf16* wp = nullptr;    // packed linear weights (forward)
+  bf16* wpt = nullptr;   // transposed (backward)
+  int pcur = 0, bncur = 0;
+
+  void* alloc(size_t bytes) {
+    size_t a = (off + 1023) & ~(size_t)1023;
+    if (a + bytes > ws_bytes) {
+      if (err == CRFR_OK) {
+        crfr_set_error("resnet34: workspace too small (%zu needed so far, %zu given)", a + bytes, ws_bytes);
+        err = CRFR_EWORKSPACE;
+      }
+      off = a + bytes;
+      return ws;
+    }
+    off = a + bytes;
+    return ws + a;
+  }
+  bool ok() const { return err == CRFR_OK; }
+  bool run() const { return exec && err == CRFR_OK; }
+  void check(int rc) {
+    if (rc != CRFR_OK && err == CRFR_OK) err = rc;
+  }
+  void check_cuda(cudaError_t e) {
+    if (e != cudaSuccess && err == CRFR_OK) {
+      crfr_set_error("resnet34: %s", cudaGetErrorString(e));
+      err = CRFR_ECUDA;
+    }
+  }
+  Tensor new_tensor(int n, int h, int w, int c) {
+    Tensor t;
+    t.n = n; t.h = h; t.w = w; t.c = c; t.ld = c < 8 ? 4 : c;
+    t.p = (bf16*)alloc((size_t)n * h * w * t.ld * sizeof(bf16));
+    t.id = (int)slots.size();
+    slots.emplace_back();
+    return t;
+  }
+  float* grad(int idx) { return (grads && idx >= 0) ? grads[idx] : nullptr; }
+
+  // ---- forward ops ----
+  Tensor conv(const Tensor& x, int w_idx, int cout, int k, int stride, int pad, bool x_needs_grad) {
+    Op op;
+    op.kind = OP_CONV;
+    crfr_conv_desc& d = op.cd;
+    d.n = x.n; d.h = x.h; d.w = x.w; d.cin = x.c; d.cout = cout; d.k = k; d.stride = stride; d.pad = pad;
+    d.transposed = 0;
+    d.oh = (x.h + 2 * pad - k) / stride + 1;
+    d.ow = (x.w + 2 * pad - k) / stride + 1;
+    Tensor y = new_tensor(x.n, d.oh, d.ow, cout);
+    d.in_ld = x.ld; d.out_ld = y.ld;
+    op.cin_pad = x.c < 8 ? 4 : x.c;
+    const int T = k * k;
+    void* wpk = alloc((size_t)T * cout * op.cin_pad * sizeof(bf16));
+    if (run()) {
+      check(crfr_pack_weight(params[w_idx], wpk, T, cout, x.c, op.cin_pad, (long long)x.c * T, T, 1, st));
+      check(crfr_conv_fwd(engine, &d, x.p, wpk, op.cin_pad, nullptr, y.p, nullptr, nullptr, io->eps, scratch,
+                          scratch_bytes, st));
+    }
+    op.a = x; op.out = y; op.w_idx = w_idx; op.x_needs_grad = x_needs_grad;
+    tape.push_back(op);
+    return y;
+  }
+
+  // BatchNorm (batch statistics over n*h*w in training, running statistics otherwise) + optional residual + ReLU
+  Tensor bn(const Tensor& y, int g_idx, int relu, const Tensor* res) {
+    const int bi = bncur++;
+    const long long count = (long long)y.n * y.h * y.w;
+    Tensor out = new_tensor(y.n, y.h, y.w, y.c);
+    float* stats = (float*)alloc((size_t)y.c * 2 * sizeof(float));
+    float* rmean = buffers ? (float*)buffers[3 * bi] : nullptr;
+    float* rvar = buffers ? (float*)buffers[3 * bi + 1] : nullptr;
+    long long* nbt = buffers ? (long long*)buffers[3 * bi + 2] : nullptr;
+    if (run()) {
+      if (io->training) {
+        check(crfr_norm_stats(y.p, 1, (int)count, y.c, y.ld, io->eps, stats, scratch, scratch_bytes, st));
+        if (rmean && rvar)
+          check(crfr_bn_update_running(stats, rmean, rvar, nbt, y.c, count, io->momentum, io->eps, st));
+      } else {
+        check(crfr_bn_running_to_stats(rmean, rvar, y.c, io->eps, stats, st));
+      }
+      check(crfr_norm_act_fwd(y.p, y.ld, stats, params[g_idx], params[g_idx + 1], nullptr, relu, res ? res->p : nullptr,
+                              res ? res->ld : 8, out.p, out.ld, 1, (int)count, y.c, st));
+    }
+    Op op;
+    op.kind = OP_BN;
+    op.a = y; op.out = out; op.stats = stats; op.g_idx = g_idx; op.beta_idx = g_idx + 1; op.relu = relu != 0;
+    op.has_res = res != nullptr;
+    if (res) op.b = *res;
+    tape.push_back(op);
+    return out;
+  }
+
+  Tensor block(const Tensor& x, int planes, int stride, bool down) {   // BasicBlock, model/resnet.py:18-47
+    const int p0 = pcur;
+    pcur += down ? 9 : 6;
+    Tensor y1 = conv(x, p0 + 0, planes, 3, stride, 1, true);
+    Tensor a1 = bn(y1, p0 + 1, 1, nullptr);
+    Tensor y2 = conv(a1, p0 + 3, planes, 3, 1, 1, true);
+    // module order of the BatchNorms is bn1, bn2, downsample.1: reserve bn2's slot before the downsample branch
+    const int bn2 = bncur++;
+    Tensor res = x;
+    if (down) {
+      Tensor yd = conv(x, p0 + 6, planes, 1, stride, 0, true);
+      res = bn(yd, p0 + 7, 0, nullptr);
+    }
+    const int save = bncur;
+    bncur = bn2;
+    Tensor out = bn(y2, p0 + 4, 1, &res);
+    bncur = save;
+    return out;
+  }
+
+  Tensor linear(const Tensor& a) {
+    const int B = a.n, K = a.h * a.w * a.c;
+    Tensor y = new_tensor(B, 1, 1, kEmb);
+    wp = (bf16*)alloc((size_t)kEmb * K * sizeof(bf16));
+    wpt = io->training ? (bf16*)alloc((size_t)kEmb * K * sizeof(bf16)) : nullptr;
+    const int w_idx = pcur;
+    pcur += 2;
+    if (run()) {
+      const long long total = (long long)kEmb * K;
+      linear_pack_kernel<<<crfr_cdiv(total, 256), 256, 0, st>>>(params[w_idx], wp, wpt, kEmb, a.c, a.h * a.w);
+      CRFR_COUNT_LAUNCH();
+      check_cuda(cudaGetLastError());
+      TcGemm g{a.p, B, 1, 1, K, K, wp, 1, 0, 1, kEmb, 64, y.p, kEmb, 0, params[w_idx + 1]};
+      check(crfr_tc_gemm(g, st));
+    }
+    Op op;
+    op.kind = OP_LINEAR;
+    op.a = a; op.out = y; op.w_idx = w_idx; op.b_idx = w_idx + 1;
+    tape.push_back(op);
+    return y;
+  }
+
+  void to_nchw(const Tensor& t, float* dst) {
+    if (dst && run()) check(crfr_nhwc_bf16_to_nchw_f32(t.p, dst, t.n, t.c, t.h, t.w, t.ld, st));
+  }
+
+  size_t scratch_need(int B, int S) const {
+    size_t m = crfr_norm_ws_bytes(1, B * (S / 2) * (S / 2), 64);
+    const int q = S / 2;
+    const crfr_conv_desc shapes[] = {
+        {B, S, S, 3, 64, 7, 2, 3, q, q, 4, 64, 0},
+        {B, q, q, 64, 64, 3, 1, 1, q, q, 64, 64, 0},
+        {B, q, q, 64, 128, 3, 2, 1, q / 2, q / 2, 64, 128, 0},
+        {B, q / 2, q / 2, 128, 128, 3, 1, 1, q / 2, q / 2, 128, 128, 0},
+        {B, q / 2, q / 2, 128, 256, 3, 2, 1, q / 4, q / 4, 128, 256, 0},
+        {B, q / 4, q / 4, 256, 256, 3, 1, 1, q / 4, q / 4, 256, 256, 0},
+        {B, q / 4, q / 4, 256, 512, 3, 2, 1, q / 8, q / 8, 256, 512, 0},
+        {B, q / 8, q / 8, 512, 512, 3, 1, 1, q / 8, q / 8, 512, 512, 0}};
+    for (const crfr_conv_desc& d : shapes) {
+      const size_t b = crfr_conv_workspace_bytes(&d);
+      if (b > m) m = b;
+    }
+    const size_t lin = sizeof(float) * (size_t)kEmb * kFeat * (q / 8) * (q / 8) + 4096;   // linear wgrad accumulator
+    return (m > lin ? m : lin) + 4096;
+  }
+
+  void forward() {
+    const int B = io->batch, S = io->size;
+    pcur = 0; bncur = 0;
+    scratch_bytes = scratch_need(B, S);
+    scratch = alloc(scratch_bytes);
+    Tensor x4 = new_tensor(B, S, S, 3);
+    if (run()) check(crfr_nchw_f32_to_nhwc_bf16(io->x, x4.p, B, 3, S, S, 4, 4, st));
+    // stem (model/resnet.py:208-211; the max-pool is commented out in the reference)
+    Tensor y = conv(x4, 0, 64, 7, 2, 3, false);
+    pcur = 1;
+    Tensor a = bn(y, 1, 1, nullptr);
+    pcur = 3;
+    const int layers[4] = {3, 4, 6, 3}, planes[4] = {64, 128, 256, 512};
+    for (int l = 0; l < 4; ++l) {
+      for (int b = 0; b < layers[l]; ++b) a = block(a, planes[l], (l > 0 && b == 0) ? 2 : 1, l > 0 && b == 0);
+      feat[l] = a;
+      to_nchw(a, io->feat[l]);
+    }
+    Tensor o1 = bn(a, pcur, 0, nullptr);      // bn_o1
+    pcur += 2;
+    Tensor yfc = linear(o1);                  // fc (pcur += 2 inside)
+    emb = bn(yfc, pcur, 0, nullptr);          // bn_o2 (BatchNorm1d)
+    pcur += 2;
+    to_nchw(emb, io->emb);
+  }
+
+  // ---- backward ----
+  void add_slot(const Tensor& t, bf16* p, int ld) { slots[t.id].push_back({p, ld}); }
+  bool has_grad(const Tensor& t) const { return t.id >= 0 && !slots[t.id].empty(); }
+  void squash(const Tensor& t, size_t max_slots) {
+    std::vector<Slot>& s = slots[t.id];
+    while (s.size() > max_slots) {
+      const bool three = s.size() >= 3;
+      bf16* out = (bf16*)alloc((size_t)t.n * t.h * t.w * t.ld * sizeof(bf16));
+      const size_t k = s.size();
+      Slot a = s[k - 1], b = s[k - 2], c = three ? s[k - 3] : Slot{nullptr, t.ld};
+      if (run()) check(crfr_add_n(a.p, a.ld, b.p, b.ld, c.p, c.ld, out, t.ld, (long long)t.n * t.h * t.w, t.ld, st));
+      s.resize(k - (three ? 3 : 2));
+      s.push_back({out, t.ld});
+    }
+  }
+  void seed_grad(const Tensor& t, const float* g) {   // external gradient of an output (fp32 NCHW)
+    if (!g) return;
+    bf16* d = (bf16*)alloc((size_t)t.n * t.h * t.w * t.ld * sizeof(bf16));
+    if (run()) check(crfr_nchw_f32_to_nhwc_bf16(g, d, t.n, t.c, t.h, t.w, t.ld, t.ld, st));
+    add_slot(t, d, t.ld);
+  }
+
+  void backward() {
+    for (int i = (int)tape.size() - 1; i >= 0 && ok(); --i) {
+      Op& op = tape[i];
+      if (!has_grad(op.out)) continue;
+      switch (op.kind) {
+        case OP_BN: {
+          squash(op.out, 2);
+          std::vector<Slot>& s = slots[op.out.id];
+          const Tensor& y = op.a;
+          const long long count = (long long)y.n * y.h * y.w;
+          const size_t bytes = (size_t)count * y.ld * sizeof(bf16);
+          bf16* dz = (bf16*)alloc(bytes);
+          bf16* dy = (bf16*)alloc(bytes);
+          if (run())
+            check(crfr_norm_act_bwd(s[0].p, s[0].ld, s.size() > 1 ? s[1].p : nullptr, s.size() > 1 ? s[1].ld : 8, y.p, y.ld,
+                                    op.stats, params[op.g_idx], params[op.beta_idx], nullptr, op.relu ? 1 : 0,
+                                    op.has_res ? op.b.p : nullptr, op.has_res ? op.b.ld : 8, dz, y.ld, dy, y.ld,
+                                    grad(op.g_idx), grad(op.beta_idx), nullptr, 1, (int)count, y.c, scratch, scratch_bytes,
+                                    st));
+          add_slot(y, dy, y.ld);
+          if (op.has_res) add_slot(op.b, dz, y.ld);
+          break;
+        }
+        case OP_CONV: {
+          squash(op.out, 1);
+          Slot dy = slots[op.out.id][0];
+          crfr_conv_desc d = op.cd;
+          d.out_ld = dy.ld;
+          if (run()) check(crfr_conv_wgrad(engine, &d, op.a.p, dy.p, grad(op.w_idx), nullptr, scratch, scratch_bytes, st));
+          if (op.x_needs_grad) {
+            const Tensor& x = op.a;
+            bf16* dx = (bf16*)alloc((size_t)x.n * x.h * x.w * x.ld * sizeof(bf16));
+            const int T = d.k * d.k;
+            void* wt = alloc((size_t)T * d.cin * d.cout * sizeof(bf16));
+            if (run()) {
+              check(crfr_pack_weight(params[op.w_idx], wt, T, d.cin, d.cout, d.cout, T, (long long)d.cin * T, 1, st));
+              check(crfr_conv_dgrad(engine, &d, dy.p, wt, d.cout, dx, scratch, scratch_bytes, st));
+            }
+            add_slot(x, dx, x.ld);
+          }
+          break;
+        }
+        case OP_LINEAR: {
+          squash(op.out, 1);
+          Slot dy = slots[op.out.id][0];
+          const Tensor& a = op.a;
+          const int B = a.n, K = a.h * a.w * a.c;
+          bf16* da = (bf16*)alloc((size_t)B * K * sizeof(bf16));
+          if (run()) {
+            TcGemm g{dy.p, B, 1, 1, kEmb, dy.ld, wpt, 1, 0, 1, K, 0, da, K, 0, nullptr};
+            check(crfr_tc_gemm(g, st));
+            float* G = (float*)scratch;
+            check_cuda(cudaMemsetAsync(G, 0, sizeof(float) * (size_t)K * kEmb, st));
+            TcWgrad wg{a.p, B, 1, 1, K, K, dy.p, kEmb, dy.ld, 0, G};
+            check(crfr_tc_wgrad_raw(wg, st));
+            if (grad(op.w_idx)) {
+              const long long total = (long long)kEmb * K;
+              linear_unpack_kernel<<<crfr_cdiv(total, 256), 256, 0, st>>>(G, grad(op.w_idx), kEmb, a.c, a.h * a.w);
+              CRFR_COUNT_LAUNCH();
+              check_cuda(cudaGetLastError());
+            }
+            if (grad(op.b_idx)) check(crfr_colsum(dy.p, dy.ld, kEmb, B, grad(op.b_idx), st));
+          }
+          add_slot(a, da, K / (a.h * a.w));
+          break;
+        }
+      }
+    }
+  }
+};
+
+int check_io(const crfr_resnet_io* io, const char* who) {
+  CRFR_CHECK_ARG(io && io->batch > 0 && io->size == 112, "%s: batch/size invalid (input must be [B,3,112,112])", who);
+  CRFR_CHECK_ARG(io->x && io->emb, "%s: null tensor pointer", who);
+  CRFR_CHECK_ARG(io->eps > 0.f && io->momentum >= 0.f && io->momentum <= 1.f, "%s: eps/momentum invalid", who);
+  return CRFR_OK;
+}
+
+void init_net(Net& net, int engine, const float* const* params, float* const* grads, void* const* buffers,
+              const crfr_resnet_io* io, void* ws, size_t ws_bytes, cudaStream_t st, bool exec) {
+  net.engine = engine; net.params = params; net.grads = grads; net.buffers = buffers; net.io = io; net.st = st;
+  net.ws = (uint8_t*)ws; net.ws_bytes = ws_bytes; net.exec = exec;
+}
+
+}  // namespace
+
+extern "C" size_t crfr_resnet34_workspace_bytes(int batch, int size, int training) {
+  if (batch <= 0 || size != 112) return 0;
+  crfr_resnet_io io = {};
+  io.batch = batch; io.size = size; io.training = training; io.momentum = 0.1f; io.eps = 1e-5f;
+  static float dummy = 0.f;   // non-null marker so that the dry run sizes every optional buffer
+  Net net;
+  init_net(net, CRFR_ENGINE_AUTO, nullptr, nullptr, nullptr, &io, nullptr, ~(size_t)0 >> 2, nullptr, false);
+  net.forward();
+  if (training) {
+    for (int l = 0; l < 4; ++l) net.seed_grad(net.feat[l], &dummy);
+    net.seed_grad(net.emb, &dummy);
+    net.backward();
+  }
+  return net.off + 65536;
+}
+
+extern "C" int crfr_resnet34_forward(int engine, const float* const* host_params, void* const* host_buffers,
+                                     const crfr_resnet_io* io, void* ws, size_t ws_bytes, void* stream) {
+  CRFR_TRY(check_io(io, "resnet34_forward"));
+  CRFR_CHECK_ARG(host_params && ws, "resnet34_forward: null pointer");
+  CRFR_CHECK_ARG(io->training || host_buffers, "resnet34_forward: eval mode needs the running statistics");
+  Net net;
+  init_net(net, engine, host_params, nullptr, host_buffers, io, ws, ws_bytes, (cudaStream_t)stream, true);
+  net.forward();
+  return net.err;
+}
+
+extern "C" int crfr_resnet34_backward(int engine, const float* const* host_params, float* const* host_grads,
+                                      const crfr_resnet_io* io, const float* d_emb, const float* const* d_feat,
+                                      void* ws, size_t ws_bytes, void* stream) {
+  CRFR_TRY(check_io(io, "resnet34_backward"));
+  CRFR_CHECK_ARG(host_params && host_grads && ws, "resnet34_backward: null pointer");
+  CRFR_CHECK_ARG(io->training, "resnet34_backward: the forward must have run in training mode");
+  Net net;
+  init_net(net, engine, host_params, host_grads, nullptr, io, ws, ws_bytes, (cudaStream_t)stream, false);
+  net.forward();   // dry run: rebuild the tape and the saved-activation offsets
+  if (!net.ok()) return net.err;
+  net.exec = true;
+  for (int l = 0; l < 4; ++l) net.seed_grad(net.feat[l], d_feat ? d_feat[l] : nullptr);
+  net.seed_grad(net.emb, d_emb);
+  if (!net.ok()) return net.err;
+  net.backward();
+  return net.err;
+}

@@ -289,6 +289,7 @@ struct WgradParams {
   int n, h, w;
   int bw, bh, bn, tiles_x, tiles_y, total_tiles;
   int cin, cout;   // cout = all dY channels; a CTA handles columns [ntile * N, +N)
+  int rows;        // pixels per tile (bw*bh*bn <= 128); rows beyond it are kept zero in shared memory
   float* G;        // [taps][cin][cout] fp32, pre-zeroed
 };
 
@@ -333,14 +334,22 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     prefetch_tmap(&tmDY);
   }
   if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  if (p.rows < 128) {
+    // pixels are the K dimension: the rows of a 128-row tile that the (smaller) TMA box never writes must read as
+    // zero, so clear the whole ring once
+    for (int i = threadIdx.x; i < Cfg::kStages * Cfg::kStageBytes / 16; i += kConvThreads)
+      reinterpret_cast<uint4*>(base)[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  // TAPS == 3: blockIdx.y = ky;  TAPS == 1: blockIdx.y = column tile of dY
-  const int ky = TAPS == 3 ? blockIdx.y : 0, kc = blockIdx.z;
-  const int ncol0 = TAPS == 3 ? 0 : blockIdx.y * N;
+  // TAPS == 3: blockIdx.y = ky + 3 * column tile;  TAPS == 1: blockIdx.y = column tile of dY
+  const int ky = TAPS == 3 ? blockIdx.y % 3 : 0, kc = blockIdx.z;
+  const int ncol0 = (TAPS == 3 ? blockIdx.y / 3 : blockIdx.y) * N;
+  const uint32_t stage_tx = (uint32_t)(TAPS + Cfg::kDyTiles) * (uint32_t)p.rows * 128u;
   const int first = blockIdx.x, step = gridDim.x;
   const int my_tiles = first < p.total_tiles ? (p.total_tiles - first + step - 1) / step : 0;
 
@@ -355,7 +364,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       const int x0 = tx * p.bw, y0 = ty * p.bh, n0 = t * p.bn;
       uint8_t* sb = base + s * Cfg::kStageBytes;
       if (leader) {
-        mbar_expect_tx(&full[s], Cfg::kStageBytes);
+        mbar_expect_tx(&full[s], stage_tx);
         if (TAPS == 3) {
 #pragma unroll
           for (int kx = 0; kx < 3; ++kx)
@@ -447,7 +456,7 @@ int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmDY, const WgradPar
                                    Cfg::kSmemBytes));
     attr_done = true;
   }
-  const int gy = TAPS == 3 ? 3 : p.cout / N;
+  const int gy = (TAPS == 3 ? 3 : 1) * (p.cout / N);
   tc_wgrad_kernel<N, TAPS><<<dim3(splits, gy, p.cin / 64), kConvThreads, Cfg::kSmemBytes, st>>>(tmX, tmDY, p);
   CRFR_COUNT_LAUNCH();
   CRFR_LAUNCH_CHECK();
@@ -458,10 +467,6 @@ bool spatial_ok(int h, int w, bool exact128) {
   Tiling t;
   if (!make_tiling(1, h, w, &t)) return false;
   if (w > 128 && (w % 128) != 0 && exact128) return false;
-  if (exact128) {
-    // wgrad sums over all 128 rows of a tile: rows must be real pixels or TMA zero fill
-    if (t.bw * t.bh * t.bn != 128) return false;
-  }
   return true;
 }
 
@@ -523,7 +528,7 @@ int crfr_tc_wgrad_raw(const TcWgrad& g, cudaStream_t st) {
                  "tc_wgrad: pointers must be 16B aligned and ld a multiple of 8");
   CRFR_CHECK_ARG(g.cin % 64 == 0 && g.cout % 64 == 0, "tc_wgrad: channels must be multiples of 64");
   Tiling t;
-  if (!make_tiling(g.n, g.h, g.w, &t) || t.bw * t.bh * t.bn != 128) {
+  if (!make_tiling(g.n, g.h, g.w, &t)) {
     crfr_set_error("tc_wgrad: unsupported spatial size %dx%d", g.h, g.w);
     return CRFR_EUNSUPPORTED;
   }
@@ -535,15 +540,16 @@ int crfr_tc_wgrad_raw(const TcWgrad& g, cudaStream_t st) {
   p.bw = t.bw; p.bh = t.bh; p.bn = t.bn; p.tiles_x = t.tiles_x; p.tiles_y = t.tiles_y;
   p.total_tiles = t.tiles_x * t.tiles_y * t.tiles_n;
   p.cin = g.cin; p.cout = g.cout; p.G = g.G;
+  p.rows = t.rows;
   const int tile_n = (g.cout % 128 == 0) ? 128 : 64;
-  const int ctas_per_split = (g.taps3x3 ? 3 : g.cout / tile_n) * (g.cin / 64);
+  const int ctas_per_split = (g.taps3x3 ? 3 : 1) * (g.cout / tile_n) * (g.cin / 64);
   int splits = (148 * 2 + ctas_per_split - 1) / ctas_per_split;
   if (splits > p.total_tiles) splits = p.total_tiles;
   if (splits < 1) splits = 1;
   if (g.taps3x3) {
     if (g.cout == 64) return launch_wgrad<64, 3>(tmX, tmDY, p, splits, st);
-    if (g.cout == 128) return launch_wgrad<128, 3>(tmX, tmDY, p, splits, st);
-    crfr_set_error("tc_wgrad: 3x3 needs cout 64 or 128, got %d", g.cout);
+    if (g.cout % 128 == 0) return launch_wgrad<128, 3>(tmX, tmDY, p, splits, st);
+    crfr_set_error("tc_wgrad: 3x3 needs cout 64 or a multiple of 128, got %d", g.cout);
     return CRFR_EUNSUPPORTED;
   }
   if (tile_n == 128) return launch_wgrad<128, 1>(tmX, tmDY, p, splits, st);
@@ -555,10 +561,10 @@ int crfr_tc_supported(int op, int h, int w, int cin, int cout, int k, int stride
   if (cin % 64 || cout % 64) return 0;
   const int nout = (op == 1) ? cin : cout;  // GEMM N
   if (op == 2) {
-    if (cout != 64 && cout != 128) return 0;
+    if (cout != 64 && cout % 128 != 0) return 0;
     return spatial_ok(h, w, true) ? 1 : 0;
   }
-  if (nout != 64 && nout != 128 && nout != 192 && nout != 256) return 0;
+  if (pick_tile_n(nout) == 0) return 0;
   return spatial_ok(h, w, false) ? 1 : 0;
 }
 
@@ -594,7 +600,7 @@ int crfr_tc_conv(const crfr_conv_desc* d, int dgrad, const void* src, const void
   g.src_ld = dgrad ? d->out_ld : d->in_ld;
   g.wt = w_packed; g.ksize = d->k; g.pad = d->pad; g.sign = dgrad ? -1 : 1;
   g.n_total = dgrad ? d->cin : d->cout;
-  g.tile_n = g.n_total;
+  g.tile_n = g.n_total <= 256 ? g.n_total : 0;   // wider layers: several column tiles per pixel tile
   g.out = dst; g.out_ld = dgrad ? d->in_ld : d->out_ld; g.out_f32 = 0; g.bias = bias;
   CRFR_TRY(crfr_tc_gemm(g, st));
   if (stats && !dgrad)

@@ -1,1 +1,1 @@
-from .loss import MSELossFunc, MSELoss_Landmark, CrossEntropyLoss2d  # noqa: F401
+from .loss import (MSELossFunc, MSELoss_Landmark, CrossEntropyLoss2d, MSELoss, ResidualKDLoss)  # noqa: F401

@@ -74,3 +74,35 @@ class CrossEntropyLoss2d(nn.Module):
 
     def forward(self, outputs, targets):
         return _CE2dFn.apply(outputs.float(), targets)
+
+
+class _KDFn(torch.autograd.Function):
+    """mean(((t - s) - a)^2) with the three input gradients produced by the same fused kernel (crfr_loss_kd)."""
+
+    @staticmethod
+    def forward(ctx, t, s, a):
+        t, a = t.contiguous().float(), a.contiguous().float()
+        s = None if s is None else s.contiguous().float()
+        want = (ctx.needs_input_grad[0], s is not None and ctx.needs_input_grad[1], ctx.needs_input_grad[2])
+        loss, grads = ops.loss_kd(t, s, a, 1.0, want=want)
+        ctx.grads = grads
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        return tuple(None if d is None else d * g for d in ctx.grads)
+
+
+class MSELoss(nn.Module):
+    """ref: nn.MSELoss() as used at distill_main.py:63 - mean((input - target)^2)."""
+
+    def forward(self, input, target):
+        return _KDFn.apply(input, None, target)
+
+
+class ResidualKDLoss(nn.Module):
+    """ref: distill_main.py:68-70 - nn.MSELoss()(teacher - student, assistant): the assistant learns the residual
+    between the HR teacher's and the LR student's features / embeddings."""
+
+    def forward(self, teacher, student, assistant):
+        return _KDFn.apply(teacher, student, assistant)

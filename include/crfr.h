@@ -93,6 +93,16 @@ int crfr_norm_act_bwd(const void* dout_a, int da_ld, const void* dout_b, int db_
                       const void* res, int res_ld, void* dz, int dz_ld, void* dy, int dy_ld, float* dgamma,
                       float* dbeta, float* dalpha, int n, int hw, int c, void* ws, size_t ws_bytes, void* stream);
 
+/* ref: train-mode nn.BatchNorm2d / BatchNorm1d buffer update (model/resnet.py:24,27,159,167,172):
+ * running = (1-momentum)*running + momentum*batch, with the unbiased batch variance (count = N*H*W samples);
+ * stats is the [c][2] (mean, rstd) produced by crfr_norm_stats with n = 1.  num_batches_tracked (int64, may be NULL) += 1. */
+int crfr_bn_update_running(const float* stats, float* running_mean, float* running_var,
+                           long long* num_batches_tracked, int c, long long count, float momentum, float eps,
+                           void* stream);
+/* eval-mode BatchNorm: stats[c][2] = (running_mean, 1/sqrt(running_var + eps)), to be used with crfr_norm_act_fwd */
+int crfr_bn_running_to_stats(const float* running_mean, const float* running_var, int c, float eps, float* stats,
+                             void* stream);
+
 /* ---------------------------------------------------------------- hourglass resampling --------------------- */
 /* ref: F.max_pool2d(x,2,2) FSRnet.py:202 ; F.interpolate(scale_factor=2)+add :210-211 */
 int crfr_maxpool2_fwd(const void* x, int x_ld, void* out, int out_ld, int n, int h, int w, int c, void* stream);
@@ -195,6 +205,31 @@ int crfr_fsrnet_backward(int engine, const float* const* host_params, float* con
  * (total, L_sr, L_coarse, L_landmark, L_ce). */
 int crfr_fsrnet_train_step(int engine, const float* const* host_params, float* const* host_grads,
                            const crfr_fsrnet_io* io, float* losses, void* ws, size_t ws_bytes, void* stream);
+
+/* ---------------------------------------------------------------- ResNet_34 embedding network program ------ */
+#define CRFR_RESNET34_NPARAMS 114 /* named_parameters() order of model/resnet.py:ResNet_34 */
+#define CRFR_RESNET34_NBN 38      /* BatchNorm layers in module order */
+typedef struct crfr_resnet_io {
+  int batch, size;       /* size = 112 (model/resnet.py:156,168: Linear(25088, 512)) */
+  const float* x;        /* [B,3,S,S] fp32 NCHW */
+  float* emb;            /* [B,512]                                   (out) */
+  float* feat[4];        /* x1..x4: [B,64,56,56] [B,128,28,28] [B,256,14,14] [B,512,7,7]; NULL entries are skipped */
+  int training;          /* 1: batch statistics + running-statistics update; 0: running statistics (eval) */
+  float momentum, eps;   /* nn.BatchNorm defaults 0.1, 1e-5 */
+} crfr_resnet_io;
+
+/* ref: ResNet.forward model/resnet.py:207-225 -> (x, x1, x2, x3, x4).
+ * params: 114 fp32 device pointers in named_parameters() order.  buffers: 3 * 38 device pointers in named_buffers()
+ * order (running_mean fp32, running_var fp32, num_batches_tracked int64 per BatchNorm; NULL table in training mode
+ * skips the buffer update). */
+size_t crfr_resnet34_workspace_bytes(int batch, int size, int training);
+int crfr_resnet34_forward(int engine, const float* const* host_params, void* const* host_buffers,
+                          const crfr_resnet_io* io, void* ws, size_t ws_bytes, void* stream);
+/* grads w.r.t. the embedding and the four stage features (fp32 NCHW, any may be NULL) -> accumulates into
+ * host_grads[114] (NULL entries skipped).  ws must be the workspace of the matching training-mode forward. */
+int crfr_resnet34_backward(int engine, const float* const* host_params, float* const* host_grads,
+                           const crfr_resnet_io* io, const float* d_emb, const float* const* d_feat, void* ws,
+                           size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -16,6 +16,7 @@ from oracle import bicubic_oracle as BO      # noqa: E402
 from oracle import eval_oracle as EO         # noqa: E402
 from oracle import fsrnet_oracle as FO       # noqa: E402
 from oracle import ref_loader as R           # noqa: E402
+from oracle import resnet_oracle as RO       # noqa: E402
 
 OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
 
@@ -142,7 +143,72 @@ def golden_eval():
     print("eval ok", top1, o15)
 
 
+def golden_resnet():
+    """ResNet_34 (model/resnet.py) + the KD losses of distill_main.py:63,68-70 on the reference's own modules."""
+    RM = R.load("model/resnet.py")
+    nets, sds = [], []
+    for i, seed in enumerate((77, 78, 79)):          # teacher, student, assistant
+        torch.manual_seed(seed)
+        net = RM.ResNet_34()
+        sd = RO.build_resnet34_state_dict(seed)
+        ref_sd = net.state_dict()
+        assert list(sd) == list(ref_sd) and all(torch.equal(sd[k], ref_sd[k]) for k in sd), "seeded init differs"
+        sd = RO.randomize_norm_params(sd, 100 + i)
+        net.load_state_dict(sd)
+        nets.append(net); sds.append(sd)
+    teacher, student, assistant = nets
+    teacher.eval(); student.train(); assistant.train()
+    x = RO.synthetic_faces(8)
+    t_outs = teacher(x)
+    s_outs = student(x)
+    a_outs = assistant(x)
+    mse = torch.nn.MSELoss()
+    l_s = mse(s_outs[0], t_outs[0].detach())
+    l_a = (mse(t_outs[1] - s_outs[1], a_outs[1]) + mse(t_outs[2] - s_outs[2], a_outs[2])
+           + mse(t_outs[3] - s_outs[3], a_outs[3]) + mse(t_outs[4] - s_outs[4], a_outs[4])
+           + mse(t_outs[0] - s_outs[0], a_outs[0]))
+    names = [k for k, _ in student.named_parameters()]
+    g_s = torch.autograd.grad(l_s, list(student.parameters()), retain_graph=True, allow_unused=True)
+    g_a = torch.autograd.grad(l_a, list(assistant.parameters()), retain_graph=True, allow_unused=True)
+    g_as = torch.autograd.grad(l_a, list(student.parameters()), allow_unused=True)
+    o_ls, o_la, og_s, og_a, og_as, (ot, os_, oa) = RO.kd_step(sds[0], sds[1], sds[2], x)
+    assert names == RO.resnet34_param_names(sds[1])
+    relo = lambda a, b: ((a - b).norm() / (b.norm() + 1e-30)).item()
+    for ref_o, ora_o in ((t_outs, ot), (s_outs, os_), (a_outs, oa)):
+        errs = [relo(b, a) for a, b in zip(ref_o, ora_o)]
+        print("output rel errors (emb, x1..x4):", ["%.2e" % e for e in errs])
+        # BatchNorm1d over a batch of 4 amplifies fp32 summation-order noise of the 25088-long dot products
+        assert errs[0] < 1e-3 and max(errs[1:]) < 1e-4, errs
+    assert abs(l_s.item() - o_ls.item()) <= 1e-5 * abs(l_s.item()) and abs(l_a.item() - o_la.item()) <= 1e-5 * abs(l_a.item())
+    rel = lambda a, b: ((a - b).norm() / (b.norm() + 1e-30)).item()
+    for gs, og in ((g_s, og_s), (g_a, og_a), (g_as, og_as)):
+        # fc.bias feeds a train-mode BatchNorm1d: its gradient is mathematically zero (rounding noise only)
+        worst = max((rel(og[k], g), k) for k, g in zip(names, gs) if k not in RO.RESNET_NULL_GRAD)
+        print("worst gradient rel error", worst)
+        assert worst[0] < 2e-2, worst   # fp32 summation-order noise through 36 train-mode BatchNorms (as for FSRNet)
+    nb = {}
+    RO.resnet34_forward(sds[1], x, training=True, new_buffers=nb)
+    new_sd = student.state_dict()
+    for k, v in nb.items():
+        assert torch.allclose(v.float(), new_sd[k].float(), rtol=1e-5, atol=1e-6), k
+    d = dict(l_s=l_s.item(), l_a=l_a.item(), names=np.array(names),
+             emb_t=t_outs[0].detach().numpy(), emb_s=s_outs[0].detach().numpy(), emb_a=a_outs[0].detach().numpy(),
+             feat_norms_s=np.array([o.norm().item() for o in s_outs[1:]]),
+             feat_means_s=np.array([o.mean().item() for o in s_outs[1:]]),
+             gnorm_s=np.array([g.norm().item() for g in g_s]), gnorm_a=np.array([g.norm().item() for g in g_a]),
+             gnorm_as=np.array([g.norm().item() for g in g_as]),
+             bn1_running_mean=new_sd["bn1.running_mean"].numpy(), bn1_running_var=new_sd["bn1.running_var"].numpy(),
+             bn_o2_running_var=new_sd["bn_o2.running_var"].numpy())
+    for k in ("bn1.weight", "layer2.0.downsample.1.weight", "layer4.2.bn2.bias", "bn_o2.weight", "fc.bias"):
+        i = names.index(k)
+        d["gs:" + k] = g_s[i].numpy(); d["ga:" + k] = g_a[i].numpy(); d["gas:" + k] = g_as[i].numpy()
+    np.savez_compressed(os.path.join(OUT, "resnet34.npz"), **d)
+    print("resnet34 kd", l_s.item(), l_a.item())
+
+
 if __name__ == "__main__":
     assert R.available(), "reference tree not present"
     os.makedirs(OUT, exist_ok=True)
-    golden_losses(); golden_bicubic(); golden_eval(); golden_fsrnet()
+    which = sys.argv[1:] or ["losses", "bicubic", "eval", "fsrnet", "resnet"]
+    for w in which:
+        globals()["golden_" + w]()

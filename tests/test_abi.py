@@ -73,7 +73,13 @@ def test_tcgen05_shape_support_table(lib):
     # edge layers ride the tensor cores through the lowered (im2col + GEMM) recipes
     assert sup(0, 128, 3, 64) and sup(2, 128, 3, 64) and not sup(1, 128, 3, 64)
     assert sup(0, 128, 64, 3) and sup(1, 128, 64, 3) and sup(0, 128, 3, 64, 7, 4, 3) and sup(1, 128, 3, 128, 7, 4, 3)
-    assert not sup(0, 32, 128, 11, 1, 1, 0) and sup(0, 100, 64, 64) and not sup(2, 100, 64, 64)
+    assert not sup(0, 32, 128, 11, 1, 1, 0) and sup(0, 100, 64, 64) and sup(2, 100, 64, 64)
+    # ResNet_34 trunk (model/resnet.py): wide layers use several column tiles, partial pixel tiles are zero filled,
+    # the stage transitions (3x3 s2, 1x1 s2) and the 7x7 s2 stem go through the lowered recipes
+    for op in (0, 1, 2):
+        assert sup(op, 56, 64, 64) and sup(op, 28, 128, 128) and sup(op, 14, 256, 256) and sup(op, 7, 512, 512)
+        assert sup(op, 56, 64, 128, 3, 2, 1) and sup(op, 28, 128, 256, 1, 2, 0) and sup(op, 14, 256, 512, 3, 2, 1)
+    assert sup(0, 112, 3, 64, 7, 2, 3) and sup(2, 112, 3, 64, 7, 2, 3)
 
 
 def test_module_mirror_keeps_reference_interface():
@@ -89,6 +95,22 @@ def test_module_mirror_keeps_reference_interface():
     for name in ("_coarse_sr_network", "_prior_estimation_network", "_fine_sr_encoder", "_fine_sr_decoder"):
         assert hasattr(net, name)                                     # used by name at FSR_main.py:146,158-159
     assert [k for k, _ in net.named_parameters()] == list(sd.keys())
+
+
+def test_resnet_mirror_keeps_reference_interface():
+    from crfr_b200.model.resnet import ResNet_34, ResNet, BasicBlock
+    from oracle import resnet_oracle as RO
+    torch.manual_seed(77)
+    net = ResNet_34()
+    sd = net.state_dict()
+    ref = RO.build_resnet34_state_dict(77)
+    assert list(sd.keys()) == list(ref.keys())
+    assert all(torch.equal(sd[k], ref[k]) for k in ref)               # identical seeded init, draw for draw
+    assert len(list(net.named_parameters())) == 114 and len(list(net.named_buffers())) == 3 * 38
+    with pytest.raises(AssertionError):
+        ResNet([96, 96], BasicBlock, [3, 4, 6, 3])                     # model/resnet.py:156
+    with pytest.raises(RuntimeError, match="CUDA"):
+        net(torch.zeros(1, 3, 112, 112))
 
 
 def test_product_fails_loudly_without_gpu():

@@ -34,6 +34,11 @@ DIRECT_SHAPES = [
     (128, 97, 1, 1, 0, 16),    # fc_landmark        (:392)
     (64, 64, 3, 1, 1, 16),     # residual conv on the direct engine (cross-check path)
     (192, 64, 3, 1, 1, 8),     # decoder conv_input (:432)
+    (3, 64, 7, 2, 3, 112),     # ResNet stem        (model/resnet.py:158)
+    (64, 128, 3, 2, 1, 56),    # layer2.0.conv1     (model/resnet.py:193-200: stage transition)
+    (64, 128, 1, 2, 0, 56),    # layer2.0.downsample.0
+    (256, 512, 3, 2, 1, 14),   # layer4.0.conv1
+    (256, 512, 1, 2, 0, 14),   # layer4.0.downsample.0
 ]
 
 

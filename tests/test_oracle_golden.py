@@ -133,3 +133,34 @@ def test_matcher_oracle_planted_identities():
     val, idx = EO.cosine_topk(p, g, 5)
     assert np.array_equal(idx[:, 0], ids)
     assert np.all(np.diff(val, axis=1) <= 0)
+
+
+def test_resnet34_kd_oracle_against_reference_fixture(golden_dir):
+    """oracle/resnet_oracle.py (ResNet_34 + KD losses) against tests/golden/resnet34.npz, which make_golden.py produced by
+    running the reference's own model/resnet.py with torch.nn.MSELoss (distill_main.py:63,68-70)."""
+    from oracle import resnet_oracle as RO
+    g = _load(golden_dir, "resnet34.npz")
+    sds = [RO.randomize_norm_params(RO.build_resnet34_state_dict(seed), 100 + i) for i, seed in enumerate((77, 78, 79))]
+    names = RO.resnet34_param_names(sds[1])
+    assert names == [str(n) for n in g["names"]] and len(names) == 114
+    assert sum(1 for k in sds[1] if k.endswith("running_mean")) == 38
+    x = RO.synthetic_faces(8)
+    l_s, l_a, g_s, g_a, g_as, (t_outs, s_outs, a_outs) = RO.kd_step(sds[0], sds[1], sds[2], x)
+    np.testing.assert_allclose(l_s.item(), float(g["l_s"]), rtol=1e-4)
+    np.testing.assert_allclose(l_a.item(), float(g["l_a"]), rtol=1e-4)
+    rel = lambda a, b: float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30))
+    assert rel(t_outs[0].numpy(), g["emb_t"]) < 1e-3 and rel(s_outs[0].detach().numpy(), g["emb_s"]) < 1e-3
+    assert rel(a_outs[0].detach().numpy(), g["emb_a"]) < 1e-3
+    np.testing.assert_allclose([o.norm().item() for o in s_outs[1:]], g["feat_norms_s"], rtol=1e-4)
+    for gs, key in ((g_s, "gnorm_s"), (g_a, "gnorm_a"), (g_as, "gnorm_as")):
+        ours = np.array([gs[k].norm().item() for k in names])
+        keep = np.array([k not in RO.RESNET_NULL_GRAD for k in names])
+        np.testing.assert_allclose(ours[keep], g[key][keep], rtol=2e-2)
+    for k in ("bn1.weight", "layer2.0.downsample.1.weight", "bn_o2.weight"):
+        assert rel(g_s[k].numpy(), g["gs:" + k]) < 2e-2 and rel(g_a[k].numpy(), g["ga:" + k]) < 2e-2
+        assert rel(g_as[k].numpy(), g["gas:" + k]) < 2e-2
+    nb = {}
+    RO.resnet34_forward(sds[1], x, training=True, new_buffers=nb)
+    np.testing.assert_allclose(nb["bn1.running_mean"].numpy(), g["bn1_running_mean"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(nb["bn1.running_var"].numpy(), g["bn1_running_var"], rtol=1e-4)
+    np.testing.assert_allclose(nb["bn_o2.running_var"].numpy(), g["bn_o2_running_var"], rtol=1e-3)

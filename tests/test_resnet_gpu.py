@@ -1,0 +1,118 @@
+"""ResNet_34 embedding + residual knowledge distillation (model/resnet.py, distill_main.py:59-74 of the reference):
+the native network program behind the drop-in module against the CPU oracle on identical weights and inputs.
+
+Tolerances: the embedding / stage features / losses / gradients are produced with bf16 storage; as for FSRNet the
+oracle's own bf16-storage evaluation (``precision="bf16"``) is the yardstick for the deviation that storage rounding
+makes unavoidable through 36 train-mode BatchNorms, with the 1e-2 bf16 budget of BASELINE.json on top."""
+import numpy as np
+import pytest
+import torch
+
+from tests.util import rel_err
+
+pytestmark = pytest.mark.gpu
+
+SLACK = 1.6
+B = 8
+
+
+def _nets():
+    from crfr_b200.model.resnet import ResNet_34
+    from oracle import resnet_oracle as RO
+    nets, sds = [], []
+    for i, seed in enumerate((77, 78, 79)):            # teacher, student, assistant (as in oracle/make_golden.py)
+        torch.manual_seed(seed)
+        net = ResNet_34()
+        sd = RO.randomize_norm_params(RO.build_resnet34_state_dict(seed), 100 + i)
+        net.load_state_dict(sd)
+        nets.append(net.cuda())
+        sds.append(sd)
+    return nets, sds
+
+
+def test_forward_train_eval_and_running_stats(cuda, golden_dir):
+    from oracle import resnet_oracle as RO
+    (teacher, student, _), sds = _nets()
+    g = np.load(golden_dir + "/resnet34.npz")
+    x = RO.synthetic_faces(B)
+    # eval mode (teacher): running statistics
+    teacher.eval()
+    with torch.no_grad():
+        t_outs = teacher(x.cuda())
+    ref = RO.resnet34_forward(sds[0], x, training=False)
+    emu = RO.resnet34_forward(sds[0], x, training=False, pr=RO.Precision("bf16"))
+    assert rel_err(ref[0], torch.from_numpy(g["emb_t"])) < 1e-3              # oracle == reference fixture
+    for o, r, e in zip(t_outs, ref, emu):
+        assert o.dtype == torch.float32 and o.shape == r.shape and torch.isfinite(o).all()
+        assert rel_err(o, r) < SLACK * rel_err(e, r) + 1e-2, (rel_err(o, r), rel_err(e, r))
+    # train mode (student): batch statistics + buffer update
+    student.train()
+    nb = {}
+    ref = RO.resnet34_forward(sds[1], x, training=True, new_buffers=nb)
+    emu = RO.resnet34_forward(sds[1], x, training=True, pr=RO.Precision("bf16"))
+    s_outs = student(x.cuda())
+    for o, r, e in zip(s_outs, ref, emu):
+        assert rel_err(o, r) < SLACK * rel_err(e, r) + 1e-2, (rel_err(o, r), rel_err(e, r))
+    new_sd = student.state_dict()
+    for k in ("bn1.running_mean", "bn1.running_var", "layer2.0.downsample.1.running_var", "layer4.2.bn2.running_mean",
+              "bn_o1.running_var", "bn_o2.running_mean", "bn_o2.running_var"):
+        # the BatchNorm1d statistics are means of 8 bf16-rounded fc outputs: looser than the image-sized BatchNorms
+        assert rel_err(new_sd[k], nb[k]) < (6e-2 if k.startswith("bn_o2") else 2e-2), k
+    assert int(new_sd["bn1.num_batches_tracked"]) == 1 and int(new_sd["layer3.5.bn2.num_batches_tracked"]) == 1
+    assert rel_err(new_sd["bn1.running_mean"], torch.from_numpy(g["bn1_running_mean"])) < 2e-2
+
+
+def test_kd_step_losses_and_gradients(cuda, golden_dir):
+    """distill_main.py:59-74 on one forward: L_s, L_a, dL_s/dtheta_S, dL_a/dtheta_A and dL_a/dtheta_S."""
+    from crfr_b200.loss import MSELoss, ResidualKDLoss
+    from oracle import resnet_oracle as RO
+    (teacher, student, assistant), sds = _nets()
+    g = np.load(golden_dir + "/resnet34.npz")
+    x = RO.synthetic_faces(B)
+    teacher.eval(); student.train(); assistant.train()
+    xc = x.cuda()
+    with torch.no_grad():
+        t_outs = teacher(xc)
+    s_outs = student(xc)
+    a_outs = assistant(xc)
+    mse, kd = MSELoss(), ResidualKDLoss()
+    l_s = mse(s_outs[0], t_outs[0].detach())
+    l_a = sum(kd(t_outs[k], s_outs[k], a_outs[k]) for k in (1, 2, 3, 4)) + kd(t_outs[0], s_outs[0], a_outs[0])
+    names = [k for k, _ in student.named_parameters()]
+    g_s = torch.autograd.grad(l_s, list(student.parameters()), retain_graph=True)
+    g_a = torch.autograd.grad(l_a, list(assistant.parameters()), retain_graph=True)
+    g_as = torch.autograd.grad(l_a, list(student.parameters()))
+    torch.cuda.synchronize()
+
+    r_ls, r_la, rg_s, rg_a, rg_as, _ = RO.kd_step(sds[0], sds[1], sds[2], x)
+    e_ls, e_la, eg_s, eg_a, eg_as, _ = RO.kd_step(sds[0], sds[1], sds[2], x, precision="bf16")
+    assert abs(r_ls.item() - float(g["l_s"])) < 1e-4 * abs(float(g["l_s"]))   # oracle == reference fixture
+    assert abs(r_la.item() - float(g["l_a"])) < 1e-4 * abs(float(g["l_a"]))
+    for ours, r, e in ((l_s, r_ls, e_ls), (l_a, r_la, e_la)):
+        assert abs(ours.item() - r.item()) < SLACK * abs(e.item() - r.item()) + 1e-2 * abs(r.item())
+    for tag, ours_g, ref_g, emu_g in (("s", g_s, rg_s, eg_s), ("a", g_a, rg_a, eg_a), ("as", g_as, rg_as, eg_as)):
+        flat_o, flat_r, flat_e = [], [], []
+        for k, og in zip(names, ours_g):
+            assert torch.isfinite(og).all(), (tag, k)
+            if k in RO.RESNET_NULL_GRAD:
+                continue
+            e_ours, e_emu = rel_err(og, ref_g[k]), rel_err(emu_g[k], ref_g[k])
+            assert e_ours < SLACK * e_emu + 2e-2, (tag, k, e_ours, e_emu)
+            flat_o.append(og.flatten().cpu().double()); flat_r.append(ref_g[k].flatten().double())
+            flat_e.append(emu_g[k].flatten().double())
+        a, b, c = torch.cat(flat_o), torch.cat(flat_r), torch.cat(flat_e)
+        cos_ours, cos_emu = float(a @ b / (a.norm() * b.norm())), float(c @ b / (c.norm() * b.norm()))
+        # direction and length of the whole gradient: as good as the bf16-storage evaluation of the oracle itself
+        # (with 8 samples behind the BatchNorm1d that evaluation is ~0.8 from fp32 on the student loss)
+        assert cos_ours > min(0.98, cos_emu - 0.02), (tag, cos_ours, cos_emu)
+        assert abs(a.norm().item() - b.norm().item()) < max(5e-2 * b.norm().item(),
+                                                            SLACK * abs(c.norm().item() - b.norm().item())), tag
+
+
+def test_rejects_unsupported(cuda):
+    from crfr_b200.model.resnet import ResNet_34
+    net = ResNet_34().cuda()
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(2, 3, 112, 112))
+    with pytest.raises(ValueError):
+        net(torch.zeros(2, 3, 96, 96, device="cuda"))

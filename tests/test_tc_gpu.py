@@ -22,6 +22,10 @@ TC_SHAPES = [
     (9, 128, 128, 4),     # 64x64-input hourglass floor (eight images per tile)
     (2, 192, 64, 32),     # decoder conv_input on cat(prior, encoder)
     (1, 64, 64, 64),      # two rows per tile
+    (2, 64, 64, 56),      # ResNet_34 layer1 (model/resnet.py:161): 112-pixel tiles (partial, zero-filled for wgrad)
+    (2, 128, 128, 28),    # layer2
+    (3, 256, 256, 14),    # layer3: 126-pixel tiles, ragged last tile
+    (5, 512, 512, 7),     # layer4: two images per tile, two 256-wide column tiles
 ]
 
 
