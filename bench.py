@@ -103,6 +103,72 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one rowconv_kernel launch over 128 images from the committed
+# `ncu --set full` capture (profiles/r1_rowconv_ncu_full.txt): 273.3 MB + 221.5 MB (algorithmic: 268.4 MB in + 268.4 MB
+# out; part of the output is still dirty in the 126 MB L2 when the kernel ends)
+ROWCONV_TRAFFIC_BYTES_PER_IMAGE = (273.27e6 + 221.48e6) / 128
+
+
+def time_matcher(torch, ops, probes=10000, gallery=1000000, dim=512, k=5, reps=3):
+    """Cosine-similarity identification (BASELINE.json configs[3]): 10 k probes x 1 M-entry 512-d gallery, top-5."""
+    g = torch.Generator(device="cuda").manual_seed(11)
+    gal = ops.l2norm_bf16(torch.randn(gallery, dim, generator=g, device="cuda"))
+    ids = torch.randint(0, gallery, (probes,), generator=g, device="cuda")
+    pr = ops.l2norm_bf16(gal[ids].float() + 0.3 * torch.randn(probes, dim, generator=g, device="cuda") / dim ** 0.5)
+    val, idx = ops.cosine_topk(pr, gal, k)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        val, idx = ops.cosine_topk(pr, gal, k)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    hit = float((idx[:, 0].long() == ids).float().mean().item())
+    return {"queries_per_sec": probes / (ms * 1e-3), "ms": ms, "tflops": 2.0 * probes * gallery * dim / (ms * 1e-3) / 1e12,
+            "rank1_hit_rate": hit, "workload": "%d probes x %d x %d gallery, top-%d, bf16" % (probes, gallery, dim, k)}
+
+
+def time_kd_step(torch, batch=256, reps=3):
+    """Residual-KD step (BASELINE.json configs[2]): teacher forward (eval) + student and assistant forward/backward."""
+    from crfr_b200.loss import MSELoss, ResidualKDLoss
+    from crfr_b200.model.resnet import ResNet_34
+    torch.manual_seed(7)
+    nets = [ResNet_34().cuda() for _ in range(3)]
+    for n in nets:                       # zero-initialised bn2 weights would make every residual branch vanish
+        for k, p in n.named_parameters():
+            if k.endswith("bn2.weight"):
+                p.data.fill_(0.5)
+    teacher, student, assistant = nets
+    teacher.eval(); student.train(); assistant.train()
+    x = torch.randn(batch, 3, 112, 112, device="cuda")
+    mse, kd = MSELoss(), ResidualKDLoss()
+
+    def step():
+        with torch.no_grad():
+            t = teacher(x)
+        s, a = student(x), assistant(x)
+        l_s = mse(s[0], t[0])
+        l_a = sum(kd(t[k], s[k], a[k]) for k in (1, 2, 3, 4)) + kd(t[0], s[0], a[0])
+        for n in (student, assistant):
+            n.zero_grad(set_to_none=True)
+        (l_s + l_a).backward()
+        return l_s, l_a
+    step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        l_s, l_a = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    flop = 55.65e9 + 14.35e9             # SURVEY.md 8(d): incl. dL_a/dtheta_S, which this graph propagates
+    return {"images_per_sec": batch / (ms * 1e-3), "ms_per_step": ms, "tflops": batch * flop / (ms * 1e-3) / 1e12,
+            "student_loss": float(l_s.item()), "assistant_loss": float(l_a.item()),
+            "workload": "ResNet_34 teacher(eval) + student + assistant KD step, batch %d, 112x112" % batch}
+
+
 def time_dominant_kernel(torch, ops, L, chunk):
     """CUDA-event timing of the dominant kernel: the 3x3 64->64 implicit GEMM at 128x128 (87 % of the MACs)."""
     g = torch.Generator(device="cuda").manual_seed(3)
@@ -229,9 +295,17 @@ def run_ours(args):
                 "step_tensor_frac": {"achieved_tflops": value / world * FLOP_PER_IMG_TRAIN / 1e12,
                                      "peak_tflops_sustained": sustained,
                                      "frac": value / world * FLOP_PER_IMG_TRAIN / 1e12 / sustained, "peak": how},
-                "roofline": {"bound": "tensor", "kernel": "tc_conv_kernel<64> (3x3 64->64 @128x128, %d images)" % args.chunk,
+                "roofline": {"bound": "tensor", "kernel": "rowconv_kernel (3x3 64->64 @128x128 forward, %d images per "
+                                                          "launch)" % args.chunk,
                              "achieved": k_tflops, "peak": burst, "unit": "TFLOP/s", "frac": k_tflops / burst,
-                             "traffic": None, "ms_per_launch": k_ms, "flops_per_launch": k_flops, "peak_source": how}}
+                             "traffic": ROWCONV_TRAFFIC_BYTES_PER_IMAGE * args.chunk, "ms_per_launch": k_ms,
+                             "flops_per_launch": k_flops, "peak_source": how}}
+        if not args.no_extras:
+            # the other two BASELINE.json paths, measured in the same run (secondary numbers, not the headline metric)
+            trainer.ws = None
+            torch.cuda.empty_cache()
+            line["matcher"] = time_matcher(torch, ops)
+            line["kd_step"] = time_kd_step(torch)
         if not args.no_cpu_baseline:
             v, cores, sec = cpu_reference_step_rate(3, 1)
             line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
@@ -250,6 +324,7 @@ def main():
     ap.add_argument("--batch", type=int, default=128)
     ap.add_argument("--chunk", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the matcher / KD-step secondary measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
