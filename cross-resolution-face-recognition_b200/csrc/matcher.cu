@@ -2,10 +2,14 @@
 // the [probes x gallery] score matrix is never materialised) and squared-L2 threshold verification.
 //
 // One CTA owns a tile of 128 probes (A operand, resident in smem for the CTA's lifetime: 128 x dim bf16) and walks a
-// contiguous range of gallery blocks of 128 rows (B operand, streamed by TMA through a 4-stage ring).  Scores
-// accumulate in TMEM (two 128-column accumulators, double buffered) and the 4 epilogue warps - one thread per probe
-// row - drain them with tcgen05.ld and keep a register-resident sorted top-8 per probe.  Per-split results are
-// merged by crfr_topk_merge (also used for gallery-sharded multi-GPU matching).
+// contiguous range of gallery blocks of 256 rows (B operand, streamed by TMA through a 4-stage ring; N = 256 MMAs:
+// the A-operand fetch is paid once per 256 columns, which keeps the shared-memory port below saturation).  Scores
+// accumulate in TMEM (two 256-column accumulators = all 512 columns, double buffered) and the 4 epilogue warps - one
+// thread per probe row - drain them with tcgen05.ld and keep a register-resident sorted top-8 per probe.  The drain
+// is written for a small instruction footprint: 8 scores are compared against the current 8th-best through one
+// running maximum, and the insertion network is only entered for a group that contains a candidate (measured: the
+// fully unrolled per-score insertion was 173 KB of SASS and instruction-fetch bound at 100 TFLOP/s).  Per-split
+// results are merged by crfr_topk_merge (also used for gallery-sharded multi-GPU matching).
 //
 // ref: utils/eval.py:6-19 (accuracy -> output.topk(maxk, 1, True, True)), utils/utils.py:14-24,41-43 (threshold on
 //      squared L2), DISTILLATION/model/model_irse.py:16-20 (l2_norm).
@@ -22,14 +26,16 @@ namespace {
 
 constexpr int kTopK = 8;        // register-resident candidates per probe
 constexpr int kThreads = 192;   // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
-constexpr int kStages = 4;
-constexpr int kTile = 128 * 128;  // 16 KB: 128 rows x 64 bf16
+constexpr int kStages = 3;     // 3 x 32 KB gallery stages + 128 KB of resident probes fill the 227 KB of shared memory at dim 512
+constexpr int kTile = 128 * 128;  // 16 KB: 128 rows x 64 bf16 (probe tile per K chunk)
+constexpr int kGBlock = 256;      // gallery rows per MMA (N)
+constexpr int kBTile = kGBlock * 128;  // 32 KB: 256 rows x 64 bf16
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int make_rows_map(CUtensorMap* m, const void* ptr, long long rows, int dim) {
+int make_rows_map(CUtensorMap* m, const void* ptr, long long rows, int dim, int box_rows) {
   static EncodeTiledFn enc = nullptr;
   if (!enc) {
     void* p = nullptr;
@@ -43,7 +49,7 @@ int make_rows_map(CUtensorMap* m, const void* ptr, long long rows, int dim) {
   }
   cuuint64_t dims[2] = {(cuuint64_t)dim, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)dim * 2};
-  cuuint32_t box[2] = {64, 128};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
   cuuint32_t es[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -85,7 +91,7 @@ struct MatchParams {
   int p;               // probes
   long long g;         // gallery rows
   int kchunks;         // dim / 64
-  int nblocks;         // gallery blocks of 128
+  int nblocks;         // gallery blocks of kGBlock rows
   int blocks_per_split;
   int index_base;
   float* out_val;      // [splits][p][kTopK]
@@ -97,8 +103,8 @@ cosine_topk_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = base;                                 // kchunks x 16 KB
-  uint8_t* sB = base + mp.kchunks * kTile;            // kStages x 16 KB
-  uint64_t* full = (uint64_t*)(sB + kStages * kTile);
+  uint8_t* sB = base + mp.kchunks * kTile;            // kStages x 32 KB
+  uint64_t* full = (uint64_t*)(sB + kStages * kBTile);
   uint64_t* empty = full + kStages;
   uint64_t* a_full = empty + kStages;
   uint64_t* acc_full = a_full + 1;    // [2]
@@ -120,7 +126,7 @@ cosine_topk_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
     prefetch_tmap(&tmP);
     prefetch_tmap(&tmG);
   }
-  if (warp == 1) tmem_alloc<256>(tmem_slot);
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -144,13 +150,13 @@ cosine_topk_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
         const int s = it % kStages;
         mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
         if (leader) {
-          mbar_expect_tx(&full[s], kTile);
-          tma_load_2d(sB + s * kTile, &tmG, &full[s], kc * 64, (blk0 + b) * 128);
+          mbar_expect_tx(&full[s], kBTile);
+          tma_load_2d(sB + s * kBTile, &tmG, &full[s], kc * 64, (blk0 + b) * kGBlock);
         }
       }
   } else if (warp == 1) {
     const bool leader = elect_one();
-    const uint32_t idesc = make_idesc_bf16(128, 128, 0, 0);
+    const uint32_t idesc = make_idesc_bf16(128, kGBlock, 0, 0);
     const uint64_t adesc0 = make_smem_desc_sw128(smem_u32(sA), 16, 1024);
     const uint64_t bdesc0 = make_smem_desc_sw128(smem_u32(sB), 16, 1024);
     mbar_wait(a_full, 0);
@@ -163,10 +169,10 @@ cosine_topk_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
         const int s = it % kStages;
         mbar_wait(&full[s], (it / kStages) & 1);
         tc_fence_after();
-        const uint64_t da = adesc0 + (uint64_t)((kc * kTile) >> 4), db = bdesc0 + (uint64_t)((s * kTile) >> 4);
+        const uint64_t da = adesc0 + (uint64_t)((kc * kTile) >> 4), db = bdesc0 + (uint64_t)((s * kBTile) >> 4);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          if (leader) umma_bf16(tmem + buf * 128, da + 2 * k, db + 2 * k, idesc, (uint32_t)((kc | k) != 0));
+          if (leader) umma_bf16(tmem + buf * kGBlock, da + 2 * k, db + 2 * k, idesc, (uint32_t)((kc | k) != 0));
         if (leader) umma_commit(&empty[s]);
         __syncwarp();
       }
@@ -182,16 +188,26 @@ cosine_topk_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
       const int buf = b & 1;
       mbar_wait(&acc_full[buf], (b >> 1) & 1);
       tc_fence_after();
-      const long long col0 = (long long)(blk0 + b) * 128;
-#pragma unroll
-      for (int c0 = 0; c0 < 128; c0 += 32) {
+      const long long col0 = (long long)(blk0 + b) * kGBlock;
+      const int valid = (int)min((long long)kGBlock, mp.g - col0);   // columns past the end of the gallery are masked
+#pragma unroll 1
+      for (int c0 = 0; c0 < kGBlock; c0 += 32) {
         uint32_t v[32];
-        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + buf * 128 + c0, v);
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + buf * kGBlock + c0, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const long long gi = col0 + c0 + j;
-          if (gi < mp.g) top.push(__uint_as_float(v[j]), (int)gi + mp.index_base);
+        for (int g8 = 0; g8 < 32; g8 += 8) {
+          float x[8];
+          float m = -INFINITY;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            x[e] = (c0 + g8 + e < valid) ? __uint_as_float(v[g8 + e]) : -INFINITY;
+            m = fmaxf(m, x[e]);
+          }
+          if (m > top.v[kTopK - 1]) {   // rare after the first few blocks: one compare per 8 scores on the hot path
+#pragma unroll
+            for (int e = 0; e < 8; ++e) top.push(x[e], (int)(col0 + c0 + g8 + e) + mp.index_base);
+          }
         }
       }
       tc_fence_before();
@@ -212,7 +228,7 @@ cosine_topk_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<256>(tmem);
+    tmem_dealloc<512>(tmem);
   }
 }
 
@@ -350,7 +366,7 @@ struct SplitPlan {
 SplitPlan plan_splits(int p, long long g) {
   SplitPlan s;
   s.tiles = (p + 127) / 128;
-  s.nblocks = (int)((g + 127) / 128);
+  s.nblocks = (int)((g + kGBlock - 1) / kGBlock);
   int want = (148 * 8 + s.tiles - 1) / s.tiles;
   if (want > s.nblocks) want = s.nblocks;
   if (want < 1) want = 1;
@@ -394,14 +410,14 @@ extern "C" int crfr_cosine_topk(int engine, const void* probes, const void* gall
   }
   cudaStream_t st = (cudaStream_t)stream;
   CUtensorMap tmP, tmG;
-  CRFR_TRY(make_rows_map(&tmP, probes, p, dim));
-  CRFR_TRY(make_rows_map(&tmG, gallery, g, dim));
+  CRFR_TRY(make_rows_map(&tmP, probes, p, dim, 128));
+  CRFR_TRY(make_rows_map(&tmG, gallery, g, dim, kGBlock));
   MatchParams mp;
   mp.p = p; mp.g = g; mp.kchunks = dim / 64; mp.nblocks = s.nblocks; mp.blocks_per_split = s.blocks_per_split;
   mp.index_base = index_base;
   mp.out_val = (float*)ws;
   mp.out_idx = (int*)((float*)ws + (size_t)s.splits * p * kTopK);
-  const int smem = (mp.kchunks + kStages) * kTile + 1024 + 256;
+  const int smem = mp.kchunks * kTile + kStages * kBTile + 1024 + 256;
   static int attr_smem = 0;
   if (smem > attr_smem) {
     CRFR_CUDA(cudaFuncSetAttribute(cosine_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

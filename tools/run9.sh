@@ -1,3 +1,5 @@
 mkdir -p gpurun_out
-python tools/bench_norm.py 128 > gpurun_out/plain_norm128.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"norm_act_fwd_kernel|norm_act_bwd_reduce_kernel|norm_act_bwd_apply_kernel|stats_partial_kernel" -s 8 -c 4 -f -o gpurun_out/norm_r1 python tools/bench_norm.py 128 > gpurun_out/ncu_norm.log 2>&1
-tail -n 4 gpurun_out/plain_norm128.log; tail -n 3 gpurun_out/ncu_norm.log
+timeout 600 python -m pytest tests/test_tc_gpu.py -q -m gpu -k "matcher" --timeout 300 > gpurun_out/t_match.log 2>&1; echo "exit $?" >> gpurun_out/t_match.log; tail -n 6 gpurun_out/t_match.log
+timeout 600 python -m pytest tests/test_kernels_gpu.py -q -m gpu -k "eval" --timeout 300 2>&1 | tail -n 3
+python tools/bench_match.py 4096 262144 2>&1 | tail -n 1
+python tools/bench_match.py 10000 1000000 2>&1 | tail -n 1
