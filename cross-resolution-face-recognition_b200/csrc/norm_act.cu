@@ -105,38 +105,33 @@ stats_partial_kernel(const bf16* __restrict__ y, int ld, int hw, int c, int chun
   cta_reduce_store<2>(acc, smem, cg, lane, lanes, c, partial + ((long long)n * gridDim.x + chunk) * 2 * c);
 }
 
-// one CTA per image: 256 threads = (256 / c) chunk lanes x c channels; deterministic two-level sum over the chunks
+// grid (image, slab of 8 channels): 256 threads = 32 chunk lanes x 8 channels; deterministic two-level sum over the
+// chunk partials (lane-strided, then lanes in order).  BatchNorm (one group over the whole batch) has hundreds of
+// chunks: the slabs keep its finalisation parallel instead of one CTA walking every channel.
 __global__ void __launch_bounds__(kThreads)
 stats_finalize_kernel(const float* __restrict__ partial, int chunks, int c, float inv_hw, float eps,
                       float* __restrict__ stats) {
   __shared__ float sm[2][kThreads];
-  const int n = blockIdx.x;
+  const int n = blockIdx.x, ch = blockIdx.y * 8 + (threadIdx.x & 7), lane = threadIdx.x >> 3;
   const float* p = partial + (long long)n * chunks * 2 * c;
-  for (int c0 = 0; c0 < c; c0 += kThreads) {
-    const int cw = min(c - c0, kThreads);          // channels handled in this pass
-    const int lanes = kThreads / cw;
-    const int ch = threadIdx.x % cw, lane = threadIdx.x / cw;
-    float s = 0.f, q = 0.f;
-    if (lane < lanes)
-      for (int k = lane; k < chunks; k += lanes) {
-        s += p[(k * 2 + 0) * c + c0 + ch];
-        q += p[(k * 2 + 1) * c + c0 + ch];
-      }
-    sm[0][threadIdx.x] = s;
-    sm[1][threadIdx.x] = q;
-    __syncthreads();
-    if (threadIdx.x < cw) {
-      float ts = 0.f, tq = 0.f;
-      for (int l = 0; l < lanes; ++l) {
-        ts += sm[0][l * cw + threadIdx.x];
-        tq += sm[1][l * cw + threadIdx.x];
-      }
-      const float mean = ts * inv_hw;
-      const float var = fmaxf(tq * inv_hw - mean * mean, 0.f);
-      stats[2 * (n * c + c0 + threadIdx.x)] = mean;
-      stats[2 * (n * c + c0 + threadIdx.x) + 1] = rsqrtf(var + eps);
+  float s = 0.f, q = 0.f;
+  for (int k = lane; k < chunks; k += 32) {
+    s += p[(k * 2 + 0) * c + ch];
+    q += p[(k * 2 + 1) * c + ch];
+  }
+  sm[0][threadIdx.x] = s;
+  sm[1][threadIdx.x] = q;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float ts = 0.f, tq = 0.f;
+    for (int l = 0; l < 32; ++l) {
+      ts += sm[0][l * 8 + threadIdx.x];
+      tq += sm[1][l * 8 + threadIdx.x];
     }
-    __syncthreads();
+    const float mean = ts * inv_hw;
+    const float var = fmaxf(tq * inv_hw - mean * mean, 0.f);
+    stats[2 * (n * c + ch)] = mean;
+    stats[2 * (n * c + ch) + 1] = rsqrtf(var + eps);
   }
 }
 
@@ -266,37 +261,30 @@ norm_act_bwd_reduce_kernel(const bf16* __restrict__ da, int da_ld, const bf16* _
   cta_reduce_store<3>(acc, smem, cg, lane, lanes, c, partial + ((long long)n * gridDim.x + chunk) * 3 * c);
 }
 
-// one CTA per image: fold the chunk partials -> bstats[n][ch] = (mean dz, mean dz*xhat); tot[n][3][c]
+// grid (image, slab of 8 channels): fold the chunk partials -> bstats[n][ch] = (mean dz, mean dz*xhat); tot[n][3][c]
 __global__ void __launch_bounds__(kThreads)
 bwd_fold_kernel(const float* __restrict__ partial, int chunks, int c, float inv_hw, float* __restrict__ bstats,
                 float* __restrict__ tot) {
   __shared__ float sm[3][kThreads];
-  const int n = blockIdx.x;
+  const int n = blockIdx.x, ch = blockIdx.y * 8 + (threadIdx.x & 7), lane = threadIdx.x >> 3;
   const float* p = partial + (long long)n * chunks * 3 * c;
-  for (int c0 = 0; c0 < c; c0 += kThreads) {
-    const int cw = min(c - c0, kThreads);
-    const int lanes = kThreads / cw;
-    const int ch = threadIdx.x % cw, lane = threadIdx.x / cw;
-    float s[3] = {0.f, 0.f, 0.f};
-    if (lane < lanes)
-      for (int k = lane; k < chunks; k += lanes)
+  float s[3] = {0.f, 0.f, 0.f};
+  for (int k = lane; k < chunks; k += 32)
 #pragma unroll
-        for (int j = 0; j < 3; ++j) s[j] += p[(k * 3 + j) * c + c0 + ch];
+    for (int j = 0; j < 3; ++j) s[j] += p[(k * 3 + j) * c + ch];
 #pragma unroll
-    for (int j = 0; j < 3; ++j) sm[j][threadIdx.x] = s[j];
-    __syncthreads();
-    if (threadIdx.x < cw) {
-      float t[3] = {0.f, 0.f, 0.f};
-      for (int l = 0; l < lanes; ++l)
+  for (int j = 0; j < 3; ++j) sm[j][threadIdx.x] = s[j];
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float t[3] = {0.f, 0.f, 0.f};
+    for (int l = 0; l < 32; ++l)
 #pragma unroll
-        for (int j = 0; j < 3; ++j) t[j] += sm[j][l * cw + threadIdx.x];
-      const int i = n * c + c0 + threadIdx.x;
-      bstats[2 * i] = t[0] * inv_hw;
-      bstats[2 * i + 1] = t[1] * inv_hw;
+      for (int j = 0; j < 3; ++j) t[j] += sm[j][l * 8 + threadIdx.x];
+    const int i = n * c + ch;
+    bstats[2 * i] = t[0] * inv_hw;
+    bstats[2 * i + 1] = t[1] * inv_hw;
 #pragma unroll
-      for (int j = 0; j < 3; ++j) tot[(n * 3 + j) * c + c0 + threadIdx.x] = t[j];
-    }
-    __syncthreads();
+    for (int j = 0; j < 3; ++j) tot[(n * 3 + j) * c + ch] = t[j];
   }
 }
 
@@ -398,7 +386,7 @@ size_t crfr_norm_ws_bytes(int n, int hw, int c) {
 // Finalise (mean, rstd) from partials laid out [n][chunks][2][c]; shared with the conv epilogue statistics.
 int crfr_norm_finalize(const float* partial, int n, int chunks, int hw, int c, float eps, float* stats,
                        cudaStream_t st) {
-  stats_finalize_kernel<<<n, kThreads, 0, st>>>(partial, chunks, c, 1.f / (float)hw, eps, stats);
+  stats_finalize_kernel<<<dim3(n, c / 8), kThreads, 0, st>>>(partial, chunks, c, 1.f / (float)hw, eps, stats);
   CRFR_COUNT_LAUNCH();
   CRFR_LAUNCH_CHECK();
   return CRFR_OK;
@@ -492,7 +480,7 @@ extern "C" int crfr_norm_act_bwd(const void* dout_a, int da_ld, const void* dout
       (const bf16*)res, res_ld, (bf16*)dz, dz_ld, hw, c, pl.chunk_pix, partial);
   CRFR_COUNT_LAUNCH();
   CRFR_LAUNCH_CHECK();
-  bwd_fold_kernel<<<n, kThreads, 0, st>>>(partial, pl.chunks, c, 1.f / (float)hw, bstats, tot);
+  bwd_fold_kernel<<<dim3(n, c / 8), kThreads, 0, st>>>(partial, pl.chunks, c, 1.f / (float)hw, bstats, tot);
   CRFR_COUNT_LAUNCH();
   CRFR_LAUNCH_CHECK();
   norm_act_bwd_apply_kernel<<<dim3(pl.chunks, n), kThreads, 0, st>>>((const bf16*)dz, dz_ld, (const bf16*)y, y_ld,

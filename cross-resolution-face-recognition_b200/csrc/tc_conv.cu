@@ -119,6 +119,7 @@ struct ConvParams {
   int n, h, w;
   int kchunks, ksize, ntaps, pad, sign;
   int bw, bh, bn, tiles_x, tiles_y, rows;
+  int total_tiles; // pixel tiles (a CTA walks several)
   int n_total;     // all output channels; this CTA computes columns [blockIdx.y * N, +N)
   int out_ld;
   int out_f32;     // 0: bf16 NHWC rows, 1: fp32 NHWC rows
@@ -138,9 +139,12 @@ struct ConvCfg {
   static constexpr int kOutTiles = (N + 63) / 64;               // 64-channel sub-tiles staged for the TMA store
   static constexpr int kOutBytes = kOutTiles * kATileBytes;
   static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + 1024 /*align slack*/ + 256 /*barriers*/;
-  static_assert(N % 32 == 0 && N <= 256, "tile width");
+  static_assert(N % 32 == 0 && N <= 256 && 2 * kTmemCols <= 512, "tile width");
 };
 
+// Persistent: the grid is (CTAs, column tiles); a CTA walks pixel tiles blockIdx.x, blockIdx.x + gridDim.x, ... so
+// that barrier setup / TMEM allocation are paid once and - with two TMEM accumulators - the epilogue of tile i
+// overlaps the TMA + MMA work of tile i+1 (the layers on this kernel have short K loops: 9-72 steps per tile).
 template <int N>
 __global__ void __launch_bounds__(kConvThreads, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -151,8 +155,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* sOut = base + Cfg::kStages * Cfg::kStageBytes;
   uint64_t* full = (uint64_t*)(sOut + Cfg::kOutBytes);
   uint64_t* empty = full + Cfg::kStages;
-  uint64_t* tmem_full = empty + Cfg::kStages;
-  uint32_t* tmem_slot = (uint32_t*)(tmem_full + 1);
+  uint64_t* tmem_full = empty + Cfg::kStages;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;         // [2]
+  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -160,111 +165,153 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(tmem_full, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full[b], 1);
+      mbar_init(&tmem_empty[b], 4);
+    }
     fence_barrier_init();
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
+    prefetch_tmap(&tmY);
   }
-  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  if (warp == 1) tmem_alloc<2 * Cfg::kTmemCols>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  int t = blockIdx.x;
-  const int tx = t % p.tiles_x; t /= p.tiles_x;
-  const int ty = t % p.tiles_y; t /= p.tiles_y;
-  const int x0 = tx * p.bw, y0 = ty * p.bh, n0 = t * p.bn;
   const int iters = p.ntaps * p.kchunks;
   const uint32_t a_bytes = (uint32_t)p.rows * 128u;
   const int ncol0 = blockIdx.y * N;
+  const int my_tiles = (int)blockIdx.x < p.total_tiles ? (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   if (warp == 0) {
     const bool leader = elect_one();
-    for (int it = 0; it < iters; ++it) {
-      const int s = it % Cfg::kStages;
-      mbar_wait(&empty[s], ((it / Cfg::kStages) & 1) ^ 1);
-      const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
-      const int ky = tap / p.ksize, kx = tap - ky * p.ksize;
-      uint8_t* sa = base + s * Cfg::kStageBytes;
-      if (leader) {
-        mbar_expect_tx(&full[s], a_bytes + Cfg::kBTileBytes);
-        tma_load_4d(sa, &tmA, &full[s], kc * 64, x0 + p.sign * (kx - p.pad), y0 + p.sign * (ky - p.pad), n0);
-        tma_load_2d(sa + kATileBytes, &tmB, &full[s], kc * 64, tap * p.n_total + ncol0);
+    int g = 0;   // running stage index across tiles
+    for (int i = 0; i < my_tiles; ++i) {
+      int t = blockIdx.x + i * gridDim.x;
+      const int tx = t % p.tiles_x; t /= p.tiles_x;
+      const int ty = t % p.tiles_y; t /= p.tiles_y;
+      const int x0 = tx * p.bw, y0 = ty * p.bh, n0 = t * p.bn;
+      for (int it = 0; it < iters; ++it, ++g) {
+        const int s = g % Cfg::kStages;
+        mbar_wait(&empty[s], ((g / Cfg::kStages) & 1) ^ 1);
+        const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
+        const int ky = tap / p.ksize, kx = tap - ky * p.ksize;
+        uint8_t* sa = base + s * Cfg::kStageBytes;
+        if (leader) {
+          mbar_expect_tx(&full[s], a_bytes + Cfg::kBTileBytes);
+          tma_load_4d(sa, &tmA, &full[s], kc * 64, x0 + p.sign * (kx - p.pad), y0 + p.sign * (ky - p.pad), n0);
+          tma_load_2d(sa + kATileBytes, &tmB, &full[s], kc * 64, tap * p.n_total + ncol0);
+        }
       }
     }
   } else if (warp == 1) {
     const bool leader = elect_one();
     const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
     const uint64_t desc0 = make_smem_desc_sw128(smem_u32(base), 16, 1024);
-    for (int it = 0; it < iters; ++it) {
-      const int s = it % Cfg::kStages;
-      mbar_wait(&full[s], (it / Cfg::kStages) & 1);
+    int g = 0;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int buf = i & 1;
+      mbar_wait(&tmem_empty[buf], ((i >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator
       tc_fence_after();
-      const uint64_t da = desc0 + (uint64_t)((s * Cfg::kStageBytes) >> 4);
-      const uint64_t db = da + (uint64_t)(kATileBytes >> 4);
+      const uint32_t d_tmem = tmem + buf * Cfg::kTmemCols;
+      for (int it = 0; it < iters; ++it, ++g) {
+        const int s = g % Cfg::kStages;
+        mbar_wait(&full[s], (g / Cfg::kStages) & 1);
+        tc_fence_after();
+        const uint64_t da = desc0 + (uint64_t)((s * Cfg::kStageBytes) >> 4);
+        const uint64_t db = da + (uint64_t)(kATileBytes >> 4);
+        if (leader) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (leader) umma_bf16(tmem, da + 2 * k, db + 2 * k, idesc, (uint32_t)((it | k) != 0));
-      if (leader) umma_commit(&empty[s]);
+          for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (uint32_t)((it | k) != 0));
+          umma_commit(&empty[s]);
+        }
+        __syncwarp();
+      }
+      if (leader) umma_commit(&tmem_full[buf]);
       __syncwarp();
     }
-    if (leader) umma_commit(tmem_full);
-    __syncwarp();
   } else {
     const int q = warp & 3;
     const int r = q * 32 + lane;
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
     const int iw = r % p.bw;
     const int rr = r / p.bw;
     const int ih = rr % p.bh, in = rr / p.bh;
-    const int x = x0 + iw, y = y0 + ih, n = n0 + in;
-    const bool valid = r < p.rows && x < p.w && y < p.h && n < p.n;
-    const long long pix = ((long long)n * p.h + y) * p.w + x;
-    float* dstf = (float*)p.out + pix * p.out_ld + ncol0;
     const float* bias = p.bias ? p.bias + ncol0 : nullptr;
+    const bool issuer = warp == 2 && lane == 0;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int buf = i & 1;
+      int t = blockIdx.x + i * gridDim.x;
+      const int tx = t % p.tiles_x; t /= p.tiles_x;
+      const int ty = t % p.tiles_y; t /= p.tiles_y;
+      const int x0 = tx * p.bw, y0 = ty * p.bh, n0 = t * p.bn;
+      const int x = x0 + iw, y = y0 + ih, n = n0 + in;
+      const bool valid = r < p.rows && x < p.w && y < p.h && n < p.n;
+      const long long pix = ((long long)n * p.h + y) * p.w + x;
+      float* dstf = (float*)p.out + pix * p.out_ld + ncol0;
+      mbar_wait(&tmem_full[buf], (i >> 1) & 1);
+      tc_fence_after();
+      if (!p.out_f32) {
+        // the TMA store of the previous tile must have finished reading the staging buffer
+        if (issuer) tma_store_wait_read<0>();
+        named_bar_sync(1, 128);
+      }
 #pragma unroll
-    for (int c0 = 0; c0 < N; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c0, v);
-      tmem_ld_wait();
+      for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + buf * Cfg::kTmemCols + c0, v);
+        tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) {
-        float f[8];
+        for (int j = 0; j < 32; j += 8) {
+          float f[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j + e]) + (bias ? bias[c0 + j + e] : 0.f);
-        if (p.out_f32) {
-          if (valid) {
-            *reinterpret_cast<float4*>(dstf + c0 + j) = make_float4(f[0], f[1], f[2], f[3]);
-            *reinterpret_cast<float4*>(dstf + c0 + j + 4) = make_float4(f[4], f[5], f[6], f[7]);
+          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[j + e]) + (bias ? bias[c0 + j + e] : 0.f);
+          if (p.out_f32) {
+            if (valid) {
+              *reinterpret_cast<float4*>(dstf + c0 + j) = make_float4(f[0], f[1], f[2], f[3]);
+              *reinterpret_cast<float4*>(dstf + c0 + j + 4) = make_float4(f[4], f[5], f[6], f[7]);
+            }
+          } else {
+            // stage the bf16 tile in the SWIZZLE_128B layout of the output tensor map: sub-tile (c / 64), row r
+            const int c = c0 + j;
+            uint8_t* srow = sOut + (c >> 6) * kATileBytes + r * 128;
+            *reinterpret_cast<bf16x8*>(srow + ((((c & 63) >> 3) ^ (r & 7)) << 4)) = pack8(f);
           }
-        } else {
-          // stage the bf16 tile in the SWIZZLE_128B layout of the output tensor map: sub-tile (c / 64), row r
-          const int c = c0 + j;
-          uint8_t* srow = sOut + (c >> 6) * kATileBytes + r * 128;
-          *reinterpret_cast<bf16x8*>(srow + ((((c & 63) >> 3) ^ (r & 7)) << 4)) = pack8(f);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[buf]);   // accumulator free for tile i + 2
+      if (!p.out_f32) {
+        fence_proxy_async();
+        named_bar_sync(1, 128);
+        if (issuer) {   // one TMA store per 64-channel sub-tile; out-of-range pixels are clipped
+#pragma unroll
+          for (int t2 = 0; t2 < Cfg::kOutTiles; ++t2)
+            tma_store_4d(&tmY, sOut + t2 * kATileBytes, ncol0 + t2 * 64, x0, y0, n0);
+          tma_store_commit();
         }
       }
     }
-    if (!p.out_f32) {
-      fence_proxy_async();
-      named_bar_sync(1, 128);
-      if (warp == 2 && lane == 0) {   // one TMA store per 64-channel sub-tile; out-of-range pixels are clipped
-#pragma unroll
-        for (int t2 = 0; t2 < Cfg::kOutTiles; ++t2)
-          tma_store_4d(&tmY, sOut + t2 * kATileBytes, ncol0 + t2 * 64, x0, y0, n0);
-        tma_store_commit();
-        tma_store_wait_read<0>();
-      }
-    }
+    if (issuer) tma_store_wait_read<0>();
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<Cfg::kTmemCols>(tmem);
+    tmem_dealloc<2 * Cfg::kTmemCols>(tmem);
   }
+}
+
+int conv_sm_count() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      sms = 148;
+  }
+  return sms;
 }
 
 template <int N>
@@ -276,7 +323,12 @@ int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
     CRFR_CUDA(cudaFuncSetAttribute(tc_conv_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_done = true;
   }
-  tc_conv_kernel<N><<<dim3(tiles, p.n_total / N), kConvThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, tmY, p);
+  // persistent over pixel tiles: about one CTA per SM in total (column tiles share the pixel-tile walk)
+  const int ncol = p.n_total / N;
+  int ctas = (conv_sm_count() + ncol - 1) / ncol;
+  if (ctas > tiles) ctas = tiles;
+  if (ctas < 1) ctas = 1;
+  tc_conv_kernel<N><<<dim3(ctas, ncol), kConvThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, tmY, p);
   CRFR_COUNT_LAUNCH();
   CRFR_LAUNCH_CHECK();
   return CRFR_OK;
@@ -510,6 +562,7 @@ int crfr_tc_gemm(const TcGemm& g, cudaStream_t st) {
   p.bw = t.bw; p.bh = t.bh; p.bn = t.bn; p.tiles_x = t.tiles_x; p.tiles_y = t.tiles_y; p.rows = t.rows;
   p.n_total = g.n_total; p.out_ld = g.out_ld; p.out_f32 = g.out_f32; p.out = g.out; p.bias = g.bias;
   const int tiles = t.tiles_x * t.tiles_y * t.tiles_n;
+  p.total_tiles = tiles;
   switch (tile_n) {
     case 32: return launch_conv<32>(tmA, tmB, tmY, p, tiles, st);
     case 64: return launch_conv<64>(tmA, tmB, tmY, p, tiles, st);
