@@ -23,6 +23,7 @@ int crfr_pack_weight_cols(const float* w, void* dst, int cin, int rows, int ld, 
 namespace {
 
 constexpr float kEps = 1e-5f;
+constexpr int kHeadsPad = 128;   // fc (11) + fc_landmark (97) output channels padded to one UMMA-friendly width
 
 // ---- parameter table (state_dict order, 202 entries) ---------------------------------------------
 enum { RB_CONV1 = 0, RB_IN1_W, RB_IN1_B, RB_RELU, RB_CONV2, RB_IN2_W, RB_IN2_B, RB_RELU_OUT };
@@ -37,6 +38,49 @@ enum {
   D_DECONV_B = 173, D_RES = 174, D_CONV_OUT_W = 198, D_CONV_OUT_B = 199
 };
 inline int hg_param(int d, int s, int b, int which) { return P_HG + (d == 0 ? 0 : 24) + ((s * 2 + b) * 3) + which; }
+
+// combined head weight [co = 128][ci = 128] (rows 0..10 fc, 11..107 fc_landmark, rest zero) and bias [128]
+__global__ void heads_pack_kernel(const float* __restrict__ w_fc, const float* __restrict__ b_fc,
+                                  const float* __restrict__ w_lm, const float* __restrict__ b_lm, bf16* __restrict__ wc,
+                                  float* __restrict__ bc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kHeadsPad * 128) return;
+  const int co = i >> 7, ci = i & 127;
+  float v = 0.f;
+  if (co < 11) v = w_fc[co * 128 + ci];
+  else if (co < 108) v = w_lm[(co - 11) * 128 + ci];
+  wc[i] = __float2bfloat16_rn(v);
+  if (ci == 0) bc[co] = co < 11 ? b_fc[co] : (co < 108 ? b_lm[co - 11] : 0.f);
+}
+
+// fp32 NHWC [npix][128] -> parsing [n][11][hw] and landmark [n][97][hw] (fp32 NCHW); one thread per output element,
+// consecutive threads walk consecutive pixels of one channel (coalesced writes, 512-byte-strided L2-resident reads)
+__global__ void heads_split_kernel(const float* __restrict__ y, float* __restrict__ parsing, float* __restrict__ landmark,
+                                   int n, int hw) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)n * 108 * hw;
+  if (i >= total) return;
+  const int p = (int)(i % hw);
+  const long long q = i / hw;
+  const int c = (int)(q % 108);
+  const long long img = q / 108;
+  const float v = y[(img * hw + p) * kHeadsPad + c];
+  if (c < 11) parsing[(img * 11 + c) * hw + p] = v;
+  else landmark[(img * 97 + (c - 11)) * hw + p] = v;
+}
+
+// dW_fc [11][128] += G[ci][co], dW_fcl [97][128] += G[ci][11 + co]
+__global__ void heads_unpack_kernel(const float* __restrict__ G, float* __restrict__ dw_fc, float* __restrict__ dw_lm) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 108 * 128) return;
+  const int co = i >> 7, ci = i & 127;
+  const float g = G[ci * kHeadsPad + co];
+  if (co < 11) {
+    if (dw_fc) dw_fc[co * 128 + ci] += g;
+  } else if (dw_lm) {
+    dw_lm[(co - 11) * 128 + ci] += g;
+  }
+}
 
 struct Tensor {
   bf16* p = nullptr;
@@ -82,7 +126,7 @@ struct Net {
   // fixed buffers
   Tensor x4, coarse4, cat;
   int tape_enc_start = 0, tape_dec_start = 0;   // first tape index of the encoder / decoder sections
-  // output gradients (bf16): NHWC4 images and the combined 112-wide heads buffer
+  // output gradients (bf16): NHWC4 images and the combined 128-wide heads buffer
   bf16* d_coarse4 = nullptr;
   bf16* d_out4 = nullptr;
   bf16* d_heads = nullptr;
@@ -264,18 +308,23 @@ struct Net {
     tape.push_back(op);
   }
 
-  void heads(const Tensor& x) {   // fc (11) and fc_landmark (97): 1x1 convs with fp32 NCHW outputs
-    const int idx[2][2] = {{P_FC_W, P_FC_B}, {P_FCL_W, P_FCL_B}};
-    const int couts[2] = {11, 97};
-    float* outs[2] = {io->parsing, io->landmark};
-    for (int i = 0; i < 2; ++i) {
-      crfr_conv_desc d;
-      d.n = x.n; d.h = x.h; d.w = x.w; d.cin = x.c; d.cout = couts[i]; d.k = 1; d.stride = 1; d.pad = 0;
-      d.oh = x.h; d.ow = x.w; d.in_ld = x.ld; d.out_ld = couts[i]; d.transposed = 0;
-      void* wp = pack(idx[i][0], couts[i], x.c, 1, x.c, false, false);
-      if (run())
-        check(crfr_conv_fwd(CRFR_ENGINE_DIRECT, &d, x.p, wp, x.c, params[idx[i][1]], nullptr, outs[i], nullptr, kEps,
-                            scratch, scratch_bytes, st));
+  // fc (11) and fc_landmark (97), model/FSRnet.py:391-392: both 1x1 heads as ONE tcgen05 GEMM over the combined
+  // [128 = 11 | 97 | zero pad][128] weight (fp32 NHWC result), then split + transposed into the two fp32 NCHW outputs
+  void heads(const Tensor& x) {
+    const long long npix = (long long)x.n * x.h * x.w;
+    bf16* wc = (bf16*)alloc((size_t)kHeadsPad * 128 * sizeof(bf16));       // [co][ci]
+    float* bc = (float*)alloc(kHeadsPad * sizeof(float));
+    float* yf = (float*)alloc((size_t)npix * kHeadsPad * sizeof(float));   // fp32 NHWC
+    if (run()) {
+      heads_pack_kernel<<<crfr_cdiv(kHeadsPad * 128, 256), 256, 0, st>>>(params[P_FC_W], params[P_FC_B], params[P_FCL_W],
+                                                                         params[P_FCL_B], wc, bc);
+      CRFR_COUNT_LAUNCH();
+      TcGemm g{x.p, x.n, x.h, x.w, 128, x.ld, wc, 1, 0, 1, kHeadsPad, kHeadsPad, yf, kHeadsPad, 1, bc};
+      check(crfr_tc_gemm(g, st));
+      const long long total = npix * 108;
+      heads_split_kernel<<<crfr_cdiv(total, 256), 256, 0, st>>>(yf, io->parsing, io->landmark, x.n, x.h * x.w);
+      CRFR_COUNT_LAUNCH();
+      check(cudaGetLastError() == cudaSuccess ? CRFR_OK : CRFR_ECUDA);
     }
     Op op;
     op.kind = OP_HEADS; op.a = x;
@@ -453,26 +502,25 @@ struct Net {
         case OP_HEADS: {
           if (!d_heads) break;
           const Tensor& x = op.a;
-          // combined [.., 112] gradient buffer: parsing channels 0..10, landmark 11..107, zero padding 108..111
-          const int idx[2][2] = {{P_FC_W, P_FC_B}, {P_FCL_W, P_FCL_B}};
-          const int couts[2] = {11, 97}, coff[2] = {0, 11};
-          for (int k = 0; k < 2; ++k) {
-            crfr_conv_desc d;
-            d.n = x.n; d.h = x.h; d.w = x.w; d.cin = x.c; d.cout = couts[k]; d.k = 1; d.stride = 1; d.pad = 0;
-            d.oh = x.h; d.ow = x.w; d.in_ld = x.ld; d.out_ld = 112; d.transposed = 0;
-            if (run()) check(crfr_conv_wgrad(CRFR_ENGINE_DIRECT, &d, x.p, d_heads + coff[k], grad(idx[k][0]), grad(idx[k][1]),
-                                  scratch, scratch_bytes, st));
+          const long long npix = (long long)x.n * x.h * x.w;
+          // combined [.., 128] gradient buffer: parsing channels 0..10, landmark 11..107, zero padding 108..127
+          float* G = (float*)scratch;                       // [ci = 128][co = 128] fp32
+          bf16* wt = (bf16*)alloc((size_t)128 * kHeadsPad * sizeof(bf16));   // [ci][co]: rows of fc, fc_landmark, zeros
+          bf16* dx = (bf16*)alloc((size_t)npix * x.c * sizeof(bf16));
+          if (run()) {
+            check(cudaMemsetAsync(G, 0, sizeof(float) * 128 * kHeadsPad, st) == cudaSuccess ? CRFR_OK : CRFR_ECUDA);
+            TcWgrad wg{x.p, x.n, x.h, x.w, 128, x.ld, d_heads, kHeadsPad, kHeadsPad, 0, G};
+            check(crfr_tc_wgrad_raw(wg, st));
+            heads_unpack_kernel<<<crfr_cdiv(108 * 128, 256), 256, 0, st>>>(G, grad(P_FC_W), grad(P_FCL_W));
+            CRFR_COUNT_LAUNCH();
+            if (grad(P_FC_B)) check(crfr_colsum(d_heads, kHeadsPad, 11, npix, grad(P_FC_B), st));
+            if (grad(P_FCL_B)) check(crfr_colsum(d_heads + 11, kHeadsPad, 97, npix, grad(P_FCL_B), st));
+            check(cudaMemsetAsync(wt, 0, (size_t)128 * kHeadsPad * sizeof(bf16), st) == cudaSuccess ? CRFR_OK : CRFR_ECUDA);
+            check(crfr_pack_weight_cols(params[P_FC_W], wt, 128, 11, kHeadsPad, 0, st));
+            check(crfr_pack_weight_cols(params[P_FCL_W], wt, 128, 97, kHeadsPad, 11, st));
+            TcGemm g{d_heads, x.n, x.h, x.w, kHeadsPad, kHeadsPad, wt, 1, 0, 1, 128, 128, dx, x.c, 0, nullptr};
+            check(crfr_tc_gemm(g, st));
           }
-          // one combined dgrad: weights [1][128][112] = rows of fc then fc_landmark, zero padded
-          bf16* wt = (bf16*)alloc((size_t)128 * 112 * sizeof(bf16));
-          if (run()) check(cudaMemsetAsync(wt, 0, (size_t)128 * 112 * sizeof(bf16), st) == cudaSuccess ? CRFR_OK : CRFR_ECUDA);
-          if (run()) check(crfr_pack_weight_cols(params[P_FC_W], wt, 128, 11, 112, 0, st));
-          if (run()) check(crfr_pack_weight_cols(params[P_FCL_W], wt, 128, 97, 112, 11, st));
-          crfr_conv_desc d;
-          d.n = x.n; d.h = x.h; d.w = x.w; d.cin = x.c; d.cout = 112; d.k = 1; d.stride = 1; d.pad = 0;
-          d.oh = x.h; d.ow = x.w; d.in_ld = x.c; d.out_ld = 112; d.transposed = 0;
-          bf16* dx = (bf16*)alloc((size_t)x.n * x.h * x.w * x.c * sizeof(bf16));
-          if (run()) check(crfr_conv_dgrad(CRFR_ENGINE_DIRECT, &d, d_heads, wt, 112, dx, scratch, scratch_bytes, st));
           add_slot(x, dx, x.c);
           break;
         }
@@ -545,7 +593,7 @@ void alloc_out_grads(Net& net, bool coarse, bool out, bool heads) {
   const int B = net.io->batch, S = net.io->size, Q = S / 4;
   net.d_coarse4 = coarse ? (bf16*)net.alloc((size_t)B * S * S * 4 * sizeof(bf16)) : nullptr;
   net.d_out4 = out ? (bf16*)net.alloc((size_t)B * S * S * 4 * sizeof(bf16)) : nullptr;
-  net.d_heads = heads ? (bf16*)net.alloc((size_t)B * Q * Q * 112 * sizeof(bf16)) : nullptr;
+  net.d_heads = heads ? (bf16*)net.alloc((size_t)B * Q * Q * kHeadsPad * sizeof(bf16)) : nullptr;
 }
 
 }  // namespace
@@ -592,9 +640,9 @@ extern "C" int crfr_fsrnet_backward(int engine, const float* const* host_params,
   if (d_coarse) CRFR_TRY(crfr_nchw_f32_to_nhwc_bf16(d_coarse, net.d_coarse4, B, 3, S, S, 4, 4, stream));
   if (d_out) CRFR_TRY(crfr_nchw_f32_to_nhwc_bf16(d_out, net.d_out4, B, 3, S, S, 4, 4, stream));
   if (net.d_heads) {
-    CRFR_CUDA(cudaMemsetAsync(net.d_heads, 0, (size_t)B * Q * Q * 112 * sizeof(bf16), st));
-    if (d_parsing) CRFR_TRY(crfr_nchw_f32_to_nhwc_bf16(d_parsing, net.d_heads, B, 11, Q, Q, 112, 11, stream));
-    if (d_landmark) CRFR_TRY(crfr_nchw_f32_to_nhwc_bf16(d_landmark, net.d_heads + 11, B, 97, Q, Q, 112, 97, stream));
+    CRFR_CUDA(cudaMemsetAsync(net.d_heads, 0, (size_t)B * Q * Q * kHeadsPad * sizeof(bf16), st));
+    if (d_parsing) CRFR_TRY(crfr_nchw_f32_to_nhwc_bf16(d_parsing, net.d_heads, B, 11, Q, Q, kHeadsPad, 11, stream));
+    if (d_landmark) CRFR_TRY(crfr_nchw_f32_to_nhwc_bf16(d_landmark, net.d_heads + 11, B, 97, Q, Q, kHeadsPad, 97, stream));
   }
   net.backward();
   return net.err;
@@ -620,10 +668,10 @@ extern "C" int crfr_fsrnet_train_step(int engine, const float* const* host_param
                            net.scratch_bytes, stream));
   CRFR_TRY(crfr_loss_mse97(io->coarse, io->hr, B, 3, S * S, io->w_pix * inv, losses + 2, net.d_coarse4, 4,
                            net.scratch, net.scratch_bytes, stream));
-  CRFR_CUDA(cudaMemsetAsync(net.d_heads, 0, (size_t)B * Q * Q * 112 * sizeof(bf16), st));
-  CRFR_TRY(crfr_loss_landmark(io->landmark, io->heatmap, B, 97, Q * Q, inv, losses + 3, net.d_heads, 112, 11,
+  CRFR_CUDA(cudaMemsetAsync(net.d_heads, 0, (size_t)B * Q * Q * kHeadsPad * sizeof(bf16), st));
+  CRFR_TRY(crfr_loss_landmark(io->landmark, io->heatmap, B, 97, Q * Q, inv, losses + 3, net.d_heads, kHeadsPad, 11,
                               net.scratch, net.scratch_bytes, stream));
-  CRFR_TRY(crfr_loss_ce2d(io->parsing, io->labels, B, 11, Q * Q, inv, losses + 4, net.d_heads, 112, 0, net.scratch,
+  CRFR_TRY(crfr_loss_ce2d(io->parsing, io->labels, B, 11, Q * Q, inv, losses + 4, net.d_heads, kHeadsPad, 0, net.scratch,
                           net.scratch_bytes, stream));
   total_loss_kernel<<<1, 1, 0, st>>>(losses, io->w_pix, inv);
   CRFR_COUNT_LAUNCH();
