@@ -11,6 +11,8 @@
 // ref: model/FSRnet.py:75-98 (_Residual_Block), :105-135 (BasicBlock), :176-215 (Hourglass), :308-340 (coarse),
 //      :342-379 (encoder), :381-426 (prior), :428-459 (decoder), :488-508 + :538-541 (OverallNetwork wiring),
 //      FSR_main.py:233-234 (loss composition).
+#include <stdlib.h>
+
 #include <vector>
 
 #include "common.cuh"
@@ -95,6 +97,40 @@ struct Slot {
 
 enum OpKind { OP_CONV, OP_NORM, OP_POOL, OP_UPADD, OP_CAT, OP_HEADS, OP_IMGCONV };
 
+// Helper stream for the weight-gradient GEMMs of the backward pass.  A conv's wgrad (tensor-bound) has no consumer
+// until the optimiser step, while the InstanceNorm backward of the layer below (HBM-bound) is on the critical path:
+// the wgrad is forked onto this stream behind the layer's dgrad so that the two run concurrently, and joined back
+// before a gradient bucket is published / before the call returns its work to the caller's stream.  From the
+// caller's point of view everything is still ordered on the stream it passed.
+struct SideStream {
+  cudaStream_t st = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+SideStream* side_stream() {
+  static thread_local SideStream per_dev[16];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  SideStream& s = per_dev[dev];
+  if (!s.st) {
+    if (cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      s.st = nullptr;
+      return nullptr;
+    }
+  }
+  return &s;
+}
+int side_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CRFR_WGRAD_STREAM");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
+
 struct Op {
   OpKind kind;
   Tensor a, b, out;        // inputs / output
@@ -123,6 +159,10 @@ struct Net {
   void* packed_bwd[CRFR_FSRNET_NPARAMS];
   void* scratch = nullptr;
   size_t scratch_bytes = 0;
+  void* scratch2 = nullptr;          // private scratch of the wgrad helper stream
+  size_t scratch2_bytes = 0;
+  SideStream* side = nullptr;
+  bool side_dirty = false;
   // fixed buffers
   Tensor x4, coarse4, cat;
   int tape_enc_start = 0, tape_dec_start = 0;   // first tape index of the encoder / decoder sections
@@ -349,6 +389,11 @@ struct Net {
       }
     }
     scratch = alloc(scratch_bytes);
+    if (training) {
+      const crfr_conv_desc big = {B, S, S, 64, 64, 3, 1, 1, S, S, 64, 64, 0};
+      scratch2_bytes = crfr_tc_workspace_bytes(&big) + sizeof(float) * 9 * 192 * 128 + 4096;
+      scratch2 = alloc(scratch2_bytes);
+    }
     x4 = new_tensor(B, S, S, 4);
     x4.c = 3;
     if (run()) check(crfr_nchw_f32_to_nhwc_bf16(io->x, x4.p, B, 3, S, S, 4, 4, st));
@@ -420,12 +465,22 @@ struct Net {
   }
   bool has_grad(const Tensor& t) const { return t.id >= 0 && !slots[t.id].empty(); }
 
+  void join_side() {   // the caller's stream waits for every forked weight gradient
+    if (side_dirty && run()) {
+      check(cudaEventRecord(side->join, side->st) == cudaSuccess ? CRFR_OK : CRFR_ECUDA);
+      check(cudaStreamWaitEvent(st, side->join, 0) == cudaSuccess ? CRFR_OK : CRFR_ECUDA);
+    }
+    side_dirty = false;
+  }
+
   void record_bucket(int k) {
+    join_side();
     if (run() && io->bucket_events[k])
       check(cudaEventRecord((cudaEvent_t)io->bucket_events[k], st) == cudaSuccess ? CRFR_OK : CRFR_ECUDA);
   }
 
   void backward() {
+    side = (exec && side_enabled()) ? side_stream() : nullptr;
     for (int i = (int)tape.size() - 1; i >= 0 && ok(); --i) {
       if (i == tape_dec_start - 1) record_bucket(0);   // every decoder op has run: its gradients are final
       if (i == tape_enc_start - 1) record_bucket(1);   // prior + encoder done
@@ -456,7 +511,11 @@ struct Net {
           Slot dy = slots[op.out.id][0];
           crfr_conv_desc d = op.cd;
           d.out_ld = dy.ld;
-          if (run()) check(crfr_conv_wgrad(engine, &d, op.a.p, dy.p, grad(op.w_idx), grad(op.b_idx), scratch, scratch_bytes, st));
+          // plain tcgen05 weight gradients go to the helper stream, behind this layer's dgrad (see SideStream)
+          const bool forked = side && scratch2 && engine != CRFR_ENGINE_DIRECT && crfr_lowered_recipe(&d) == 0 &&
+                              !d.transposed && crfr_tc_supported(2, d.h, d.w, d.cin, d.cout, d.k, d.stride, d.pad);
+          if (!forked && run())
+            check(crfr_conv_wgrad(engine, &d, op.a.p, dy.p, grad(op.w_idx), grad(op.b_idx), scratch, scratch_bytes, st));
           if (op.x_needs_grad) {
             const Tensor& x = op.a;
             const int xc = x.c < 8 ? 4 : x.c;
@@ -467,6 +526,13 @@ struct Net {
             const int cout_pad = d.cout;
             if (run()) check(crfr_conv_dgrad(engine, &dd, dy.p, wt, cout_pad, dx, scratch, scratch_bytes, st));
             add_slot(x, dx, xc);
+          }
+          if (forked && run()) {
+            check(cudaEventRecord(side->fork, st) == cudaSuccess ? CRFR_OK : CRFR_ECUDA);
+            check(cudaStreamWaitEvent(side->st, side->fork, 0) == cudaSuccess ? CRFR_OK : CRFR_ECUDA);
+            check(crfr_conv_wgrad(engine, &d, op.a.p, dy.p, grad(op.w_idx), grad(op.b_idx), scratch2, scratch2_bytes,
+                                  side->st));
+            side_dirty = true;
           }
           break;
         }
