@@ -7,8 +7,12 @@
 //                                                                     dgrad, wgrad : im2col(dY) as the GEMM operand
 //   R3  Conv2d 7x7 s4|s2 p3, cin = 3 (encoder / prior stems :345, :384; ResNet stem model/resnet.py:158)   fwd, wgrad : im2col(147 -> 192 ch) . W
 //                                                                     dgrad : dY . W (192 cols, fp32) then col2im
-//   R4  ConvTranspose2d 7x7 s4 p2 op1, 64 -> 64 (decoder :436)         fwd : x . W (49*64 cols, fp32) then col2im
-//                                                                     dgrad, wgrad : im2col(dOut) as the GEMM operand
+//   R4  ConvTranspose2d 7x7 s4 p2 op1, 64 -> 64 (decoder :436): sub-pixel decomposition.  Output pixel (4a+py, 4b+px)
+//       only sees the taps ky = (py+2) mod 4 (+4), kx likewise, i.e. every one of the 16 output phases is a <= 2x2-tap
+//       convolution of the 32x32 input with offsets in {-1,0,1}.  All phases together are ONE 3x3 pad-1 convolution
+//       64 -> 16*64 channels with a block-sparse weight (49 of 144 blocks non-zero), run on the implicit-GEMM kernel,
+//       followed by a pixel shuffle; dgrad / wgrad are that convolution's dgrad / wgrad on the un-shuffled dOut.
+//       (The earlier x . W -> 1.6 GB fp32 -> col2im formulation moved 12x more bytes.)
 //   R5  Conv2d 3x3 s2 p1 / 1x1 s2 p0, channels % 64 == 0 (ResNet stage transitions and downsample branches,
 //       model/resnet.py:9-16, 193-200)                                 fwd, wgrad : im2col(T*cin) . W
 //                                                                     dgrad : dY . W (T*cin cols, fp32) then col2im
@@ -90,63 +94,62 @@ __global__ void col2im_small_kernel(const float* __restrict__ src, int src_ld, i
     for (int c = 0; c < y_ld; ++c) y[i * y_ld + c] = __float2bfloat16_rn(c < C ? acc[c] : 0.f);
 }
 
-// ConvTranspose col2im, 8 channels per thread: out[Y][X][co] = bias + sum_{valid taps} Z[(Y+pad-ky)/s][(X+pad-kx)/s][tap*C + co]
-__global__ void deconv_col2im_kernel(const float* __restrict__ Z, int C, int sh, int sw, int bh, int bw, int ks,
-                                     int stride, int pad, const float* __restrict__ bias, bf16* __restrict__ out,
-                                     int out_ld, long long total) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int groups = C >> 3;
-  const int g = (int)(i % groups);
-  long long p = i / groups;
-  const int X = (int)(p % bw);
-  long long q = p / bw;
-  const int Y = (int)(q % bh);
-  const long long n = q / bh;
-  const int zld = ks * ks * C;
-  float acc[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = bias ? bias[g * 8 + j] : 0.f;
-  for (int ky = 0; ky < ks; ++ky) {
-    const int ty = Y + pad - ky;
-    if (ty < 0 || ty % stride) continue;
-    const int sy = ty / stride;
-    if (sy >= sh) continue;
-    for (int kx = 0; kx < ks; ++kx) {
-      const int tx = X + pad - kx;
-      if (tx < 0 || tx % stride) continue;
-      const int sx = tx / stride;
-      if (sx >= sw) continue;
-      const float4* s = reinterpret_cast<const float4*>(Z + ((n * sh + sy) * sw + sx) * zld + (ky * ks + kx) * C + g * 8);
-      const float4 a = s[0], b = s[1];
-      acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
-      acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
-    }
-  }
-  *reinterpret_cast<bf16x8*>(out + p * out_ld + g * 8) = pack8(acc);
+// ---- sub-pixel (phase) decomposition of the 7x7 s4 p2 transposed convolution --------------------------------
+// tap k (0..6) -> output phase p = (k + 2) mod 4 and input offset d = (p + 2 - k) / 4 in {-1, 0, 1}
+__device__ __forceinline__ void subpixel_of_tap(int k, int* phase, int* off) {
+  const int p = (k + 2) & 3;
+  *phase = p;
+  *off = (p + 2 - k) / 4;   // exact: -4, 0 or 4 in the numerator
 }
 
-// ConvTranspose im2col: dZ[i][tap*C + co] = dOut[i*s - pad + tap][co] (zero outside)
-__global__ void deconv_im2col_kernel(const bf16* __restrict__ dout, int dout_ld, int C, int sh, int sw, int bh, int bw,
-                                     int ks, int stride, int pad, bf16* __restrict__ dZ, long long total) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+// mode 0 (forward):  src [49][co][ci] -> dst [9][(py*4+px)*64 + co][ci]
+// mode 1 (dgrad):    src [49][ci][co] -> dst [9][ci][(py*4+px)*64 + co]            (dst pre-zeroed)
+__global__ void deconv_subpixel_pack_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, int mode) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 49 * 64 * 64) return;
+  const int s_ = i & 63, r = (i >> 6) & 63, tap = i >> 12;
+  int py, dy, px, dx;
+  subpixel_of_tap(tap / 7, &py, &dy);
+  subpixel_of_tap(tap % 7, &px, &dx);
+  const int t9 = (dy + 1) * 3 + (dx + 1), ph = py * 4 + px;
+  if (mode == 0) dst[((size_t)t9 * 1024 + ph * 64 + r) * 64 + s_] = src[i];       // r = co, s = ci
+  else dst[((size_t)t9 * 64 + r) * 1024 + ph * 64 + s_] = src[i];                 // r = ci, s = co
+}
+
+__global__ void deconv_bias_kernel(const float* __restrict__ bias, float* __restrict__ big) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 1024) big[i] = bias ? bias[i & 63] : 0.f;
+}
+
+// to_all == 0: y[n][4a+py][4b+px][co] = all[n][a][b][(py*4+px)*64 + co]   (pixel shuffle; y has per-pixel stride y_ld)
+// to_all == 1: the inverse (un-shuffle of dOut).  One thread per 16 bytes.
+__global__ void deconv_shuffle_kernel(bf16* __restrict__ y, int y_ld, bf16* __restrict__ all, int sh, int sw, int to_all,
+                                      long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  const int groups = C >> 3;
-  const int g = (int)(i % groups);
-  long long r = i / groups;
-  const int T = ks * ks;
-  const int tap = (int)(r % T);
-  long long p = r / T;
-  const int sx = (int)(p % sw);
-  long long q = p / sw;
-  const int sy = (int)(q % sh);
-  const long long n = q / sh;
-  const int ky = tap / ks, kx = tap - ky * ks;
-  const int Y = sy * stride - pad + ky, X = sx * stride - pad + kx;
-  uint4 v = make_uint4(0, 0, 0, 0);
-  if (Y >= 0 && Y < bh && X >= 0 && X < bw)
-    v = *reinterpret_cast<const uint4*>(dout + ((n * bh + Y) * bw + X) * dout_ld + g * 8);
-  *reinterpret_cast<uint4*>(dZ + p * ((long long)T * C) + (long long)tap * C + g * 8) = v;
+  const int g = (int)(i & 7);
+  long long p = i >> 3;                     // output pixel (n, Y, X)
+  const int X = (int)(p % (4 * sw));
+  long long q = p / (4 * sw);
+  const int Y = (int)(q % (4 * sh));
+  const long long n = q / (4 * sh);
+  const long long ai = ((n * sh + (Y >> 2)) * sw + (X >> 2)) * 1024 + ((Y & 3) * 4 + (X & 3)) * 64 + g * 8;
+  uint4* py_ = reinterpret_cast<uint4*>(y + p * y_ld + g * 8);
+  uint4* pa = reinterpret_cast<uint4*>(all + ai);
+  if (to_all) *pa = *py_;
+  else *py_ = *pa;
+}
+
+// dW[ci][co][ky][kx] += G[t9][ci][(py*4+px)*64 + co]
+__global__ void deconv_subpixel_unpack_kernel(const float* __restrict__ G, float* __restrict__ dw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // over [ci][co][49]
+  if (i >= 64 * 64 * 49) return;
+  const int tap = i % 49, co = (i / 49) & 63, ci = i / (49 * 64);
+  int py, dy, px, dx;
+  subpixel_of_tap(tap / 7, &py, &dy);
+  subpixel_of_tap(tap % 7, &px, &dx);
+  const int t9 = (dy + 1) * 3 + (dx + 1), ph = py * 4 + px;
+  dw[i] += G[((size_t)t9 * 64 + ci) * 1024 + ph * 64 + co];
 }
 
 // Generic im2col for channel counts that are multiples of 8 (16-byte vectors):
@@ -301,11 +304,9 @@ size_t crfr_lowered_ws_bytes(const crfr_conv_desc* d) {
     case 1: b = big * 64 * 2 + (size_t)256 * 64 * 2 + (size_t)64 * 256 * 4; break;
     case 2: b = big * 64 * 2 + big * 32 * 4 + (size_t)64 * 64 * 2 * 2 + (size_t)64 * 64 * 4; break;
     case 3: b = small * 192 * 2 + small * 192 * 4 + (size_t)192 * 128 * 2 * 2 + (size_t)192 * 128 * 4; break;
-    case 4: {
-      const size_t zc = 49 * 64;
-      b = big * zc * 4 + (size_t)64 * zc * 2 + (size_t)64 * zc * 4;   // big = input (small) grid here
+    case 4:   // big = input (small) grid here: [ipix][16 phases * 64] bf16 + block-sparse weights + wgrad accumulator
+      b = big * 1024 * 2 + (size_t)9 * 1024 * 64 * 2 + (size_t)9 * 64 * 1024 * 4 + 1024 * 4 + 8192;
       break;
-    }
     case 5: {
       const size_t kc = (size_t)d->k * d->k * d->cin;
       b = small * kc * 2 + small * kc * 4 + (size_t)d->cout * kc * 2 + kc * d->cout * 4;
@@ -378,13 +379,15 @@ int crfr_lowered_fwd(const crfr_conv_desc* d, const void* x, const void* w_packe
       return CRFR_EUNSUPPORTED;
     }
     const long long ipix = (long long)d->n * d->h * d->w, opix = (long long)d->n * d->oh * d->ow;
-    const int zc = T * 64;
-    TAKE(Z, float, A, (size_t)ipix * zc * 4);
-    // w_packed is [tap][co][ci]: exactly the [tap*64 + co][ci] GEMM weight
-    TcGemm g{x, d->n, d->h, d->w, 64, d->in_ld, w_packed, 1, 0, 1, zc, 224, Z, zc, 1, nullptr};
+    TAKE(All, bf16, A, (size_t)ipix * 1024 * 2);
+    TAKE(Wbig, bf16, A, (size_t)9 * 1024 * 64 * 2);
+    TAKE(bbig, float, A, 1024 * 4);
+    CRFR_CUDA(cudaMemsetAsync(Wbig, 0, (size_t)9 * 1024 * 64 * 2, st));
+    LAUNCH(deconv_subpixel_pack_kernel, 49 * 64 * 64, st, (const bf16*)w_packed, Wbig, 0);
+    LAUNCH(deconv_bias_kernel, 1024, st, bias, bbig);
+    TcGemm g{x, d->n, d->h, d->w, 64, d->in_ld, Wbig, 3, 1, 1, 1024, 256, All, 1024, 0, bbig};
     CRFR_TRY(crfr_tc_gemm(g, st));
-    LAUNCH(deconv_col2im_kernel, opix * 8, st, Z, 64, d->h, d->w, d->oh, d->ow, d->k, d->stride, d->pad, bias, (bf16*)y,
-           d->out_ld, opix * 8);
+    LAUNCH(deconv_shuffle_kernel, opix * 8, st, (bf16*)y, d->out_ld, All, d->h, d->w, 0, opix * 8);
     return CRFR_OK;
   }
   crfr_set_error("lowered conv: no recipe for this shape");
@@ -439,15 +442,15 @@ int crfr_lowered_dgrad(const crfr_conv_desc* d, const void* dy, const void* w_pa
     return CRFR_OK;
   }
   if (recipe == 4) {
-    // d_in[i][ci] = sum_{tap,co} dZ[i][tap*64+co] W[ci][co][tap]
-    const long long ipix = (long long)d->n * d->h * d->w;
-    const int zc = T * 64;
-    TAKE(dZ, bf16, A, (size_t)ipix * zc * 2);
-    TAKE(Wd, bf16, A, (size_t)64 * zc * 2);
-    LAUNCH(deconv_im2col_kernel, ipix * T * 8, st, (const bf16*)dy, d->out_ld, 64, d->h, d->w, d->oh, d->ow, d->k, d->stride,
-           d->pad, dZ, ipix * T * 8);
-    LAUNCH(repack_tapmajor_kernel, 64 * zc, st, (const bf16*)w_packed_t, T, 64, 64, cout_pad, Wd, 64, zc);
-    TcGemm g{dZ, d->n, d->h, d->w, zc, zc, Wd, 1, 0, 1, 64, 64, dx, d->in_ld, 0, nullptr};
+    // dgrad of the sub-pixel convolution: un-shuffle dOut, then the 3x3 conv 1024 -> 64 with the transposed weight
+    CRFR_CHECK_ARG(cout_pad == 64, "lowered dgrad: cout_pad %d != 64", cout_pad);
+    const long long ipix = (long long)d->n * d->h * d->w, opix = (long long)d->n * d->oh * d->ow;
+    TAKE(All, bf16, A, (size_t)ipix * 1024 * 2);
+    TAKE(Wbig, bf16, A, (size_t)9 * 64 * 1024 * 2);
+    LAUNCH(deconv_shuffle_kernel, opix * 8, st, (bf16*)const_cast<void*>(dy), d->out_ld, All, d->h, d->w, 1, opix * 8);
+    CRFR_CUDA(cudaMemsetAsync(Wbig, 0, (size_t)9 * 64 * 1024 * 2, st));
+    LAUNCH(deconv_subpixel_pack_kernel, 49 * 64 * 64, st, (const bf16*)w_packed_t, Wbig, 1);
+    TcGemm g{All, d->n, d->h, d->w, 1024, 1024, Wbig, 3, 1, -1, 64, 64, dx, d->in_ld, 0, nullptr};
     return crfr_tc_gemm(g, st);
   }
   crfr_set_error("lowered dgrad: no recipe for this shape");
@@ -501,16 +504,14 @@ int crfr_lowered_wgrad(const crfr_conv_desc* d, const void* x, const void* dy, f
     return CRFR_OK;
   }
   if (recipe == 4) {
-    const long long ipix = (long long)d->n * d->h * d->w;
-    const int zc = T * 64;
-    TAKE(dZ, bf16, A, (size_t)ipix * zc * 2);
-    TAKE(G, float, A, (size_t)64 * zc * 4);
-    LAUNCH(deconv_im2col_kernel, ipix * T * 8, st, (const bf16*)dy, d->out_ld, 64, d->h, d->w, d->oh, d->ow, d->k, d->stride,
-           d->pad, dZ, ipix * T * 8);
-    CRFR_CUDA(cudaMemsetAsync(G, 0, (size_t)64 * zc * 4, st));
-    TcWgrad g{x, d->n, d->h, d->w, 64, d->in_ld, dZ, zc, zc, 0, G};
+    const long long ipix = (long long)d->n * d->h * d->w, opix = (long long)d->n * d->oh * d->ow;
+    TAKE(All, bf16, A, (size_t)ipix * 1024 * 2);
+    TAKE(G, float, A, (size_t)9 * 64 * 1024 * 4);
+    LAUNCH(deconv_shuffle_kernel, opix * 8, st, (bf16*)const_cast<void*>(dy), d->out_ld, All, d->h, d->w, 1, opix * 8);
+    CRFR_CUDA(cudaMemsetAsync(G, 0, (size_t)9 * 64 * 1024 * 4, st));
+    TcWgrad g{x, d->n, d->h, d->w, 64, d->in_ld, All, 1024, 1024, 1, G};
     CRFR_TRY(crfr_tc_wgrad_raw(g, st));
-    LAUNCH(unpack_lowered_kernel, (long long)64 * 64 * T, st, G, zc, dw, 64, 64, T, 2);
+    LAUNCH(deconv_subpixel_unpack_kernel, 64 * 64 * 49, st, G, dw);
     return CRFR_OK;
   }
   crfr_set_error("lowered wgrad: no recipe for this shape");
