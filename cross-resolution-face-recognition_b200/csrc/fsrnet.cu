@@ -492,7 +492,8 @@ struct Net {
           std::vector<Slot>& s = slots[op.out.id];
           const Tensor& y = op.a;
           const size_t bytes = (size_t)y.n * y.h * y.w * y.c * sizeof(bf16);
-          bf16* dz = (bf16*)alloc(bytes);
+          // dz is only materialised when somebody consumes it (the residual branch) or a second gradient is summed in
+          bf16* dz = (op.has_res || s.size() > 1) ? (bf16*)alloc(bytes) : nullptr;
           bf16* dy = (bf16*)alloc(bytes);
           if (run()) check(crfr_norm_act_bwd(s[0].p, s[0].ld, s.size() > 1 ? s[1].p : nullptr, s.size() > 1 ? s[1].ld : 8, y.p, y.ld,
                                   op.stats, op.g_idx >= 0 ? params[op.g_idx] : nullptr,

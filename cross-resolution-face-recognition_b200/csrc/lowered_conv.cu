@@ -29,27 +29,28 @@ namespace {
 // ---------------------------------------------------------------------------------------------------------
 // P[o][tap*3 + c] = x[o*stride + sign*(tap - pad)][c] for 3-channel images stored 4 bf16 per pixel (zero outside the
 // image and for k >= T*3); kpad % 8 == 0.  One thread writes one 16-byte group of a row, so a warp writes whole
-// 128-byte lines; the 8 values of a group come from at most 4 taps, each fetched as one 8-byte pixel.
-__global__ void im2col_small_kernel(const bf16* __restrict__ x, int h, int w, int oh, int ow, int ks, int stride, int pad,
-                                    int sign, bf16* __restrict__ P, int kpad, long long total) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
+// 128-byte lines; the 8 values of a group come from at most 4 taps, each fetched as one 8-byte pixel.  The grid is
+// (groups of an output row, n * oh) and KS is a template parameter so that no per-thread runtime division is left
+// (the first version spent most of its time in them).
+template <int KS>
+__global__ void im2col_small_kernel(const bf16* __restrict__ x, int h, int w, int oh, int ow, int stride, int pad, int sign,
+                                    bf16* __restrict__ P, int kpad, int rows) {
   const int groups = kpad >> 3;
-  const int g = (int)(i % groups);
-  long long o = i / groups;
-  const int k0 = g * 8, kmax = ks * ks * 3;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // (ox, g) within the output row
+  if (idx >= ow * groups) return;
+  const int ox = idx / groups, g = idx - ox * groups;
+  const int k0 = g * 8, kmax = KS * KS * 3;
+  for (int row = blockIdx.y; row < rows; row += gridDim.y) {   // row = n * oh + oy
+  const int n = row / oh, oy = row - n * oh;
   uint32_t out[4] = {0u, 0u, 0u, 0u};
   if (k0 < kmax) {
-    const int ox = (int)(o % ow);
-    long long q = o / ow;
-    const int oy = (int)(q % oh);
-    const long long n = q / oh;
-    const int t0 = k0 / 3, t1 = min((k0 + 7) / 3, ks * ks - 1);
+    const int t0 = k0 / 3, t1 = min((k0 + 7) / 3, KS * KS - 1);
     for (int tap = t0; tap <= t1; ++tap) {
-      const int ky = tap / ks, kx = tap - ky * ks;
+      const int ky = tap / KS, kx = tap - ky * KS;
       const int y = oy * stride + sign * (ky - pad), xx = ox * stride + sign * (kx - pad);
       uint2 v = make_uint2(0u, 0u);
-      if (y >= 0 && y < h && xx >= 0 && xx < w) v = *reinterpret_cast<const uint2*>(x + ((n * h + y) * w + xx) * 4);
+      if (y >= 0 && y < h && xx >= 0 && xx < w)
+        v = *reinterpret_cast<const uint2*>(x + (((long long)n * h + y) * w + xx) * 4);
       const uint32_t ch[3] = {v.x & 0xffffu, v.x >> 16, v.y & 0xffffu};
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
@@ -58,7 +59,23 @@ __global__ void im2col_small_kernel(const bf16* __restrict__ x, int h, int w, in
       }
     }
   }
-  *reinterpret_cast<uint4*>(P + o * kpad + g * 8) = make_uint4(out[0], out[1], out[2], out[3]);
+  *reinterpret_cast<uint4*>(P + ((long long)row * ow + ox) * kpad + g * 8) = make_uint4(out[0], out[1], out[2], out[3]);
+  }
+}
+
+int launch_im2col_small(const bf16* x, int n, int h, int w, int oh, int ow, int ks, int stride, int pad, int sign, bf16* P,
+                        int kpad, cudaStream_t st) {
+  const int rows = n * oh;
+  const dim3 grid((unsigned)crfr_cdiv((long long)ow * (kpad >> 3), 256), (unsigned)(rows < 65535 ? rows : 65535));
+  if (ks == 3) im2col_small_kernel<3><<<grid, 256, 0, st>>>(x, h, w, oh, ow, stride, pad, sign, P, kpad, rows);
+  else if (ks == 7) im2col_small_kernel<7><<<grid, 256, 0, st>>>(x, h, w, oh, ow, stride, pad, sign, P, kpad, rows);
+  else {
+    crfr_set_error("im2col_small: kernel size %d not instantiated", ks);
+    return CRFR_EUNSUPPORTED;
+  }
+  CRFR_COUNT_LAUNCH();
+  CRFR_LAUNCH_CHECK();
+  return CRFR_OK;
 }
 
 // dst[P][c] = bias[c] + sum_{tap : t = P + sgn*(pad - tap), t % stride == 0, t/stride inside} src[t/stride][tap*C + c]
@@ -334,8 +351,7 @@ int crfr_lowered_fwd(const crfr_conv_desc* d, const void* x, const void* w_packe
     const long long opix = (long long)d->n * d->oh * d->ow;
     TAKE(P, bf16, A, (size_t)opix * kp * 2);
     TAKE(Wg, bf16, A, (size_t)d->cout * kp * 2);
-    LAUNCH(im2col_small_kernel, opix * (kp / 8), st, (const bf16*)x, d->h, d->w, d->oh, d->ow, d->k, d->stride,
-           d->pad, 1, P, kp, opix * (kp / 8));
+    CRFR_TRY(launch_im2col_small((const bf16*)x, d->n, d->h, d->w, d->oh, d->ow, d->k, d->stride, d->pad, 1, P, kp, st));
     LAUNCH(repack_tapmajor_kernel, d->cout * kp, st, (const bf16*)w_packed, T, d->cout, 3, cin_pad, Wg, d->cout, kp);
     TcGemm g{P, d->n, d->oh, d->ow, kp, kp, Wg, 1, 0, 1, d->cout, 0, y, d->out_ld, 0, bias};
     return crfr_tc_gemm(g, st);
@@ -407,8 +423,7 @@ int crfr_lowered_dgrad(const crfr_conv_desc* d, const void* dy, const void* w_pa
     const long long pix = (long long)d->n * d->h * d->w;
     TAKE(R, bf16, A, (size_t)pix * 64 * 2);
     TAKE(Wd, bf16, A, (size_t)64 * 64 * 2);
-    LAUNCH(im2col_small_kernel, pix * 8, st, (const bf16*)dy, d->h, d->w, d->h, d->w, 3, 1, 1, -1, R, 64,
-           pix * 8);
+    CRFR_TRY(launch_im2col_small((const bf16*)dy, d->n, d->h, d->w, d->h, d->w, 3, 1, 1, -1, R, 64, st));
     LAUNCH(repack_tapmajor_kernel, 64 * 64, st, (const bf16*)w_packed_t, T, 64, 3, cout_pad, Wd, 64, 64);
     TcGemm g{R, d->n, d->h, d->w, 64, 64, Wd, 1, 0, 1, 64, 64, dx, d->in_ld, 0, nullptr};
     return crfr_tc_gemm(g, st);
@@ -470,8 +485,7 @@ int crfr_lowered_wgrad(const crfr_conv_desc* d, const void* x, const void* dy, f
     const long long opix = (long long)d->n * d->oh * d->ow;
     TAKE(P, bf16, A, (size_t)opix * kp * 2);
     TAKE(G, float, A, (size_t)kp * d->cout * 4);
-    LAUNCH(im2col_small_kernel, opix * (kp / 8), st, (const bf16*)x, d->h, d->w, d->oh, d->ow, d->k, d->stride,
-           d->pad, 1, P, kp, opix * (kp / 8));
+    CRFR_TRY(launch_im2col_small((const bf16*)x, d->n, d->h, d->w, d->oh, d->ow, d->k, d->stride, d->pad, 1, P, kp, st));
     CRFR_CUDA(cudaMemsetAsync(G, 0, (size_t)kp * d->cout * 4, st));
     TcWgrad g{P, d->n, d->oh, d->ow, kp, kp, dy, d->cout, d->out_ld, 0, G};
     CRFR_TRY(crfr_tc_wgrad_raw(g, st));
@@ -495,8 +509,7 @@ int crfr_lowered_wgrad(const crfr_conv_desc* d, const void* x, const void* dy, f
     const long long pix = (long long)d->n * d->h * d->w;
     TAKE(R, bf16, A, (size_t)pix * 64 * 2);
     TAKE(G, float, A, (size_t)64 * 64 * 4);
-    LAUNCH(im2col_small_kernel, pix * 8, st, (const bf16*)dy, d->h, d->w, d->h, d->w, 3, 1, 1, -1, R, 64,
-           pix * 8);
+    CRFR_TRY(launch_im2col_small((const bf16*)dy, d->n, d->h, d->w, d->h, d->w, 3, 1, 1, -1, R, 64, st));
     CRFR_CUDA(cudaMemsetAsync(G, 0, (size_t)64 * 64 * 4, st));
     TcWgrad g{x, d->n, d->h, d->w, 64, d->in_ld, R, 64, 64, 0, G};
     CRFR_TRY(crfr_tc_wgrad_raw(g, st));

@@ -254,7 +254,7 @@ norm_act_bwd_reduce_kernel(const bf16* __restrict__ da, int da_ld, const bf16* _
           acc[0][j] += d;
           acc[1][j] += d * (f[j] - mu[j]) * rs[j];
         }
-        *reinterpret_cast<bf16x8*>(dz + (pix0 + pp) * dz_ld + cg * 8) = pack8(g);
+        if (dz) *reinterpret_cast<bf16x8*>(dz + (pix0 + pp) * dz_ld + cg * 8) = pack8(g);
       }
     }
   }
@@ -288,13 +288,16 @@ bwd_fold_kernel(const float* __restrict__ partial, int chunks, int c, float inv_
   }
 }
 
-// backward pass 2: dy = gamma * rstd * (dz - mean(dz) - xhat * mean(dz * xhat))
+// backward pass 2: dy = gamma * rstd * (dz - mean(dz) - xhat * mean(dz * xhat)).
+// dz == nullptr (layers without a residual branch: nobody else consumes dz): it is not stored by pass 1 but
+// recomputed here from dout (da) and y with exactly the same arithmetic and rounding - one map less per layer.
 __global__ void __launch_bounds__(kThreads)
 norm_act_bwd_apply_kernel(const bf16* __restrict__ dz, int dz_ld, const bf16* __restrict__ y, int y_ld,
                           const float* __restrict__ stats, const float* __restrict__ bstats,
                           const float* __restrict__ gamma, bf16* __restrict__ dy, int dy_ld, int hw, int c,
                           int chunk_pix, const float* __restrict__ tot, int nimg, float* __restrict__ dgamma,
-                          float* __restrict__ dbeta, float* __restrict__ dalpha) {
+                          float* __restrict__ dbeta, float* __restrict__ dalpha, const bf16* __restrict__ da, int da_ld,
+                          const float* __restrict__ beta, const float* __restrict__ alpha, int relu) {
   // CTA (0,0) also folds the per-image totals into the parameter gradients, in fixed order (deterministic)
   if (blockIdx.x == 0 && blockIdx.y == 0 && (dgamma || dbeta || dalpha)) {
     for (int ch = threadIdx.x; ch < c; ch += kThreads) {
@@ -313,7 +316,11 @@ norm_act_bwd_apply_kernel(const bf16* __restrict__ dz, int dz_ld, const bf16* __
   const int cg = threadIdx.x % groups, lane = threadIdx.x / groups;
   const int n = blockIdx.y;
   const int p0 = blockIdx.x * chunk_pix, p1 = min(hw, p0 + chunk_pix);
-  float mu[8], rs[8], gr[8], m1[8], m2[8];
+  const bool recompute = dz == nullptr;
+  const bool act = relu || alpha;
+  const bf16* dsrc = recompute ? da : dz;
+  const int dsrc_ld = recompute ? da_ld : dz_ld;
+  float mu[8], rs[8], gr[8], m1[8], m2[8], bt[8], al[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     int ch = cg * 8 + j;
@@ -322,6 +329,8 @@ norm_act_bwd_apply_kernel(const bf16* __restrict__ dz, int dz_ld, const bf16* __
     gr[j] = (gamma ? gamma[ch] : 1.f) * rs[j];
     m1[j] = bstats[2 * (n * c + ch)];
     m2[j] = bstats[2 * (n * c + ch) + 1];
+    bt[j] = beta ? beta[ch] : 0.f;
+    al[j] = relu ? 0.f : (alpha ? alpha[ch] : 1.f);
   }
   const long long pix0 = (long long)n * hw;
   for (int p = p0 + lane; p < p1; p += 4 * lanes) {
@@ -330,7 +339,7 @@ norm_act_bwd_apply_kernel(const bf16* __restrict__ dz, int dz_ld, const bf16* __
     for (int u = 0; u < 4; ++u) {
       const int pp = p + u * lanes;
       if (pp < p1) {
-        vd[u] = ld_stream(dz + (pix0 + pp) * dz_ld + cg * 8);
+        vd[u] = ld_stream(dsrc + (pix0 + pp) * dsrc_ld + cg * 8);
         vy[u] = ld_stream(y + (pix0 + pp) * y_ld + cg * 8);
       }
     }
@@ -341,6 +350,14 @@ norm_act_bwd_apply_kernel(const bf16* __restrict__ dz, int dz_ld, const bf16* __
         float d[8], f[8];
         unpack8(vd[u], d);
         unpack8(vy[u], f);
+        if (recompute && act) {   // dz = dout * act'(z), z = gamma * xhat + beta written as in pass 1, rounded to bf16
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float z = fmaf(f[j], gr[j], bt[j] - mu[j] * gr[j]);
+            if (!(z > 0.f)) d[j] *= al[j];
+            d[j] = bf16_round(d[j]);
+          }
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float xh = (f[j] - mu[j]) * rs[j];
@@ -457,7 +474,8 @@ extern "C" int crfr_norm_act_bwd(const void* dout_a, int da_ld, const void* dout
                                  const float* alpha, int relu, const void* res, int res_ld, void* dz, int dz_ld,
                                  void* dy, int dy_ld, float* dgamma, float* dbeta, float* dalpha, int n, int hw,
                                  int c, void* ws, size_t ws_bytes, void* stream) {
-  CRFR_CHECK_ARG(dout_a && y && stats && dz && dy && n > 0 && hw > 0, "norm_act_bwd: bad argument");
+  CRFR_CHECK_ARG(dout_a && y && stats && dy && n > 0 && hw > 0, "norm_act_bwd: bad argument");
+  CRFR_CHECK_ARG(dz || (!res && !dout_b), "norm_act_bwd: dz may only be omitted without a residual / second gradient");
   CRFR_CHECK_ARG(channels_ok(c) && ((da_ld | db_ld | y_ld | res_ld | dz_ld | dy_ld) & 7) == 0,
                  "norm_act_bwd: unsupported channels %d", c);
   ChunkPlan pl = plan_chunks(n, hw);
@@ -485,7 +503,8 @@ extern "C" int crfr_norm_act_bwd(const void* dout_a, int da_ld, const void* dout
   CRFR_LAUNCH_CHECK();
   norm_act_bwd_apply_kernel<<<dim3(pl.chunks, n), kThreads, 0, st>>>((const bf16*)dz, dz_ld, (const bf16*)y, y_ld,
                                                                      stats, bstats, gamma, (bf16*)dy, dy_ld, hw, c,
-                                                                     pl.chunk_pix, tot, n, dgamma, dbeta, dalpha);
+                                                                     pl.chunk_pix, tot, n, dgamma, dbeta, dalpha,
+                                                                     (const bf16*)dout_a, da_ld, beta, alpha, relu);
   CRFR_COUNT_LAUNCH();
   CRFR_LAUNCH_CHECK();
   return CRFR_OK;

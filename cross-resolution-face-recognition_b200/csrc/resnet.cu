@@ -296,7 +296,7 @@ struct Net {
           const Tensor& y = op.a;
           const long long count = (long long)y.n * y.h * y.w;
           const size_t bytes = (size_t)count * y.ld * sizeof(bf16);
-          bf16* dz = (bf16*)alloc(bytes);
+          bf16* dz = (op.has_res || s.size() > 1) ? (bf16*)alloc(bytes) : nullptr;   // only if somebody consumes it
           bf16* dy = (bf16*)alloc(bytes);
           if (run())
             check(crfr_norm_act_bwd(s[0].p, s[0].ld, s.size() > 1 ? s[1].p : nullptr, s.size() > 1 ? s[1].ld : 8, y.p, y.ld,

@@ -175,7 +175,8 @@ def norm_act_bwd(dout, y, stats, gamma=None, beta=None, alpha=None, relu=False, 
     n, h, w, ld = y.shape
     c = ld if c is None else c
     dev = y.device
-    dz = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=dev)
+    # dz (gradient w.r.t. the residual input) is only produced when somebody can consume it
+    dz = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=dev) if (res is not None or dout_b is not None) else None
     dy = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=dev)
     dg = torch.zeros((c,), dtype=torch.float32, device=dev) if gamma is not None else None
     db = torch.zeros((c,), dtype=torch.float32, device=dev) if beta is not None else None

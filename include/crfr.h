@@ -86,8 +86,9 @@ int crfr_norm_stats(const void* y, int n, int hw, int c, int ld, float eps, floa
 int crfr_norm_act_fwd(const void* y, int y_ld, const float* stats, const float* gamma, const float* beta,
                       const float* alpha, int relu, const void* res, int res_ld, void* out, int out_ld, int n,
                       int hw, int c, void* stream);
-/* dout = dout_a (+ dout_b).  Outputs: dz (grad wrt pre-activation, == grad wrt res), dy (grad wrt conv output),
- * dgamma/dbeta/dalpha fp32 [c] accumulated (NULL to skip). */
+/* dout = dout_a (+ dout_b).  Outputs: dz (grad wrt pre-activation, == grad wrt res; may be NULL when res and dout_b
+ * are NULL: it is then neither stored nor re-read, which saves one full map of HBM traffic), dy (grad wrt conv
+ * output), dgamma/dbeta/dalpha fp32 [c] accumulated (NULL to skip). */
 int crfr_norm_act_bwd(const void* dout_a, int da_ld, const void* dout_b, int db_ld, const void* y, int y_ld,
                       const float* stats, const float* gamma, const float* beta, const float* alpha, int relu,
                       const void* res, int res_ld, void* dz, int dz_ld, void* dy, int dy_ld, float* dgamma,
