@@ -219,7 +219,7 @@ def run_ours(args):
     net = OverallNetwork()
     net.apply(weights_init)
     net = net.to(dev).train()
-    trainer = FSRNetTrainer(net, lr=1e-3, chunk=args.chunk)
+    trainer = FSRNetTrainer(net, lr=1e-3, chunk=args.chunk, lanes=args.lanes, use_graph=bool(args.graph))
 
     # synthetic data, a few distinct batches in pinned host memory
     g = torch.Generator().manual_seed(4321 + rank)
@@ -288,7 +288,7 @@ def run_ours(args):
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": "FSRNet train step bf16, batch %d per GPU, 16x16 -> 128x128, parsing + landmark "
                                        "priors (BASELINE.json configs[1])" % B, "global_batch": B * world,
-                           "chunk": args.chunk, "parallelism": "dp%d" % world,
+                           "chunk": args.chunk, "lanes": args.lanes, "cuda_graph": bool(args.graph), "parallelism": "dp%d" % world,
                            "l2": "inputs + saved activations per chunk (GBs) exceed the 126 MB L2; no explicit flush"},
                 "clocks": clocks, "loss": loss_val,
                 "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
@@ -323,7 +323,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=128)
-    ap.add_argument("--chunk", type=int, default=128)
+    ap.add_argument("--chunk", type=int, default=128, help="images per native call")
+    ap.add_argument("--lanes", type=int, default=1, help="concurrent chunk pipelines (streams) per GPU")
+    ap.add_argument("--graph", type=int, default=0, help="1: replay the step from a captured CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the matcher / KD-step secondary measurements")
     args = ap.parse_args()

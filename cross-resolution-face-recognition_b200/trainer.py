@@ -11,6 +11,18 @@ One process per GPU.  Per step and per rank:
      issued on a side stream behind that event and overlaps the rest of the backward (only collective in the loop);
   4. fused RMSprop on the flat arena (torch.optim.RMSprop semantics, FSR_main.py:185).
 
+Concurrent lanes (``lanes`` > 1, CUDA only): the chunks are dealt to independent pipelines, each with its own CUDA
+stream, workspace and gradient arena.  InstanceNorm makes the chunks independent, so lane A's tensor-bound convolution
+kernels overlap lane B's HBM-bound normalisation kernels instead of alternating with them on one stream; the lane
+arenas are summed per bucket right before the bucket's all-reduce / the optimiser step.
+
+CUDA graph (``use_graph=True``): the native step issues ~1 100 launches (each conv encodes three tensor maps on the
+host), i.e. 20-25 ms of host time per 128 images - as long as one lane keeps the GPU busy for longer than that the
+host runs ahead and nothing is lost, but several lanes double the launch count and become host-bound.  With
+``use_graph`` the forward + loss + backward of all chunks / lanes is captured once per input shape (stream capture
+follows the lane streams and the library's internal weight-gradient stream through their fork / join events) and
+replayed from static input buffers; only the all-reduce and the optimiser step stay outside the graph.
+
 Loss scaling: FSR_main.py:234 divides by 2*train_batch.  With G = global batch (all ranks) and chunk size c, the
 chunk's share of the batch-mean losses is c/G, so each chunk is run with loss_div = 2*G*G/c and gradients are
 SUM-reduced across ranks: the result equals the single-GPU gradient of the concatenated batch.
@@ -52,9 +64,30 @@ def chunk_loss_div(global_batch, chunk):
     return 2.0 * global_batch * global_batch / chunk
 
 
+class _Lane:
+    """One independent chunk pipeline: stream, workspace, gradient arena, loss accumulators, bucket events."""
+
+    def __init__(self, trainer, index):
+        dev = trainer.device
+        self.index = index
+        self.stream = torch.cuda.Stream(device=dev)
+        self.flat_g = trainer.flat_g if index == 0 else torch.zeros_like(trainer.flat_g)
+        params = trainer.model.ordered_parameters()
+        self.grad_views = [self.flat_g[o:o + p.numel()].view(p.shape) for p, o in zip(params, trainer.offs)]
+        self.gtable = M._ParamTable(self.grad_views)
+        self.losses = torch.zeros((5,), dtype=torch.float32, device=dev)
+        self.loss_acc = torch.zeros((5,), dtype=torch.float32, device=dev)
+        self.events = [torch.cuda.Event() for _ in trainer.buckets]
+        for e in self.events:
+            e.record()
+        self.done = torch.cuda.Event()
+        self.ws = None
+        self.outs = None
+
+
 class FSRNetTrainer:
     def __init__(self, model, lr=1e-3, alpha=0.99, eps=1e-8, weight_decay=1e-5, chunk=16, w_pix=5.0,
-                 engine=L.ENGINE_AUTO, process_group=None, world_size=None):
+                 engine=L.ENGINE_AUTO, process_group=None, world_size=None, lanes=1, use_graph=False):
         import torch.distributed as dist
         self.model = model
         self.lr, self.alpha, self.eps, self.wd = lr, alpha, eps, weight_decay
@@ -90,6 +123,10 @@ class FSRNetTrainer:
                 e.record()                  # materialise the cudaEvent_t handles
         else:
             self.comm_stream, self.events = None, []
+        self.lanes = [_Lane(self, i) for i in range(lanes)] if (dev.type == "cuda" and lanes > 1) else []
+        self._w_cache = {}
+        self.use_graph = bool(use_graph) and dev.type == "cuda"
+        self._graph, self._graph_key, self._static = None, None, None
 
     def reset_optimizer_state(self):
         """The reference re-creates RMSprop every epoch (FSR_main.py:183-185): the square average restarts."""
@@ -111,11 +148,123 @@ class FSRNetTrainer:
         lo, hi = self.buckets[k]
         return self.dist.all_reduce(self.flat_g[lo:hi], op=self.dist.ReduceOp.SUM, group=self.pg, async_op=True)
 
+    def _loss_weights(self, c, B):
+        """total adds up over chunks; the parts are chunk means -> weight by c/B (cached device constants)."""
+        key = (c, B)
+        if key not in self._w_cache:
+            self._w_cache[key] = torch.tensor([1.0] + [c / B] * 4, device=self.device)
+        return self._w_cache[key]
+
+    def _step_lanes(self, x, hr, heatmap, labels, lr, events_for_dp=True, finish=True):
+        """Chunks dealt round-robin to concurrent lanes (see the module docstring)."""
+        B = x.shape[0]
+        G = B * self.world
+        dp = self.dist is not None and self.world > 1 and events_for_dp
+        main = torch.cuda.current_stream()
+        start = torch.cuda.Event()
+        start.record(main)
+        starts = list(range(0, B, self.chunk))
+        used = self.lanes[:min(len(self.lanes), len(starts))]
+        for ln in used:
+            ln.stream.wait_event(start)
+            with torch.cuda.stream(ln.stream):
+                ln.flat_g.zero_()
+                ln.loss_acc.zero_()
+        for ci, s0 in enumerate(starts):
+            s1 = min(B, s0 + self.chunk)
+            c = s1 - s0
+            ln = used[ci % len(used)]
+            last_of_lane = ci + len(used) >= len(starts)
+            with torch.cuda.stream(ln.stream):
+                if ln.outs is None or ln.outs[0].shape[0] != c or ln.outs[0].shape[2] != x.shape[2]:
+                    ln.outs = M.alloc_outputs(x[s0:s1])
+                need = L.lib().crfr_fsrnet_workspace_bytes(c, x.shape[2], 1)
+                if ln.ws is None or ln.ws.numel() < need:
+                    ln.ws = torch.empty(need, dtype=torch.uint8, device=x.device)
+                io = M._io(x[s0:s1], ln.outs, (hr[s0:s1], heatmap[s0:s1], labels[s0:s1]),
+                           loss_div=chunk_loss_div(G, c), w_pix=self.w_pix)
+                if dp and last_of_lane:
+                    for i, e in enumerate(ln.events):
+                        io.bucket_events[i] = e.cuda_event
+                L.call("crfr_fsrnet_train_step", self.engine, self.ptable.arr, ln.gtable.arr, C.byref(io),
+                       ln.losses.data_ptr(), ln.ws.data_ptr(), ln.ws.numel(), ops.stream())
+                ln.loss_acc.add_(ln.losses * self._loss_weights(c, B))
+                if last_of_lane:
+                    ln.done.record(ln.stream)
+        if dp:
+            works = []
+            with torch.cuda.stream(self.comm_stream):
+                for k, (lo, hi) in enumerate(self.buckets):
+                    for ln in used:
+                        self.comm_stream.wait_event(ln.events[k])
+                    for ln in used[1:]:
+                        self.flat_g[lo:hi].add_(ln.flat_g[lo:hi])
+                    works.append(self._allreduce_bucket(k))
+            for wk in works:
+                wk.wait()
+            for ln in used:
+                main.wait_event(ln.done)
+        else:
+            for ln in used:
+                main.wait_event(ln.done)
+            for ln in used[1:]:
+                self.flat_g.add_(ln.flat_g)
+        self.loss_acc.copy_(used[0].loss_acc)
+        for ln in used[1:]:
+            self.loss_acc.add_(ln.loss_acc)
+        if finish:
+            self._optimizer_step(self.lr if lr is None else lr)
+        return self.loss_acc
+
+    def _compute(self, x, hr, heatmap, labels):
+        """forward + losses + backward of every chunk into flat_g / loss_acc; no collective, no optimiser step."""
+        if self.lanes and x.shape[0] > self.chunk:
+            self._step_lanes(x, hr, heatmap, labels, None, events_for_dp=False, finish=False)
+            return
+        B = x.shape[0]
+        G = B * self.world
+        self.flat_g.zero_()
+        self.loss_acc.zero_()
+        for s0 in range(0, B, self.chunk):
+            s1 = min(B, s0 + self.chunk)
+            c = s1 - s0
+            if self.outs is None or self.outs[0].shape[0] != c or self.outs[0].shape[2] != x.shape[2]:
+                self.outs = M.alloc_outputs(x[s0:s1])
+            self._native_chunk(x[s0:s1], hr[s0:s1], heatmap[s0:s1], labels[s0:s1], self.outs, chunk_loss_div(G, c), None)
+            self.loss_acc.add_(self.losses * self._loss_weights(c, B))
+
+    def _step_graph(self, x, hr, heatmap, labels, lr):
+        key = (tuple(x.shape), tuple(hr.shape), tuple(heatmap.shape), tuple(labels.shape), x.dtype, labels.dtype)
+        if self._graph is None or self._graph_key != key:
+            self._static = tuple(torch.empty_like(t) for t in (x, hr, heatmap, labels))
+            for d, t in zip(self._static, (x, hr, heatmap, labels)):
+                d.copy_(t)
+            self._compute(*self._static)           # eager warm-up: workspaces, kernel attributes, helper streams
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._compute(*self._static)
+            self._graph, self._graph_key = graph, key
+        else:
+            for d, t in zip(self._static, (x, hr, heatmap, labels)):
+                d.copy_(t, non_blocking=True)
+        self._graph.replay()
+        if self.dist is not None and self.world > 1:
+            works = [self._allreduce_bucket(k) for k in range(len(self.buckets))]
+            for wk in works:
+                wk.wait()
+        self._optimizer_step(self.lr if lr is None else lr)
+        return self.loss_acc
+
     def step(self, x, hr, heatmap, labels, lr=None):
         """x [B,3,S,S] fp32 (already upsampled + normalised), hr [B,3,S,S], heatmap [B,S/4,S/4], labels int64
         [B,1,S/4,S/4]; all on this rank's device.  Returns the device tensor (total, L_sr, L_coarse, L_lm, L_ce) of
         this rank's share of the global-batch loss (parts are rank-local batch means)."""
         M.check_input(x) if x.is_cuda else None
+        if self.use_graph and x.is_cuda:
+            return self._step_graph(x, hr, heatmap, labels, lr)
+        if self.lanes and x.is_cuda and x.shape[0] > self.chunk:
+            return self._step_lanes(x, hr, heatmap, labels, lr)
         B = x.shape[0]
         G = B * self.world
         self.flat_g.zero_()
@@ -132,9 +281,7 @@ class FSRNetTrainer:
             use_events = last and self.dist is not None and self.world > 1 and self.events
             self._native_chunk(x[s0:s1], hr[s0:s1], heatmap[s0:s1], labels[s0:s1], outs, chunk_loss_div(G, c),
                                self.events if use_events else None)
-            # total adds up over chunks; the parts are chunk means -> weight by c/B
-            w = torch.tensor([1.0] + [c / B] * 4, device=self.loss_acc.device)
-            self.loss_acc.add_(self.losses * w)
+            self.loss_acc.add_(self.losses * self._loss_weights(c, B))
             if use_events:
                 main = torch.cuda.current_stream()
                 with torch.cuda.stream(self.comm_stream):

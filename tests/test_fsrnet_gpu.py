@@ -168,3 +168,29 @@ def test_rejects_cpu_and_bad_shapes(cuda):
         net(torch.zeros(1, 3, 64, 64))
     with pytest.raises(ValueError):
         net(torch.zeros(1, 3, 60, 60, device="cuda"))
+
+
+def test_trainer_lanes_match_single_stream(cuda):
+    """FSRNetTrainer with concurrent lanes (chunks on independent streams / workspaces / gradient arenas) produces the
+    same gradients, losses and parameter update as the single-stream trainer."""
+    from crfr_b200 import _lib as L
+    from crfr_b200.trainer import FSRNetTrainer
+    from oracle import fsrnet_oracle as FO
+    x, hr, lbl, hm = (t.cuda() for t in FO.synthetic_batch(4, 64, seed=9))
+    results = []
+    for lanes, chunk, graph in ((1, 4, False), (2, 2, False), (3, 1, False), (1, 4, True), (2, 2, True)):
+        tr = FSRNetTrainer(_net(L.ENGINE_AUTO), lr=1e-3, chunk=chunk, lanes=lanes, use_graph=graph)
+        losses = tr.step(x, hr, hm, lbl).clone()
+        if graph:                                 # second call = pure replay from the static buffers
+            tr2 = FSRNetTrainer(_net(L.ENGINE_AUTO), lr=0.0, chunk=chunk, lanes=lanes, use_graph=True)
+            tr2.step(x * 0.5, hr, hm, lbl)        # captured on other data (lr = 0: the parameters stay put) ...
+            l2 = tr2.step(x, hr, hm, lbl).clone()  # ... and replayed on ours
+            torch.cuda.synchronize()
+            assert rel_err(tr2.flat_g, results[0][0]) < 2e-2 and rel_err(l2, results[0][2]) < 1e-4
+        torch.cuda.synchronize()
+        results.append((tr.flat_g.clone(), tr.flat_p.clone(), losses))
+    g0, p0, l0 = results[0]
+    for g, p, l in results[1:]:
+        assert rel_err(l, l0) < 1e-4
+        assert rel_err(g, g0) < 2e-2            # chunked bf16 rounding differs slightly from the full batch
+        assert rel_err(p, p0) < 1e-3
