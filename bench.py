@@ -170,6 +170,27 @@ def time_kd_step(torch, batch=256, reps=3):
             "workload": "ResNet_34 teacher(eval) + student + assistant KD step, batch %d, 112x112" % batch}
 
 
+def time_ir50(torch, batch=256, reps=3):
+    """Frozen IR_50 teacher forward (DISTILLATION/model/model_irse.py), eval mode, 12.59 GFLOP/image."""
+    from crfr_b200.model.model_irse import IR_50
+    torch.manual_seed(9)
+    net = IR_50([112, 112]).cuda().eval()
+    x = torch.randn(batch, 3, 112, 112, device="cuda")
+    with torch.no_grad():
+        for _ in range(2):
+            net(x)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            net(x)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    return {"images_per_sec": batch / (ms * 1e-3), "ms": ms, "tflops": batch * 12.59e9 / (ms * 1e-3) / 1e12,
+            "workload": "IR_50 teacher forward (eval), batch %d, 112x112" % batch}
+
+
 def time_dominant_kernel(torch, ops, L, chunk):
     """CUDA-event timing of the dominant kernel: the 3x3 64->64 implicit GEMM at 128x128 (87 % of the MACs)."""
     g = torch.Generator(device="cuda").manual_seed(3)
@@ -307,6 +328,7 @@ def run_ours(args):
             torch.cuda.empty_cache()
             line["matcher"] = time_matcher(torch, ops)
             line["kd_step"] = time_kd_step(torch)
+            line["ir50_teacher"] = time_ir50(torch)
         if not args.no_cpu_baseline:
             v, cores, sec = cpu_reference_step_rate(3, 1)
             line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",

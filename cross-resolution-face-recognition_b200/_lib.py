@@ -30,6 +30,7 @@ class ResnetIO(C.Structure):
 
 
 RESNET34_NPARAMS, RESNET34_NBN = 114, 38
+IR50_NPARAMS, IR50_NBN = 187, 54
 
 # name -> (restype, argtypes); every symbol declared in include/crfr.h
 SIGNATURES = {
@@ -77,6 +78,8 @@ SIGNATURES = {
     "crfr_bn_running_to_stats": (ci, [vp, vp, ci, cf, vp, vp]),
     "crfr_resnet34_workspace_bytes": (csz, [ci, ci, ci]),
     "crfr_resnet34_forward": (ci, [ci, vp, vp, C.POINTER(ResnetIO), vp, csz, vp]),
+    "crfr_ir50_workspace_bytes": (csz, [ci, ci]),
+    "crfr_ir50_forward": (ci, [ci, vp, vp, C.POINTER(ResnetIO), vp, csz, vp]),
     "crfr_resnet34_backward": (ci, [ci, vp, vp, C.POINTER(ResnetIO), vp, vp, vp, csz, vp]),
 }
 

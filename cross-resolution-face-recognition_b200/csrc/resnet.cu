@@ -8,7 +8,11 @@
 // head as a tcgen05 GEMM over the NHWC-flattened feature (weights re-ordered from the reference's NCHW flatten), and
 // BatchNorm1d on the embedding.
 //
-// ref: model/resnet.py:18-47 (BasicBlock), :152-225 (ResNet.__init__/_make_layer/forward), :231-236 (ResNet_34).
+// The frozen IR_50 teacher (DISTILLATION/model/model_irse.py) is a second, forward-only program over the same ops:
+// BN -> conv3x3 -> PReLU -> conv3x3(stride) -> BN, plus a MaxPool2d(1, stride) / conv1x1+BN shortcut, 24 blocks.
+//
+// ref: model/resnet.py:18-47 (BasicBlock), :152-225 (ResNet.__init__/_make_layer/forward), :231-236 (ResNet_34);
+//      DISTILLATION/model/model_irse.py:49-66 (bottleneck_IR), :103-110 (get_blocks(50)), :129-172 (Backbone).
 #include <vector>
 
 #include "common.cuh"
@@ -62,6 +66,30 @@ __global__ void linear_unpack_kernel(const float* __restrict__ G, float* __restr
   const long long r = i - (long long)o * K;       // c*HW + hw
   const int c = (int)(r / HW), hw = (int)(r - (long long)c * HW);
   dw[i] += G[((long long)hw * C + c) * O + o];
+}
+
+// MaxPool2d(kernel 1, stride 2) = pixel subsampling (model_irse.py:53): out[n][y][x][:] = x[n][2y][2x][:]
+__global__ void subsample2_kernel(const bf16* __restrict__ x, int x_ld, bf16* __restrict__ out, int out_ld, int oh,
+                                  int ow, int groups, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int g = (int)(i % groups);
+  long long p = i / groups;
+  const int ox = (int)(p % ow);
+  long long q = p / ow;
+  const int oy = (int)(q % oh);
+  const long long n = q / oh;
+  const long long src = ((n * (2 * oh) + 2 * oy) * (2LL * ow) + 2 * ox) * x_ld + g * 8;
+  *reinterpret_cast<uint4*>(out + p * out_ld + g * 8) = *reinterpret_cast<const uint4*>(x + src);
+}
+
+// stats[c] = (mean 0, rstd 1): turns the fused normalise kernel into a plain PReLU pass
+__global__ void identity_stats_kernel(float* __restrict__ stats, int c) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < c) {
+    stats[2 * i] = 0.f;
+    stats[2 * i + 1] = 1.f;
+  }
 }
 
 struct Net {
@@ -143,8 +171,8 @@ struct Net {
   }
 
   // BatchNorm (batch statistics over n*h*w in training, running statistics otherwise) + optional residual + ReLU
-  Tensor bn(const Tensor& y, int g_idx, int relu, const Tensor* res) {
-    const int bi = bncur++;
+  Tensor bn(const Tensor& y, int g_idx, int relu, const Tensor* res, int alpha_idx = -1, int bn_index = -1) {
+    const int bi = bn_index >= 0 ? bn_index : bncur++;
     const long long count = (long long)y.n * y.h * y.w;
     Tensor out = new_tensor(y.n, y.h, y.w, y.c);
     float* stats = (float*)alloc((size_t)y.c * 2 * sizeof(float));
@@ -159,7 +187,8 @@ struct Net {
       } else {
         check(crfr_bn_running_to_stats(rmean, rvar, y.c, io->eps, stats, st));
       }
-      check(crfr_norm_act_fwd(y.p, y.ld, stats, params[g_idx], params[g_idx + 1], nullptr, relu, res ? res->p : nullptr,
+      check(crfr_norm_act_fwd(y.p, y.ld, stats, params[g_idx], params[g_idx + 1],
+                              alpha_idx >= 0 ? params[alpha_idx] : nullptr, relu, res ? res->p : nullptr,
                               res ? res->ld : 8, out.p, out.ld, 1, (int)count, y.c, st));
     }
     Op op;
@@ -191,13 +220,13 @@ struct Net {
     return out;
   }
 
-  Tensor linear(const Tensor& a) {
+  Tensor linear(const Tensor& a, int w_index = -1) {
     const int B = a.n, K = a.h * a.w * a.c;
     Tensor y = new_tensor(B, 1, 1, kEmb);
     wp = (bf16*)alloc((size_t)kEmb * K * sizeof(bf16));
     wpt = io->training ? (bf16*)alloc((size_t)kEmb * K * sizeof(bf16)) : nullptr;
-    const int w_idx = pcur;
-    pcur += 2;
+    const int w_idx = w_index >= 0 ? w_index : pcur;
+    if (w_index < 0) pcur += 2;
     if (run()) {
       const long long total = (long long)kEmb * K;
       linear_pack_kernel<<<crfr_cdiv(total, 256), 256, 0, st>>>(params[w_idx], wp, wpt, kEmb, a.c, a.h * a.w);
@@ -261,6 +290,85 @@ struct Net {
     emb = bn(yfc, pcur, 0, nullptr);          // bn_o2 (BatchNorm1d)
     pcur += 2;
     to_nchw(emb, io->emb);
+  }
+
+  // ---- IR_50 (forward only, eval-mode BatchNorm) ----
+  Tensor prelu(const Tensor& y, int alpha_idx, float* ident) {   // plain PReLU pass
+    Tensor out = new_tensor(y.n, y.h, y.w, y.c);
+    if (run())
+      check(crfr_norm_act_fwd(y.p, y.ld, ident, nullptr, nullptr, params[alpha_idx], 0, nullptr, 8, out.p, out.ld, 1,
+                              y.n * y.h * y.w, y.c, st));
+    return out;
+  }
+  Tensor subsample2(const Tensor& x) {
+    Tensor out = new_tensor(x.n, x.h / 2, x.w / 2, x.c);
+    if (run()) {
+      const long long total = (long long)out.n * out.h * out.w * (x.c / 8);
+      subsample2_kernel<<<crfr_cdiv(total, 256), 256, 0, st>>>(x.p, x.ld, out.p, out.ld, out.h, out.w, x.c / 8, total);
+      CRFR_COUNT_LAUNCH();
+      check_cuda(cudaGetLastError());
+    }
+    return out;
+  }
+
+  // parameter order (named_parameters): input_layer (4), output_layer (6), body blocks (7, or 10 with a conv shortcut);
+  // BatchNorm order (named_buffers): input_layer.1, output_layer.0, output_layer.4, then per block
+  // [shortcut_layer.1], res_layer.0, res_layer.4
+  void forward_ir50() {
+    const int B = io->batch, S = io->size;
+    scratch_bytes = scratch_need_ir50(B, S);
+    scratch = alloc(scratch_bytes);
+    float* ident = (float*)alloc(512 * 2 * sizeof(float));
+    if (run()) {
+      identity_stats_kernel<<<4, 128, 0, st>>>(ident, 512);
+      CRFR_COUNT_LAUNCH();
+    }
+    Tensor x4 = new_tensor(B, S, S, 3);
+    if (run()) check(crfr_nchw_f32_to_nhwc_bf16(io->x, x4.p, B, 3, S, S, 4, 4, st));
+    Tensor a = bn(conv(x4, 0, 64, 3, 1, 1, false), 1, 0, nullptr, 3, 0);     // input_layer: conv, BN, PReLU
+    int p = 10, bi = 3;
+    const int units[4] = {3, 4, 14, 3}, depth[4] = {64, 128, 256, 512};
+    int in_ch = 64;
+    for (int l = 0; l < 4; ++l)
+      for (int u = 0; u < units[l]; ++u) {   // bottleneck_IR, model_irse.py:49-66
+        const int stride = u == 0 ? 2 : 1, d = depth[l];
+        const bool conv_sc = in_ch != d;
+        Tensor sc = a;
+        if (conv_sc) {
+          sc = bn(conv(a, p, d, 1, stride, 0, false), p + 1, 0, nullptr, -1, bi);
+          p += 3; bi += 1;
+        } else if (stride == 2) {
+          sc = subsample2(a);
+        }
+        Tensor r = bn(a, p, 0, nullptr, -1, bi);                       // res_layer.0
+        r = prelu(conv(r, p + 2, d, 3, 1, 1, false), p + 3, ident);    // res_layer.1, .2
+        r = conv(r, p + 4, d, 3, stride, 1, false);                    // res_layer.3
+        a = bn(r, p + 5, 0, &sc, -1, bi + 1);                          // res_layer.4 + shortcut
+        p += 7; bi += 2;
+        in_ch = d;
+      }
+    Tensor o = bn(a, 4, 0, nullptr, -1, 1);                            // output_layer.0 (Dropout: identity in eval)
+    Tensor y = linear(o, 6);                                           // output_layer.3
+    emb = bn(y, 8, 0, nullptr, -1, 2);                                 // output_layer.4 (BatchNorm1d)
+    to_nchw(emb, io->emb);
+  }
+
+  size_t scratch_need_ir50(int B, int S) const {
+    size_t m = crfr_norm_ws_bytes(1, B * S * S, 64);
+    const int q = S / 2;
+    const crfr_conv_desc shapes[] = {
+        {B, S, S, 3, 64, 3, 1, 1, S, S, 4, 64, 0},
+        {B, S, S, 64, 64, 3, 2, 1, q, q, 64, 64, 0},
+        {B, q, q, 64, 128, 3, 2, 1, q / 2, q / 2, 64, 128, 0},
+        {B, q, q, 64, 128, 1, 2, 0, q / 2, q / 2, 64, 128, 0},
+        {B, q / 2, q / 2, 128, 256, 3, 2, 1, q / 4, q / 4, 128, 256, 0},
+        {B, q / 4, q / 4, 256, 512, 3, 2, 1, q / 8, q / 8, 256, 512, 0},
+        {B, q / 8, q / 8, 512, 512, 3, 1, 1, q / 8, q / 8, 512, 512, 0}};
+    for (const crfr_conv_desc& d : shapes) {
+      const size_t b = crfr_conv_workspace_bytes(&d);
+      if (b > m) m = b;
+    }
+    return m + 4096;
   }
 
   // ---- backward ----
@@ -395,6 +503,27 @@ extern "C" int crfr_resnet34_forward(int engine, const float* const* host_params
   Net net;
   init_net(net, engine, host_params, nullptr, host_buffers, io, ws, ws_bytes, (cudaStream_t)stream, true);
   net.forward();
+  return net.err;
+}
+
+extern "C" size_t crfr_ir50_workspace_bytes(int batch, int size) {
+  if (batch <= 0 || size != 112) return 0;
+  crfr_resnet_io io = {};
+  io.batch = batch; io.size = size; io.training = 0; io.momentum = 0.1f; io.eps = 1e-5f;
+  Net net;
+  init_net(net, CRFR_ENGINE_AUTO, nullptr, nullptr, nullptr, &io, nullptr, ~(size_t)0 >> 2, nullptr, false);
+  net.forward_ir50();
+  return net.off + 65536;
+}
+
+extern "C" int crfr_ir50_forward(int engine, const float* const* host_params, void* const* host_buffers,
+                                 const crfr_resnet_io* io, void* ws, size_t ws_bytes, void* stream) {
+  CRFR_TRY(check_io(io, "ir50_forward"));
+  CRFR_CHECK_ARG(host_params && host_buffers && ws, "ir50_forward: null pointer");
+  CRFR_CHECK_ARG(!io->training, "ir50_forward: the teacher runs in eval mode only (train-mode Dropout is stochastic)");
+  Net net;
+  init_net(net, engine, host_params, nullptr, host_buffers, io, ws, ws_bytes, (cudaStream_t)stream, true);
+  net.forward_ir50();
   return net.err;
 }
 

@@ -232,6 +232,15 @@ int crfr_resnet34_backward(int engine, const float* const* host_params, float* c
                            const crfr_resnet_io* io, const float* d_emb, const float* const* d_feat, void* ws,
                            size_t ws_bytes, void* stream);
 
+/* ---------------------------------------------------------------- IR_50 teacher (forward only) -------------- */
+#define CRFR_IR50_NPARAMS 187 /* named_parameters() order of DISTILLATION/model/model_irse.py:IR_50 */
+#define CRFR_IR50_NBN 54      /* BatchNorm layers in module order (input_layer, output_layer, body) */
+/* ref: Backbone.forward model_irse.py:167-172 in eval mode (the frozen teacher of distill_main.py:43,201): returns the
+ * 512-d embedding in io->emb; io->feat is ignored, io->training must be 0.  buffers: 3 * 54 pointers as above. */
+size_t crfr_ir50_workspace_bytes(int batch, int size);
+int crfr_ir50_forward(int engine, const float* const* host_params, void* const* host_buffers,
+                      const crfr_resnet_io* io, void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

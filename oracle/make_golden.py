@@ -206,9 +206,32 @@ def golden_resnet():
     print("resnet34 kd", l_s.item(), l_a.item())
 
 
+def golden_ir50():
+    """IR_50 teacher (DISTILLATION/model/model_irse.py) in eval mode on the reference's own module."""
+    IR = R.load("DISTILLATION/model/model_irse.py")
+    torch.manual_seed(91)
+    net = IR.IR_50([112, 112])
+    sd = RO.build_ir50_state_dict(91)
+    ref_sd = net.state_dict()
+    assert list(sd) == list(ref_sd) and all(torch.equal(sd[k], ref_sd[k]) for k in sd), "seeded init differs"
+    assert len(list(net.named_parameters())) == 187 and sum(1 for k in sd if k.endswith("running_mean")) == 54
+    sd = RO.randomize_bn_everywhere(sd, 191)
+    net.load_state_dict(sd)
+    net.eval()
+    x = RO.synthetic_faces(4, seed=4322)
+    with torch.no_grad():
+        emb = net(x)
+        o = RO.ir50_forward(sd, x)
+    rel = ((o - emb).norm() / emb.norm()).item()
+    assert rel < 1e-4, rel
+    np.savez_compressed(os.path.join(OUT, "ir50.npz"), emb=emb.numpy(), names=np.array(list(sd)),
+                        checksums=np.array([v.double().sum().item() for v in RO.build_ir50_state_dict(91).values()]))
+    print("ir50 eval forward ok, rel", rel, "emb norm", emb.norm().item())
+
+
 if __name__ == "__main__":
     assert R.available(), "reference tree not present"
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["losses", "bicubic", "eval", "fsrnet", "resnet"]
+    which = sys.argv[1:] or ["losses", "bicubic", "eval", "fsrnet", "resnet", "ir50"]
     for w in which:
         globals()["golden_" + w]()

@@ -187,3 +187,99 @@ def kd_step(sd_t, sd_s, sd_a, x, precision="fp32"):
     g_as = torch.autograd.grad(l_a, [ls[k] for k in names], allow_unused=True)
     as_dict = lambda gs: {k: (torch.zeros_like(ls[k]) if g is None else g) for k, g in zip(names, gs)}
     return l_s.detach(), l_a.detach(), as_dict(g_s), as_dict(g_a), as_dict(g_as), (t_outs, s_outs, a_outs)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# IR_50 teacher (DISTILLATION/model/model_irse.py:49-66, 103-110, 129-197), eval mode
+# ----------------------------------------------------------------------------------------------------------------
+IR50_UNITS = (3, 4, 14, 3)
+
+
+def ir50_block_specs():
+    """(in_channel, depth, stride) of the 24 bottleneck_IR units, model_irse.py:96-110."""
+    specs, in_ch = [], 64
+    for units, depth in zip(IR50_UNITS, PLANES):
+        for u in range(units):
+            specs.append((in_ch, depth, 2 if u == 0 else 1))
+            in_ch = depth
+    return specs
+
+
+def build_ir50_state_dict(seed):
+    """state_dict of a freshly constructed ``IR_50([112, 112])`` (reference key order, draw-for-draw identical init)."""
+    torch.manual_seed(seed)
+    mods = OrderedDict()
+    mods["input_layer.0"] = nn.Conv2d(3, 64, 3, 1, 1, bias=False)
+    mods["input_layer.1"] = nn.BatchNorm2d(64)
+    mods["input_layer.2"] = nn.PReLU(64)
+    mods["output_layer.0"] = nn.BatchNorm2d(512)
+    mods["output_layer.3"] = nn.Linear(512 * 7 * 7, 512)
+    mods["output_layer.4"] = nn.BatchNorm1d(512)
+    for i, (cin, d, stride) in enumerate(ir50_block_specs()):
+        p = "body.%d." % i
+        if cin != d:
+            mods[p + "shortcut_layer.0"] = nn.Conv2d(cin, d, 1, stride, bias=False)
+            mods[p + "shortcut_layer.1"] = nn.BatchNorm2d(d)
+        mods[p + "res_layer.0"] = nn.BatchNorm2d(cin)
+        mods[p + "res_layer.1"] = nn.Conv2d(cin, d, 3, 1, 1, bias=False)
+        mods[p + "res_layer.2"] = nn.PReLU(d)
+        mods[p + "res_layer.3"] = nn.Conv2d(d, d, 3, stride, 1, bias=False)
+        mods[p + "res_layer.4"] = nn.BatchNorm2d(d)
+    for m in mods.values():                   # model_irse.py:174-188
+        if isinstance(m, (nn.Conv2d, nn.Linear)):
+            nn.init.xavier_uniform_(m.weight.data)
+            if m.bias is not None:
+                m.bias.data.zero_()
+        elif isinstance(m, (nn.BatchNorm2d, nn.BatchNorm1d)):
+            m.weight.data.fill_(1)
+            m.bias.data.zero_()
+    sd = OrderedDict()
+    for k, m in mods.items():
+        for n, v in m.state_dict().items():
+            sd[k + "." + n] = v.detach().clone()
+    return sd
+
+
+def randomize_bn_everywhere(sd, seed):
+    """Seeded non-trivial BatchNorm scales / shifts / running statistics for every BatchNorm of a state_dict."""
+    g = torch.Generator().manual_seed(seed)
+    out = OrderedDict((k, v.clone()) for k, v in sd.items())
+    for k in sd:
+        if k.endswith("running_mean"):
+            p = k[:-len("running_mean")]
+            out[p + "weight"] = 0.5 + torch.rand(sd[p + "weight"].shape, generator=g)
+            out[p + "bias"] = 0.2 * torch.randn(sd[p + "bias"].shape, generator=g)
+            out[p + "running_mean"] = 0.1 * torch.randn(sd[k].shape, generator=g)
+            out[p + "running_var"] = 0.5 + torch.rand(sd[k].shape, generator=g)
+    return out
+
+
+def ir50_forward(sd, x, pr=FP32):
+    """Backbone.forward (model_irse.py:167-172) in eval mode -> embedding [B, 512]."""
+    def prelu(y, a):
+        a = a.view(1, -1, 1, 1)
+        return pr.q(torch.clamp(y, min=0) + a * torch.clamp(y, max=0))
+
+    def bn_prelu(y, p, a):   # BatchNorm (running statistics) + PReLU as one stored pass
+        z = (y - sd[p + "running_mean"].view(1, -1, 1, 1)) / torch.sqrt(sd[p + "running_var"].view(1, -1, 1, 1) + BN_EPS)
+        z = z * sd[p + "weight"].view(1, -1, 1, 1) + sd[p + "bias"].view(1, -1, 1, 1)
+        a = a.view(1, -1, 1, 1)
+        return pr.q(torch.clamp(z, min=0) + a * torch.clamp(z, max=0))
+
+    a = _conv(pr, pr.q(x), sd["input_layer.0.weight"], 1, 1)
+    a = bn_prelu(a, "input_layer.1.", sd["input_layer.2.weight"])
+    for i, (cin, d, stride) in enumerate(ir50_block_specs()):
+        p = "body.%d." % i
+        if cin != d:
+            sc = _conv(pr, a, sd[p + "shortcut_layer.0.weight"], stride, 0)
+            sc = _bn(pr, sd, p + "shortcut_layer.1.", sc, False, False)
+        else:
+            sc = a[:, :, ::stride, ::stride]                       # MaxPool2d(1, stride)
+        r = _bn(pr, sd, p + "res_layer.0.", a, False, False)
+        r = prelu(_conv(pr, r, sd[p + "res_layer.1.weight"], 1, 1), sd[p + "res_layer.2.weight"])
+        r = _conv(pr, r, sd[p + "res_layer.3.weight"], stride, 1)
+        a = _bn(pr, sd, p + "res_layer.4.", r, False, False, res=sc)
+    o = _bn(pr, sd, "output_layer.0.", a, False, False)
+    o = o.reshape(o.shape[0], -1)
+    y = pr.qb(F.linear(pr.qg(o), pr.q(sd["output_layer.3.weight"]), sd["output_layer.3.bias"]))
+    return _bn(pr, sd, "output_layer.4.", y, False, False)

@@ -113,6 +113,21 @@ def test_resnet_mirror_keeps_reference_interface():
         net(torch.zeros(1, 3, 112, 112))
 
 
+def test_ir50_mirror_keeps_reference_interface():
+    from crfr_b200.model.model_irse import IR_50, Backbone
+    from oracle import resnet_oracle as RO
+    torch.manual_seed(91)
+    net = IR_50([112, 112])
+    sd, ref = net.state_dict(), RO.build_ir50_state_dict(91)
+    assert list(sd.keys()) == list(ref.keys()) and all(torch.equal(sd[k], ref[k]) for k in ref)
+    assert len(list(net.named_parameters())) == 187 and len(list(net.named_buffers())) == 3 * 54
+    with pytest.raises(AssertionError):
+        Backbone([96, 96], 50, "ir")                                   # model_irse.py:132
+    net.eval()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        net(torch.zeros(1, 3, 112, 112))
+
+
 def test_product_fails_loudly_without_gpu():
     from crfr_b200.model.FSRnet import OverallNetwork
     from crfr_b200 import ops

@@ -164,3 +164,17 @@ def test_resnet34_kd_oracle_against_reference_fixture(golden_dir):
     np.testing.assert_allclose(nb["bn1.running_mean"].numpy(), g["bn1_running_mean"], rtol=1e-4, atol=1e-6)
     np.testing.assert_allclose(nb["bn1.running_var"].numpy(), g["bn1_running_var"], rtol=1e-4)
     np.testing.assert_allclose(nb["bn_o2.running_var"].numpy(), g["bn_o2_running_var"], rtol=1e-3)
+
+
+def test_ir50_oracle_against_reference_fixture(golden_dir):
+    """oracle ir50_forward (eval mode) against the embedding the reference's own IR_50 produced (make_golden.py)."""
+    from oracle import resnet_oracle as RO
+    g = _load(golden_dir, "ir50.npz")
+    sd0 = RO.build_ir50_state_dict(91)
+    assert list(sd0) == [str(n) for n in g["names"]]
+    np.testing.assert_allclose([v.double().sum().item() for v in sd0.values()], g["checksums"], rtol=0, atol=1e-9)
+    assert len(RO.ir50_block_specs()) == 24
+    sd = RO.randomize_bn_everywhere(sd0, 191)
+    with torch.no_grad():
+        emb = RO.ir50_forward(sd, RO.synthetic_faces(4, seed=4322))
+    assert float(np.linalg.norm(emb.numpy() - g["emb"]) / np.linalg.norm(g["emb"])) < 1e-4

@@ -109,6 +109,29 @@ def test_kd_step_losses_and_gradients(cuda, golden_dir):
                                                             SLACK * abs(c.norm().item() - b.norm().item())), tag
 
 
+def test_ir50_teacher_eval_forward(cuda, golden_dir):
+    """The frozen IR_50 teacher (DISTILLATION/model/model_irse.py, distill_main.py:201) in eval mode."""
+    from crfr_b200.model.model_irse import IR_50
+    from oracle import resnet_oracle as RO
+    torch.manual_seed(91)
+    net = IR_50([112, 112])
+    sd = RO.randomize_bn_everywhere(RO.build_ir50_state_dict(91), 191)
+    net.load_state_dict(sd)
+    net = net.cuda().eval()
+    x = RO.synthetic_faces(4, seed=4322)
+    with torch.no_grad():
+        emb = net(x.cuda())
+        ref = RO.ir50_forward(sd, x)
+        emu = RO.ir50_forward(sd, x, pr=RO.Precision("bf16"))
+    g = np.load(golden_dir + "/ir50.npz")
+    assert rel_err(ref, torch.from_numpy(g["emb"])) < 1e-4                    # oracle == reference fixture
+    assert emb.shape == (4, 512) and torch.isfinite(emb).all()
+    assert rel_err(emb, ref) < SLACK * rel_err(emu, ref) + 1e-2, (rel_err(emb, ref), rel_err(emu, ref))
+    net.train()
+    with pytest.raises(RuntimeError):
+        net(x.cuda())
+
+
 def test_rejects_unsupported(cuda):
     from crfr_b200.model.resnet import ResNet_34
     net = ResNet_34().cuda()
