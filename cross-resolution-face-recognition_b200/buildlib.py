@@ -4,6 +4,7 @@ The library sits next to this file so that it travels with the repo snapshot to 
 gpurun-ignored).  No torch headers are involved: the ABI is plain C (include/crfr.h).
 """
 import concurrent.futures as cf
+import fcntl
 import hashlib
 import os
 import shutil
@@ -27,10 +28,12 @@ def _nvcc():
 
 
 def _digest(paths):
+    """Content hash of the sources keyed by their path RELATIVE to the repo, so that a snapshot of the repo at another
+    absolute location (the GPU box) recognises the library that travelled with it as up to date."""
     h = hashlib.sha256()
     for p in sorted(paths):
         with open(p, "rb") as f:
-            h.update(p.encode() + b"\0" + f.read())
+            h.update(os.path.relpath(p, ROOT).encode() + b"\0" + f.read())
     return h.hexdigest()
 
 
@@ -43,11 +46,26 @@ def build(force=False, verbose=True):
     srcs = sources()
     deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))] + \
         [os.path.join(ROOT, "include", "crfr.h")]
-    stamp = os.path.join(OBJ, "stamp")
+    stamp = LIB + ".stamp"            # next to the library: travels with it (the object directory may not)
     dig = _digest(deps)
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
+
+    def fresh():
+        return os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig
+
+    if not force and fresh():
         return LIB
     os.makedirs(OBJ, exist_ok=True)
+    # one builder at a time (torchrun starts one process per GPU, all of which call build()); the others wait on the
+    # lock and then find a fresh library.  The link goes to a temporary name and is renamed into place atomically, so
+    # a concurrent loader can never map a half-written file.
+    with open(os.path.join(HERE, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and fresh():
+            return LIB
+        return _build_locked(srcs, stamp, dig, verbose)
+
+
+def _build_locked(srcs, stamp, dig, verbose):
     nvcc = _nvcc()
 
     def one(src):
@@ -60,12 +78,15 @@ def build(force=False, verbose=True):
 
     with cf.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(one, srcs))
-    cmd = [nvcc] + ARCH + ["-shared", "-o", LIB] + objs
+    tmp = LIB + ".tmp.%d" % os.getpid()
+    cmd = [nvcc] + ARCH + ["-shared", "-o", tmp] + objs
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
-    with open(stamp, "w") as f:
+    os.replace(tmp, LIB)
+    with open(stamp + ".tmp", "w") as f:
         f.write(dig)
+    os.replace(stamp + ".tmp", stamp)
     if verbose:
         print("built", LIB, file=sys.stderr)
     return LIB
