@@ -135,6 +135,16 @@ stats_finalize_kernel(const float* __restrict__ partial, int chunks, int c, floa
   }
 }
 
+// streaming (evict-first) 16-byte store: the activation is not re-read before ~100 MB of other traffic went by
+__device__ __forceinline__ void st_stream(bf16* p, const bf16x8& v) {
+  const uint4 u = *reinterpret_cast<const uint4*>(&v);
+  asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
+}
+
+// 8 independent 16-byte loads per input in flight per thread and streaming stores: measured 6.0 TB/s against 5.5 TB/s
+// for the 4-deep variant with default stores (2 reads + 1 write, 128 images of 64 x 128 x 128)
+constexpr int kFwdUnroll = 8;
+
 __global__ void __launch_bounds__(kThreads)
 norm_act_fwd_kernel(const bf16* __restrict__ y, int y_ld, const float* __restrict__ stats,
                     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ alpha,
@@ -155,10 +165,10 @@ norm_act_fwd_kernel(const bf16* __restrict__ y, int y_ld, const float* __restric
     al[j] = relu ? 0.f : (alpha ? alpha[ch] : 1.f);
   }
   const long long pix0 = (long long)n * hw;
-  for (int p = p0 + lane; p < p1; p += 4 * lanes) {
-    bf16x8 vy[4], vr[4];
+  for (int p = p0 + lane; p < p1; p += kFwdUnroll * lanes) {
+    bf16x8 vy[kFwdUnroll], vr[kFwdUnroll];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < kFwdUnroll; ++u) {
       const int pp = p + u * lanes;
       if (pp < p1) {
         vy[u] = ld_stream(y + (pix0 + pp) * y_ld + cg * 8);
@@ -166,7 +176,7 @@ norm_act_fwd_kernel(const bf16* __restrict__ y, int y_ld, const float* __restric
       }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < kFwdUnroll; ++u) {
       const int pp = p + u * lanes;
       if (pp < p1) {
         float f[8], r[8];
@@ -178,7 +188,7 @@ norm_act_fwd_kernel(const bf16* __restrict__ y, int y_ld, const float* __restric
           if (res) z += r[j];
           f[j] = z > 0.f ? z : z * al[j];
         }
-        *reinterpret_cast<bf16x8*>(out + (pix0 + pp) * out_ld + cg * 8) = pack8(f);
+        st_stream(out + (pix0 + pp) * out_ld + cg * 8, pack8(f));
       }
     }
   }
