@@ -312,6 +312,16 @@ def bicubic_u8(src, out_h, out_w, want_f32=False):
     return dst, f32
 
 
+def landmark_heatmap(landmarks, h, w, sigma=1.3):
+    """landmarks fp32 [N, K, 2] (x, y) -> heat-map fp32 [N, h, w] (helen_loader.py:118-143, s = 1.3 at :116)."""
+    _need_cuda(landmarks)
+    lm = landmarks.contiguous().float()
+    n, k, _ = lm.shape
+    hm = torch.empty((n, h, w), dtype=torch.float32, device=lm.device)
+    L.call("crfr_landmark_heatmap", ptr(lm), n, k, float(sigma), h, w, ptr(hm), stream())
+    return hm
+
+
 # ---------------------------------------------------------------------------------------------- matcher
 def l2norm_bf16(x):
     _need_cuda(x)

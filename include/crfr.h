@@ -150,6 +150,12 @@ int crfr_bicubic_tables(int in_size, int out_size, int32_t* host_tab);    /* [ou
 int crfr_bicubic_u8(const uint8_t* src, int n, int ih, int iw, int c, const int32_t* tab_h, const int32_t* tab_w,
                     int oh, int ow, uint8_t* tmp, uint8_t* dst, float* dst_f32, void* stream);
 
+/* ref: HelenLoader.generate_hm / gaussian_k helen_loader.py:118-143 - the landmark heat-map target of the prior loss:
+ * hm[n][y][x] = sum_j exp(-((x - lx_j)^2 + (y - ly_j)^2) / (2 sigma^2)), Gaussians in fp64, running sum rounded to fp32
+ * after every landmark (as numpy's in-place += on a float32 array).  landmarks fp32 [n][k][2] = (x, y) in heat-map
+ * pixels (helen_loader.py:104-113: already rotated / scaled by the loader). */
+int crfr_landmark_heatmap(const float* landmarks, int n, int k, float sigma, int h, int w, float* hm, void* stream);
+
 /* ---------------------------------------------------------------- matcher --------------------------------- */
 /* ref: l2_norm DISTILLATION/model/model_irse.py:16-20 ; accuracy()/topk utils/eval.py:6-19 ; threshold decision
  * utils/utils.py:14-24.  rows of x (fp32 [rows][dim]) -> unit-norm bf16. */

@@ -81,3 +81,15 @@ def normalise_to_input(u8_nhwc):
     x = u8_nhwc.astype(np.float32) / np.float32(255.0)
     x = (x - np.float32(0.5)) / np.float32(0.5)
     return np.ascontiguousarray(np.moveaxis(x, -1, -3))
+
+
+def landmark_heatmap(landmarks, height, width, sigma=1.3):
+    """Restatement of HelenLoader.generate_hm / gaussian_k (/root/reference/helen_loader.py:118-143): the sum over the
+    landmarks of exp(-((x - x0)^2 + (y - y0)^2) / (2 sigma^2)), Gaussians in float64, accumulated in place into a
+    float32 map (i.e. rounded to float32 after every landmark).  landmarks: [K, 2] (x, y).  TEST INFRASTRUCTURE ONLY."""
+    x = np.arange(0, width, 1, float)
+    y = np.arange(0, height, 1, float)[:, np.newaxis]
+    hm = np.zeros((height, width), dtype=np.float32)
+    for x0, y0 in np.asarray(landmarks, dtype=np.float64):
+        hm += np.exp(-((x - x0) ** 2 + (y - y0) ** 2) / (2 * sigma ** 2))
+    return hm

@@ -206,6 +206,28 @@ def golden_resnet():
     print("resnet34 kd", l_s.item(), l_a.item())
 
 
+def golden_heatmap():
+    """Landmark heat-map target: HelenLoader.generate_hm (helen_loader.py:118-143) called on the reference's own class
+    (matplotlib / scipy.misc, which the module imports but this method does not use, are stubbed)."""
+    import types
+    for name in ("matplotlib", "matplotlib.pyplot", "scipy.misc"):
+        if name not in sys.modules:
+            try:
+                __import__(name)
+            except Exception:
+                sys.modules[name] = types.ModuleType(name)
+    HL = R.load("helen_loader.py")
+    rng = np.random.RandomState(5)
+    lm = (rng.rand(3, 97, 2) * 36.0 - 2.0).astype(np.float32)      # some landmarks fall outside the 32x32 map
+    loader = HL.HelenLoader.__new__(HL.HelenLoader)
+    ref = np.stack([HL.HelenLoader.generate_hm(loader, height=32, width=32, landmark=[p for p in l.astype(np.float64)], s=1.3)
+                    for l in lm])
+    ora = np.stack([BO.landmark_heatmap(l, 32, 32, 1.3) for l in lm])
+    assert ref.dtype == np.float32 and np.array_equal(ref, ora), np.abs(ref - ora).max()
+    np.savez_compressed(os.path.join(OUT, "heatmap.npz"), landmarks=lm, hm=ref)
+    print("heatmap ok", float(ref.max()))
+
+
 def golden_ir50():
     """IR_50 teacher (DISTILLATION/model/model_irse.py) in eval mode on the reference's own module."""
     IR = R.load("DISTILLATION/model/model_irse.py")
@@ -232,6 +254,6 @@ def golden_ir50():
 if __name__ == "__main__":
     assert R.available(), "reference tree not present"
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["losses", "bicubic", "eval", "fsrnet", "resnet", "ir50"]
+    which = sys.argv[1:] or ["losses", "bicubic", "eval", "fsrnet", "resnet", "ir50", "heatmap"]
     for w in which:
         globals()["golden_" + w]()

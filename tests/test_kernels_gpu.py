@@ -1,6 +1,8 @@
 """Per-kernel parity on the GPU: every C-ABI family against a plain fp32 PyTorch (CPU) statement of the same op on
 identical bf16-representable inputs.  Tolerances: outputs stored as bf16 carry one rounding (2^-9 relative per
 element) -> norm-wise 5e-3; fp32 results (weight gradients, losses) -> 1e-4 (north_star tolerance)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -298,6 +300,19 @@ def test_bicubic_bit_exact(cuda, golden_dir):
     src = rng.integers(0, 256, (128, 16, 16, 3), dtype=np.uint8)
     got, _ = ops.bicubic_u8(torch.from_numpy(src).cuda(), 128, 128)
     assert np.array_equal(got.cpu().numpy(), BO.bicubic_u8(src, 128, 128))
+
+
+def test_landmark_heatmap(cuda, golden_dir):
+    """Device-side landmark heat-map target (helen_loader.py:118-143) against the reference's own generate_hm."""
+    ops = _ops()
+    g = np.load(os.path.join(golden_dir, "heatmap.npz"))
+    hm = ops.landmark_heatmap(torch.from_numpy(g["landmarks"]).cuda(), 32, 32, 1.3).cpu().numpy()
+    np.testing.assert_allclose(hm, g["hm"], rtol=1e-6, atol=1e-7)    # fp64 exp: last-ulp libm differences only
+    from oracle import bicubic_oracle as BO
+    lm = torch.rand(5, 97, 2) * 32
+    got = ops.landmark_heatmap(lm.cuda(), 32, 32).cpu().numpy()
+    want = np.stack([BO.landmark_heatmap(l.numpy(), 32, 32) for l in lm])
+    np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-7)
 
 
 def test_eval_dropins(cuda, golden_dir):

@@ -178,3 +178,9 @@ def test_ir50_oracle_against_reference_fixture(golden_dir):
     with torch.no_grad():
         emb = RO.ir50_forward(sd, RO.synthetic_faces(4, seed=4322))
     assert float(np.linalg.norm(emb.numpy() - g["emb"]) / np.linalg.norm(g["emb"])) < 1e-4
+
+
+def test_landmark_heatmap_oracle_against_reference_fixture(golden_dir):
+    g = _load(golden_dir, "heatmap.npz")
+    for l, ref in zip(g["landmarks"], g["hm"]):
+        assert np.array_equal(BO.landmark_heatmap(l, 32, 32, 1.3), ref)
