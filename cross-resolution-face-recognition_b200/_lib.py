@@ -70,6 +70,7 @@ SIGNATURES = {
     "crfr_topk_merge": (ci, [vp, vp, ci, ci, ci, vp, vp, vp]),
     "crfr_topk_rows": (ci, [vp, ci, cll, ci, vp, vp, vp]),
     "crfr_verify_counts": (ci, [vp, vp, cll, cf, vp, vp]),
+    "crfr_verify_sweep": (ci, [vp, vp, vp, ci, vp, ci, vp, vp]),
     "crfr_pair_verify": (ci, [vp, vp, cll, ci, cf, vp, vp, vp]),
     "crfr_fsrnet_workspace_bytes": (csz, [ci, ci, ci]),
     "crfr_fsrnet_forward": (ci, [ci, vp, C.POINTER(FsrnetIO), ci, vp, csz, vp]),

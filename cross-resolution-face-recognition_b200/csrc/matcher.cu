@@ -360,6 +360,35 @@ __global__ void verify_counts_kernel(const float* __restrict__ dist, const uint8
   }
 }
 
+// Threshold sweep of the verification protocol: counts[t][0..3] = tp, fp, tn, fn of (dist < thr[t]) vs issame, restricted
+// to the pairs listed in `subset` (a K-fold train or test split; NULL = all pairs).  One thread per threshold; the pair
+// data is staged through shared memory in tiles so that every block streams it once.
+__global__ void __launch_bounds__(256)
+verify_sweep_kernel(const float* __restrict__ dist, const uint8_t* __restrict__ issame, const int* __restrict__ subset,
+                    int n, const float* __restrict__ thr, int nthr, unsigned int* __restrict__ counts) {
+  __shared__ float sd[1024];
+  __shared__ uint8_t ss[1024];
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const float th = t < nthr ? thr[t] : 0.f;
+  unsigned int c[4] = {0u, 0u, 0u, 0u};
+  for (int base = 0; base < n; base += 1024) {
+    const int m = min(1024, n - base);
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+      const int src = subset ? subset[base + i] : base + i;
+      sd[i] = dist[src];
+      ss[i] = issame[src];
+    }
+    __syncthreads();
+    for (int i = 0; i < m; ++i) {
+      const bool pred = sd[i] < th, same = ss[i] != 0;
+      c[pred ? (same ? 0 : 1) : (same ? 3 : 2)]++;
+    }
+    __syncthreads();
+  }
+  if (t < nthr)
+    for (int j = 0; j < 4; ++j) counts[4 * t + j] = c[j];
+}
+
 struct SplitPlan {
   int tiles, nblocks, splits, blocks_per_split;
 };
@@ -449,6 +478,16 @@ extern "C" int crfr_verify_counts(const float* dist, const uint8_t* issame, long
   long long blocks = (n + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   verify_counts_kernel<<<(unsigned)blocks, 256, 0, st>>>(dist, issame, n, thr, counts);
+  CRFR_COUNT_LAUNCH();
+  CRFR_LAUNCH_CHECK();
+  return CRFR_OK;
+}
+
+extern "C" int crfr_verify_sweep(const float* dist, const uint8_t* issame, const int* subset, int n,
+                                 const float* thresholds, int nthr, unsigned int* counts, void* stream) {
+  CRFR_CHECK_ARG(dist && issame && thresholds && counts && n > 0 && nthr > 0, "verify_sweep: bad argument");
+  verify_sweep_kernel<<<crfr_cdiv(nthr, 256), 256, 0, (cudaStream_t)stream>>>(dist, issame, subset, n, thresholds, nthr,
+                                                                              counts);
   CRFR_COUNT_LAUNCH();
   CRFR_LAUNCH_CHECK();
   return CRFR_OK;

@@ -376,6 +376,20 @@ def topk_rows(scores, k):
     return val, idx
 
 
+def verify_sweep(dist, issame, thresholds, subset=None):
+    """(tp, fp, tn, fn) of ``dist < t`` for every threshold t over the pairs in ``subset`` (int32 indices; None = all):
+    int32 tensor [T, 4] on the device, one launch for the whole sweep (utils/utils.py:70-82)."""
+    _need_cuda(dist, issame, thresholds, subset)
+    d = dist.contiguous().float()
+    s = issame.contiguous().to(torch.uint8)
+    t = thresholds.contiguous().float()
+    sub = None if subset is None else subset.contiguous().to(torch.int32)
+    n = d.numel() if sub is None else sub.numel()
+    counts = torch.empty((t.numel(), 4), dtype=torch.int32, device=d.device)
+    L.call("crfr_verify_sweep", ptr(d), ptr(s), ptr(sub), n, ptr(t), t.numel(), ptr(counts), stream())
+    return counts
+
+
 def verify_counts(dist, issame, thr):
     """(tp, fp, tn, fn) of ``dist < thr`` against ``issame`` as a device int64 tensor of 4."""
     _need_cuda(dist, issame)

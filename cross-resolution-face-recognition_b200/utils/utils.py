@@ -24,10 +24,12 @@ def calculate_accuracy(threshold, dist, actual_issame):
 
 def calculate_roc(thresholds, embeddings1, embeddings2, actual_issame, nrof_folds=10, seed=0):
     """ref: utils/utils.py:26-87 with the K-fold shuffle seeded (the reference's is not) and the dead margin_list
-    work dropped.  Pair distances and every threshold count run on the GPU."""
+    work dropped.  Pair distances run on the GPU and every fold costs two launches: one threshold sweep over its
+    training pairs, one over its test pairs (crfr_verify_sweep); thresholds are compared in fp32."""
     e1 = torch.as_tensor(embeddings1).float().cuda()
     e2 = torch.as_tensor(embeddings2).float().cuda()
     same = torch.as_tensor(np.asarray(actual_issame)).cuda()
+    thr = torch.as_tensor(np.asarray(thresholds, dtype=np.float32)).cuda()
     dist, _ = ops.pair_verify(e1, e2, 0.0)
     n = dist.numel()
     idx = np.arange(n)
@@ -37,17 +39,24 @@ def calculate_roc(thresholds, embeddings1, embeddings2, actual_issame, nrof_fold
     nt = len(thresholds)
     tprs = np.zeros((nrof_folds, nt)); fprs = np.zeros((nrof_folds, nt))
     accuracy = np.zeros(nrof_folds); best = np.zeros(nrof_folds)
+
+    def rates(counts):
+        tp, fp, tn, fn = (counts[:, j].astype(np.float64) for j in range(4))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            tpr = np.where(tp + fn == 0, 0.0, tp / (tp + fn))
+            fpr = np.where(fp + tn == 0, 0.0, fp / (fp + tn))
+        return tpr, fpr, (tp + tn) / (tp + fp + tn + fn)
+
     cur = 0
     for f, sz in enumerate(sizes):
         test = np.sort(idx[cur:cur + sz]); cur += sz
         mask = np.ones(n, bool); mask[test] = False
-        tr = torch.from_numpy(np.nonzero(mask)[0]).cuda(); te = torch.from_numpy(test).cuda()
-        d_tr, s_tr, d_te, s_te = dist[tr], same[tr], dist[te], same[te]
-        acc_train = np.array([calculate_accuracy(t, d_tr, s_tr)[2] for t in thresholds])
+        tr = torch.from_numpy(np.nonzero(mask)[0].astype(np.int32)).cuda()
+        te = torch.from_numpy(test.astype(np.int32)).cuda()
+        _, _, acc_train = rates(ops.verify_sweep(dist, same, thr, tr).cpu().numpy())
+        tprs[f], fprs[f], acc_test = rates(ops.verify_sweep(dist, same, thr, te).cpu().numpy())
         bi = int(np.argmax(acc_train)); best[f] = thresholds[bi]
-        for ti, t in enumerate(thresholds):
-            tprs[f, ti], fprs[f, ti], _ = calculate_accuracy(t, d_te, s_te)
-        accuracy[f] = calculate_accuracy(thresholds[bi], d_te, s_te)[2]
+        accuracy[f] = acc_test[bi]
     return tprs.mean(0), fprs.mean(0), accuracy.mean(), best
 
 

@@ -174,6 +174,10 @@ int crfr_topk_rows(const float* scores, int p, long long g, int k, float* out_va
 /* ref: calculate_accuracy utils/utils.py:14-24: counts[4] = tp, fp, tn, fn of (dist < thr) vs issame (u8) */
 int crfr_verify_counts(const float* dist, const uint8_t* issame, long long n, float thr, unsigned long long* counts,
                        void* stream);
+/* ref: the threshold sweeps of calculate_roc utils/utils.py:70-82: counts[t][4] = tp, fp, tn, fn of (dist < thresholds[t])
+ * over the pairs listed in subset[n] (indices into dist / issame; NULL = the first n pairs).  fp32 thresholds. */
+int crfr_verify_sweep(const float* dist, const uint8_t* issame, const int* subset, int n, const float* thresholds,
+                      int nthr, unsigned int* counts, void* stream);
 /* verification: same[i] = (sum((e1-e2)^2) < thr) for fp32 pairs; also writes dist */
 int crfr_pair_verify(const float* e1, const float* e2, long long pairs, int dim, float thr, float* dist,
                      uint8_t* same, void* stream);

@@ -338,3 +338,22 @@ def test_eval_dropins(cuda, golden_dir):
     tpr, fpr, acc, best = calculate_roc(gd["thr"], gd["e1"], gd["e2"], gd["same"], nrof_folds=10, seed=0)
     o = EO.calculate_roc(gd["thr"], gd["e1"], gd["e2"], gd["same"], nrof_folds=10, seed=0)
     assert np.allclose(tpr, o[0]) and np.allclose(fpr, o[1]) and abs(acc - o[2]) < 1e-12 and np.array_equal(best, o[3])
+
+
+def test_verify_sweep_4000_thresholds(cuda):
+    """The threshold sweep of the verification protocol (utils/utils.py:70-82; distill_main.test sweeps 4000 thresholds)
+    as one launch per fold: bit-exact counts against numpy, with and without a K-fold subset."""
+    ops = _ops()
+    rng = np.random.RandomState(3)
+    n = 6000
+    dist = (rng.rand(n) * 4).astype(np.float32)
+    same = rng.rand(n) < 0.5
+    thr = np.arange(0, 4, 0.001).astype(np.float32)
+    sub = np.sort(rng.permutation(n)[:5400]).astype(np.int32)
+    d, s, t = torch.from_numpy(dist).cuda(), torch.from_numpy(same).cuda(), torch.from_numpy(thr).cuda()
+    for subset in (None, sub):
+        got = ops.verify_sweep(d, s, t, None if subset is None else torch.from_numpy(subset).cuda()).cpu().numpy()
+        dd, ss = (dist, same) if subset is None else (dist[subset], same[subset])
+        pred = dd[None, :] < thr[:, None]
+        want = np.stack([(pred & ss).sum(1), (pred & ~ss).sum(1), (~pred & ~ss).sum(1), (~pred & ss).sum(1)], 1)
+        assert np.array_equal(got, want)
