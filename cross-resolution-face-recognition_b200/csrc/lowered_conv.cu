@@ -44,19 +44,27 @@ __global__ void im2col_small_kernel(const bf16* __restrict__ x, int h, int w, in
   const int n = row / oh, oy = row - n * oh;
   uint32_t out[4] = {0u, 0u, 0u, 0u};
   if (k0 < kmax) {
-    const int t0 = k0 / 3, t1 = min((k0 + 7) / 3, KS * KS - 1);
-    for (int tap = t0; tap <= t1; ++tap) {
+    // the 8 values of this group come from taps t0 .. t0+3: fetch those (up to) four pixels, then pick per value with
+    // selects - every array below is indexed statically, so nothing is demoted to local memory
+    const int t0 = k0 / 3;
+    uint2 pv[4];
+#pragma unroll
+    for (int ti = 0; ti < 4; ++ti) {
+      const int tap = t0 + ti;
       const int ky = tap / KS, kx = tap - ky * KS;
       const int y = oy * stride + sign * (ky - pad), xx = ox * stride + sign * (kx - pad);
-      uint2 v = make_uint2(0u, 0u);
-      if (y >= 0 && y < h && xx >= 0 && xx < w)
-        v = *reinterpret_cast<const uint2*>(x + (((long long)n * h + y) * w + xx) * 4);
-      const uint32_t ch[3] = {v.x & 0xffffu, v.x >> 16, v.y & 0xffffu};
+      pv[ti] = make_uint2(0u, 0u);
+      if (tap < KS * KS && y >= 0 && y < h && xx >= 0 && xx < w)
+        pv[ti] = *reinterpret_cast<const uint2*>(x + (((long long)n * h + y) * w + xx) * 4);
+    }
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const int j = tap * 3 + c - k0;
-        if (j >= 0 && j < 8) out[j >> 1] |= ch[c] << ((j & 1) * 16);
-      }
+    for (int j = 0; j < 8; ++j) {
+      const int k = k0 + j;
+      const int tap = k / 3, c = k - tap * 3, ti = tap - t0;
+      const uint2 v = ti == 0 ? pv[0] : (ti == 1 ? pv[1] : (ti == 2 ? pv[2] : pv[3]));
+      uint32_t val = c == 0 ? (v.x & 0xffffu) : (c == 1 ? (v.x >> 16) : (v.y & 0xffffu));
+      if (k >= kmax) val = 0u;
+      out[j >> 1] |= val << ((j & 1) * 16);
     }
   }
   *reinterpret_cast<uint4*>(P + ((long long)row * ow + ox) * kpad + g * 8) = make_uint4(out[0], out[1], out[2], out[3]);
@@ -66,7 +74,12 @@ __global__ void im2col_small_kernel(const bf16* __restrict__ x, int h, int w, in
 int launch_im2col_small(const bf16* x, int n, int h, int w, int oh, int ow, int ks, int stride, int pad, int sign, bf16* P,
                         int kpad, cudaStream_t st) {
   const int rows = n * oh;
-  const dim3 grid((unsigned)crfr_cdiv((long long)ow * (kpad >> 3), 256), (unsigned)(rows < 65535 ? rows : 65535));
+  // a block per (row slice) would be 65 k one-store blocks at 128x128: block launch rate, not bandwidth, bounds that.
+  // ~16 blocks per SM, each walking rows with the grid stride
+  const unsigned gx = (unsigned)crfr_cdiv((long long)ow * (kpad >> 3), 256);
+  unsigned gy = (148u * 16u + gx - 1) / gx;
+  if (gy > (unsigned)rows) gy = (unsigned)rows;
+  const dim3 grid(gx, gy);
   if (ks == 3) im2col_small_kernel<3><<<grid, 256, 0, st>>>(x, h, w, oh, ow, stride, pad, sign, P, kpad, rows);
   else if (ks == 7) im2col_small_kernel<7><<<grid, 256, 0, st>>>(x, h, w, oh, ow, stride, pad, sign, P, kpad, rows);
   else {
