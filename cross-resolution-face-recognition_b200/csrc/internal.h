@@ -5,6 +5,12 @@
 
 #include "crfr.h"
 
+// tmap.cu: bf16 / SWIZZLE_128B / zero-fill tensor map of rank <= 5; strides_bytes has rank-1 entries (dimension 0 is
+// contiguous).  CUtensorMap comes from <cuda.h> (included by every caller through sm100.cuh / cudaTypedefs.h).
+struct CUtensorMap_st;
+int crfr_tmap_encode_bf16(CUtensorMap_st* m, const void* ptr, int rank, const unsigned long long* dims,
+                          const unsigned long long* strides_bytes, const unsigned int* box, const char* what);
+
 // norm_act.cu
 size_t crfr_norm_ws_bytes(int n, int hw, int c);
 int crfr_norm_finalize(const float* partial, int n, int chunks, int hw, int c, float eps, float* stats,

@@ -18,6 +18,7 @@
 
 #include "common.cuh"
 #include "crfr.h"
+#include "internal.h"
 #include "sm100.cuh"
 
 using namespace sm100;
@@ -31,34 +32,11 @@ constexpr int kTile = 128 * 128;  // 16 KB: 128 rows x 64 bf16 (probe tile per K
 constexpr int kGBlock = 256;      // gallery rows per MMA (N)
 constexpr int kBTile = kGBlock * 128;  // 32 KB: 256 rows x 64 bf16
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
 int make_rows_map(CUtensorMap* m, const void* ptr, long long rows, int dim, int box_rows) {
-  static EncodeTiledFn enc = nullptr;
-  if (!enc) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
-        q != cudaDriverEntryPointSuccess) {
-      crfr_set_error("cuTensorMapEncodeTiled entry point not available");
-      return CRFR_ECUDA;
-    }
-    enc = (EncodeTiledFn)p;
-  }
-  cuuint64_t dims[2] = {(cuuint64_t)dim, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)dim * 2};
-  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
-  cuuint32_t es[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    crfr_set_error("cuTensorMapEncodeTiled(rows=%lld dim=%d) failed: %d", rows, dim, (int)r);
-    return CRFR_ECUDA;
-  }
-  return CRFR_OK;
+  const unsigned long long dims[2] = {(unsigned long long)dim, (unsigned long long)rows};
+  const unsigned long long strides[1] = {(unsigned long long)dim * 2};
+  const unsigned int box[2] = {64, (unsigned int)box_rows};
+  return crfr_tmap_encode_bf16(m, ptr, 2, dims, strides, box, "embedding rows");
 }
 
 struct TopK {

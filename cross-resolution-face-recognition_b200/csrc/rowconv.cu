@@ -51,22 +51,6 @@ constexpr int kAccSlots = 8;               // TMEM ring: 8 x 64 columns = all 51
 constexpr int kSmemBytes = kWeightBytes + kSlots * kSlotBytes + 2 * kStageOutBytes + 4 * 128 * 4 /*stats*/ +
                            kC * 4 /*bias*/ + 1024 /*align*/ + 512 /*barriers*/;
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
-        q != cudaDriverEntryPointSuccess)
-      return nullptr;
-    fn = (EncodeTiledFn)p;
-  }
-  return fn;
-}
-
 struct RowParams {
   int n, h;              // images, rows per image (width is kW)
   int total_rows;        // n * h
@@ -313,22 +297,9 @@ rowconv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   }
 }
 
-int encode(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
-           const cuuint32_t* box, const char* what) {
-  EncodeTiledFn enc = get_encode();
-  if (!enc) {
-    crfr_set_error("cuTensorMapEncodeTiled entry point not available");
-    return CRFR_ECUDA;
-  }
-  cuuint32_t es[4] = {1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), dims, strides, box, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    crfr_set_error("rowconv: cuTensorMapEncodeTiled(%s) failed: %d", what, (int)r);
-    return CRFR_ECUDA;
-  }
-  return CRFR_OK;
+int encode(CUtensorMap* m, const void* ptr, int rank, const unsigned long long* dims, const unsigned long long* strides,
+           const unsigned int* box, const char* what) {
+  return crfr_tmap_encode_bf16(m, ptr, rank, dims, strides, box, what);
 }
 
 int sm_count() {
@@ -370,21 +341,21 @@ int crfr_rowconv(const void* src, int src_ld, int n, int h, const void* w_packed
                  "rowconv: pointers must be 16B aligned and ld a multiple of 8");
   CUtensorMap tmX, tmW, tmY;
   {
-    cuuint64_t dims[4] = {(cuuint64_t)kC, (cuuint64_t)kW, (cuuint64_t)h, (cuuint64_t)n};
-    cuuint64_t strides[3] = {(cuuint64_t)dst_ld * 2, (cuuint64_t)kW * dst_ld * 2, (cuuint64_t)h * kW * dst_ld * 2};
-    cuuint32_t box[4] = {64, 128, 1, 1};
+    unsigned long long dims[4] = {(unsigned long long)kC, (unsigned long long)kW, (unsigned long long)h, (unsigned long long)n};
+    unsigned long long strides[3] = {(unsigned long long)dst_ld * 2, (unsigned long long)kW * dst_ld * 2, (unsigned long long)h * kW * dst_ld * 2};
+    unsigned int box[4] = {64, 128, 1, 1};
     CRFR_TRY(encode(&tmY, dst, 4, dims, strides, box, "output"));
   }
   {
-    cuuint64_t dims[4] = {(cuuint64_t)kC, (cuuint64_t)kW, (cuuint64_t)h, (cuuint64_t)n};
-    cuuint64_t strides[3] = {(cuuint64_t)src_ld * 2, (cuuint64_t)kW * src_ld * 2, (cuuint64_t)h * kW * src_ld * 2};
-    cuuint32_t box[4] = {64, 130, 1, 1};
+    unsigned long long dims[4] = {(unsigned long long)kC, (unsigned long long)kW, (unsigned long long)h, (unsigned long long)n};
+    unsigned long long strides[3] = {(unsigned long long)src_ld * 2, (unsigned long long)kW * src_ld * 2, (unsigned long long)h * kW * src_ld * 2};
+    unsigned int box[4] = {64, 130, 1, 1};
     CRFR_TRY(encode(&tmX, src, 4, dims, strides, box, "activation"));
   }
   {
-    cuuint64_t dims[2] = {64, 9 * 64};
-    cuuint64_t strides[1] = {128};
-    cuuint32_t box[2] = {64, 64};
+    unsigned long long dims[2] = {64, 9 * 64};
+    unsigned long long strides[1] = {128};
+    unsigned int box[2] = {64, 64};
     CRFR_TRY(encode(&tmW, w_packed, 2, dims, strides, box, "weights"));
   }
   static bool attr_done = false;

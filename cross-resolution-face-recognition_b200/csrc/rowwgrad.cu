@@ -39,22 +39,6 @@ constexpr int kThreads = 192;
 constexpr int kSlabFloats = 9 * kC * kC;
 constexpr int kSmemBytes = kXSlots * kXSlotBytes + kDySlots * kDyRowBytes + 1024 + 512;
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
-        q != cudaDriverEntryPointSuccess)
-      return nullptr;
-    fn = (EncodeTiledFn)p;
-  }
-  return fn;
-}
-
 struct WgParams {
   int n, h, total_rows;
   float* slabs;   // [gridDim.x][9][64][64]
@@ -243,23 +227,12 @@ slab_reduce_kernel(const float* __restrict__ slabs, int nslabs, float* __restric
 }
 
 int encode(CUtensorMap* m, const void* ptr, int n, int h, int ld, int box_w, const char* what) {
-  EncodeTiledFn enc = get_encode();
-  if (!enc) {
-    crfr_set_error("cuTensorMapEncodeTiled entry point not available");
-    return CRFR_ECUDA;
-  }
-  cuuint64_t dims[4] = {(cuuint64_t)kC, (cuuint64_t)kW, (cuuint64_t)h, (cuuint64_t)n};
-  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)kW * ld * 2, (cuuint64_t)h * kW * ld * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)box_w, 1, 1};
-  cuuint32_t es[4] = {1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    crfr_set_error("rowwgrad: cuTensorMapEncodeTiled(%s) failed: %d", what, (int)r);
-    return CRFR_ECUDA;
-  }
-  return CRFR_OK;
+  const unsigned long long dims[4] = {(unsigned long long)kC, (unsigned long long)kW, (unsigned long long)h,
+                                      (unsigned long long)n};
+  const unsigned long long strides[3] = {(unsigned long long)ld * 2, (unsigned long long)kW * ld * 2,
+                                         (unsigned long long)h * kW * ld * 2};
+  const unsigned int box[4] = {64, (unsigned int)box_w, 1, 1};
+  return crfr_tmap_encode_bf16(m, ptr, 4, dims, strides, box, what);
 }
 
 int grid_for(int total_rows) {

@@ -27,66 +27,24 @@ using namespace sm100;
 namespace {
 
 // ------------------------------------------------------------------------------------------------
-// host: tensor-map encoding through the driver entry point (no link-time dependency on libcuda)
+// host: tensor maps (tmap.cu)
 // ------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
-        q != cudaDriverEntryPointSuccess)
-      return nullptr;
-    fn = (EncodeTiledFn)p;
-  }
-  return fn;
-}
-
 // NHWC bf16 activation view [n][h][w][c] with per-pixel stride ld; box = (64, bw, bh, bn), SWIZZLE_128B
 int make_act_map(CUtensorMap* m, const void* ptr, int n, int h, int w, int c, int ld, int bw, int bh, int bn) {
-  EncodeTiledFn enc = get_encode();
-  if (!enc) {
-    crfr_set_error("cuTensorMapEncodeTiled entry point not available");
-    return CRFR_ECUDA;
-  }
-  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
-  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)w * ld * 2, (cuuint64_t)h * w * ld * 2};
-  cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
-  cuuint32_t es[4] = {1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    crfr_set_error("cuTensorMapEncodeTiled(activation n=%d h=%d w=%d c=%d ld=%d box=%dx%dx%d) failed: %d", n, h, w, c,
-                   ld, bw, bh, bn, (int)r);
-    return CRFR_ECUDA;
-  }
-  return CRFR_OK;
+  const unsigned long long dims[4] = {(unsigned long long)c, (unsigned long long)w, (unsigned long long)h,
+                                      (unsigned long long)n};
+  const unsigned long long strides[3] = {(unsigned long long)ld * 2, (unsigned long long)w * ld * 2,
+                                         (unsigned long long)h * w * ld * 2};
+  const unsigned int box[4] = {64, (unsigned int)bw, (unsigned int)bh, (unsigned int)bn};
+  return crfr_tmap_encode_bf16(m, ptr, 4, dims, strides, box, "activation");
 }
 
 // packed weights [rows][kdim] bf16 (kdim contiguous); box = (64, box_rows)
 int make_weight_map(CUtensorMap* m, const void* ptr, long long rows, int kdim, int box_rows) {
-  EncodeTiledFn enc = get_encode();
-  if (!enc) {
-    crfr_set_error("cuTensorMapEncodeTiled entry point not available");
-    return CRFR_ECUDA;
-  }
-  cuuint64_t dims[2] = {(cuuint64_t)kdim, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)kdim * 2};
-  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
-  cuuint32_t es[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    crfr_set_error("cuTensorMapEncodeTiled(weights rows=%lld k=%d) failed: %d", rows, kdim, (int)r);
-    return CRFR_ECUDA;
-  }
-  return CRFR_OK;
+  const unsigned long long dims[2] = {(unsigned long long)kdim, (unsigned long long)rows};
+  const unsigned long long strides[1] = {(unsigned long long)kdim * 2};
+  const unsigned int box[2] = {64, (unsigned int)box_rows};
+  return crfr_tmap_encode_bf16(m, ptr, 2, dims, strides, box, "weights");
 }
 
 struct Tiling {

@@ -104,7 +104,7 @@ def golden_bicubic():
     import PIL
     rng = np.random.default_rng(20261018)
     d = {"pillow_version": np.array(PIL.__version__)}
-    for s, o, n in ((16, 128, 4), (28, 224, 2), (16, 64, 1), (20, 50, 1)):
+    for s, o, n in ((16, 128, 4), (28, 224, 2), (16, 64, 1), (20, 50, 1), (128, 16, 2), (112, 28, 1), (50, 20, 1)):
         src = rng.integers(0, 256, (n, s, s, 3), dtype=np.uint8)
         src[0, :, : s // 2] = 255 * (np.arange(s)[:, None, None] % 2)       # hard edges: exercises the clip
         dst = np.stack([np.asarray(Image.fromarray(a).resize((o, o), Image.BICUBIC)) for a in src])
