@@ -144,16 +144,11 @@ def time_kd_step(torch, batch=256, reps=3):
     x = torch.randn(batch, 3, 112, 112, device="cuda")
     mse, kd = MSELoss(), ResidualKDLoss()
 
-    def step():
-        with torch.no_grad():
-            t = teacher(x)
-        s, a = student(x), assistant(x)
-        l_s = mse(s[0], t[0])
-        l_a = sum(kd(t[k], s[k], a[k]) for k in (1, 2, 3, 4)) + kd(t[0], s[0], a[0])
-        for n in (student, assistant):
-            n.zero_grad(set_to_none=True)
-        (l_s + l_a).backward()
-        return l_s, l_a
+    from crfr_b200.model.resnet import kd_train_step
+
+    def step():   # one native call: crfr_kd_train_step (the module + autograd composition gives the same gradients)
+        losses = kd_train_step(teacher, student, assistant, x)
+        return losses[0], losses[1]
     for _ in range(2):                   # warm-up: kernel attributes, allocator pools for the 9 GB workspaces
         step()
     torch.cuda.synchronize()

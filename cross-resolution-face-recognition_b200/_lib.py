@@ -29,6 +29,10 @@ class ResnetIO(C.Structure):
                 ("momentum", cf), ("eps", cf)]
 
 
+class KdIO(C.Structure):
+    _fields_ = [("batch", ci), ("size", ci), ("x", vp), ("momentum", cf), ("eps", cf), ("assistant_grad_to_student", ci)]
+
+
 RESNET34_NPARAMS, RESNET34_NBN = 114, 38
 IR50_NPARAMS, IR50_NBN = 187, 54
 
@@ -80,6 +84,8 @@ SIGNATURES = {
     "crfr_bn_running_to_stats": (ci, [vp, vp, ci, cf, vp, vp]),
     "crfr_resnet34_workspace_bytes": (csz, [ci, ci, ci]),
     "crfr_resnet34_forward": (ci, [ci, vp, vp, C.POINTER(ResnetIO), vp, csz, vp]),
+    "crfr_kd_workspace_bytes": (csz, [ci, ci]),
+    "crfr_kd_train_step": (ci, [ci, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(KdIO), vp, vp, csz, vp]),
     "crfr_ir50_workspace_bytes": (csz, [ci, ci]),
     "crfr_ir50_forward": (ci, [ci, vp, vp, C.POINTER(ResnetIO), vp, csz, vp]),
     "crfr_resnet34_backward": (ci, [ci, vp, vp, C.POINTER(ResnetIO), vp, vp, vp, csz, vp]),

@@ -506,6 +506,110 @@ extern "C" int crfr_resnet34_forward(int engine, const float* const* host_params
   return net.err;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Residual knowledge-distillation step (distill_main.py:59-74, evaluated on one forward: SURVEY.md 8c-iii):
+// teacher forward (eval), student + assistant forward (train), the six MSE terms on the NHWC bf16 features as they
+// sit in the workspace (no fp32 NCHW round trip), and both backward passes - one native call.
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void kd_total_kernel(const float* __restrict__ parts, float* __restrict__ losses) {
+  losses[0] = parts[0];
+  losses[1] = ((parts[1] + parts[2]) + (parts[3] + parts[4])) + parts[5];
+}
+
+struct KdLayout {
+  size_t teacher, train, scratch, total;
+};
+KdLayout kd_layout(int batch, int size) {
+  KdLayout l;
+  l.teacher = (crfr_resnet34_workspace_bytes(batch, size, 0) + 4095) & ~(size_t)4095;
+  // + room for the second embedding-gradient slot of the student (L_s and L_a both reach s_emb)
+  l.train = (crfr_resnet34_workspace_bytes(batch, size, 1) + (size_t)batch * kEmb * 2 + (4u << 20)) & ~(size_t)4095;
+  l.scratch = 1 << 20;
+  l.total = l.teacher + 2 * l.train + l.scratch;
+  return l;
+}
+
+}  // namespace
+
+extern "C" size_t crfr_kd_workspace_bytes(int batch, int size) {
+  if (batch <= 0 || size != 112) return 0;
+  return kd_layout(batch, size).total;
+}
+
+extern "C" int crfr_kd_train_step(int engine, const float* const* teacher_params, void* const* teacher_buffers,
+                                  const float* const* student_params, void* const* student_buffers,
+                                  float* const* student_grads, const float* const* assistant_params,
+                                  void* const* assistant_buffers, float* const* assistant_grads, const crfr_kd_io* kio,
+                                  float* losses, void* ws, size_t ws_bytes, void* stream) {
+  CRFR_CHECK_ARG(kio && kio->batch > 0 && kio->size == 112 && kio->x, "kd_train_step: batch/size/x invalid");
+  CRFR_CHECK_ARG(teacher_params && teacher_buffers && student_params && student_grads && assistant_params &&
+                     assistant_grads && losses && ws,
+                 "kd_train_step: null pointer");
+  const KdLayout lay = kd_layout(kio->batch, kio->size);
+  if (ws_bytes < lay.total) {
+    crfr_set_error("kd_train_step: workspace %zu < %zu", ws_bytes, lay.total);
+    return CRFR_EWORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* base = (uint8_t*)ws;
+  crfr_resnet_io io_eval = {}, io_train = {};
+  io_eval.batch = io_train.batch = kio->batch;
+  io_eval.size = io_train.size = kio->size;
+  io_eval.x = io_train.x = kio->x;
+  io_eval.momentum = io_train.momentum = kio->momentum;
+  io_eval.eps = io_train.eps = kio->eps;
+  io_eval.training = 0;
+  io_train.training = 1;
+  Net T, S, A;
+  init_net(T, engine, teacher_params, nullptr, teacher_buffers, &io_eval, base, lay.teacher, st, true);
+  init_net(S, engine, student_params, student_grads, student_buffers, &io_train, base + lay.teacher, lay.train, st, true);
+  init_net(A, engine, assistant_params, assistant_grads, assistant_buffers, &io_train, base + lay.teacher + lay.train,
+           lay.train, st, true);
+  T.forward();
+  if (!T.ok()) return T.err;
+  S.forward();
+  if (!S.ok()) return S.err;
+  A.forward();
+  if (!A.ok()) return A.err;
+
+  float* parts = (float*)(base + lay.teacher + 2 * lay.train);   // [6] loss terms, then the reduction scratch
+  void* lws = parts + 64;
+  const size_t lws_bytes = lay.scratch - 64 * sizeof(float);
+  const bool to_student = kio->assistant_grad_to_student != 0;
+  auto grad_buf = [](Net& net, const Tensor& t) {
+    bf16* g = (bf16*)net.alloc((size_t)t.n * t.h * t.w * t.ld * sizeof(bf16));
+    net.add_slot(t, g, t.ld);
+    return g;
+  };
+  // student loss: MSE(s_emb, t_emb.detach())
+  {
+    const long long numel = (long long)S.emb.n * S.emb.c;
+    bf16* d_s = grad_buf(S, S.emb);
+    CRFR_TRY(crfr_loss_kd(S.emb.p, nullptr, T.emb.p, numel, 0, 1.f, parts + 0, d_s, nullptr, nullptr, lws, lws_bytes, stream));
+  }
+  // assistant loss: sum_k MSE(t_k - s_k, a_k) over the four stage features and the embedding
+  for (int k = 0; k < 5; ++k) {
+    const Tensor& t = k < 4 ? T.feat[k] : T.emb;
+    const Tensor& s_ = k < 4 ? S.feat[k] : S.emb;
+    const Tensor& a = k < 4 ? A.feat[k] : A.emb;
+    const long long numel = (long long)t.n * t.h * t.w * t.c;
+    bf16* d_s = to_student ? grad_buf(S, s_) : nullptr;
+    bf16* d_a = grad_buf(A, a);
+    CRFR_TRY(crfr_loss_kd(t.p, s_.p, a.p, numel, 0, 1.f, parts + 1 + k, nullptr, d_s, d_a, lws, lws_bytes, stream));
+  }
+  if (!S.ok()) return S.err;
+  if (!A.ok()) return A.err;
+  kd_total_kernel<<<1, 1, 0, st>>>(parts, losses);
+  CRFR_COUNT_LAUNCH();
+  CRFR_LAUNCH_CHECK();
+  S.backward();
+  if (!S.ok()) return S.err;
+  A.backward();
+  return A.err;
+}
+
 extern "C" size_t crfr_ir50_workspace_bytes(int batch, int size) {
   if (batch <= 0 || size != 112) return 0;
   crfr_resnet_io io = {};

@@ -20,7 +20,7 @@ from torch.nn import BatchNorm1d, BatchNorm2d, Conv2d, Dropout, Linear, MaxPool2
 from .. import _lib as L
 from .. import ops
 
-__all__ = ["ResNet", "BasicBlock", "ResNet_34"]
+__all__ = ["ResNet", "BasicBlock", "ResNet_34", "kd_train_step"]
 
 
 def conv3x3(in_planes, out_planes, stride=1):
@@ -178,3 +178,54 @@ class ResNet(Module):
 def ResNet_34(input_size=[112, 112]):
     """ref: model/resnet.py:231-236."""
     return ResNet(input_size, BasicBlock, [3, 4, 6, 3])
+
+
+def _flat_grads(net):
+    """A zeroed flat fp32 arena with one view per parameter (named_parameters order, 16-byte aligned)."""
+    params = net.ordered_parameters()
+    offs, tot = [], 0
+    for p in params:
+        offs.append(tot)
+        tot += (p.numel() + 3) // 4 * 4
+    flat = torch.zeros(tot, dtype=torch.float32, device=params[0].device)
+    return params, [flat[o:o + p.numel()].view(p.shape) for o, p in zip(offs, params)]
+
+
+def kd_train_step(teacher, student, assistant, x, assistant_grad_to_student=True):
+    """The residual knowledge-distillation step of distill_main.py:59-74 as ONE native call (crfr_kd_train_step):
+    teacher forward (eval), student and assistant forward (train, BatchNorm buffers updated), the MSE terms of
+    distill_main.py:63,68-70 on the bf16 features in place, and both backward passes.
+
+    Sets ``p.grad`` of the student to d(L_s [+ L_a])/dp and of the assistant to dL_a/dp (overwriting), and returns the
+    device tensor ``(L_s, L_a)``.  Equivalent to ``(mse(s_emb, t_emb) + sum_k kd(t_k, s_k, a_k)).backward()`` through
+    the drop-in modules, without the fp32 NCHW round trip of the five outputs of each network."""
+    for net in (teacher, student, assistant):
+        if not (isinstance(net, ResNet) and net._native):
+            raise NotImplementedError("kd_train_step needs three native ResNet_34 modules")
+    if teacher.training or not (student.training and assistant.training):
+        raise RuntimeError("kd_train_step: teacher.eval(), student.train(), assistant.train() expected (distill_main.py:41-43)")
+    if not x.is_cuda or x.dim() != 4 or tuple(x.shape[1:]) != (3, 112, 112):
+        raise ValueError("expected a CUDA tensor [B,3,112,112], got %s" % (tuple(x.shape),))
+    x = x.contiguous().float()
+    b = x.shape[0]
+    tp = _TableOfPointers([p.detach() for p in teacher.ordered_parameters()], L.RESNET34_NPARAMS)
+    tb = _TableOfPointers(teacher.ordered_buffers(), 3 * L.RESNET34_NBN)
+    sparams, sgrads = _flat_grads(student)
+    aparams, agrads = _flat_grads(assistant)
+    sp = _TableOfPointers([p.detach() for p in sparams], L.RESNET34_NPARAMS)
+    ap = _TableOfPointers([p.detach() for p in aparams], L.RESNET34_NPARAMS)
+    sb = _TableOfPointers(student.ordered_buffers(), 3 * L.RESNET34_NBN)
+    ab = _TableOfPointers(assistant.ordered_buffers(), 3 * L.RESNET34_NBN)
+    sg, ag = _TableOfPointers(sgrads, L.RESNET34_NPARAMS), _TableOfPointers(agrads, L.RESNET34_NPARAMS)
+    io = L.KdIO()
+    io.batch, io.size, io.x = b, 112, x.data_ptr()
+    io.momentum, io.eps, io.assistant_grad_to_student = 0.1, 1e-5, int(bool(assistant_grad_to_student))
+    losses = torch.empty((2,), dtype=torch.float32, device=x.device)
+    ws = ops.workspace(L.lib().crfr_kd_workspace_bytes(b, 112))
+    L.call("crfr_kd_train_step", student.engine, tp.arr, tb.arr, sp.arr, sb.arr, sg.arr, ap.arr, ab.arr, ag.arr,
+           C.byref(io), losses.data_ptr(), ws.data_ptr(), ws.numel(), ops.stream())
+    for p, g in zip(sparams, sgrads):
+        p.grad = g
+    for p, g in zip(aparams, agrads):
+        p.grad = g
+    return losses

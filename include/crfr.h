@@ -242,6 +242,25 @@ int crfr_resnet34_backward(int engine, const float* const* host_params, float* c
                            const crfr_resnet_io* io, const float* d_emb, const float* const* d_feat, void* ws,
                            size_t ws_bytes, void* stream);
 
+/* ref: the residual knowledge-distillation step distill_main.py:59-74 evaluated on ONE forward (the committed order -
+ * optimiser step between two backward passes over one graph - raises on torch >= 1.5):
+ *   L_s = MSE(s_emb, t_emb.detach());  L_a = sum_{k=1..4} MSE(t_k - s_k, a_k) + MSE(t_emb - s_emb, a_emb)
+ * teacher (ResNet_34, eval), student and assistant (ResNet_34, train).  Accumulates dL_s/dtheta_S
+ * (+ dL_a/dtheta_S when assistant_grad_to_student, as the reference graph does) into student_grads and dL_a/dtheta_A
+ * into assistant_grads; losses: device fp32[2] = (L_s, L_a).  Parameter / buffer tables as for crfr_resnet34_forward. */
+typedef struct crfr_kd_io {
+  int batch, size;               /* size = 112 */
+  const float* x;                /* [B,3,112,112] fp32 NCHW, the same batch for all three networks (distill_main.py:60-62) */
+  float momentum, eps;           /* BatchNorm: 0.1, 1e-5 */
+  int assistant_grad_to_student; /* 1: keep the reference's un-detached t_k - s_k in L_a */
+} crfr_kd_io;
+size_t crfr_kd_workspace_bytes(int batch, int size);
+int crfr_kd_train_step(int engine, const float* const* teacher_params, void* const* teacher_buffers,
+                       const float* const* student_params, void* const* student_buffers, float* const* student_grads,
+                       const float* const* assistant_params, void* const* assistant_buffers,
+                       float* const* assistant_grads, const crfr_kd_io* io, float* losses, void* ws, size_t ws_bytes,
+                       void* stream);
+
 /* ---------------------------------------------------------------- IR_50 teacher (forward only) -------------- */
 #define CRFR_IR50_NPARAMS 187 /* named_parameters() order of DISTILLATION/model/model_irse.py:IR_50 */
 #define CRFR_IR50_NBN 54      /* BatchNorm layers in module order (input_layer, output_layer, body) */

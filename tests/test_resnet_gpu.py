@@ -109,6 +109,46 @@ def test_kd_step_losses_and_gradients(cuda, golden_dir):
                                                             SLACK * abs(c.norm().item() - b.norm().item())), tag
 
 
+def test_native_kd_step_matches_module_path(cuda):
+    """crfr_kd_train_step == the same step composed from the drop-in modules and autograd (same kernels; the native
+    call only skips the fp32 NCHW round trip of the outputs and seeds the feature gradients in bf16 directly)."""
+    from crfr_b200.loss import MSELoss, ResidualKDLoss
+    from crfr_b200.model.resnet import kd_train_step
+    from oracle import resnet_oracle as RO
+    (teacher, student, assistant), sds = _nets()
+    teacher.eval(); student.train(); assistant.train()
+    xc = RO.synthetic_faces(B).cuda()
+    with torch.no_grad():
+        t_outs = teacher(xc)
+    s_outs, a_outs = student(xc), assistant(xc)
+    mse, kd = MSELoss(), ResidualKDLoss()
+    l_s = mse(s_outs[0], t_outs[0])
+    l_a = sum(kd(t_outs[k], s_outs[k], a_outs[k]) for k in (1, 2, 3, 4)) + kd(t_outs[0], s_outs[0], a_outs[0])
+    (l_s + l_a).backward()
+    ref_s = [p.grad.clone() for p in student.parameters()]
+    ref_a = [p.grad.clone() for p in assistant.parameters()]
+    for net, sd in zip((student, assistant), sds[1:]):      # undo the BatchNorm buffer update of the first forward
+        net.load_state_dict(sd)
+        net.zero_grad(set_to_none=True)
+    losses = kd_train_step(teacher, student, assistant, xc)
+    torch.cuda.synchronize()
+    assert abs(losses[0].item() - l_s.item()) < 1e-4 * abs(l_s.item())
+    assert abs(losses[1].item() - l_a.item()) < 1e-4 * abs(l_a.item())
+    names = [k for k, _ in student.named_parameters()]
+    # the two paths round the summed embedding gradient differently (autograd sums in fp32 and rounds once, the native
+    # step sums two bf16 slots); 36 BatchNorm backward passes amplify that to a few per cent on the deepest tensors
+    for tag, net, ref in (("s", student, ref_s), ("a", assistant, ref_a)):
+        fo, fr = [], []
+        for k, p, r in zip(names, net.parameters(), ref):
+            if k in RO.RESNET_NULL_GRAD:
+                continue
+            assert rel_err(p.grad, r) < 6e-2, (tag, k, rel_err(p.grad, r))
+            fo.append(p.grad.flatten().double()); fr.append(r.flatten().double())
+        a, b = torch.cat(fo), torch.cat(fr)
+        assert float(a @ b / (a.norm() * b.norm())) > 0.999, tag
+    assert int(student.state_dict()["bn1.num_batches_tracked"]) == 1
+
+
 def test_ir50_teacher_eval_forward(cuda, golden_dir):
     """The frozen IR_50 teacher (DISTILLATION/model/model_irse.py, distill_main.py:201) in eval mode."""
     from crfr_b200.model.model_irse import IR_50
