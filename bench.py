@@ -33,25 +33,39 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
+    """Samples SM clocks and throttle reasons while the timed region runs: ONE nvidia-smi process in loop mode
+    (-lms 100) streamed line by line (a query per sample costs ~0.4 s of start-up each and yields 1-2 samples)."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.rows, self.stop_flag, self.proc = index, [], False, None
+        self.t_start = float("inf")      # samples before the timed region starts are discarded
 
     def run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
-                if len(f) >= 6:
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                f = [x.strip() for x in line.strip().split(",")]
+                if len(f) >= 6 and time.perf_counter() >= self.t_start:
                     self.rows.append(f)
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def stop(self):
+        self.stop_flag = True
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
             except Exception:
                 pass
-            time.sleep(0.2)
+        self.join(timeout=3)
 
     def summary(self):
         sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
@@ -266,14 +280,16 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def timed(fn, steps, warmup):
+        sampler = ClockSampler(local) if rank == 0 else None
+        if sampler:
+            sampler.start()            # nvidia-smi comes up during the warm-up; only samples after t_start are kept
         for i in range(warmup):
             fn(i)
         barrier()
-        sampler = ClockSampler(local) if rank == 0 else None
-        if sampler:
-            sampler.start()
         launches0 = L.lib().crfr_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if sampler:
+            sampler.t_start = time.perf_counter()
         e0.record()
         last = None
         for i in range(steps):
@@ -283,8 +299,7 @@ def run_ours(args):
         ms = e0.elapsed_time(e1)
         launches = L.lib().crfr_launch_count() - launches0
         if sampler:
-            sampler.stop_flag = True
-            sampler.join(timeout=3)
+            sampler.stop()
         t = torch.tensor([ms], device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
