@@ -1,6 +1,7 @@
 // C-ABI convolution entry points: shape validation + engine dispatch (tcgen05 implicit GEMM or CUDA-core direct).
 #include <stdarg.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "crfr.h"
@@ -19,6 +20,17 @@ void crfr_set_error(const char* fmt, ...) {
 extern "C" const char* crfr_last_error(void) { return g_err; }
 extern "C" int crfr_version(void) { return 100; }
 extern "C" unsigned long long crfr_launch_count(void) { return g_crfr_launches; }
+
+void crfr_norm_set_impl(int v);   // norm_act.cu
+extern "C" int crfr_set_option(const char* name, int value) {
+  CRFR_CHECK_ARG(name, "set_option: null name");
+  if (!strcmp(name, "norm_bwd_impl")) {
+    crfr_norm_set_impl(value);
+    return CRFR_OK;
+  }
+  crfr_set_error("set_option: unknown option '%s'", name);
+  return CRFR_EINVAL;
+}
 
 static int check_desc(const crfr_conv_desc* d, const char* who) {
   CRFR_CHECK_ARG(d, "%s: null descriptor", who);

@@ -16,6 +16,19 @@ size_t crfr_norm_ws_bytes(int n, int hw, int c);
 int crfr_norm_finalize(const float* partial, int n, int chunks, int hw, int c, float eps, float* stats,
                        cudaStream_t st);
 
+// norm_stream.cu: TMA-fed reduce / apply passes of the normalisation backward (same contract as the kernels in
+// norm_act.cu; views = the tensors the passes touch, checked for TMA alignment)
+int crfr_norm_stream_supported(int c, long long npix, const void* const* views, const int* lds, int count);
+int crfr_norm_stream_parts(int n, int hw, int c);   // partial slots per image ([n][parts][3][c] floats), 0 = unsupported
+int crfr_norm_bwd_reduce_stream(const void* da, int da_ld, const void* db, int db_ld, const void* y, int y_ld,
+                                const float* stats, const float* gamma, const float* beta, const float* alpha, int relu,
+                                const void* res, int res_ld, void* dz, int dz_ld, int n, int hw, int c, float* partial,
+                                cudaStream_t st);
+int crfr_norm_bwd_apply_stream(const void* dsrc, int dsrc_ld, int recompute, const void* y, int y_ld, const float* stats,
+                               const float* bstats, const float* tot, const float* gamma, const float* beta,
+                               const float* alpha, int relu, void* dy, int dy_ld, float* dgamma, float* dbeta,
+                               float* dalpha, int n, int hw, int c, cudaStream_t st);
+
 // direct_conv.cu
 int crfr_direct_gather(int down, int n, int bh, int bw, int sh, int sw, int k, int stride, int pad, const void* src,
                        int src_ld, const void* w, int R, int s_pad, const float* bias, void* y, int y_ld,

@@ -1,0 +1,488 @@
+// TMA-fed versions of the two InstanceNorm / BatchNorm backward passes (norm_act.cu holds the arithmetic contract).
+//
+// Why: the register-staged passes keep 128 registers per thread busy, so only 512 threads per SM are resident and each
+// of them can have 4-8 sixteen-byte loads in flight: 32-64 KB per SM.  At the ~1.5 us loaded HBM latency of the B200
+// that is 3-5 TB/s by Little's law - measured 3.1 TB/s for the reduce pass against 6.45 TB/s peak.  Here a producer warp
+// streams [P pixels x 64 channels] boxes of every input map through a ring of shared-memory stages with
+// cp.async.bulk.tensor (SWIZZLE_128B, mbarrier complete_tx): ~96 KB per CTA, two CTAs per SM = 190 KB in flight, and the
+// 8 consumer warps only ever hold the two pixels they are working on.
+//
+// The kernels are persistent: CTA b owns the contiguous range [b R / G, (b + 1) R / G) of the flattened (image, pixel)
+// space (R = n x hw, G = 2 CTAs per SM), split into per-image segments.  The producer runs ahead across segment
+// boundaries, so the per-segment work of the consumers (reloading the image's coefficients, folding the partial sums)
+// overlaps the loads of the next segment; with the former (chunk, image) grid of ~600-pixel CTAs that start-up and
+// tail cost ~35 % of the bandwidth.  Partial sums go to fixed (image, CTA) slots and are folded in fixed order by
+// bwd_fold_kernel: deterministic.  Same arithmetic per element as norm_act_bwd_reduce/apply_kernel.
+//
+// ref: backward of nn.InstanceNorm2d + nn.PReLU + residual add (model/FSRnet.py:75-98, 105-135) and of train-mode
+//      nn.BatchNorm2d + ReLU (model/resnet.py:24-45).
+#include <cudaTypedefs.h>
+
+#include "common.cuh"
+#include "crfr.h"
+#include "internal.h"
+#include "sm100.cuh"
+
+using namespace sm100;
+
+namespace {
+
+constexpr int kConsumers = 256;
+constexpr int kThreads = kConsumers + 32;   // + one producer warp
+constexpr int kTileBytes = 4096;            // one map, one stage: P pixels x c channels x 2 B (one pixel per consumer)
+constexpr int kRingBytes = 88 * 1024;       // stage ring per CTA (two CTAs per SM)
+constexpr int kMaxStages = 16;
+constexpr int kScratchBytes = 8192;         // [lanes][c] floats = 256 x 8 x 4 B
+
+struct Maps {
+  CUtensorMap t[4];
+};
+
+struct StreamArgs {
+  int ntensors, stages;
+  int hw, c, nimg, parts;
+  long long total;                  // n x hw pixels
+  int relu, has_b, has_res, recompute;
+  const float* stats; const float* gamma; const float* beta; const float* alpha;
+  const float* bstats; const float* tot;
+  bf16* out; int out_ld;            // reduce: dz (may be null); apply: dy
+  float* partial;                   // reduce: [n][parts][3][c]
+  float* dgamma; float* dbeta; float* dalpha;
+};
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void st_stream(bf16* p, const uint4& u) {
+  asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
+}
+// bf16x2 word <-> two fp32 (low half = even channel)
+__device__ __forceinline__ float2 up2(uint32_t w) {
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+__device__ __forceinline__ uint32_t pk2(float2 v) {
+  const __nv_bfloat162 b = __floats2bfloat162_rn(v.x, v.y);
+  return *reinterpret_cast<const uint32_t*>(&b);
+}
+__device__ __forceinline__ uint32_t word(const uint4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
+__device__ __forceinline__ void set_word(uint4& v, int i, uint32_t w) {
+  if (i == 0) v.x = w; else if (i == 1) v.y = w; else if (i == 2) v.z = w; else v.w = w;
+}
+
+// first CTA whose range [total b / G, total (b + 1) / G) contains pixel x
+__device__ __forceinline__ int first_cta_of(long long x, long long total, int G) {
+  return (int)(((x + 1) * G + total - 1) / total) - 1;
+}
+
+struct Setup {
+  uint32_t ring;        // shared-window addresses
+  uint32_t full, empty;
+  float* scratch;
+  int r_begin, r_end;   // this CTA's range of the flattened (image, pixel) space (n x hw < 2^31)
+};
+
+__device__ __forceinline__ uint64_t* bar_ptr(uint8_t* ring, int which, int s) {
+  return (uint64_t*)(ring + kRingBytes + kScratchBytes) + which * kMaxStages + s;
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (uint32_t i = 0; i < (1u << 24) && !ok; ++i)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  if (!ok) __trap();   // a protocol bug traps instead of hanging the GPU box
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ Setup setup(const StreamArgs& a, uint8_t* smem_raw) {
+  Setup u;
+  uint8_t* ring = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  u.ring = smem_u32(ring);
+  u.scratch = (float*)(ring + kRingBytes);
+  u.full = smem_u32(bar_ptr(ring, 0, 0));
+  u.empty = smem_u32(bar_ptr(ring, 1, 0));
+  u.r_begin = (int)(a.total * blockIdx.x / gridDim.x);
+  u.r_end = (int)(a.total * (blockIdx.x + 1) / gridDim.x);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < a.stages; ++s) {
+      mbar_init(bar_ptr(ring, 0, s), 1);
+      mbar_init(bar_ptr(ring, 1, s), kConsumers / 32);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  return u;
+}
+
+// producer warp: stream every stage of this CTA's range, running ahead of the consumers across segment boundaries
+__device__ __forceinline__ void produce(const Maps& maps, const StreamArgs& a, const Setup& u, int P) {
+  const bool leader = elect_one();
+  const int subs = a.c >> 6;
+  const uint32_t stage_bytes = a.ntensors * kTileBytes;
+  int s = 0;
+  uint32_t phase = 1;
+  int r = u.r_begin;
+  while (r < u.r_end) {
+    const int off = r % a.hw;
+    const int seg = min(a.hw - off, u.r_end - r);
+    const int nst = (seg + P - 1) / P;
+    for (int k = 0; k < nst; ++k) {
+      mbar_wait_a(u.empty + 8 * s, phase);
+      if (leader) {
+        const uint32_t fb = u.full + 8 * s;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"(stage_bytes) : "memory");
+        const uint32_t stage = u.ring + s * stage_bytes;
+        for (int t = 0; t < a.ntensors; ++t)
+          for (int sub = 0; sub < subs; ++sub)
+            asm volatile(
+                "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                ::"r"(stage + t * kTileBytes + sub * (P * 128)), "l"(&maps.t[t]), "r"(fb), "r"(sub * 64), "r"(r + k * P)
+                : "memory");
+      }
+      __syncwarp();
+      if (++s == a.stages) { s = 0; phase ^= 1; }
+    }
+    r += seg;
+  }
+}
+
+// pass 1: dz = dout * act'(z) (bf16), per-(image, CTA) partial sums of dz, dz * xhat, dout * min(z, 0).
+// The inner loop is issue-bound, not bandwidth-bound, unless it is kept to ~8 instructions per channel: two channels
+// per packed fp32x2 instruction (FFMA2 / FADD2), sum(dz * xhat) accumulated as sum(dz * y) and centred once per
+// segment, rounding and packing of dz in one cvt.rn.bf16x2.
+template <bool HAS_B, bool HAS_RES>
+__device__ __forceinline__ void reduce_consume(const StreamArgs& a, const Setup& u, int P) {
+  const int c = a.c, groups = c >> 3, lanes = kConsumers / groups;
+  const int cg = threadIdx.x % groups, lane = threadIdx.x / groups;
+  const bool act = a.relu || a.alpha;
+  const uint32_t stage_bytes = a.ntensors * kTileBytes;
+  const uint32_t my_off = (cg >> 3) * (P * 128) + lane * 128 + (((cg & 7) ^ (lane & 7)) << 4);
+  constexpr int ty = HAS_B ? 2 : 1, tr = ty + 1;   // tensor order in a stage: dout_a, [dout_b], y, [res]
+  int s = 0;
+  uint32_t phase = 0;
+  int r = u.r_begin;
+  while (r < u.r_end) {
+    const int img = r / a.hw, off = r - img * a.hw;
+    const int seg = min(a.hw - off, u.r_end - r);
+    const int nst = (seg + P - 1) / P;
+    float2 sc[4], sh[4], al[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float t[6];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int ch = cg * 8 + 2 * i + e;
+        const float mu = a.stats[2 * (img * c + ch)], rs = a.stats[2 * (img * c + ch) + 1];
+        t[e] = (a.gamma ? a.gamma[ch] : 1.f) * rs;
+        t[2 + e] = (a.beta ? a.beta[ch] : 0.f) - mu * t[e];
+        t[4 + e] = a.relu ? 0.f : (a.alpha ? a.alpha[ch] : 1.f);
+      }
+      sc[i] = make_float2(t[0], t[1]);
+      sh[i] = make_float2(t[2], t[3]);
+      al[i] = make_float2(t[4], t[5]);
+    }
+    float2 acc0[4], acc1[4], acc2[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc0[i] = acc1[i] = acc2[i] = make_float2(0.f, 0.f);
+    const bool store = a.out != nullptr;
+    bf16* optr = a.out + ((long long)r + lane) * a.out_ld + cg * 8;
+    const long long ostep = (long long)P * a.out_ld;
+    for (int k = 0; k < nst; ++k) {
+      mbar_wait_a(u.full + 8 * s, phase);
+      const uint32_t addr = u.ring + s * stage_bytes + my_off;
+      if (k * P + lane < seg) {
+        const uint4 A = lds128(addr);
+        uint4 B, R;
+        if (HAS_B) B = lds128(addr + kTileBytes);
+        const uint4 Y = lds128(addr + ty * kTileBytes);
+        if (HAS_RES) R = lds128(addr + tr * kTileBytes);
+        uint4 O;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float2 g = up2(word(A, i));
+          if (HAS_B) g = __fadd2_rn(g, up2(word(B, i)));
+          const float2 f = up2(word(Y, i));
+          if (act) {
+            float2 z = __ffma2_rn(f, sc[i], sh[i]);
+            if (HAS_RES) z = __fadd2_rn(z, up2(word(R, i)));
+            if (!(z.x > 0.f)) { acc2[i].x = fmaf(g.x, z.x, acc2[i].x); g.x *= al[i].x; }
+            if (!(z.y > 0.f)) { acc2[i].y = fmaf(g.y, z.y, acc2[i].y); g.y *= al[i].y; }
+          }
+          const uint32_t w = pk2(g);
+          set_word(O, i, w);
+          const float2 d = up2(w);
+          acc0[i] = __fadd2_rn(acc0[i], d);
+          acc1[i] = __ffma2_rn(d, f, acc1[i]);
+        }
+        if (store) *reinterpret_cast<uint4*>(optr) = O;
+      }
+      optr += ostep;
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) mbar_arrive_a(u.empty + 8 * s);
+      if (++s == a.stages) { s = 0; phase ^= 1; }
+    }
+    // centre and scale: sum(dz * xhat) = rstd * (sum(dz * y) - mean * sum(dz))
+    float q[3][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int ch = cg * 8 + 2 * i + e;
+        const float mu = a.stats[2 * (img * c + ch)], rs = a.stats[2 * (img * c + ch) + 1];
+        const float s0 = e ? acc0[i].y : acc0[i].x, s1 = e ? acc1[i].y : acc1[i].x;
+        q[0][2 * i + e] = s0;
+        q[1][2 * i + e] = (s1 - mu * s0) * rs;
+        q[2][2 * i + e] = e ? acc2[i].y : acc2[i].x;
+      }
+    }
+    // fold the pixel lanes in fixed order, one quantity at a time through the [lanes][c] scratch, and publish this
+    // CTA's partial of the image in its fixed slot
+    const int part = blockIdx.x - first_cta_of((long long)img * a.hw, a.total, gridDim.x);
+    float* dst = a.partial + ((long long)img * a.parts + part) * 3 * c;
+#pragma unroll
+    for (int qq = 0; qq < 3; ++qq) {
+      named_bar_sync(1, kConsumers);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) u.scratch[lane * c + cg * 8 + j] = q[qq][j];
+      named_bar_sync(1, kConsumers);
+      for (int ch = threadIdx.x; ch < c; ch += kConsumers) {
+        float t = 0.f;
+        for (int l = 0; l < lanes; ++l) t += u.scratch[l * c + ch];
+        dst[qq * c + ch] = t;
+      }
+    }
+    if (off + seg == a.hw)   // last CTA of this image: the unused slots must read as zero
+      for (int z = part + 1; z < a.parts; ++z)
+        for (int i = threadIdx.x; i < 3 * c; i += kConsumers) a.partial[((long long)img * a.parts + z) * 3 * c + i] = 0.f;
+    r += seg;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
+norm_bwd_reduce_stream_kernel(const __grid_constant__ Maps maps, const __grid_constant__ StreamArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const int P = kTileBytes / (2 * a.c);             // pixels per stage = pixel lanes of the consumers
+  const Setup u = setup(a, smem_raw);
+  if ((threadIdx.x >> 5) == kConsumers / 32) {
+    produce(maps, a, u, P);
+    return;
+  }
+  if (a.has_b) {
+    if (a.has_res) reduce_consume<true, true>(a, u, P);
+    else reduce_consume<true, false>(a, u, P);
+  } else {
+    if (a.has_res) reduce_consume<false, true>(a, u, P);
+    else reduce_consume<false, false>(a, u, P);
+  }
+}
+
+// pass 2: dy = gamma * rstd * (dz - mean(dz) - xhat * mean(dz * xhat)) = ca * dz + cb * y + cc per channel;
+// dz streamed back, or recomputed from dout (z = ca * y + shift, same rounding as pass 1)
+__global__ void __launch_bounds__(kThreads, 2)
+norm_bwd_apply_stream_kernel(const __grid_constant__ Maps maps, const __grid_constant__ StreamArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const int c = a.c, groups = c >> 3;
+  const int P = kTileBytes / (2 * c);
+  const Setup u = setup(a, smem_raw);
+  if ((threadIdx.x >> 5) == kConsumers / 32) {
+    produce(maps, a, u, P);
+    return;
+  }
+  // CTA 0 also folds the per-image totals into the parameter gradients, in fixed order (deterministic)
+  if (blockIdx.x == 0 && (a.dgamma || a.dbeta || a.dalpha)) {
+    for (int ch = threadIdx.x; ch < c; ch += kConsumers) {
+      float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+      for (int i = 0; i < a.nimg; ++i) {
+        t0 += a.tot[(i * 3 + 0) * c + ch];
+        t1 += a.tot[(i * 3 + 1) * c + ch];
+        t2 += a.tot[(i * 3 + 2) * c + ch];
+      }
+      if (a.dbeta) a.dbeta[ch] += t0;
+      if (a.dgamma) a.dgamma[ch] += t1;
+      if (a.dalpha) a.dalpha[ch] += t2;
+    }
+  }
+  const int cg = threadIdx.x % groups, lane = threadIdx.x / groups;
+  const bool redo = a.recompute && (a.relu || a.alpha);
+  const uint32_t stage_bytes = 2 * kTileBytes;
+  const uint32_t my_off = (cg >> 3) * (P * 128) + lane * 128 + (((cg & 7) ^ (lane & 7)) << 4);
+  int s = 0;
+  uint32_t phase = 0;
+  int r = u.r_begin;
+  while (r < u.r_end) {
+    const int img = r / a.hw, off = r - img * a.hw;
+    const int seg = min(a.hw - off, u.r_end - r);
+    const int nst = (seg + P - 1) / P;
+    float2 ca[4], cb[4], cc[4], sh[4], al[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float t[10];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int ch = cg * 8 + 2 * i + e;
+        const float mu = a.stats[2 * (img * c + ch)], rs = a.stats[2 * (img * c + ch) + 1];
+        const float m1 = a.bstats[2 * (img * c + ch)], m2 = a.bstats[2 * (img * c + ch) + 1];
+        const float gr = (a.gamma ? a.gamma[ch] : 1.f) * rs;
+        t[e] = gr;
+        t[2 + e] = -gr * m2 * rs;
+        t[4 + e] = -gr * m1 - t[2 + e] * mu;
+        t[6 + e] = (a.beta ? a.beta[ch] : 0.f) - mu * gr;
+        t[8 + e] = a.relu ? 0.f : (a.alpha ? a.alpha[ch] : 1.f);
+      }
+      ca[i] = make_float2(t[0], t[1]);
+      cb[i] = make_float2(t[2], t[3]);
+      cc[i] = make_float2(t[4], t[5]);
+      sh[i] = make_float2(t[6], t[7]);
+      al[i] = make_float2(t[8], t[9]);
+    }
+    bf16* optr = a.out + ((long long)r + lane) * a.out_ld + cg * 8;
+    const long long ostep = (long long)P * a.out_ld;
+    for (int k = 0; k < nst; ++k) {
+      mbar_wait_a(u.full + 8 * s, phase);
+      const uint32_t addr = u.ring + s * stage_bytes + my_off;
+      if (k * P + lane < seg) {
+        const uint4 D = lds128(addr), Y = lds128(addr + kTileBytes);
+        uint4 O;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float2 d = up2(word(D, i));
+          const float2 f = up2(word(Y, i));
+          if (redo) {
+            const float2 z = __ffma2_rn(f, ca[i], sh[i]);
+            if (!(z.x > 0.f)) d.x *= al[i].x;
+            if (!(z.y > 0.f)) d.y *= al[i].y;
+            d = up2(pk2(d));
+          }
+          set_word(O, i, pk2(__ffma2_rn(ca[i], d, __ffma2_rn(cb[i], f, cc[i]))));
+        }
+        st_stream(optr, O);
+      }
+      optr += ostep;
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) mbar_arrive_a(u.empty + 8 * s);
+      if (++s == a.stages) { s = 0; phase ^= 1; }
+    }
+    r += seg;
+  }
+}
+
+constexpr size_t kSmemBytes = 1024 /*align*/ + kRingBytes + kScratchBytes + 2 * kMaxStages * sizeof(uint64_t);
+
+int encode_map(CUtensorMap* m, const void* ptr, int ld, int c, long long npix, int P, const char* what) {
+  unsigned long long dims[2] = {(unsigned long long)c, (unsigned long long)npix};
+  unsigned long long strides[1] = {(unsigned long long)ld * 2};
+  unsigned int box[2] = {64, (unsigned int)P};
+  return crfr_tmap_encode_bf16(m, ptr, 2, dims, strides, box, what);
+}
+
+int sm_count() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      sms = 148;
+  }
+  return sms;
+}
+
+// persistent grid: two CTAs per SM, at least 16 stages of work per CTA
+int grid_for(long long total, int c) {
+  const int P = kTileBytes / (2 * c);
+  long long g = total / (16 * P);
+  if (g < 1) g = 1;
+  const int cap = 2 * sm_count();
+  return (int)(g < cap ? g : cap);
+}
+
+int set_attrs() {
+  static bool done = false;
+  if (!done) {
+    CRFR_CUDA(cudaFuncSetAttribute(norm_bwd_reduce_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    CRFR_CUDA(cudaFuncSetAttribute(norm_bwd_apply_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    done = true;
+  }
+  return CRFR_OK;
+}
+
+}  // namespace
+
+// c a multiple of 64 (one TMA box = 64 channels = one 128-byte swizzle row), views 16-byte aligned
+int crfr_norm_stream_supported(int c, long long npix, const void* const* ptrs, const int* lds, int count) {
+  if (c < 64 || c > 512 || (c & 63) || npix >= (1ll << 31)) return 0;
+  for (int i = 0; i < count; ++i)
+    if (ptrs[i] && ((((uintptr_t)ptrs[i]) & 15) || (lds[i] & 7) || lds[i] < c)) return 0;
+  return 1;
+}
+
+// partial slots per image: an image of hw pixels is covered by at most this many CTAs
+int crfr_norm_stream_parts(int n, int hw, int c) {
+  if (c < 64 || c > 512 || (c & 63)) return 0;
+  const long long total = (long long)n * hw;
+  const long long min_px = total / grid_for(total, c);   // every CTA owns at least floor(total / grid) >= 1 pixels
+  return (int)((hw + min_px - 1) / min_px) + 1;
+}
+
+int crfr_norm_bwd_reduce_stream(const void* da, int da_ld, const void* db, int db_ld, const void* y, int y_ld,
+                                const float* stats, const float* gamma, const float* beta, const float* alpha, int relu,
+                                const void* res, int res_ld, void* dz, int dz_ld, int n, int hw, int c, float* partial,
+                                cudaStream_t st) {
+  const bool act = relu || alpha;
+  Maps maps;
+  StreamArgs a = {};
+  const int P = kTileBytes / (2 * c);
+  const long long npix = (long long)n * hw;
+  int t = 0;
+  CRFR_TRY(encode_map(&maps.t[t++], da, da_ld, c, npix, P, "dout_a"));
+  if (db) CRFR_TRY(encode_map(&maps.t[t++], db, db_ld, c, npix, P, "dout_b"));
+  CRFR_TRY(encode_map(&maps.t[t++], y, y_ld, c, npix, P, "y"));
+  if (act && res) CRFR_TRY(encode_map(&maps.t[t++], res, res_ld, c, npix, P, "residual"));
+  for (int i = t; i < 4; ++i) maps.t[i] = maps.t[0];
+  a.ntensors = t;
+  a.stages = kRingBytes / (t * kTileBytes);
+  if (a.stages > kMaxStages) a.stages = kMaxStages;
+  a.hw = hw; a.c = c; a.nimg = n; a.parts = crfr_norm_stream_parts(n, hw, c); a.total = npix;
+  a.relu = relu; a.has_b = db != nullptr; a.has_res = act && res != nullptr;
+  a.stats = stats; a.gamma = gamma; a.beta = beta; a.alpha = alpha;
+  a.out = (bf16*)dz; a.out_ld = dz_ld;
+  a.partial = partial;
+  CRFR_TRY(set_attrs());
+  norm_bwd_reduce_stream_kernel<<<grid_for(npix, c), kThreads, kSmemBytes, st>>>(maps, a);
+  CRFR_COUNT_LAUNCH();
+  CRFR_LAUNCH_CHECK();
+  return CRFR_OK;
+}
+
+int crfr_norm_bwd_apply_stream(const void* dsrc, int dsrc_ld, int recompute, const void* y, int y_ld, const float* stats,
+                               const float* bstats, const float* tot, const float* gamma, const float* beta,
+                               const float* alpha, int relu, void* dy, int dy_ld, float* dgamma, float* dbeta,
+                               float* dalpha, int n, int hw, int c, cudaStream_t st) {
+  Maps maps;
+  StreamArgs a = {};
+  const int P = kTileBytes / (2 * c);
+  const long long npix = (long long)n * hw;
+  CRFR_TRY(encode_map(&maps.t[0], dsrc, dsrc_ld, c, npix, P, recompute ? "dout" : "dz"));
+  CRFR_TRY(encode_map(&maps.t[1], y, y_ld, c, npix, P, "y"));
+  maps.t[2] = maps.t[3] = maps.t[0];
+  a.ntensors = 2;
+  a.stages = kRingBytes / (2 * kTileBytes);
+  if (a.stages > kMaxStages) a.stages = kMaxStages;
+  a.hw = hw; a.c = c; a.nimg = n; a.total = npix;
+  a.relu = relu; a.recompute = recompute;
+  a.stats = stats; a.gamma = gamma; a.beta = beta; a.alpha = alpha;
+  a.bstats = bstats; a.tot = tot;
+  a.out = (bf16*)dy; a.out_ld = dy_ld;
+  a.dgamma = dgamma; a.dbeta = dbeta; a.dalpha = dalpha;
+  CRFR_TRY(set_attrs());
+  norm_bwd_apply_stream_kernel<<<grid_for(npix, c), kThreads, kSmemBytes, st>>>(maps, a);
+  CRFR_COUNT_LAUNCH();
+  CRFR_LAUNCH_CHECK();
+  return CRFR_OK;
+}

@@ -134,6 +134,11 @@ def conv_wgrad(x, dy, cin, cout, k, stride, pad, engine=L.ENGINE_AUTO, transpose
     return dw, db
 
 
+def set_option(name, value):
+    """Implementation switch for A/B measurements and tests (crfr_set_option in include/crfr.h)."""
+    L.call("crfr_set_option", name.encode(), int(value))
+
+
 def engine_supported(engine, op, h, w, cin, cout, k, stride, pad):
     return bool(L.lib().crfr_conv_engine_supported(engine, op, h, w, cin, cout, k, stride, pad))
 

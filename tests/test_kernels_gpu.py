@@ -156,6 +156,68 @@ def test_instance_norm_prelu_add(cuda, c, h, affine, act, res):
         assert rel_err(da, ar.grad) < 1e-2
 
 
+@pytest.mark.parametrize("n,c,h,res,two", [(40, 64, 32, True, True), (40, 64, 32, False, False), (24, 128, 16, True, False),
+                                           (300, 64, 8, False, True), (5, 64, 40, True, True)])
+def test_instance_norm_bwd_implementations(cuda, n, c, h, res, two):
+    """The three implementations of crfr_norm_act_bwd - register-staged passes (0), the persistent one-kernel form with
+    per-image flags (1), the TMA-fed passes (2) - against autograd and against each other, on enough images that work
+    items outnumber resident CTAs."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(n + c + h)
+    y = bf16_round(torch.randn(n, c, h, h, generator=g) * 1.7 + 0.8)
+    r = bf16_round(torch.randn(n, c, h, h, generator=g)) if res else None
+    gamma, beta = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g)
+    alpha = torch.rand(c, generator=g) * 0.5
+    yr, gr, br, ar = (t.clone().requires_grad_(True) for t in (y, gamma, beta, alpha))
+    rr = r.clone().requires_grad_(True) if res else None
+    z = F.instance_norm(yr, weight=gr, bias=br, eps=1e-5)
+    if res:
+        z = z + rr
+    out_ref = _prelu(z, ar)
+    dout = bf16_round(torch.randn(out_ref.shape, generator=g))
+    dout2 = bf16_round(torch.randn(out_ref.shape, generator=g)) if two else None
+    out_ref.backward(dout + dout2 if two else dout)
+    yg = nhwc_from(y)
+    stats = ops.norm_stats(yg)
+    args = (nhwc_from(dout), yg, stats, gamma.cuda(), beta.cuda(), alpha.cuda())
+    kw = dict(res=None if r is None else nhwc_from(r), dout_b=None if dout2 is None else nhwc_from(dout2))
+    results = {}
+    try:
+        for mode in (0, 1, 2):
+            ops.set_option("norm_bwd_impl", mode)
+            results[mode] = ops.norm_act_bwd(*args, **kw)
+            torch.cuda.synchronize()
+    finally:
+        ops.set_option("norm_bwd_impl", -1)
+    for mode in (0, 1, 2):
+        dz, dy, dg, db, da = results[mode]
+        assert rel_err(to_nchw(dy), yr.grad) < 2e-2
+        if res:
+            assert rel_err(to_nchw(dz), rr.grad) < BF16_TOL
+        assert rel_err(dg, gr.grad) < 1e-2 and rel_err(db, br.grad) < 1e-2 and rel_err(da, ar.grad) < 1e-2
+    # same arithmetic up to the association of the fp32 sums: dz identical, dy within one bf16 ulp
+    if results[0][0] is not None:
+        assert torch.equal(results[0][0], results[1][0])
+    assert rel_err(results[1][1].float(), results[0][1].float()) < 3e-3
+    for k in (2, 3, 4):
+        assert rel_err(results[1][k], results[0][k]) < 1e-5
+    # the TMA-fed passes use the same per-element arithmetic; only the association of the fp32 partial sums differs
+    if results[0][0] is not None:
+        assert torch.equal(results[0][0], results[2][0])
+    assert rel_err(results[2][1].float(), results[0][1].float()) < 3e-3
+    for k in (2, 3, 4):
+        assert rel_err(results[2][k], results[0][k]) < 1e-5
+    # deterministic: a second run reproduces every bit
+    for mode in (1, 2):
+        ops.set_option("norm_bwd_impl", mode)
+        try:
+            again = ops.norm_act_bwd(*args, **kw)
+        finally:
+            ops.set_option("norm_bwd_impl", -1)
+        for a, b in zip(again, results[mode]):
+            assert (a is None and b is None) or torch.equal(a, b)
+
+
 def test_batch_norm_relu_mode(cuda):
     """The same kernels with one statistic group over the whole batch = train-mode BatchNorm2d + ReLU (resnet.py:24-28)."""
     ops = _ops()
