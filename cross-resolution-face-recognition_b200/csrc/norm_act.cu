@@ -382,323 +382,17 @@ norm_act_bwd_apply_kernel(const bf16* __restrict__ dz, int dz_ld, const bf16* __
   }
 }
 
-// ------------------------------------------------------------------------------------------------------------------
-// Fused InstanceNorm backward: ONE persistent kernel runs both passes, ordered so that pass 2 of an image finds the
-// maps pass 1 streamed a few images earlier still in the 126 MB L2 (the two-kernel form re-reads dout and y of the
-// whole batch - 2 x 268 MB at 128 images of 64 x 128 x 128 - from HBM).
-//
-// Work items = (pass, image, chunk), claimed in a fixed global order through one atomic counter:
-//     R(0) .. R(lag-1), A(0), R(lag), A(1), R(lag+1), ...        (R = reduce pass, A = apply pass, whole images)
-// R items never wait.  An A item waits for its image's "folded" flag, which only depends on R items that precede it
-// in claim order, i.e. on CTAs that are already running: no co-residency assumption, no deadlock whatever else shares
-// the GPU.  `lag` is chosen so that more items than there are resident CTAs lie between R(i) and A(i) (the wait is
-// then never taken in steady state) while the bytes streamed in between stay well inside L2.
-// The last R item of an image (atomic arrival count) folds the chunk partials in fixed order -> deterministic.
-// ------------------------------------------------------------------------------------------------------------------
-struct FusedBwd {
-  const bf16* da; const bf16* db; const bf16* y; const bf16* res;
-  bf16* dz; bf16* dy;
-  int da_ld, db_ld, y_ld, res_ld, dz_ld, dy_ld;
-  const float* stats; const float* gamma; const float* beta; const float* alpha;
-  int relu;
-  int n, hw, c, chunks, chunk_pix, lag;
-  float inv_hw;
-  float* partial;   // [n][chunks][3][c]
-  float* bstats;    // [n][c][2]
-  float* tot;       // [n][3][c]
-  int* ctrl;        // [0] next item, [1] folded images, [2, 2+n) arrived chunks, [2+n, 2+2n) folded flags
-  float* dgamma; float* dbeta; float* dalpha;
-};
-
-__device__ __forceinline__ bf16x8 ld_l2(const bf16* p) {   // L2-coherent load of data written earlier in this kernel
-  const uint4 u = __ldcg(reinterpret_cast<const uint4*>(p));
-  return *reinterpret_cast<const bf16x8*>(&u);
-}
-__device__ __forceinline__ int ld_acquire(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release(int* p, int v) {
-  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-// pass 1 over one chunk; U pixels per thread in flight
-template <int U, bool HEAVY>
-__device__ __noinline__ void fused_reduce_chunk(const FusedBwd& p, int img, int chunk, float* smem) {
-  const int c = p.c, groups = c >> 3, lanes = kThreads / groups;
-  const int cg = threadIdx.x % groups, lane = threadIdx.x / groups;
-  const int p0 = chunk * p.chunk_pix, p1 = min(p.hw, p0 + p.chunk_pix);
-  const long long pix0 = (long long)img * p.hw;
-  const bool act = p.relu || p.alpha;
-  float acc[3][8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = acc[2][j] = 0.f;
-  // in the loop only z = sc * y + sh and alpha are needed: sum(dz * xhat) is accumulated as sum(dz * y) and
-  // centred / scaled once per chunk (xhat = (y - mean) * rstd), which keeps the loop at 3 coefficient vectors
-  float sc[8];
-  const float* s_sh = smem + 96 * c + cg * 8;   // shift and PReLU slope of this item's channels (filled by the caller)
-  const float* s_al = s_sh + c;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int ch = cg * 8 + j;
-    sc[j] = (p.gamma ? p.gamma[ch] : 1.f) * p.stats[2 * (img * c + ch) + 1];
-  }
-  const bool has_b = HEAVY && p.db != nullptr, has_r = HEAVY && act && p.res != nullptr;
-  for (int q = p0 + lane; q < p1; q += U * lanes) {
-    bf16x8 va[U], vb[U], vy[U], vr[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int pp = q + u * lanes;
-      if (pp < p1) {
-        va[u] = ld_stream(p.da + (pix0 + pp) * p.da_ld + cg * 8);
-        if (has_b) vb[u] = ld_stream(p.db + (pix0 + pp) * p.db_ld + cg * 8);
-        vy[u] = ld_stream(p.y + (pix0 + pp) * p.y_ld + cg * 8);
-        if (has_r) vr[u] = ld_stream(p.res + (pix0 + pp) * p.res_ld + cg * 8);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int pp = q + u * lanes;
-      if (pp < p1) {
-        bf16x8 out;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {   // two channels at a time straight from the packed registers (few live temporaries)
-          float2 gg = __bfloat1622float2(va[u].v[i]);
-          if (has_b) {
-            const float2 g2 = __bfloat1622float2(vb[u].v[i]);
-            gg.x += g2.x; gg.y += g2.y;
-          }
-          const float2 ff = __bfloat1622float2(vy[u].v[i]);
-          float d[2] = {gg.x, gg.y};
-          const float f[2] = {ff.x, ff.y};
-          if (act) {
-            float2 rr = make_float2(0.f, 0.f);
-            if (has_r) rr = __bfloat1622float2(vr[u].v[i]);
-            const float r[2] = {rr.x, rr.y};
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int j = 2 * i + e;
-              float z = fmaf(f[e], sc[j], s_sh[j]);
-              if (has_r) z += r[e];
-              if (!(z > 0.f)) {
-                acc[2][j] = fmaf(d[e], z, acc[2][j]);
-                d[e] *= s_al[j];
-              }
-            }
-          }
-          out.v[i] = __floats2bfloat162_rn(d[0], d[1]);
-          const float2 dd = __bfloat1622float2(out.v[i]);
-          acc[0][2 * i] += dd.x;
-          acc[0][2 * i + 1] += dd.y;
-          acc[1][2 * i] = fmaf(dd.x, f[0], acc[1][2 * i]);
-          acc[1][2 * i + 1] = fmaf(dd.y, f[1], acc[1][2 * i + 1]);
-        }
-        if (p.dz) *reinterpret_cast<bf16x8*>(p.dz + (pix0 + pp) * p.dz_ld + cg * 8) = out;
-      }
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int ch = cg * 8 + j;
-    const float mu = p.stats[2 * (img * c + ch)], rs = p.stats[2 * (img * c + ch) + 1];
-    acc[1][j] = (acc[1][j] - mu * acc[0][j]) * rs;
-  }
-  cta_reduce_store<3>(acc, smem, cg, lane, lanes, c, p.partial + ((long long)img * p.chunks + chunk) * 3 * c);
-}
-
-// pass 2 over one chunk: dy = gr * (dz - m1 - xhat * m2) = gr * dz + cb * y + cc, with dz read back (L2) or, for layers
-// where nobody else consumes it, recomputed from dout and y exactly as pass 1 did (z = gr * y + shift)
-__device__ __noinline__ void fused_apply_chunk(const FusedBwd& p, int img, int chunk, const float* smem) {
-  const int c = p.c, groups = c >> 3, lanes = kThreads / groups;
-  const int cg = threadIdx.x % groups, lane = threadIdx.x / groups;
-  const int p0 = chunk * p.chunk_pix, p1 = min(p.hw, p0 + p.chunk_pix);
-  const long long pix0 = (long long)img * p.hw;
-  const bool act = p.relu || p.alpha;
-  const bool recompute = p.dz == nullptr;
-  float gr[8], cb[8], cc[8];
-  const float* s_sh = smem + 96 * c + cg * 8;
-  const float* s_al = s_sh + c;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int ch = cg * 8 + j;
-    const float mu = p.stats[2 * (img * c + ch)], rs = p.stats[2 * (img * c + ch) + 1];
-    const float m1 = __ldcg(p.bstats + 2 * (img * c + ch)), m2 = __ldcg(p.bstats + 2 * (img * c + ch) + 1);
-    gr[j] = (p.gamma ? p.gamma[ch] : 1.f) * rs;
-    cb[j] = -gr[j] * m2 * rs;
-    cc[j] = -gr[j] * m1 - cb[j] * mu;
-  }
-  for (int qx = p0 + lane; qx < p1; qx += 4 * lanes) {
-    bf16x8 vd[4], vy[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int pp = qx + u * lanes;
-      if (pp < p1) {
-        vd[u] = recompute ? ld_stream(p.da + (pix0 + pp) * p.da_ld + cg * 8)
-                          : ld_l2(p.dz + (pix0 + pp) * p.dz_ld + cg * 8);
-        vy[u] = ld_stream(p.y + (pix0 + pp) * p.y_ld + cg * 8);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int pp = qx + u * lanes;
-      if (pp < p1) {
-        float d[8], f[8];
-        unpack8(vd[u], d);
-        unpack8(vy[u], f);
-        if (recompute && act) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float z = fmaf(f[j], gr[j], s_sh[j]);
-            if (!(z > 0.f)) d[j] *= s_al[j];
-            d[j] = bf16_round(d[j]);
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) d[j] = fmaf(gr[j], d[j], fmaf(cb[j], f[j], cc[j]));
-        st_stream(p.dy + (pix0 + pp) * p.dy_ld + cg * 8, pack8(d));
-      }
-    }
-  }
-}
-
-__global__ void __launch_bounds__(kThreads, 2) norm_act_bwd_fused_kernel(const __grid_constant__ FusedBwd p) {
-  extern __shared__ float smem[];   // [96 c: reduction scratch (3 * lanes <= 96) | c: shift | c: slope]
-  __shared__ int s_next, s_flag;
-  const int c = p.c, groups = c >> 3, lanes = kThreads / groups;
-  const int cg = threadIdx.x % groups, lane = threadIdx.x / groups;
-  const int total = 2 * p.n * p.chunks;
-  const bool act = p.relu || p.alpha;
-  int* arrived = p.ctrl + 2;
-  int* folded = p.ctrl + 2 + p.n;
-  if (threadIdx.x == 0) s_next = atomicAdd(&p.ctrl[0], 1);
-  __syncthreads();
-  int item = s_next;
-  while (item < total) {
-    __syncthreads();                                   // everybody has read s_next
-    if (threadIdx.x == 0) s_next = atomicAdd(&p.ctrl[0], 1);   // claim the next item early: its latency is hidden
-    const int q = item / p.chunks, chunk = item - q * p.chunks;
-    int img;
-    bool reduce;
-    if (q < p.lag) {
-      img = q; reduce = true;
-    } else if (q < 2 * p.n - p.lag) {
-      const int t = q - p.lag;
-      reduce = (t & 1) != 0;
-      img = (t >> 1) + (reduce ? p.lag : 0);
-    } else {
-      img = q - p.n; reduce = false;
-    }
-    // per-channel shift (beta - mean * gamma * rstd) and activation slope of this image, shared by both passes
-    for (int ch = threadIdx.x; ch < c; ch += kThreads) {
-      const float mu = p.stats[2 * (img * c + ch)], rs = p.stats[2 * (img * c + ch) + 1];
-      smem[96 * c + ch] = (p.beta ? p.beta[ch] : 0.f) - mu * (p.gamma ? p.gamma[ch] : 1.f) * rs;
-      smem[97 * c + ch] = p.relu ? 0.f : (p.alpha ? p.alpha[ch] : 1.f);
-    }
-    __syncthreads();
-    if (reduce) {
-      if (p.db || (act && p.res)) fused_reduce_chunk<2, true>(p, img, chunk, smem);
-      else fused_reduce_chunk<4, false>(p, img, chunk, smem);
-      __threadfence();                                 // partials and dz of this chunk are visible GPU-wide ...
-      __syncthreads();
-      if (threadIdx.x == 0) s_flag = atomicAdd(&arrived[img], 1) == p.chunks - 1;   // ... before the arrival is
-      __syncthreads();
-      if (s_flag) {
-        // last chunk of the image: fold its partials (lane-strided, then the 32 lanes in order - fixed order)
-        __threadfence();
-        const float* part = p.partial + (long long)img * p.chunks * 3 * c;
-        const int l = threadIdx.x >> 3;
-        for (int slab = 0; slab < groups; ++slab) {
-          const int ch = slab * 8 + (threadIdx.x & 7);
-          float s[3] = {0.f, 0.f, 0.f};
-          for (int k = l; k < p.chunks; k += 32)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) s[j] += __ldcg(part + (k * 3 + j) * c + ch);
-#pragma unroll
-          for (int j = 0; j < 3; ++j) smem[(j * 32 + l) * c + ch] = s[j];
-        }
-        __syncthreads();
-        for (int i = threadIdx.x; i < 3 * c; i += kThreads) {
-          const int j = i / c, ch = i - j * c;
-          float t = 0.f;
-          for (int k = 0; k < 32; ++k) t += smem[(j * 32 + k) * c + ch];
-          p.tot[(img * 3 + j) * c + ch] = t;
-          if (j < 2) p.bstats[2 * (img * c + ch) + j] = t * p.inv_hw;
-        }
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-          st_release(&folded[img], 1);
-          s_flag = atomicAdd(&p.ctrl[1], 1) == p.n - 1;
-        }
-        __syncthreads();
-        if (s_flag && (p.dgamma || p.dbeta || p.dalpha)) {
-          // every image is folded: parameter gradients = per-image totals summed in image order (deterministic)
-          __threadfence();
-          for (int i = threadIdx.x; i < 3 * c; i += kThreads) {
-            const int j = i / c, ch = i - j * c;
-            float* dst = j == 0 ? p.dbeta : (j == 1 ? p.dgamma : p.dalpha);
-            if (!dst) continue;
-            float t = 0.f;
-#pragma unroll 8
-            for (int im = 0; im < p.n; ++im) t += __ldcg(p.tot + (im * 3 + j) * c + ch);
-            dst[ch] += t;
-          }
-        }
-      }
-    } else {
-      if (threadIdx.x == 0)
-        while (ld_acquire(&folded[img]) == 0) __nanosleep(200);
-      __syncthreads();
-      fused_apply_chunk(p, img, chunk, smem);
-    }
-    __syncthreads();
-    item = s_next;
-  }
-}
-
-// implementation of crfr_norm_act_bwd: 0 = register-staged reduce + fold + apply kernels, 1 = one persistent L2-reusing
-// kernel (experimental), 2 = TMA-fed reduce + fold + apply (norm_stream.cu).  CRFR_NORM_BWD=regs|fused|stream.
+// implementation of crfr_norm_act_bwd: 0 = register-staged reduce + fold + apply kernels (below), 1 = persistent TMA-fed
+// reduce + fold + apply kernels (norm_stream.cu; default wherever the views are TMA-addressable).  CRFR_NORM_BWD=regs|stream.
 int env_impl() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("CRFR_NORM_BWD");
-    v = !e ? 2 : (e[0] == 'r' ? 0 : (e[0] == 'f' ? 1 : 2));
+    v = (e && e[0] == 'r') ? 0 : 1;
   }
   return v;
 }
-int g_impl_override = -1;   // crfr_set_option("norm_bwd_impl", 0 / 1 / 2), -1 = environment / default
-
-int device_sms() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-      sms = 148;
-  }
-  return sms;
-}
-
-struct FusedPlan {
-  int chunks, chunk_pix, lag, grid;
-};
-// heavy = pass 1 streams 3-4 maps per pixel (second gradient and / or residual) instead of 2
-inline FusedPlan plan_fused(int n, int hw, int heavy) {
-  FusedPlan f;
-  const int target = heavy ? 256 : 512;
-  f.chunks = (hw + target - 1) / target;
-  f.chunk_pix = (hw + f.chunks - 1) / f.chunks;
-  f.chunks = (hw + f.chunk_pix - 1) / f.chunk_pix;
-  const long long total = 2LL * n * f.chunks;
-  const int resident = device_sms() * 2;
-  f.grid = (int)(total < resident ? total : resident);
-  // items between the end of R(i) and the start of A(i) = 2 (lag - 1) chunks  >=  1.25 x resident CTAs
-  int lag = (resident + resident / 4 + 2 * f.chunks - 1) / (2 * f.chunks) + 1;
-  f.lag = lag < n ? lag : n;
-  return f;
-}
-inline bool fused_applicable(int n, int c) { return n >= 2 && c <= 256; }
-inline int fused_max_chunks(int hw) { return (hw + 255) / 256 + 1; }
+int g_impl_override = -1;   // crfr_set_option("norm_bwd_impl", 0 / 1), -1 = environment / default
 
 // BatchNorm buffer maintenance (one thread per channel)
 __global__ void bn_update_running_kernel(const float* __restrict__ stats, float* __restrict__ rmean,
@@ -728,10 +422,9 @@ inline bool channels_ok(int c) { return c >= 8 && c <= 2048 && (c & 7) == 0 && (
 size_t crfr_norm_ws_bytes(int n, int hw, int c) {
   ChunkPlan pl = plan_chunks(n, hw);
   int chunks = pl.chunks;
-  if (fused_applicable(n, c) && fused_max_chunks(hw) > chunks) chunks = fused_max_chunks(hw);
   if (crfr_norm_stream_parts(n, hw, c) > chunks) chunks = crfr_norm_stream_parts(n, hw, c);
-  // partials [n][chunks][3][c] + bstats [n][c][2] + tot [n][3][c] + control words of the fused backward [2 + 2 n]
-  return sizeof(float) * ((size_t)n * chunks * 3 * c + (size_t)n * c * 2 + (size_t)n * 3 * c + 2 * (size_t)n + 2) + 256;
+  // partials [n][chunks][3][c] + bstats [n][c][2] + tot [n][3][c]
+  return sizeof(float) * ((size_t)n * chunks * 3 * c + (size_t)n * c * 2 + (size_t)n * 3 * c) + 256;
 }
 
 // Finalise (mean, rstd) from partials laid out [n][chunks][2][c]; shared with the conv epilogue statistics.
@@ -823,36 +516,9 @@ extern "C" int crfr_norm_act_bwd(const void* dout_a, int da_ld, const void* dout
   cudaStream_t st = (cudaStream_t)stream;
   int lanes = kThreads / (c >> 3);
   const int impl = g_impl_override >= 0 ? g_impl_override : env_impl();
-  if (impl == 1 && fused_applicable(n, c)) {
-    const bool act = relu || alpha;
-    const FusedPlan fp = plan_fused(n, hw, dout_b != nullptr || (act && res != nullptr));
-    FusedBwd p;
-    p.da = (const bf16*)dout_a; p.db = (const bf16*)dout_b; p.y = (const bf16*)y; p.res = (const bf16*)res;
-    p.dz = (bf16*)dz; p.dy = (bf16*)dy;
-    p.da_ld = da_ld; p.db_ld = db_ld; p.y_ld = y_ld; p.res_ld = res_ld; p.dz_ld = dz_ld; p.dy_ld = dy_ld;
-    p.stats = stats; p.gamma = gamma; p.beta = beta; p.alpha = alpha; p.relu = relu;
-    p.n = n; p.hw = hw; p.c = c; p.chunks = fp.chunks; p.chunk_pix = fp.chunk_pix; p.lag = fp.lag;
-    p.inv_hw = 1.f / (float)hw;
-    p.partial = (float*)ws;
-    p.bstats = p.partial + (size_t)n * fp.chunks * 3 * c;
-    p.tot = p.bstats + (size_t)n * c * 2;
-    p.ctrl = (int*)(p.tot + (size_t)n * 3 * c);
-    p.dgamma = dgamma; p.dbeta = dbeta; p.dalpha = dalpha;
-    const size_t fsmem = sizeof(float) * 98 * (size_t)c;
-    static size_t smem_set = 48 * 1024;
-    if (fsmem > smem_set) {
-      CRFR_CUDA(cudaFuncSetAttribute(norm_act_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem));
-      smem_set = fsmem;
-    }
-    CRFR_CUDA(cudaMemsetAsync(p.ctrl, 0, sizeof(int) * (2 * (size_t)n + 2), st));
-    norm_act_bwd_fused_kernel<<<fp.grid, kThreads, fsmem, st>>>(p);
-    CRFR_COUNT_LAUNCH();
-    CRFR_LAUNCH_CHECK();
-    return CRFR_OK;
-  }
   const void* views[6] = {dout_a, dout_b, y, res, dz, dy};
   const int lds[6] = {da_ld, db_ld, y_ld, res_ld, dz_ld, dy_ld};
-  const bool tma = impl == 2 && crfr_norm_stream_supported(c, (long long)n * hw, views, lds, 6);
+  const bool tma = impl >= 1 && crfr_norm_stream_supported(c, (long long)n * hw, views, lds, 6);
   const int chunks = tma ? crfr_norm_stream_parts(n, hw, c) : pl.chunks;
   float* partial = (float*)ws;
   float* bstats = partial + (size_t)n * chunks * 3 * c;

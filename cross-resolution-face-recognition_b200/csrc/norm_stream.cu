@@ -39,7 +39,7 @@ struct Maps {
 };
 
 struct StreamArgs {
-  int ntensors, stages;
+  int ntensors, stages, ring_bytes;
   int hw, c, nimg, parts;
   long long total;                  // n x hw pixels
   int relu, has_b, has_res, recompute;
@@ -71,6 +71,15 @@ __device__ __forceinline__ void set_word(uint4& v, int i, uint32_t w) {
   if (i == 0) v.x = w; else if (i == 1) v.y = w; else if (i == 2) v.z = w; else v.w = w;
 }
 
+// Byte offset, inside a stage's tile of one map, of the 16 bytes (8 channels) that consumer (channel group cg, pixel lane)
+// reads.  The tile is c / 64 SWIZZLE_128B boxes of [P pixels][64 channels]; the swizzle XORs the 16-byte chunk index
+// with bits 7..9 of the shared-memory address (tiles are 4 KB aligned), which is the pixel row only while a box is a
+// whole number of 1 KB swizzle atoms - at 512 channels a box is 4 rows = 512 bytes.
+__device__ __forceinline__ uint32_t sw128_offset(int cg, int lane, int P) {
+  const uint32_t row = (uint32_t)((cg >> 3) * P + lane);            // 128-byte row inside the tile
+  return row * 128 + ((((uint32_t)cg & 7) ^ (row & 7)) << 4);
+}
+
 // first CTA whose range [total b / G, total (b + 1) / G) contains pixel x
 __device__ __forceinline__ int first_cta_of(long long x, long long total, int G) {
   return (int)(((x + 1) * G + total - 1) / total) - 1;
@@ -83,8 +92,8 @@ struct Setup {
   int r_begin, r_end;   // this CTA's range of the flattened (image, pixel) space (n x hw < 2^31)
 };
 
-__device__ __forceinline__ uint64_t* bar_ptr(uint8_t* ring, int which, int s) {
-  return (uint64_t*)(ring + kRingBytes + kScratchBytes) + which * kMaxStages + s;
+__device__ __forceinline__ uint64_t* bar_ptr(uint8_t* ring, int ring_bytes, int which, int s) {
+  return (uint64_t*)(ring + ring_bytes + kScratchBytes) + which * kMaxStages + s;
 }
 __device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
   uint32_t ok = 0;
@@ -106,15 +115,15 @@ __device__ __forceinline__ Setup setup(const StreamArgs& a, uint8_t* smem_raw) {
   Setup u;
   uint8_t* ring = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   u.ring = smem_u32(ring);
-  u.scratch = (float*)(ring + kRingBytes);
-  u.full = smem_u32(bar_ptr(ring, 0, 0));
-  u.empty = smem_u32(bar_ptr(ring, 1, 0));
+  u.scratch = (float*)(ring + a.ring_bytes);
+  u.full = smem_u32(bar_ptr(ring, a.ring_bytes, 0, 0));
+  u.empty = smem_u32(bar_ptr(ring, a.ring_bytes, 1, 0));
   u.r_begin = (int)(a.total * blockIdx.x / gridDim.x);
   u.r_end = (int)(a.total * (blockIdx.x + 1) / gridDim.x);
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.stages; ++s) {
-      mbar_init(bar_ptr(ring, 0, s), 1);
-      mbar_init(bar_ptr(ring, 1, s), kConsumers / 32);
+      mbar_init(bar_ptr(ring, a.ring_bytes, 0, s), 1);
+      mbar_init(bar_ptr(ring, a.ring_bytes, 1, s), kConsumers / 32);
     }
     fence_barrier_init();
   }
@@ -164,7 +173,7 @@ __device__ __forceinline__ void reduce_consume(const StreamArgs& a, const Setup&
   const int cg = threadIdx.x % groups, lane = threadIdx.x / groups;
   const bool act = a.relu || a.alpha;
   const uint32_t stage_bytes = a.ntensors * kTileBytes;
-  const uint32_t my_off = (cg >> 3) * (P * 128) + lane * 128 + (((cg & 7) ^ (lane & 7)) << 4);
+  const uint32_t my_off = sw128_offset(cg, lane, P);
   constexpr int ty = HAS_B ? 2 : 1, tr = ty + 1;   // tensor order in a stage: dout_a, [dout_b], y, [res]
   int s = 0;
   uint32_t phase = 0;
@@ -313,7 +322,7 @@ norm_bwd_apply_stream_kernel(const __grid_constant__ Maps maps, const __grid_con
   const int cg = threadIdx.x % groups, lane = threadIdx.x / groups;
   const bool redo = a.recompute && (a.relu || a.alpha);
   const uint32_t stage_bytes = 2 * kTileBytes;
-  const uint32_t my_off = (cg >> 3) * (P * 128) + lane * 128 + (((cg & 7) ^ (lane & 7)) << 4);
+  const uint32_t my_off = sw128_offset(cg, lane, P);
   int s = 0;
   uint32_t phase = 0;
   int r = u.r_begin;
@@ -393,7 +402,10 @@ int sm_count() {
   return sms;
 }
 
-// persistent grid: two CTAs per SM, at least 16 stages of work per CTA
+// persistent grid: two CTAs per SM, at least 16 stages of work per CTA.  (A "slim" shape - 32 KB ring, four ranges per
+// SM, so that one CTA fits beside a 181 KB row-streaming weight-gradient CTA of the helper stream - streams just as fast
+// on its own (64 KB in flight per SM suffice) but did not shorten the step: 48.4 -> 48.8 ms, with or without a
+// high-priority helper stream; the two kernels share the HBM and shared-memory pipes they are both bound by.)
 int grid_for(long long total, int c) {
   const int P = kTileBytes / (2 * c);
   long long g = total / (16 * P);
@@ -446,7 +458,8 @@ int crfr_norm_bwd_reduce_stream(const void* da, int da_ld, const void* db, int d
   if (act && res) CRFR_TRY(encode_map(&maps.t[t++], res, res_ld, c, npix, P, "residual"));
   for (int i = t; i < 4; ++i) maps.t[i] = maps.t[0];
   a.ntensors = t;
-  a.stages = kRingBytes / (t * kTileBytes);
+  a.ring_bytes = kRingBytes;
+  a.stages = a.ring_bytes / (t * kTileBytes);
   if (a.stages > kMaxStages) a.stages = kMaxStages;
   a.hw = hw; a.c = c; a.nimg = n; a.parts = crfr_norm_stream_parts(n, hw, c); a.total = npix;
   a.relu = relu; a.has_b = db != nullptr; a.has_res = act && res != nullptr;
@@ -472,7 +485,8 @@ int crfr_norm_bwd_apply_stream(const void* dsrc, int dsrc_ld, int recompute, con
   CRFR_TRY(encode_map(&maps.t[1], y, y_ld, c, npix, P, "y"));
   maps.t[2] = maps.t[3] = maps.t[0];
   a.ntensors = 2;
-  a.stages = kRingBytes / (2 * kTileBytes);
+  a.ring_bytes = kRingBytes;
+  a.stages = a.ring_bytes / (2 * kTileBytes);
   if (a.stages > kMaxStages) a.stages = kMaxStages;
   a.hw = hw; a.c = c; a.nimg = n; a.total = npix;
   a.relu = relu; a.recompute = recompute;

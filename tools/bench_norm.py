@@ -42,7 +42,11 @@ t = timeit(lambda i: ops.norm_stats(ys[i % K]))
 print("stats (partial+finalize)      %6.1f us  %5.2f TB/s (1 map read)" % (t, MiB * 2**20 / t / 1e6))
 t = timeit(lambda i: ops.norm_act_fwd(ys[i % K], stats, gamma, beta, alpha, res=res))
 print("fwd apply (+res)              %6.1f us  %5.2f TB/s (2 reads + 1 write)" % (t, 3 * MiB * 2**20 / t / 1e6))
-for mode, name in ((0, "regs    "), (1, "fused   "), (2, "stream  ")):
+import os
+MODES = [(0, "regs    "), (1, "stream  ")]
+if os.environ.get("BENCH_MODES"):
+    MODES = [m for m in MODES if str(m[0]) in os.environ["BENCH_MODES"]]
+for mode, name in MODES:
     ops.set_option("norm_bwd_impl", mode)
     t = timeit(lambda i: ops.norm_act_bwd(das[i % K], ys[i % K], stats, gamma, beta, alpha, res=res, dout_b=db))
     print("bwd %s res + 2nd grad     %6.1f us  %5.2f TB/s (6 reads + 2 writes)"
