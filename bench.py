@@ -226,6 +226,38 @@ def time_dominant_kernel(torch, ops, L, chunk):
     return flops / (ms * 1e-3) / 1e12, ms, flops
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of the two passes over 128 images from the committed `ncu --set full`
+# capture (profiles/r1_norm_stream_ncu_full.txt): reduce 1078.0 + 255.1 MB, apply 538.7 + 235.3 MB (algorithmic: 8 maps
+# of 268.4 MB; the tail of each output map is still dirty in L2 when its kernel ends)
+NORM_BWD_TRAFFIC_BYTES_PER_IMAGE = (1078.0e6 + 255.1e6 + 538.7e6 + 235.3e6) / 128
+
+
+def time_norm_bwd(torch, ops, chunk):
+    """CUDA-event timing of the dominant HBM-bound op: the InstanceNorm + PReLU + residual backward of a block output
+    (64 x 128 x 128, second gradient summed in): reduce pass dout_a, dout_b, y, res in, dz out; apply pass dz, y in,
+    dy out = 8 maps of chunk x 2 MiB; rotating buffers > L2."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    c, h, sets = 64, 128, 3
+    mk = lambda: torch.randn(chunk, h, h, c, generator=g, device="cuda").to(torch.bfloat16)
+    ys, das, dbs, rs = ([mk() for _ in range(sets)] for _ in range(4))
+    gamma, beta, alpha = (torch.rand(c, device="cuda") + 0.5 for _ in range(3))
+    stats = ops.norm_stats(ys[0])
+    for i in range(2):
+        ops.norm_act_bwd(das[i], ys[i], stats, gamma, beta, alpha, res=rs[i], dout_b=dbs[i])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 12
+    e0.record()
+    for i in range(reps):
+        k = i % sets
+        ops.norm_act_bwd(das[k], ys[k], stats, gamma, beta, alpha, res=rs[k], dout_b=dbs[k])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    nbytes = 8.0 * chunk * h * h * c * 2
+    return nbytes / (ms * 1e-3) / 1e9, ms, nbytes
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -332,6 +364,13 @@ def run_ours(args):
                              "achieved": k_tflops, "peak": burst, "unit": "TFLOP/s", "frac": k_tflops / burst,
                              "traffic": ROWCONV_TRAFFIC_BYTES_PER_IMAGE * args.chunk, "ms_per_launch": k_ms,
                              "flops_per_launch": k_flops, "peak_source": how}}
+        n_gbs, n_ms, n_bytes = time_norm_bwd(torch, ops, args.chunk)
+        line["roofline_hbm"] = {"bound": "hbm", "kernel": "norm_bwd_reduce_stream_kernel + bwd_fold_kernel + "
+                                                          "norm_bwd_apply_stream_kernel (InstanceNorm + PReLU + residual "
+                                                          "backward, 64 x 128 x 128, %d images)" % args.chunk,
+                                "achieved": n_gbs, "peak": hbm, "unit": "GB/s", "frac": n_gbs / hbm,
+                                "traffic": NORM_BWD_TRAFFIC_BYTES_PER_IMAGE * args.chunk,
+                                "ms_per_op": n_ms, "bytes_per_op": n_bytes, "peak_source": how}
         if not args.no_extras:
             # the other two BASELINE.json paths, measured in the same run (secondary numbers, not the headline metric)
             trainer.ws = None
