@@ -180,6 +180,54 @@ __global__ void col2im_small_kernel(const float* __restrict__ src, int src_ld, i
     for (int c = 0; c < y_ld; ++c) y[i * y_ld + c] = __float2bfloat16_rn(c < C ? acc[c] : 0.f);
 }
 
+// The 3x3 / stride 1 / pad 1, three-channel case of col2im (forward of conv_mid / conv_out, FSRnet.py:318,439): a block
+// stages the [10 x 34 source pixels][27 partial products] halo tile of an 8 x 32 output tile in shared memory with
+// coalesced 16-byte loads (row stride 33 floats: the nine-neighbour reads below are then conflict free) and every
+// thread sums its 27 terms from there.  The generic kernel issues 27 scalar loads per pixel whose addresses are 128
+// bytes apart across a warp - 32 L1 wavefronts per instruction - and is bound by exactly that (195 us for 128 images).
+__global__ void __launch_bounds__(256)
+col2im3_s1_kernel(const float* __restrict__ src, int h, int w, int sgn, const float* __restrict__ bias,
+                  float* __restrict__ y_nchw, bf16* __restrict__ y, int y_ld) {
+  constexpr int TH = 8, TW = 32, SH = TH + 2, SW = TW + 2, LD = 33;
+  __shared__ float tile[SH * SW * LD];
+  const int tiles_x = w / TW, tiles_y = h / TH;
+  int b = blockIdx.x;
+  const int tx0 = (b % tiles_x) * TW;
+  b /= tiles_x;
+  const int ty0 = (b % tiles_y) * TH;
+  const long long n = b / tiles_y;
+  const float* img = src + n * h * w * 32;
+  for (int i = threadIdx.x; i < SH * SW * 8; i += 256) {   // one 16-byte quarter-line of a source pixel per iteration
+    const int px = i >> 3, q = i & 7;
+    const int sy = ty0 - 1 + px / SW, sx = tx0 - 1 + px % SW;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (sy >= 0 && sy < h && sx >= 0 && sx < w) v = *reinterpret_cast<const float4*>(img + ((long long)sy * w + sx) * 32 + q * 4);
+    float* t = tile + px * LD + q * 4;
+    t[0] = v.x; t[1] = v.y; t[2] = v.z; t[3] = v.w;
+  }
+  __syncthreads();
+  const int ly = threadIdx.x >> 5, lx = threadIdx.x & 31;
+  float acc[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) acc[c] = bias ? bias[c] : 0.f;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const float* t = tile + ((ly + 1 + sgn * (1 - ky)) * SW + (lx + 1 + sgn * (1 - kx))) * LD + (ky * 3 + kx) * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) acc[c] += t[c];
+    }
+  const int Y = ty0 + ly, X = tx0 + lx;
+  if (y_nchw)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) y_nchw[((n * 3 + c) * h + Y) * w + X] = acc[c];
+  if (y) {
+    const long long i = (n * h + Y) * w + X;
+    for (int c = 0; c < y_ld; ++c) y[i * y_ld + c] = __float2bfloat16_rn(c < 3 ? acc[c] : 0.f);
+  }
+}
+
 // ---- sub-pixel (phase) decomposition of the 7x7 s4 p2 transposed convolution --------------------------------
 // tap k (0..6) -> output phase p = (k + 2) mod 4 and input offset d = (p + 2 - k) / 4 in {-1, 0, 1}
 __device__ __forceinline__ void subpixel_of_tap(int k, int* phase, int* off) {
@@ -454,6 +502,13 @@ int crfr_lowered_fwd(const crfr_conv_desc* d, const void* x, const void* w_packe
     TcGemm g{x, d->n, d->h, d->w, 64, d->in_ld, Wq, 1, 0, 1, 32, 32, Q, 32, 1, nullptr};
     CRFR_TRY(crfr_tc_gemm(g, st));
     // y[p] = bias + sum_tap Q[p + (tap - pad)][tap*3 + co]
+    if (d->h % 8 == 0 && d->w % 32 == 0) {
+      col2im3_s1_kernel<<<(unsigned)(d->n * (d->h / 8) * (d->w / 32)), 256, 0, st>>>(Q, d->h, d->w, -1, bias, y_nchw, (bf16*)y,
+                                                                                   y ? d->out_ld : 0);
+      CRFR_COUNT_LAUNCH();
+      CRFR_LAUNCH_CHECK();
+      return CRFR_OK;
+    }
     LAUNCH(col2im_small_kernel, pix, st, Q, 32, 3, d->h, d->w, d->h, d->w, 3, 1, 1, -1, bias, y_nchw, (bf16*)y,
            y ? d->out_ld : 0, pix);
     return CRFR_OK;
