@@ -45,6 +45,9 @@ struct TcGemm {           // out[pixel][n] = bias[n] + sum_{tap,k} src[pixel + s
   int n_total, tile_n;    // tile_n = 0: pick automatically
   void* out; int out_ld, out_f32;
   const float* bias;
+  // optional fused InstanceNorm statistics of the stored bf16 output: partial sums [n][slots][2][n_total] are written
+  // to stat_ws when the tiling allows it and *stat_slots is set to the slot count (0: not fused, caller runs a pass)
+  float* stat_ws = nullptr; size_t stat_ws_bytes = 0; int* stat_slots = nullptr;
 };
 int crfr_tc_gemm(const TcGemm& g, cudaStream_t st);
 struct TcWgrad {          // G[tap][ci][co] += sum_pixel x[pixel + tap - 1][ci] * dy[pixel][co]   (fp32, caller zeroes G)

@@ -83,6 +83,8 @@ struct ConvParams {
   int out_f32;     // 0: bf16 NHWC rows, 1: fp32 NHWC rows
   void* out;
   const float* bias;
+  float* partial;  // InstanceNorm partials [n][slots][2][n_total] of the stored (bf16) output, or nullptr
+  int slots, gpt;  // partial slots per image; 32-row groups of a tile that belong to one image (4, 2 or 1)
 };
 
 constexpr int kConvThreads = 192;  // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
@@ -249,6 +251,30 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int t2 = 0; t2 < Cfg::kOutTiles; ++t2)
             tma_store_4d(&tmY, sOut + t2 * kATileBytes, ncol0 + t2 * 64, x0, y0, n0);
           tma_store_commit();
+        }
+        if (p.partial) {
+          // InstanceNorm statistics of the stored (rounded) values, from the staged tile: thread = (channel pair,
+          // 32-row group); a warp reads one 128-byte row per step (conflict free).  Every group lies inside one image;
+          // its sums go to a fixed (image, tile, group) slot and are folded in fixed order by crfr_norm_finalize.
+          const int et = (warp - 2) * 32 + lane, cp = et & 31, pg = et >> 5;
+          const int img = n0 + (pg * 32) / (p.bw * p.bh);
+          const int slot = (ty * p.tiles_x + tx) * p.gpt + pg % p.gpt;
+          float* dst = p.partial + ((long long)img * p.slots + slot) * 2 * p.n_total + ncol0 + 2 * cp;
+          if (img < p.n)
+#pragma unroll
+          for (int t2 = 0; t2 < Cfg::kOutTiles; ++t2) {
+            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+            for (int k = 0; k < 32; ++k) {
+              const int px = pg * 32 + k;
+              const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(
+                  sOut + t2 * kATileBytes + px * 128 + ((((cp >> 2) ^ (px & 7)) << 4) | ((cp & 3) << 2))));
+              s0 += f.x; q0 = fmaf(f.x, f.x, q0);
+              s1 += f.y; q1 = fmaf(f.y, f.y, q1);
+            }
+            *reinterpret_cast<float2*>(dst + t2 * 64) = make_float2(s0, s1);
+            *reinterpret_cast<float2*>(dst + p.n_total + t2 * 64) = make_float2(q0, q1);
+          }
         }
       }
     }
@@ -521,6 +547,21 @@ int crfr_tc_gemm(const TcGemm& g, cudaStream_t st) {
   p.n_total = g.n_total; p.out_ld = g.out_ld; p.out_f32 = g.out_f32; p.out = g.out; p.bias = g.bias;
   const int tiles = t.tiles_x * t.tiles_y * t.tiles_n;
   p.total_tiles = tiles;
+  p.partial = nullptr; p.slots = 0; p.gpt = 0;
+  if (g.stat_slots) *g.stat_slots = 0;
+  if (g.stat_ws && g.stat_slots && !g.out_f32 && tile_n % 64 == 0 && t.rows == 128 && g.h % t.bh == 0 && g.w % t.bw == 0 &&
+      (t.bw * t.bh) % 32 == 0) {
+    // fused statistics: 128-row tiles of whole image rows whose 32-row groups never straddle an image.  Eligibility
+    // must not depend on the batch size (a ragged last tile just skips the images that do not exist): the statistics
+    // of an image - and with them every result downstream - are the same bits however the batch is chunked or sharded
+    const int area = t.bw * t.bh;
+    p.gpt = area >= 128 ? 4 : area / 32;
+    p.slots = t.tiles_x * t.tiles_y * p.gpt;
+    if (sizeof(float) * (size_t)g.n * p.slots * 2 * g.n_total <= g.stat_ws_bytes) {
+      p.partial = g.stat_ws;
+      *g.stat_slots = p.slots;
+    }
+  }
   switch (tile_n) {
     case 32: return launch_conv<32>(tmA, tmB, tmY, p, tiles, st);
     case 64: return launch_conv<64>(tmA, tmB, tmY, p, tiles, st);
@@ -581,6 +622,13 @@ int crfr_tc_supported(int op, int h, int w, int cin, int cout, int k, int stride
 
 size_t crfr_tc_workspace_bytes(const crfr_conv_desc* d) {
   size_t wg = sizeof(float) * (size_t)d->k * d->k * d->cin * d->cout + 256;  // wgrad scratch
+  {   // statistics partials of the fused epilogue: [n][tiles per image x 4][2][cout]
+    Tiling t;
+    if (make_tiling(d->n, d->oh, d->ow, &t)) {
+      const size_t sp = sizeof(float) * (size_t)d->n * t.tiles_x * t.tiles_y * 4 * 2 * d->cout + 256;
+      if (sp > wg) wg = sp;
+    }
+  }
   if (crfr_rowconv_supported(d->h, d->w, d->cin, d->cout, d->k, d->stride, d->pad)) {
     const size_t rc = crfr_rowconv_ws_bytes(d->n, d->h);
     if (rc > wg) wg = rc;
@@ -613,9 +661,18 @@ int crfr_tc_conv(const crfr_conv_desc* d, int dgrad, const void* src, const void
   g.n_total = dgrad ? d->cin : d->cout;
   g.tile_n = g.n_total <= 256 ? g.n_total : 0;   // wider layers: several column tiles per pixel tile
   g.out = dst; g.out_ld = dgrad ? d->in_ld : d->out_ld; g.out_f32 = 0; g.bias = bias;
+  // InstanceNorm statistics: in the epilogue where the tiling allows it (partials in the workspace, folded by
+  // crfr_norm_finalize), otherwise by a separate pass over the stored output
+  int slots = 0;
+  const bool want_stats = stats && !dgrad;
+  g.stat_ws = want_stats ? (float*)ws : nullptr;
+  g.stat_ws_bytes = want_stats ? ws_bytes : 0;
+  g.stat_slots = &slots;
   CRFR_TRY(crfr_tc_gemm(g, st));
-  if (stats && !dgrad)
-    CRFR_TRY(crfr_norm_stats(dst, d->n, d->oh * d->ow, d->cout, d->out_ld, eps, stats, ws, ws_bytes, (void*)st));
+  if (want_stats) {
+    if (slots) CRFR_TRY(crfr_norm_finalize((const float*)ws, d->n, slots, d->oh * d->ow, d->cout, eps, stats, st));
+    else CRFR_TRY(crfr_norm_stats(dst, d->n, d->oh * d->ow, d->cout, d->out_ld, eps, stats, ws, ws_bytes, (void*)st));
+  }
   return CRFR_OK;
 }
 

@@ -19,6 +19,7 @@ TC_SHAPES = [
     (2, 128, 128, 32),    # prior residual convs, hourglass level 2
     (3, 128, 128, 16),    # hourglass level 1
     (5, 128, 128, 8),     # hourglass level 0 (two images per tile, ragged last tile)
+    (4, 128, 128, 8),     # the same with whole tiles: statistics fused in the epilogue, two images per tile
     (9, 128, 128, 4),     # 64x64-input hourglass floor (eight images per tile)
     (2, 192, 64, 32),     # decoder conv_input on cat(prior, encoder)
     (1, 64, 64, 64),      # two rows per tile
