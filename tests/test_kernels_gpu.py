@@ -208,6 +208,55 @@ def test_instance_norm_bwd_implementations(cuda, n, c, h, res, two):
         assert (a is None and b is None) or torch.equal(a, b)
 
 
+def test_instance_norm_bwd_full_size_properties(cuda):
+    """BASELINE.json config 2 size (128 images x 64 ch x 128 x 128, the shape of 36 of the 98 layers), checked through
+    properties that do not need a CPU reference: dy of an InstanceNorm is orthogonal to 1 and to x_hat over every
+    (image, channel) plane; dz is the masked / scaled dout exactly; images are independent (a permuted batch gives the
+    permuted result); the two implementations agree."""
+    ops = _ops()
+    n, c, h = 128, 64, 128
+    g = torch.Generator(device="cuda").manual_seed(77)
+    mk = lambda s=1.0, m=0.0: (torch.randn(n, h, h, c, generator=g, device="cuda") * s + m).to(torch.bfloat16)
+    y, res, dout = mk(1.5, 0.4), mk(), mk()
+    gamma = torch.rand(c, generator=g, device="cuda") + 0.5
+    beta = torch.randn(c, generator=g, device="cuda")
+    alpha = torch.rand(c, generator=g, device="cuda") * 0.5
+    stats = ops.norm_stats(y)
+    dz, dy, dg, db, da = ops.norm_act_bwd(dout, y, stats, gamma, beta, alpha, res=res)
+    torch.cuda.synchronize()
+    # dz = dout * (z > 0 ? 1 : alpha), z = gamma * x_hat + beta + res (fp32), rounded once to bf16
+    xh = (y.float() - stats[:, None, None, :, 0]) * stats[:, None, None, :, 1]
+    z = xh * gamma + beta + res.float()
+    mask = torch.where(z > 0, torch.ones_like(z), alpha.expand_as(z))
+    dz_ref = (dout.float() * mask).to(torch.bfloat16)
+    mism = (dz != dz_ref).float().mean().item()       # z within an ulp of 0 may take the other branch
+    assert mism < 1e-5, mism
+    del z, mask, dz_ref
+    # orthogonality: sum_p dy = 0 and sum_p dy * x_hat = 0 per (image, channel), up to the bf16 rounding of dy
+    dyf = dy.float()
+    scale = dyf.abs().sum((1, 2))
+    assert (dyf.sum((1, 2)).abs() / scale).max().item() < 2e-3
+    assert ((dyf * xh).sum((1, 2)).abs() / scale).max().item() < 2e-3
+    # parameter gradients against their definitions
+    dzf = dz.float()
+    assert rel_err(db, dzf.sum((0, 1, 2))) < 1e-4 and rel_err(dg, (dzf * xh).sum((0, 1, 2))) < 1e-4
+    del dyf, dzf, xh
+    # independence of the images: reversed batch -> reversed result (sums are regrouped: fp32 rounding only)
+    flip = lambda t: t.flip(0).contiguous()
+    dz2, dy2, dg2, db2, da2 = ops.norm_act_bwd(flip(dout), flip(y), flip(stats), gamma, beta, alpha, res=flip(res))
+    assert torch.equal(flip(dz2), dz)
+    assert rel_err(flip(dy2).float(), dy.float()) < 1e-3
+    assert rel_err(dg2, dg) < 1e-5 and rel_err(da2, da) < 1e-5
+    # the register-staged implementation
+    try:
+        ops.set_option("norm_bwd_impl", 0)
+        dz0, dy0, dg0, db0, da0 = ops.norm_act_bwd(dout, y, stats, gamma, beta, alpha, res=res)
+    finally:
+        ops.set_option("norm_bwd_impl", -1)
+    assert torch.equal(dz0, dz) and rel_err(dy0.float(), dy.float()) < 1e-3
+    assert rel_err(dg0, dg) < 1e-5 and rel_err(db0, db) < 1e-5 and rel_err(da0, da) < 1e-5
+
+
 def test_batch_norm_relu_mode(cuda):
     """The same kernels with one statistic group over the whole batch = train-mode BatchNorm2d + ReLU (resnet.py:24-28)."""
     ops = _ops()
