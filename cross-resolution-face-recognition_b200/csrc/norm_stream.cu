@@ -1,18 +1,23 @@
 // TMA-fed versions of the two InstanceNorm / BatchNorm backward passes (norm_act.cu holds the arithmetic contract).
 //
-// Why: the register-staged passes keep 128 registers per thread busy, so only 512 threads per SM are resident and each
-// of them can have 4-8 sixteen-byte loads in flight: 32-64 KB per SM.  At the ~1.5 us loaded HBM latency of the B200
-// that is 3-5 TB/s by Little's law - measured 3.1 TB/s for the reduce pass against 6.45 TB/s peak.  Here a producer warp
-// streams [P pixels x 64 channels] boxes of every input map through a ring of shared-memory stages with
-// cp.async.bulk.tensor (SWIZZLE_128B, mbarrier complete_tx): ~96 KB per CTA, two CTAs per SM = 190 KB in flight, and the
-// 8 consumer warps only ever hold the two pixels they are working on.
-//
-// The kernels are persistent: CTA b owns the contiguous range [b R / G, (b + 1) R / G) of the flattened (image, pixel)
-// space (R = n x hw, G = 2 CTAs per SM), split into per-image segments.  The producer runs ahead across segment
-// boundaries, so the per-segment work of the consumers (reloading the image's coefficients, folding the partial sums)
-// overlaps the loads of the next segment; with the former (chunk, image) grid of ~600-pixel CTAs that start-up and
-// tail cost ~35 % of the bandwidth.  Partial sums go to fixed (image, CTA) slots and are folded in fixed order by
-// bwd_fold_kernel: deterministic.  Same arithmetic per element as norm_act_bwd_reduce/apply_kernel.
+// Why: the register-staged passes ran at 3.1 TB/s (reduce) and 5.3 TB/s (apply) against 6.45 TB/s.  They are not short
+// of loads in flight - a first TMA-fed version with the same arithmetic was no faster - they are ISSUE bound: ~12
+// instructions per channel (scalar fp32, per-load address arithmetic, two unpacks, a round trip through bf16, three
+// accumulations) at ~5 channels per clock per SM.  Here:
+//   * a producer warp streams [32 pixels x 64 channels] SWIZZLE_128B boxes of every input map (2-4 maps) through an
+//     88 KB ring of 4 KB-per-map stages with cp.async.bulk.tensor + mbarrier complete_tx; two CTAs per SM;
+//   * the 8 consumer warps read their 16 bytes per map with one ld.shared.v4 (no address arithmetic, no predication)
+//     and do two channels per packed fp32x2 instruction (FFMA2 / FADD2, sm_100): sum(dz * xhat) is accumulated as
+//     sum(dz * y) and centred once per segment, dz is rounded and packed by one cvt.rn.bf16x2, the apply pass is
+//     ca * dz + cb * y + cc - about 8 instructions per channel;
+//   * the kernels are persistent: CTA b owns the contiguous range [b R / G, (b + 1) R / G) of the flattened
+//     (image, pixel) space (R = n x hw, G = 2 CTAs per SM), split into per-image segments.  The producer runs ahead
+//     across segment boundaries, so the per-segment work of the consumers (the image's coefficients, folding the
+//     partial sums) overlaps the loads of the next segment; the former (chunk, image) grid of ~600-pixel CTAs lost a
+//     third of the bandwidth to start-up and reduction tails.
+// Partial sums go to fixed (image, CTA) slots and are folded in fixed order by bwd_fold_kernel: deterministic.  Same
+// arithmetic per element as norm_act_bwd_reduce/apply_kernel up to the association of the fp32 sums.
+// Measured (profiles/r1_norm_stream_ncu_full.txt): 6.26 / 6.10 TB/s of DRAM traffic inside the reduce / apply kernel.
 //
 // ref: backward of nn.InstanceNorm2d + nn.PReLU + residual add (model/FSRnet.py:75-98, 105-135) and of train-mode
 //      nn.BatchNorm2d + ReLU (model/resnet.py:24-45).
