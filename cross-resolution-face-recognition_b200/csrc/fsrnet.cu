@@ -163,6 +163,10 @@ struct Net {
   size_t scratch2_bytes = 0;
   SideStream* side = nullptr;
   bool side_dirty = false;
+  // weight packing: a dry run of the program (exec = false) collects every pack job here, the entry point issues them
+  // as one batch, and the real run (packs_done) only re-derives the same arena offsets
+  std::vector<crfr_pack_job>* collect = nullptr;
+  bool packs_done = false;
   // fixed buffers
   Tensor x4, coarse4, cat;
   int tape_enc_start = 0, tape_dec_start = 0;   // first tape index of the encoder / decoder sections
@@ -223,7 +227,8 @@ struct Net {
     s_pad = for_dgrad ? ((S + 7) / 8) * 8 : cin_pad;
     if (for_dgrad && S < 8) s_pad = 4;
     void* dst = alloc((size_t)T * R * s_pad * sizeof(bf16));
-    if (run()) check(crfr_pack_weight(params[idx], dst, T, R, S, s_pad, rs, ss, 1, st));
+    if (collect && ok()) collect->push_back({params[idx], dst, T, R, S, s_pad, rs, ss, 0, 0});
+    else if (run() && !packs_done) check(crfr_pack_weight(params[idx], dst, T, R, S, s_pad, rs, ss, 1, st));
     cache[idx] = dst;
     return dst;
   }
@@ -663,6 +668,24 @@ void alloc_out_grads(Net& net, bool coarse, bool out, bool heads) {
   net.d_heads = heads ? (bf16*)net.alloc((size_t)B * Q * Q * kHeadsPad * sizeof(bf16)) : nullptr;
 }
 
+// Dry run of the program over the real arena: collects the weight-pack jobs of the forward (and backward) pass and
+// issues them as one batch.  The arena is a deterministic bump allocator, so the real run finds every packed weight at
+// the offset the dry run gave it.
+int pack_all(int engine, const float* const* params, const crfr_fsrnet_io* io, void* ws, size_t ws_bytes, cudaStream_t st,
+             bool training, bool backward, bool og_coarse, bool og_out, bool og_heads) {
+  std::vector<crfr_pack_job> jobs;
+  Net dry;
+  init_net(dry, engine, params, nullptr, io, ws, ws_bytes, st, false, training);
+  dry.collect = &jobs;
+  dry.forward();
+  if (backward && dry.ok()) {
+    alloc_out_grads(dry, og_coarse, og_out, og_heads);
+    dry.backward();
+  }
+  if (!dry.ok()) return dry.err;
+  return crfr_pack_weight_batch(jobs.data(), (int)jobs.size(), st);
+}
+
 }  // namespace
 
 extern "C" size_t crfr_fsrnet_workspace_bytes(int batch, int size, int training) {
@@ -683,8 +706,10 @@ extern "C" int crfr_fsrnet_forward(int engine, const float* const* host_params, 
                                    int training, void* ws, size_t ws_bytes, void* stream) {
   CRFR_TRY(check_io(io, "fsrnet_forward"));
   CRFR_CHECK_ARG(host_params && ws, "fsrnet_forward: null pointer");
+  CRFR_TRY(pack_all(engine, host_params, io, ws, ws_bytes, (cudaStream_t)stream, training != 0, false, false, false, false));
   Net net;
   init_net(net, engine, host_params, nullptr, io, ws, ws_bytes, (cudaStream_t)stream, true, training != 0);
+  net.packs_done = true;
   net.forward();
   return net.err;
 }
@@ -722,8 +747,10 @@ extern "C" int crfr_fsrnet_train_step(int engine, const float* const* host_param
   CRFR_CHECK_ARG(host_params && host_grads && ws && losses, "fsrnet_train_step: null pointer");
   CRFR_CHECK_ARG(io->hr && io->heatmap && io->labels && io->loss_div > 0.f, "fsrnet_train_step: missing targets");
   cudaStream_t st = (cudaStream_t)stream;
+  CRFR_TRY(pack_all(engine, host_params, io, ws, ws_bytes, st, true, true, true, true, true));
   Net net;
   init_net(net, engine, host_params, host_grads, io, ws, ws_bytes, st, true, true);
+  net.packs_done = true;
   net.forward();
   if (!net.ok()) return net.err;
   const int B = io->batch, S = io->size, Q = S / 4;

@@ -11,6 +11,20 @@ struct CUtensorMap_st;
 int crfr_tmap_encode_bf16(CUtensorMap_st* m, const void* ptr, int rank, const unsigned long long* dims,
                           const unsigned long long* strides_bytes, const unsigned int* box, const char* what);
 
+// layout.cu: dst[t][r][s] (bf16, s padded to s_pad) = src[r * rs + s * ss + t] for a list of jobs, 64 per launch
+#define CRFR_PACK_BATCH 64
+struct crfr_pack_job {
+  const float* src; void* dst;
+  int T, R, S, s_pad;
+  long long rs, ss;
+  int block0, reserved;   // filled by the launcher
+};
+struct crfr_pack_batch {
+  crfr_pack_job job[CRFR_PACK_BATCH];
+  int njobs;
+};
+int crfr_pack_weight_batch(const crfr_pack_job* jobs, int n, cudaStream_t st);
+
 // norm_act.cu
 size_t crfr_norm_ws_bytes(int n, int hw, int c);
 int crfr_norm_finalize(const float* partial, int n, int chunks, int hw, int c, float eps, float* stats,

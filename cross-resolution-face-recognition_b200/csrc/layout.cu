@@ -1,6 +1,7 @@
 // Layout conversions at the nn.Module boundary and weight packing.
 #include "common.cuh"
 #include "crfr.h"
+#include "internal.h"
 
 namespace {
 
@@ -40,7 +41,41 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, bf16* __restri
   dst[i] = __float2bfloat16_rn(v);
 }
 
+// every job of a batch in one launch: block -> job through the (ascending) first-block table in the kernel parameters
+__global__ void pack_weight_batch_kernel(const __grid_constant__ crfr_pack_batch b) {
+  int j = 0;
+  for (int k = 1; k < b.njobs; ++k)
+    if ((int)blockIdx.x >= b.job[k].block0) j = k;
+  const crfr_pack_job& J = b.job[j];
+  const long long i = (long long)((int)blockIdx.x - J.block0) * 256 + threadIdx.x;
+  if (i >= (long long)J.T * J.R * J.s_pad) return;
+  const int s = (int)(i % J.s_pad);
+  const long long q = i / J.s_pad;
+  const int r = (int)(q % J.R), t = (int)(q / J.R);
+  const float v = (s < J.S) ? J.src[r * J.rs + s * J.ss + t] : 0.f;
+  reinterpret_cast<bf16*>(J.dst)[i] = __float2bfloat16_rn(v);
+}
+
 }  // namespace
+
+// internal.h: the weight packs of a whole network program (one per convolution and direction, ~120 per FSRNet step)
+// as ceil(n / 64) launches instead of n
+int crfr_pack_weight_batch(const crfr_pack_job* jobs, int n, cudaStream_t st) {
+  for (int first = 0; first < n; first += CRFR_PACK_BATCH) {
+    crfr_pack_batch b;
+    b.njobs = n - first < CRFR_PACK_BATCH ? n - first : CRFR_PACK_BATCH;
+    int blocks = 0;
+    for (int k = 0; k < b.njobs; ++k) {
+      b.job[k] = jobs[first + k];
+      b.job[k].block0 = blocks;
+      blocks += crfr_cdiv((long long)b.job[k].T * b.job[k].R * b.job[k].s_pad, 256);
+    }
+    pack_weight_batch_kernel<<<blocks, 256, 0, st>>>(b);
+    CRFR_COUNT_LAUNCH();
+    CRFR_LAUNCH_CHECK();
+  }
+  return CRFR_OK;
+}
 
 extern "C" int crfr_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int n, int c, int h, int w, int dst_ld,
                                           int c_zero_to, void* stream) {
