@@ -113,6 +113,28 @@ def test_deconv(cuda, engine):
     assert rel_err(db, br.grad) < F32_TOL
 
 
+@pytest.mark.parametrize("n,c,h,w,ld,zero_to", [(2, 3, 16, 16, 4, 4), (3, 97, 9, 7, 128, 97), (2, 64, 56, 56, 64, 64),
+                                                 (3, 40, 5, 33, 48, 48), (2, 512, 7, 7, 512, 512)])
+def test_layout_conversions(cuda, n, c, h, w, ld, zero_to):
+    """fp32 NCHW <-> bf16 NHWC at the nn.Module boundary (per-pixel kernels for images, tiled transposes for feature
+    maps): exact on bf16-representable data, zero fill of [c, zero_to), channels beyond zero_to left untouched."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(c * h + w)
+    x = bf16_round(torch.randn(n, c, h, w, generator=g))
+    sentinel = 7.0
+    out = torch.full((n, h, w, ld), sentinel, dtype=torch.bfloat16, device="cuda")
+    from crfr_b200 import _lib as L
+    L.call("crfr_nchw_f32_to_nhwc_bf16", ops.ptr(x.cuda()), ops.ptr(out), n, c, h, w, ld, zero_to, ops.stream())
+    torch.cuda.synchronize()
+    ref = x.permute(0, 2, 3, 1)
+    assert torch.equal(out[..., :c].float().cpu(), ref)
+    assert float(out[..., c:zero_to].float().abs().max()) == 0.0 if zero_to > c else True
+    if ld > zero_to:
+        assert torch.equal(out[..., zero_to:].float().cpu(), torch.full((n, h, w, ld - zero_to), sentinel))
+    back = ops.nhwc_to_nchw(out, c)
+    assert torch.equal(back.cpu(), x)
+
+
 def _prelu(x, a):
     return torch.clamp(x, min=0) + a.view(1, -1, 1, 1) * torch.clamp(x, max=0)
 
