@@ -327,6 +327,30 @@ def landmark_heatmap(landmarks, h, w, sigma=1.3):
     return hm
 
 
+def rotate_coeffs(h, w, angles):
+    """Pillow's 16.16 fixed-point affine coefficients of Image.rotate(angle) for every angle: int32 [N, 6] (host)."""
+    out = torch.empty((len(angles), 6), dtype=torch.int32)
+    buf = (C.c_int32 * 6)()
+    for i, a in enumerate(angles):
+        L.call("crfr_rotate_coeffs", h, w, float(a), C.cast(buf, C.c_void_p))
+        out[i] = torch.tensor(list(buf), dtype=torch.int32)
+    return out
+
+
+def augment_u8(src, angles, factors=None):
+    """helen_loader.py:75-104 on the device: src uint8 [N, H, W, C] rotated by angles[i] degrees (PIL Image.rotate) and
+    enhanced with ImageEnhance.Contrast once per column of factors [N, F] (None: rotation only)."""
+    _need_cuda(src)
+    n, h, w, c = src.shape
+    src = src.contiguous()
+    coef = rotate_coeffs(h, w, angles).to(src.device)
+    fac = None if factors is None else torch.as_tensor(factors, dtype=torch.float32).reshape(n, -1).contiguous().to(src.device)
+    dst = torch.empty_like(src)
+    L.call("crfr_augment_u8", ptr(src), n, h, w, c, ptr(coef), ptr(fac), 0 if fac is None else fac.shape[1], ptr(dst),
+           stream())
+    return dst
+
+
 # ---------------------------------------------------------------------------------------------- matcher
 def l2norm_bf16(x):
     _need_cuda(x)

@@ -155,6 +155,17 @@ int crfr_bicubic_tables(int in_size, int out_size, int32_t* host_tab);    /* [ou
 int crfr_bicubic_u8(const uint8_t* src, int n, int ih, int iw, int c, const int32_t* tab_h, const int32_t* tab_w,
                     int oh, int ow, uint8_t* tmp, uint8_t* dst, float* dst_f32, void* stream);
 
+/* ref: the augmentation of HelenLoader.__getitem__ helen_loader.py:75-104 (Pillow, third party): Image.rotate(angle) -
+ * NEAREST, no expand, zero fill: Pillow's 16.16 fixed-point affine gather - followed by one
+ * ImageEnhance.Contrast(img).enhance(f) per factor (blend with the rounded mean luma in float32, truncated for
+ * 0 <= f <= 1, clipped otherwise).  Bit-exact with Pillow 12.2.0.
+ * crfr_rotate_coeffs: the six fixed-point coefficients of one image (HOST, double precision, exactly as Pillow).
+ * crfr_augment_u8: src/dst u8 NHWC [n][h][w][c] (c = 1 or 3, src != dst); coef int32 [n][6] and factors fp32 [n][nfac] on
+ * the device; nfac = 0 rotates only (the parsing map, :103-104). */
+int crfr_rotate_coeffs(int h, int w, double angle_deg, int32_t* host_coef6);
+int crfr_augment_u8(const uint8_t* src, int n, int h, int w, int c, const int32_t* coef, const float* factors, int nfac,
+                    uint8_t* dst, void* stream);
+
 /* ref: HelenLoader.generate_hm / gaussian_k helen_loader.py:118-143 - the landmark heat-map target of the prior loss:
  * hm[n][y][x] = sum_j exp(-((x - lx_j)^2 + (y - ly_j)^2) / (2 sigma^2)), Gaussians in fp64, running sum rounded to fp32
  * after every landmark (as numpy's in-place += on a float32 array).  landmarks fp32 [n][k][2] = (x, y) in heat-map

@@ -206,6 +206,45 @@ def golden_resnet():
     print("resnet34 kd", l_s.item(), l_a.item())
 
 
+def golden_augment():
+    """Image.rotate + ImageEnhance.Contrast (helen_loader.py:75-104) against Pillow itself, bit for bit."""
+    import random
+    from PIL import Image, ImageEnhance
+    from oracle import augment_oracle as AO
+    rng, nrng = random.Random(5), np.random.default_rng(6)
+    d = {}
+    for i, (h, w, c) in enumerate([(28, 28, 3), (33, 40, 1), (56, 56, 3), (112, 112, 1), (128, 128, 3), (224, 224, 3)]):
+        for rep in range(40 if h <= 56 else 6):        # many random draws are checked, the first of each size is stored
+            src = nrng.integers(0, 256, (h, w, c), dtype=np.uint8)
+            ang = rng.uniform(-10, 10) if rep % 4 else rng.uniform(-180, 180)
+            fac = [rng.uniform(0.9, 1.1), rng.uniform(0.8, 1.2), rng.uniform(0.9, 1.1)]
+            im = Image.fromarray(src if c == 3 else src[..., 0])
+            rot = im.rotate(ang)
+            stages = [np.asarray(rot).reshape(h, w, c)]
+            cur = rot
+            for f in fac:
+                cur = ImageEnhance.Contrast(cur).enhance(f)
+                stages.append(np.asarray(cur).reshape(h, w, c))
+            assert np.array_equal(AO.rotate_u8(src, ang), stages[0]), (h, w, c, ang)
+            o = stages[0]
+            for k, f in enumerate(fac):
+                o = AO.contrast_u8(o, f)
+                assert np.array_equal(o, stages[k + 1]), (h, w, c, k, f)
+            assert np.array_equal(AO.augment_u8(src, ang, fac), stages[-1])
+            if rep == 0 and h <= 112:                  # the larger sizes are checked here but not stored (random bytes)
+                d["src%d" % i], d["angle%d" % i], d["fac%d" % i] = src, np.float64(ang), np.array(fac, np.float64)
+                d["rot%d" % i], d["out%d" % i] = stages[0], stages[-1]
+                d["coef%d" % i] = AO.rotate_coeffs(h, w, ang)
+    # interpolation-only and degenerate factors
+    src = nrng.integers(0, 256, (28, 28, 3), dtype=np.uint8)
+    im = Image.fromarray(src)
+    for f in (0.0, 1.0, 0.5, 1.5, -0.25):
+        assert np.array_equal(AO.contrast_u8(src, f), np.asarray(ImageEnhance.Contrast(im).enhance(f))), f
+    d["count"] = np.int64(4)
+    np.savez_compressed(os.path.join(OUT, "augment.npz"), **d)
+    print("augment ok")
+
+
 def golden_heatmap():
     """Landmark heat-map target: HelenLoader.generate_hm (helen_loader.py:118-143) called on the reference's own class
     (matplotlib / scipy.misc, which the module imports but this method does not use, are stubbed)."""
@@ -254,6 +293,6 @@ def golden_ir50():
 if __name__ == "__main__":
     assert R.available(), "reference tree not present"
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["losses", "bicubic", "eval", "fsrnet", "resnet", "ir50", "heatmap"]
+    which = sys.argv[1:] or ["losses", "bicubic", "eval", "fsrnet", "resnet", "ir50", "heatmap", "augment"]
     for w in which:
         globals()["golden_" + w]()

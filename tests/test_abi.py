@@ -58,6 +58,22 @@ def test_bicubic_tables_match_oracle(lib):
         assert np.array_equal(tab[:, 2:2 + kk.shape[1]], kk)
 
 
+def test_rotate_coeffs_match_oracle(lib):
+    """crfr_rotate_coeffs (C: cos / sin rounded to 15 decimals through the decimal string, 16.16 FIX) against the Python
+    restatement of Pillow's Image.rotate matrix - the host part of the augmentation, no GPU needed."""
+    import ctypes as C
+    import random
+    from oracle import augment_oracle as AO
+    rng = random.Random(3)
+    buf = (C.c_int32 * 6)()
+    cases = [(28, 28, 0.0), (28, 28, 360.0), (112, 112, -10.0), (224, 224, 10.0), (33, 40, 180.0), (17, 5, -725.5)]
+    cases += [(rng.choice([28, 112, 128, 224, 31]), rng.choice([28, 112, 128, 224, 57]), rng.uniform(-400, 400))
+              for _ in range(500)]
+    for h, w, ang in cases:
+        assert lib.crfr_rotate_coeffs(h, w, ang, C.cast(buf, C.c_void_p)) == 0
+        assert list(buf) == AO.rotate_coeffs(h, w, ang).tolist(), (h, w, ang)
+
+
 def test_workspace_sizing_is_monotonic(lib):
     a = lib.crfr_fsrnet_workspace_bytes(2, 64, 1)
     b = lib.crfr_fsrnet_workspace_bytes(4, 64, 1)

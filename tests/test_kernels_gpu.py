@@ -135,6 +135,31 @@ def test_layout_conversions(cuda, n, c, h, w, ld, zero_to):
     assert torch.equal(back.cpu(), x)
 
 
+@pytest.mark.parametrize("n,h,w,c", [(16, 128, 128, 3), (5, 112, 112, 1), (3, 33, 40, 3), (2, 224, 224, 3)])
+def test_augment_u8_bit_exact(cuda, golden_dir, n, h, w, c):
+    """Rotation + contrast enhancements of helen_loader.py:75-104 on the device: bit-exact with the oracle (pinned to
+    Pillow) on random batches, with the stored Pillow vectors, and for the degenerate factors."""
+    import random
+    from oracle import augment_oracle as AO
+    ops = _ops()
+    rng, nrng = random.Random(n * h + c), np.random.default_rng(h + w)
+    src = nrng.integers(0, 256, (n, h, w, c), dtype=np.uint8)
+    angles = [rng.uniform(-10, 10) for _ in range(n)]
+    angles[0] = 0.0
+    fac = np.array([[rng.uniform(0.9, 1.1), rng.uniform(0.8, 1.2), rng.uniform(0.9, 1.1)] for _ in range(n)])
+    fac[-1] = [0.0, 1.0, 1.5]
+    out = ops.augment_u8(torch.from_numpy(src).cuda(), angles, fac).cpu().numpy()
+    rot = ops.augment_u8(torch.from_numpy(src).cuda(), angles).cpu().numpy()
+    for i in range(n):
+        assert np.array_equal(rot[i], AO.rotate_u8(src[i], angles[i])), i
+        assert np.array_equal(out[i], AO.augment_u8(src[i], angles[i], fac[i])), i
+    g = np.load(os.path.join(golden_dir, "augment.npz"))
+    for i in range(int(g["count"])):
+        s_, ang, f_ = g["src%d" % i], float(g["angle%d" % i]), g["fac%d" % i]
+        o = ops.augment_u8(torch.from_numpy(s_[None]).cuda(), [ang], f_[None]).cpu().numpy()[0]
+        assert np.array_equal(o, g["out%d" % i]), i
+
+
 def _prelu(x, a):
     return torch.clamp(x, min=0) + a.view(1, -1, 1, 1) * torch.clamp(x, max=0)
 

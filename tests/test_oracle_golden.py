@@ -184,3 +184,22 @@ def test_landmark_heatmap_oracle_against_reference_fixture(golden_dir):
     g = _load(golden_dir, "heatmap.npz")
     for l, ref in zip(g["landmarks"], g["hm"]):
         assert np.array_equal(BO.landmark_heatmap(l, 32, 32, 1.3), ref)
+
+
+def test_augment_oracle_against_pillow_fixture(golden_dir):
+    """Image.rotate + ImageEnhance.Contrast (helen_loader.py:75-104): the restatement against vectors Pillow produced."""
+    from oracle import augment_oracle as AO
+    g = np.load(os.path.join(golden_dir, "augment.npz"))
+    for i in range(int(g["count"])):
+        src, ang, fac = g["src%d" % i], float(g["angle%d" % i]), g["fac%d" % i]
+        h, w = src.shape[:2]
+        assert np.array_equal(AO.rotate_coeffs(h, w, ang), g["coef%d" % i])
+        assert np.array_equal(AO.rotate_u8(src, ang), g["rot%d" % i])
+        assert np.array_equal(AO.augment_u8(src, ang, fac), g["out%d" % i])
+    img = np.arange(5 * 7 * 3, dtype=np.uint8).reshape(5, 7, 3)
+    assert np.array_equal(AO.rotate_u8(img, 0.0), img) and np.array_equal(AO.rotate_u8(img, 720.0), img)
+    assert np.array_equal(AO.contrast_u8(img, 1.0), img)
+    assert np.array_equal(AO.contrast_u8(img, 0.0), np.full_like(img, AO.luma_mean(img)))
+    lm = np.array([[56.0, 56.0], [66.0, 56.0]])
+    out = AO.rotate_landmarks(lm, 90.0, 56.0)         # rotate_matrix(-90): (x, y) - c -> (y', -x') ... about the centre
+    assert np.allclose(out[0], [56.0, 56.0]) and np.allclose(out[1], [56.0, 46.0])
