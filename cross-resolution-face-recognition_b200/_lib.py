@@ -71,6 +71,7 @@ SIGNATURES = {
     "crfr_landmark_heatmap": (ci, [vp, ci, ci, cf, ci, ci, vp, vp]),
     "crfr_rotate_coeffs": (ci, [ci, ci, C.c_double, vp]),
     "crfr_augment_u8": (ci, [vp, ci, ci, ci, ci, vp, vp, ci, vp, vp]),
+    "crfr_crop_u8": (ci, [vp, ci, ci, ci, ci, vp, ci, ci, vp, vp]),
     "crfr_l2norm_bf16": (ci, [vp, vp, cll, ci, vp]),
     "crfr_cosine_topk": (ci, [ci, vp, vp, ci, cll, ci, ci, ci, vp, vp, vp, csz, vp]),
     "crfr_cosine_topk_workspace_bytes": (csz, [ci, cll, ci, ci]),

@@ -78,6 +78,19 @@ augment_kernel(const uint8_t* __restrict__ src, int h, int w, int c, const int* 
   }
 }
 
+// per-image window copy: dst[n][y][x][:] = src[n][off_y[n] + y][off_x[n] + x][:]; one thread per output byte
+__global__ void crop_kernel(const uint8_t* __restrict__ src, int h, int w, int c, const int* __restrict__ off, int oh, int ow,
+                            uint8_t* __restrict__ dst, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int row = ow * c;
+  const int xb = (int)(i % row);
+  const long long q = i / row;
+  const int y = (int)(q % oh);
+  const long long n = q / oh;
+  dst[i] = src[((n * h + off[2 * n] + y) * w + off[2 * n + 1]) * c + xb];
+}
+
 // Python's round(x, 15): correctly rounded 15-decimal string, back to the nearest double
 double round15(double x) {
   char buf[64];
@@ -120,6 +133,17 @@ extern "C" int crfr_augment_u8(const uint8_t* src, int n, int h, int w, int c, c
   CRFR_CHECK_ARG(src != dst, "augment_u8: the rotation is a gather, it cannot run in place");
   CRFR_CHECK_ARG((long long)h * w * 3 < (1ll << 31) / 2, "augment_u8: image too large");
   augment_kernel<<<n, kT, 0, (cudaStream_t)stream>>>(src, h, w, c, coef, factors, nfac, dst);
+  CRFR_COUNT_LAUNCH();
+  CRFR_LAUNCH_CHECK();
+  return CRFR_OK;
+}
+
+extern "C" int crfr_crop_u8(const uint8_t* src, int n, int h, int w, int c, const int32_t* offsets_yx, int oh, int ow,
+                            uint8_t* dst, void* stream) {
+  CRFR_CHECK_ARG(src && dst && offsets_yx && n > 0 && c > 0 && oh > 0 && ow > 0 && oh <= h && ow <= w,
+                 "crop_u8: bad argument (window %dx%d of %dx%d)", oh, ow, h, w);
+  const long long total = (long long)n * oh * ow * c;
+  crop_kernel<<<crfr_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(src, h, w, c, offsets_yx, oh, ow, dst, total);
   CRFR_COUNT_LAUNCH();
   CRFR_LAUNCH_CHECK();
   return CRFR_OK;

@@ -351,6 +351,18 @@ def augment_u8(src, angles, factors=None):
     return dst
 
 
+def crop_u8(src, offsets_yx, out_h, out_w):
+    """FHN_loader.py:61-63: per-image windows src[i, y0:y0+out_h, x0:x0+out_w] with (y0, x0) = offsets_yx[i]."""
+    _need_cuda(src)
+    n, h, w, c = src.shape
+    off = torch.as_tensor(offsets_yx, dtype=torch.int32).reshape(n, 2)
+    if int(off.min()) < 0 or int(off[:, 0].max()) + out_h > h or int(off[:, 1].max()) + out_w > w:
+        raise ValueError("crop_u8: window outside the image")
+    dst = torch.empty((n, out_h, out_w, c), dtype=torch.uint8, device=src.device)
+    L.call("crfr_crop_u8", ptr(src.contiguous()), n, h, w, c, ptr(off.to(src.device)), out_h, out_w, ptr(dst), stream())
+    return dst
+
+
 # ---------------------------------------------------------------------------------------------- matcher
 def l2norm_bf16(x):
     _need_cuda(x)

@@ -165,6 +165,11 @@ int crfr_bicubic_u8(const uint8_t* src, int n, int ih, int iw, int c, const int3
 int crfr_rotate_coeffs(int h, int w, double angle_deg, int32_t* host_coef6);
 int crfr_augment_u8(const uint8_t* src, int n, int h, int w, int c, const int32_t* coef, const float* factors, int nfac,
                     uint8_t* dst, void* stream);
+/* ref: the random crop of SUPER_RESOLUTION/FHN_loader.py:61-63,92 (Image.crop((nw, nh, nw + 112, nh + 112))):
+ * dst[n][y][x] = src[n][off[n][0] + y][off[n][1] + x]; offsets int32 [n][2] = (nh, nw) on the device; the caller keeps the
+ * windows inside the image (random.randint(0, 128 - 112)). */
+int crfr_crop_u8(const uint8_t* src, int n, int h, int w, int c, const int32_t* offsets_yx, int oh, int ow, uint8_t* dst,
+                 void* stream);
 
 /* ref: HelenLoader.generate_hm / gaussian_k helen_loader.py:118-143 - the landmark heat-map target of the prior loss:
  * hm[n][y][x] = sum_j exp(-((x - lx_j)^2 + (y - ly_j)^2) / (2 sigma^2)), Gaussians in fp64, running sum rounded to fp32

@@ -160,6 +160,40 @@ def test_augment_u8_bit_exact(cuda, golden_dir, n, h, w, c):
         assert np.array_equal(o, g["out%d" % i]), i
 
 
+def test_fhn_pipeline_rotate_crop_resample_enhance(cuda):
+    """SUPER_RESOLUTION/FHN_loader.py:55-86 on the device, stage by stage against the Pillow-pinned oracles (bit-exact):
+    rotate, random 112-crop, LR synthesis (down by 2/4/8, bicubic back up), three contrast enhancements on both images."""
+    import random
+    from oracle import augment_oracle as AO
+    from oracle import bicubic_oracle as BO
+    ops = _ops()
+    rng, nrng = random.Random(12), np.random.default_rng(13)
+    n = 6
+    src = nrng.integers(0, 256, (n, 128, 128, 3), dtype=np.uint8)
+    angles = [rng.uniform(-20, 20) for _ in range(n)]
+    offs = [(rng.randint(0, 16), rng.randint(0, 16)) for _ in range(n)]
+    fac = np.array([[rng.uniform(0.93, 1.07), rng.uniform(0.92, 1.08), rng.uniform(0.93, 1.07)] for _ in range(n)])
+    scales = [2, 4, 8, 8, 4, 2]
+    rot = ops.augment_u8(torch.from_numpy(src).cuda(), angles)
+    sr = ops.crop_u8(rot, offs, 112, 112)
+    sr_np = sr.cpu().numpy()
+    zeros = [0.0] * n
+    hr = ops.augment_u8(sr, zeros, fac).cpu().numpy()
+    for i in range(n):
+        ref_sr = AO.rotate_u8(src[i], angles[i])[offs[i][0]:offs[i][0] + 112, offs[i][1]:offs[i][1] + 112]
+        assert np.array_equal(sr_np[i], ref_sr), i
+        assert np.array_equal(hr[i], AO.augment_u8(ref_sr, 0.0, fac[i])), i
+        s_ = 128 // scales[i]
+        small, _ = ops.bicubic_u8(sr[i:i + 1], s_, s_)
+        lr, _ = ops.bicubic_u8(small, 112, 112)
+        ref_lr = BO.bicubic_u8(BO.bicubic_u8(ref_sr, s_, s_), 112, 112)
+        assert np.array_equal(lr[0].cpu().numpy(), ref_lr), i
+        lr_e = ops.augment_u8(lr, [0.0], fac[i:i + 1]).cpu().numpy()[0]
+        assert np.array_equal(lr_e, AO.augment_u8(ref_lr, 0.0, fac[i])), i
+    with pytest.raises(ValueError):
+        ops.crop_u8(rot, [(20, 0)] * n, 112, 112)
+
+
 def _prelu(x, a):
     return torch.clamp(x, min=0) + a.view(1, -1, 1, 1) * torch.clamp(x, max=0)
 
