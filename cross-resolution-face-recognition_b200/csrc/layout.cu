@@ -85,10 +85,13 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, bf16* __restri
 
 // every job of a batch in one launch: block -> job through the (ascending) first-block table in the kernel parameters
 __global__ void pack_weight_batch_kernel(const __grid_constant__ crfr_pack_batch b) {
-  int j = 0;
-  for (int k = 1; k < b.njobs; ++k)
-    if ((int)blockIdx.x >= b.job[k].block0) j = k;
-  const crfr_pack_job& J = b.job[j];
+  int lo = 0, hi = b.njobs - 1;   // largest job whose first block is <= blockIdx.x (binary search: the table is sorted)
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if ((int)blockIdx.x >= b.job[mid].block0) lo = mid;
+    else hi = mid - 1;
+  }
+  const crfr_pack_job& J = b.job[lo];
   const long long i = (long long)((int)blockIdx.x - J.block0) * 256 + threadIdx.x;
   if (i >= (long long)J.T * J.R * J.s_pad) return;
   const int s = (int)(i % J.s_pad);
