@@ -34,7 +34,9 @@ namespace {
 
 constexpr int kConsumers = 256;
 constexpr int kThreads = kConsumers + 32;   // + one producer warp
-constexpr int kTileBytes = 4096;            // one map, one stage: P pixels x c channels x 2 B (one pixel per consumer)
+constexpr int kTileBytes = 4096;            // one map, one stage, one pixel per consumer: 256 x 16 B; passes that stream
+                                            // two maps use two pixels per consumer and stage (8 KB tiles): half the
+                                            // per-stage barrier / address work in loops that are close to issue bound
 constexpr int kRingBytes = 88 * 1024;       // stage ring per CTA (two CTAs per SM)
 constexpr int kMaxStages = 16;
 constexpr int kScratchBytes = 8192;         // [lanes][c] floats = 256 x 8 x 4 B
@@ -44,7 +46,7 @@ struct Maps {
 };
 
 struct StreamArgs {
-  int ntensors, stages, ring_bytes;
+  int ntensors, stages, ring_bytes, tile_bytes;
   int hw, c, nimg, parts;
   long long total;                  // n x hw pixels
   int relu, has_b, has_res, recompute;
@@ -140,7 +142,7 @@ __device__ __forceinline__ Setup setup(const StreamArgs& a, uint8_t* smem_raw) {
 __device__ __forceinline__ void produce(const Maps& maps, const StreamArgs& a, const Setup& u, int P) {
   const bool leader = elect_one();
   const int subs = a.c >> 6;
-  const uint32_t stage_bytes = a.ntensors * kTileBytes;
+  const uint32_t stage_bytes = a.ntensors * a.tile_bytes;
   int s = 0;
   uint32_t phase = 1;
   int r = u.r_begin;
@@ -158,7 +160,7 @@ __device__ __forceinline__ void produce(const Maps& maps, const StreamArgs& a, c
           for (int sub = 0; sub < subs; ++sub)
             asm volatile(
                 "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                ::"r"(stage + t * kTileBytes + sub * (P * 128)), "l"(&maps.t[t]), "r"(fb), "r"(sub * 64), "r"(r + k * P)
+                ::"r"(stage + t * a.tile_bytes + sub * (P * 128)), "l"(&maps.t[t]), "r"(fb), "r"(sub * 64), "r"(r + k * P)
                 : "memory");
       }
       __syncwarp();
@@ -174,11 +176,15 @@ __device__ __forceinline__ void produce(const Maps& maps, const StreamArgs& a, c
 // segment, rounding and packing of dz in one cvt.rn.bf16x2.
 template <bool HAS_B, bool HAS_RES>
 __device__ __forceinline__ void reduce_consume(const StreamArgs& a, const Setup& u, int P) {
+  constexpr int PX = (HAS_B || HAS_RES) ? 1 : 2;   // pixels per consumer and stage
+  constexpr int kTile = PX * kTileBytes;
   const int c = a.c, groups = c >> 3, lanes = kConsumers / groups;
   const int cg = threadIdx.x % groups, lane = threadIdx.x / groups;
   const bool act = a.relu || a.alpha;
-  const uint32_t stage_bytes = a.ntensors * kTileBytes;
-  const uint32_t my_off = sw128_offset(cg, lane, P);
+  const uint32_t stage_bytes = a.ntensors * kTile;
+  uint32_t my_off[PX];
+#pragma unroll
+  for (int h = 0; h < PX; ++h) my_off[h] = sw128_offset(cg, lane + h * lanes, P);
   constexpr int ty = HAS_B ? 2 : 1, tr = ty + 1;   // tensor order in a stage: dout_a, [dout_b], y, [res]
   int s = 0;
   uint32_t phase = 0;
@@ -211,32 +217,35 @@ __device__ __forceinline__ void reduce_consume(const StreamArgs& a, const Setup&
     const long long ostep = (long long)P * a.out_ld;
     for (int k = 0; k < nst; ++k) {
       mbar_wait_a(u.full + 8 * s, phase);
-      const uint32_t addr = u.ring + s * stage_bytes + my_off;
-      if (k * P + lane < seg) {
-        const uint4 A = lds128(addr);
-        uint4 B, R;
-        if (HAS_B) B = lds128(addr + kTileBytes);
-        const uint4 Y = lds128(addr + ty * kTileBytes);
-        if (HAS_RES) R = lds128(addr + tr * kTileBytes);
-        uint4 O;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float2 g = up2(word(A, i));
-          if (HAS_B) g = __fadd2_rn(g, up2(word(B, i)));
-          const float2 f = up2(word(Y, i));
-          if (act) {
-            float2 z = __ffma2_rn(f, sc[i], sh[i]);
-            if (HAS_RES) z = __fadd2_rn(z, up2(word(R, i)));
-            if (!(z.x > 0.f)) { acc2[i].x = fmaf(g.x, z.x, acc2[i].x); g.x *= al[i].x; }
-            if (!(z.y > 0.f)) { acc2[i].y = fmaf(g.y, z.y, acc2[i].y); g.y *= al[i].y; }
+      for (int h = 0; h < PX; ++h) {
+        const uint32_t addr = u.ring + s * stage_bytes + my_off[h];
+        if (k * P + lane + h * lanes < seg) {
+          const uint4 A = lds128(addr);
+          uint4 B, R;
+          if (HAS_B) B = lds128(addr + kTile);
+          const uint4 Y = lds128(addr + ty * kTile);
+          if (HAS_RES) R = lds128(addr + tr * kTile);
+          uint4 O;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float2 g = up2(word(A, i));
+            if (HAS_B) g = __fadd2_rn(g, up2(word(B, i)));
+            const float2 f = up2(word(Y, i));
+            if (act) {
+              float2 z = __ffma2_rn(f, sc[i], sh[i]);
+              if (HAS_RES) z = __fadd2_rn(z, up2(word(R, i)));
+              if (!(z.x > 0.f)) { acc2[i].x = fmaf(g.x, z.x, acc2[i].x); g.x *= al[i].x; }
+              if (!(z.y > 0.f)) { acc2[i].y = fmaf(g.y, z.y, acc2[i].y); g.y *= al[i].y; }
+            }
+            const uint32_t w = pk2(g);
+            set_word(O, i, w);
+            const float2 d = up2(w);
+            acc0[i] = __fadd2_rn(acc0[i], d);
+            acc1[i] = __ffma2_rn(d, f, acc1[i]);
           }
-          const uint32_t w = pk2(g);
-          set_word(O, i, w);
-          const float2 d = up2(w);
-          acc0[i] = __fadd2_rn(acc0[i], d);
-          acc1[i] = __ffma2_rn(d, f, acc1[i]);
+          if (store) *reinterpret_cast<uint4*>(optr + (long long)h * lanes * a.out_ld) = O;
         }
-        if (store) *reinterpret_cast<uint4*>(optr) = O;
       }
       optr += ostep;
       __syncwarp();
@@ -283,7 +292,7 @@ __device__ __forceinline__ void reduce_consume(const StreamArgs& a, const Setup&
 __global__ void __launch_bounds__(kThreads, 2)
 norm_bwd_reduce_stream_kernel(const __grid_constant__ Maps maps, const __grid_constant__ StreamArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  const int P = kTileBytes / (2 * a.c);             // pixels per stage = pixel lanes of the consumers
+  const int P = a.tile_bytes / (2 * a.c);           // pixels per stage = pixel lanes of the consumers x 1 or 2
   const Setup u = setup(a, smem_raw);
   if ((threadIdx.x >> 5) == kConsumers / 32) {
     produce(maps, a, u, P);
@@ -303,8 +312,9 @@ norm_bwd_reduce_stream_kernel(const __grid_constant__ Maps maps, const __grid_co
 __global__ void __launch_bounds__(kThreads, 2)
 norm_bwd_apply_stream_kernel(const __grid_constant__ Maps maps, const __grid_constant__ StreamArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  const int c = a.c, groups = c >> 3;
-  const int P = kTileBytes / (2 * c);
+  constexpr int PX = 2, kTile = PX * kTileBytes;   // two maps per stage: two pixels per consumer and stage
+  const int c = a.c, groups = c >> 3, lanes = kConsumers / groups;
+  const int P = kTile / (2 * c);
   const Setup u = setup(a, smem_raw);
   if ((threadIdx.x >> 5) == kConsumers / 32) {
     produce(maps, a, u, P);
@@ -326,8 +336,10 @@ norm_bwd_apply_stream_kernel(const __grid_constant__ Maps maps, const __grid_con
   }
   const int cg = threadIdx.x % groups, lane = threadIdx.x / groups;
   const bool redo = a.recompute && (a.relu || a.alpha);
-  const uint32_t stage_bytes = 2 * kTileBytes;
-  const uint32_t my_off = sw128_offset(cg, lane, P);
+  const uint32_t stage_bytes = 2 * kTile;
+  uint32_t my_off[PX];
+#pragma unroll
+  for (int h = 0; h < PX; ++h) my_off[h] = sw128_offset(cg, lane + h * lanes, P);
   int s = 0;
   uint32_t phase = 0;
   int r = u.r_begin;
@@ -361,23 +373,26 @@ norm_bwd_apply_stream_kernel(const __grid_constant__ Maps maps, const __grid_con
     const long long ostep = (long long)P * a.out_ld;
     for (int k = 0; k < nst; ++k) {
       mbar_wait_a(u.full + 8 * s, phase);
-      const uint32_t addr = u.ring + s * stage_bytes + my_off;
-      if (k * P + lane < seg) {
-        const uint4 D = lds128(addr), Y = lds128(addr + kTileBytes);
-        uint4 O;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float2 d = up2(word(D, i));
-          const float2 f = up2(word(Y, i));
-          if (redo) {
-            const float2 z = __ffma2_rn(f, ca[i], sh[i]);
-            if (!(z.x > 0.f)) d.x *= al[i].x;
-            if (!(z.y > 0.f)) d.y *= al[i].y;
-            d = up2(pk2(d));
+      for (int h = 0; h < PX; ++h) {
+        const uint32_t addr = u.ring + s * stage_bytes + my_off[h];
+        if (k * P + lane + h * lanes < seg) {
+          const uint4 D = lds128(addr), Y = lds128(addr + kTile);
+          uint4 O;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float2 d = up2(word(D, i));
+            const float2 f = up2(word(Y, i));
+            if (redo) {
+              const float2 z = __ffma2_rn(f, ca[i], sh[i]);
+              if (!(z.x > 0.f)) d.x *= al[i].x;
+              if (!(z.y > 0.f)) d.y *= al[i].y;
+              d = up2(pk2(d));
+            }
+            set_word(O, i, pk2(__ffma2_rn(ca[i], d, __ffma2_rn(cb[i], f, cc[i]))));
           }
-          set_word(O, i, pk2(__ffma2_rn(ca[i], d, __ffma2_rn(cb[i], f, cc[i]))));
+          st_stream(optr + (long long)h * lanes * a.out_ld, O);
         }
-        st_stream(optr, O);
       }
       optr += ostep;
       __syncwarp();
@@ -454,7 +469,9 @@ int crfr_norm_bwd_reduce_stream(const void* da, int da_ld, const void* db, int d
   const bool act = relu || alpha;
   Maps maps;
   StreamArgs a = {};
-  const int P = kTileBytes / (2 * c);
+  const int ntensors = 2 + (db ? 1 : 0) + ((act && res) ? 1 : 0);
+  a.tile_bytes = (ntensors <= 2 ? 2 : 1) * kTileBytes;
+  const int P = a.tile_bytes / (2 * c);              // box height = pixels per stage
   const long long npix = (long long)n * hw;
   int t = 0;
   CRFR_TRY(encode_map(&maps.t[t++], da, da_ld, c, npix, P, "dout_a"));
@@ -464,7 +481,7 @@ int crfr_norm_bwd_reduce_stream(const void* da, int da_ld, const void* db, int d
   for (int i = t; i < 4; ++i) maps.t[i] = maps.t[0];
   a.ntensors = t;
   a.ring_bytes = kRingBytes;
-  a.stages = a.ring_bytes / (t * kTileBytes);
+  a.stages = a.ring_bytes / (t * a.tile_bytes);
   if (a.stages > kMaxStages) a.stages = kMaxStages;
   a.hw = hw; a.c = c; a.nimg = n; a.parts = crfr_norm_stream_parts(n, hw, c); a.total = npix;
   a.relu = relu; a.has_b = db != nullptr; a.has_res = act && res != nullptr;
@@ -484,14 +501,15 @@ int crfr_norm_bwd_apply_stream(const void* dsrc, int dsrc_ld, int recompute, con
                                float* dalpha, int n, int hw, int c, cudaStream_t st) {
   Maps maps;
   StreamArgs a = {};
-  const int P = kTileBytes / (2 * c);
+  const int P = 2 * kTileBytes / (2 * c);            // two maps per stage: 8 KB tiles, two pixels per consumer
   const long long npix = (long long)n * hw;
   CRFR_TRY(encode_map(&maps.t[0], dsrc, dsrc_ld, c, npix, P, recompute ? "dout" : "dz"));
   CRFR_TRY(encode_map(&maps.t[1], y, y_ld, c, npix, P, "y"));
   maps.t[2] = maps.t[3] = maps.t[0];
   a.ntensors = 2;
   a.ring_bytes = kRingBytes;
-  a.stages = a.ring_bytes / (2 * kTileBytes);
+  a.tile_bytes = 2 * kTileBytes;
+  a.stages = a.ring_bytes / (2 * a.tile_bytes);
   if (a.stages > kMaxStages) a.stages = kMaxStages;
   a.hw = hw; a.c = c; a.nimg = n; a.total = npix;
   a.relu = relu; a.recompute = recompute;
