@@ -22,10 +22,15 @@ extern "C" int crfr_version(void) { return 100; }
 extern "C" unsigned long long crfr_launch_count(void) { return g_crfr_launches; }
 
 void crfr_norm_set_impl(int v);   // norm_act.cu
+void crfr_norm_set_fwd_stream(int v);
 extern "C" int crfr_set_option(const char* name, int value) {
   CRFR_CHECK_ARG(name, "set_option: null name");
   if (!strcmp(name, "norm_bwd_impl")) {
     crfr_norm_set_impl(value);
+    return CRFR_OK;
+  }
+  if (!strcmp(name, "norm_fwd_stream")) {
+    crfr_norm_set_fwd_stream(value);
     return CRFR_OK;
   }
   crfr_set_error("set_option: unknown option '%s'", name);

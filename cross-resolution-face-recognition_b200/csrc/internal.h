@@ -43,6 +43,10 @@ int crfr_norm_bwd_apply_stream(const void* dsrc, int dsrc_ld, int recompute, con
                                const float* alpha, int relu, void* dy, int dy_ld, float* dgamma, float* dbeta,
                                float* dalpha, int n, int hw, int c, cudaStream_t st);
 
+int crfr_norm_fwd_stream(const void* y, int y_ld, const float* stats, const float* gamma, const float* beta,
+                         const float* alpha, int relu, const void* res, int res_ld, void* out, int out_ld, int n, int hw,
+                         int c, cudaStream_t st);
+
 // direct_conv.cu
 int crfr_direct_gather(int down, int n, int bh, int bw, int sh, int sw, int k, int stride, int pad, const void* src,
                        int src_ld, const void* w, int R, int s_pad, const float* bias, void* y, int y_ld,

@@ -392,6 +392,7 @@ int env_impl() {
   }
   return v;
 }
+int g_fwd_stream = 1;        // crfr_set_option("norm_fwd_stream", 0 / 1): register-staged / TMA-fed forward pass (norm_stream.cu)
 int g_impl_override = -1;   // crfr_set_option("norm_bwd_impl", 0 / 1), -1 = environment / default
 
 // BatchNorm buffer maintenance (one thread per channel)
@@ -462,6 +463,7 @@ extern "C" int crfr_bn_running_to_stats(const float* running_mean, const float* 
 extern "C" size_t crfr_norm_workspace_bytes(int n, int hw, int c) { return crfr_norm_ws_bytes(n, hw, c); }
 
 void crfr_norm_set_impl(int v) { g_impl_override = v; }
+void crfr_norm_set_fwd_stream(int v) { g_fwd_stream = v; }
 
 extern "C" int crfr_norm_stats(const void* y, int n, int hw, int c, int ld, float eps, float* stats, void* ws,
                                size_t ws_bytes, void* stream) {
@@ -489,6 +491,13 @@ extern "C" int crfr_norm_act_fwd(const void* y, int y_ld, const float* stats, co
   CRFR_CHECK_ARG(y && stats && out && n > 0 && hw > 0, "norm_act_fwd: bad argument");
   CRFR_CHECK_ARG(channels_ok(c) && y_ld >= c && out_ld >= c && ((y_ld | out_ld | res_ld) & 7) == 0,
                  "norm_act_fwd: unsupported channels %d", c);
+  {
+    const void* views[3] = {y, res, out};
+    const int lds[3] = {y_ld, res_ld, out_ld};
+    if (g_fwd_stream && crfr_norm_stream_supported(c, (long long)n * hw, views, lds, 3))
+      return crfr_norm_fwd_stream(y, y_ld, stats, gamma, beta, alpha, relu, res, res_ld, out, out_ld, n, hw, c,
+                                  (cudaStream_t)stream);
+  }
   ChunkPlan pl = plan_chunks(n, hw);
   norm_act_fwd_kernel<<<dim3(pl.chunks, n), kThreads, 0, (cudaStream_t)stream>>>(
       (const bf16*)y, y_ld, stats, gamma, beta, alpha, relu, (const bf16*)res, res_ld, (bf16*)out, out_ld, hw, c,

@@ -403,6 +403,80 @@ norm_bwd_apply_stream_kernel(const __grid_constant__ Maps maps, const __grid_con
   }
 }
 
+// forward: out = act(gamma * (y - mean) * rstd + beta (+ res)), one or two maps in, one out; same ring, two pixels per
+// consumer and stage
+__global__ void __launch_bounds__(kThreads, 2)
+norm_fwd_stream_kernel(const __grid_constant__ Maps maps, const __grid_constant__ StreamArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  constexpr int PX = 2, kTile = PX * kTileBytes;
+  const int c = a.c, groups = c >> 3, lanes = kConsumers / groups;
+  const int P = kTile / (2 * c);
+  const Setup u = setup(a, smem_raw);
+  if ((threadIdx.x >> 5) == kConsumers / 32) {
+    produce(maps, a, u, P);
+    return;
+  }
+  const int cg = threadIdx.x % groups, lane = threadIdx.x / groups;
+  const bool has_res = a.has_res != 0;
+  const uint32_t stage_bytes = a.ntensors * kTile;
+  uint32_t my_off[PX];
+#pragma unroll
+  for (int h = 0; h < PX; ++h) my_off[h] = sw128_offset(cg, lane + h * lanes, P);
+  int s = 0;
+  uint32_t phase = 0;
+  int r = u.r_begin;
+  while (r < u.r_end) {
+    const int img = r / a.hw, off = r - img * a.hw;
+    const int seg = min(a.hw - off, u.r_end - r);
+    const int nst = (seg + P - 1) / P;
+    float2 sc[4], sh[4], al[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float t[6];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int ch = cg * 8 + 2 * i + e;
+        const float mu = a.stats[2 * (img * c + ch)], rs = a.stats[2 * (img * c + ch) + 1];
+        t[e] = (a.gamma ? a.gamma[ch] : 1.f) * rs;
+        t[2 + e] = (a.beta ? a.beta[ch] : 0.f) - mu * t[e];
+        t[4 + e] = a.relu ? 0.f : (a.alpha ? a.alpha[ch] : 1.f);
+      }
+      sc[i] = make_float2(t[0], t[1]);
+      sh[i] = make_float2(t[2], t[3]);
+      al[i] = make_float2(t[4], t[5]);
+    }
+    bf16* optr = a.out + ((long long)r + lane) * a.out_ld + cg * 8;
+    const long long ostep = (long long)P * a.out_ld;
+    for (int k = 0; k < nst; ++k) {
+      mbar_wait_a(u.full + 8 * s, phase);
+#pragma unroll
+      for (int h = 0; h < PX; ++h) {
+        const uint32_t addr = u.ring + s * stage_bytes + my_off[h];
+        if (k * P + lane + h * lanes < seg) {
+          const uint4 Y = lds128(addr);
+          uint4 R;
+          if (has_res) R = lds128(addr + kTile);
+          uint4 O;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float2 z = __ffma2_rn(up2(word(Y, i)), sc[i], sh[i]);
+            if (has_res) z = __fadd2_rn(z, up2(word(R, i)));
+            if (!(z.x > 0.f)) z.x *= al[i].x;
+            if (!(z.y > 0.f)) z.y *= al[i].y;
+            set_word(O, i, pk2(z));
+          }
+          st_stream(optr + (long long)h * lanes * a.out_ld, O);
+        }
+      }
+      optr += ostep;
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) mbar_arrive_a(u.empty + 8 * s);
+      if (++s == a.stages) { s = 0; phase ^= 1; }
+    }
+    r += seg;
+  }
+}
+
 constexpr size_t kSmemBytes = 1024 /*align*/ + kRingBytes + kScratchBytes + 2 * kMaxStages * sizeof(uint64_t);
 
 int encode_map(CUtensorMap* m, const void* ptr, int ld, int c, long long npix, int P, const char* what) {
@@ -439,6 +513,7 @@ int set_attrs() {
   if (!done) {
     CRFR_CUDA(cudaFuncSetAttribute(norm_bwd_reduce_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     CRFR_CUDA(cudaFuncSetAttribute(norm_bwd_apply_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+    CRFR_CUDA(cudaFuncSetAttribute(norm_fwd_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
     done = true;
   }
   return CRFR_OK;
@@ -519,6 +594,33 @@ int crfr_norm_bwd_apply_stream(const void* dsrc, int dsrc_ld, int recompute, con
   a.dgamma = dgamma; a.dbeta = dbeta; a.dalpha = dalpha;
   CRFR_TRY(set_attrs());
   norm_bwd_apply_stream_kernel<<<grid_for(npix, c), kThreads, kSmemBytes, st>>>(maps, a);
+  CRFR_COUNT_LAUNCH();
+  CRFR_LAUNCH_CHECK();
+  return CRFR_OK;
+}
+
+int crfr_norm_fwd_stream(const void* y, int y_ld, const float* stats, const float* gamma, const float* beta,
+                         const float* alpha, int relu, const void* res, int res_ld, void* out, int out_ld, int n, int hw,
+                         int c, cudaStream_t st) {
+  Maps maps;
+  StreamArgs a = {};
+  const int P = 2 * kTileBytes / (2 * c);
+  const long long npix = (long long)n * hw;
+  CRFR_TRY(encode_map(&maps.t[0], y, y_ld, c, npix, P, "y"));
+  if (res) CRFR_TRY(encode_map(&maps.t[1], res, res_ld, c, npix, P, "residual"));
+  else maps.t[1] = maps.t[0];
+  maps.t[2] = maps.t[3] = maps.t[0];
+  a.ntensors = res ? 2 : 1;
+  a.ring_bytes = kRingBytes;
+  a.tile_bytes = 2 * kTileBytes;
+  a.stages = a.ring_bytes / (a.ntensors * a.tile_bytes);
+  if (a.stages > kMaxStages) a.stages = kMaxStages;
+  a.hw = hw; a.c = c; a.nimg = n; a.total = npix;
+  a.relu = relu; a.has_res = res != nullptr;
+  a.stats = stats; a.gamma = gamma; a.beta = beta; a.alpha = alpha;
+  a.out = (bf16*)out; a.out_ld = out_ld;
+  CRFR_TRY(set_attrs());
+  norm_fwd_stream_kernel<<<grid_for(npix, c), kThreads, kSmemBytes, st>>>(maps, a);
   CRFR_COUNT_LAUNCH();
   CRFR_LAUNCH_CHECK();
   return CRFR_OK;

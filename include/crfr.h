@@ -36,7 +36,9 @@ unsigned long long crfr_launch_count(void);
 /* Implementation switches for A/B measurements and tests (results are equivalent either way):
  *   "norm_bwd_impl": crfr_norm_act_bwd as 0 = register-staged reduce + fold + apply kernels, 1 = persistent TMA-fed
  *                    reduce + fold + apply kernels (default where the views are TMA-addressable: channels a multiple
- *                    of 64, 16-byte aligned), -1 = default / environment CRFR_NORM_BWD=regs|stream. */
+ *                    of 64, 16-byte aligned), -1 = default / environment CRFR_NORM_BWD=regs|stream.
+ *   "norm_fwd_stream": crfr_norm_act_fwd as 0 = register-staged kernel, 1 = persistent TMA-fed kernel (default where the
+ *                    views are TMA-addressable); identical results bit for bit. */
 int crfr_set_option(const char* name, int value);
 /* 1 if the engine can run the shape (h,w,cin,cout,k,stride,pad), else 0 */
 int crfr_conv_engine_supported(int engine, int op, int h, int w, int cin, int cout, int k, int stride, int pad);

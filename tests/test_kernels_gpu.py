@@ -338,6 +338,29 @@ def test_instance_norm_bwd_full_size_properties(cuda):
     assert rel_err(dg0, dg) < 1e-5 and rel_err(db0, db) < 1e-5 and rel_err(da0, da) < 1e-5
 
 
+@pytest.mark.parametrize("n,c,h,res,bn", [(5, 64, 40, True, False), (40, 64, 32, False, False), (7, 128, 16, True, False),
+                                          (8, 256, 14, True, True), (3, 512, 5, False, True)])
+def test_norm_fwd_stream_matches_register_kernel(cuda, n, c, h, res, bn):
+    """The TMA-fed forward pass (crfr_set_option norm_fwd_stream) performs the same operations per element as the
+    register-staged kernel: identical bits, for InstanceNorm + PReLU (+ residual) and for BatchNorm + ReLU."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(n * c + h)
+    y = nhwc_from(bf16_round(torch.randn(n, c, h, h, generator=g) * 1.3 + 0.2))
+    r = nhwc_from(bf16_round(torch.randn(n, c, h, h, generator=g))) if res else None
+    gamma, beta = (torch.rand(c, generator=g) + 0.5).cuda(), torch.randn(c, generator=g).cuda()
+    alpha = None if bn else (torch.rand(c, generator=g) * 0.5).cuda()
+    stats = ops.norm_stats(y, groups_as_batch=bn)
+    outs = []
+    try:
+        for mode in (0, 1):
+            ops.set_option("norm_fwd_stream", mode)
+            outs.append(ops.norm_act_fwd(y, stats, gamma, beta, alpha, relu=bn, res=r, batch_norm=bn))
+            torch.cuda.synchronize()
+    finally:
+        ops.set_option("norm_fwd_stream", 1)
+    assert torch.equal(outs[0], outs[1])
+
+
 def test_batch_norm_relu_mode(cuda):
     """The same kernels with one statistic group over the whole batch = train-mode BatchNorm2d + ReLU (resnet.py:24-28)."""
     ops = _ops()

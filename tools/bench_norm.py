@@ -40,8 +40,13 @@ def timeit(fn, reps=20):
 stats = ops.norm_stats(ys[0])
 t = timeit(lambda i: ops.norm_stats(ys[i % K]))
 print("stats (partial+finalize)      %6.1f us  %5.2f TB/s (1 map read)" % (t, MiB * 2**20 / t / 1e6))
-t = timeit(lambda i: ops.norm_act_fwd(ys[i % K], stats, gamma, beta, alpha, res=res))
-print("fwd apply (+res)              %6.1f us  %5.2f TB/s (2 reads + 1 write)" % (t, 3 * MiB * 2**20 / t / 1e6))
+for fs in (0, 1):
+    ops.set_option("norm_fwd_stream", fs)
+    t = timeit(lambda i: ops.norm_act_fwd(ys[i % K], stats, gamma, beta, alpha, res=res))
+    print("fwd %s apply (+res)      %6.1f us  %5.2f TB/s (2 reads + 1 write)" % ("stream" if fs else "regs  ", t, 3 * MiB * 2**20 / t / 1e6))
+    t = timeit(lambda i: ops.norm_act_fwd(ys[i % K], stats, gamma, beta, alpha))
+    print("fwd %s apply             %6.1f us  %5.2f TB/s (1 read + 1 write)" % ("stream" if fs else "regs  ", t, 2 * MiB * 2**20 / t / 1e6))
+ops.set_option("norm_fwd_stream", 1)
 import os
 MODES = [(0, "regs    "), (1, "stream  ")]
 if os.environ.get("BENCH_MODES"):
