@@ -196,10 +196,117 @@ void run_pattern(int rows, int variant, Res* d_res) {
          (double)r.cycles / (12.0 * rows), (double)r.cycles / rows, ms, err == cudaSuccess ? "" : cudaGetErrorString(err));
 }
 
-int main() {
+// ---- cta_group::2: a CTA pair issues M = 256 (128 rows of A per CTA), N columns, with each CTA holding N/2 rows of B ----
+__device__ __forceinline__ void umma2_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+
+// a_tiles distinct 16 KB A tiles per CTA; B half of N/2 rows per CTA.  Only rank 0 issues; the commit is multicast to the
+// barrier of both CTAs.  Cycles per MMA are per PAIR-MMA (2 x 128 x N x 16 MACs x 2).
+template <int N>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) mma2_kernel(int iters, int a_tiles, Res* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int a_bytes = 8 * 16384;
+  for (int i = threadIdx.x; i < (a_bytes + (N / 2) * 128) / 16; i += blockDim.x) ((uint4*)base)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  const int warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  cluster_sync();                       // both CTAs' operands and barriers are ready before the first pair MMA
+  const uint32_t tmem = tmem_slot;
+  const uint32_t rank = cluster_rank();
+  if (warp == 0) {
+    const bool leader = elect_one();
+    if (rank == 0) {
+      const uint32_t idesc = make_idesc_bf16(256, N, 0, 0);
+      const uint64_t adesc0 = make_smem_desc_sw128(smem_u32(base), 16, 1024);
+      const uint64_t bdesc0 = make_smem_desc_sw128(smem_u32(base + a_bytes), 16, 1024);
+      long long t0 = clock64();
+      for (int it = 0; it < iters; ++it) {
+        const uint64_t ad = adesc0 + (uint64_t)(((it % a_tiles) * 16384) >> 4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (leader) umma2_bf16(tmem, ad + 2 * k, bdesc0 + 2 * k, idesc, 1u);
+        __syncwarp();
+      }
+      if (leader)
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                     ::"r"(smem_u32(&bar)), "h"((uint16_t)3) : "memory");
+      __syncwarp();
+      mbar_wait(&bar, 0);
+      long long t1 = clock64();
+      if (leader && blockIdx.x == 0) out->cycles = t1 - t0;
+    } else {
+      mbar_wait(&bar, 0);               // the multicast commit arrives here too
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();                       // nobody frees TMEM while the peer may still be inside the MMAs
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+  }
+}
+
+template <int N>
+void run2(int iters, int a_tiles, Res* d_res) {
+  const int smem = 8 * 16384 + (N / 2) * 128 + 2048;
+  cudaFuncSetAttribute(mma2_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  mma2_kernel<N><<<148, 128, smem>>>(iters, a_tiles, d_res);
+  cudaError_t err = cudaDeviceSynchronize();
+  if (err != cudaSuccess) { printf("cta_group::2 N=%d: %s\n", N, cudaGetErrorString(err)); return; }
+  cudaEventRecord(e0);
+  mma2_kernel<N><<<148, 128, smem>>>(iters, a_tiles, d_res);
+  cudaEventRecord(e1);
+  err = cudaDeviceSynchronize();
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  Res r;
+  cudaMemcpy(&r, d_res, sizeof(r), cudaMemcpyDeviceToHost);
+  const double flops = 2.0 * 256 * N * 16 * 4.0 * iters * 74;
+  printf("cta_group::2 M=256 N=%3d a_tiles=%d: %7.1f cycles/pair-MMA  %8.1f TFLOP/s (wall %.3f ms) %s\n", N, a_tiles,
+         (double)r.cycles / (4.0 * iters), flops / (ms * 1e-3) / 1e12, ms, err == cudaSuccess ? "" : cudaGetErrorString(err));
+}
+
+int main(int argc, char** argv) {
   Res* d_res;
   cudaMalloc(&d_res, sizeof(Res));
   const int iters = 4000;
+  if (argc > 1 && atoi(argv[1]) == 2) {   // cta_group::2 issue rate next to the single-CTA SS figures
+    run<128>(iters, 0, 8, d_res);
+    run<192>(iters, 0, 8, d_res);
+    run<256>(iters, 0, 8, d_res);
+    run2<128>(iters, 8, d_res);
+    run2<192>(iters, 8, d_res);
+    run2<256>(iters, 8, d_res);
+    return 0;
+  }
   for (int mode = 0; mode < 0; ++mode) {
     for (int a_tiles : {8}) {
       run<64>(iters, mode, a_tiles, d_res);
