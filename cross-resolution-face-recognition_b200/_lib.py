@@ -24,6 +24,11 @@ class FsrnetIO(C.Structure):
                 ("hr", vp), ("heatmap", vp), ("labels", vp), ("loss_div", cf), ("w_pix", cf), ("bucket_events", vp * 3)]
 
 
+class TapeEntry(C.Structure):
+    _fields_ = [("kind", ci), ("n", ci), ("h", ci), ("w", ci), ("c", ci), ("ld", ci), ("out_off", cll),
+                ("in_off", cll), ("stats_off", cll), ("w_idx", ci), ("has_res", ci)]
+
+
 class ResnetIO(C.Structure):
     _fields_ = [("batch", ci), ("size", ci), ("x", vp), ("emb", vp), ("feat", vp * 4), ("training", ci),
                 ("momentum", cf), ("eps", cf)]
@@ -81,6 +86,7 @@ SIGNATURES = {
     "crfr_verify_sweep": (ci, [vp, vp, vp, ci, vp, ci, vp, vp]),
     "crfr_pair_verify": (ci, [vp, vp, cll, ci, cf, vp, vp, vp]),
     "crfr_fsrnet_workspace_bytes": (csz, [ci, ci, ci]),
+    "crfr_fsrnet_tape": (ci, [ci, ci, ci, C.POINTER(TapeEntry), ci]),
     "crfr_fsrnet_forward": (ci, [ci, vp, C.POINTER(FsrnetIO), ci, vp, csz, vp]),
     "crfr_fsrnet_backward": (ci, [ci, vp, vp, C.POINTER(FsrnetIO), vp, vp, vp, vp, vp, csz, vp]),
     "crfr_fsrnet_train_step": (ci, [ci, vp, vp, C.POINTER(FsrnetIO), vp, vp, csz, vp]),

@@ -68,12 +68,22 @@ def build(force=False, verbose=True):
 def _build_locked(srcs, stamp, dig, verbose):
     nvcc = _nvcc()
 
+    headers = sorted([os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))] +
+                     [os.path.join(ROOT, "include", "crfr.h")])
+    hdig = _digest(headers)
+
     def one(src):
+        # incremental: an object is reused when its own source and every header are unchanged
         obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
+        ostamp, odig = obj + ".stamp", _digest([src]) + hdig + " ".join(FLAGS[:4])
+        if os.path.exists(obj) and os.path.exists(ostamp) and open(ostamp).read() == odig:
+            return obj
         cmd = [nvcc] + ARCH + FLAGS + ["-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
+        with open(ostamp, "w") as f:
+            f.write(odig)
         return obj
 
     with cf.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:

@@ -598,9 +598,15 @@ struct Net {
         }
         case OP_IMGCONV: {
           // gradient of the 3-channel image: explicit (loss / caller) + consumers' slots if it fed the stems
+          // The 3-element bias gradient is a sum with heavy cancellation (|sum| ~ 1e-3 of sum|.|): the explicit part is
+          // summed in fp32 from the fp32 loss gradient by the caller (mse97 / nchw_chansum), the stems' contributions
+          // are summed slot by slot here - never from the bf16-rounded total.
           const bool is_coarse = op.out.p != nullptr;
           bf16* g = is_coarse ? d_coarse4 : d_out4;
           if (is_coarse && has_grad(op.out)) {
+            if (run() && grad(op.b_idx))
+              for (const Slot& sl : slots[op.out.id])
+                check(crfr_colsum(sl.p, sl.ld, 3, (long long)op.cd.n * op.cd.h * op.cd.w, grad(op.b_idx), st));
             if (g) add_slot(op.out, g, 4);
             squash(op.out, 1);
             g = slots[op.out.id][0].p;
@@ -608,8 +614,8 @@ struct Net {
           if (!g) break;
           crfr_conv_desc d = op.cd;
           d.out_ld = 4;
-          if (run()) check(crfr_conv_wgrad(engine, &d, op.a.p, g, grad(op.w_idx), grad(op.b_idx), scratch,
-                                scratch_bytes, st));
+          if (run() && grad(op.w_idx))
+            check(crfr_conv_wgrad(engine, &d, op.a.p, g, grad(op.w_idx), nullptr, scratch, scratch_bytes, st));
           const Tensor& x = op.a;
           bf16* dx = (bf16*)alloc((size_t)x.n * x.h * x.w * x.c * sizeof(bf16));
           void* wt = pack(op.w_idx, 3, x.c, 3, 0, false, true);
@@ -702,6 +708,31 @@ extern "C" size_t crfr_fsrnet_workspace_bytes(int batch, int size, int training)
   return net.off + 65536;
 }
 
+// Layout of the saved forward tensors in the workspace (a dry run: nothing is launched).  Parity tests read the stored
+// bf16 activations through this table and replay them into the CPU oracle (teacher-forced forward / backward checks).
+extern "C" int crfr_fsrnet_tape(int batch, int size, int training, crfr_tape_entry* entries, int max_entries) {
+  if (batch <= 0 || size < 32 || size % 16) return -1;
+  crfr_fsrnet_io io = {};
+  io.batch = batch; io.size = size;
+  Net net;
+  init_net(net, CRFR_ENGINE_AUTO, nullptr, nullptr, &io, nullptr, ~(size_t)0 >> 2, nullptr, false, training != 0);
+  net.forward();
+  const int count = (int)net.tape.size();
+  for (int i = 0; i < count && i < max_entries && entries; ++i) {
+    const Op& op = net.tape[i];
+    crfr_tape_entry& e = entries[i];
+    const Tensor& t = op.out;
+    e.kind = (int)op.kind;
+    e.n = t.n; e.h = t.h; e.w = t.w; e.c = t.c; e.ld = t.ld;
+    e.out_off = t.p ? (long long)((uint8_t*)t.p - (uint8_t*)nullptr) : -1;
+    e.in_off = op.a.p ? (long long)((uint8_t*)op.a.p - (uint8_t*)nullptr) : -1;
+    e.stats_off = op.stats ? (long long)((uint8_t*)op.stats - (uint8_t*)nullptr) : -1;
+    e.w_idx = op.w_idx;
+    e.has_res = op.has_res ? 1 : 0;
+  }
+  return count;
+}
+
 extern "C" int crfr_fsrnet_forward(int engine, const float* const* host_params, const crfr_fsrnet_io* io,
                                    int training, void* ws, size_t ws_bytes, void* stream) {
   CRFR_TRY(check_io(io, "fsrnet_forward"));
@@ -729,8 +760,16 @@ extern "C" int crfr_fsrnet_backward(int engine, const float* const* host_params,
   const int B = io->batch, S = io->size, Q = S / 4;
   alloc_out_grads(net, d_coarse != nullptr, d_out != nullptr, d_landmark || d_parsing);
   if (!net.ok()) return net.err;
-  if (d_coarse) CRFR_TRY(crfr_nchw_f32_to_nhwc_bf16(d_coarse, net.d_coarse4, B, 3, S, S, 4, 4, stream));
-  if (d_out) CRFR_TRY(crfr_nchw_f32_to_nhwc_bf16(d_out, net.d_out4, B, 3, S, S, 4, 4, stream));
+  if (d_coarse) {
+    CRFR_TRY(crfr_nchw_f32_to_nhwc_bf16(d_coarse, net.d_coarse4, B, 3, S, S, 4, 4, stream));
+    if (host_grads[C_CONV_MID_B])
+      CRFR_TRY(crfr_nchw_chansum(d_coarse, B, 3, S * S, host_grads[C_CONV_MID_B], net.scratch, net.scratch_bytes, st));
+  }
+  if (d_out) {
+    CRFR_TRY(crfr_nchw_f32_to_nhwc_bf16(d_out, net.d_out4, B, 3, S, S, 4, 4, stream));
+    if (host_grads[D_CONV_OUT_B])
+      CRFR_TRY(crfr_nchw_chansum(d_out, B, 3, S * S, host_grads[D_CONV_OUT_B], net.scratch, net.scratch_bytes, st));
+  }
   if (net.d_heads) {
     CRFR_CUDA(cudaMemsetAsync(net.d_heads, 0, (size_t)B * Q * Q * kHeadsPad * sizeof(bf16), st));
     if (d_parsing) CRFR_TRY(crfr_nchw_f32_to_nhwc_bf16(d_parsing, net.d_heads, B, 11, Q, Q, kHeadsPad, 11, stream));
@@ -758,10 +797,10 @@ extern "C" int crfr_fsrnet_train_step(int engine, const float* const* host_param
   if (!net.ok()) return net.err;
   // FSR_main.py:233-234: (w*mse(sr,hr) + w*mse(coarse,hr) + landmark + ce) / (2*train_batch)
   const float inv = 1.f / io->loss_div;
-  CRFR_TRY(crfr_loss_mse97(io->out, io->hr, B, 3, S * S, io->w_pix * inv, losses + 1, net.d_out4, 4, net.scratch,
-                           net.scratch_bytes, stream));
-  CRFR_TRY(crfr_loss_mse97(io->coarse, io->hr, B, 3, S * S, io->w_pix * inv, losses + 2, net.d_coarse4, 4,
-                           net.scratch, net.scratch_bytes, stream));
+  CRFR_TRY(crfr_loss_mse97_chan(io->out, io->hr, B, 3, S * S, io->w_pix * inv, losses + 1, net.d_out4, 4,
+                                host_grads[D_CONV_OUT_B], net.scratch, net.scratch_bytes, st));
+  CRFR_TRY(crfr_loss_mse97_chan(io->coarse, io->hr, B, 3, S * S, io->w_pix * inv, losses + 2, net.d_coarse4, 4,
+                                host_grads[C_CONV_MID_B], net.scratch, net.scratch_bytes, st));
   CRFR_CUDA(cudaMemsetAsync(net.d_heads, 0, (size_t)B * Q * Q * kHeadsPad * sizeof(bf16), st));
   CRFR_TRY(crfr_loss_landmark(io->landmark, io->heatmap, B, 97, Q * Q, inv, losses + 3, net.d_heads, kHeadsPad, 11,
                               net.scratch, net.scratch_bytes, stream));

@@ -47,6 +47,12 @@ int crfr_norm_fwd_stream(const void* y, int y_ld, const float* stats, const floa
                          const float* alpha, int relu, const void* res, int res_ld, void* out, int out_ld, int n, int hw,
                          int c, cudaStream_t st);
 
+// losses.cu: MSE*97 loss with the fp32 per-channel sums of its gradient (bias gradient of the producing convolution),
+// and the same sums for an explicit fp32 NCHW gradient
+int crfr_loss_mse97_chan(const float* x, const float* t, int n, int c, int hw, float gscale, float* loss, void* dx,
+                         int dx_ld, float* dchan, void* ws, size_t ws_bytes, cudaStream_t st);
+int crfr_nchw_chansum(const float* g, int n, int c, int hw, float* out, void* ws, size_t ws_bytes, cudaStream_t st);
+
 // direct_conv.cu
 int crfr_direct_gather(int down, int n, int bh, int bw, int sh, int sw, int k, int stride, int pad, const void* src,
                        int src_ld, const void* w, int R, int s_pad, const float* bias, void* y, int y_ld,

@@ -4,6 +4,7 @@
 //      distill_main.py:63,68-70 (nn.MSELoss residual-KD terms).
 #include "common.cuh"
 #include "crfr.h"
+#include "internal.h"
 
 namespace {
 
@@ -34,11 +35,13 @@ __global__ void finalize_kernel(const float* __restrict__ partial, int nblocks, 
   if (threadIdx.x == 0) loss[0] = (float)(sm[0] * scale);
 }
 
+// partial layout: [1 + (dchan ? c : 0)][gridDim.x] - squared-error partials first, then per-channel sums of (x - t)
 __global__ void __launch_bounds__(kT)
 mse97_kernel(const float* __restrict__ x, const float* __restrict__ t, long long npix, int hw, int c, float gcoef,
-             bf16* __restrict__ dx, int dx_ld, float* __restrict__ partial) {
+             bf16* __restrict__ dx, int dx_ld, float* __restrict__ partial, int want_chan) {
   long long i = (long long)blockIdx.x * kT + threadIdx.x;
   float acc = 0.f;
+  float dsum[4] = {0.f, 0.f, 0.f, 0.f};
   if (i < npix) {
     long long n = i / hw;
     int p = (int)(i - n * hw);
@@ -47,12 +50,47 @@ mse97_kernel(const float* __restrict__ x, const float* __restrict__ t, long long
     for (int ch = 0; ch < c; ++ch) {
       float d = xs[(long long)ch * hw] - ts[(long long)ch * hw];
       acc += d * d;
+      if (ch < 4) dsum[ch] = d;
       if (dx) dx[i * dx_ld + ch] = __float2bfloat16_rn(gcoef * d);
     }
     if (dx)
       for (int ch = c; ch < dx_ld; ++ch) dx[i * dx_ld + ch] = __float2bfloat16_rn(0.f);
   }
   block_partial(acc, partial);
+  if (want_chan)
+    for (int ch = 0; ch < c && ch < 4; ++ch) {
+      __syncthreads();
+      block_partial(dsum[ch], partial + (size_t)(1 + ch) * gridDim.x);
+    }
+}
+
+// dchan[ch] += scale * sum(partial[ch][0..nblocks)) in double, fixed order (one block per channel)
+__global__ void chan_finalize_kernel(const float* __restrict__ partial, int nblocks, double scale,
+                                     float* __restrict__ dchan) {
+  __shared__ double sm[kT];
+  const float* pp = partial + (size_t)blockIdx.x * nblocks;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < nblocks; i += kT) s += (double)pp[i];
+  sm[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = kT / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) sm[threadIdx.x] += sm[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) dchan[blockIdx.x] += (float)(sm[0] * scale);
+}
+
+// per-(block, channel) partial sums of an fp32 NCHW tensor: grid (chunks, c), partial[c][chunks]
+__global__ void __launch_bounds__(kT)
+nchw_chansum_kernel(const float* __restrict__ g, int n, int c, int hw, float* __restrict__ partial) {
+  const int ch = blockIdx.y;
+  const long long total = (long long)n * hw;
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < total; i += (long long)gridDim.x * kT) {
+    const long long img = i / hw;
+    acc += g[(img * c + ch) * hw + (i - img * hw)];
+  }
+  block_partial(acc, partial + (size_t)ch * gridDim.x);
 }
 
 __global__ void __launch_bounds__(kT)
@@ -133,18 +171,45 @@ int check_ws(const char* who, void* ws, size_t ws_bytes, int blocks) {
 
 }  // namespace
 
-extern "C" int crfr_loss_mse97(const float* x, const float* t, int n, int c, int hw, float gscale, float* loss,
-                               void* dx, int dx_ld, void* ws, size_t ws_bytes, void* stream) {
-  CRFR_CHECK_ARG(x && t && loss && n > 0 && c > 0 && hw > 0 && (!dx || dx_ld >= c), "loss_mse97: bad argument");
+// dchan (optional, c <= 4): dchan[ch] += sum over all pixels of the fp32 loss gradient of channel ch (the bias gradient of
+// the convolution that produced x; kept in fp32 because the bf16-rounded map sums with heavy cancellation)
+int crfr_loss_mse97_chan(const float* x, const float* t, int n, int c, int hw, float gscale, float* loss, void* dx,
+                         int dx_ld, float* dchan, void* ws, size_t ws_bytes, cudaStream_t st) {
+  CRFR_CHECK_ARG(x && t && loss && n > 0 && c > 0 && hw > 0 && (!dx || dx_ld >= c) && (!dchan || c <= 4),
+                 "loss_mse97: bad argument");
   long long npix = (long long)n * hw;
   int blocks = crfr_cdiv(npix, kT);
-  CRFR_TRY(check_ws("loss_mse97", ws, ws_bytes, blocks));
+  CRFR_TRY(check_ws("loss_mse97", ws, ws_bytes, blocks * (dchan ? 1 + c : 1)));
   double numel = (double)npix * c;
-  cudaStream_t st = (cudaStream_t)stream;
-  mse97_kernel<<<blocks, kT, 0, st>>>(x, t, npix, hw, c, (float)(gscale * 2.0 * 97.0 / numel), (bf16*)dx, dx_ld,
-                                      (float*)ws);
+  const double gcoef = gscale * 2.0 * 97.0 / numel;
+  mse97_kernel<<<blocks, kT, 0, st>>>(x, t, npix, hw, c, (float)gcoef, (bf16*)dx, dx_ld, (float*)ws, dchan ? 1 : 0);
   CRFR_COUNT_LAUNCH();
   finalize_kernel<<<1, kT, 0, st>>>((const float*)ws, blocks, 97.0 / numel, loss);
+  CRFR_COUNT_LAUNCH();
+  if (dchan) {
+    chan_finalize_kernel<<<c, kT, 0, st>>>((const float*)ws + blocks, blocks, gcoef, dchan);
+    CRFR_COUNT_LAUNCH();
+  }
+  CRFR_LAUNCH_CHECK();
+  return CRFR_OK;
+}
+
+extern "C" int crfr_loss_mse97(const float* x, const float* t, int n, int c, int hw, float gscale, float* loss,
+                               void* dx, int dx_ld, void* ws, size_t ws_bytes, void* stream) {
+  return crfr_loss_mse97_chan(x, t, n, c, hw, gscale, loss, dx, dx_ld, nullptr, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+// out[ch] += sum over (n, h, w) of g[n][ch][h][w]  (fp32 NCHW), deterministic two-stage reduction
+int crfr_nchw_chansum(const float* g, int n, int c, int hw, float* out, void* ws, size_t ws_bytes, cudaStream_t st) {
+  CRFR_CHECK_ARG(g && out && n > 0 && c > 0 && hw > 0, "nchw_chansum: bad argument");
+  long long total = (long long)n * hw;
+  int chunks = (int)((total + kT * 8 - 1) / (kT * 8));
+  if (chunks > 592) chunks = 592;
+  if (chunks < 1) chunks = 1;
+  CRFR_TRY(check_ws("nchw_chansum", ws, ws_bytes, chunks * c));
+  nchw_chansum_kernel<<<dim3(chunks, c), kT, 0, st>>>(g, n, c, hw, (float*)ws);
+  CRFR_COUNT_LAUNCH();
+  chan_finalize_kernel<<<c, kT, 0, st>>>((const float*)ws, chunks, 1.0, out);
   CRFR_COUNT_LAUNCH();
   CRFR_LAUNCH_CHECK();
   return CRFR_OK;

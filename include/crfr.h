@@ -226,6 +226,20 @@ typedef struct crfr_fsrnet_io {
   void* bucket_events[3];
 } crfr_fsrnet_io;
 
+/* One recorded op of the network program (test / debugging aid: where the saved forward tensors live in the workspace).
+ * kind: 0 conv, 1 InstanceNorm(+PReLU)(+residual), 2 max-pool, 3 nearest-up + add, 4 concat (view), 5 heads,
+ * 6 3-channel image conv.  Offsets are bytes from the workspace base, -1 when absent. */
+typedef struct crfr_tape_entry {
+  int kind;
+  int n, h, w, c, ld;      /* output tensor: NHWC bf16 with a pixel stride of ld elements */
+  long long out_off;
+  long long in_off;        /* first input */
+  long long stats_off;     /* kind 1: fp32 (mean, rstd) [n][c][2] */
+  int w_idx, has_res;
+} crfr_tape_entry;
+/* fills up to max_entries entries (entries may be NULL) and returns the number of recorded ops, < 0 on bad arguments */
+int crfr_fsrnet_tape(int batch, int size, int training, crfr_tape_entry* entries, int max_entries);
+
 /* ref: OverallNetwork.forward model/FSRnet.py:497-508 with the runnable wiring of :538-541.
  * params: 202 fp32 device pointers in state_dict order.  engine selects the conv engine for eligible layers. */
 size_t crfr_fsrnet_workspace_bytes(int batch, int size, int training);

@@ -294,6 +294,46 @@ class Precision:
     def qb(self, x):
         return self.q(self.qg(x)) if self.on else x
 
+    # storage points of ACTIVATIONS (conv outputs, normalise+PReLU outputs, hourglass sums).  Same rounding as q / qb;
+    # kept apart from the weight / input roundings so that ``ForcedPrecision`` can substitute them.
+    def st(self, x):
+        return self.q(x)
+
+    def sb(self, x):
+        return self.st(self.qg(x)) if self.on else x
+
+
+class ForcedPrecision(Precision):
+    """Teacher-forced evaluation: the bf16 storage contract, but every stored ACTIVATION takes the value another
+    implementation stored at that point (``feed``: the tensors in program order, fp32 NCHW), straight-through for the
+    gradient.  Two things follow:
+      * ``errors[i]`` = norm-wise relative deviation between the oracle's value computed from the forced inputs and
+        the forced value: a per-layer forward check on identical inputs, for every layer of the network in place;
+      * the backward pass runs on exactly the forward tensors of the other implementation.  Backward is linear once
+        the forward is fixed, so parameter gradients must then agree to rounding noise - the chaotic amplification
+        that limits free-running whole-network comparisons (tests/test_fsrnet_gpu.py) is gone, and a sequencing bug
+        (a dropped weight-sharing accumulation, a wrong gradient slot) cannot hide behind it.
+    """
+
+    def __init__(self, feed):
+        super().__init__("bf16")
+        self.feed = list(feed)
+        self.pos = 0
+        self.errors = []        # ||computed - forced|| / ||forced||            (includes the bf16 rounding itself)
+        self.errors_q = []      # ||bf16(computed) - forced|| / ||forced||      (0 unless a rounding flips)
+
+    def st(self, x):
+        assert self.pos < len(self.feed), "more storage points in the oracle than forced tensors"
+        f = self.feed[self.pos]
+        self.feed[self.pos] = None          # free as we go: the list holds GBs at 128 x 128
+        self.pos += 1
+        assert tuple(f.shape) == tuple(x.shape), (self.pos - 1, tuple(f.shape), tuple(x.shape))
+        xd = x.detach()
+        fn = f.double().norm().clamp_min(1e-30)
+        self.errors.append(((xd - f).double().norm() / fn).item())
+        self.errors_q.append(((xd.to(torch.bfloat16).to(torch.float32) - f).double().norm() / fn).item())
+        return x + (f - xd)
+
 
 FP32 = Precision("fp32")
 
@@ -302,24 +342,19 @@ FP32 = Precision("fp32")
 # forward restatement
 # ----------------------------------------------------------------------------------------------------------------
 def _inorm(x, w=None, b=None):
-    # InstanceNorm2d: per-(n,c) biased variance over H*W, eps 1e-5, no running stats (train == eval)
-    mu = x.mean(dim=(2, 3), keepdim=True)
-    var = ((x - mu) ** 2).mean(dim=(2, 3), keepdim=True)
-    y = (x - mu) / torch.sqrt(var + EPS)
-    if w is not None:
-        y = y * w.view(1, -1, 1, 1) + b.view(1, -1, 1, 1)
-    return y
+    # InstanceNorm2d: per-(n,c) biased variance over H*W, eps 1e-5, no running stats (train == eval).
+    # F.instance_norm is what nn.InstanceNorm2d.forward calls (model/FSRnet.py:81,87,112,115 ...).
+    return F.instance_norm(x, None, None, w, b, True, 0.0, EPS)
 
 
 def _prelu(x, a):
-    a = a.view(1, -1, 1, 1)
-    return torch.clamp(x, min=0) + a * torch.clamp(x, max=0)
+    return F.prelu(x, a)
 
 
 def _conv(pr, x, w, b=None, stride=1, pad=0, store=True):
     """Conv2d on a stored activation: bf16 weights, gradient w.r.t. the input stored, output stored (unless fp32)."""
     y = F.conv2d(pr.qg(x), pr.q(w), b, stride, pad)
-    return pr.qb(y) if store else y
+    return pr.sb(y) if store else y
 
 
 def _norm_act(pr, y, w=None, b=None, alpha=None, res=None):
@@ -327,7 +362,7 @@ def _norm_act(pr, y, w=None, b=None, alpha=None, res=None):
     if res is not None:
         z = z + res
     z = pr.qg(z)                       # gradient w.r.t. the pre-activation (== gradient of the residual input)
-    return pr.q(_prelu(z, alpha) if alpha is not None else z)
+    return pr.st(_prelu(z, alpha) if alpha is not None else z)
 
 
 def _res_block(pr, sd, p, x):
@@ -364,7 +399,7 @@ def _hourglass(pr, sd, p, n, x):
     low2 = _hourglass(pr, sd, p, n - 1, low1) if n > 1 else _hg_seq(pr, sd, p, 0, 3, low1)
     low3 = _hg_seq(pr, sd, p, n - 1, 2, low2)
     out = up1 + F.interpolate(pr.qg(low3), scale_factor=2)      # default mode: nearest
-    return pr.qb(out)
+    return pr.sb(out)
 
 
 def coarse_forward(sd, x, p="_coarse_sr_network.", pr=FP32):
@@ -399,7 +434,7 @@ def prior_forward(sd, x, p="_prior_estimation_network.", pr=FP32):
 def decoder_forward(sd, x, p="_fine_sr_decoder.", pr=FP32):
     y = _conv(pr, x, sd[p + "conv_input.weight"], sd[p + "conv_input.bias"], 1, 1)
     y = _norm_act(pr, y, sd[p + "bn_mid.weight"], sd[p + "bn_mid.bias"], sd[p + "relu.weight"])
-    y = pr.qb(F.conv_transpose2d(pr.qg(y), pr.q(sd[p + "deconv.weight"]), sd[p + "deconv.bias"], 4, 2, 1))
+    y = pr.sb(F.conv_transpose2d(pr.qg(y), pr.q(sd[p + "deconv.weight"]), sd[p + "deconv.bias"], 4, 2, 1))
     y = _norm_act(pr, y, sd[p + "bn_mid.weight"], sd[p + "bn_mid.bias"], sd[p + "relu.weight"])
     y = _res_stack(pr, sd, p, y, 3)
     y = _norm_act(pr, y, sd[p + "bn_mid.weight"], sd[p + "bn_mid.bias"])
@@ -451,8 +486,9 @@ def synthetic_batch(batch, size=128, seed=4321):
 
 
 def fsrnet_loss_and_grads(sd, x, hr, hm, lbl, train_batch=None, precision="fp32"):
-    """One forward+backward; returns (outputs, total, parts, {name: grad}) - used as the parity oracle."""
-    pr = Precision(precision)
+    """One forward+backward; returns (outputs, total, parts, {name: grad}) - used as the parity oracle.
+    ``precision``: "fp32", "bf16" or a ``Precision`` instance (e.g. ``ForcedPrecision``)."""
+    pr = precision if isinstance(precision, Precision) else Precision(precision)
     leaves = OrderedDict((k, v.detach().clone().requires_grad_(True)) for k, v in sd.items())
     outs = fsrnet_forward(leaves, x, pr)
     total, parts = fsrnet_loss(outs, hr, hm, lbl, train_batch, pr=pr)

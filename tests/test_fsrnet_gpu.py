@@ -119,9 +119,8 @@ def test_train_step_matches_module_path(cuda):
     for (k, p), gr in zip(net.named_parameters(), grads):
         if p.grad is None or FO.fsrnet_dead_param(k) or k in FO.FSRNET_NULL_GRAD:
             continue
-        # the 3-element image-conv biases are plain sums of a large, sign-cancelling gradient map (|sum| ~ 1e-3 of
-        # sum|.|), so bf16 rounding noise of the map shows up amplified there: looser bound for those
-        assert rel_err(gr, p.grad) < (1e-1 if p.numel() <= 3 else 2e-2), k
+        # (the 3-element image-conv bias gradients are summed in fp32 from the fp32 loss gradient on both paths)
+        assert rel_err(gr, p.grad) < 2e-2, k
 
 
 def test_chunked_accumulation_equals_full_batch(cuda):
@@ -159,7 +158,7 @@ def test_chunked_accumulation_equals_full_batch(cuda):
     for (k, _), a, b in zip(net.named_parameters(), g_two, g_full):
         if FO.fsrnet_dead_param(k) or k in FO.FSRNET_NULL_GRAD:
             continue
-        assert rel_err(a, b) < (1e-1 if a.numel() <= 3 else 2e-2), k
+        assert rel_err(a, b) < 2e-2, k
 
 
 def test_rejects_cpu_and_bad_shapes(cuda):
