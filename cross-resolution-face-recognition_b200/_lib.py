@@ -47,6 +47,7 @@ SIGNATURES = {
     "crfr_version": (ci, []),
     "crfr_launch_count": (C.c_ulonglong, []),
     "crfr_set_option": (ci, [C.c_char_p, ci]),
+    "crfr_debug_pair_profile": (ci, [C.POINTER(cll), ci]),
     "crfr_conv_engine_supported": (ci, [ci] * 9),
     "crfr_nchw_f32_to_nhwc_bf16": (ci, [vp, vp, ci, ci, ci, ci, ci, ci, vp]),
     "crfr_nhwc_bf16_to_nchw_f32": (ci, [vp, vp, ci, ci, ci, ci, ci, vp]),

@@ -1,7 +1,10 @@
 // C-ABI convolution entry points: shape validation + engine dispatch (tcgen05 implicit GEMM or CUDA-core direct).
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <atomic>
 
 #include "common.cuh"
 #include "crfr.h"
@@ -21,18 +24,58 @@ extern "C" const char* crfr_last_error(void) { return g_err; }
 extern "C" int crfr_version(void) { return 100; }
 extern "C" unsigned long long crfr_launch_count(void) { return g_crfr_launches; }
 
-void crfr_norm_set_impl(int v);   // norm_act.cu
-void crfr_norm_set_fwd_stream(int v);
+// ---- tuning switches (internal.h) ------------------------------------------------------------------------------
+namespace {
+struct OptDef { const char* name; const char* env; int dflt; };
+const OptDef kOpts[CRFR_OPT_COUNT] = {
+    {"rowconv", "CRFR_ROWCONV", 1},           {"rowconv_pair", "CRFR_ROWCONV_PAIR", 1},
+    {"pair_swap", "CRFR_PAIR_SWAP", 0},       {"wgrad_stream", "CRFR_WGRAD_STREAM", 1},
+    {"norm_bwd_impl", "CRFR_NORM_BWD", 1},    {"norm_fwd_stream", "CRFR_NORM_FWD_STREAM", 1},
+    {"rowwgrad_pair", "CRFR_ROWWGRAD_PAIR", 1}, {"pair_debug", "CRFR_PAIR_DEBUG", 0}};
+std::atomic<int> g_opt[CRFR_OPT_COUNT];
+std::atomic<int> g_opt_init{0};
+void opts_init() {
+  if (g_opt_init.load(std::memory_order_acquire) == 2) return;
+  int expect = 0;
+  if (g_opt_init.compare_exchange_strong(expect, 1)) {
+    for (int i = 0; i < CRFR_OPT_COUNT; ++i) {
+      const char* e = getenv(kOpts[i].env);
+      int v = kOpts[i].dflt;
+      if (e && *e) v = (i == CRFR_OPT_NORM_BWD_STREAM) ? (e[0] == 'r' || e[0] == '0' ? 0 : 1) : atoi(e);
+      g_opt[i].store(v, std::memory_order_relaxed);
+    }
+    g_opt_init.store(2, std::memory_order_release);
+  } else {
+    while (g_opt_init.load(std::memory_order_acquire) != 2) {}
+  }
+}
+std::atomic<int> g_sms[64];
+}  // namespace
+
+int crfr_opt(int id) {
+  opts_init();
+  return (id >= 0 && id < CRFR_OPT_COUNT) ? g_opt[id].load(std::memory_order_relaxed) : 0;
+}
+
+int crfr_sm_count() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  int v = g_sms[dev].load(std::memory_order_relaxed);
+  if (!v) {
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    g_sms[dev].store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+
 extern "C" int crfr_set_option(const char* name, int value) {
   CRFR_CHECK_ARG(name, "set_option: null name");
-  if (!strcmp(name, "norm_bwd_impl")) {
-    crfr_norm_set_impl(value);
-    return CRFR_OK;
-  }
-  if (!strcmp(name, "norm_fwd_stream")) {
-    crfr_norm_set_fwd_stream(value);
-    return CRFR_OK;
-  }
+  opts_init();
+  for (int i = 0; i < CRFR_OPT_COUNT; ++i)
+    if (!strcmp(name, kOpts[i].name)) {
+      g_opt[i].store(value, std::memory_order_relaxed);
+      return CRFR_OK;
+    }
   crfr_set_error("set_option: unknown option '%s'", name);
   return CRFR_EINVAL;
 }

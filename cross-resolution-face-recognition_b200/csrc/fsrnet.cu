@@ -122,14 +122,7 @@ SideStream* side_stream() {
   }
   return &s;
 }
-int side_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("CRFR_WGRAD_STREAM");
-    v = e ? atoi(e) : 1;
-  }
-  return v;
-}
+int side_enabled() { return crfr_opt(CRFR_OPT_WGRAD_STREAM); }
 
 struct Op {
   OpKind kind;

@@ -5,6 +5,42 @@
 
 #include "crfr.h"
 
+#ifdef __cplusplus
+#include <atomic>
+#endif
+
+// ---- process-wide tuning switches (conv_api.cu).  Every setting computes the same results; they exist for A/B
+// measurements and debugging.  Defaults come from the environment (CRFR_ROWCONV, CRFR_ROWCONV_PAIR, CRFR_PAIR_SWAP,
+// CRFR_WGRAD_STREAM, CRFR_NORM_BWD=regs|stream, CRFR_NORM_FWD_STREAM) once; crfr_set_option overrides atomically.
+enum {
+  CRFR_OPT_ROWCONV = 0,      // row-streaming kernels for 64 -> 64 convolutions at width 128 (else the tile engine)
+  CRFR_OPT_ROWCONV_PAIR,     // cta_group::2 form of the row-streaming forward / dgrad kernel (even image counts)
+  CRFR_OPT_PAIR_SWAP,        // debugging: which CTA of a pair holds the lower half of B
+  CRFR_OPT_WGRAD_STREAM,     // FSRNet backward: weight gradients on a helper stream
+  CRFR_OPT_NORM_BWD_STREAM,  // TMA-fed normalisation backward (else register-staged)
+  CRFR_OPT_NORM_FWD_STREAM,  // TMA-fed normalisation forward
+  CRFR_OPT_ROWWGRAD_PAIR,    // cta_group::2 form of the row-streaming weight gradient
+  CRFR_OPT_PAIR_DEBUG,       // ablation bits for tools/pair_diag.py (results are WRONG when set): 1 no loads, 2 no MMAs,
+                             // 4 no pack / store / statistics, 8 no store, 16 no statistics
+  CRFR_OPT_COUNT
+};
+int crfr_opt(int id);
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per DEVICE: remember which devices have it (one process may drive
+// several GPUs), and cache the SM count per device likewise.
+template <typename K>
+inline int crfr_smem_attr(K kernel, int bytes, std::atomic<unsigned long long>& done) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) dev = -1;
+  const unsigned long long bit = (dev >= 0 && dev < 64) ? 1ull << dev : 0ull;
+  if (bit && (done.load(std::memory_order_acquire) & bit)) return 0;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return (int)e;
+  if (bit) done.fetch_or(bit, std::memory_order_release);
+  return 0;
+}
+int crfr_sm_count();   // SMs of the current device (cached per device)
+
 // tmap.cu: bf16 / SWIZZLE_128B / zero-fill tensor map of rank <= 5; strides_bytes has rank-1 entries (dimension 0 is
 // contiguous).  CUtensorMap comes from <cuda.h> (included by every caller through sm100.cuh / cudaTypedefs.h).
 struct CUtensorMap_st;
@@ -103,6 +139,11 @@ int crfr_lowered_wgrad(const crfr_conv_desc* d, const void* x, const void* dy, f
 // rowconv.cu: persistent row-streaming kernel for 3x3 64->64 convolutions at width 128
 int crfr_rowconv_supported(int h, int w, int cin, int cout, int k, int stride, int pad);
 size_t crfr_rowconv_ws_bytes(int n, int h);
+// rowconv2.cu: cta_group::2 form of the same kernel (two CTAs walk the same rows of two images); n must be even
+int crfr_rowconv_pair_supported(int n, int h);
+size_t crfr_rowconv_pair_ws_bytes(int n, int h);
+int crfr_rowconv_pair(const void* src, int src_ld, int n, int h, const void* w_packed, int flip, const float* bias,
+                      void* dst, int dst_ld, float* stats, float eps, void* ws, size_t ws_bytes, cudaStream_t st);
 // rowwgrad.cu: persistent row-streaming weight gradient of the same shape (deterministic slab reduction)
 int crfr_rowwgrad_supported(int h, int w, int cin, int cout, int k, int stride, int pad);
 size_t crfr_rowwgrad_ws_bytes(int n, int h);

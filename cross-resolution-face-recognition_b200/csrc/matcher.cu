@@ -425,11 +425,9 @@ extern "C" int crfr_cosine_topk(int engine, const void* probes, const void* gall
   mp.out_val = (float*)ws;
   mp.out_idx = (int*)((float*)ws + (size_t)s.splits * p * kTopK);
   const int smem = mp.kchunks * kTile + kStages * kBTile + 1024 + 256;
-  static int attr_smem = 0;
-  if (smem > attr_smem) {
-    CRFR_CUDA(cudaFuncSetAttribute(cosine_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_smem = smem;
-  }
+  // the dynamic shared-memory size depends on the embedding width: raise the per-device limit to the hardware maximum once
+  static std::atomic<unsigned long long> attr_done{0};
+  CRFR_CUDA((cudaError_t)crfr_smem_attr(cosine_topk_kernel, 232448, attr_done));
   cosine_topk_kernel<<<dim3(s.tiles, s.splits), kThreads, smem, st>>>(tmP, tmG, mp);
   CRFR_COUNT_LAUNCH();
   CRFR_LAUNCH_CHECK();

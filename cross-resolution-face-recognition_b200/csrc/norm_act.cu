@@ -382,18 +382,8 @@ norm_act_bwd_apply_kernel(const bf16* __restrict__ dz, int dz_ld, const bf16* __
   }
 }
 
-// implementation of crfr_norm_act_bwd: 0 = register-staged reduce + fold + apply kernels (below), 1 = persistent TMA-fed
-// reduce + fold + apply kernels (norm_stream.cu; default wherever the views are TMA-addressable).  CRFR_NORM_BWD=regs|stream.
-int env_impl() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("CRFR_NORM_BWD");
-    v = (e && e[0] == 'r') ? 0 : 1;
-  }
-  return v;
-}
-int g_fwd_stream = 1;        // crfr_set_option("norm_fwd_stream", 0 / 1): register-staged / TMA-fed forward pass (norm_stream.cu)
-int g_impl_override = -1;   // crfr_set_option("norm_bwd_impl", 0 / 1), -1 = environment / default
+// implementation of crfr_norm_act_bwd: option norm_bwd_impl 0 = register-staged reduce + fold + apply kernels (below),
+// 1 = persistent TMA-fed reduce + fold + apply kernels (norm_stream.cu; default wherever the views are TMA-addressable).
 
 // BatchNorm buffer maintenance (one thread per channel)
 __global__ void bn_update_running_kernel(const float* __restrict__ stats, float* __restrict__ rmean,
@@ -462,8 +452,6 @@ extern "C" int crfr_bn_running_to_stats(const float* running_mean, const float* 
 
 extern "C" size_t crfr_norm_workspace_bytes(int n, int hw, int c) { return crfr_norm_ws_bytes(n, hw, c); }
 
-void crfr_norm_set_impl(int v) { g_impl_override = v; }
-void crfr_norm_set_fwd_stream(int v) { g_fwd_stream = v; }
 
 extern "C" int crfr_norm_stats(const void* y, int n, int hw, int c, int ld, float eps, float* stats, void* ws,
                                size_t ws_bytes, void* stream) {
@@ -494,7 +482,7 @@ extern "C" int crfr_norm_act_fwd(const void* y, int y_ld, const float* stats, co
   {
     const void* views[3] = {y, res, out};
     const int lds[3] = {y_ld, res_ld, out_ld};
-    if (g_fwd_stream && crfr_norm_stream_supported(c, (long long)n * hw, views, lds, 3))
+    if (crfr_opt(CRFR_OPT_NORM_FWD_STREAM) && crfr_norm_stream_supported(c, (long long)n * hw, views, lds, 3))
       return crfr_norm_fwd_stream(y, y_ld, stats, gamma, beta, alpha, relu, res, res_ld, out, out_ld, n, hw, c,
                                   (cudaStream_t)stream);
   }
@@ -524,7 +512,7 @@ extern "C" int crfr_norm_act_bwd(const void* dout_a, int da_ld, const void* dout
   }
   cudaStream_t st = (cudaStream_t)stream;
   int lanes = kThreads / (c >> 3);
-  const int impl = g_impl_override >= 0 ? g_impl_override : env_impl();
+  const int impl = crfr_opt(CRFR_OPT_NORM_BWD_STREAM);
   const void* views[6] = {dout_a, dout_b, y, res, dz, dy};
   const int lds[6] = {da_ld, db_ld, y_ld, res_ld, dz_ld, dy_ld};
   const bool tma = impl >= 1 && crfr_norm_stream_supported(c, (long long)n * hw, views, lds, 6);

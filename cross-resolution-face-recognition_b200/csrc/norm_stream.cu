@@ -486,15 +486,7 @@ int encode_map(CUtensorMap* m, const void* ptr, int ld, int c, long long npix, i
   return crfr_tmap_encode_bf16(m, ptr, 2, dims, strides, box, what);
 }
 
-int sm_count() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-      sms = 148;
-  }
-  return sms;
-}
+int sm_count() { return crfr_sm_count(); }
 
 // persistent grid: two CTAs per SM, at least 16 stages of work per CTA.  (A "slim" shape - 32 KB ring, four ranges per
 // SM, so that one CTA fits beside a 181 KB row-streaming weight-gradient CTA of the helper stream - streams just as fast
@@ -509,13 +501,10 @@ int grid_for(long long total, int c) {
 }
 
 int set_attrs() {
-  static bool done = false;
-  if (!done) {
-    CRFR_CUDA(cudaFuncSetAttribute(norm_bwd_reduce_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    CRFR_CUDA(cudaFuncSetAttribute(norm_bwd_apply_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    CRFR_CUDA(cudaFuncSetAttribute(norm_fwd_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-    done = true;
-  }
+  static std::atomic<unsigned long long> d0{0}, d1{0}, d2{0};
+  CRFR_CUDA((cudaError_t)crfr_smem_attr(norm_bwd_reduce_stream_kernel, (int)kSmemBytes, d0));
+  CRFR_CUDA((cudaError_t)crfr_smem_attr(norm_bwd_apply_stream_kernel, (int)kSmemBytes, d1));
+  CRFR_CUDA((cudaError_t)crfr_smem_attr(norm_fwd_stream_kernel, (int)kSmemBytes, d2));
   return CRFR_OK;
 }
 

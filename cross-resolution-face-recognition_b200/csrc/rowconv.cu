@@ -302,15 +302,7 @@ int encode(CUtensorMap* m, const void* ptr, int rank, const unsigned long long* 
   return crfr_tmap_encode_bf16(m, ptr, rank, dims, strides, box, what);
 }
 
-int sm_count() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-      sms = 148;
-  }
-  return sms;
-}
+int sm_count() { return crfr_sm_count(); }
 
 int grid_for(int total_rows) {
   const int sms = sm_count();
@@ -330,12 +322,17 @@ int crfr_rowconv_supported(int h, int w, int cin, int cout, int k, int stride, i
   return w == kW && cin == kC && cout == kC && k == 3 && stride == 1 && pad == 1 && h >= 1;
 }
 
-size_t crfr_rowconv_ws_bytes(int n, int h) { return sizeof(float) * (size_t)n * parts_for(n, h) * 2 * kC + 256; }
+size_t crfr_rowconv_ws_bytes(int n, int h) {
+  const size_t one = sizeof(float) * (size_t)n * parts_for(n, h) * 2 * kC + 256, two = crfr_rowconv_pair_ws_bytes(n, h);
+  return one > two ? one : two;
+}
 
 // src/dst: NHWC bf16 [n][h][128][64] views; w_packed: [9][64][64] bf16 ([tap][n][k]); flip = 1 for dgrad.
 // stats (optional, forward only): InstanceNorm (mean, rstd) [n][64][2] of the stored output; needs ws.
 int crfr_rowconv(const void* src, int src_ld, int n, int h, const void* w_packed, int flip, const float* bias, void* dst,
                  int dst_ld, float* stats, float eps, void* ws, size_t ws_bytes, cudaStream_t st) {
+  if (crfr_opt(CRFR_OPT_ROWCONV_PAIR) && crfr_rowconv_pair_supported(n, h))   // CTA-pair kernel (rowconv2.cu)
+    return crfr_rowconv_pair(src, src_ld, n, h, w_packed, flip, bias, dst, dst_ld, stats, eps, ws, ws_bytes, st);
   CRFR_CHECK_ARG(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0 && ((uintptr_t)w_packed & 15) == 0 &&
                      (src_ld & 7) == 0 && (dst_ld & 7) == 0,
                  "rowconv: pointers must be 16B aligned and ld a multiple of 8");
@@ -358,18 +355,15 @@ int crfr_rowconv(const void* src, int src_ld, int n, int h, const void* w_packed
     unsigned int box[2] = {64, 64};
     CRFR_TRY(encode(&tmW, w_packed, 2, dims, strides, box, "weights"));
   }
-  static bool attr_done = false;
-  if (!attr_done) {
-    CRFR_CUDA(cudaFuncSetAttribute(rowconv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    attr_done = true;
-  }
+  static std::atomic<unsigned long long> attr_done{0};
+  CRFR_CUDA((cudaError_t)crfr_smem_attr(rowconv_kernel, kSmemBytes, attr_done));
   RowParams p;
   p.n = n; p.h = h; p.total_rows = n * h; p.flip = flip;
   p.bias = bias;
   p.partial = nullptr;
   p.parts = 0;
   if (stats) {
-    const size_t need = crfr_rowconv_ws_bytes(n, h);
+    const size_t need = sizeof(float) * (size_t)n * parts_for(n, h) * 2 * kC + 256;
     if (!ws || ws_bytes < need) {
       crfr_set_error("rowconv: workspace %zu < %zu", ws_bytes, need);
       return CRFR_EWORKSPACE;

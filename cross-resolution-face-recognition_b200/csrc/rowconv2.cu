@@ -1,0 +1,559 @@
+// CTA-pair (tcgen05 cta_group::2) version of the row-streaming 3x3 convolution of rowconv.cu (64 -> 64 channels,
+// width 128: model/FSRnet.py:79,85 inside the coarse and decoder stacks, forward and dgrad).
+//
+// Why: the single-CTA kernel issues M = 128, N = 192 MMAs whose operands (4 KB of A + 6 KB of B per MMA) take most of
+// the shared-memory bandwidth of the SM; measured, such an MMA costs 134 cycles in isolation (175 inside the kernel)
+// against the 96 the tensor pipe needs.  A CTA pair issues ONE M = 256 MMA for two SMs: every CTA still supplies its
+// own 128 rows of A, but only HALF of the B rows (the tensor cores of the pair exchange the halves), and the pair runs
+// at exactly 96 cycles per K = 16 step (tools/micro/mma_bench.cu 2, profiles/r1_mma_microbench.txt).
+//
+// Work split: the two CTAs of a cluster walk the SAME rows of two DIFFERENT images (rank r -> image 2 * pair + r), so
+// that one issuing thread can drive both with one descriptor set: identical ring positions, identical TMEM slots,
+// identical (first tap, tap count) sequences at image and range edges.  The flattened (image pair, row) space is cut
+// into one contiguous range per cluster exactly as rowconv.cu cuts (image, row) per CTA.
+//
+// B operand: with cta_group::2 rank 0 holds rows [0, N/2) and rank 1 rows [N/2, N) of the N x K matrix the MMA names
+// with ONE shared-memory address.  The ky-stacked B of rowconv.cu is addressed as a sub-range (first tap j0, count cnt)
+// of 192 rows, so every combination that occurs - (0,3) interior rows, (0,2) (1,2) image / range edges, (0,1) (1,1)
+// (2,1) where the TMEM ring wraps - has its own per-rank half in shared memory: 320 rows x 128 B per kx, 120 KB.
+//
+// Protocol (everything else is rowconv.cu): own TMA producer and epilogue per CTA; rank 1's otherwise idle MMA warp
+// forwards its "row landed" barrier to rank 0 (remote mbarrier arrive); rank 0 issues tcgen05.mma.cta_group::2 and
+// commits with .multicast::cluster, which releases ring slots and publishes accumulator slots in BOTH CTAs; the
+// epilogue warps of both CTAs return drained TMEM slots on rank 0's barrier (8 arrivals).
+#include <cudaTypedefs.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "crfr.h"
+#include "internal.h"
+#include "sm100.cuh"
+
+using namespace sm100;
+
+namespace {
+
+constexpr int kW = 128;
+constexpr int kC = 64;
+constexpr int kRowBytes = 130 * 128;       // one input row with halo, 128 B per pixel
+constexpr int kSlotBytes = 17 * 1024;      // ring slot stride (1024-aligned)
+constexpr int kSlots = 4;
+constexpr int kCaseRows = 320;             // per kx: 96 + 64 + 64 + 32 + 32 + 32 rows (see case_row)
+constexpr int kKxBytes = kCaseRows * 128;
+constexpr int kWeightBytes = 3 * kKxBytes;
+constexpr int kThreads = 320;              // producer warp, MMA warp, 2 epilogue groups of 4 warps
+constexpr int kStageOutBytes = 128 * 128;
+constexpr int kAccSlots = 8;
+constexpr int kDone = 8;                   // ring of "input row consumed" barriers (a power of two >= kAccSlots)
+constexpr int kPrefetch = 12;              // rows pulled into L2 ahead of the shared-memory ring
+constexpr int kSmemBytes = kWeightBytes + kSlots * kSlotBytes + 2 * kStageOutBytes + 2 * 4 * 128 * 4 /*stats*/ +
+                           kC * 4 /*bias*/ + 1024 /*align*/ + 512 /*barriers*/;
+static_assert(kSmemBytes <= 232448, "shared memory budget");
+
+struct PairParams {
+  int n, h;              // images (even), rows per image
+  int total_rows;        // (n / 2) * h: rows of the flattened (image pair, row) space
+  int flip;              // 1: dgrad
+  int swap_halves;       // debugging aid: rank 0 holds the upper half of B
+  int dbg;               // ablation bits (CRFR_OPT_PAIR_DEBUG), 0 in production
+  const float* bias;
+  float* partial;        // InstanceNorm partials [n][parts][2][64] or nullptr
+  int parts;
+};
+
+// first row (of the 320 per kx) of the half that belongs to the sub-range (first tap j0, cnt taps) of the stacked B
+__host__ __device__ __forceinline__ int case_row(int j0, int cnt) {
+  return cnt == 3 ? 0 : (cnt == 2 ? 96 + 64 * j0 : 224 + 32 * j0);
+}
+
+__device__ __forceinline__ int first_cluster_of_row(long long x, int R, int G) {
+  return (int)(((x + 1) * G + R - 1) / R) - 1;
+}
+
+// cycle counters for tools/pair_diag.py (written only when the debug option has bit 32): per cluster
+// [0] MMA warp total, [1] wait acc_empty, [2] wait full, [3] wait peer_full, [4] issue + commits,
+// [5] epilogue group 0 total, [6] its wait acc_full, [7] its tcgen05.ld / st / arrive, [8] its pack + store, [9] its statistics
+__device__ long long g_pair_prof[74 * 16];
+
+// input rows (with the halo rows of every segment) of a cluster's range, in load order
+struct RowWalk {
+  long long r, r_end;
+  int h, pr, iy, iy1;
+  bool valid;
+  __device__ RowWalk(long long r_begin, long long r_end_, int h_) : r(r_begin), r_end(r_end_), h(h_) { start_seg(); }
+  __device__ void start_seg() {
+    valid = r < r_end;
+    if (!valid) return;
+    pr = (int)(r / h);
+    const int y0 = (int)(r % h);
+    const int seg = (int)min((long long)(h - y0), r_end - r);
+    iy = max(y0 - 1, 0);
+    iy1 = min(y0 + seg, h - 1);
+    r += seg;
+  }
+  __device__ void next() {
+    if (++iy > iy1) start_seg();
+  }
+};
+
+// ---- cluster / cta_group::2 primitives ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_rank(const void* local, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(local)), "r"(rank));
+  return r;
+}
+// Remote arrive with the default (.release.cta) semantics, as CUTLASS' ClusterBarrier::arrive(cta_id) does.  What the
+// arrivals of this kernel order is asynchronous-proxy work (TMA writes observed through complete_tx, tcgen05.ld / st
+// completed by tcgen05.wait + fence::before_thread_sync), not generic-proxy stores, so no cluster-scope fence is needed;
+// the .release.cluster / .acquire.cluster forms compile to MEMBAR.ALL.GPU + ERRBAR and CCTL.IVALL per arrive / wait and
+// made the first version of this kernel 1.7x slower than the single-CTA one (profiles/r2_rowconv_pair_ncu.txt).
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* slot_in_smem) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)), "n"(512)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(512) : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, 1, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc)
+      : "memory");
+}
+// arrives on the barrier at this shared-memory offset in BOTH CTAs once every MMA issued so far has completed
+__device__ __forceinline__ void umma2_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+               : "memory");
+}
+
+// 12 pair MMAs of one input row into one destination window: 3 kx shifts x 4 K steps.  The descriptors differ only in
+// their low word (start address), so the issue loop is two 32-bit adds and one UTCHMMA per MMA: the issuing warp is the
+// one serial resource of the kernel (230 instructions per row in the first version = 1 300 of 2 200 cycles per row).
+__device__ __forceinline__ void umma2_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, 1, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc)
+      : "memory");
+}
+__device__ __forceinline__ void issue_row(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc) {
+#pragma unroll
+  for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      umma2_lo(d_tmem, a_lo + (uint32_t)(kx * 8 + 2 * k), b_lo + (uint32_t)(kx * (kKxBytes >> 4) + 2 * k), desc_hi, idesc);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+rowconv_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                    const __grid_constant__ CUtensorMap tmY, PairParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sW = base;
+  uint8_t* sRing = base + kWeightBytes;
+  uint8_t* sOut = sRing + kSlots * kSlotBytes;
+  float* sStat = (float*)(sOut + 2 * kStageOutBytes);   // [2 groups][4 warps][2][64]
+  float* sBias = sStat + 2 * 4 * 128;
+  uint64_t* full = (uint64_t*)(sBias + kC);        // [kSlots] this CTA's input row has landed
+  uint64_t* peer_full = full + kSlots;             // [kSlots] rank 0 only: rank 1's row has landed
+  uint64_t* done = peer_full + kSlots;             // [kDone] the pair's MMAs of input row g are complete (multicast commit):
+                                                   //         frees ring slot g % kSlots AND completes an output row
+  uint64_t* w_full = done + kDone;
+  uint64_t* peer_w_full = w_full + 1;
+  uint64_t* acc_empty = peer_w_full + 1;           // [kAccSlots] rank 0 only: 4 + 4 epilogue warps
+  uint32_t* tmem_slot = (uint32_t*)(acc_empty + kAccSlots);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_rank();
+  const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kSlots; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&peer_full[s], 1);
+    }
+    for (int b = 0; b < kDone; ++b) mbar_init(&done[b], 1);
+    mbar_init(w_full, 1);
+    mbar_init(peer_w_full, 1);
+    for (int b = 0; b < kAccSlots; ++b) mbar_init(&acc_empty[b], 8);
+    fence_barrier_init();
+    prefetch_tmap(&tmX);
+    prefetch_tmap(&tmW);
+    prefetch_tmap(&tmY);
+  }
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + kC) sBias[threadIdx.x - 64] = p.bias ? p.bias[threadIdx.x - 64] : 0.f;
+  if (warp == 1) tmem_alloc_pair(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (warp >= 2 && warp < 6) {   // all accumulators start at zero: every MMA of this kernel accumulates
+    for (int c = 0; c < 512; c += 32) tmem_st32_zero(tmem + ((uint32_t)((warp & 3) * 32) << 16) + c);
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // barriers initialised and TMEM zeroed in BOTH CTAs before any remote arrive / pair MMA
+  tc_fence_after();
+
+  // contiguous range of flattened (image pair, row) rows for this cluster; this CTA works on image 2 * pair + rank
+  const long long r_begin = (long long)p.total_rows * cid / ncl;
+  const long long r_end = (long long)p.total_rows * (cid + 1) / ncl;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    const bool leader = elect_one();
+    if (leader) {
+      mbar_expect_tx(w_full, kWeightBytes);
+      const int hi = (int)(rank ^ (uint32_t)p.swap_halves);   // 0: lower half of the stacked rows, 1: upper half
+      for (int kx = 0; kx < 3; ++kx)
+        for (int cnt = 1; cnt <= 3; ++cnt)
+          for (int j0 = 0; j0 + cnt <= 3; ++j0) {
+            const int half = 32 * cnt;                         // rows this CTA holds of the 64 * cnt stacked rows
+            const int start = 64 * j0 + hi * half;
+            for (int i = 0; i < half; i += 32) {
+              const int R = start + i, j = R >> 6, co0 = R & 63;
+              const int tap = (2 - j) * 3 + kx;                // stacked block j maps input row r to output row r-1+j
+              tma_load_2d(sW + kx * kKxBytes + (case_row(j0, cnt) + i) * 128, &tmW, w_full, 0,
+                          (p.flip ? 8 - tap : tap) * kC + co0);
+            }
+          }
+    }
+    // The ring holds 4 rows (68 KB), less than the DRAM latency x bandwidth product at the rate the MMAs consume rows:
+    // a second cursor runs kPrefetch rows ahead of the loads and pulls those rows into L2.
+    RowWalk ld(r_begin, r_end, p.h), pf(r_begin, r_end, p.h);
+    for (int i = 0; i < kPrefetch && pf.valid; ++i, pf.next())
+      if (leader) tma_prefetch_4d(&tmX, 0, -1, pf.iy, 2 * pf.pr + (int)rank);
+    for (int g = 0; ld.valid; ++g, ld.next()) {
+      const int s = g % kSlots;
+      if (pf.valid) {
+        if (leader) tma_prefetch_4d(&tmX, 0, -1, pf.iy, 2 * pf.pr + (int)rank);
+        pf.next();
+      }
+      if (g >= kSlots) mbar_wait(&done[(g - kSlots) % kDone], ((g - kSlots) / kDone) & 1);   // row g - kSlots consumed
+      if (leader) {
+        if (p.dbg & 1) {
+          mbar_arrive(&full[s]);
+        } else {
+          mbar_expect_tx(&full[s], kRowBytes);
+          tma_load_4d(sRing + s * kSlotBytes, &tmX, &full[s], 0, -1, ld.iy, 2 * ld.pr + (int)rank);
+        }
+      }
+    }
+  } else if (warp == 1 && rank != 0) {
+    // ------------------------------------------------------------------ rank 1: forward "landed" to the issuing CTA
+    const uint32_t remote_w = map_to_rank(peer_w_full, 0);
+    const uint32_t remote_full0 = map_to_rank(&peer_full[0], 0);
+    mbar_wait(w_full, 0);
+    if (lane == 0) mbar_arrive_cluster(remote_w);
+    RowWalk ld(r_begin, r_end, p.h);
+    for (int g = 0; ld.valid; ++g, ld.next()) {
+      const int s = g % kSlots;
+      mbar_wait(&full[s], (g / kSlots) & 1);
+      if (lane == 0) mbar_arrive_cluster(remote_full0 + 8u * (uint32_t)s);
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ rank 0: MMA issuer for the pair
+    // One warp issues every MMA of two SMs; whatever it executes between two rows is time the tensor pipes may idle,
+    // so all per-row state is kept incrementally (no divisions), the descriptors are built from precomputed low words,
+    // and ONE commit per input row serves both the producers (ring slot free) and the epilogues (output row complete).
+    const bool leader = elect_one();
+    const uint64_t wdesc0 = make_smem_desc_sw128(smem_u32(sW), 16, 1024);
+    const uint64_t rdesc0 = make_smem_desc_sw128(smem_u32(sRing), 16, 1024);
+    const uint32_t desc_hi = (uint32_t)(wdesc0 >> 32), w_lo = (uint32_t)wdesc0, ring_lo = (uint32_t)rdesc0;
+    const uint32_t idesc1 = make_idesc_bf16(256, kC, 0, 0), idesc2 = make_idesc_bf16(256, 2 * kC, 0, 0),
+                   idesc3 = make_idesc_bf16(256, 3 * kC, 0, 0);
+    mbar_wait(w_full, 0);
+    mbar_wait_cluster(peer_w_full, 0);
+    const bool prof = (p.dbg & 32) != 0;
+    long long c_acc = 0, c_full = 0, c_peer = 0, c_issue = 0, t_start = clock64(), t0 = 0;
+    int sg = 0;                 // ring slot of the current input row, and its parity
+    uint32_t sph = 0;
+    int dg = 0;                 // done barrier of the current input row (g % kDone)
+    int o_touched = 0;          // output rows [0, o_touched) of this cluster have been claimed (their slot waited for)
+    int obase = 0;
+    long long r = r_begin;
+    while (r < r_end) {
+      const int y0 = (int)(r % p.h);
+      const int seg = (int)min((long long)(p.h - y0), r_end - r);
+      const int iy0 = max(y0 - 1, 0), iy1 = min(y0 + seg, p.h - 1);
+      for (int iy = iy0; iy <= iy1; ++iy) {
+        // output rows fed by this input row, clipped to the segment
+        const int t_lo = max(iy - 1, y0), t_hi = min(iy + 1, y0 + seg - 1);
+        const int o_lo = obase + (t_lo - y0), o_hi = obase + (t_hi - y0);
+        if (prof) t0 = clock64();
+        while (o_touched <= o_hi) {   // first touch: both epilogues have drained (and zeroed) the slot
+          mbar_wait_cluster(&acc_empty[o_touched & (kAccSlots - 1)], ((o_touched >> 3) & 1) ^ 1);
+          ++o_touched;
+        }
+        if (prof) { const long long t1 = clock64(); c_acc += t1 - t0; t0 = t1; }
+        const int slot = o_lo & (kAccSlots - 1);
+        const int cnt = o_hi - o_lo + 1;
+        const int j0 = t_lo - (iy - 1);
+        mbar_wait(&full[sg], sph);
+        if (prof) { const long long t1 = clock64(); c_full += t1 - t0; t0 = t1; }
+        mbar_wait_cluster(&peer_full[sg], sph);
+        if (prof) { const long long t1 = clock64(); c_peer += t1 - t0; t0 = t1; }
+        tc_fence_after();
+        const uint32_t a_lo = ring_lo + (uint32_t)(sg * (kSlotBytes >> 4));
+        if (leader && !(p.dbg & 2)) {
+          if (slot + cnt <= kAccSlots) {
+            issue_row(tmem + slot * kC, a_lo, w_lo + (uint32_t)(case_row(j0, cnt) * 8), desc_hi,
+                      cnt == 3 ? idesc3 : (cnt == 2 ? idesc2 : idesc1));
+          } else {   // the window wraps around the TMEM ring: the part up to the end, then the remainder from column 0
+            const int ca = kAccSlots - slot, cb = cnt - ca;
+            issue_row(tmem + slot * kC, a_lo, w_lo + (uint32_t)(case_row(j0, ca) * 8), desc_hi, ca == 2 ? idesc2 : idesc1);
+            issue_row(tmem, a_lo, w_lo + (uint32_t)(case_row(j0 + ca, cb) * 8), desc_hi, cb == 2 ? idesc2 : idesc1);
+          }
+        }
+        if (leader) umma2_commit(&done[dg]);
+        __syncwarp();
+        if (++sg == kSlots) { sg = 0; sph ^= 1; }
+        dg = (dg + 1) & (kDone - 1);
+        if (prof) c_issue += clock64() - t0;
+      }
+      obase += seg;
+      r += seg;
+    }
+    if (prof && lane == 0) {
+      long long* o = g_pair_prof + cid * 16;
+      o[0] = clock64() - t_start; o[1] = c_acc; o[2] = c_full; o[3] = c_peer; o[4] = c_issue;
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (both CTAs)
+    // Two groups of four warps take alternate output rows.  One group's row is a serial chain (wait, tcgen05.ld, zero,
+    // pack, fence, TMA store, statistics) with a single warp per scheduler; two groups give each chain two rows of time.
+    // Each group has its own staging tile, named barriers, statistics accumulators and partial-sum slot.
+    const int ew = warp - 2, gi = ew >> 2;
+    const int q = warp & 3;                   // TMEM lane quadrant this warp may read
+    const int x = q * 32 + lane;              // pixel within the row (TMEM lane)
+    const int et = (ew & 3) * 32 + lane;      // 0..127 within the group
+    const int cg = et & 7, pl = et >> 3;      // statistics role: channels [8 cg, 8 cg + 8), pixels pl + 16 i
+    const bool issuer = ((ew & 3) == 0) && (lane == 0);
+    const bool has_bias = p.bias != nullptr;
+    const int bar_pack = 1 + 2 * gi, bar_stat = 2 + 2 * gi;
+    uint8_t* stile = sOut + gi * kStageOutBytes;
+    float* sSt = sStat + gi * 512;
+    const uint32_t remote_acc_empty0 = map_to_rank(&acc_empty[0], 0);   // rank 0's barrier array (own one for rank 0)
+    float2 as[4], aq[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) as[k] = aq[k] = make_float2(0.f, 0.f);
+    const bool prof = (p.dbg & 32) != 0 && rank == 0 && ew == 0;
+    long long e_wait = 0, e_tmem = 0, e_pack = 0, e_stat = 0, e_start = clock64(), t0 = 0;
+    int orow = 0;
+    int gbase = 0;              // input rows of the previous segments
+    long long r = r_begin;
+    while (r < r_end) {
+      const int y0 = (int)(r % p.h), pr = (int)(r / p.h);
+      const int seg = (int)min((long long)(p.h - y0), r_end - r);
+      const int iy0 = max(y0 - 1, 0), iy1 = min(y0 + seg, p.h - 1);
+      const int n = 2 * pr + (int)rank;
+      for (int y = y0; y < y0 + seg; ++y, ++orow) {
+        if ((orow & 1) != gi) continue;
+        const int slot = orow & (kAccSlots - 1);
+        const int g = gbase + (min(y + 1, iy1) - iy0);       // the input row whose MMAs complete this output row
+        if (prof) t0 = clock64();
+        mbar_wait(&done[g & (kDone - 1)], (g / kDone) & 1);
+        if (prof) { const long long t1 = clock64(); e_wait += t1 - t0; t0 = t1; }
+        tc_fence_after();
+        uint32_t v0[32], v1[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + slot * kC, v0);
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + slot * kC + 32, v1);
+        tmem_ld_wait();
+        tmem_st32_zero(tmem + ((uint32_t)(q * 32) << 16) + slot * kC);        // hand the slot back zeroed
+        tmem_st32_zero(tmem + ((uint32_t)(q * 32) << 16) + slot * kC + 32);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(remote_acc_empty0 + 8u * (uint32_t)slot);
+        if (prof) { const long long t1 = clock64(); e_tmem += t1 - t0; t0 = t1; }
+        if (p.dbg & 4) continue;
+        // the TMA store this group issued two rows ago must have finished reading its staging tile
+        if (issuer) tma_store_wait_read<0>();
+        named_bar_sync(bar_pack, 128);
+        uint8_t* srow = stile + x * 128;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          float f[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v0[j + e]) + (has_bias ? sBias[j + e] : 0.f);
+          *reinterpret_cast<bf16x8*>(srow + (((j >> 3) ^ (x & 7)) << 4)) = pack8(f);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          float f[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v1[j + e]) + (has_bias ? sBias[32 + j + e] : 0.f);
+          *reinterpret_cast<bf16x8*>(srow + ((((32 + j) >> 3) ^ (x & 7)) << 4)) = pack8(f);
+        }
+        fence_proxy_async();
+        named_bar_sync(bar_pack, 128);
+        if (issuer && !(p.dbg & 8)) {
+          tma_store_4d(&tmY, stile, 0, 0, y, n);
+          tma_store_commit();
+        }
+        if (prof) { const long long t1 = clock64(); e_pack += t1 - t0; t0 = t1; }
+        if (p.partial && !(p.dbg & 16)) {
+          // per-channel sums over this row from the staged (rounded) values: one 16-byte chunk (8 channels) of 8
+          // pixels per thread, packed fp32x2 arithmetic; a warp reads 4 whole pixel lines per step -> conflict free
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int px = pl + 16 * i;
+            const uint4 v = *reinterpret_cast<const uint4*>(stile + px * 128 + ((cg ^ (px & 7)) << 4));
+            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 f = make_float2(__uint_as_float(w4[k] << 16), __uint_as_float(w4[k] & 0xffff0000u));
+              as[k] = __fadd2_rn(as[k], f);
+              aq[k] = __ffma2_rn(f, f, aq[k]);
+            }
+          }
+        }
+        if (prof) e_stat += clock64() - t0;
+      }
+      if (p.partial) {
+        // end of this CTA's rows of image n: fold the group's pixel lanes in fixed order (4 lanes by shuffle, the 4
+        // warps through shared memory) and publish the group's partial in its own slot - also when it is all zero
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          as[k].x += __shfl_xor_sync(0xffffffffu, as[k].x, 8);  as[k].y += __shfl_xor_sync(0xffffffffu, as[k].y, 8);
+          aq[k].x += __shfl_xor_sync(0xffffffffu, aq[k].x, 8);  aq[k].y += __shfl_xor_sync(0xffffffffu, aq[k].y, 8);
+          as[k].x += __shfl_xor_sync(0xffffffffu, as[k].x, 16); as[k].y += __shfl_xor_sync(0xffffffffu, as[k].y, 16);
+          aq[k].x += __shfl_xor_sync(0xffffffffu, aq[k].x, 16); aq[k].y += __shfl_xor_sync(0xffffffffu, aq[k].y, 16);
+        }
+        named_bar_sync(bar_stat, 128);   // previous use of the scratch is over
+        if (lane < 8) {
+          float* d0 = sSt + ((ew & 3) * 2 + 0) * kC + cg * 8;
+          float* d1 = sSt + ((ew & 3) * 2 + 1) * kC + cg * 8;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            d0[2 * k] = as[k].x; d0[2 * k + 1] = as[k].y;
+            d1[2 * k] = aq[k].x; d1[2 * k + 1] = aq[k].y;
+          }
+        }
+        named_bar_sync(bar_stat, 128);
+        const int b0 = first_cluster_of_row((long long)pr * p.h, p.total_rows, ncl);
+        const int part = cid - b0;
+        float* dst = p.partial + ((long long)n * p.parts + 2 * part + gi) * 2 * kC;
+        dst[et] = (sSt[et] + sSt[128 + et]) + (sSt[256 + et] + sSt[384 + et]);
+        if (y0 + seg == p.h && gi == 0)   // last cluster of this image: the unused slots must read as zero
+          for (int z = 2 * (part + 1); z < p.parts; ++z) p.partial[((long long)n * p.parts + z) * 2 * kC + et] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) as[k] = aq[k] = make_float2(0.f, 0.f);
+      }
+      gbase += iy1 - iy0 + 1;
+      r += seg;
+    }
+    if (issuer) tma_store_wait_read<0>();
+    if (prof && lane == 0) {
+      long long* o = g_pair_prof + cid * 16;
+      o[5] = clock64() - e_start; o[6] = e_wait; o[7] = e_tmem; o[8] = e_pack; o[9] = e_stat;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // nobody frees TMEM or leaves while the peer may still issue MMAs / remote arrives
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem);
+  }
+}
+
+int clusters_for(int total_rows) {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int cl = sms / 2;
+  return cl < total_rows ? cl : total_rows;
+}
+
+// partial slots per image: clusters that can share an image x 2 epilogue groups
+int parts_for(int pairs, int h) {
+  const int total = pairs * h, grid = clusters_for(total);
+  const int min_rows = total / grid;
+  return 2 * ((h + min_rows - 1) / min_rows + 1);
+}
+
+}  // namespace
+
+int crfr_rowconv_pair_supported(int n, int h) { return n >= 2 && (n & 1) == 0 && h >= 1; }
+
+size_t crfr_rowconv_pair_ws_bytes(int n, int h) {
+  if (!crfr_rowconv_pair_supported(n, h)) return 0;
+  return sizeof(float) * (size_t)n * parts_for(n / 2, h) * 2 * kC + 256;
+}
+
+// Same contract as crfr_rowconv (rowconv.cu); n must be even.
+int crfr_rowconv_pair(const void* src, int src_ld, int n, int h, const void* w_packed, int flip, const float* bias,
+                      void* dst, int dst_ld, float* stats, float eps, void* ws, size_t ws_bytes, cudaStream_t st) {
+  CRFR_CHECK_ARG(crfr_rowconv_pair_supported(n, h), "rowconv_pair: needs an even number of images");
+  CRFR_CHECK_ARG(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0 && ((uintptr_t)w_packed & 15) == 0 &&
+                     (src_ld & 7) == 0 && (dst_ld & 7) == 0,
+                 "rowconv_pair: pointers must be 16B aligned and ld a multiple of 8");
+  CUtensorMap tmX, tmW, tmY;
+  {
+    unsigned long long dims[4] = {(unsigned long long)kC, (unsigned long long)kW, (unsigned long long)h, (unsigned long long)n};
+    unsigned long long strides[3] = {(unsigned long long)dst_ld * 2, (unsigned long long)kW * dst_ld * 2, (unsigned long long)h * kW * dst_ld * 2};
+    unsigned int box[4] = {64, 128, 1, 1};
+    CRFR_TRY(crfr_tmap_encode_bf16(&tmY, dst, 4, dims, strides, box, "output"));
+  }
+  {
+    unsigned long long dims[4] = {(unsigned long long)kC, (unsigned long long)kW, (unsigned long long)h, (unsigned long long)n};
+    unsigned long long strides[3] = {(unsigned long long)src_ld * 2, (unsigned long long)kW * src_ld * 2, (unsigned long long)h * kW * src_ld * 2};
+    unsigned int box[4] = {64, 130, 1, 1};
+    CRFR_TRY(crfr_tmap_encode_bf16(&tmX, src, 4, dims, strides, box, "activation"));
+  }
+  {
+    unsigned long long dims[2] = {64, 9 * 64};
+    unsigned long long strides[1] = {128};
+    unsigned int box[2] = {64, 32};
+    CRFR_TRY(crfr_tmap_encode_bf16(&tmW, w_packed, 2, dims, strides, box, "weights"));
+  }
+  CRFR_CUDA(cudaFuncSetAttribute(rowconv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  PairParams p;
+  p.n = n; p.h = h; p.total_rows = (n / 2) * h; p.flip = flip;
+  p.swap_halves = crfr_opt(CRFR_OPT_PAIR_SWAP);
+  p.dbg = crfr_opt(CRFR_OPT_PAIR_DEBUG);
+  p.bias = bias;
+  p.partial = nullptr;
+  p.parts = 0;
+  if (stats) {
+    const size_t need = crfr_rowconv_pair_ws_bytes(n, h);
+    if (!ws || ws_bytes < need) {
+      crfr_set_error("rowconv_pair: workspace %zu < %zu", ws_bytes, need);
+      return CRFR_EWORKSPACE;
+    }
+    p.partial = (float*)ws;
+    p.parts = parts_for(n / 2, h);
+  }
+  rowconv_pair_kernel<<<2 * clusters_for(p.total_rows), kThreads, kSmemBytes, st>>>(tmX, tmW, tmY, p);
+  CRFR_COUNT_LAUNCH();
+  CRFR_LAUNCH_CHECK();
+  if (stats) CRFR_TRY(crfr_norm_finalize(p.partial, n, p.parts, h * kW, kC, eps, stats, st));
+  return CRFR_OK;
+}
+
+// debugging aid for tools/pair_diag.py: copies the cycle counters of the last profiled launch (option pair_debug bit 32)
+extern "C" int crfr_debug_pair_profile(long long* host_out, int count) {
+  CRFR_CHECK_ARG(host_out && count > 0 && count <= 74 * 16, "debug_pair_profile: bad argument");
+  CRFR_CUDA(cudaMemcpyFromSymbol(host_out, g_pair_prof, sizeof(long long) * (size_t)count));
+  return CRFR_OK;
+}

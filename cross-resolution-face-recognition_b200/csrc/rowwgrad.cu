@@ -236,12 +236,7 @@ int encode(CUtensorMap* m, const void* ptr, int n, int h, int ld, int box_w, con
 }
 
 int grid_for(int total_rows) {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-      sms = 148;
-  }
+  const int sms = crfr_sm_count();
   return sms < total_rows ? sms : total_rows;
 }
 
@@ -266,11 +261,8 @@ int crfr_rowwgrad(const void* x, int x_ld, const void* dy, int dy_ld, int n, int
   CUtensorMap tmX, tmDY;
   CRFR_TRY(encode(&tmX, x, n, h, x_ld, 132, "x"));
   CRFR_TRY(encode(&tmDY, dy, n, h, dy_ld, 128, "dy"));
-  static bool attr_done = false;
-  if (!attr_done) {
-    CRFR_CUDA(cudaFuncSetAttribute(rowwgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    attr_done = true;
-  }
+  static std::atomic<unsigned long long> attr_done{0};
+  CRFR_CUDA((cudaError_t)crfr_smem_attr(rowwgrad_kernel, kSmemBytes, attr_done));
   WgParams p;
   p.n = n; p.h = h; p.total_rows = n * h;
   p.slabs = (float*)ws;

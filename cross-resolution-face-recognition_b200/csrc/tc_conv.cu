@@ -288,25 +288,14 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
-int conv_sm_count() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-      sms = 148;
-  }
-  return sms;
-}
+int conv_sm_count() { return crfr_sm_count(); }
 
 template <int N>
 int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const ConvParams& p, int tiles,
                 cudaStream_t st) {
   using Cfg = ConvCfg<N>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    CRFR_CUDA(cudaFuncSetAttribute(tc_conv_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_done = true;
-  }
+  static std::atomic<unsigned long long> attr_done{0};
+  CRFR_CUDA((cudaError_t)crfr_smem_attr(tc_conv_kernel<N>, Cfg::kSmemBytes, attr_done));
   // persistent over pixel tiles: about one CTA per SM in total (column tiles share the pixel-tile walk)
   const int ncol = p.n_total / N;
   int ctas = (conv_sm_count() + ncol - 1) / ncol;
@@ -486,12 +475,8 @@ __global__ void wgrad_unpack_kernel(const float* __restrict__ G, float* __restri
 template <int N, int TAPS>
 int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmDY, const WgradParams& p, int splits, cudaStream_t st) {
   using Cfg = WgCfg<N, TAPS>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    CRFR_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<N, TAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   Cfg::kSmemBytes));
-    attr_done = true;
-  }
+  static std::atomic<unsigned long long> attr_done{0};
+  CRFR_CUDA((cudaError_t)crfr_smem_attr(tc_wgrad_kernel<N, TAPS>, Cfg::kSmemBytes, attr_done));
   const int gy = (TAPS == 3 ? 3 : 1) * (p.cout / N);
   tc_wgrad_kernel<N, TAPS><<<dim3(splits, gy, p.cin / 64), kConvThreads, Cfg::kSmemBytes, st>>>(tmX, tmDY, p);
   CRFR_COUNT_LAUNCH();
@@ -639,14 +624,7 @@ size_t crfr_tc_workspace_bytes(const crfr_conv_desc* d) {
   return wg;
 }
 
-static int rowconv_enabled() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("CRFR_ROWCONV");
-    v = e ? atoi(e) : 1;
-  }
-  return v;
-}
+static int rowconv_enabled() { return crfr_opt(CRFR_OPT_ROWCONV); }
 
 int crfr_tc_conv(const crfr_conv_desc* d, int dgrad, const void* src, const void* w_packed, const float* bias,
                  void* dst, float* stats, float eps, void* ws, size_t ws_bytes, cudaStream_t st) {

@@ -40,6 +40,9 @@ unsigned long long crfr_launch_count(void);
  *   "norm_fwd_stream": crfr_norm_act_fwd as 0 = register-staged kernel, 1 = persistent TMA-fed kernel (default where the
  *                    views are TMA-addressable); identical results bit for bit. */
 int crfr_set_option(const char* name, int value);
+/* debugging aid (tools/pair_diag.py): cycle counters of the last rowconv pair-kernel launch made with option
+ * "pair_debug" bit 32; 16 counters per cluster */
+int crfr_debug_pair_profile(long long* host_out, int count);
 /* 1 if the engine can run the shape (h,w,cin,cout,k,stride,pad), else 0 */
 int crfr_conv_engine_supported(int engine, int op, int h, int w, int cin, int cout, int k, int stride, int pad);
 

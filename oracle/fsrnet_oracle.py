@@ -335,6 +335,15 @@ class ForcedPrecision(Precision):
         return x + (f - xd)
 
 
+class ForcedExact(ForcedPrecision):
+    """Forced forward, NO gradient rounding: the exact (fp32) backward of the stored forward tensors.  The yardstick
+    for how much deviation bf16 gradient storage itself causes (about 1e-3 per sqrt(stored gradient) along the chain:
+    ~1.1e-2 after the ~180 roundings between the loss and the first coarse layer, profiles/r2_forced_gradient_depth.txt)."""
+
+    def qg(self, x):
+        return x
+
+
 FP32 = Precision("fp32")
 
 

@@ -201,3 +201,33 @@ def test_rowconv_ragged_row_ranges(cuda, n, h):
     _, _, st2 = ops.conv_fwd(nhwc_from(x), ops.pack_conv_weight(w.cuda()), c, c, 3, 1, 1, engine=L.ENGINE_TCGEN05,
                              want_stats=True)
     assert torch.equal(dw, dw2) and torch.equal(st, st2)
+
+
+@pytest.mark.parametrize("n,h", [(2, 1), (2, 2), (6, 3), (300, 1), (40, 16), (8, 50), (2, 128), (34, 128)])
+def test_rowconv_pair_kernel_is_bit_identical(cuda, n, h):
+    """The cta_group::2 row-streaming kernel (rowconv2.cu: two CTAs walk the same rows of two images, one M = 256 MMA
+    per K step for the pair) against the single-CTA kernel on the paired row-block partitioning: 1-row segments, ranges
+    that start / end inside an image, TMEM-ring wraps, clusters that span several image pairs.  Same MMA order per
+    output element, so forward and dgrad must agree BIT FOR BIT; the statistics differ only in fp32 summation order."""
+    from crfr_b200 import _lib as L, ops
+    g = torch.Generator().manual_seed(500 + n + h)
+    c, w_ = 64, 128
+    x = bf16_round(torch.randn(n, c, h, w_, generator=g))
+    w = bf16_round(torch.randn(c, c, 3, 3, generator=g) * 0.05)
+    b = torch.randn(c, generator=g)
+    ref = F.conv2d(x, w, b, 1, 1)
+    res = {}
+    try:
+        for pair in (0, 1):
+            L.call("crfr_set_option", b"rowconv_pair", pair)
+            y, _, st = ops.conv_fwd(nhwc_from(x), ops.pack_conv_weight(w.cuda()), c, c, 3, 1, 1, bias=b.cuda(),
+                                    engine=L.ENGINE_TCGEN05, want_stats=True)
+            dx = ops.conv_dgrad(nhwc_from(x), ops.pack_conv_weight(w.cuda(), for_dgrad=True), (n, h, w_, c), c, c, 3, 1, 1,
+                                engine=L.ENGINE_TCGEN05)
+            torch.cuda.synchronize()
+            res[pair] = (y, st, dx)
+    finally:
+        L.call("crfr_set_option", b"rowconv_pair", 1)
+    assert rel_err(to_nchw(res[1][0]), ref) < BF16_TOL
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][2], res[1][2])
+    assert rel_err(res[1][1], res[0][1]) < 1e-5

@@ -294,10 +294,128 @@ void run2(int iters, int a_tiles, Res* d_res) {
          (double)r.cycles / (4.0 * iters), flops / (ms * 1e-3) / 1e12, ms, err == cudaSuccess ? "" : cudaGetErrorString(err));
 }
 
+// ---- replica of the rowconv PAIR issue pattern (rowconv2.cu): per row 12 pair-MMAs of N = 192 (3 kx x 4 k-steps), A from
+// a 4-slot ring of 17 KB rows, B = the per-rank 96-row half of three 40 KB kx blocks, D rotating over 8 x 64 columns.
+// variant bit0: +128 B kx shift on A; bit1: four extra warps hammer shared memory; bit2: B fixed (kx block 0 only);
+// bit3: random operand data; bit4: D fixed
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) rowpattern2_kernel(int rows, int variant, Res* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  __shared__ volatile int stop;
+  const int ring_bytes = 4 * 17408, w_bytes = 3 * 40960, extra = 32768;
+  for (int i = threadIdx.x; i < (ring_bytes + w_bytes + extra) / 16; i += blockDim.x) {
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (variant & 8) {
+      uint32_t h = (uint32_t)i * 2654435761u + blockIdx.x * 40503u;
+      uint32_t w[4];
+      for (int j = 0; j < 4; ++j) {
+        h = h * 1664525u + 1013904223u;
+        const uint32_t lo = 0x3f00u | ((h >> 9) & 0x80ffu), hi = 0x3f00u | ((h >> 17) & 0x80ffu);
+        w[j] = lo | (hi << 16);
+      }
+      v = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    ((uint4*)base)[i] = v;
+  }
+  if (threadIdx.x == 0) { mbar_init(&bar, 1); fence_barrier_init(); stop = 0; }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "n"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  cluster_sync();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t rank = cluster_rank();
+  if (warp == 0) {
+    const bool leader = elect_one();
+    if (rank == 0) {
+      const uint32_t idesc = make_idesc_bf16(256, 192, 0, 0);
+      const uint64_t adesc0 = make_smem_desc_sw128(smem_u32(base), 16, 1024);
+      const uint64_t bdesc0 = make_smem_desc_sw128(smem_u32(base + ring_bytes), 16, 1024);
+      long long t0 = clock64();
+      for (int it = 0; it < rows; ++it) {
+        const uint64_t rowd = adesc0 + (uint64_t)(((it % 4) * 17408) >> 4);
+        const uint32_t d = tmem + ((variant & 16) ? 0 : (it % 6) * 64);
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t ad = rowd + (uint64_t)((((variant & 1) ? kx * 128 : 0) >> 4) + 2 * k);
+            const uint64_t bd = bdesc0 + (uint64_t)(((((variant & 4) ? 0 : kx) * 40960) >> 4) + 2 * k);
+            if (leader) umma2_bf16(d, ad, bd, idesc, 1u);
+          }
+        __syncwarp();
+      }
+      if (leader)
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                     ::"r"(smem_u32(&bar)), "h"((uint16_t)3) : "memory");
+      __syncwarp();
+      mbar_wait(&bar, 0);
+      long long t1 = clock64();
+      if (leader && blockIdx.x == 0) out->cycles = t1 - t0;
+    } else {
+      mbar_wait(&bar, 0);
+    }
+    stop = 1;
+  } else if (warp >= 4) {
+    uint8_t* scratch = base + ring_bytes + w_bytes;
+    uint4 v = make_uint4(lane, 1, 2, 3);
+    if (variant & 2) {
+      while (!stop) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          *reinterpret_cast<uint4*>(scratch + ((warp - 4) * 8192) + ((j * 32 + lane) * 16)) = v;
+          v.x += reinterpret_cast<uint4*>(scratch + ((warp - 4) * 8192) + (((7 - j) * 32 + lane) * 16))->y;
+        }
+      }
+    }
+    if (v.x == 0x9abcdef) out->cycles = 0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+  }
+}
+
+void run_pattern2(int rows, int variant, Res* d_res) {
+  const int smem = 4 * 17408 + 3 * 40960 + 32768 + 2048;
+  cudaFuncSetAttribute(rowpattern2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  rowpattern2_kernel<<<148, 256, smem>>>(rows, variant, d_res);
+  cudaError_t err = cudaDeviceSynchronize();
+  if (err != cudaSuccess) { printf("rowpattern2 variant=%d: %s\n", variant, cudaGetErrorString(err)); return; }
+  cudaEventRecord(e0);
+  rowpattern2_kernel<<<148, 256, smem>>>(rows, variant, d_res);
+  cudaEventRecord(e1);
+  err = cudaDeviceSynchronize();
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  Res r;
+  cudaMemcpy(&r, d_res, sizeof(r), cudaMemcpyDeviceToHost);
+  printf("rowpattern2 (pair) variant=%2d: %7.1f cycles/pair-MMA  %7.1f cycles/row  %7.1f TFLOP/s (wall %.3f ms) %s\n", variant,
+         (double)r.cycles / (12.0 * rows), (double)r.cycles / rows, 2.0 * 256 * 192 * 16 * 12.0 * rows * 74 / (ms * 1e-3) / 1e12,
+         ms, err == cudaSuccess ? "" : cudaGetErrorString(err));
+}
+
 int main(int argc, char** argv) {
   Res* d_res;
   cudaMalloc(&d_res, sizeof(Res));
   const int iters = 4000;
+  if (argc > 1 && atoi(argv[1]) == 3) {   // pair row pattern: what costs what
+    for (int v : {0, 1, 4, 5, 16, 17, 8, 9, 2, 3, 11}) run_pattern2(4000, v, d_res);
+    for (int v : {0, 1, 8, 9}) run_pattern(4000, v, d_res);
+    return 0;
+  }
   if (argc > 1 && atoi(argv[1]) == 2) {   // cta_group::2 issue rate next to the single-CTA SS figures
     run<128>(iters, 0, 8, d_res);
     run<192>(iters, 0, 8, d_res);
