@@ -34,15 +34,34 @@ constexpr int kXRowBytes = 132 * 128;      // X row with halo: x = -1 .. 130 (sh
 constexpr int kXSlotBytes = 17 * 1024;
 constexpr int kXSlots = 4;
 constexpr int kDyRowBytes = 128 * 128;
-constexpr int kDySlots = 7;
+constexpr int kDyRing = 6;                 // dY ring positions ...
+constexpr int kDySlots = kDyRing + 2;      // ... plus two MIRROR slots: rows at ring positions 0 and 1 are also loaded behind the
+                                           // last position, so the three consecutive dY rows of an X row are always contiguous
+                                           // in shared memory (one N = 192 MMA, never a split where the ring wraps)
+constexpr int kDone = 8;                   // ring of "X row consumed" barriers
+constexpr int kPrefetch = 10;              // rows pulled into L2 ahead of the shared-memory rings
 constexpr int kThreads = 192;
 constexpr int kSlabFloats = 9 * kC * kC;
 constexpr int kSmemBytes = kXSlots * kXSlotBytes + kDySlots * kDyRowBytes + 1024 + 512;
+static_assert(kSmemBytes <= 232448, "shared memory budget");
 
 struct WgParams {
   int n, h, total_rows;
   float* slabs;   // [gridDim.x][9][64][64]
 };
+
+// One MMA: descriptors that differ only in their low word (start address) from precomputed bases - the issuing warp is the
+// serial resource of a single-issuer kernel (see rowconv2.cu): two 32-bit adds and one UTCHMMA per MMA.
+__device__ __forceinline__ void umma_lo(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %3};\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "setp.ne.b32 p, 1, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc)
+      : "memory");
+}
 
 __global__ void __launch_bounds__(kThreads, 1)
 rowwgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY, WgParams p) {
@@ -51,23 +70,17 @@ rowwgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   uint8_t* sX = base;
   uint8_t* sDY = base + kXSlots * kXSlotBytes;
   uint64_t* full_x = (uint64_t*)(sDY + kDySlots * kDyRowBytes);
-  uint64_t* empty_x = full_x + kXSlots;
-  uint64_t* full_dy = empty_x + kXSlots;
-  uint64_t* empty_dy = full_dy + kDySlots;
-  uint64_t* done = empty_dy + kDySlots;
-  uint32_t* tmem_slot = (uint32_t*)(done + 1);
+  uint64_t* full_dy = full_x + kXSlots;       // [kDyRing]
+  uint64_t* done = full_dy + kDyRing;         // [kDone] the MMAs of X row g are complete: frees its X slot and dY row g - 1
+  uint64_t* fin = done + kDone;
+  uint32_t* tmem_slot = (uint32_t*)(fin + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kXSlots; ++s) {
-      mbar_init(&full_x[s], 1);
-      mbar_init(&empty_x[s], 1);
-    }
-    for (int s = 0; s < kDySlots; ++s) {
-      mbar_init(&full_dy[s], 1);
-      mbar_init(&empty_dy[s], 1);
-    }
-    mbar_init(done, 1);
+    for (int s = 0; s < kXSlots; ++s) mbar_init(&full_x[s], 1);
+    for (int s = 0; s < kDyRing; ++s) mbar_init(&full_dy[s], 1);
+    for (int s = 0; s < kDone; ++s) mbar_init(&done[s], 1);
+    mbar_init(fin, 1);
     fence_barrier_init();
     prefetch_tmap(&tmX);
     prefetch_tmap(&tmDY);
@@ -77,32 +90,71 @@ rowwgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  if (warp >= 2) {   // the accumulators start at zero: every MMA of this kernel accumulates
+    for (int c = 0; c < 512; c += 32) tmem_st32_zero(tmem + ((uint32_t)((warp & 3) * 32) << 16) + c);
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
 
   const long long r_begin = (long long)p.total_rows * blockIdx.x / gridDim.x;
   const long long r_end = (long long)p.total_rows * (blockIdx.x + 1) / gridDim.x;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
+    // Load order = use order: per segment dY rows y0-1 .. y0+seg (out-of-image rows are zero filled) interleaved with X
+    // rows y0 .. y0+seg-1.  X row i (running index gx) uses dY rows i, i+1, i+2 of its segment; a dY row is free again
+    // when the last X row that uses it is done, an X slot when its own row is done: both are the SAME event, the one
+    // commit per X row on done[gx % kDone].  A prefetch cursor runs kPrefetch rows ahead and pulls rows into L2 (the
+    // rings hold less than the DRAM latency x bandwidth product at the rate the MMAs consume rows).
     const bool leader = elect_one();
+    int last_user[kDyRing];                       // running X index of the last user of the dY row in each ring position
+#pragma unroll
+    for (int i = 0; i < kDyRing; ++i) last_user[i] = -1;
     int gx = 0, gd = 0;
-    long long r = r_begin;
+    long long r = r_begin, rp = r_begin;          // load cursor / prefetch cursor (segment starts)
+    int pf_i = -1, pf_seg = 0, pf_n = 0, pf_y0 = 0, pf_ahead = 0;
+    bool pf_valid = false;
+    auto pf_start = [&]() {
+      pf_valid = rp < r_end;
+      if (!pf_valid) return;
+      pf_n = (int)(rp / p.h); pf_y0 = (int)(rp % p.h);
+      pf_seg = (int)min((long long)(p.h - pf_y0), r_end - rp);
+      pf_i = -1;
+      rp += pf_seg;
+    };
+    auto pf_step = [&]() {   // prefetch the dY row (and X row) of one step of the load order
+      if (!pf_valid) return;
+      const int yd = pf_y0 + pf_i;
+      if (leader && yd >= 0 && yd < p.h) tma_prefetch_4d(&tmDY, 0, 0, yd, pf_n);
+      if (leader && pf_i >= 1) tma_prefetch_4d(&tmX, 0, -1, pf_y0 + pf_i - 1, pf_n);
+      if (++pf_i > pf_seg) pf_start();
+    };
+    pf_start();
+    for (; pf_ahead < kPrefetch; ++pf_ahead) pf_step();
     while (r < r_end) {
       const int n = (int)(r / p.h), y0 = (int)(r % p.h);
       const int seg = (int)min((long long)(p.h - y0), r_end - r);
-      // dY rows y0-1 .. y0+seg (out-of-image rows are zero filled), X rows y0 .. y0+seg-1; interleaved in use order
+      const int gx0 = gx;
       for (int i = -1; i <= seg; ++i) {
+        pf_step();
         {
-          const int s = gd % kDySlots;
-          mbar_wait(&empty_dy[s], ((gd / kDySlots) & 1) ^ 1);
+          const int pos = gd % kDyRing;
+          const int lu = last_user[pos];
+          if (lu >= 0) mbar_wait(&done[lu & (kDone - 1)], (lu / kDone) & 1);
+          last_user[pos] = gx0 + min(i + 1, seg - 1);   // dY row j = i + 1 of the segment is used by X rows j-2 .. j
           if (leader) {
-            mbar_expect_tx(&full_dy[s], kDyRowBytes);
-            tma_load_4d(sDY + s * kDyRowBytes, &tmDY, &full_dy[s], 0, 0, y0 + i, n);
+            const bool mirror = pos < 2;
+            mbar_expect_tx(&full_dy[pos], mirror ? 2 * kDyRowBytes : kDyRowBytes);
+            tma_load_4d(sDY + pos * kDyRowBytes, &tmDY, &full_dy[pos], 0, 0, y0 + i, n);
+            if (mirror) tma_load_4d(sDY + (kDyRing + pos) * kDyRowBytes, &tmDY, &full_dy[pos], 0, 0, y0 + i, n);
           }
           ++gd;
         }
         if (i >= 1) {   // X row y0+i-1 is first needed once dY row y0+i has been requested
           const int s = gx % kXSlots;
-          mbar_wait(&empty_x[s], ((gx / kXSlots) & 1) ^ 1);
+          if (gx >= kXSlots) mbar_wait(&done[(gx - kXSlots) & (kDone - 1)], ((gx - kXSlots) / kDone) & 1);
           if (leader) {
             mbar_expect_tx(&full_x[s], kXRowBytes);
             tma_load_4d(sX + s * kXSlotBytes, &tmX, &full_x[s], 0, -1, y0 + i - 1, n);
@@ -118,66 +170,58 @@ rowwgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     // A: two 64-channel atoms 128 B apart (the kx and kx+1 views of the same row); B: N atoms one dY slot apart
     const uint64_t xdesc0 = make_smem_desc_sw128(smem_u32(sX), 128, 1024);
     const uint64_t dydesc0 = make_smem_desc_sw128(smem_u32(sDY), kDyRowBytes, 1024);
-    int gx = 0, gd = 0;   // gd: ring index of dY row (q-1) of the current X row
-    bool first = true;
+    const uint32_t desc_hi = (uint32_t)(xdesc0 >> 32), x_lo = (uint32_t)xdesc0, dy_lo = (uint32_t)dydesc0;
+    const uint32_t idesc = make_idesc_bf16(128, 3 * kC, 1, 1);
+    int sx = 0;  uint32_t xph = 0;    // X ring slot of the current row and its parity
+    int dp = 0;  uint32_t dph = 0;    // dY ring position of the current row's first dY row (q - 1), and its parity
+    int dg = 0;
     long long r = r_begin;
     while (r < r_end) {
       const int y0 = (int)(r % p.h);
       const int seg = (int)min((long long)(p.h - y0), r_end - r);
-      for (int i = 0; i < seg; ++i, ++gx, ++gd) {
-        const int sx = gx % kXSlots;
+      for (int i = 0; i < seg; ++i) {
+        // dY rows q-1, q, q+1 = ring positions dp, dp+1, dp+2 (mod kDyRing); the first two were waited for by the previous
+        // row of the segment
+        int p1 = dp + 1, p2 = dp + 2;
+        uint32_t ph1 = dph, ph2 = dph;
+        if (p1 >= kDyRing) { p1 -= kDyRing; ph1 ^= 1; }
+        if (p2 >= kDyRing) { p2 -= kDyRing; ph2 ^= 1; }
         if (i == 0) {
-          mbar_wait(&full_dy[gd % kDySlots], (gd / kDySlots) & 1);
-          mbar_wait(&full_dy[(gd + 1) % kDySlots], ((gd + 1) / kDySlots) & 1);
+          mbar_wait(&full_dy[dp], dph);
+          mbar_wait(&full_dy[p1], ph1);
         }
-        mbar_wait(&full_dy[(gd + 2) % kDySlots], ((gd + 2) / kDySlots) & 1);
-        mbar_wait(&full_x[sx], (gx / kXSlots) & 1);
+        mbar_wait(&full_dy[p2], ph2);
+        mbar_wait(&full_x[sx], xph);
         tc_fence_after();
-        const uint64_t xd = xdesc0 + (uint64_t)((sx * kXSlotBytes) >> 4);
-        const int s0 = gd % kDySlots;
-        const int cnt1 = min(3, kDySlots - s0);     // dY rows before the ring wraps
-        const uint64_t b0 = dydesc0 + (uint64_t)((s0 * kDyRowBytes) >> 4);
-        const uint32_t id1 = make_idesc_bf16(128, kC * cnt1, 1, 1);
-        const uint32_t id2 = make_idesc_bf16(128, kC * (cnt1 < 3 ? 3 - cnt1 : 1), 1, 1);
-        const uint32_t d2 = tmem + kC * cnt1;
-        const uint32_t acc0 = first ? 0u : 1u;
+        const uint32_t a01 = x_lo + (uint32_t)(sx * (kXSlotBytes >> 4));
+        const uint32_t a2x = a01 + (uint32_t)(256 >> 4);
+        const uint32_t b0 = dy_lo + (uint32_t)(dp * (kDyRowBytes >> 4));   // contiguous thanks to the mirror slots
         if (leader) {
 #pragma unroll
           for (int k = 0; k < 8; ++k) {             // 8 x 16 pixels
-            const uint32_t acc = k == 0 ? acc0 : 1u;
-            const uint64_t a01 = xd + (uint64_t)(k * (2048 >> 4));
-            const uint64_t a2x = a01 + (uint64_t)(256 >> 4);
-            umma_bf16(tmem, a01, b0 + (uint64_t)(k * (2048 >> 4)), id1, acc);
-            umma_bf16(tmem + 256, a2x, b0 + (uint64_t)(k * (2048 >> 4)), id1, acc);
-            if (cnt1 < 3) {
-              umma_bf16(d2, a01, dydesc0 + (uint64_t)(k * (2048 >> 4)), id2, acc);
-              umma_bf16(d2 + 256, a2x, dydesc0 + (uint64_t)(k * (2048 >> 4)), id2, acc);
-            }
+            umma_lo(tmem, a01 + (uint32_t)(k * (2048 >> 4)), b0 + (uint32_t)(k * (2048 >> 4)), desc_hi, idesc);
+            umma_lo(tmem + 256, a2x + (uint32_t)(k * (2048 >> 4)), b0 + (uint32_t)(k * (2048 >> 4)), desc_hi, idesc);
           }
-        }
-        first = false;
-        if (leader) {
-          umma_commit(&empty_x[sx]);
-          umma_commit(&empty_dy[s0]);               // dY row q-1 is not needed by later X rows
+          umma_commit(&done[dg]);
         }
         __syncwarp();
+        if (++sx == kXSlots) { sx = 0; xph ^= 1; }
+        if (++dp == kDyRing) { dp = 0; dph ^= 1; }
+        dg = (dg + 1) & (kDone - 1);
       }
-      if (leader) {                                  // the last two dY rows of the segment
-        umma_commit(&empty_dy[gd % kDySlots]);
-        umma_commit(&empty_dy[(gd + 1) % kDySlots]);
-      }
-      __syncwarp();
-      gd += 2;
+      // the segment's last two dY rows belong to no later X row of this segment
+      dp += 2;
+      if (dp >= kDyRing) { dp -= kDyRing; dph ^= 1; }
       r += seg;
     }
-    if (leader) umma_commit(done);
+    if (leader) umma_commit(fin);
     __syncwarp();
   } else {
     // ------------------------------------------------------------------ epilogue: TMEM -> this CTA's slab
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int ci = row & 63;
-    mbar_wait(done, 0);
+    mbar_wait(fin, 0);
     tc_fence_after();
     float* slab = p.slabs + (size_t)blockIdx.x * kSlabFloats;
 #pragma unroll
@@ -208,22 +252,29 @@ rowwgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   }
 }
 
-// dW[co][ci][t] += sum_slabs slab[s][t][ci][co]   (fixed order)
+// dW[co][ci][t] += sum_slabs slab[s][t][ci][co]   (fixed order).  64 outputs per block; four thread groups each sum every
+// fourth slab with four independent accumulators (the first version - one thread per output walking all 148 slabs - was a
+// 14 us latency chain, 0.5 ms per training step), then the groups are folded in fixed order through shared memory.
 __global__ void __launch_bounds__(256)
 slab_reduce_kernel(const float* __restrict__ slabs, int nslabs, float* __restrict__ dw) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // over [t][ci][co]
-  if (i >= kSlabFloats) return;
+  __shared__ float part[4][64];
+  const int o = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  const int i = blockIdx.x * 64 + o;   // over [t][ci][co]
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int s = 0;
-  for (; s + 4 <= nslabs; s += 4) {
+  int s = grp;
+  for (; s + 12 < nslabs; s += 16) {
     s0 += slabs[(size_t)s * kSlabFloats + i];
-    s1 += slabs[(size_t)(s + 1) * kSlabFloats + i];
-    s2 += slabs[(size_t)(s + 2) * kSlabFloats + i];
-    s3 += slabs[(size_t)(s + 3) * kSlabFloats + i];
+    s1 += slabs[(size_t)(s + 4) * kSlabFloats + i];
+    s2 += slabs[(size_t)(s + 8) * kSlabFloats + i];
+    s3 += slabs[(size_t)(s + 12) * kSlabFloats + i];
   }
-  for (; s < nslabs; ++s) s0 += slabs[(size_t)s * kSlabFloats + i];
-  const int co = i & 63, ci = (i >> 6) & 63, t = i >> 12;
-  dw[((size_t)co * kC + ci) * 9 + t] += (s0 + s1) + (s2 + s3);
+  for (; s < nslabs; s += 4) s0 += slabs[(size_t)s * kSlabFloats + i];
+  part[grp][o] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (grp == 0) {
+    const int co = i & 63, ci = (i >> 6) & 63, t = i >> 12;
+    dw[((size_t)co * kC + ci) * 9 + t] += (part[0][o] + part[1][o]) + (part[2][o] + part[3][o]);
+  }
 }
 
 int encode(CUtensorMap* m, const void* ptr, int n, int h, int ld, int box_w, const char* what) {
@@ -270,7 +321,7 @@ int crfr_rowwgrad(const void* x, int x_ld, const void* dy, int dy_ld, int n, int
   rowwgrad_kernel<<<grid, kThreads, kSmemBytes, st>>>(tmX, tmDY, p);
   CRFR_COUNT_LAUNCH();
   CRFR_LAUNCH_CHECK();
-  slab_reduce_kernel<<<crfr_cdiv(kSlabFloats, 256), 256, 0, st>>>((const float*)ws, grid, dw);
+  slab_reduce_kernel<<<kSlabFloats / 64, 256, 0, st>>>((const float*)ws, grid, dw);
   CRFR_COUNT_LAUNCH();
   CRFR_LAUNCH_CHECK();
   return CRFR_OK;
