@@ -29,13 +29,21 @@ class TapeEntry(C.Structure):
                 ("in_off", cll), ("stats_off", cll), ("w_idx", ci), ("has_res", ci)]
 
 
+class FsrnetSectionIO(C.Structure):
+    _fields_ = [("section", ci), ("batch", ci), ("size", ci), ("x", vp), ("out", vp * 3)]
+
+
+FSRNET_COARSE, FSRNET_ENCODER, FSRNET_PRIOR, FSRNET_DECODER = 0, 1, 2, 3
+
+
 class ResnetIO(C.Structure):
     _fields_ = [("batch", ci), ("size", ci), ("x", vp), ("emb", vp), ("feat", vp * 4), ("training", ci),
                 ("momentum", cf), ("eps", cf)]
 
 
 class KdIO(C.Structure):
-    _fields_ = [("batch", ci), ("size", ci), ("x", vp), ("momentum", cf), ("eps", cf), ("assistant_grad_to_student", ci)]
+    _fields_ = [("batch", ci), ("size", ci), ("x", vp), ("momentum", cf), ("eps", cf), ("assistant_grad_to_student", ci),
+                ("x_lr", vp), ("teacher_ir50", ci), ("events", vp * 2)]
 
 
 RESNET34_NPARAMS, RESNET34_NBN = 114, 38
@@ -86,16 +94,23 @@ SIGNATURES = {
     "crfr_verify_counts": (ci, [vp, vp, cll, cf, vp, vp]),
     "crfr_verify_sweep": (ci, [vp, vp, vp, ci, vp, ci, vp, vp]),
     "crfr_pair_verify": (ci, [vp, vp, cll, ci, cf, vp, vp, vp]),
+    "crfr_linear_workspace_bytes": (csz, [ci, ci, ci, ci]),
+    "crfr_linear_fwd": (ci, [vp, ci, ci, ci, vp, vp, ci, vp, vp, csz, vp]),
+    "crfr_linear_bwd": (ci, [vp, vp, ci, ci, ci, vp, ci, vp, vp, vp, vp, csz, vp]),
     "crfr_fsrnet_workspace_bytes": (csz, [ci, ci, ci]),
     "crfr_fsrnet_tape": (ci, [ci, ci, ci, C.POINTER(TapeEntry), ci]),
     "crfr_fsrnet_forward": (ci, [ci, vp, C.POINTER(FsrnetIO), ci, vp, csz, vp]),
     "crfr_fsrnet_backward": (ci, [ci, vp, vp, C.POINTER(FsrnetIO), vp, vp, vp, vp, vp, csz, vp]),
+    "crfr_fsrnet_section_workspace_bytes": (csz, [ci, ci, ci, ci]),
+    "crfr_fsrnet_section_forward": (ci, [ci, vp, C.POINTER(FsrnetSectionIO), ci, vp, csz, vp]),
+    "crfr_fsrnet_section_backward": (ci, [ci, vp, vp, C.POINTER(FsrnetSectionIO), vp, vp, vp, csz, vp]),
     "crfr_fsrnet_train_step": (ci, [ci, vp, vp, C.POINTER(FsrnetIO), vp, vp, csz, vp]),
     "crfr_bn_update_running": (ci, [vp, vp, vp, vp, ci, cll, cf, cf, vp]),
     "crfr_bn_running_to_stats": (ci, [vp, vp, ci, cf, vp, vp]),
     "crfr_resnet34_workspace_bytes": (csz, [ci, ci, ci]),
     "crfr_resnet34_forward": (ci, [ci, vp, vp, C.POINTER(ResnetIO), vp, csz, vp]),
     "crfr_kd_workspace_bytes": (csz, [ci, ci]),
+    "crfr_kd_workspace_bytes_ex": (csz, [ci, ci, ci]),
     "crfr_kd_train_step": (ci, [ci, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(KdIO), vp, vp, csz, vp]),
     "crfr_ir50_workspace_bytes": (csz, [ci, ci]),
     "crfr_ir50_forward": (ci, [ci, vp, vp, C.POINTER(ResnetIO), vp, csz, vp]),

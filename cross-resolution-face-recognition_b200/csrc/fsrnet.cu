@@ -167,6 +167,11 @@ struct Net {
   bf16* d_coarse4 = nullptr;
   bf16* d_out4 = nullptr;
   bf16* d_heads = nullptr;
+  // sub-network mode (crfr_fsrnet_section_*): one of the four sub-networks on its own, fp32 NCHW in and out
+  int section = -1;
+  const crfr_fsrnet_section_io* sio = nullptr;
+  bool want_dx = false;       // backward: the gradient w.r.t. the section input is requested
+  Tensor sec_in, sec_feat;    // the section's bf16 input (NHWC) and its bf16 feature output
 
   void* alloc(size_t bytes) {
     size_t a = (off + 1023) & ~(size_t)1023;
@@ -348,7 +353,7 @@ struct Net {
 
   // fc (11) and fc_landmark (97), model/FSRnet.py:391-392: both 1x1 heads as ONE tcgen05 GEMM over the combined
   // [128 = 11 | 97 | zero pad][128] weight (fp32 NHWC result), then split + transposed into the two fp32 NCHW outputs
-  void heads(const Tensor& x) {
+  void heads(const Tensor& x, float* landmark, float* parsing) {
     const long long npix = (long long)x.n * x.h * x.w;
     bf16* wc = (bf16*)alloc((size_t)kHeadsPad * 128 * sizeof(bf16));       // [co][ci]
     float* bc = (float*)alloc(kHeadsPad * sizeof(float));
@@ -360,7 +365,7 @@ struct Net {
       TcGemm g{x.p, x.n, x.h, x.w, 128, x.ld, wc, 1, 0, 1, kHeadsPad, kHeadsPad, yf, kHeadsPad, 1, bc};
       check(crfr_tc_gemm(g, st));
       const long long total = npix * 108;
-      heads_split_kernel<<<crfr_cdiv(total, 256), 256, 0, st>>>(yf, io->parsing, io->landmark, x.n, x.h * x.w);
+      heads_split_kernel<<<crfr_cdiv(total, 256), 256, 0, st>>>(yf, parsing, landmark, x.n, x.h * x.w);
       CRFR_COUNT_LAUNCH();
       check(cudaGetLastError() == cudaSuccess ? CRFR_OK : CRFR_ECUDA);
     }
@@ -369,8 +374,7 @@ struct Net {
     tape.push_back(op);
   }
 
-  void forward() {
-    const int B = io->batch, S = io->size;
+  void prologue(int B, int S) {
     for (int i = 0; i < CRFR_FSRNET_NPARAMS; ++i) packed_fwd[i] = packed_bwd[i] = nullptr;
     // shared scratch: norm partials / wgrad accumulators of the largest layer
     scratch_bytes = crfr_norm_ws_bytes(B, S * S, 128) + sizeof(float) * 9 * 192 * 128 + 4096;
@@ -392,56 +396,121 @@ struct Net {
       scratch2_bytes = crfr_tc_workspace_bytes(&big) + sizeof(float) * 9 * 192 * 128 + 4096;
       scratch2 = alloc(scratch2_bytes);
     }
-    x4 = new_tensor(B, S, S, 4);
-    x4.c = 3;
-    if (run()) check(crfr_nchw_f32_to_nhwc_bf16(io->x, x4.p, B, 3, S, S, 4, 4, st));
+  }
 
-    // ---- coarse SR network (:328-340) ----
+  // fp32 NCHW 3-channel image -> bf16 NHWC4
+  Tensor image_in(const float* src, int B, int S) {
+    Tensor t = new_tensor(B, S, S, 4);
+    t.c = 3;
+    if (run()) check(crfr_nchw_f32_to_nhwc_bf16(src, t.p, B, 3, S, S, 4, 4, st));
+    return t;
+  }
+
+  // ---- coarse SR network (:328-340): returns the 64-channel feature; coarse image -> y_nchw (+ bf16 copy y4) ----
+  Tensor coarse_net(const Tensor& xin, float* coarse_nchw, Tensor* c4, bool x_grad) {
     float* s0;
-    Tensor y = conv(x4, C_CONV_IN_W, C_CONV_IN_B, 64, 3, 1, 1, false, &s0, nullptr, false);
+    Tensor y = conv(xin, C_CONV_IN_W, C_CONV_IN_B, 64, 3, 1, 1, false, &s0, nullptr, x_grad);
     Tensor a = norm_act(y, s0, C_BN_MID_W, C_BN_MID_B, C_RELU, nullptr);
     a = res_stack(a, C_RES, 3);
     Tensor feat = norm_act(a, stats_of(a), C_BN_MID_W, C_BN_MID_B, -1, nullptr);
-    coarse4 = new_tensor(B, S, S, 4);
-    coarse4.c = 3;
-    img_conv(feat, C_CONV_MID_W, C_CONV_MID_B, io->coarse, &coarse4);
+    img_conv(feat, C_CONV_MID_W, C_CONV_MID_B, coarse_nchw, c4);
+    return feat;
+  }
 
-    const int Q = S / 4;
-    cat = new_tensor(B, Q, Q, 192);
-    Tensor pe_view = view(cat, 0, 128), enc_view = view(cat, 128, 64);
-
-    // ---- fine SR encoder (:359-379) ----
-    tape_enc_start = (int)tape.size();
+  // ---- fine SR encoder (:359-379) ----
+  Tensor encoder_net(const Tensor& img4, const Tensor* out_view, bool x_grad) {
     float* se;
-    Tensor ye = conv(coarse4, E_CONV_IN_W, E_CONV_IN_B, 64, 7, 4, 3, false, &se);
+    Tensor ye = conv(img4, E_CONV_IN_W, E_CONV_IN_B, 64, 7, 4, 3, false, &se, nullptr, x_grad);
     Tensor ae = norm_act(ye, se, E_BN_MID_W, E_BN_MID_B, E_RELU, nullptr);
     ae = res_stack(ae, E_RES, 3);
     float* se2;
     Tensor ye2 = conv(ae, E_CONV_END_W, E_CONV_END_B, 64, 3, 1, 1, false, &se2);
-    norm_act(ye2, se2, E_BN_MID_W, E_BN_MID_B, E_RELU, nullptr, &enc_view);
+    return norm_act(ye2, se2, E_BN_MID_W, E_BN_MID_B, E_RELU, nullptr, out_view);
+  }
 
-    // ---- prior estimation network (:408-426) ----
+  // ---- prior estimation network (:408-426): 128-channel feature; heads -> landmark / parsing (fp32 NCHW) ----
+  Tensor prior_net(const Tensor& img4, const Tensor* out_view, float* landmark, float* parsing, bool x_grad) {
     float* sp;
-    Tensor yp = conv(coarse4, P_CONV_W, P_CONV_B, 128, 7, 4, 3, false, &sp);
+    Tensor yp = conv(img4, P_CONV_W, P_CONV_B, 128, 7, 4, 3, false, &sp, nullptr, x_grad);
     Tensor ap = norm_act(yp, sp, P_BN_W, P_BN_B, P_RELU, nullptr);
     ap = res_stack(ap, P_RES, 1);
-    Tensor pe = hourglass(2, ap, &pe_view);
-    heads(pe);
+    Tensor pe = hourglass(2, ap, out_view);
+    heads(pe, landmark, parsing);
+    return pe;
+  }
 
-    // ---- fine SR decoder (:448-459) on cat(prior, encoder) (:505) ----
-    tape_dec_start = (int)tape.size();
-    Op cop;
-    cop.kind = OP_CAT; cop.a = pe_view; cop.b = enc_view; cop.out = cat;
-    tape.push_back(cop);
+  // ---- fine SR decoder (:448-459) ----
+  void decoder_net(const Tensor& in192, float* out_nchw) {
     float* sd;
-    Tensor yd = conv(cat, D_CONV_IN_W, D_CONV_IN_B, 64, 3, 1, 1, false, &sd);
+    Tensor yd = conv(in192, D_CONV_IN_W, D_CONV_IN_B, 64, 3, 1, 1, false, &sd);
     Tensor ad = norm_act(yd, sd, D_BN_MID_W, D_BN_MID_B, D_RELU, nullptr);
     float* sd2;
     Tensor yd2 = conv(ad, D_DECONV_W, D_DECONV_B, 64, 7, 4, 2, true, &sd2);
     Tensor ad2 = norm_act(yd2, sd2, D_BN_MID_W, D_BN_MID_B, D_RELU, nullptr);
     ad2 = res_stack(ad2, D_RES, 3);
     Tensor fd = norm_act(ad2, stats_of(ad2), D_BN_MID_W, D_BN_MID_B, -1, nullptr);
-    img_conv(fd, D_CONV_OUT_W, D_CONV_OUT_B, io->out, nullptr);
+    img_conv(fd, D_CONV_OUT_W, D_CONV_OUT_B, out_nchw, nullptr);
+  }
+
+  void forward() {
+    if (section >= 0) {
+      forward_section();
+      return;
+    }
+    const int B = io->batch, S = io->size;
+    prologue(B, S);
+    x4 = image_in(io->x, B, S);
+    coarse4 = new_tensor(B, S, S, 4);
+    coarse4.c = 3;
+    coarse_net(x4, io->coarse, &coarse4, false);
+
+    const int Q = S / 4;
+    cat = new_tensor(B, Q, Q, 192);
+    Tensor pe_view = view(cat, 0, 128), enc_view = view(cat, 128, 64);
+    tape_enc_start = (int)tape.size();
+    encoder_net(coarse4, &enc_view, true);
+    prior_net(coarse4, &pe_view, io->landmark, io->parsing, true);
+
+    // ---- decoder on cat(prior, encoder) (:505) ----
+    tape_dec_start = (int)tape.size();
+    Op cop;
+    cop.kind = OP_CAT; cop.a = pe_view; cop.b = enc_view; cop.out = cat;
+    tape.push_back(cop);
+    decoder_net(cat, io->out);
+  }
+
+  // One sub-network on its own (Course_SR_Network / Fine_SR_Encoder / Prior_Estimation_Network / Fine_SR_Decoder
+  // .forward of the reference, model/FSRnet.py:328-340, 359-379, 408-426, 448-459): fp32 NCHW in and out.
+  void forward_section() {
+    const int B = sio->batch, S = sio->size, Q = S / 4;
+    prologue(B, S);
+    tape_enc_start = tape_dec_start = -1;
+    switch (section) {
+      case CRFR_FSRNET_COARSE: {
+        sec_in = image_in(sio->x, B, S);
+        sec_feat = coarse_net(sec_in, sio->out[1], nullptr, want_dx);
+        if (run()) check(crfr_nhwc_bf16_to_nchw_f32(sec_feat.p, sio->out[0], B, 64, S, S, sec_feat.ld, st));
+        break;
+      }
+      case CRFR_FSRNET_ENCODER: {
+        sec_in = image_in(sio->x, B, S);
+        sec_feat = encoder_net(sec_in, nullptr, want_dx);
+        if (run()) check(crfr_nhwc_bf16_to_nchw_f32(sec_feat.p, sio->out[0], B, 64, Q, Q, sec_feat.ld, st));
+        break;
+      }
+      case CRFR_FSRNET_PRIOR: {
+        sec_in = image_in(sio->x, B, S);
+        sec_feat = prior_net(sec_in, nullptr, sio->out[1], sio->out[2], want_dx);
+        if (run()) check(crfr_nhwc_bf16_to_nchw_f32(sec_feat.p, sio->out[0], B, 128, Q, Q, sec_feat.ld, st));
+        break;
+      }
+      default: {   // CRFR_FSRNET_DECODER: [B,192,Q,Q] -> [B,3,S,S]
+        sec_in = new_tensor(B, Q, Q, 192);
+        if (run()) check(crfr_nchw_f32_to_nhwc_bf16(sio->x, sec_in.p, B, 192, Q, Q, 192, 192, st));
+        decoder_net(sec_in, sio->out[0]);
+        break;
+      }
+    }
   }
 
   // ---- backward helpers ----
@@ -473,7 +542,7 @@ struct Net {
 
   void record_bucket(int k) {
     join_side();
-    if (run() && io->bucket_events[k])
+    if (run() && io && io->bucket_events[k])
       check(cudaEventRecord((cudaEvent_t)io->bucket_events[k], st) == cudaSuccess ? CRFR_OK : CRFR_ECUDA);
   }
 
@@ -642,9 +711,10 @@ void init_net(Net& net, int engine, const float* const* params, float* const* gr
   net.ws = (uint8_t*)ws; net.ws_bytes = ws_bytes; net.exec = exec; net.training = training;
 }
 
-int check_io(const crfr_fsrnet_io* io, const char* who) {
+int check_io(const crfr_fsrnet_io* io, const char* who, bool need_tensors = true) {
   CRFR_CHECK_ARG(io && io->batch > 0 && io->size >= 32 && io->size % 16 == 0, "%s: batch/size invalid (size must be a multiple of 16, >= 32)", who);
-  CRFR_CHECK_ARG(io->x && io->coarse && io->out && io->landmark && io->parsing, "%s: null tensor pointer", who);
+  // the backward pass reads neither the input nor the outputs (everything it needs was saved in the workspace)
+  CRFR_CHECK_ARG(!need_tensors || (io->x && io->coarse && io->out && io->landmark && io->parsing), "%s: null tensor pointer", who);
   return CRFR_OK;
 }
 
@@ -661,7 +731,7 @@ namespace {
 
 // allocate the output-gradient buffers right after the forward region (same order in sizing and execution)
 void alloc_out_grads(Net& net, bool coarse, bool out, bool heads) {
-  const int B = net.io->batch, S = net.io->size, Q = S / 4;
+  const int B = net.io ? net.io->batch : net.sio->batch, S = net.io ? net.io->size : net.sio->size, Q = S / 4;
   net.d_coarse4 = coarse ? (bf16*)net.alloc((size_t)B * S * S * 4 * sizeof(bf16)) : nullptr;
   net.d_out4 = out ? (bf16*)net.alloc((size_t)B * S * S * 4 * sizeof(bf16)) : nullptr;
   net.d_heads = heads ? (bf16*)net.alloc((size_t)B * Q * Q * kHeadsPad * sizeof(bf16)) : nullptr;
@@ -742,7 +812,7 @@ extern "C" int crfr_fsrnet_backward(int engine, const float* const* host_params,
                                     const crfr_fsrnet_io* io, const float* d_coarse, const float* d_out,
                                     const float* d_landmark, const float* d_parsing, void* ws, size_t ws_bytes,
                                     void* stream) {
-  CRFR_TRY(check_io(io, "fsrnet_backward"));
+  CRFR_TRY(check_io(io, "fsrnet_backward", false));
   CRFR_CHECK_ARG(host_params && host_grads && ws, "fsrnet_backward: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   Net net;
@@ -769,6 +839,134 @@ extern "C" int crfr_fsrnet_backward(int engine, const float* const* host_params,
     if (d_landmark) CRFR_TRY(crfr_nchw_f32_to_nhwc_bf16(d_landmark, net.d_heads + 11, B, 97, Q, Q, kHeadsPad, 97, stream));
   }
   net.backward();
+  return net.err;
+}
+
+// ---- sub-networks on their own -----------------------------------------------------------------------------------
+namespace {
+
+int check_section(const crfr_fsrnet_section_io* io, const char* who) {
+  CRFR_CHECK_ARG(io && io->section >= 0 && io->section <= 3 && io->batch > 0 && io->size >= 32 && io->size % 16 == 0,
+                 "%s: section/batch/size invalid (size must be a multiple of 16, >= 32)", who);
+  const int nout = io->section == CRFR_FSRNET_COARSE ? 2 : (io->section == CRFR_FSRNET_PRIOR ? 3 : 1);
+  CRFR_CHECK_ARG(io->x, "%s: null input", who);
+  for (int i = 0; i < nout; ++i) CRFR_CHECK_ARG(io->out[i], "%s: null output %d", who, i);
+  return CRFR_OK;
+}
+
+void init_section(Net& net, int engine, const float* const* params, float* const* grads, const crfr_fsrnet_section_io* sio,
+                  void* ws, size_t ws_bytes, cudaStream_t st, bool exec, bool training) {
+  init_net(net, engine, params, grads, nullptr, ws, ws_bytes, st, exec, training);
+  net.section = sio->section;
+  net.sio = sio;
+}
+
+}  // namespace
+
+extern "C" size_t crfr_fsrnet_section_workspace_bytes(int section, int batch, int size, int training) {
+  if (section < 0 || section > 3 || batch <= 0 || size < 32 || size % 16) return 0;
+  crfr_fsrnet_section_io sio = {};
+  sio.section = section; sio.batch = batch; sio.size = size;
+  Net net;
+  init_section(net, CRFR_ENGINE_AUTO, nullptr, nullptr, &sio, nullptr, ~(size_t)0 >> 2, nullptr, false, training != 0);
+  net.want_dx = true;
+  net.forward();
+  if (training) {
+    const int Q = size / 4;
+    alloc_out_grads(net, false, section == CRFR_FSRNET_COARSE || section == CRFR_FSRNET_DECODER,
+                    section == CRFR_FSRNET_PRIOR);
+    if (section != CRFR_FSRNET_DECODER) {   // gradient of the feature output, converted to bf16 NHWC
+      net.add_slot(net.sec_feat, (bf16*)net.alloc((size_t)batch * net.sec_feat.h * net.sec_feat.w * net.sec_feat.c * sizeof(bf16)),
+                   net.sec_feat.c);
+    }
+    (void)Q;
+    net.backward();
+    if (net.has_grad(net.sec_in)) net.squash(net.sec_in, 1);
+  }
+  return net.off + 65536;
+}
+
+extern "C" int crfr_fsrnet_section_forward(int engine, const float* const* host_params, const crfr_fsrnet_section_io* io,
+                                           int training, void* ws, size_t ws_bytes, void* stream) {
+  CRFR_TRY(check_section(io, "fsrnet_section_forward"));
+  CRFR_CHECK_ARG(host_params && ws, "fsrnet_section_forward: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  {   // batched weight packing (dry run collects the jobs)
+    std::vector<crfr_pack_job> jobs;
+    Net dry;
+    init_section(dry, engine, host_params, nullptr, io, ws, ws_bytes, st, false, training != 0);
+    dry.want_dx = true;
+    dry.collect = &jobs;
+    dry.forward();
+    if (!dry.ok()) return dry.err;
+    CRFR_TRY(crfr_pack_weight_batch(jobs.data(), (int)jobs.size(), st));
+  }
+  Net net;
+  init_section(net, engine, host_params, nullptr, io, ws, ws_bytes, st, true, training != 0);
+  net.want_dx = true;
+  net.packs_done = true;
+  net.forward();
+  return net.err;
+}
+
+extern "C" int crfr_fsrnet_section_backward(int engine, const float* const* host_params, float* const* host_grads,
+                                            const crfr_fsrnet_section_io* io, const float* const* d_out, float* dx,
+                                            void* ws, size_t ws_bytes, void* stream) {
+  CRFR_TRY(check_section(io, "fsrnet_section_backward"));
+  CRFR_CHECK_ARG(host_params && host_grads && ws && d_out, "fsrnet_section_backward: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = io->batch, S = io->size, Q = S / 4, sec = io->section;
+  Net net;
+  init_section(net, engine, host_params, host_grads, io, ws, ws_bytes, st, false, true);
+  net.want_dx = dx != nullptr;   // (only decides whether the first layer's input gradient is computed; the forward
+  net.forward();                 //  layout does not depend on it)  dry run: rebuild the tape and the saved offsets
+  if (!net.ok()) return net.err;
+  net.exec = true;
+  const float* d_img = sec == CRFR_FSRNET_COARSE ? d_out[1] : (sec == CRFR_FSRNET_DECODER ? d_out[0] : nullptr);
+  const float* d_feat = sec == CRFR_FSRNET_DECODER ? nullptr : d_out[0];
+  const float* d_lm = sec == CRFR_FSRNET_PRIOR ? d_out[1] : nullptr;
+  const float* d_ps = sec == CRFR_FSRNET_PRIOR ? d_out[2] : nullptr;
+  alloc_out_grads(net, false, sec == CRFR_FSRNET_COARSE || sec == CRFR_FSRNET_DECODER, sec == CRFR_FSRNET_PRIOR);
+  bf16* gfeat = nullptr;
+  if (sec != CRFR_FSRNET_DECODER)
+    gfeat = (bf16*)net.alloc((size_t)B * net.sec_feat.h * net.sec_feat.w * net.sec_feat.c * sizeof(bf16));
+  if (!net.ok()) return net.err;
+  if (net.d_out4) {
+    if (d_img) {
+      CRFR_TRY(crfr_nchw_f32_to_nhwc_bf16(d_img, net.d_out4, B, 3, S, S, 4, 4, stream));
+      float* db = host_grads[sec == CRFR_FSRNET_COARSE ? C_CONV_MID_B : D_CONV_OUT_B];
+      if (db) CRFR_TRY(crfr_nchw_chansum(d_img, B, 3, S * S, db, net.scratch, net.scratch_bytes, st));
+    } else {
+      net.d_out4 = nullptr;   // no gradient for the image output: the image conv is skipped
+    }
+  }
+  if (net.d_heads) {
+    if (d_lm || d_ps) {
+      CRFR_CUDA(cudaMemsetAsync(net.d_heads, 0, (size_t)B * Q * Q * kHeadsPad * sizeof(bf16), st));
+      if (d_ps) CRFR_TRY(crfr_nchw_f32_to_nhwc_bf16(d_ps, net.d_heads, B, 11, Q, Q, kHeadsPad, 11, stream));
+      if (d_lm) CRFR_TRY(crfr_nchw_f32_to_nhwc_bf16(d_lm, net.d_heads + 11, B, 97, Q, Q, kHeadsPad, 97, stream));
+    } else {
+      net.d_heads = nullptr;
+    }
+  }
+  if (gfeat && d_feat) {
+    const Tensor& f = net.sec_feat;
+    CRFR_TRY(crfr_nchw_f32_to_nhwc_bf16(d_feat, gfeat, B, f.c, f.h, f.w, f.c, f.c, stream));
+    net.add_slot(f, gfeat, f.c);
+  }
+  net.backward();
+  if (!net.ok()) return net.err;
+  if (dx) {
+    const Tensor& x = net.sec_in;
+    if (!net.has_grad(x)) {
+      crfr_set_error("fsrnet_section_backward: no gradient reached the section input");
+      return CRFR_EINVAL;
+    }
+    net.squash(x, 1);
+    if (!net.ok()) return net.err;
+    const Slot g = net.slots[x.id][0];
+    CRFR_TRY(crfr_nhwc_bf16_to_nchw_f32(g.p, dx, B, x.c, x.h, x.w, g.ld, stream));
+  }
   return net.err;
 }
 

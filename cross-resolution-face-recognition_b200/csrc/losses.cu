@@ -128,12 +128,16 @@ ce2d_kernel(const float* __restrict__ x, const long long* __restrict__ target, l
     float se = 0.f;
     for (int ch = 0; ch < c; ++ch) se += expf(xs[(long long)ch * hw] - m);
     float lse = m + logf(se);
-    int tg = (int)target[i];
-    acc = lse - xs[(long long)tg * hw];
+    const long long tl = target[i];
+    // torch's NLLLoss raises on a label outside [0, c); a kernel cannot raise, so such a pixel poisons the loss with NaN
+    // (loud, and no out-of-bounds read) and contributes no gradient
+    const bool valid = tl >= 0 && tl < c;
+    const int tg = valid ? (int)tl : 0;
+    acc = valid ? lse - xs[(long long)tg * hw] : __int_as_float(0x7fc00000);
     if (dx)
       for (int ch = 0; ch < c; ++ch) {
         float sm = expf(xs[(long long)ch * hw] - lse);
-        dx[i * dx_ld + coff + ch] = __float2bfloat16_rn(gcoef * (sm - (ch == tg ? 1.f : 0.f)));
+        dx[i * dx_ld + coff + ch] = __float2bfloat16_rn(valid ? gcoef * (sm - (ch == tg ? 1.f : 0.f)) : 0.f);
       }
   }
   block_partial(acc, partial);

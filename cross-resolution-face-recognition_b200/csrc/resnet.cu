@@ -346,6 +346,10 @@ struct Net {
         a = bn(r, p + 5, 0, &sc, -1, bi + 1);                          // res_layer.4 + shortcut
         p += 7; bi += 2;
         in_ch = d;
+        if (u == units[l] - 1) {   // stage output: 64@56^2, 128@28^2, 256@14^2, 512@7^2 - the shapes of ResNet_34's x1..x4,
+          feat[l] = a;             // i.e. the t_k of the residual-KD loss when IR_50 is the teacher (distill_main.py:59,68-69)
+          to_nchw(a, io->feat[l]);
+        }
       }
     Tensor o = bn(a, 4, 0, nullptr, -1, 1);                            // output_layer.0 (Dropout: identity in eval)
     Tensor y = linear(o, 6);                                           // output_layer.3
@@ -521,9 +525,10 @@ __global__ void kd_total_kernel(const float* __restrict__ parts, float* __restri
 struct KdLayout {
   size_t teacher, train, scratch, total;
 };
-KdLayout kd_layout(int batch, int size) {
+KdLayout kd_layout(int batch, int size, int teacher_ir50 = 0) {
   KdLayout l;
-  l.teacher = (crfr_resnet34_workspace_bytes(batch, size, 0) + 4095) & ~(size_t)4095;
+  l.teacher = ((teacher_ir50 ? crfr_ir50_workspace_bytes(batch, size) : crfr_resnet34_workspace_bytes(batch, size, 0)) + 4095) &
+              ~(size_t)4095;
   // + room for the second embedding-gradient slot of the student (L_s and L_a both reach s_emb)
   l.train = (crfr_resnet34_workspace_bytes(batch, size, 1) + (size_t)batch * kEmb * 2 + (4u << 20)) & ~(size_t)4095;
   l.scratch = 1 << 20;
@@ -537,6 +542,10 @@ extern "C" size_t crfr_kd_workspace_bytes(int batch, int size) {
   if (batch <= 0 || size != 112) return 0;
   return kd_layout(batch, size).total;
 }
+extern "C" size_t crfr_kd_workspace_bytes_ex(int batch, int size, int teacher_ir50) {
+  if (batch <= 0 || size != 112) return 0;
+  return kd_layout(batch, size, teacher_ir50).total;
+}
 
 extern "C" int crfr_kd_train_step(int engine, const float* const* teacher_params, void* const* teacher_buffers,
                                   const float* const* student_params, void* const* student_buffers,
@@ -547,7 +556,7 @@ extern "C" int crfr_kd_train_step(int engine, const float* const* teacher_params
   CRFR_CHECK_ARG(teacher_params && teacher_buffers && student_params && student_grads && assistant_params &&
                      assistant_grads && losses && ws,
                  "kd_train_step: null pointer");
-  const KdLayout lay = kd_layout(kio->batch, kio->size);
+  const KdLayout lay = kd_layout(kio->batch, kio->size, kio->teacher_ir50);
   if (ws_bytes < lay.total) {
     crfr_set_error("kd_train_step: workspace %zu < %zu", ws_bytes, lay.total);
     return CRFR_EWORKSPACE;
@@ -557,7 +566,8 @@ extern "C" int crfr_kd_train_step(int engine, const float* const* teacher_params
   crfr_resnet_io io_eval = {}, io_train = {};
   io_eval.batch = io_train.batch = kio->batch;
   io_eval.size = io_train.size = kio->size;
-  io_eval.x = io_train.x = kio->x;
+  io_eval.x = kio->x;                                  // HR batch for the teacher
+  io_train.x = kio->x_lr ? kio->x_lr : kio->x;         // LR batch (or the same one, as distill_main.py:59-61 feeds it)
   io_eval.momentum = io_train.momentum = kio->momentum;
   io_eval.eps = io_train.eps = kio->eps;
   io_eval.training = 0;
@@ -567,7 +577,8 @@ extern "C" int crfr_kd_train_step(int engine, const float* const* teacher_params
   init_net(S, engine, student_params, student_grads, student_buffers, &io_train, base + lay.teacher, lay.train, st, true);
   init_net(A, engine, assistant_params, assistant_grads, assistant_buffers, &io_train, base + lay.teacher + lay.train,
            lay.train, st, true);
-  T.forward();
+  if (kio->teacher_ir50) T.forward_ir50();
+  else T.forward();
   if (!T.ok()) return T.err;
   S.forward();
   if (!S.ok()) return S.err;
@@ -606,7 +617,9 @@ extern "C" int crfr_kd_train_step(int engine, const float* const* teacher_params
   CRFR_LAUNCH_CHECK();
   S.backward();
   if (!S.ok()) return S.err;
+  if (kio->events[0]) CRFR_CUDA(cudaEventRecord((cudaEvent_t)kio->events[0], st));   // student gradients are final
   A.backward();
+  if (A.ok() && kio->events[1]) CRFR_CUDA(cudaEventRecord((cudaEvent_t)kio->events[1], st));
   return A.err;
 }
 

@@ -111,7 +111,7 @@ class Backbone(Module):
                 if m.bias is not None:
                     m.bias.data.zero_()
 
-    def forward(self, x):
+    def _run(self, x, want_features):
         if not self._native:
             raise NotImplementedError("only IR_50([112, 112]) has a native network program")
         if self.training:
@@ -124,15 +124,30 @@ class Backbone(Module):
         x = x.contiguous().float()
         b = x.shape[0]
         emb = torch.empty((b, 512), dtype=torch.float32, device=x.device)
+        feats = [torch.empty((b, c, s, s), dtype=torch.float32, device=x.device)
+                 for c, s in ((64, 56), (128, 28), (256, 14), (512, 7))] if want_features else []
         params = [p.detach() for _, p in self.named_parameters()]
         buffers = [t for _, t in self.named_buffers()]
         ptab, btab = _Table(params, L.IR50_NPARAMS), _Table(buffers, 3 * L.IR50_NBN)
         io = L.ResnetIO()
         io.batch, io.size, io.x, io.emb = b, 112, x.data_ptr(), emb.data_ptr()
+        for i, f in enumerate(feats):
+            io.feat[i] = f.data_ptr()
         io.training, io.momentum, io.eps = 0, 0.1, 1e-5
         ws = ops.workspace(L.lib().crfr_ir50_workspace_bytes(b, 112))
         L.call("crfr_ir50_forward", self.engine, ptab.arr, btab.arr, C.byref(io), ws.data_ptr(), ws.numel(), ops.stream())
-        return emb
+        return emb, feats
+
+    def forward(self, x):
+        """ref: model_irse.py:167-172: the embedding only."""
+        return self._run(x, False)[0]
+
+    def forward_features(self, x):
+        """(embedding, x1, x2, x3, x4): the outputs of the four body stages next to the embedding - the tuple
+        distill_main.py:59 unpacks from its teacher, and the 'extracted layers' use of DISTILLATION/model/utils.py:36-52
+        (perceptual features, SUPER_RESOLUTION/train_FHN.py:255-265)."""
+        emb, feats = self._run(x, True)
+        return (emb,) + tuple(feats)
 
 
 def IR_50(input_size):

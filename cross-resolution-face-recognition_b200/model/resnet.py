@@ -191,39 +191,80 @@ def _flat_grads(net):
     return params, [flat[o:o + p.numel()].view(p.shape) for o, p in zip(offs, params)]
 
 
-def kd_train_step(teacher, student, assistant, x, assistant_grad_to_student=True):
+def _is_ir50(net):
+    from .model_irse import Backbone
+    return isinstance(net, Backbone) and net._native
+
+
+def _teacher_tables(teacher):
+    if _is_ir50(teacher):
+        params = [p.detach() for _, p in teacher.named_parameters()]
+        buffers = [t for _, t in teacher.named_buffers()]
+        return _TableOfPointers(params, L.IR50_NPARAMS), _TableOfPointers(buffers, 3 * L.IR50_NBN), 1
+    return (_TableOfPointers([p.detach() for p in teacher.ordered_parameters()], L.RESNET34_NPARAMS),
+            _TableOfPointers(teacher.ordered_buffers(), 3 * L.RESNET34_NBN), 0)
+
+
+def check_kd_nets(teacher, student, assistant):
+    if not ((isinstance(teacher, ResNet) and teacher._native) or _is_ir50(teacher)):
+        raise NotImplementedError("the KD teacher must be a native ResNet_34 or IR_50")
+    for net in (student, assistant):
+        if not (isinstance(net, ResNet) and net._native):
+            raise NotImplementedError("the KD student and assistant must be native ResNet_34 modules")
+    if teacher.training or not (student.training and assistant.training):
+        raise RuntimeError("KD step: teacher.eval(), student.train(), assistant.train() expected (distill_main.py:41-43)")
+
+
+def check_kd_input(x, name="x"):
+    if not x.is_cuda or x.dim() != 4 or tuple(x.shape[1:]) != (3, 112, 112):
+        raise ValueError("expected a CUDA tensor %s [B,3,112,112], got %s" % (name, tuple(x.shape)))
+    return x.contiguous().float()
+
+
+def kd_native_call(teacher, student, assistant, x_hr, x_lr, stabs, atabs, losses, assistant_grad_to_student=True,
+                   events=None):
+    """crfr_kd_train_step on prepared tables: stabs / atabs = (params, buffers, grads) _TableOfPointers of the student and
+    the assistant (gradients are ACCUMULATED into the grads tables)."""
+    tp, tb, is_ir50 = _teacher_tables(teacher)
+    b = x_hr.shape[0]
+    io = L.KdIO()
+    io.batch, io.size, io.x = b, 112, x_hr.data_ptr()
+    io.x_lr = None if x_lr is None else x_lr.data_ptr()
+    io.teacher_ir50 = is_ir50
+    io.momentum, io.eps, io.assistant_grad_to_student = 0.1, 1e-5, int(bool(assistant_grad_to_student))
+    for i, e in enumerate(events or ()):
+        io.events[i] = e.cuda_event
+    ws = ops.workspace(L.lib().crfr_kd_workspace_bytes_ex(b, 112, is_ir50))
+    L.call("crfr_kd_train_step", student.engine, tp.arr, tb.arr, stabs[0].arr, stabs[1].arr, stabs[2].arr, atabs[0].arr,
+           atabs[1].arr, atabs[2].arr, C.byref(io), losses.data_ptr(), ws.data_ptr(), ws.numel(), ops.stream())
+
+
+def kd_train_step(teacher, student, assistant, x, x_lr=None, assistant_grad_to_student=True):
     """The residual knowledge-distillation step of distill_main.py:59-74 as ONE native call (crfr_kd_train_step):
     teacher forward (eval), student and assistant forward (train, BatchNorm buffers updated), the MSE terms of
     distill_main.py:63,68-70 on the bf16 features in place, and both backward passes.
 
+    ``x`` is the HR batch the teacher sees; the student and the assistant see ``x_lr`` when given ("HR teacher / LR
+    student"), else ``x`` as well (what distill_main.py:59-61 does).  The teacher is a native ``ResNet_34`` or ``IR_50``
+    (whose four stage outputs are the t_k).
+
     Sets ``p.grad`` of the student to d(L_s [+ L_a])/dp and of the assistant to dL_a/dp (overwriting), and returns the
     device tensor ``(L_s, L_a)``.  Equivalent to ``(mse(s_emb, t_emb) + sum_k kd(t_k, s_k, a_k)).backward()`` through
     the drop-in modules, without the fp32 NCHW round trip of the five outputs of each network."""
-    for net in (teacher, student, assistant):
-        if not (isinstance(net, ResNet) and net._native):
-            raise NotImplementedError("kd_train_step needs three native ResNet_34 modules")
-    if teacher.training or not (student.training and assistant.training):
-        raise RuntimeError("kd_train_step: teacher.eval(), student.train(), assistant.train() expected (distill_main.py:41-43)")
-    if not x.is_cuda or x.dim() != 4 or tuple(x.shape[1:]) != (3, 112, 112):
-        raise ValueError("expected a CUDA tensor [B,3,112,112], got %s" % (tuple(x.shape),))
-    x = x.contiguous().float()
-    b = x.shape[0]
-    tp = _TableOfPointers([p.detach() for p in teacher.ordered_parameters()], L.RESNET34_NPARAMS)
-    tb = _TableOfPointers(teacher.ordered_buffers(), 3 * L.RESNET34_NBN)
+    check_kd_nets(teacher, student, assistant)
+    x = check_kd_input(x)
+    if x_lr is not None:
+        x_lr = check_kd_input(x_lr, "x_lr")
+        if x_lr.shape[0] != x.shape[0]:
+            raise ValueError("x and x_lr must hold the same number of images")
     sparams, sgrads = _flat_grads(student)
     aparams, agrads = _flat_grads(assistant)
-    sp = _TableOfPointers([p.detach() for p in sparams], L.RESNET34_NPARAMS)
-    ap = _TableOfPointers([p.detach() for p in aparams], L.RESNET34_NPARAMS)
-    sb = _TableOfPointers(student.ordered_buffers(), 3 * L.RESNET34_NBN)
-    ab = _TableOfPointers(assistant.ordered_buffers(), 3 * L.RESNET34_NBN)
-    sg, ag = _TableOfPointers(sgrads, L.RESNET34_NPARAMS), _TableOfPointers(agrads, L.RESNET34_NPARAMS)
-    io = L.KdIO()
-    io.batch, io.size, io.x = b, 112, x.data_ptr()
-    io.momentum, io.eps, io.assistant_grad_to_student = 0.1, 1e-5, int(bool(assistant_grad_to_student))
+    stabs = (_TableOfPointers([p.detach() for p in sparams], L.RESNET34_NPARAMS),
+             _TableOfPointers(student.ordered_buffers(), 3 * L.RESNET34_NBN), _TableOfPointers(sgrads, L.RESNET34_NPARAMS))
+    atabs = (_TableOfPointers([p.detach() for p in aparams], L.RESNET34_NPARAMS),
+             _TableOfPointers(assistant.ordered_buffers(), 3 * L.RESNET34_NBN), _TableOfPointers(agrads, L.RESNET34_NPARAMS))
     losses = torch.empty((2,), dtype=torch.float32, device=x.device)
-    ws = ops.workspace(L.lib().crfr_kd_workspace_bytes(b, 112))
-    L.call("crfr_kd_train_step", student.engine, tp.arr, tb.arr, sp.arr, sb.arr, sg.arr, ap.arr, ab.arr, ag.arr,
-           C.byref(io), losses.data_ptr(), ws.data_ptr(), ws.numel(), ops.stream())
+    kd_native_call(teacher, student, assistant, x, x_lr, stabs, atabs, losses, assistant_grad_to_student)
     for p, g in zip(sparams, sgrads):
         p.grad = g
     for p, g in zip(aparams, agrads):

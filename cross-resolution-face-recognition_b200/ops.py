@@ -241,7 +241,7 @@ def loss_mse97(x, t, gscale=1.0, want_grad=True):
     loss = torch.empty((1,), dtype=torch.float32, device=x.device)
     dx = torch.empty((n, h, w, 4 if c < 8 else c), dtype=torch.bfloat16, device=x.device) if want_grad else None
     ws = _loss_ws(n, h * w)
-    L.call("crfr_loss_mse97", ptr(x.contiguous()), ptr(t.contiguous().float()), n, c, h * w, gscale, ptr(loss), ptr(dx),
+    L.call("crfr_loss_mse97", ptr(x.contiguous().float()), ptr(t.contiguous().float()), n, c, h * w, gscale, ptr(loss), ptr(dx),
            0 if dx is None else dx.shape[3], ptr(ws), ws.numel(), stream())
     return loss, dx
 
@@ -251,7 +251,7 @@ def loss_landmark(x, t, gscale=1.0, dx=None, coff=0):
     n, c, h, w = x.shape
     loss = torch.empty((1,), dtype=torch.float32, device=x.device)
     ws = _loss_ws(n, h * w)
-    L.call("crfr_loss_landmark", ptr(x.contiguous()), ptr(t.contiguous().float()), n, c, h * w, gscale, ptr(loss),
+    L.call("crfr_loss_landmark", ptr(x.contiguous().float()), ptr(t.contiguous().float()), n, c, h * w, gscale, ptr(loss),
            ptr(dx), 0 if dx is None else dx.shape[3], coff, ptr(ws), ws.numel(), stream())
     return loss
 
@@ -261,7 +261,7 @@ def loss_ce2d(logits, target, gscale=1.0, dx=None, coff=0):
     n, c, h, w = logits.shape
     loss = torch.empty((1,), dtype=torch.float32, device=logits.device)
     ws = _loss_ws(n, h * w)
-    L.call("crfr_loss_ce2d", ptr(logits.contiguous()), ptr(target.contiguous().long()), n, c, h * w, gscale, ptr(loss),
+    L.call("crfr_loss_ce2d", ptr(logits.contiguous().float()), ptr(target.contiguous().long()), n, c, h * w, gscale, ptr(loss),
            ptr(dx), 0 if dx is None else dx.shape[3], coff, ptr(ws), ws.numel(), stream())
     return loss
 

@@ -59,6 +59,20 @@ def bucket_slices(offs, total, ranges=BUCKET_PARAM_RANGES):
     return out
 
 
+def live_ranges(offs, total, dead):
+    """Contiguous [start, end) element ranges of the flat arena that hold live (gradient-receiving) parameters."""
+    out, start = [], None
+    n = len(offs)
+    for i in range(n + 1):
+        live = i < n and i not in dead
+        if live and start is None:
+            start = offs[i]
+        if not live and start is not None:
+            out.append((start, offs[i] if i < n else total))
+            start = None
+    return out
+
+
 def chunk_loss_div(global_batch, chunk):
     """loss_div for one chunk so that the summed chunk gradients equal the gradient of FSR_main.py:233-234."""
     return 2.0 * global_batch * global_batch / chunk
@@ -110,6 +124,7 @@ class FSRNetTrainer:
             p.data = v                      # parameters now live in the arena (state_dict / optimisers still work)
             self.grad_views.append(self.flat_g[o:o + p.numel()].view(p.shape))
         self.buckets = bucket_slices(offs, tot)
+        self.live_ranges = live_ranges(offs, tot, M._DEAD_PARAMS)
         self.ptable = M._ParamTable([p.data for p in params])
         self.gtable = M._ParamTable(self.grad_views)
         self.losses = torch.zeros((5,), dtype=torch.float32, device=dev)
@@ -260,7 +275,11 @@ class FSRNetTrainer:
         """x [B,3,S,S] fp32 (already upsampled + normalised), hr [B,3,S,S], heatmap [B,S/4,S/4], labels int64
         [B,1,S/4,S/4]; all on this rank's device.  Returns the device tensor (total, L_sr, L_coarse, L_lm, L_ce) of
         this rank's share of the global-batch loss (parts are rank-local batch means)."""
-        M.check_input(x) if x.is_cuda else None
+        if x.is_cuda:
+            M.check_input(x)
+            # the native program reads raw pointers: coerce dtype / contiguity here (slices of a bigger batch are fine)
+            x, hr, heatmap = x.contiguous().float(), hr.contiguous().float(), heatmap.contiguous().float()
+            labels = labels.contiguous().long()
         if self.use_graph and x.is_cuda:
             return self._step_graph(x, hr, heatmap, labels, lr)
         if self.lanes and x.is_cuda and x.shape[0] > self.chunk:
@@ -298,4 +317,111 @@ class FSRNetTrainer:
         return self.loss_acc
 
     def _optimizer_step(self, lr):
-        ops.rmsprop_step(self.flat_p, self.flat_g, self.flat_sq, lr, self.alpha, self.eps, self.wd, gscale=1.0)
+        # torch.optim.RMSprop skips parameters whose grad is None: the parameters that never influence the outputs (bn_end,
+        # residual_next.*, the encoder's conv_mid, the decoder's instance_norm) must not decay towards zero either, so the
+        # fused update runs over the live ranges of the arena only
+        for lo, hi in self.live_ranges:
+            ops.rmsprop_step(self.flat_p[lo:hi], self.flat_g[lo:hi], self.flat_sq[lo:hi], lr, self.alpha, self.eps, self.wd,
+                             gscale=1.0)
+
+
+class _FlatNet:
+    """Parameters, gradients and RMSprop state of one network in flat fp32 arenas (named_parameters order)."""
+
+    def __init__(self, net):
+        from .model import resnet as R
+        params = net.ordered_parameters()
+        dev = params[0].device
+        offs, tot = flat_layout([tuple(p.shape) for p in params])
+        self.net, self.offs, self.total = net, offs, tot
+        self.flat_p = torch.zeros(tot, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(tot, dtype=torch.float32, device=dev)
+        self.flat_sq = torch.zeros(tot, dtype=torch.float32, device=dev)
+        self.grad_views = []
+        for p, o in zip(params, offs):
+            v = self.flat_p[o:o + p.numel()].view(p.shape)
+            v.copy_(p.data)
+            p.data = v
+            self.grad_views.append(self.flat_g[o:o + p.numel()].view(p.shape))
+        if dev.type == "cuda":
+            self.tabs = (R._TableOfPointers([p.data for p in params], L.RESNET34_NPARAMS),
+                         R._TableOfPointers(net.ordered_buffers(), 3 * L.RESNET34_NBN),
+                         R._TableOfPointers(self.grad_views, L.RESNET34_NPARAMS))
+
+
+class KDTrainer:
+    """Data-parallel residual knowledge-distillation loop (the replacement for distill_main.py:42-74 with the optimisers
+    of :222-225), one process per GPU.
+
+    Per step and per rank: ONE native call (crfr_kd_train_step) runs the frozen teacher (ResNet_34 or IR_50, eval), the
+    student and the assistant (ResNet_34, train: per-replica BatchNorm statistics, as the reference's single-device
+    semantics) on this rank's share of the batch, the six MSE terms and both backward passes.  Student and assistant
+    gradients live in one flat arena each = one all-reduce bucket each (136 MB fp32): the native call records an event
+    when the student's gradients are final, its NCCL all-reduce is issued on a side stream behind that event and
+    overlaps the assistant's backward; the assistant's bucket follows at the end.  Gradients are SUM-reduced and scaled
+    by 1 / world inside the fused RMSprop (every term is a mean over the rank's batch), so the update equals the
+    single-GPU update on the concatenated batch up to the per-replica BatchNorm statistics.
+    ``x_hr`` feeds the teacher, ``x_lr`` (default: the same tensor, as distill_main.py:59-61) the student and assistant.
+    """
+
+    def __init__(self, teacher, student, assistant, lr=1e-4, alpha=0.99, eps=1e-8, weight_decay=1e-5,
+                 assistant_grad_to_student=True, process_group=None, world_size=None):
+        import torch.distributed as dist
+        self.teacher, self.student, self.assistant = teacher, student, assistant
+        self.lr, self.alpha, self.eps, self.wd = lr, alpha, eps, weight_decay
+        self.to_student = assistant_grad_to_student
+        self.dist = dist if (dist.is_available() and dist.is_initialized()) else None
+        self.pg = process_group
+        self.world = world_size if world_size is not None else (self.dist.get_world_size(self.pg) if self.dist else 1)
+        self.S, self.A = _FlatNet(student), _FlatNet(assistant)
+        dev = self.S.flat_p.device
+        self.device = dev
+        self.losses = torch.zeros((2,), dtype=torch.float32, device=dev)
+        if dev.type == "cuda":
+            self.comm_stream = torch.cuda.Stream(device=dev)
+            self.events = [torch.cuda.Event(), torch.cuda.Event()]
+            for e in self.events:
+                e.record()
+        else:
+            self.comm_stream, self.events = None, []
+
+    def reset_optimizer_state(self):
+        """The reference re-creates both RMSprop optimisers every epoch (distill_main.py:222-225)."""
+        self.S.flat_sq.zero_()
+        self.A.flat_sq.zero_()
+
+    # overridable so that the CPU (gloo) tests can exercise the host logic without a GPU
+    def _native_step(self, x_hr, x_lr, events):
+        from .model import resnet as R
+        R.kd_native_call(self.teacher, self.student, self.assistant, x_hr, x_lr, self.S.tabs, self.A.tabs, self.losses,
+                         self.to_student, events)
+
+    def _optimizer_step(self, lr):
+        for f in (self.S, self.A):
+            ops.rmsprop_step(f.flat_p, f.flat_g, f.flat_sq, lr, self.alpha, self.eps, self.wd, gscale=1.0 / self.world)
+
+    def step(self, x_hr, x_lr=None, lr=None):
+        """One KD step on this rank's batch; returns the device tensor (L_s, L_a) of the rank-local batch."""
+        if x_hr.is_cuda:
+            from .model import resnet as R
+            R.check_kd_nets(self.teacher, self.student, self.assistant)
+            x_hr = R.check_kd_input(x_hr, "x_hr")
+            x_lr = None if x_lr is None else R.check_kd_input(x_lr, "x_lr")
+        self.S.flat_g.zero_()
+        self.A.flat_g.zero_()
+        dp = self.dist is not None and self.world > 1
+        self._native_step(x_hr, x_lr, self.events if (dp and self.events) else None)
+        if dp:
+            works = []
+            if self.events:
+                with torch.cuda.stream(self.comm_stream):
+                    for f, ev in zip((self.S, self.A), self.events):
+                        self.comm_stream.wait_event(ev)
+                        works.append(self.dist.all_reduce(f.flat_g, op=self.dist.ReduceOp.SUM, group=self.pg, async_op=True))
+            else:
+                works = [self.dist.all_reduce(f.flat_g, op=self.dist.ReduceOp.SUM, group=self.pg, async_op=True)
+                         for f in (self.S, self.A)]
+            for wk in works:
+                wk.wait()
+        self._optimizer_step(self.lr if lr is None else lr)
+        return self.losses

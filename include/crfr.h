@@ -208,6 +208,16 @@ int crfr_verify_sweep(const float* dist, const uint8_t* issame, const int* subse
 int crfr_pair_verify(const float* e1, const float* e2, long long pairs, int dim, float thr, float* dist,
                      uint8_t* same, void* stream);
 
+/* ---------------------------------------------------------------- fully connected layer ------------------- */
+/* ref: nn.Linear on `x.view(B, -1)` of an NCHW map (model/FSRnet.py:469,484-486 Discriminator.fc; model/resnet.py:170,
+ * 221-222).  x: NHWC bf16 [B][hw][c]; w: fp32 [out][c * hw] in the reference's NCHW-flatten order; y / dy: bf16 [B][out].
+ * in_features = c * hw must be a multiple of 64, out 64 or a multiple of 128.  dw / dbias are accumulated (+=). */
+size_t crfr_linear_workspace_bytes(int batch, int hw, int c, int out);
+int crfr_linear_fwd(const void* x, int batch, int hw, int c, const float* w, const float* bias, int out, void* y,
+                    void* ws, size_t ws_bytes, void* stream);
+int crfr_linear_bwd(const void* x, const void* dy, int batch, int hw, int c, const float* w, int out, void* dx,
+                    float* dw, float* dbias, void* ws, size_t ws_bytes, void* stream);
+
 /* ---------------------------------------------------------------- FSRNet network program ------------------ */
 #define CRFR_FSRNET_NPARAMS 202
 typedef struct crfr_fsrnet_io {
@@ -252,6 +262,26 @@ int crfr_fsrnet_forward(int engine, const float* const* host_params, const crfr_
 int crfr_fsrnet_backward(int engine, const float* const* host_params, float* const* host_grads,
                          const crfr_fsrnet_io* io, const float* d_coarse, const float* d_out,
                          const float* d_landmark, const float* d_parsing, void* ws, size_t ws_bytes, void* stream);
+/* The four sub-networks on their own: Course_SR_Network / Fine_SR_Encoder / Prior_Estimation_Network / Fine_SR_Decoder
+ * .forward of the reference (model/FSRnet.py:328-340, 359-379, 408-426, 448-459), each with its own backward.
+ * params / grads are the same 202-entry tables (only the section's entries are touched). */
+enum { CRFR_FSRNET_COARSE = 0, CRFR_FSRNET_ENCODER = 1, CRFR_FSRNET_PRIOR = 2, CRFR_FSRNET_DECODER = 3 };
+typedef struct crfr_fsrnet_section_io {
+  int section, batch;
+  int size;                 /* full-resolution H = W; the encoder / prior outputs and the decoder input live at size / 4 */
+  const float* x;           /* coarse, encoder, prior: [B,3,size,size]; decoder: [B,192,size/4,size/4]   (fp32 NCHW) */
+  float* out[3];            /* coarse: {feat [B,64,S,S], coarse [B,3,S,S]}; encoder: {feat [B,64,S/4,S/4]};
+                               prior: {feat [B,128,S/4,S/4], landmark [B,97,..], parsing [B,11,..]}; decoder: {sr [B,3,S,S]} */
+} crfr_fsrnet_section_io;
+size_t crfr_fsrnet_section_workspace_bytes(int section, int batch, int size, int training);
+int crfr_fsrnet_section_forward(int engine, const float* const* host_params, const crfr_fsrnet_section_io* io,
+                                int training, void* ws, size_t ws_bytes, void* stream);
+/* d_out: gradients w.r.t. out[0..2] (fp32 NCHW, NULL entries = no gradient); accumulates into host_grads; dx (optional):
+ * gradient w.r.t. the section input, same shape as x */
+int crfr_fsrnet_section_backward(int engine, const float* const* host_params, float* const* host_grads,
+                                 const crfr_fsrnet_section_io* io, const float* const* d_out, float* dx, void* ws,
+                                 size_t ws_bytes, void* stream);
+
 /* forward + losses (FSR_main.py:233-234) + backward in one call.  losses: device fp32[5] =
  * (total, L_sr, L_coarse, L_landmark, L_ce). */
 int crfr_fsrnet_train_step(int engine, const float* const* host_params, float* const* host_grads,
@@ -293,8 +323,16 @@ typedef struct crfr_kd_io {
   const float* x;                /* [B,3,112,112] fp32 NCHW, the same batch for all three networks (distill_main.py:60-62) */
   float momentum, eps;           /* BatchNorm: 0.1, 1e-5 */
   int assistant_grad_to_student; /* 1: keep the reference's un-detached t_k - s_k in L_a */
+  const float* x_lr;             /* optional: the LR batch for the student and the assistant ("HR teacher / LR student");
+                                    NULL: all three networks see x, as distill_main.py:59-61 feeds them */
+  int teacher_ir50;              /* 1: teacher_params / teacher_buffers are IR_50's tables (187 / 3 x 54), its four stage outputs
+                                    are the t_k (DISTILLATION/model/model_irse.py: 64@56^2, 128@28^2, 256@14^2, 512@7^2) */
+  void* events[2];               /* optional cudaEvent_t handles recorded on `stream`: [0] student gradients final (the data-
+                                    parallel loop starts their all-reduce behind it, overlapping the assistant's backward),
+                                    [1] assistant gradients final */
 } crfr_kd_io;
 size_t crfr_kd_workspace_bytes(int batch, int size);
+size_t crfr_kd_workspace_bytes_ex(int batch, int size, int teacher_ir50);
 int crfr_kd_train_step(int engine, const float* const* teacher_params, void* const* teacher_buffers,
                        const float* const* student_params, void* const* student_buffers, float* const* student_grads,
                        const float* const* assistant_params, void* const* assistant_buffers,
@@ -305,7 +343,8 @@ int crfr_kd_train_step(int engine, const float* const* teacher_params, void* con
 #define CRFR_IR50_NPARAMS 187 /* named_parameters() order of DISTILLATION/model/model_irse.py:IR_50 */
 #define CRFR_IR50_NBN 54      /* BatchNorm layers in module order (input_layer, output_layer, body) */
 /* ref: Backbone.forward model_irse.py:167-172 in eval mode (the frozen teacher of distill_main.py:43,201): returns the
- * 512-d embedding in io->emb; io->feat is ignored, io->training must be 0.  buffers: 3 * 54 pointers as above. */
+ * 512-d embedding in io->emb and, for non-NULL io->feat[k], the output of body stage k (the "extracted layers" use of
+ * DISTILLATION/model/utils.py:36-52 and the t_k of the KD loss); io->training must be 0.  buffers: 3 * 54 pointers as above. */
 size_t crfr_ir50_workspace_bytes(int batch, int size);
 int crfr_ir50_forward(int engine, const float* const* host_params, void* const* host_buffers,
                       const crfr_resnet_io* io, void* ws, size_t ws_bytes, void* stream);

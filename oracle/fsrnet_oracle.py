@@ -507,3 +507,46 @@ def fsrnet_loss_and_grads(sd, x, hr, hm, lbl, train_batch=None, precision="fp32"
     for k, g in zip(names, grads):
         gd[k] = g
     return [o.detach() for o in outs], total.detach(), [p.detach() for p in parts], gd
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Discriminator / OverallNetwork_GAN (model/FSRnet.py:461-486, 512-545)
+# ----------------------------------------------------------------------------------------------------------------
+def discriminator_param_shapes(spatial=56):
+    ks = [("conv_input.weight", (64, 192, 3, 3)), ("conv_input.bias", (64,)), ("relu.weight", (64,)),
+          ("bn_mid.weight", (64,)), ("bn_mid.bias", (64,))]
+    for b in range(3):
+        ks += _res_block_keys("residual.%d." % b, 64)
+    ks += [("fc.weight", (512, 64 * spatial * spatial)), ("fc.bias", (512,)), ("bn_end.weight", (512,)), ("bn_end.bias", (512,))]
+    return ks
+
+
+def _batch_norm_train(x, w, b, dims, eps=1e-5):
+    mu = x.mean(dim=dims, keepdim=True)
+    var = ((x - mu) ** 2).mean(dim=dims, keepdim=True)
+    shape = [1, -1] + [1] * (x.dim() - 2)
+    return (x - mu) / torch.sqrt(var + eps) * w.view(shape) + b.view(shape)
+
+
+def discriminator_forward(sd, x, p="", pr=FP32):
+    """Discriminator.forward (:479-487) in training mode (batch statistics): conv -> BN -> PReLU -> the same BN -> flatten
+    (NCHW order) -> Linear -> BatchNorm1d.  The residual stack is never called."""
+    y = _conv(pr, pr.q(x), sd[p + "conv_input.weight"], sd[p + "conv_input.bias"], 1, 1)
+    a = pr.st(_prelu(pr.qg(_batch_norm_train(y, sd[p + "bn_mid.weight"], sd[p + "bn_mid.bias"], (0, 2, 3))), sd[p + "relu.weight"]))
+    a = pr.st(pr.qg(_batch_norm_train(a, sd[p + "bn_mid.weight"], sd[p + "bn_mid.bias"], (0, 2, 3))))
+    o = a.reshape(a.shape[0], -1)
+    o = pr.sb(F.linear(pr.qg(o), pr.q(sd[p + "fc.weight"]), sd[p + "fc.bias"]))
+    return pr.st(pr.qg(_batch_norm_train(o, sd[p + "bn_end.weight"], sd[p + "bn_end.bias"], (0,))))
+
+
+def gan_forward(sd, lr, hr, pr=FP32):
+    """OverallNetwork_GAN.forward (:538-545) on a state dict with the _discriminator.* keys next to the sub-networks."""
+    def once(x):
+        enc = encoder_forward(sd, x, pr=pr)
+        pe, landmark, parsing = prior_forward(sd, x, pr=pr)
+        out = torch.cat((pe, enc), 1)
+        return out, landmark, parsing, discriminator_forward(sd, out, "_discriminator.", pr)
+    _, coarse = coarse_forward(sd, lr, pr=pr)
+    out1, lm1, ps1, e1 = once(coarse)
+    _, _, _, e2 = once(hr)
+    return decoder_forward(sd, out1, pr=pr), coarse, lm1, ps1, e1, e2

@@ -290,9 +290,35 @@ def golden_ir50():
     print("ir50 eval forward ok, rel", rel, "emb norm", emb.norm().item())
 
 
+def golden_gan():
+    """OverallNetwork_GAN + Discriminator (model/FSRnet.py:461-486, 512-545) at the only size the reference's Discriminator
+    accepts (224 x 224 -> 56 x 56 maps, fc 64*56*56): the oracle restatement is pinned against the reference modules, and
+    the fixture keeps the two discriminator embeddings plus how far the oracle's own bf16-storage evaluation moves them."""
+    F = R.load("model/FSRnet.py")
+    torch.manual_seed(4242)
+    net = F.OverallNetwork_GAN()
+    net.apply(R.reference_weights_init)
+    net.train()
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items() if "running_" not in k and "num_batches" not in k}
+    g = torch.Generator().manual_seed(99)
+    lr, hr = torch.randn(4, 3, 224, 224, generator=g), torch.randn(4, 3, 224, 224, generator=g)
+    with torch.no_grad():
+        ref = net(lr, hr)
+        ours = FO.gan_forward(sd, lr, hr)
+        emu = FO.gan_forward(sd, lr, hr, FO.Precision("bf16"))
+    for a, b, name in zip(ref, ours, ("sr", "coarse", "landmark", "parsing", "embedding1", "embedding2")):
+        assert torch.allclose(a, b, rtol=1e-3, atol=2e-4), (name, (a - b).abs().max())
+    rel = lambda a, b: ((a - b).double().norm() / b.double().norm()).item()
+    np.savez_compressed(os.path.join(OUT, "gan224.npz"), embedding1=ref[4].numpy(), embedding2=ref[5].numpy(),
+                        sr_mean=ref[0].mean().item(), sr_std=ref[0].std().item(),
+                        emu_rel=np.array([rel(e, r) for e, r in zip(emu, ref)]),
+                        keys=np.array(list(sd.keys())))
+    print("gan224: oracle == reference; bf16-storage deviation per output", [round(rel(e, r), 4) for e, r in zip(emu, ref)])
+
+
 if __name__ == "__main__":
     assert R.available(), "reference tree not present"
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["losses", "bicubic", "eval", "fsrnet", "resnet", "ir50", "heatmap", "augment"]
+    which = sys.argv[1:] or ["losses", "bicubic", "eval", "fsrnet", "resnet", "ir50", "heatmap", "augment", "gan"]
     for w in which:
         globals()["golden_" + w]()

@@ -254,8 +254,10 @@ def randomize_bn_everywhere(sd, seed):
     return out
 
 
-def ir50_forward(sd, x, pr=FP32):
-    """Backbone.forward (model_irse.py:167-172) in eval mode -> embedding [B, 512]."""
+def ir50_forward(sd, x, pr=FP32, want_features=False):
+    """Backbone.forward (model_irse.py:167-172) in eval mode -> embedding [B, 512]; with ``want_features`` also the
+    outputs of the four body stages (units [3, 4, 14, 3], model_irse.py:103-110), i.e. what a FeatureExtractor
+    (DISTILLATION/model/utils.py:36-52) walking ``body`` collects after blocks 2, 6, 20 and 23."""
     def prelu(y, a):
         a = a.view(1, -1, 1, 1)
         return pr.q(torch.clamp(y, min=0) + a * torch.clamp(y, max=0))
@@ -266,6 +268,7 @@ def ir50_forward(sd, x, pr=FP32):
         a = a.view(1, -1, 1, 1)
         return pr.q(torch.clamp(z, min=0) + a * torch.clamp(z, max=0))
 
+    feats = []
     a = _conv(pr, pr.q(x), sd["input_layer.0.weight"], 1, 1)
     a = bn_prelu(a, "input_layer.1.", sd["input_layer.2.weight"])
     for i, (cin, d, stride) in enumerate(ir50_block_specs()):
@@ -279,7 +282,10 @@ def ir50_forward(sd, x, pr=FP32):
         r = prelu(_conv(pr, r, sd[p + "res_layer.1.weight"], 1, 1), sd[p + "res_layer.2.weight"])
         r = _conv(pr, r, sd[p + "res_layer.3.weight"], stride, 1)
         a = _bn(pr, sd, p + "res_layer.4.", r, False, False, res=sc)
+        if i in (2, 6, 20, 23):
+            feats.append(a)
     o = _bn(pr, sd, "output_layer.0.", a, False, False)
     o = o.reshape(o.shape[0], -1)
     y = pr.qb(F.linear(pr.qg(o), pr.q(sd["output_layer.3.weight"]), sd["output_layer.3.bias"]))
-    return _bn(pr, sd, "output_layer.4.", y, False, False)
+    emb = _bn(pr, sd, "output_layer.4.", y, False, False)
+    return (emb, feats) if want_features else emb

@@ -109,3 +109,119 @@ def test_trainer_moves_parameters_into_arena_and_keeps_state_dict():
     assert p0.data.data_ptr() == tr.flat_p.data_ptr()
     tr.flat_p[:4] += 1.0
     assert torch.equal(p0.data.reshape(-1)[:4], tr.flat_p[:4])
+
+
+# ---- KD trainer (distill_main.py:59-74, 222-225): two flat arenas, one all-reduce bucket each, 1/world scaling ------
+def _make_kd_trainer(world):
+    from crfr_b200.model.resnet import ResNet_34
+    from crfr_b200.trainer import KDTrainer
+
+    class FakeKD(KDTrainer):
+        """Stand-in for crfr_kd_train_step: every term of the KD losses is a MEAN over the rank's batch, so the stand-in
+        gradient is (batch mean of mean(x_lr_i)) * (k+1) for the student and (mean of x_hr) * (k+2) for the assistant."""
+
+        def _native_step(self, x_hr, x_lr, events):
+            x_lr = x_hr if x_lr is None else x_lr
+            s, a = float(x_lr.double().mean()), float(x_hr.double().mean())
+            for k, g in enumerate(self.S.grad_views):
+                g.add_(s * (k + 1))
+            for k, g in enumerate(self.A.grad_views):
+                g.add_(a * (k + 2))
+            self.losses.copy_(torch.tensor([s, a]))
+
+        def _optimizer_step(self, lr):
+            for f in (self.S, self.A):
+                g = f.flat_g / self.world + self.wd * f.flat_p
+                f.flat_sq.mul_(self.alpha).addcmul_(g, g, value=1 - self.alpha)
+                f.flat_p.addcdiv_(g, f.flat_sq.sqrt().add_(self.eps), value=-lr)
+
+    nets = []
+    for seed in (1, 2, 3):
+        torch.manual_seed(seed)
+        nets.append(ResNet_34())
+    nets[0].eval()
+    return FakeKD(nets[0], nets[1], nets[2], lr=1e-3, world_size=world), nets
+
+
+def _kd_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        tr, _ = _make_kd_trainer(world)
+        g = torch.Generator().manual_seed(5)
+        x_hr, x_lr = torch.randn(4 * world, 3, 8, 8, generator=g), torch.randn(4 * world, 3, 8, 8, generator=g)
+        sl = slice(rank * 4, rank * 4 + 4)
+        losses = tr.step(x_hr[sl], x_lr[sl])
+        ret[rank] = (tr.S.flat_g.clone(), tr.A.flat_g.clone(), tr.S.flat_p.clone(), tr.A.flat_p.clone(), losses.clone())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_kd_dp2_update_equals_single_process_concatenated_batch():
+    world = 2
+    ret = mp.Manager().dict()
+    mp.spawn(_kd_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    tr, _ = _make_kd_trainer(1)
+    g = torch.Generator().manual_seed(5)
+    x_hr, x_lr = torch.randn(4 * world, 3, 8, 8, generator=g), torch.randn(4 * world, 3, 8, 8, generator=g)
+    tr.step(x_hr, x_lr)
+    for r in range(world):
+        sg, ag, sp, ap, _ = ret[r]
+        # SUM over ranks of rank-batch means = world x the global-batch mean; RMSprop divides by world
+        assert torch.allclose(sg / world, tr.S.flat_g, rtol=1e-5, atol=1e-9)
+        assert torch.allclose(ag / world, tr.A.flat_g, rtol=1e-5, atol=1e-9)
+        assert torch.allclose(sp, tr.S.flat_p, rtol=1e-4, atol=1e-6)
+        assert torch.allclose(ap, tr.A.flat_p, rtol=1e-4, atol=1e-6)
+    assert torch.equal(ret[0][2], ret[1][2])          # replicas stay in lock step
+
+
+# ---- sharded-gallery identification (utils/eval.py:11 semantics over a row-sharded gallery) ---------------------------
+def _torch_topk(p, g, k, index_base=0):
+    s = p.float() @ g.float().t()
+    v, i = torch.sort(s, dim=1, descending=True, stable=True)       # stable: ties -> lowest index
+    return v[:, :k].contiguous(), (i[:, :k] + index_base).to(torch.int32).contiguous()
+
+
+def _torch_merge(vals, idx, k):
+    parts, p, kk = vals.shape
+    v = vals.permute(1, 0, 2).reshape(p, parts * kk)
+    i = idx.permute(1, 0, 2).reshape(p, parts * kk)
+    order = torch.sort(i, dim=1, stable=True)[1]                    # by index first, then a stable sort by score:
+    v, i = torch.gather(v, 1, order), torch.gather(i, 1, order)     # equal scores keep the lowest index in front
+    o2 = torch.sort(v, dim=1, descending=True, stable=True)[1]
+    return torch.gather(v, 1, o2)[:, :k], torch.gather(i, 1, o2)[:, :k]
+
+
+def _match_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from crfr_b200 import ops
+        from crfr_b200.utils import utils as U
+        ops.cosine_topk = lambda p, g, k, index_base=0, engine=0: _torch_topk(p, g, k, index_base)   # CPU stand-ins for
+        ops.topk_merge = _torch_merge                                                                  # the two kernels
+        gen = torch.Generator().manual_seed(11)
+        gal = torch.nn.functional.normalize(torch.randn(103, 16, generator=gen), dim=1)
+        gal[50] = gal[7]                                            # an exact tie across two shards
+        pr = torch.nn.functional.normalize(gal[torch.arange(0, 100, 9)] + 0.1 * torch.randn(12, 16, generator=gen), dim=1)
+        lo, hi = U.shard_rows(gal.shape[0], world, rank)
+        v, i = U.cosine_identify(pr, gal[lo:hi], k=5, normalized=True, index_base=lo, sharded=True)
+        ret[rank] = (v.clone(), i.clone(), (lo, hi))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_sharded_identification_equals_unsharded():
+    world = 3
+    ret = mp.Manager().dict()
+    mp.spawn(_match_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    gen = torch.Generator().manual_seed(11)
+    gal = torch.nn.functional.normalize(torch.randn(103, 16, generator=gen), dim=1)
+    gal[50] = gal[7]
+    pr = torch.nn.functional.normalize(gal[torch.arange(0, 100, 9)] + 0.1 * torch.randn(12, 16, generator=gen), dim=1)
+    v, i = _torch_topk(pr, gal, 5)
+    assert [ret[r][2] for r in range(world)] == [(0, 35), (35, 69), (69, 103)]
+    for r in range(world):
+        assert torch.equal(ret[r][1], i) and torch.allclose(ret[r][0], v)

@@ -179,3 +179,105 @@ def test_rejects_unsupported(cuda):
         net(torch.zeros(2, 3, 112, 112))
     with pytest.raises(ValueError):
         net(torch.zeros(2, 3, 96, 96, device="cuda"))
+
+
+def test_ir50_stage_features(cuda):
+    """IR_50 as a feature extractor (DISTILLATION/model/utils.py:36-52): the four body-stage outputs next to the embedding;
+    they have the shapes of ResNet_34's x1..x4, which is what distill_main.py:59 unpacks from its teacher."""
+    from crfr_b200.model.model_irse import IR_50
+    from oracle import resnet_oracle as RO
+    torch.manual_seed(91)
+    net = IR_50([112, 112])
+    sd = RO.randomize_bn_everywhere(RO.build_ir50_state_dict(91), 191)
+    net.load_state_dict(sd)
+    net = net.cuda().eval()
+    x = RO.synthetic_faces(2, seed=4322)
+    with torch.no_grad():
+        outs = net.forward_features(x.cuda())
+        emb = net(x.cuda())
+        ref_emb, ref = RO.ir50_forward(sd, x, want_features=True)
+        _, emu = RO.ir50_forward(sd, x, pr=RO.Precision("bf16"), want_features=True)
+    assert torch.equal(outs[0], emb)
+    for f, r, e, shape in zip(outs[1:], ref, emu, ((64, 56), (128, 28), (256, 14), (512, 7))):
+        assert tuple(f.shape) == (2, shape[0], shape[1], shape[1])
+        assert rel_err(f, r) < SLACK * rel_err(e, r) + 1e-2, (shape, rel_err(f, r), rel_err(e, r))
+
+
+@pytest.mark.parametrize("teacher_kind", ["resnet34", "ir50"])
+def test_kd_step_hr_teacher_lr_student(cuda, teacher_kind):
+    """'HR teacher / LR student' (BASELINE configs[2]): the teacher sees x_hr, the student and the assistant x_lr, with a
+    ResNet_34 or an IR_50 teacher (whose stage outputs are the t_k): the native step == the same step composed from the
+    drop-in modules, the loss modules and autograd."""
+    from crfr_b200.loss import MSELoss, ResidualKDLoss
+    from crfr_b200.model.model_irse import IR_50
+    from crfr_b200.model.resnet import kd_train_step
+    from oracle import resnet_oracle as RO
+    (teacher, student, assistant), sds = _nets()
+    if teacher_kind == "ir50":
+        torch.manual_seed(91)
+        teacher = IR_50([112, 112])
+        teacher.load_state_dict(RO.randomize_bn_everywhere(RO.build_ir50_state_dict(91), 191))
+        teacher = teacher.cuda()
+    teacher.eval(); student.train(); assistant.train()
+    x_hr = RO.synthetic_faces(B).cuda()
+    x_lr = RO.synthetic_faces(B, seed=999).cuda()
+    with torch.no_grad():
+        t_outs = teacher.forward_features(x_hr) if teacher_kind == "ir50" else teacher(x_hr)
+    s_outs, a_outs = student(x_lr), assistant(x_lr)
+    mse, kd = MSELoss(), ResidualKDLoss()
+    l_s = mse(s_outs[0], t_outs[0])
+    l_a = sum(kd(t_outs[k], s_outs[k], a_outs[k]) for k in (1, 2, 3, 4)) + kd(t_outs[0], s_outs[0], a_outs[0])
+    (l_s + l_a).backward()
+    ref_s = [p.grad.clone() for p in student.parameters()]
+    ref_a = [p.grad.clone() for p in assistant.parameters()]
+    for net, sd in zip((student, assistant), sds[1:]):
+        net.load_state_dict(sd)
+        net.zero_grad(set_to_none=True)
+    losses = kd_train_step(teacher, student, assistant, x_hr, x_lr=x_lr)
+    torch.cuda.synchronize()
+    assert abs(losses[0].item() - l_s.item()) < 1e-4 * abs(l_s.item())
+    assert abs(losses[1].item() - l_a.item()) < 1e-4 * abs(l_a.item())
+    # and the LR input really is what the student saw: the same call on x_hr alone gives different losses
+    for net, sd in zip((student, assistant), sds[1:]):
+        net.load_state_dict(sd)
+    same = kd_train_step(teacher, student, assistant, x_hr)
+    assert abs(same[0].item() - losses[0].item()) > 1e-3 * abs(losses[0].item())
+    names = [k for k, _ in student.named_parameters()]
+    for net, sd in zip((student, assistant), sds[1:]):
+        net.load_state_dict(sd)
+    kd_train_step(teacher, student, assistant, x_hr, x_lr=x_lr)
+    for tag, net, ref in (("s", student, ref_s), ("a", assistant, ref_a)):
+        fo, fr = [], []
+        for k, p, r in zip(names, net.parameters(), ref):
+            if k in RO.RESNET_NULL_GRAD:
+                continue
+            assert rel_err(p.grad, r) < 6e-2, (tag, k, rel_err(p.grad, r))
+            fo.append(p.grad.flatten().double()); fr.append(r.flatten().double())
+        a, b = torch.cat(fo), torch.cat(fr)
+        assert float(a @ b / (a.norm() * b.norm())) > 0.999, tag
+
+
+def test_kd_trainer_step_equals_native_step_plus_rmsprop(cuda):
+    """KDTrainer (flat arenas, fused RMSprop, the data-parallel plumbing with world = 1) == kd_train_step followed by
+    torch.optim.RMSprop with the reference's hyper-parameters (distill_main.py:222-225)."""
+    from crfr_b200.model.resnet import kd_train_step
+    from crfr_b200.trainer import KDTrainer
+    from oracle import resnet_oracle as RO
+    x_hr, x_lr = RO.synthetic_faces(B).cuda(), RO.synthetic_faces(B, seed=5).cuda()
+    (teacher, student, assistant), sds = _nets()
+    teacher.eval(); student.train(); assistant.train()
+    opts = [torch.optim.RMSprop(n.parameters(), lr=1e-4, alpha=0.99, weight_decay=1e-5) for n in (student, assistant)]
+    ref_losses = kd_train_step(teacher, student, assistant, x_hr, x_lr=x_lr).clone()
+    for o in opts:
+        o.step()
+    ref = [[p.detach().clone() for p in n.parameters()] for n in (student, assistant)]
+    (teacher2, student2, assistant2), _ = _nets()
+    teacher2.eval(); student2.train(); assistant2.train()
+    tr = KDTrainer(teacher2, student2, assistant2, lr=1e-4)
+    losses = tr.step(x_hr, x_lr)
+    torch.cuda.synchronize()
+    assert torch.allclose(losses, ref_losses, rtol=1e-5)
+    for net, r in zip((student2, assistant2), ref):
+        for (k, p), q in zip(net.named_parameters(), r):
+            assert torch.allclose(p, q, rtol=1e-4, atol=1e-6), k
+    assert int(student2.state_dict()["bn1.num_batches_tracked"]) == 1
