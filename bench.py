@@ -77,76 +77,124 @@ class ClockSampler(threading.Thread):
 
 
 def cpu_reference_step_rate(steps, warmup, batch=4, size=128):
-    """The reference algorithm (oracle port, fp32) on the host cores: forward + backward + RMSprop, config 1."""
+    """The reference's FSRNet train step on the host cores (fp32, config 1 of BASELINE.json): forward + losses + backward
+    + RMSprop.  With oracle/_ref (the reference's own modules, byte-compiled by oracle/build_ref.py in the build container)
+    this runs THE REFERENCE - model/FSRnet.py, loss/loss.py, torch.optim.RMSprop as FSR_main.py:185,231-251 - and reports
+    kind "reference"; without it, the oracle port (kind "port").  Returns (images/s, cores, s/step, kind, what)."""
     import torch
+    from oracle import build_ref as BR
     from oracle import fsrnet_oracle as FO
+    from oracle import ref_loader as RL
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sd = FO.build_fsrnet_state_dict(1234)
-    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
-    live = [v for k, v in leaves.items() if not FO.fsrnet_dead_param(k)]
-    opt = torch.optim.RMSprop(live, lr=1e-3, alpha=0.99, weight_decay=1e-5)
     x, hr, lbl, hm = FO.synthetic_batch(batch, size)
+    if BR.available():
+        F, Ls = BR.load("FSRnet"), BR.load("loss")
+        torch.manual_seed(1234)
+        net = F.OverallNetwork()
+        net.apply(RL.reference_weights_init)
+        net.train()
+        mse, lmk, ce = Ls.MSELossFunc(), Ls.MSELoss_Landmark(), Ls.CrossEntropyLoss2d()
+        opt = torch.optim.RMSprop(net.parameters(), lr=1e-3, alpha=0.99, weight_decay=1e-5)
+        kind, what = "reference", "the reference's own modules (oracle/_ref: model/FSRnet.py, loss/loss.py) + torch RMSprop"
+
+        def step():
+            outs = RL.reference_fsrnet_forward(net, x)
+            total = (5. * mse(outs[1], hr) + 5. * mse(outs[0], hr) + lmk(outs[2], hm) + ce(outs[3], lbl)) / (2.0 * batch)
+            opt.zero_grad()
+            total.backward()
+            opt.step()
+    else:
+        sd = FO.build_fsrnet_state_dict(1234)
+        leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        live = [v for k, v in leaves.items() if not FO.fsrnet_dead_param(k)]
+        opt = torch.optim.RMSprop(live, lr=1e-3, alpha=0.99, weight_decay=1e-5)
+        kind, what = "port", "oracle port of model/FSRnet.py + loss/loss.py + torch RMSprop"
+
+        def step():
+            outs = FO.fsrnet_forward(leaves, x)
+            total, _ = FO.fsrnet_loss(outs, hr, hm, lbl)
+            opt.zero_grad()
+            total.backward()
+            opt.step()
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        outs = FO.fsrnet_forward(leaves, x)
-        total, _ = FO.fsrnet_loss(outs, hr, hm, lbl)
-        opt.zero_grad()
-        total.backward()
-        opt.step()
+        step()
         if i >= warmup:
             times.append(time.perf_counter() - t0)
-    return batch * len(times) / sum(times), cores, sum(times) / len(times)
+    return batch * len(times) / sum(times), cores, sum(times) / len(times), kind, what
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    value, cores, sec = cpu_reference_step_rate(max(1, args.steps), max(1, min(args.warmup, 2)))
+    # bounded sample: every step is batch 4 (about 1-3 s of CPU work); at most 12 timed steps whatever --steps says
+    value, cores, sec, kind, what = cpu_reference_step_rate(max(1, min(args.steps, 12)), max(1, min(args.warmup, 2)))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "FSRNet train step 16->128 (128x128 input), reference algorithm on host CPU",
                        "sample": "batch 4 per step (config 1 of BASELINE.json)"},
-            "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port",
-                             "sample": "oracle port of model/FSRnet.py + loss/loss.py, batch 4 x 128x128, fp32"},
+            "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": kind,
+                             "sample": "%s, batch 4 x 128x128 per step, fp32" % what},
             "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one rowconv_kernel launch over 128 images from the committed
-# `ncu --set full` capture (profiles/r1_rowconv_ncu_full.txt): 273.3 MB + 221.5 MB (algorithmic: 268.4 MB in + 268.4 MB
-# out; part of the output is still dirty in the 126 MB L2 when the kernel ends)
-ROWCONV_TRAFFIC_BYTES_PER_IMAGE = (273.27e6 + 221.48e6) / 128
+# dram__bytes_read.sum + dram__bytes_write.sum of one rowconv_pair_kernel launch over 128 images from the committed
+# `ncu --set full` capture of this round (profiles/r2_rowconv_pair_ncu.txt): 273.3 MB + 217.0 MB (algorithmic: 268.4 MB in
+# + 268.4 MB out; part of the output is still dirty in the 126 MB L2 when the kernel ends).  A counter cannot be read
+# inside an un-profiled run, so the figure is labelled with its source (`traffic_source`).
+ROWCONV_TRAFFIC_BYTES_PER_IMAGE = (273.32e6 + 217.04e6) / 128
+ROWCONV_TRAFFIC_SOURCE = "ncu --set full capture profiles/r2_rowconv_pair_ncu.txt (round 2, rowconv_pair_kernel, 128 images)"
 
 
-def time_matcher(torch, ops, probes=10000, gallery=1000000, dim=512, k=5, reps=3):
-    """Cosine-similarity identification (BASELINE.json configs[3]): 10 k probes x 1 M-entry 512-d gallery, top-5."""
-    g = torch.Generator(device="cuda").manual_seed(11)
+def time_matcher(torch, ops, dist, world, rank, probes=10000, gallery=1000000, dim=512, k=5, reps=3):
+    """Cosine-similarity identification (BASELINE.json configs[3]): 10 k probes x 1 M-entry 512-d gallery, top-5.
+    N > 1: the gallery rows are sharded across the ranks, every rank runs the fused GEMM + top-k on its shard, the per-rank
+    (score, index) lists are all-gathered over NCCL and merged (crfr_b200.utils.cosine_identify(sharded=True))."""
+    from crfr_b200.utils import utils as U
+    g = torch.Generator(device="cuda").manual_seed(11)             # same seed on every rank: identical gallery / probes
     gal = ops.l2norm_bf16(torch.randn(gallery, dim, generator=g, device="cuda"))
     ids = torch.randint(0, gallery, (probes,), generator=g, device="cuda")
     pr = ops.l2norm_bf16(gal[ids].float() + 0.3 * torch.randn(probes, dim, generator=g, device="cuda") / dim ** 0.5)
-    val, idx = ops.cosine_topk(pr, gal, k)
+    lo, hi = U.shard_rows(gallery, world, rank)
+    shard = gal[lo:hi].contiguous()
+    del gal
+
+    def run():
+        return U.cosine_identify(pr, shard, k, normalized=True, index_base=lo, sharded=world > 1)
+    val, idx = run()
+    if world > 1:
+        dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
-        val, idx = ops.cosine_topk(pr, gal, k)
+        val, idx = run()
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
+    t = torch.tensor([e0.elapsed_time(e1) / reps], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
     hit = float((idx[:, 0].long() == ids).float().mean().item())
     return {"queries_per_sec": probes / (ms * 1e-3), "ms": ms, "tflops": 2.0 * probes * gallery * dim / (ms * 1e-3) / 1e12,
-            "rank1_hit_rate": hit, "workload": "%d probes x %d x %d gallery, top-%d, bf16" % (probes, gallery, dim, k)}
+            "rank1_hit_rate": hit, "gallery_shards": world,
+            "workload": "%d probes x %d x %d gallery, top-%d, bf16%s" % (
+                probes, gallery, dim, k, "" if world == 1 else ", gallery sharded over %d GPUs + all-gather + merge" % world)}
 
 
-def time_kd_step(torch, batch=256, reps=3):
-    """Residual-KD step (BASELINE.json configs[2]): teacher forward (eval) + student and assistant forward/backward."""
-    from crfr_b200.loss import MSELoss, ResidualKDLoss
+def time_kd_step(torch, dist, world, batch=256, reps=3, teacher_kind="resnet34"):
+    """Residual-KD training step (BASELINE.json configs[2] / [4]): HR batch -> frozen teacher (eval), LR batch -> student
+    and assistant (train), six MSE terms, both backward passes, gradient all-reduce of both networks (N > 1) and the fused
+    RMSprop - crfr_b200.trainer.KDTrainer, per-GPU batch 256.  Device-timed, max over ranks."""
+    from crfr_b200.model.model_irse import IR_50
     from crfr_b200.model.resnet import ResNet_34
+    from crfr_b200.trainer import KDTrainer
     torch.manual_seed(7)
     nets = [ResNet_34().cuda() for _ in range(3)]
     for n in nets:                       # zero-initialised bn2 weights would make every residual branch vanish
@@ -154,29 +202,33 @@ def time_kd_step(torch, batch=256, reps=3):
             if k.endswith("bn2.weight"):
                 p.data.fill_(0.5)
     teacher, student, assistant = nets
+    if teacher_kind == "ir50":
+        teacher = IR_50([112, 112]).cuda()
     teacher.eval(); student.train(); assistant.train()
-    x = torch.randn(batch, 3, 112, 112, device="cuda")
-    mse, kd = MSELoss(), ResidualKDLoss()
-
-    from crfr_b200.model.resnet import kd_train_step
-
-    def step():   # one native call: crfr_kd_train_step (the module + autograd composition gives the same gradients)
-        losses = kd_train_step(teacher, student, assistant, x)
-        return losses[0], losses[1]
+    tr = KDTrainer(teacher, student, assistant, lr=1e-4)
+    x_hr = torch.randn(batch, 3, 112, 112, device="cuda")
+    x_lr = torch.randn(batch, 3, 112, 112, device="cuda")
     for _ in range(2):                   # warm-up: kernel attributes, allocator pools for the 9 GB workspaces
-        step()
+        tr.step(x_hr, x_lr)
+    if world > 1:
+        dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
-        l_s, l_a = step()
+        losses = tr.step(x_hr, x_lr)
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
-    flop = 55.65e9 + 14.35e9             # incl. dL_a/dtheta_S, which this graph propagates
-    return {"images_per_sec": batch / (ms * 1e-3), "ms_per_step": ms, "tflops": batch * flop / (ms * 1e-3) / 1e12,
-            "student_loss": float(l_s.item()), "assistant_loss": float(l_a.item()),
-            "workload": "ResNet_34 teacher(eval) + student + assistant KD step, batch %d, 112x112" % batch}
+    t = torch.tensor([e0.elapsed_time(e1) / reps], device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    # student + assistant 2 x 21.53 GFLOP, + 14.35 for dL_a/dtheta_S (propagated), + the teacher's forward
+    flop = 2 * 21.53e9 + 14.35e9 + (12.59e9 if teacher_kind == "ir50" else 7.175e9)
+    return {"images_per_sec": world * batch / (ms * 1e-3), "ms_per_step": ms, "tflops_per_gpu": batch * flop / (ms * 1e-3) / 1e12,
+            "student_loss": float(losses[0].item()), "assistant_loss": float(losses[1].item()),
+            "workload": "KDTrainer step: %s teacher (eval, HR batch) + ResNet_34 student + assistant (LR batch), batch %d per "
+                        "GPU, 112x112, all-reduce + RMSprop included" % (teacher_kind, batch)}
 
 
 def time_ir50(torch, batch=256, reps=3):
@@ -256,6 +308,39 @@ def time_norm_bwd(torch, ops, chunk):
     ms = e0.elapsed_time(e1) / reps
     nbytes = 8.0 * chunk * h * h * c * 2
     return nbytes / (ms * 1e-3) / 1e9, ms, nbytes
+
+
+def verify_dp(torch, dist, world, rank, dev, per_rank=4, size=128):
+    """Data-parallel correctness on hardware: the SUM-all-reduced gradient of `world` ranks with `per_rank` images each
+    against the single-GPU gradient of the concatenated batch (computed on every rank, so no extra exchange).  FSRNet uses
+    InstanceNorm only, so the two are equal up to the bf16 storage noise of two differently partitioned evaluations."""
+    from crfr_b200.model.FSRnet import OverallNetwork, weights_init
+    from crfr_b200.trainer import FSRNetTrainer
+
+    class GradOnly(FSRNetTrainer):
+        def _optimizer_step(self, lr):
+            pass
+    g = torch.Generator().manual_seed(2024)
+    n = per_rank * world
+    x = torch.randn(n, 3, size, size, generator=g).to(dev)
+    hr = torch.randn(n, 3, size, size, generator=g).to(dev)
+    hm = torch.rand(n, size // 4, size // 4, generator=g).to(dev)
+    lbl = torch.randint(0, 11, (n, 1, size // 4, size // 4), generator=g).to(dev)
+    out = []
+    for dp in (True, False):
+        torch.manual_seed(1234)
+        net = OverallNetwork()
+        net.apply(weights_init)
+        tr = GradOnly(net.to(dev).train(), chunk=n, world_size=world if dp else 1)
+        if not dp:
+            tr.dist = None
+        sl = slice(rank * per_rank, (rank + 1) * per_rank) if dp else slice(0, n)
+        tr.step(x[sl], hr[sl], hm[sl], lbl[sl])
+        torch.cuda.synchronize()
+        out.append(tr.flat_g.double().clone())
+    rel = ((out[0] - out[1]).norm() / out[1].norm()).item()
+    cos = float(out[0] @ out[1] / (out[0].norm() * out[1].norm()))
+    return {"rel_err_allreduced_vs_single_gpu": rel, "cosine": cos, "images": n, "ranks": world, "pass": bool(rel < 5e-2)}
 
 
 def run_ours(args):
@@ -343,6 +428,19 @@ def run_ours(args):
     value = world * B * args.steps / (ms * 1e-3)
     e2e = world * B * max(2, args.steps // 2) / (ms_e2e * 1e-3)
 
+    extras = {}
+    if not args.no_extras:
+        # the other BASELINE.json paths, measured in the same run on all ranks (secondary numbers, not the headline metric)
+        trainer.ws = None
+        trainer._graph, trainer._static = None, None
+        torch.cuda.empty_cache()
+        extras["matcher"] = time_matcher(torch, ops, dist, world, rank)
+        extras["kd_step"] = time_kd_step(torch, dist, world)
+        if world == 1:
+            extras["kd_step_ir50_teacher"] = time_kd_step(torch, dist, world, teacher_kind="ir50")
+            extras["ir50_teacher"] = time_ir50(torch)
+    if args.verify and world > 1:
+        extras["dp_verify"] = verify_dp(torch, dist, world, rank, dev)
     if rank == 0:
         burst, sustained, hbm, how = measured_peaks()
         k_tflops, k_ms, k_flops = time_dominant_kernel(torch, ops, L, args.chunk)
@@ -359,10 +457,11 @@ def run_ours(args):
                 "step_tensor_frac": {"achieved_tflops": value / world * FLOP_PER_IMG_TRAIN / 1e12,
                                      "peak_tflops_sustained": sustained,
                                      "frac": value / world * FLOP_PER_IMG_TRAIN / 1e12 / sustained, "peak": how},
-                "roofline": {"bound": "tensor", "kernel": "rowconv_kernel (3x3 64->64 @128x128 forward, %d images per "
-                                                          "launch)" % args.chunk,
+                "roofline": {"bound": "tensor", "kernel": "rowconv_pair_kernel (cta_group::2, 3x3 64->64 @128x128 forward, %d "
+                                                          "images per launch)" % args.chunk,
                              "achieved": k_tflops, "peak": burst, "unit": "TFLOP/s", "frac": k_tflops / burst,
-                             "traffic": ROWCONV_TRAFFIC_BYTES_PER_IMAGE * args.chunk, "ms_per_launch": k_ms,
+                             "traffic": ROWCONV_TRAFFIC_BYTES_PER_IMAGE * args.chunk,
+                             "traffic_source": ROWCONV_TRAFFIC_SOURCE, "ms_per_launch": k_ms,
                              "flops_per_launch": k_flops, "peak_source": how}}
         n_gbs, n_ms, n_bytes = time_norm_bwd(torch, ops, args.chunk)
         line["roofline_hbm"] = {"bound": "hbm", "kernel": "norm_bwd_reduce_stream_kernel + bwd_fold_kernel + "
@@ -370,18 +469,13 @@ def run_ours(args):
                                                           "backward, 64 x 128 x 128, %d images)" % args.chunk,
                                 "achieved": n_gbs, "peak": hbm, "unit": "GB/s", "frac": n_gbs / hbm,
                                 "traffic": NORM_BWD_TRAFFIC_BYTES_PER_IMAGE * args.chunk,
+                                "traffic_source": "ncu --set full capture profiles/r1_norm_stream_ncu_full.txt (kernels unchanged)",
                                 "ms_per_op": n_ms, "bytes_per_op": n_bytes, "peak_source": how}
-        if not args.no_extras:
-            # the other two BASELINE.json paths, measured in the same run (secondary numbers, not the headline metric)
-            trainer.ws = None
-            torch.cuda.empty_cache()
-            line["matcher"] = time_matcher(torch, ops)
-            line["kd_step"] = time_kd_step(torch)
-            line["ir50_teacher"] = time_ir50(torch)
+        line.update(extras)
         if not args.no_cpu_baseline:
-            v, cores, sec = cpu_reference_step_rate(3, 1)
-            line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
-                                    "sample": "oracle port, 3 timed steps of batch 4 x 128x128 fp32 (%.2f s/step)" % sec}
+            v, cores, sec, kind, what = cpu_reference_step_rate(3, 1)
+            line["cpu_baseline"] = {"value": v, "unit": "images/s", "cores": cores, "kind": kind,
+                                    "sample": "%s: 3 timed steps of batch 4 x 128x128 fp32 (%.2f s/step)" % (what, sec)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -396,7 +490,9 @@ def main():
     ap.add_argument("--batch", type=int, default=128)
     ap.add_argument("--chunk", type=int, default=128, help="images per native call")
     ap.add_argument("--lanes", type=int, default=1, help="concurrent chunk pipelines (streams) per GPU")
-    ap.add_argument("--graph", type=int, default=0, help="1: replay the step from a captured CUDA graph")
+    ap.add_argument("--graph", type=int, default=1, help="1: replay the step from a captured CUDA graph (default), 0: eager")
+    ap.add_argument("--verify", action="store_true", help="N > 1: check the all-reduced gradient against the single-GPU "
+                                                           "gradient of the concatenated batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the matcher / KD-step secondary measurements")
     args = ap.parse_args()

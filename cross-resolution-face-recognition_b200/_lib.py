@@ -94,6 +94,10 @@ SIGNATURES = {
     "crfr_verify_counts": (ci, [vp, vp, cll, cf, vp, vp]),
     "crfr_verify_sweep": (ci, [vp, vp, vp, ci, vp, ci, vp, vp]),
     "crfr_pair_verify": (ci, [vp, vp, cll, ci, cf, vp, vp, vp]),
+    "crfr_reflect_pad_fwd": (ci, [vp, ci, vp, ci, ci, ci, ci, ci, ci, vp]),
+    "crfr_reflect_pad_bwd": (ci, [vp, ci, vp, ci, ci, ci, ci, ci, ci, vp]),
+    "crfr_tanh_fwd": (ci, [vp, vp, cll, vp]),
+    "crfr_tanh_bwd": (ci, [vp, vp, vp, cll, vp]),
     "crfr_linear_workspace_bytes": (csz, [ci, ci, ci, ci]),
     "crfr_linear_fwd": (ci, [vp, ci, ci, ci, vp, vp, ci, vp, vp, csz, vp]),
     "crfr_linear_bwd": (ci, [vp, vp, ci, ci, ci, vp, ci, vp, vp, vp, vp, csz, vp]),

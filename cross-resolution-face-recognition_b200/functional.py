@@ -52,7 +52,11 @@ class _Conv2d(torch.autograd.Function):
     def forward(ctx, x, weight, bias, stride, pad, cin, engine):
         cout, k = weight.shape[0], weight.shape[2]
         wp = ops.pack_conv_weight(weight.detach(), s_pad=x.shape[3] if cin < 8 else None)
-        y, _, _ = ops.conv_fwd(x, wp, cin, cout, k, stride, pad, bias=None if bias is None else bias.detach(), engine=engine)
+        out_ld = 4 if cout < 8 else (cout + 7) // 8 * 8          # 16-byte aligned pixels (13 parsing / 68 landmark channels)
+        y, _, _ = ops.conv_fwd(x, wp, cin, cout, k, stride, pad, bias=None if bias is None else bias.detach(), engine=engine,
+                               out_ld=out_ld)
+        if out_ld != cout:
+            y[..., cout:] = 0                                     # padding channels are never written by the kernels
         ctx.save_for_backward(x, weight)
         ctx.cfg = (stride, pad, cin, cout, k, engine, bias is not None)
         return y
@@ -154,3 +158,130 @@ def linear(x, weight, bias=None):
     """nn.Linear applied to ``x.view(B, -1)`` of the NCHW tensor whose NHWC bf16 form is ``x`` [B, h, w, c];
     ``weight`` fp32 [out, c*h*w] in the reference's flatten order.  Returns NHWC bf16 [B, 1, 1, out]."""
     return _Linear.apply(x.contiguous(), weight, bias)
+
+
+class _ReflectPad(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, pad, c):
+        n, h, w, ld = x.shape
+        out = torch.empty((n, h + 2 * pad, w + 2 * pad, ld), dtype=torch.bfloat16, device=x.device)
+        L.call("crfr_reflect_pad_fwd", ops.ptr(x), ld, ops.ptr(out), ld, n, h, w, c, pad, ops.stream())
+        ctx.cfg = (n, h, w, ld, c, pad)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        n, h, w, ld, c, pad = ctx.cfg
+        dout = dout.contiguous()
+        dx = torch.zeros((n, h, w, ld), dtype=torch.bfloat16, device=dout.device) if ld != c else \
+            torch.empty((n, h, w, ld), dtype=torch.bfloat16, device=dout.device)
+        L.call("crfr_reflect_pad_bwd", ops.ptr(dout), ld, ops.ptr(dx), ld, n, h, w, c, pad, ops.stream())
+        return dx, None, None
+
+
+def reflect_pad(x, pad, c=None):
+    """nn.ReflectionPad2d(pad) on an NHWC bf16 activation (``c`` real channels; 3-channel images are stored with ld 4)."""
+    return _ReflectPad.apply(x.contiguous(), pad, x.shape[3] if c is None else c)
+
+
+class _Tanh(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous().float()
+        y = torch.empty_like(x)
+        L.call("crfr_tanh_fwd", ops.ptr(x), ops.ptr(y), x.numel(), ops.stream())
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        dy = dy.contiguous().float()
+        dx = torch.empty_like(y)
+        L.call("crfr_tanh_bwd", ops.ptr(y), ops.ptr(dy), ops.ptr(dx), y.numel(), ops.stream())
+        return dx
+
+
+def tanh(x):
+    """nn.Tanh on an fp32 tensor (the 3-channel image heads)."""
+    return _Tanh.apply(x)
+
+
+class _Add(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        return ops.add_n(a.contiguous(), b.contiguous())
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, g
+
+
+def add(a, b):
+    """a + b on NHWC bf16 activations (fp32 sum, one rounding)."""
+    return _Add.apply(a, b)
+
+
+class _ConvTranspose2d(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, stride, pad, out_pad, engine):
+        cin, cout, k = weight.shape[0], weight.shape[1], weight.shape[2]
+        n, h, w, _ = x.shape
+        oh = (h - 1) * stride - 2 * pad + k + out_pad
+        ow = (w - 1) * stride - 2 * pad + k + out_pad
+        wp = ops.pack_conv_weight(weight.detach(), transposed=True)
+        y, _, _ = ops.conv_fwd(x, wp, cin, cout, k, stride, pad, engine=engine, transposed=True, out_hw=(oh, ow))
+        ctx.save_for_backward(x, weight)
+        ctx.cfg = (stride, pad, cin, cout, k, engine)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        stride, pad, cin, cout, k, engine = ctx.cfg
+        dy = dy.contiguous()
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            wt = ops.pack_conv_weight(weight.detach(), for_dgrad=True, transposed=True)
+            dx = ops.conv_dgrad(dy, wt, tuple(x.shape), cin, cout, k, stride, pad, engine=engine, transposed=True)
+        if ctx.needs_input_grad[1]:
+            dw, _ = ops.conv_wgrad(x, dy, cin, cout, k, stride, pad, engine=engine, transposed=True)
+        return dx, dw, None, None, None, None
+
+
+def conv_transpose2d(x, weight, stride, pad, out_pad, engine=L.ENGINE_AUTO):
+    """nn.ConvTranspose2d (no bias) on an NHWC bf16 activation; ``weight`` fp32 [cin, cout, k, k]."""
+    return _ConvTranspose2d.apply(x.contiguous(), weight, stride, pad, out_pad, engine)
+
+
+class _MaxPool2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return ops.maxpool2_fwd(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return ops.maxpool2_bwd(x, g.contiguous())
+
+
+def max_pool2(x):
+    """F.max_pool2d(x, 2, stride=2)."""
+    return _MaxPool2.apply(x.contiguous())
+
+
+class _UpAdd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, up, low):
+        return ops.upnearest2_add_fwd(up.contiguous(), low.contiguous())
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        return g, ops.upnearest2_bwd(g)
+
+
+def up2_add(up, low):
+    """up + F.interpolate(low, scale_factor=2) (nearest)."""
+    return _UpAdd.apply(up, low)

@@ -91,10 +91,10 @@ def conv_desc(x, cin, cout, k, stride, pad, transposed=False, out_hw=None, out_l
 
 
 def conv_fwd(x, w_packed, cin, cout, k, stride, pad, bias=None, engine=L.ENGINE_AUTO, transposed=False, out_hw=None,
-             want_stats=False, nchw_out=False, eps=1e-5):
+             want_stats=False, nchw_out=False, eps=1e-5, out_ld=None):
     """Returns (y_nhwc_bf16 or None, y_nchw_f32 or None, stats [n,cout,2] or None)."""
     _need_cuda(x, w_packed, bias)
-    d = conv_desc(x, cin, cout, k, stride, pad, transposed, out_hw)
+    d = conv_desc(x, cin, cout, k, stride, pad, transposed, out_hw, out_ld)
     y = None if nchw_out else torch.empty((d.n, d.oh, d.ow, d.out_ld), dtype=torch.bfloat16, device=x.device)
     yn = torch.empty((d.n, cout, d.oh, d.ow), dtype=torch.float32, device=x.device) if nchw_out else None
     stats = torch.empty((d.n, cout, 2), dtype=torch.float32, device=x.device) if want_stats else None

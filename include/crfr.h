@@ -208,6 +208,15 @@ int crfr_verify_sweep(const float* dist, const uint8_t* issame, const int* subse
 int crfr_pair_verify(const float* e1, const float* e2, long long pairs, int dim, float thr, float* dist,
                      uint8_t* same, void* stream);
 
+/* ---------------------------------------------------------------- reflection padding, tanh ----------------- */
+/* ref: nn.ReflectionPad2d / nn.Tanh of the SUPER_RESOLUTION FSRNet variant (SUPER_RESOLUTION/model/FSRnet.py:251-416).
+ * x: NHWC bf16 [n][h][w][ld], out: [n][h+2p][w+2p][ld]; c a multiple of 8, or <= 4 with ld 4.  bwd folds dout back. */
+int crfr_reflect_pad_fwd(const void* x, int x_ld, void* out, int out_ld, int n, int h, int w, int c, int pad, void* stream);
+int crfr_reflect_pad_bwd(const void* dout, int dout_ld, void* dx, int dx_ld, int n, int h, int w, int c, int pad,
+                         void* stream);
+int crfr_tanh_fwd(const float* x, float* y, long long numel, void* stream);
+int crfr_tanh_bwd(const float* y, const float* dy, float* dx, long long numel, void* stream);
+
 /* ---------------------------------------------------------------- fully connected layer ------------------- */
 /* ref: nn.Linear on `x.view(B, -1)` of an NCHW map (model/FSRnet.py:469,484-486 Discriminator.fc; model/resnet.py:170,
  * 221-222).  x: NHWC bf16 [B][hw][c]; w: fp32 [out][c * hw] in the reference's NCHW-flatten order; y / dy: bf16 [B][out].

@@ -316,9 +316,50 @@ def golden_gan():
     print("gan224: oracle == reference; bf16-storage deviation per output", [round(rel(e, r), 4) for e, r in zip(emu, ref)])
 
 
+def golden_sr():
+    """SUPER_RESOLUTION/model/FSRnet.py:251-416: the four sub-networks of the newer FSRNet variant.  The restatement in
+    oracle/sr_oracle.py is pinned against the reference's modules; the fixture keeps the small outputs, statistics of the
+    large ones and the deviation of the oracle's own bf16-storage evaluation."""
+    from oracle import sr_oracle as SO
+    F = R.load("SUPER_RESOLUTION/model/FSRnet.py")
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(2, 3, 64, 64, generator=g)
+    xd = torch.randn(2, 128, 64, 64, generator=g)
+    rel = lambda a, b: ((a - b).double().norm() / b.double().norm()).item()
+    out = {}
+    for seed, (name, cls, fn, inp) in enumerate((("coarse", F.Coarse_SR_Network, SO.coarse_forward, x),
+                                                 ("encoder", F.Fine_SR_Encoder, SO.encoder_forward, x),
+                                                 ("prior", F.Prior_Estimation_Network, SO.prior_forward, x),
+                                                 ("decoder", F.Fine_SR_Decoder, SO.decoder_forward, xd)), start=700):
+        torch.manual_seed(seed)
+        net = cls()
+        with torch.no_grad():                    # non-trivial affine / PReLU parameters
+            for k, p in net.named_parameters():
+                if p.dim() == 1:
+                    p.add_(0.2 * torch.randn_like(p))
+        net.train()
+        sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+        with torch.no_grad():
+            ref = net(inp)
+            ours = fn(sd, inp)
+            emu = fn(sd, inp, pr=FO.Precision("bf16"))
+        ref = ref if isinstance(ref, tuple) else (ref,)
+        ours = ours if isinstance(ours, tuple) else (ours,)
+        emu = emu if isinstance(emu, tuple) else (emu,)
+        for a, b in zip(ref, ours):
+            assert torch.allclose(a, b, rtol=1e-3, atol=2e-4), (name, (a - b).abs().max())
+        out[name + "_seed"] = seed
+        for i, (a, e) in enumerate(zip(ref, emu)):
+            out["%s_%d_emu_rel" % (name, i)] = rel(e, a)
+            out["%s_%d_mean_std_norm" % (name, i)] = np.array([a.mean().item(), a.std().item(), a.norm().item()])
+            out["%s_%d_sample" % (name, i)] = a[:, :, ::8, ::8].numpy()
+        print("sr", name, "oracle == reference; bf16-storage deviation", [round(rel(e, a), 4) for a, e in zip(ref, emu)])
+    np.savez_compressed(os.path.join(OUT, "sr_variant.npz"), **out)
+
+
 if __name__ == "__main__":
     assert R.available(), "reference tree not present"
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or ["losses", "bicubic", "eval", "fsrnet", "resnet", "ir50", "heatmap", "augment", "gan"]
+    which = sys.argv[1:] or ["losses", "bicubic", "eval", "fsrnet", "resnet", "ir50", "heatmap", "augment", "gan", "sr"]
     for w in which:
         globals()["golden_" + w]()
