@@ -313,7 +313,7 @@ def time_norm_bwd(torch, ops, chunk):
 def verify_dp(torch, dist, world, rank, dev, per_rank=4, size=128):
     """Data-parallel correctness on hardware: the SUM-all-reduced gradient of `world` ranks with `per_rank` images each
     against the single-GPU gradient of the concatenated batch (computed on every rank, so no extra exchange).  FSRNet uses
-    InstanceNorm only, so the two are equal up to the bf16 storage noise of two differently partitioned evaluations."""
+    InstanceNorm only, so the two are equal up to fp32 summation order."""
     from crfr_b200.model.FSRnet import OverallNetwork, weights_init
     from crfr_b200.trainer import FSRNetTrainer
 
@@ -331,7 +331,10 @@ def verify_dp(torch, dist, world, rank, dev, per_rank=4, size=128):
         torch.manual_seed(1234)
         net = OverallNetwork()
         net.apply(weights_init)
-        tr = GradOnly(net.to(dev).train(), chunk=n, world_size=world if dp else 1)
+        # the single-GPU run walks the same images in chunks of `per_rank`: every chunk is then the same native call a rank
+        # makes (identical kernels, partitions and roundings), so the comparison isolates the data-parallel plumbing - loss
+        # scaling, bucket coverage, all-reduce - from the chaotic bf16 storage noise of differently partitioned forwards
+        tr = GradOnly(net.to(dev).train(), chunk=per_rank, world_size=world if dp else 1)
         if not dp:
             tr.dist = None
         sl = slice(rank * per_rank, (rank + 1) * per_rank) if dp else slice(0, n)
@@ -340,7 +343,7 @@ def verify_dp(torch, dist, world, rank, dev, per_rank=4, size=128):
         out.append(tr.flat_g.double().clone())
     rel = ((out[0] - out[1]).norm() / out[1].norm()).item()
     cos = float(out[0] @ out[1] / (out[0].norm() * out[1].norm()))
-    return {"rel_err_allreduced_vs_single_gpu": rel, "cosine": cos, "images": n, "ranks": world, "pass": bool(rel < 5e-2)}
+    return {"rel_err_allreduced_vs_single_gpu": rel, "cosine": cos, "images": n, "ranks": world, "pass": bool(rel < 1e-3)}
 
 
 def run_ours(args):
@@ -404,6 +407,7 @@ def run_ours(args):
             fn(i)
         barrier()
         launches0 = L.lib().crfr_launch_count()
+        replays0 = trainer.replays
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         if sampler:
             sampler.t_start = time.perf_counter()
@@ -414,7 +418,8 @@ def run_ours(args):
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
-        launches = L.lib().crfr_launch_count() - launches0
+        # eager launches are counted by the library; a CUDA-graph replay re-issues the launches counted during its capture
+        launches = L.lib().crfr_launch_count() - launches0 + (trainer.replays - replays0) * trainer.graph_launches
         if sampler:
             sampler.stop()
         t = torch.tensor([ms], device=dev)

@@ -142,6 +142,7 @@ class FSRNetTrainer:
         self._w_cache = {}
         self.use_graph = bool(use_graph) and dev.type == "cuda"
         self._graph, self._graph_key, self._static = None, None, None
+        self.graph_launches, self.replays = 0, 0     # launch accounting under graph replay (bench.py gpu_launches)
 
     def reset_optimizer_state(self):
         """The reference re-creates RMSprop every epoch (FSR_main.py:183-185): the square average restarts."""
@@ -257,13 +258,16 @@ class FSRNetTrainer:
             self._compute(*self._static)           # eager warm-up: workspaces, kernel attributes, helper streams
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
+            n0 = L.lib().crfr_launch_count()
             with torch.cuda.graph(graph):
                 self._compute(*self._static)
+            self.graph_launches = int(L.lib().crfr_launch_count() - n0)    # kernels of ours inside one replay
             self._graph, self._graph_key = graph, key
         else:
             for d, t in zip(self._static, (x, hr, heatmap, labels)):
                 d.copy_(t, non_blocking=True)
         self._graph.replay()
+        self.replays += 1
         if self.dist is not None and self.world > 1:
             works = [self._allreduce_bucket(k) for k in range(len(self.buckets))]
             for wk in works:

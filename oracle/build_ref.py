@@ -1,7 +1,7 @@
 """Builds oracle/_ref/: the reference's OWN modules for the hot path, byte-compiled.  TEST / BASELINE INFRASTRUCTURE ONLY.
 
 The reference is pure Python; its sources stay where they lie under /root/reference (never copied into the repo).  This
-recipe compiles the six modules of the path to CPython bytecode and writes ONLY those .pyc artefacts into oracle/_ref/
+recipe compiles the six modules of the path to CPython bytecode and writes ONLY those artefacts (*.refbin) into oracle/_ref/
 (git-ignored, but shipped to the GPU box with the snapshot, like our own built .so).  `bench.py --impl reference` and the
 `cpu_baseline` leg then time the real reference modules on the host cores (`kind: "reference"`); without oracle/_ref they
 fall back to the oracle port (`kind: "port"`).  Run in the build container:  python -m oracle.build_ref
@@ -21,6 +21,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 OUT = os.path.join(HERE, "_ref")
 REF_ROOT = os.environ.get("CRFR_REFERENCE_ROOT", "/root/reference")
+EXT = ".refbin"    # CPython bytecode; not named .pyc so that snapshot tools that skip byte-code caches still ship it
 MODULES = {"FSRnet": "model/FSRnet.py", "loss": "loss/loss.py", "resnet": "model/resnet.py",
            "model_irse": "DISTILLATION/model/model_irse.py", "eval": "utils/eval.py", "utils": "utils/utils.py"}
 
@@ -31,7 +32,7 @@ def build():
         return available()
     os.makedirs(OUT, exist_ok=True)
     for name, rel in MODULES.items():
-        py_compile.compile(os.path.join(REF_ROOT, rel), cfile=os.path.join(OUT, name + ".pyc"), doraise=True,
+        py_compile.compile(os.path.join(REF_ROOT, rel), cfile=os.path.join(OUT, name + EXT), doraise=True,
                            dfile="reference/" + rel)
     with open(os.path.join(OUT, "VERSION"), "w") as f:
         f.write("python %d.%d\n" % sys.version_info[:2])
@@ -39,7 +40,7 @@ def build():
 
 
 def available():
-    if not os.path.isfile(os.path.join(OUT, "FSRnet.pyc")):
+    if not os.path.isfile(os.path.join(OUT, "FSRnet" + EXT)):
         return False
     try:
         return open(os.path.join(OUT, "VERSION")).read().strip() == "python %d.%d" % sys.version_info[:2]
@@ -49,7 +50,7 @@ def available():
 
 def load(name):
     """Imports one byte-compiled reference module from oracle/_ref."""
-    path = os.path.join(OUT, name + ".pyc")
+    path = os.path.join(OUT, name + EXT)
     loader = importlib.machinery.SourcelessFileLoader("crfr_refbin_" + name, path)
     spec = importlib.util.spec_from_loader(loader.name, loader)
     mod = importlib.util.module_from_spec(spec)
