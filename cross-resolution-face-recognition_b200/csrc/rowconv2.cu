@@ -37,17 +37,16 @@ constexpr int kW = 128;
 constexpr int kC = 64;
 constexpr int kRowBytes = 130 * 128;       // one input row with halo, 128 B per pixel
 constexpr int kSlotBytes = 17 * 1024;      // ring slot stride (1024-aligned)
-constexpr int kSlots = 4;
+constexpr int kSlots = 5;
 constexpr int kCaseRows = 320;             // per kx: 96 + 64 + 64 + 32 + 32 + 32 rows (see case_row)
 constexpr int kKxBytes = kCaseRows * 128;
 constexpr int kWeightBytes = 3 * kKxBytes;
 constexpr int kThreads = 320;              // producer warp, MMA warp, 2 epilogue groups of 4 warps
-constexpr int kStageOutBytes = 128 * 128;
 constexpr int kAccSlots = 8;
 constexpr int kDone = 8;                   // ring of "input row consumed" barriers (a power of two >= kAccSlots)
-constexpr int kPrefetch = 12;              // rows pulled into L2 ahead of the shared-memory ring
-constexpr int kSmemBytes = kWeightBytes + kSlots * kSlotBytes + 2 * kStageOutBytes + 2 * 4 * 128 * 4 /*stats*/ +
-                           kC * 4 /*bias*/ + 1024 /*align*/ + 512 /*barriers*/;
+constexpr int kPrefetch = 8;               // rows pulled into L2 ahead of the shared-memory ring
+constexpr int kSmemBytes = kWeightBytes + kSlots * kSlotBytes + 2 * 4 * 128 * 4 /*stats*/ + kC * 4 /*bias*/ +
+                           1024 /*align*/ + 512 /*barriers*/;
 static_assert(kSmemBytes <= 232448, "shared memory budget");
 
 struct PairParams {
@@ -59,6 +58,8 @@ struct PairParams {
   const float* bias;
   float* partial;        // InstanceNorm partials [n][parts][2][64] or nullptr
   int parts;
+  bf16* dst;             // output NHWC [n][h][128][dst_ld]
+  int dst_ld;
 };
 
 // first row (of the 320 per kx) of the half that belongs to the sub-range (first tap j0, cnt taps) of the stacked B
@@ -164,14 +165,12 @@ __device__ __forceinline__ void issue_row(uint32_t d_tmem, uint32_t a_lo, uint32
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-rowconv_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
-                    const __grid_constant__ CUtensorMap tmY, PairParams p) {
+rowconv_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, PairParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sW = base;
   uint8_t* sRing = base + kWeightBytes;
-  uint8_t* sOut = sRing + kSlots * kSlotBytes;
-  float* sStat = (float*)(sOut + 2 * kStageOutBytes);   // [2 groups][4 warps][2][64]
+  float* sStat = (float*)(sRing + kSlots * kSlotBytes);   // [2 groups][4 warps][2][64]
   float* sBias = sStat + 2 * 4 * 128;
   uint64_t* full = (uint64_t*)(sBias + kC);        // [kSlots] this CTA's input row has landed
   uint64_t* peer_full = full + kSlots;             // [kSlots] rank 0 only: rank 1's row has landed
@@ -197,7 +196,6 @@ rowconv_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     fence_barrier_init();
     prefetch_tmap(&tmX);
     prefetch_tmap(&tmW);
-    prefetch_tmap(&tmY);
   }
   if (threadIdx.x >= 64 && threadIdx.x < 64 + kC) sBias[threadIdx.x - 64] = p.bias ? p.bias[threadIdx.x - 64] : 0.f;
   if (warp == 1) tmem_alloc_pair(tmem_slot);
@@ -237,17 +235,12 @@ rowconv_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
             }
           }
     }
-    // The ring holds 4 rows (68 KB), less than the DRAM latency x bandwidth product at the rate the MMAs consume rows:
-    // a second cursor runs kPrefetch rows ahead of the loads and pulls those rows into L2.
-    RowWalk ld(r_begin, r_end, p.h), pf(r_begin, r_end, p.h);
-    for (int i = 0; i < kPrefetch && pf.valid; ++i, pf.next())
-      if (leader) tma_prefetch_4d(&tmX, 0, -1, pf.iy, 2 * pf.pr + (int)rank);
+    // (An L2 prefetch cursor running 8-12 rows ahead of the ring - cp.async.bulk.prefetch.tensor or prefetch.global.L2 from
+    // this warp's lanes - made the kernel 3-6 us SLOWER once the issuing warp was no longer the bottleneck: the launch moves
+    // 537 MB in ~120 us, i.e. the memory system is already at 4.4 TB/s of mixed read / write traffic.)
+    RowWalk ld(r_begin, r_end, p.h);
     for (int g = 0; ld.valid; ++g, ld.next()) {
       const int s = g % kSlots;
-      if (pf.valid) {
-        if (leader) tma_prefetch_4d(&tmX, 0, -1, pf.iy, 2 * pf.pr + (int)rank);
-        pf.next();
-      }
       if (g >= kSlots) mbar_wait(&done[(g - kSlots) % kDone], ((g - kSlots) / kDone) & 1);   // row g - kSlots consumed
       if (leader) {
         if (p.dbg & 1) {
@@ -340,18 +333,20 @@ rowconv_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     }
   } else {
     // ------------------------------------------------------------------ epilogue (both CTAs)
-    // Two groups of four warps take alternate output rows.  One group's row is a serial chain (wait, tcgen05.ld, zero,
-    // pack, fence, TMA store, statistics) with a single warp per scheduler; two groups give each chain two rows of time.
-    // Each group has its own staging tile, named barriers, statistics accumulators and partial-sum slot.
+    // Two groups of four warps take alternate output rows (one group's row is a serial chain with a single warp per
+    // scheduler; two groups give each chain two rows of time).  The epilogue touches NO shared memory: the kernel is bound
+    // by shared-memory bandwidth (MMA operands 84 KB + TMA fill 17 KB per row), and a staging tile + TMA store + a
+    // statistics pass over the staged tile were another 48 KB per row.  Instead each warp transposes its 32 pixels x 64
+    // channels in registers - an 8 x 8 transpose of 16-byte chunks inside every group of 8 lanes (3 butterfly stages of
+    // shuffles) - after which lane j of a group holds chunk j (channels 8j .. 8j+7) of the group's 8 pixels: its stores are
+    // coalesced (8 lanes write one whole 128-byte pixel line) and its statistics accumulate locally per channel.
     const int ew = warp - 2, gi = ew >> 2;
-    const int q = warp & 3;                   // TMEM lane quadrant this warp may read
-    const int x = q * 32 + lane;              // pixel within the row (TMEM lane)
+    const int q = warp & 3;                   // TMEM lane quadrant this warp may read: pixels 32 q .. 32 q + 31
     const int et = (ew & 3) * 32 + lane;      // 0..127 within the group
-    const int cg = et & 7, pl = et >> 3;      // statistics role: channels [8 cg, 8 cg + 8), pixels pl + 16 i
-    const bool issuer = ((ew & 3) == 0) && (lane == 0);
+    const int cg = lane & 7;                  // after the transpose: this lane's channel chunk ...
+    const int pg = lane >> 3;                 // ... of pixels 32 q + 8 pg + (0..7)
     const bool has_bias = p.bias != nullptr;
-    const int bar_pack = 1 + 2 * gi, bar_stat = 2 + 2 * gi;
-    uint8_t* stile = sOut + gi * kStageOutBytes;
+    const int bar_stat = 1 + gi;
     float* sSt = sStat + gi * 512;
     const uint32_t remote_acc_empty0 = map_to_rank(&acc_empty[0], 0);   // rank 0's barrier array (own one for rank 0)
     float2 as[4], aq[4];
@@ -387,42 +382,48 @@ rowconv_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
         if (lane == 0) mbar_arrive_cluster(remote_acc_empty0 + 8u * (uint32_t)slot);
         if (prof) { const long long t1 = clock64(); e_tmem += t1 - t0; t0 = t1; }
         if (p.dbg & 4) continue;
-        // the TMA store this group issued two rows ago must have finished reading its staging tile
-        if (issuer) tma_store_wait_read<0>();
-        named_bar_sync(bar_pack, 128);
-        uint8_t* srow = stile + x * 128;
+        // + bias, round to bf16: w[4 c .. 4 c + 3] = chunk c (channels 8 c .. 8 c + 7) of this lane's pixel
+        uint32_t w[32];
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          float f[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v0[j + e]) + (has_bias ? sBias[j + e] : 0.f);
-          *reinterpret_cast<bf16x8*>(srow + (((j >> 3) ^ (x & 7)) << 4)) = pack8(f);
+        for (int k = 0; k < 16; ++k) {
+          const __nv_bfloat162 lo = __floats2bfloat162_rn(__uint_as_float(v0[2 * k]) + (has_bias ? sBias[2 * k] : 0.f),
+                                                          __uint_as_float(v0[2 * k + 1]) + (has_bias ? sBias[2 * k + 1] : 0.f));
+          const __nv_bfloat162 hi = __floats2bfloat162_rn(__uint_as_float(v1[2 * k]) + (has_bias ? sBias[32 + 2 * k] : 0.f),
+                                                          __uint_as_float(v1[2 * k + 1]) + (has_bias ? sBias[33 + 2 * k] : 0.f));
+          w[k] = *reinterpret_cast<const uint32_t*>(&lo);
+          w[16 + k] = *reinterpret_cast<const uint32_t*>(&hi);
         }
+        // 8 x 8 chunk transpose inside each group of 8 lanes: afterwards w[4 i .. 4 i + 3] = chunk cg of pixel 8 pg + i
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          float f[8];
+        for (int s = 4; s >= 1; s >>= 1) {
+          const bool up = (lane & s) != 0;
 #pragma unroll
-          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v1[j + e]) + (has_bias ? sBias[32 + j + e] : 0.f);
-          *reinterpret_cast<bf16x8*>(srow + ((((32 + j) >> 3) ^ (x & 7)) << 4)) = pack8(f);
+          for (int c = 0; c < 8; ++c) {
+            if (c & s) continue;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const uint32_t a = w[4 * c + e], b = w[4 * (c | s) + e];
+              const uint32_t recv = __shfl_xor_sync(0xffffffffu, up ? a : b, s);
+              w[4 * c + e] = up ? recv : a;
+              w[4 * (c | s) + e] = up ? b : recv;
+            }
+          }
         }
-        fence_proxy_async();
-        named_bar_sync(bar_pack, 128);
-        if (issuer && !(p.dbg & 8)) {
-          tma_store_4d(&tmY, stile, 0, 0, y, n);
-          tma_store_commit();
+        if (!(p.dbg & 8)) {
+          bf16* line = p.dst + (((long long)n * p.h + y) * kW + (q * 32 + pg * 8)) * p.dst_ld + cg * 8;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<uint4*>(line + (long long)i * p.dst_ld) = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
         }
         if (prof) { const long long t1 = clock64(); e_pack += t1 - t0; t0 = t1; }
         if (p.partial && !(p.dbg & 16)) {
-          // per-channel sums over this row from the staged (rounded) values: one 16-byte chunk (8 channels) of 8
-          // pixels per thread, packed fp32x2 arithmetic; a warp reads 4 whole pixel lines per step -> conflict free
+          // per-channel sums of the stored (rounded) values: this lane's 8 channels over its 8 pixels, packed fp32x2
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const int px = pl + 16 * i;
-            const uint4 v = *reinterpret_cast<const uint4*>(stile + px * 128 + ((cg ^ (px & 7)) << 4));
-            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const float2 f = make_float2(__uint_as_float(w4[k] << 16), __uint_as_float(w4[k] & 0xffff0000u));
+              const uint32_t u = w[4 * i + k];
+              const float2 f = make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
               as[k] = __fadd2_rn(as[k], f);
               aq[k] = __ffma2_rn(f, f, aq[k]);
             }
@@ -463,7 +464,6 @@ rowconv_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       gbase += iy1 - iy0 + 1;
       r += seg;
     }
-    if (issuer) tma_store_wait_read<0>();
     if (prof && lane == 0) {
       long long* o = g_pair_prof + cid * 16;
       o[5] = clock64() - e_start; o[6] = e_wait; o[7] = e_tmem; o[8] = e_pack; o[9] = e_stat;
@@ -508,13 +508,7 @@ int crfr_rowconv_pair(const void* src, int src_ld, int n, int h, const void* w_p
   CRFR_CHECK_ARG(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0 && ((uintptr_t)w_packed & 15) == 0 &&
                      (src_ld & 7) == 0 && (dst_ld & 7) == 0,
                  "rowconv_pair: pointers must be 16B aligned and ld a multiple of 8");
-  CUtensorMap tmX, tmW, tmY;
-  {
-    unsigned long long dims[4] = {(unsigned long long)kC, (unsigned long long)kW, (unsigned long long)h, (unsigned long long)n};
-    unsigned long long strides[3] = {(unsigned long long)dst_ld * 2, (unsigned long long)kW * dst_ld * 2, (unsigned long long)h * kW * dst_ld * 2};
-    unsigned int box[4] = {64, 128, 1, 1};
-    CRFR_TRY(crfr_tmap_encode_bf16(&tmY, dst, 4, dims, strides, box, "output"));
-  }
+  CUtensorMap tmX, tmW;
   {
     unsigned long long dims[4] = {(unsigned long long)kC, (unsigned long long)kW, (unsigned long long)h, (unsigned long long)n};
     unsigned long long strides[3] = {(unsigned long long)src_ld * 2, (unsigned long long)kW * src_ld * 2, (unsigned long long)h * kW * src_ld * 2};
@@ -535,6 +529,9 @@ int crfr_rowconv_pair(const void* src, int src_ld, int n, int h, const void* w_p
   p.bias = bias;
   p.partial = nullptr;
   p.parts = 0;
+  p.dst = (bf16*)dst;
+  p.dst_ld = dst_ld;
+
   if (stats) {
     const size_t need = crfr_rowconv_pair_ws_bytes(n, h);
     if (!ws || ws_bytes < need) {
@@ -544,7 +541,7 @@ int crfr_rowconv_pair(const void* src, int src_ld, int n, int h, const void* w_p
     p.partial = (float*)ws;
     p.parts = parts_for(n / 2, h);
   }
-  rowconv_pair_kernel<<<2 * clusters_for(p.total_rows), kThreads, kSmemBytes, st>>>(tmX, tmW, tmY, p);
+  rowconv_pair_kernel<<<2 * clusters_for(p.total_rows), kThreads, kSmemBytes, st>>>(tmX, tmW, p);
   CRFR_COUNT_LAUNCH();
   CRFR_LAUNCH_CHECK();
   if (stats) CRFR_TRY(crfr_norm_finalize(p.partial, n, p.parts, h * kW, kC, eps, stats, st));
