@@ -205,7 +205,7 @@ def time_kd_step(torch, dist, world, batch=256, reps=3, teacher_kind="resnet34")
     if teacher_kind == "ir50":
         teacher = IR_50([112, 112]).cuda()
     teacher.eval(); student.train(); assistant.train()
-    tr = KDTrainer(teacher, student, assistant, lr=1e-4)
+    tr = KDTrainer(teacher, student, assistant, lr=1e-4, use_graph=True)
     x_hr = torch.randn(batch, 3, 112, 112, device="cuda")
     x_lr = torch.randn(batch, 3, 112, 112, device="cuda")
     for _ in range(2):                   # warm-up: kernel attributes, allocator pools for the 9 GB workspaces
@@ -228,7 +228,7 @@ def time_kd_step(torch, dist, world, batch=256, reps=3, teacher_kind="resnet34")
     return {"images_per_sec": world * batch / (ms * 1e-3), "ms_per_step": ms, "tflops_per_gpu": batch * flop / (ms * 1e-3) / 1e12,
             "student_loss": float(losses[0].item()), "assistant_loss": float(losses[1].item()),
             "workload": "KDTrainer step: %s teacher (eval, HR batch) + ResNet_34 student + assistant (LR batch), batch %d per "
-                        "GPU, 112x112, all-reduce + RMSprop included" % (teacher_kind, batch)}
+                        "GPU, 112x112, CUDA-graph replay, all-reduce + RMSprop included" % (teacher_kind, batch)}
 
 
 def time_ir50(torch, batch=256, reps=3):

@@ -222,7 +222,7 @@ def check_kd_input(x, name="x"):
 
 
 def kd_native_call(teacher, student, assistant, x_hr, x_lr, stabs, atabs, losses, assistant_grad_to_student=True,
-                   events=None):
+                   events=None, ws=None):
     """crfr_kd_train_step on prepared tables: stabs / atabs = (params, buffers, grads) _TableOfPointers of the student and
     the assistant (gradients are ACCUMULATED into the grads tables)."""
     tp, tb, is_ir50 = _teacher_tables(teacher)
@@ -234,7 +234,9 @@ def kd_native_call(teacher, student, assistant, x_hr, x_lr, stabs, atabs, losses
     io.momentum, io.eps, io.assistant_grad_to_student = 0.1, 1e-5, int(bool(assistant_grad_to_student))
     for i, e in enumerate(events or ()):
         io.events[i] = e.cuda_event
-    ws = ops.workspace(L.lib().crfr_kd_workspace_bytes_ex(b, 112, is_ir50))
+    need = L.lib().crfr_kd_workspace_bytes_ex(b, 112, is_ir50)
+    if ws is None or ws.numel() < need:
+        ws = ops.workspace(need)
     L.call("crfr_kd_train_step", student.engine, tp.arr, tb.arr, stabs[0].arr, stabs[1].arr, stabs[2].arr, atabs[0].arr,
            atabs[1].arr, atabs[2].arr, C.byref(io), losses.data_ptr(), ws.data_ptr(), ws.numel(), ops.stream())
 

@@ -369,7 +369,7 @@ class KDTrainer:
     """
 
     def __init__(self, teacher, student, assistant, lr=1e-4, alpha=0.99, eps=1e-8, weight_decay=1e-5,
-                 assistant_grad_to_student=True, process_group=None, world_size=None):
+                 assistant_grad_to_student=True, process_group=None, world_size=None, use_graph=False):
         import torch.distributed as dist
         self.teacher, self.student, self.assistant = teacher, student, assistant
         self.lr, self.alpha, self.eps, self.wd = lr, alpha, eps, weight_decay
@@ -388,6 +388,13 @@ class KDTrainer:
                 e.record()
         else:
             self.comm_stream, self.events = None, []
+        # CUDA graph (``use_graph=True``): the ~1 300 launches of the native step are captured once per input shape and
+        # replayed from static input buffers (-2.8 ms of launch gaps on a 38 ms step); the all-reduces and the optimiser
+        # step stay outside the graph, so under data parallelism the student's all-reduce no longer overlaps the
+        # assistant's backward (2 x 136 MB over NVLink after the replay).
+        self.use_graph = bool(use_graph) and dev.type == "cuda"
+        self._graph, self._graph_key, self._static, self._ws = None, None, None, None
+        self.graph_launches, self.replays = 0, 0
 
     def reset_optimizer_state(self):
         """The reference re-creates both RMSprop optimisers every epoch (distill_main.py:222-225)."""
@@ -398,7 +405,41 @@ class KDTrainer:
     def _native_step(self, x_hr, x_lr, events):
         from .model import resnet as R
         R.kd_native_call(self.teacher, self.student, self.assistant, x_hr, x_lr, self.S.tabs, self.A.tabs, self.losses,
-                         self.to_student, events)
+                         self.to_student, events, ws=self._ws)
+
+    def _graph_step(self, x_hr, x_lr):
+        """Replay of the captured native step (gradient zeroing included) from static input buffers."""
+        key = (tuple(x_hr.shape), x_lr is not None)
+        if self._graph is None or self._graph_key != key:
+            from .model import resnet as R
+            self._static = (torch.empty_like(x_hr), None if x_lr is None else torch.empty_like(x_lr))
+            self._static[0].copy_(x_hr)
+            if x_lr is not None:
+                self._static[1].copy_(x_lr)
+            need = L.lib().crfr_kd_workspace_bytes_ex(x_hr.shape[0], 112, 1 if R._is_ir50(self.teacher) else 0)
+            self._ws = torch.empty(need, dtype=torch.uint8, device=x_hr.device)     # private: the graph holds its address
+            # eager warm-up (kernel attributes, helper streams) with the BatchNorm buffers restored afterwards, so that the
+            # first replayed step is the first running-statistics update
+            bufs = [b for n in (self.student, self.assistant) for b in n.ordered_buffers()]
+            saved = [b.clone() for b in bufs]
+            self._native_step(self._static[0], self._static[1], None)
+            for b, v in zip(bufs, saved):
+                b.copy_(v)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            n0 = L.lib().crfr_launch_count()
+            with torch.cuda.graph(graph):
+                self.S.flat_g.zero_()
+                self.A.flat_g.zero_()
+                self._native_step(self._static[0], self._static[1], None)
+            self.graph_launches = int(L.lib().crfr_launch_count() - n0)
+            self._graph, self._graph_key = graph, key
+        else:
+            self._static[0].copy_(x_hr, non_blocking=True)
+            if x_lr is not None:
+                self._static[1].copy_(x_lr, non_blocking=True)
+        self._graph.replay()
+        self.replays += 1
 
     def _optimizer_step(self, lr):
         for f in (self.S, self.A):
@@ -411,13 +452,17 @@ class KDTrainer:
             R.check_kd_nets(self.teacher, self.student, self.assistant)
             x_hr = R.check_kd_input(x_hr, "x_hr")
             x_lr = None if x_lr is None else R.check_kd_input(x_lr, "x_lr")
-        self.S.flat_g.zero_()
-        self.A.flat_g.zero_()
         dp = self.dist is not None and self.world > 1
-        self._native_step(x_hr, x_lr, self.events if (dp and self.events) else None)
+        graphed = self.use_graph and x_hr.is_cuda
+        if graphed:
+            self._graph_step(x_hr, x_lr)
+        else:
+            self.S.flat_g.zero_()
+            self.A.flat_g.zero_()
+            self._native_step(x_hr, x_lr, self.events if (dp and self.events) else None)
         if dp:
             works = []
-            if self.events:
+            if self.events and not graphed:
                 with torch.cuda.stream(self.comm_stream):
                     for f, ev in zip((self.S, self.A), self.events):
                         self.comm_stream.wait_event(ev)

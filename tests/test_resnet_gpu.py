@@ -257,7 +257,8 @@ def test_kd_step_hr_teacher_lr_student(cuda, teacher_kind):
         assert float(a @ b / (a.norm() * b.norm())) > 0.999, tag
 
 
-def test_kd_trainer_step_equals_native_step_plus_rmsprop(cuda):
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_kd_trainer_step_equals_native_step_plus_rmsprop(cuda, use_graph):
     """KDTrainer (flat arenas, fused RMSprop, the data-parallel plumbing with world = 1): its gradients are those of
     kd_train_step, and its update is torch.optim.RMSprop's with the reference's hyper-parameters (distill_main.py:222-225)
     applied to exactly those gradients.  (The first RMSprop step moves every element by ~10 lr whatever its size, so
@@ -273,7 +274,7 @@ def test_kd_trainer_step_equals_native_step_plus_rmsprop(cuda):
     ref_g = [[p.grad.clone() for p in n.parameters()] for n in (student, assistant)]
     (teacher2, student2, assistant2), _ = _nets()
     teacher2.eval(); student2.train(); assistant2.train()
-    tr = KDTrainer(teacher2, student2, assistant2, lr=1e-4)
+    tr = KDTrainer(teacher2, student2, assistant2, lr=1e-4, use_graph=use_graph)
     before = [f.flat_p.clone() for f in (tr.S, tr.A)]
     losses = tr.step(x_hr, x_lr)
     torch.cuda.synchronize()
