@@ -69,6 +69,9 @@ SIGNATURES = {
     "crfr_norm_act_fwd": (ci, [vp, ci, vp, vp, vp, vp, ci, vp, ci, vp, ci, ci, ci, ci, vp]),
     "crfr_norm_act_bwd": (ci, [vp, ci, vp, ci, vp, ci, vp, vp, vp, vp, ci, vp, ci, vp, ci, vp, ci, vp, vp, vp, ci, ci,
                                ci, vp, csz, vp]),
+    "crfr_conv_dgrad_norm_bwd_workspace_bytes": (csz, [C.POINTER(ConvDesc)]),
+    "crfr_conv_dgrad_norm_bwd": (ci, [ci, C.POINTER(ConvDesc), vp, vp, ci, vp, ci, vp, ci, vp, vp, vp, vp, ci, vp, ci, vp,
+                                      ci, vp, ci, vp, vp, vp, vp, csz, vp]),
     "crfr_maxpool2_fwd": (ci, [vp, ci, vp, ci, ci, ci, ci, ci, vp]),
     "crfr_maxpool2_bwd": (ci, [vp, ci, vp, ci, vp, ci, ci, ci, ci, ci, vp]),
     "crfr_upnearest2_add_fwd": (ci, [vp, ci, vp, ci, vp, ci, ci, ci, ci, ci, vp]),

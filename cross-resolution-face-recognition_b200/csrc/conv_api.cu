@@ -31,7 +31,8 @@ const OptDef kOpts[CRFR_OPT_COUNT] = {
     {"rowconv", "CRFR_ROWCONV", 1},           {"rowconv_pair", "CRFR_ROWCONV_PAIR", 1},
     {"pair_swap", "CRFR_PAIR_SWAP", 0},       {"wgrad_stream", "CRFR_WGRAD_STREAM", 1},
     {"norm_bwd_impl", "CRFR_NORM_BWD", 1},    {"norm_fwd_stream", "CRFR_NORM_FWD_STREAM", 1},
-    {"rowwgrad_pair", "CRFR_ROWWGRAD_PAIR", 1}, {"pair_debug", "CRFR_PAIR_DEBUG", 0}};
+    {"rowwgrad_pair", "CRFR_ROWWGRAD_PAIR", 1}, {"fuse_norm_bwd", "CRFR_FUSE_NORM_BWD", 1},
+    {"pair_debug", "CRFR_PAIR_DEBUG", 0}};
 std::atomic<int> g_opt[CRFR_OPT_COUNT];
 std::atomic<int> g_opt_init{0};
 void opts_init() {
@@ -177,6 +178,62 @@ extern "C" int crfr_conv_dgrad(int engine, const crfr_conv_desc* d, const void* 
                               d->cin, cout_pad, nullptr, dx, d->in_ld, nullptr, st);
   return crfr_direct_gather(1, d->n, d->oh, d->ow, d->h, d->w, d->k, d->stride, d->pad, dy, d->out_ld, w_packed_t,
                             d->cin, cout_pad, nullptr, dx, d->in_ld, nullptr, st);
+}
+
+// ---- dgrad + backward of the normalisation that produced the convolution's input, as one operation ----------------
+static bool dgrad_norm_fusable(int engine, const crfr_conv_desc* d, int cout_pad) {
+  return engine != CRFR_ENGINE_DIRECT && crfr_opt(CRFR_OPT_FUSE_NORM_BWD) && crfr_opt(CRFR_OPT_ROWCONV) &&
+         crfr_opt(CRFR_OPT_ROWCONV_PAIR) && !d->transposed && cout_pad == d->cout && crfr_lowered_recipe(d) < 2 &&
+         crfr_rowconv_supported(d->h, d->w, d->cin, d->cout, d->k, d->stride, d->pad) &&
+         crfr_rowconv_pair_supported(d->n, d->h);
+}
+
+extern "C" size_t crfr_conv_dgrad_norm_bwd_workspace_bytes(const crfr_conv_desc* d) {
+  if (!d) return 0;
+  const size_t conv = crfr_conv_workspace_bytes(d), norm = crfr_norm_ws_bytes(d->n, d->h * d->w, d->cin);
+  size_t fused = 0;
+  if (crfr_rowconv_supported(d->h, d->w, d->cin, d->cout, d->k, d->stride, d->pad) && crfr_rowconv_pair_supported(d->n, d->h))
+    fused = sizeof(float) * ((size_t)d->n * crfr_rowconv_pair_parts(d->n, d->h) * 3 * d->cin + (size_t)d->n * d->cin * 5) + 256;
+  size_t m = conv > norm ? conv : norm;
+  return (m > fused ? m : fused) + 1024;
+}
+
+extern "C" int crfr_conv_dgrad_norm_bwd(int engine, const crfr_conv_desc* d, const void* dout, const void* w_packed_t,
+                                        int cout_pad, const void* dx_b, int dxb_ld, const void* y, int y_ld,
+                                        const float* stats, const float* gamma, const float* beta, const float* alpha,
+                                        int relu, const void* res, int res_ld, void* dz, int dz_ld, void* dy, int dy_ld,
+                                        float* dgamma, float* dbeta, float* dalpha, void* ws, size_t ws_bytes,
+                                        void* stream) {
+  CRFR_TRY(check_desc(d, "conv_dgrad_norm_bwd"));
+  CRFR_CHECK_ARG(dout && w_packed_t && y && stats && dz && dy, "conv_dgrad_norm_bwd: null pointer");
+  CRFR_CHECK_ARG(dz_ld >= d->cin && dy_ld >= d->cin && y_ld >= d->cin, "conv_dgrad_norm_bwd: ld smaller than channel count");
+  const size_t need = crfr_conv_dgrad_norm_bwd_workspace_bytes(d);
+  if (!ws || ws_bytes < need) {
+    crfr_set_error("conv_dgrad_norm_bwd: workspace %zu < %zu", ws_bytes, need);
+    return CRFR_EWORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = d->n, hw = d->h * d->w, c = d->cin;
+  if (dgrad_norm_fusable(engine, d, cout_pad)) {
+    const int parts = crfr_rowconv_pair_parts(n, d->h);
+    float* partial = (float*)ws;
+    float* bstats = partial + (size_t)n * parts * 3 * c;
+    float* tot = bstats + (size_t)n * c * 2;
+    crfr_rowconv_fuse f = {y, y_ld, dx_b, dx_b ? dxb_ld : 8, res, res ? res_ld : 8, stats, gamma, beta, alpha, relu, partial};
+    CRFR_TRY(crfr_rowconv_pair(dout, d->out_ld, n, d->h, w_packed_t, 1, nullptr, dz, dz_ld, nullptr, 0.f, nullptr, 0, st, &f));
+    const void* views[3] = {dz, y, dy};
+    const int lds[3] = {dz_ld, y_ld, dy_ld};
+    const int use_stream = crfr_opt(CRFR_OPT_NORM_BWD_STREAM) >= 1 && crfr_norm_stream_supported(c, (long long)n * hw, views, lds, 3);
+    return crfr_norm_bwd_finish(partial, parts, dz, dz_ld, 0, y, y_ld, stats, gamma, beta, alpha, relu, dy, dy_ld, dgamma,
+                                dbeta, dalpha, n, hw, c, bstats, tot, use_stream, st);
+  }
+  // unfused: the dgrad output goes through the dz buffer, which the first pass then rewrites in place (element-wise,
+  // each element read before it is written by the same thread)
+  crfr_conv_desc dd = *d;
+  dd.in_ld = dz_ld;
+  CRFR_TRY(crfr_conv_dgrad(engine, &dd, dout, w_packed_t, cout_pad, dz, ws, ws_bytes, stream));
+  return crfr_norm_act_bwd(dz, dz_ld, dx_b, dx_b ? dxb_ld : 8, y, y_ld, stats, gamma, beta, alpha, relu, res, res ? res_ld : 8,
+                           dz, dz_ld, dy, dy_ld, dgamma, dbeta, dalpha, n, hw, c, ws, ws_bytes, stream);
 }
 
 extern "C" int crfr_conv_wgrad(int engine, const crfr_conv_desc* d, const void* x, const void* dy, float* dw,

@@ -133,6 +133,7 @@ struct Op {
   float* stats = nullptr;  // OP_NORM
   bool has_res = false;
   bool x_needs_grad = true;
+  bool bwd_done = false;   // OP_NORM: its backward already ran, fused into the backward of the convolution it feeds
 };
 
 struct Net {
@@ -389,6 +390,8 @@ struct Net {
         size_t b = crfr_conv_workspace_bytes(&sd);
         if (b > scratch_bytes) scratch_bytes = b;
       }
+      const size_t fb = crfr_conv_dgrad_norm_bwd_workspace_bytes(&shapes[0]);
+      if (fb > scratch_bytes) scratch_bytes = fb;
     }
     scratch = alloc(scratch_bytes);
     if (training) {
@@ -554,7 +557,7 @@ struct Net {
       Op& op = tape[i];
       switch (op.kind) {
         case OP_NORM: {
-          if (!has_grad(op.out)) break;
+          if (op.bwd_done || !has_grad(op.out)) break;
           squash(op.out, 2);
           std::vector<Slot>& s = slots[op.out.id];
           const Tensor& y = op.a;
@@ -584,7 +587,38 @@ struct Net {
                               !d.transposed && crfr_tc_supported(2, d.h, d.w, d.cin, d.cout, d.k, d.stride, d.pad);
           if (!forked && run())
             check(crfr_conv_wgrad(engine, &d, op.a.p, dy.p, grad(op.w_idx), grad(op.b_idx), scratch, scratch_bytes, st));
-          if (op.x_needs_grad) {
+          // The convolution's input is the output of the normalisation recorded just before it (every other consumer of
+          // that tensor comes later in the tape, so its remaining gradient slots are complete): dgrad + the whole
+          // normalisation backward as one operation - for the row-streaming shapes the first pass of the normalisation
+          // backward runs inside the dgrad epilogue and the dgrad output never reaches memory.
+          Op* nop = (i > 0 && tape[i - 1].kind == OP_NORM && tape[i - 1].out.id == op.a.id) ? &tape[i - 1] : nullptr;
+          if (op.x_needs_grad && nop && !d.transposed && engine != CRFR_ENGINE_DIRECT && crfr_opt(CRFR_OPT_FUSE_NORM_BWD) &&
+              crfr_lowered_recipe(&d) == 0 && crfr_rowconv_supported(d.h, d.w, d.cin, d.cout, d.k, d.stride, d.pad) &&
+              crfr_rowconv_pair_supported(d.n, d.h) && op.a.c == nop->a.c) {
+            const Tensor& x = op.a;
+            const Tensor& yn = nop->a;
+            squash(x, 1);
+            std::vector<Slot>& xs = slots[x.id];
+            const size_t bytes = (size_t)x.n * x.h * x.w * x.c * sizeof(bf16);
+            bf16* dz = (bf16*)alloc(bytes);
+            bf16* dyn = (bf16*)alloc(bytes);
+            crfr_conv_desc dd = d;
+            dd.in_ld = x.c;
+            void* wt = pack(op.w_idx, d.cout, d.cin, d.k, 0, false, true);
+            if (run())
+              check(crfr_conv_dgrad_norm_bwd(engine, &dd, dy.p, wt, d.cout, xs.empty() ? nullptr : xs[0].p,
+                                             xs.empty() ? 8 : xs[0].ld, yn.p, yn.ld, nop->stats,
+                                             nop->g_idx >= 0 ? params[nop->g_idx] : nullptr,
+                                             nop->beta_idx >= 0 ? params[nop->beta_idx] : nullptr,
+                                             nop->alpha_idx >= 0 ? params[nop->alpha_idx] : nullptr, 0,
+                                             nop->has_res ? nop->b.p : nullptr, nop->has_res ? nop->b.ld : 8, dz, x.c, dyn,
+                                             x.c, grad(nop->g_idx), grad(nop->beta_idx), grad(nop->alpha_idx), scratch,
+                                             scratch_bytes, st));
+            xs.clear();
+            add_slot(yn, dyn, x.c);
+            if (nop->has_res) add_slot(nop->b, dz, x.c);
+            nop->bwd_done = true;
+          } else if (op.x_needs_grad) {
             const Tensor& x = op.a;
             const int xc = x.c < 8 ? 4 : x.c;
             bf16* dx = (bf16*)alloc((size_t)x.n * x.h * x.w * xc * sizeof(bf16));

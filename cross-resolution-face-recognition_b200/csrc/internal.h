@@ -20,6 +20,7 @@ enum {
   CRFR_OPT_NORM_BWD_STREAM,  // TMA-fed normalisation backward (else register-staged)
   CRFR_OPT_NORM_FWD_STREAM,  // TMA-fed normalisation forward
   CRFR_OPT_ROWWGRAD_PAIR,    // cta_group::2 form of the row-streaming weight gradient
+  CRFR_OPT_FUSE_NORM_BWD,    // crfr_conv_dgrad_norm_bwd: first pass of the normalisation backward in the dgrad epilogue
   CRFR_OPT_PAIR_DEBUG,       // ablation bits for tools/pair_diag.py (results are WRONG when set): 1 no loads, 2 no MMAs,
                              // 4 no pack / store / statistics, 8 no store, 16 no statistics
   CRFR_OPT_COUNT
@@ -65,6 +66,12 @@ int crfr_pack_weight_batch(const crfr_pack_job* jobs, int n, cudaStream_t st);
 size_t crfr_norm_ws_bytes(int n, int hw, int c);
 int crfr_norm_finalize(const float* partial, int n, int chunks, int hw, int c, float eps, float* stats,
                        cudaStream_t st);
+// second half of the normalisation backward (fold of the first pass' partials [n][chunks][3][c] + apply pass); bstats
+// [n][c][2] and tot [n][3][c] are scratch.  dsrc = dz, or dout with recompute != 0.
+int crfr_norm_bwd_finish(const float* partial, int chunks, const void* dsrc, int dsrc_ld, int recompute, const void* y,
+                         int y_ld, const float* stats, const float* gamma, const float* beta, const float* alpha, int relu,
+                         void* dy, int dy_ld, float* dgamma, float* dbeta, float* dalpha, int n, int hw, int c,
+                         float* bstats, float* tot, int use_stream, cudaStream_t st);
 
 // norm_stream.cu: TMA-fed reduce / apply passes of the normalisation backward (same contract as the kernels in
 // norm_act.cu; views = the tensors the passes touch, checked for TMA alignment)
@@ -142,8 +149,20 @@ size_t crfr_rowconv_ws_bytes(int n, int h);
 // rowconv2.cu: cta_group::2 form of the same kernel (two CTAs walk the same rows of two images); n must be even
 int crfr_rowconv_pair_supported(int n, int h);
 size_t crfr_rowconv_pair_ws_bytes(int n, int h);
+// optional fusion of the first pass of a normalisation backward into the dgrad epilogue: the convolution's input was
+// out = act(gamma * (y - mean) * rstd + beta (+ res)); with D = dgrad output (+ db) the kernel stores dz = D * act'(z)
+// instead of the dgrad output and the partial sums of (dz, dz * xhat, D * min(z, 0)) per (image, channel)
+struct crfr_rowconv_fuse {
+  const void* y; int y_ld;        // raw map the normalisation read (same pixels as the dgrad output)
+  const void* db; int db_ld;      // second gradient of the normalised tensor, or NULL
+  const void* res; int res_ld;    // residual input of the normalisation, or NULL
+  const float* stats; const float* gamma; const float* beta; const float* alpha; int relu;
+  float* partial;                 // out: [n][crfr_rowconv_pair_parts(n, h)][3][64]
+};
+int crfr_rowconv_pair_parts(int n, int h);
 int crfr_rowconv_pair(const void* src, int src_ld, int n, int h, const void* w_packed, int flip, const float* bias,
-                      void* dst, int dst_ld, float* stats, float eps, void* ws, size_t ws_bytes, cudaStream_t st);
+                      void* dst, int dst_ld, float* stats, float eps, void* ws, size_t ws_bytes, cudaStream_t st,
+                      const crfr_rowconv_fuse* fuse = nullptr);
 // rowwgrad.cu: persistent row-streaming weight gradient of the same shape (deterministic slab reduction)
 int crfr_rowwgrad_supported(int h, int w, int cin, int cout, int k, int stride, int pad);
 size_t crfr_rowwgrad_ws_bytes(int n, int h);

@@ -534,16 +534,27 @@ extern "C" int crfr_norm_act_bwd(const void* dout_a, int da_ld, const void* dout
     CRFR_COUNT_LAUNCH();
     CRFR_LAUNCH_CHECK();
   }
+  return crfr_norm_bwd_finish(partial, chunks, dz ? dz : dout_a, dz ? dz_ld : da_ld, dz == nullptr, y, y_ld, stats, gamma,
+                              beta, alpha, relu, dy, dy_ld, dgamma, dbeta, dalpha, n, hw, c, bstats, tot, tma ? 1 : 0, st);
+}
+
+// Second half of the normalisation backward: fold the first pass' partials [n][chunks][3][c] (wherever that pass ran:
+// the reduce kernels above / in norm_stream.cu, or the dgrad epilogue of rowconv2.cu), then the apply pass.
+// dsrc = dz, or dout when recompute != 0 (dz is then rebuilt from dout and y with the first pass' arithmetic).
+int crfr_norm_bwd_finish(const float* partial, int chunks, const void* dsrc, int dsrc_ld, int recompute, const void* y,
+                         int y_ld, const float* stats, const float* gamma, const float* beta, const float* alpha, int relu,
+                         void* dy, int dy_ld, float* dgamma, float* dbeta, float* dalpha, int n, int hw, int c,
+                         float* bstats, float* tot, int use_stream, cudaStream_t st) {
   bwd_fold_kernel<<<dim3(n, c / 8), kThreads, 0, st>>>(partial, chunks, c, 1.f / (float)hw, bstats, tot);
   CRFR_COUNT_LAUNCH();
   CRFR_LAUNCH_CHECK();
-  if (tma)
-    return crfr_norm_bwd_apply_stream(dz ? dz : dout_a, dz ? dz_ld : da_ld, dz == nullptr, y, y_ld, stats, bstats, tot,
-                                      gamma, beta, alpha, relu, dy, dy_ld, dgamma, dbeta, dalpha, n, hw, c, st);
-  norm_act_bwd_apply_kernel<<<dim3(pl.chunks, n), kThreads, 0, st>>>((const bf16*)dz, dz_ld, (const bf16*)y, y_ld,
-                                                                     stats, bstats, gamma, (bf16*)dy, dy_ld, hw, c,
-                                                                     pl.chunk_pix, tot, n, dgamma, dbeta, dalpha,
-                                                                     (const bf16*)dout_a, da_ld, beta, alpha, relu);
+  if (use_stream)
+    return crfr_norm_bwd_apply_stream(dsrc, dsrc_ld, recompute, y, y_ld, stats, bstats, tot, gamma, beta, alpha, relu, dy,
+                                      dy_ld, dgamma, dbeta, dalpha, n, hw, c, st);
+  ChunkPlan pl = plan_chunks(n, hw);
+  norm_act_bwd_apply_kernel<<<dim3(pl.chunks, n), kThreads, 0, st>>>(
+      recompute ? nullptr : (const bf16*)dsrc, dsrc_ld, (const bf16*)y, y_ld, stats, bstats, gamma, (bf16*)dy, dy_ld, hw, c,
+      pl.chunk_pix, tot, n, dgamma, dbeta, dalpha, recompute ? (const bf16*)dsrc : nullptr, dsrc_ld, beta, alpha, relu);
   CRFR_COUNT_LAUNCH();
   CRFR_LAUNCH_CHECK();
   return CRFR_OK;

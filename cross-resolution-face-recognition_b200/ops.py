@@ -194,6 +194,29 @@ def norm_act_bwd(dout, y, stats, gamma=None, beta=None, alpha=None, relu=False, 
     return dz, dy, dg, db, da
 
 
+def conv_dgrad_norm_bwd(dout, w_packed_t, y, stats, cin, cout, k, stride, pad, gamma=None, beta=None, alpha=None,
+                        relu=False, res=None, dx_b=None, engine=L.ENGINE_AUTO):
+    """Backward across `conv(act(norm(y) (+ res)))`: dgrad of the convolution + the normalisation backward in one call
+    (crfr_conv_dgrad_norm_bwd).  dout: NHWC bf16 gradient of the convolution output; y: the raw map the normalisation
+    read.  Returns (dz, dy, dgamma, dbeta, dalpha) as norm_act_bwd does (dz always produced)."""
+    _need_cuda(dout, w_packed_t, y, stats)
+    n, h, w, ld = y.shape
+    c = cin
+    d = L.ConvDesc(n, h, w, cin, cout, k, stride, pad, dout.shape[1], dout.shape[2], ld, dout.shape[3], 0)
+    dev = y.device
+    dz = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=dev)
+    dy = torch.empty((n, h, w, c), dtype=torch.bfloat16, device=dev)
+    dg = torch.zeros((c,), dtype=torch.float32, device=dev) if gamma is not None else None
+    db = torch.zeros((c,), dtype=torch.float32, device=dev) if beta is not None else None
+    da = torch.zeros((c,), dtype=torch.float32, device=dev) if alpha is not None else None
+    ws = workspace(L.lib().crfr_conv_dgrad_norm_bwd_workspace_bytes(C.byref(d)))
+    L.call("crfr_conv_dgrad_norm_bwd", engine, C.byref(d), ptr(dout), ptr(w_packed_t), w_packed_t.shape[2], ptr(dx_b),
+           8 if dx_b is None else dx_b.shape[3], ptr(y), ld, ptr(stats), ptr(gamma), ptr(beta), ptr(alpha), int(relu),
+           ptr(res), 8 if res is None else res.shape[3], ptr(dz), c, ptr(dy), c, ptr(dg), ptr(db), ptr(da), ptr(ws),
+           ws.numel(), stream())
+    return dz, dy, dg, db, da
+
+
 # ---------------------------------------------------------------------------------------------- resampling
 def maxpool2_fwd(x):
     n, h, w, c = x.shape

@@ -37,6 +37,8 @@ unsigned long long crfr_launch_count(void);
  *   "norm_bwd_impl": crfr_norm_act_bwd as 0 = register-staged reduce + fold + apply kernels, 1 = persistent TMA-fed
  *                    reduce + fold + apply kernels (default where the views are TMA-addressable: channels a multiple
  *                    of 64, 16-byte aligned), -1 = default / environment CRFR_NORM_BWD=regs|stream.
+ *   "fuse_norm_bwd": crfr_conv_dgrad_norm_bwd as 0 = dgrad + crfr_norm_act_bwd, 1 = first pass of the normalisation
+ *                    backward inside the dgrad epilogue where the row-streaming pair kernel runs (default).
  *   "norm_fwd_stream": crfr_norm_act_fwd as 0 = register-staged kernel, 1 = persistent TMA-fed kernel (default where the
  *                    views are TMA-addressable); identical results bit for bit. */
 int crfr_set_option(const char* name, int value);
@@ -103,6 +105,22 @@ int crfr_norm_act_bwd(const void* dout_a, int da_ld, const void* dout_b, int db_
                       const float* stats, const float* gamma, const float* beta, const float* alpha, int relu,
                       const void* res, int res_ld, void* dz, int dz_ld, void* dy, int dy_ld, float* dgamma,
                       float* dbeta, float* dalpha, int n, int hw, int c, void* ws, size_t ws_bytes, void* stream);
+
+/* Backward of "conv(act(norm(y) (+ res)))" across the convolution's input, as one operation (ref: the
+ * InstanceNorm2d -> PReLU -> Conv2d and InstanceNorm2d -> add -> PReLU -> Conv2d chains of _Residual_Block,
+ * model/FSRnet.py:91-97):  D = dgrad(dout) (+ dx_b, a further gradient of the convolution's input from its other
+ * consumers, or NULL); then exactly crfr_norm_act_bwd on D: dz = D * act'(z) (always written: it is the gradient of
+ * `res`), dy, dgamma / dbeta / dalpha accumulated.  Same results as crfr_conv_dgrad followed by crfr_norm_act_bwd (the
+ * fp32 sums may associate differently).  For the row-streaming shapes (3x3 s1 64 -> 64 at width 128, even image
+ * count) the first pass of the normalisation backward runs inside the dgrad epilogue (option "fuse_norm_bwd", default
+ * 1): the dgrad output never reaches memory and one pass over 2-4 maps disappears; other shapes run the two calls.
+ * ws >= crfr_conv_dgrad_norm_bwd_workspace_bytes(d). */
+size_t crfr_conv_dgrad_norm_bwd_workspace_bytes(const crfr_conv_desc* d);
+int crfr_conv_dgrad_norm_bwd(int engine, const crfr_conv_desc* d, const void* dout, const void* w_packed_t, int cout_pad,
+                             const void* dx_b, int dxb_ld, const void* y, int y_ld, const float* stats,
+                             const float* gamma, const float* beta, const float* alpha, int relu, const void* res,
+                             int res_ld, void* dz, int dz_ld, void* dy, int dy_ld, float* dgamma, float* dbeta,
+                             float* dalpha, void* ws, size_t ws_bytes, void* stream);
 
 /* ref: train-mode nn.BatchNorm2d / BatchNorm1d buffer update (model/resnet.py:24,27,159,167,172):
  * running = (1-momentum)*running + momentum*batch, with the unbiased batch variance (count = N*H*W samples);
