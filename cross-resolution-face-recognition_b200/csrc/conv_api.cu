@@ -32,6 +32,7 @@ const OptDef kOpts[CRFR_OPT_COUNT] = {
     {"pair_swap", "CRFR_PAIR_SWAP", 0},       {"wgrad_stream", "CRFR_WGRAD_STREAM", 1},
     {"norm_bwd_impl", "CRFR_NORM_BWD", 1},    {"norm_fwd_stream", "CRFR_NORM_FWD_STREAM", 1},
     {"rowwgrad_pair", "CRFR_ROWWGRAD_PAIR", 1}, {"fuse_norm_bwd", "CRFR_FUSE_NORM_BWD", 1},
+    {"fuse_norm_fwd", "CRFR_FUSE_NORM_FWD", 0},
     {"pair_debug", "CRFR_PAIR_DEBUG", 0}};
 std::atomic<int> g_opt[CRFR_OPT_COUNT];
 std::atomic<int> g_opt_init{0};
@@ -178,6 +179,29 @@ extern "C" int crfr_conv_dgrad(int engine, const crfr_conv_desc* d, const void* 
                               d->cin, cout_pad, nullptr, dx, d->in_ld, nullptr, st);
   return crfr_direct_gather(1, d->n, d->oh, d->ow, d->h, d->w, d->k, d->stride, d->pad, dy, d->out_ld, w_packed_t,
                             d->cin, cout_pad, nullptr, dx, d->in_ld, nullptr, st);
+}
+
+// ---- normalisation + activation (+ residual) + convolution forward as one operation -------------------------------
+extern "C" int crfr_norm_act_conv_fwd(int engine, const crfr_conv_desc* d, const void* y, int y_ld, const float* stats,
+                                      const float* gamma, const float* beta, const float* alpha, int relu, const void* res,
+                                      int res_ld, void* act, int act_ld, const void* w_packed, int cin_pad,
+                                      const float* bias, void* out, float* out_stats, float eps, void* ws, size_t ws_bytes,
+                                      void* stream) {
+  CRFR_TRY(check_desc(d, "norm_act_conv_fwd"));
+  CRFR_CHECK_ARG(y && stats && act && w_packed && out, "norm_act_conv_fwd: null pointer");
+  CRFR_CHECK_ARG(cin_pad >= d->cin && act_ld >= cin_pad && d->in_ld == act_ld && y_ld >= d->cin,
+                 "norm_act_conv_fwd: in_ld must be the ld of the activated map");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (engine != CRFR_ENGINE_DIRECT && crfr_opt(CRFR_OPT_FUSE_NORM_FWD) && crfr_opt(CRFR_OPT_ROWCONV) &&
+      crfr_opt(CRFR_OPT_ROWCONV_PAIR) && !d->transposed && cin_pad == d->cin && crfr_lowered_recipe(d) == 0 &&
+      crfr_rowconv_supported(d->h, d->w, d->cin, d->cout, d->k, d->stride, d->pad) && crfr_rowconv_pair_supported(d->n, d->h)) {
+    crfr_rowconv_xform xf = {y, y_ld, res, res ? res_ld : 8, stats, gamma, beta, alpha, relu, act, act_ld};
+    return crfr_rowconv_pair(y, y_ld, d->n, d->h, w_packed, 0, bias, out, d->out_ld, out_stats, eps, ws, ws_bytes, st,
+                             nullptr, &xf);
+  }
+  CRFR_TRY(crfr_norm_act_fwd(y, y_ld, stats, gamma, beta, alpha, relu, res, res ? res_ld : 8, act, act_ld, d->n,
+                             d->h * d->w, d->cin, stream));
+  return crfr_conv_fwd(engine, d, act, w_packed, cin_pad, bias, out, nullptr, out_stats, eps, ws, ws_bytes, stream);
 }
 
 // ---- dgrad + backward of the normalisation that produced the convolution's input, as one operation ----------------

@@ -21,6 +21,7 @@ enum {
   CRFR_OPT_NORM_FWD_STREAM,  // TMA-fed normalisation forward
   CRFR_OPT_ROWWGRAD_PAIR,    // cta_group::2 form of the row-streaming weight gradient
   CRFR_OPT_FUSE_NORM_BWD,    // crfr_conv_dgrad_norm_bwd: first pass of the normalisation backward in the dgrad epilogue
+  CRFR_OPT_FUSE_NORM_FWD,    // crfr_norm_act_conv_fwd: normalise + activate inside the convolution's producer warps
   CRFR_OPT_PAIR_DEBUG,       // ablation bits for tools/pair_diag.py (results are WRONG when set): 1 no loads, 2 no MMAs,
                              // 4 no pack / store / statistics, 8 no store, 16 no statistics
   CRFR_OPT_COUNT
@@ -159,10 +160,18 @@ struct crfr_rowconv_fuse {
   const float* stats; const float* gamma; const float* beta; const float* alpha; int relu;
   float* partial;                 // out: [n][crfr_rowconv_pair_parts(n, h)][3][64]
 };
+// optional transform producer (forward only): the convolution's input is act(gamma * (y - mean) * rstd + beta (+ res)),
+// computed on the fly from the raw map y; out (nullable) also receives the activated map
+struct crfr_rowconv_xform {
+  const void* y; int y_ld;
+  const void* res; int res_ld;
+  const float* stats; const float* gamma; const float* beta; const float* alpha; int relu;
+  void* out; int out_ld;
+};
 int crfr_rowconv_pair_parts(int n, int h);
 int crfr_rowconv_pair(const void* src, int src_ld, int n, int h, const void* w_packed, int flip, const float* bias,
                       void* dst, int dst_ld, float* stats, float eps, void* ws, size_t ws_bytes, cudaStream_t st,
-                      const crfr_rowconv_fuse* fuse = nullptr);
+                      const crfr_rowconv_fuse* fuse = nullptr, const crfr_rowconv_xform* xf = nullptr);
 // rowwgrad.cu: persistent row-streaming weight gradient of the same shape (deterministic slab reduction)
 int crfr_rowwgrad_supported(int h, int w, int cin, int cout, int k, int stride, int pad);
 size_t crfr_rowwgrad_ws_bytes(int n, int h);

@@ -52,15 +52,23 @@ constexpr int kWeightBytes = 3 * kKxBytes;
 //   FUSE = 0: 2 groups of 8 warps; warp (quadrant q, half hf) owns 32 pixels x 32 channels: 104 registers, 113 us
 //   FUSE = 1: 3 groups of 4 warps; warp q owns 32 pixels x 64 channels: 152 registers for the extra maps and sums
 // Group g takes the output rows with orow % kGroups == g.
-template <int FUSE>
+// Kernel variants V: 0 = plain, 1 = fused dgrad epilogue (FUSE above), 2 = forward with a TRANSFORM producer: 8 warps read
+// the raw map the preceding normalisation would have read, apply out = act(gamma * (y - mean) * rstd + beta (+ res)) in
+// registers and write the activated row straight into the shared-memory ring (and, optionally, to global memory for the
+// weight gradient): the separate normalisation pass over 2-3 maps disappears.  Whole-row epilogue, 2 groups.
+template <int V>
 struct Cfg {
-  static constexpr int kGroups = FUSE ? 3 : 2;
-  static constexpr int kRowWarps = FUSE ? 4 : 8;                      // warps that share one output row
-  static constexpr int kThreads = 128 + 32 * kRowWarps * kGroups;     // 512 / 640
-  // the CTA's register pool is what the launch allocates; the epilogue's share once warpgroup 0 keeps kRegsLean per thread
+  static constexpr int kGroups = V == 1 ? 3 : 2;
+  static constexpr int kRowWarps = V == 0 ? 8 : 4;                    // warps that share one output row
+  static constexpr int kXformWarps = V == 2 ? 8 : 0;                  // two teams of 4, alternate input rows
+  static constexpr int kEpiThreads = 32 * kRowWarps * kGroups;
+  static constexpr int kThreads = 128 + kEpiThreads + 32 * kXformWarps;   // 640 / 512 / 640
+  // the CTA's register pool is what the launch allocates; the epilogue's share once the other warpgroups keep theirs
   static constexpr int kRegsLaunch = (65536 / kThreads) & ~7;
-  static constexpr int kRegsLean = FUSE ? 56 : 64;
-  static constexpr int kRegsEpi = ((kThreads * kRegsLaunch - 128 * kRegsLean) / (kThreads - 128)) & ~7;
+  static constexpr int kRegsLean = V == 1 ? 56 : 64;
+  static constexpr int kRegsXform = 96;
+  static constexpr int kRegsEpi =
+      ((kThreads * kRegsLaunch - 128 * kRegsLean - 32 * kXformWarps * kRegsXform) / kEpiThreads) & ~7;
 };
 constexpr int kMaxGroups = 3;
 constexpr int kAccSlots = 8;
@@ -89,6 +97,12 @@ struct PairParams {
   const bf16* fres; int fres_ld;      // nullable
   const float* fstats; const float* fgamma; const float* fbeta; const float* falpha; int frelu;
   float* partial3;                    // [n][parts][3][64]: sum dz, sum dz * xhat, sum D * min(z, 0)
+  // V = 2 (forward only): the input rows are produced by transform warps from the raw map of the preceding normalisation,
+  // in = act(gamma * (xy - mean) * rstd + beta (+ xres)); xout (nullable): the activated rows also go to global memory
+  const bf16* xy; int xy_ld;
+  const bf16* xres; int xres_ld;
+  const float* xstats; const float* xgamma; const float* xbeta; const float* xalpha; int xrelu;
+  bf16* xout; int xout_ld;
 };
 
 // first row (of the 320 per kx) of the half that belongs to the sub-range (first tap j0, cnt taps) of the stacked B
@@ -366,8 +380,11 @@ __device__ __forceinline__ void epilogue_half(const PairParams& p, const EpiCtx&
 // FUSE = 1 (dgrad): the first pass of the normalisation backward on the rounded dgrad output, exactly as norm_stream.cu's
 // reduce pass: D = dgrad (+ db); z = sc * y + sh (+ res); z <= 0: ad += D * z, D *= al; dz = bf16(D) is stored in place of
 // the dgrad output; as += dz; aq += dz * y.  3 groups of 4 warps; warp q owns 32 pixels x 64 channels.
-__device__ __forceinline__ void epilogue_row_fused(const PairParams& p, const EpiCtx& cx) {
-  constexpr int kGroups = Cfg<1>::kGroups;
+template <int V>
+__device__ __forceinline__ void epilogue_row(const PairParams& p, const EpiCtx& cx) {
+  constexpr int kGroups = Cfg<V>::kGroups;
+  constexpr bool FUSED = V == 1;            // else: bias, plain store, InstanceNorm statistics of the stored values
+  constexpr int NQ = FUSED ? 3 : 2;
   const int warp = cx.warp, lane = cx.lane;
   const uint32_t tmem = cx.tmem;
   const int ew = warp - 4, gi = ew >> 2;
@@ -376,10 +393,11 @@ __device__ __forceinline__ void epilogue_row_fused(const PairParams& p, const Ep
   const int cg = lane & 7;                  // after the transpose: this lane's channel chunk (channels 8 cg .. 8 cg + 7) ...
   const int pg = lane >> 3;                 // ... of pixels 32 q + 8 pg + (0..7)
   const int bar_stat = 1 + gi;
-  float* sSt = cx.sStat + gi * 768;         // [4 warps][3][64]
+  float* sSt = cx.sStat + gi * 768;         // [4 warps][NQ][64]
   const uint32_t remote_acc_empty0 = map_to_rank(&cx.acc_empty[0], 0);
-  const bool f_act = p.frelu || p.falpha != nullptr;
-  const bool f_b = p.fb != nullptr, f_res = f_act && p.fres != nullptr;
+  const bool f_act = FUSED && (p.frelu || p.falpha != nullptr);
+  const bool f_b = FUSED && p.fb != nullptr, f_res = f_act && p.fres != nullptr;
+  const bool has_bias = !FUSED && p.bias != nullptr;
   // coefficients of this lane's 8 channels for the current image (z = sc * y + sh, slope al for z <= 0); sums
   float2 sc[4], sh[4], al[4], as[4], aq[4], ad[4];
 #pragma unroll
@@ -394,6 +412,7 @@ __device__ __forceinline__ void epilogue_row_fused(const PairParams& p, const Ep
     const int n = 2 * pr + (int)cx.rank;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
+      if (!FUSED) break;
       float t[6];
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
@@ -413,7 +432,7 @@ __device__ __forceinline__ void epilogue_row_fused(const PairParams& p, const Ep
       const int g = gbase + (min(y + 1, iy1) - iy0);       // the input row whose MMAs complete this output row
       // element offset of this lane's 8 pixels of the row (pixel q * 32 + pg * 8 + i), before the per-map ld
       const long long pix0 = ((long long)n * p.h + y) * kW + (q * 32 + pg * 8);
-      {   // pull the lines the fused pass reads into L2 while this warp waits for the MMAs (lane cg: pixel cg of its 8)
+      if (FUSED) {   // pull the lines the fused pass reads into L2 while this warp waits for the MMAs (lane cg: pixel cg of its 8)
         asm volatile("prefetch.global.L2 [%0];" ::"l"(p.fy + (pix0 + cg) * p.fy_ld));
         if (f_b) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.fb + (pix0 + cg) * p.fb_ld));
         if (f_res) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.fres + (pix0 + cg) * p.fres_ld));
@@ -429,7 +448,8 @@ __device__ __forceinline__ void epilogue_row_fused(const PairParams& p, const Ep
         tmem_ld_wait();
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-          const __nv_bfloat162 lo = __floats2bfloat162_rn(__uint_as_float(v[2 * k]), __uint_as_float(v[2 * k + 1]));
+          const __nv_bfloat162 lo = __floats2bfloat162_rn(__uint_as_float(v[2 * k]) + (has_bias ? cx.sBias[2 * k] : 0.f),
+                                                          __uint_as_float(v[2 * k + 1]) + (has_bias ? cx.sBias[2 * k + 1] : 0.f));
           w[k] = *reinterpret_cast<const uint32_t*>(&lo);
         }
         tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + slot * kC + 32, v);
@@ -442,7 +462,8 @@ __device__ __forceinline__ void epilogue_row_fused(const PairParams& p, const Ep
         if (lane == 0) mbar_arrive_cluster(remote_acc_empty0 + 8u * (uint32_t)slot);
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
-          const __nv_bfloat162 hi = __floats2bfloat162_rn(__uint_as_float(v[2 * k]), __uint_as_float(v[2 * k + 1]));
+          const __nv_bfloat162 hi = __floats2bfloat162_rn(__uint_as_float(v[2 * k]) + (has_bias ? cx.sBias[32 + 2 * k] : 0.f),
+                                                          __uint_as_float(v[2 * k + 1]) + (has_bias ? cx.sBias[33 + 2 * k] : 0.f));
           w[16 + k] = *reinterpret_cast<const uint32_t*>(&hi);
         }
       }
@@ -466,6 +487,7 @@ __device__ __forceinline__ void epilogue_row_fused(const PairParams& p, const Ep
       const bf16* bp = p.fb + pix0 * p.fb_ld + cg * 8;
       const bf16* rp = p.fres + pix0 * p.fres_ld + cg * 8;
       bf16* line = p.dst + pix0 * p.dst_ld + cg * 8;
+      if (FUSED) {
 #pragma unroll
       for (int h2 = 0; h2 < 4; ++h2) {   // four quarters of 2 pixels: bounds the registers of the maps in flight
         uint4 Yv[2], Bv[2], Rv[2];
@@ -503,8 +525,25 @@ __device__ __forceinline__ void epilogue_row_fused(const PairParams& p, const Ep
           *reinterpret_cast<uint4*>(line + (long long)i * p.dst_ld) = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
         }
       }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          *reinterpret_cast<uint4*>(line + (long long)i * p.dst_ld) = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+        if (p.partial) {
+          // per-channel sums of the stored (rounded) values: this lane's 8 channels over its 8 pixels, packed fp32x2
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 f = bf2(w[4 * i + k]);
+              as[k] = __fadd2_rn(as[k], f);
+              aq[k] = __ffma2_rn(f, f, aq[k]);
+            }
+          }
+        }
+      }
     }
-    {
+    if (FUSED || p.partial) {
       // end of this CTA's rows of image n: fold the group's pixel lanes in fixed order (4 lanes by shuffle, the 4 warps
       // through shared memory) and publish the group's partial in its own slot - also when it is all zero
 #pragma unroll
@@ -513,26 +552,32 @@ __device__ __forceinline__ void epilogue_row_fused(const PairParams& p, const Ep
         for (int k = 0; k < 4; ++k) {
           as[k].x += __shfl_xor_sync(0xffffffffu, as[k].x, o);  as[k].y += __shfl_xor_sync(0xffffffffu, as[k].y, o);
           aq[k].x += __shfl_xor_sync(0xffffffffu, aq[k].x, o);  aq[k].y += __shfl_xor_sync(0xffffffffu, aq[k].y, o);
-          ad[k].x += __shfl_xor_sync(0xffffffffu, ad[k].x, o);  ad[k].y += __shfl_xor_sync(0xffffffffu, ad[k].y, o);
+          if (FUSED) { ad[k].x += __shfl_xor_sync(0xffffffffu, ad[k].x, o);  ad[k].y += __shfl_xor_sync(0xffffffffu, ad[k].y, o); }
         }
       }
       named_bar_sync(bar_stat, 128);   // previous use of the scratch is over
       if (lane < 8) {
-        float* d0 = sSt + ((ew & 3) * 3 + 0) * kC + cg * 8;
-        float* d1 = sSt + ((ew & 3) * 3 + 1) * kC + cg * 8;
-        float* d2 = sSt + ((ew & 3) * 3 + 2) * kC + cg * 8;
+        float* d0 = sSt + ((ew & 3) * NQ + 0) * kC + cg * 8;
+        float* d1 = sSt + ((ew & 3) * NQ + 1) * kC + cg * 8;
+        float* d2 = sSt + ((ew & 3) * NQ + 2) * kC + cg * 8;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           d0[2 * k] = as[k].x; d0[2 * k + 1] = as[k].y;
           d1[2 * k] = aq[k].x; d1[2 * k + 1] = aq[k].y;
-          d2[2 * k] = ad[k].x; d2[2 * k + 1] = ad[k].y;
+          if (FUSED) { d2[2 * k] = ad[k].x; d2[2 * k + 1] = ad[k].y; }
         }
       }
       named_bar_sync(bar_stat, 128);
       const int b0 = first_cluster_of_row((long long)pr * p.h, p.total_rows, cx.ncl);
       const int part = cx.cid - b0;
+      if (!FUSED) {
+        float* dst2 = p.partial + ((long long)n * p.parts + kGroups * part + gi) * 2 * kC;
+        dst2[et] = (sSt[et] + sSt[128 + et]) + (sSt[256 + et] + sSt[384 + et]);
+        if (y0 + seg == p.h && gi == 0)   // last cluster of this image: the unused slots must read as zero
+          for (int z = kGroups * (part + 1); z < p.parts; ++z) p.partial[((long long)n * p.parts + z) * 2 * kC + et] = 0.f;
+      }
       float* dst = p.partial3 + ((long long)n * p.parts + kGroups * part + gi) * 3 * kC;
-      if (et < kC) {
+      if (FUSED && et < kC) {
         float t[3];
 #pragma unroll
         for (int j = 0; j < 3; ++j)
@@ -543,7 +588,7 @@ __device__ __forceinline__ void epilogue_row_fused(const PairParams& p, const Ep
         dst[kC + et] = (t[1] - mu * t[0]) * rs;
         dst[2 * kC + et] = t[2];
       }
-      if (y0 + seg == p.h && gi == 0)   // last cluster of this image: the unused slots must read as zero
+      if (FUSED && y0 + seg == p.h && gi == 0)   // last cluster of this image: the unused slots must read as zero
         for (int z = kGroups * (part + 1); z < p.parts; ++z)
           for (int j = et; j < 3 * kC; j += 128) p.partial3[((long long)n * p.parts + z) * 3 * kC + j] = 0.f;
 #pragma unroll
@@ -551,6 +596,108 @@ __device__ __forceinline__ void epilogue_row_fused(const PairParams& p, const Ep
     }
     gbase += iy1 - iy0 + 1;
     r += seg;
+  }
+}
+
+
+// V = 2: the transform producer.  Two teams of 4 warps take alternate input rows; thread tt of a team owns the 16-byte chunk
+// cg = tt % 8 (channels 8 cg .. 8 cg + 7: its coefficients stay in registers) of pixels tt / 8 + 16 j.  A row is read with
+// ld.global (L2-resident: every thread pulls one 128-byte line of the row kXfAhead rows ahead into L2), normalised and
+// activated in registers and stored with st.shared.v4 exactly where the TMA box load of the plain kernel puts it
+// (SWIZZLE_128B: chunk index xor (row & 7); row 0 and row 129 of a slot are the zero halo, written once at start); then
+// fence.proxy.async (the tensor core reads through the async proxy) and one arrival per warp on the slot's barrier.
+constexpr int kXfAhead = 8;   // even: a team prefetches the rows it will transform itself
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint32_t uw(const uint4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
+__device__ __forceinline__ void xform_produce(const PairParams& p, uint8_t* sRing, uint64_t* full, uint64_t* done,
+                                              long long r_begin, long long r_end, uint32_t rank, int tw, int lane) {
+  const int team = tw >> 2, tt = (tw & 3) * 32 + lane;
+  const int cg = tt & 7, px0 = tt >> 3;
+  const bool act = p.xrelu || p.xalpha != nullptr, has_res = p.xres != nullptr, side = p.xout != nullptr;
+  // byte offset of this thread's chunk of pixel px0 inside a slot (+ 2048 per 16 pixels: the swizzle phase repeats)
+  const uint32_t soff = (uint32_t)((px0 + 1) * 128 + ((cg ^ ((px0 + 1) & 7)) << 4));
+  float2 sc[4], sh[4], al[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) sc[k] = sh[k] = al[k] = make_float2(0.f, 0.f);
+  int cur = -1;
+  RowWalk ld(r_begin, r_end, p.h);
+  // L2 prefetch cursor over the OUTPUT rows of the range (the input rows are the same rows +- 1), kXfAhead rows ahead
+  int ppr = (int)(r_begin / p.h), py = (int)(r_begin % p.h), pleft = (int)(r_end - r_begin);
+#define CRFR_XF_PREFETCH_STEP(mine)                                                                        \
+  if (pleft > 0) {                                                                                         \
+    if (mine) {                                                                                            \
+      const long long pl = ((long long)(2 * ppr + (int)rank) * p.h + py) * kW + tt;                        \
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p.xy + pl * p.xy_ld));                                 \
+      if (has_res) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.xres + pl * p.xres_ld));                \
+    }                                                                                                      \
+    if (++py == p.h) { py = 0; ++ppr; }                                                                    \
+    --pleft;                                                                                               \
+  }
+#pragma unroll 1
+  for (int g = 0; g < kXfAhead; ++g) { CRFR_XF_PREFETCH_STEP((g & 1) == team) }
+#pragma unroll 1
+  for (int g = 0; ld.valid; ++g, ld.next()) {
+    CRFR_XF_PREFETCH_STEP((g & 1) == team)
+    if ((g & 1) != team) continue;
+    const int s = g % kSlots;
+    const int n = 2 * ld.pr + (int)rank;
+    if (n != cur) {
+      cur = n;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float t[6];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int ch = cg * 8 + 2 * k + e;
+          const float mu = p.xstats[2 * (n * kC + ch)], rs = p.xstats[2 * (n * kC + ch) + 1];
+          t[e] = (p.xgamma ? p.xgamma[ch] : 1.f) * rs;
+          t[2 + e] = (p.xbeta ? p.xbeta[ch] : 0.f) - mu * t[e];
+          t[4 + e] = p.xrelu ? 0.f : (p.xalpha ? p.xalpha[ch] : 1.f);
+        }
+        sc[k] = make_float2(t[0], t[1]);
+        sh[k] = make_float2(t[2], t[3]);
+        al[k] = make_float2(t[4], t[5]);
+      }
+    }
+    const long long rowpix = ((long long)n * p.h + ld.iy) * kW + px0;
+    const bf16* src = p.xy + rowpix * p.xy_ld + cg * 8;
+    const bf16* rsrc = p.xres + rowpix * p.xres_ld + cg * 8;
+    bf16* osrc = p.xout + rowpix * p.xout_ld + cg * 8;
+    const uint32_t sbase = smem_u32(sRing + s * kSlotBytes) + soff;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      uint4 Y[4], R[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) Y[j] = ldg_stream(src + (long long)(16 * (4 * hh + j)) * p.xy_ld);
+      if (has_res) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) R[j] = ldg_stream(rsrc + (long long)(16 * (4 * hh + j)) * p.xres_ld);
+      }
+      if (hh == 0 && g >= kSlots) mbar_wait(&done[(g - kSlots) % kDone], ((g - kSlots) / kDone) & 1);   // slot consumed
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 O;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float2 z = __ffma2_rn(bf2(uw(Y[j], k)), sc[k], sh[k]);
+          if (has_res) z = __fadd2_rn(z, bf2(uw(R[j], k)));
+          if (act) {
+            if (!(z.x > 0.f)) z.x *= al[k].x;
+            if (!(z.y > 0.f)) z.y *= al[k].y;
+          }
+          const __nv_bfloat162 pb = __floats2bfloat162_rn(z.x, z.y);
+          const uint32_t wv = *reinterpret_cast<const uint32_t*>(&pb);
+          if (k == 0) O.x = wv; else if (k == 1) O.y = wv; else if (k == 2) O.z = wv; else O.w = wv;
+        }
+        sts128(sbase + (uint32_t)((4 * hh + j) * 2048), O);
+        if (side) *reinterpret_cast<uint4*>(osrc + (long long)(16 * (4 * hh + j)) * p.xout_ld) = O;
+      }
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&full[s]);
   }
 }
 
@@ -577,7 +724,7 @@ rowconv_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
   if (threadIdx.x == 0) {
     for (int s = 0; s < kSlots; ++s) {
-      mbar_init(&full[s], 1);
+      mbar_init(&full[s], FUSE == 2 ? 4 : 1);
       mbar_init(&peer_full[s], 1);
     }
     for (int b = 0; b < kDone; ++b) mbar_init(&done[b], 1);
@@ -589,6 +736,13 @@ rowconv_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     prefetch_tmap(&tmW);
   }
   if (threadIdx.x >= 64 && threadIdx.x < 64 + kC) sBias[threadIdx.x - 64] = p.bias ? p.bias[threadIdx.x - 64] : 0.f;
+  if (FUSE == 2) {   // zero halo pixels (rows 0 and 129) of every ring slot: the transform producer never writes them
+    for (int i = threadIdx.x; i < kSlots * 2 * 32; i += Cfg<FUSE>::kThreads) {
+      const int s = i >> 6, row = ((i >> 5) & 1) ? 129 : 0, word = i & 31;
+      *reinterpret_cast<uint32_t*>(sRing + s * kSlotBytes + row * 128 + word * 4) = 0u;
+    }
+    fence_proxy_async();
+  }
   if (warp == 1) tmem_alloc_pair(tmem_slot);
   tc_fence_before();
   __syncthreads();
@@ -632,7 +786,7 @@ rowconv_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     // this warp's lanes - made the kernel 3-6 us SLOWER once the issuing warp was no longer the bottleneck: the launch moves
     // 537 MB in ~120 us, i.e. the memory system is already at 4.4 TB/s of mixed read / write traffic.)
     RowWalk ld(r_begin, r_end, p.h);
-    for (int g = 0; ld.valid; ++g, ld.next()) {
+    for (int g = 0; FUSE != 2 && ld.valid; ++g, ld.next()) {
       const int s = g % kSlots;
       if (g >= kSlots) mbar_wait(&done[(g - kSlots) % kDone], ((g - kSlots) / kDone) & 1);   // row g - kSlots consumed
       if (leader) {
@@ -725,13 +879,18 @@ rowconv_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
       o[0] = clock64() - t_start; o[1] = c_acc; o[2] = c_full; o[3] = c_peer; o[4] = c_issue;
     }
   }
+  } else if (FUSE == 2 && warp >= 4 + Cfg<FUSE>::kEpiThreads / 32) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg<FUSE>::kRegsXform));
+    const long long r_begin = (long long)p.total_rows * cid / ncl;
+    const long long r_end = (long long)p.total_rows * (cid + 1) / ncl;
+    xform_produce(p, sRing, full, done, r_begin, r_end, rank, warp - 4 - Cfg<FUSE>::kEpiThreads / 32, lane);
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg<FUSE>::kRegsEpi));
     const long long r_begin = (long long)p.total_rows * cid / ncl;
     const long long r_end = (long long)p.total_rows * (cid + 1) / ncl;
     const EpiCtx cx = {tmem, done, acc_empty, sStat, sBias, r_begin, r_end, cid, ncl, rank, warp, lane};
-    if (FUSE) epilogue_row_fused(p, cx);
-    else epilogue_half(p, cx);
+    if (FUSE == 0) epilogue_half(p, cx);
+    else epilogue_row<FUSE>(p, cx);
   }
   tc_fence_before();
   __syncthreads();
@@ -772,7 +931,7 @@ int crfr_rowconv_pair_parts(int n, int h) { return crfr_rowconv_pair_supported(n
 // first pass to fuse->partial ([n][crfr_rowconv_pair_parts(n, h)][3][64] floats, to be folded by bwd_fold_kernel).
 int crfr_rowconv_pair(const void* src, int src_ld, int n, int h, const void* w_packed, int flip, const float* bias,
                       void* dst, int dst_ld, float* stats, float eps, void* ws, size_t ws_bytes, cudaStream_t st,
-                      const crfr_rowconv_fuse* fuse) {
+                      const crfr_rowconv_fuse* fuse, const crfr_rowconv_xform* xf) {
   CRFR_CHECK_ARG(crfr_rowconv_pair_supported(n, h), "rowconv_pair: needs an even number of images");
   CRFR_CHECK_ARG(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0 && ((uintptr_t)w_packed & 15) == 0 &&
                      (src_ld & 7) == 0 && (dst_ld & 7) == 0,
@@ -782,6 +941,14 @@ int crfr_rowconv_pair(const void* src, int src_ld, int n, int h, const void* w_p
     CRFR_CHECK_ARG(((uintptr_t)fuse->y & 15) == 0 && ((uintptr_t)fuse->db & 15) == 0 && ((uintptr_t)fuse->res & 15) == 0 &&
                        ((fuse->y_ld | fuse->db_ld | fuse->res_ld) & 7) == 0,
                    "rowconv_pair: fused maps must be 16B aligned and ld a multiple of 8");
+  }
+  if (xf) {   // transform producer: src is not read (the rows come from xf->y), the activation map describes xf->y instead
+    CRFR_CHECK_ARG(!flip && !fuse && xf->y && xf->stats, "rowconv_pair: transform producer needs forward, y, stats");
+    CRFR_CHECK_ARG(((uintptr_t)xf->y & 15) == 0 && ((uintptr_t)xf->res & 15) == 0 && ((uintptr_t)xf->out & 15) == 0 &&
+                       ((xf->y_ld | xf->res_ld | xf->out_ld) & 7) == 0,
+                   "rowconv_pair: transform maps must be 16B aligned and ld a multiple of 8");
+    src = xf->y;
+    src_ld = xf->y_ld;
   }
   CUtensorMap tmX, tmW;
   {
@@ -796,9 +963,10 @@ int crfr_rowconv_pair(const void* src, int src_ld, int n, int h, const void* w_p
     unsigned int box[2] = {64, 32};
     CRFR_TRY(crfr_tmap_encode_bf16(&tmW, w_packed, 2, dims, strides, box, "weights"));
   }
-  static std::atomic<unsigned long long> attr0{0}, attr1{0};
+  static std::atomic<unsigned long long> attr0{0}, attr1{0}, attr2{0};
   CRFR_CUDA((cudaError_t)crfr_smem_attr(rowconv_pair_kernel<0>, kSmemBytes, attr0));
   CRFR_CUDA((cudaError_t)crfr_smem_attr(rowconv_pair_kernel<1>, kSmemBytes, attr1));
+  CRFR_CUDA((cudaError_t)crfr_smem_attr(rowconv_pair_kernel<2>, kSmemBytes, attr2));
   PairParams p = {};
   p.n = n; p.h = h; p.total_rows = (n / 2) * h; p.flip = flip;
   p.swap_halves = crfr_opt(CRFR_OPT_PAIR_SWAP);
@@ -826,6 +994,12 @@ int crfr_rowconv_pair(const void* src, int src_ld, int n, int h, const void* w_p
     p.partial3 = fuse->partial;
     p.parts = parts_for(n / 2, h, Cfg<1>::kGroups);
     rowconv_pair_kernel<1><<<2 * clusters_for(p.total_rows), Cfg<1>::kThreads, kSmemBytes, st>>>(tmX, tmW, p);
+  } else if (xf) {
+    p.xy = (const bf16*)xf->y; p.xy_ld = xf->y_ld;
+    p.xres = (const bf16*)xf->res; p.xres_ld = xf->res_ld;
+    p.xstats = xf->stats; p.xgamma = xf->gamma; p.xbeta = xf->beta; p.xalpha = xf->alpha; p.xrelu = xf->relu;
+    p.xout = (bf16*)xf->out; p.xout_ld = xf->out_ld;
+    rowconv_pair_kernel<2><<<2 * clusters_for(p.total_rows), Cfg<2>::kThreads, kSmemBytes, st>>>(tmX, tmW, p);
   } else {
     rowconv_pair_kernel<0><<<2 * clusters_for(p.total_rows), Cfg<0>::kThreads, kSmemBytes, st>>>(tmX, tmW, p);
   }

@@ -194,6 +194,23 @@ def norm_act_bwd(dout, y, stats, gamma=None, beta=None, alpha=None, relu=False, 
     return dz, dy, dg, db, da
 
 
+def norm_act_conv_fwd(y, stats, w_packed, cin, cout, k, stride, pad, gamma=None, beta=None, alpha=None, relu=False, res=None,
+                      bias=None, want_stats=True, engine=L.ENGINE_AUTO):
+    """act = norm_act_fwd(y, ...); out = conv_fwd(act) as one call (crfr_norm_act_conv_fwd).  Returns (act, out, out_stats)."""
+    _need_cuda(y, stats, w_packed)
+    n, h, w, ld = y.shape
+    oh, ow = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+    d = L.ConvDesc(n, h, w, cin, cout, k, stride, pad, oh, ow, cin, cout, 0)
+    act = torch.empty((n, h, w, cin), dtype=torch.bfloat16, device=y.device)
+    out = torch.empty((n, oh, ow, cout), dtype=torch.bfloat16, device=y.device)
+    st = torch.empty((n, cout, 2), dtype=torch.float32, device=y.device) if want_stats else None
+    ws = workspace(L.lib().crfr_conv_workspace_bytes(C.byref(d)))
+    L.call("crfr_norm_act_conv_fwd", engine, C.byref(d), ptr(y), ld, ptr(stats), ptr(gamma), ptr(beta), ptr(alpha), int(relu),
+           ptr(res), 8 if res is None else res.shape[3], ptr(act), cin, ptr(w_packed), cin, ptr(bias), ptr(out), ptr(st),
+           1e-5, ptr(ws), ws.numel(), stream())
+    return act, out, st
+
+
 def conv_dgrad_norm_bwd(dout, w_packed_t, y, stats, cin, cout, k, stride, pad, gamma=None, beta=None, alpha=None,
                         relu=False, res=None, dx_b=None, engine=L.ENGINE_AUTO):
     """Backward across `conv(act(norm(y) (+ res)))`: dgrad of the convolution + the normalisation backward in one call
