@@ -756,6 +756,9 @@ rowconv_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   __syncthreads();
   cluster_sync_all();   // barriers initialised and TMEM zeroed in BOTH CTAs before any remote arrive / pair MMA
   tc_fence_after();
+  pdl_trigger();
+  pdl_wait();           // the prologue above overlapped the previous kernel's tail; from here on its output is read
+                        // (a launch with a bias, which the prologue stages, does not use the attribute)
 
   // contiguous range of flattened (image pair, row) rows for this cluster; this CTA works on image 2 * pair + rank.
   // (Computed after setmaxnreg in each branch: what is live across it is spilled to local memory and reloaded in the loops.)
@@ -993,15 +996,15 @@ int crfr_rowconv_pair(const void* src, int src_ld, int n, int h, const void* w_p
     p.fstats = fuse->stats; p.fgamma = fuse->gamma; p.fbeta = fuse->beta; p.falpha = fuse->alpha; p.frelu = fuse->relu;
     p.partial3 = fuse->partial;
     p.parts = parts_for(n / 2, h, Cfg<1>::kGroups);
-    rowconv_pair_kernel<1><<<2 * clusters_for(p.total_rows), Cfg<1>::kThreads, kSmemBytes, st>>>(tmX, tmW, p);
+    CRFR_CUDA(crfr_launch_pdl(rowconv_pair_kernel<1>, dim3(2 * clusters_for(p.total_rows)), dim3(Cfg<1>::kThreads), kSmemBytes, st, tmX, tmW, p));
   } else if (xf) {
     p.xy = (const bf16*)xf->y; p.xy_ld = xf->y_ld;
     p.xres = (const bf16*)xf->res; p.xres_ld = xf->res_ld;
     p.xstats = xf->stats; p.xgamma = xf->gamma; p.xbeta = xf->beta; p.xalpha = xf->alpha; p.xrelu = xf->relu;
     p.xout = (bf16*)xf->out; p.xout_ld = xf->out_ld;
-    rowconv_pair_kernel<2><<<2 * clusters_for(p.total_rows), Cfg<2>::kThreads, kSmemBytes, st>>>(tmX, tmW, p);
+    CRFR_CUDA(crfr_launch_pdl_if(bias == nullptr, rowconv_pair_kernel<2>, dim3(2 * clusters_for(p.total_rows)), dim3(Cfg<2>::kThreads), kSmemBytes, st, tmX, tmW, p));
   } else {
-    rowconv_pair_kernel<0><<<2 * clusters_for(p.total_rows), Cfg<0>::kThreads, kSmemBytes, st>>>(tmX, tmW, p);
+    CRFR_CUDA(crfr_launch_pdl_if(bias == nullptr, rowconv_pair_kernel<0>, dim3(2 * clusters_for(p.total_rows)), dim3(Cfg<0>::kThreads), kSmemBytes, st, tmX, tmW, p));
   }
   CRFR_COUNT_LAUNCH();
   CRFR_LAUNCH_CHECK();

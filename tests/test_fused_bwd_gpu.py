@@ -66,7 +66,7 @@ def test_fused_dgrad_norm_bwd(cuda, n, h, res, second):
     o.backward(dout, retain_graph=True)
     if second:
         x.backward(dxb)
-    assert rel_err(to_nchw(dy1), yr.grad) < 2e-2
+    assert rel_err(to_nchw(dy1), yr.grad) < 1e-2          # three bf16 roundings (dgrad output, dz, dy)
     if res:
         assert rel_err(to_nchw(dz1), rr.grad) < 1e-2
     assert rel_err(dg1, gr.grad) < 1e-2 and rel_err(db1, br.grad) < 1e-2 and rel_err(da1, ar.grad) < 1e-2

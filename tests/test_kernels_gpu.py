@@ -228,7 +228,8 @@ def test_instance_norm_prelu_add(cuda, c, h, affine, act, res):
     assert rel_err(to_nchw(out), out_ref) < BF16_TOL
     dz, dy, dg, db, da = ops.norm_act_bwd(nhwc_from(dout), yg, stats, cu(gamma), cu(beta), cu(alpha),
                                           res=None if r is None else nhwc_from(r), dout_b=nhwc_from(dout2))
-    assert rel_err(to_nchw(dy), yr.grad) < 2e-2          # two bf16 roundings (dz, dy) on a cancelling expression
+    # two bf16 roundings (dz, dy): measured 1.7e-3 .. 2.5e-3 on B200 (tools/norm_bwd_error_probe.py); north_star bound 1e-2
+    assert rel_err(to_nchw(dy), yr.grad) < 6e-3
     if res:
         assert rel_err(to_nchw(dz), rr.grad) < BF16_TOL
     if affine:
@@ -274,10 +275,10 @@ def test_instance_norm_bwd_implementations(cuda, n, c, h, res, two):
         ops.set_option("norm_bwd_impl", -1)
     for mode in (0, 1):
         dz, dy, dg, db, da = results[mode]
-        assert rel_err(to_nchw(dy), yr.grad) < 2e-2
+        assert rel_err(to_nchw(dy), yr.grad) < 6e-3          # measured <= 2.5e-3 (tools/norm_bwd_error_probe.py)
         if res:
             assert rel_err(to_nchw(dz), rr.grad) < BF16_TOL
-        assert rel_err(dg, gr.grad) < 1e-2 and rel_err(db, br.grad) < 1e-2 and rel_err(da, ar.grad) < 1e-2
+        assert rel_err(dg, gr.grad) < 5e-3 and rel_err(db, br.grad) < 5e-3 and rel_err(da, ar.grad) < 1e-4
     # same per-element arithmetic up to the association of the fp32 sums: dz identical, dy within one bf16 ulp
     if results[0][0] is not None:
         assert torch.equal(results[0][0], results[1][0])
@@ -377,7 +378,7 @@ def test_batch_norm_relu_mode(cuda):
     out = ops.norm_act_fwd(yg, stats, gamma.cuda(), beta.cuda(), relu=True, batch_norm=True)
     assert rel_err(to_nchw(out), out_ref) < BF16_TOL
     dz, dy, dg, db, _ = ops.norm_act_bwd(nhwc_from(dout), yg, stats, gamma.cuda(), beta.cuda(), relu=True, batch_norm=True)
-    assert rel_err(to_nchw(dy), yr.grad) < 2e-2
+    assert rel_err(to_nchw(dy), yr.grad) < 1e-2
     assert rel_err(dg, gr.grad) < 1e-2 and rel_err(db, br.grad) < 1e-2
 
 
@@ -401,7 +402,7 @@ def test_batch_norm_bwd_wide_channels(cuda, n, c, h):
             ops.set_option("norm_bwd_impl", mode)
             dz, dy, dg, db, _ = ops.norm_act_bwd(nhwc_from(dout), yg, stats, gamma.cuda(), beta.cuda(), relu=True,
                                                  res=nhwc_from(r), batch_norm=True)
-            assert rel_err(to_nchw(dy), yr.grad) < 2e-2, mode
+            assert rel_err(to_nchw(dy), yr.grad) < 1e-2, mode
             assert rel_err(to_nchw(dz), rr.grad) < BF16_TOL, mode
             assert rel_err(dg, gr.grad) < 1e-2 and rel_err(db, br.grad) < 1e-2, mode
     finally:

@@ -231,3 +231,43 @@ def test_rowconv_pair_kernel_is_bit_identical(cuda, n, h):
     assert rel_err(to_nchw(res[1][0]), ref) < BF16_TOL
     assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][2], res[1][2])
     assert rel_err(res[1][1], res[0][1]) < 1e-5
+
+
+def test_matcher_full_scale_probe_subset(cuda):
+    """BASELINE.json configs[3] at full size (10 000 probes x 1 000 000 x 512 gallery, top-5): the scores and indices of a
+    probe subset against an fp32 evaluation of the same bf16 vectors chunked over the gallery (utils/eval.py:11: p @ g.T,
+    topk).  A random gallery has near-ties at 1e-6, where the fp32 summation order decides: an index may differ from the
+    checker's only where the two scores agree to 2e-6; rank 1 (the planted identity, separated by ~0.5) must be exact."""
+    from crfr_b200 import ops
+    P, G, D, K, SUB = 10000, 1000000, 512, 5, 192
+    g = torch.Generator(device="cuda").manual_seed(11)
+    gal = torch.randn(G, D, generator=g, device="cuda")
+    ids = torch.randint(0, G, (P,), generator=g, device="cuda")
+    pr = gal[ids] + 0.6 * torch.randn(P, D, generator=g, device="cuda")
+    gb, pb = ops.l2norm_bf16(gal), ops.l2norm_bf16(pr)
+    del gal, pr
+    val, idx = ops.cosine_topk(pb, gb, K)
+    torch.cuda.synchronize()
+    sel = torch.linspace(0, P - 1, SUB, device="cuda").long()
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        q = pb[sel].float()
+        best_v = torch.full((SUB, K), -2.0, device="cuda")
+        best_i = torch.full((SUB, K), -1, dtype=torch.long, device="cuda")
+        for lo in range(0, G, 125000):
+            s = q @ gb[lo:lo + 125000].float().T
+            v, i = s.topk(K, dim=1)
+            cv, ci = torch.cat([best_v, v], 1), torch.cat([best_i, i + lo], 1)
+            o = cv.argsort(dim=1, descending=True, stable=True)[:, :K]
+            best_v, best_i = cv.gather(1, o), ci.gather(1, o)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    ours_v, ours_i = val[sel], idx[sel].long()
+    assert torch.equal(ours_i[:, 0], ids[sel]) and torch.equal(best_i[:, 0], ids[sel])
+    assert (ours_v - best_v).abs().max().item() < 2e-6
+    diff = ours_i != best_i
+    assert not diff[:, 0].any()
+    # a differing index must be a near-tie: our score for it equals the checker's score at that rank to 2e-6
+    assert ((ours_v - best_v).abs()[diff] < 2e-6).all()
+    assert diff.float().mean().item() < 0.02
