@@ -241,7 +241,7 @@ extern "C" int crfr_conv_dgrad_norm_bwd(int engine, const crfr_conv_desc* d, con
   cudaStream_t st = (cudaStream_t)stream;
   const int n = d->n, hw = d->h * d->w, c = d->cin;
   if (dgrad_norm_fusable(engine, d, cout_pad)) {
-    const int parts = crfr_rowconv_pair_parts(n, d->h);
+    const int parts = crfr_rowconv_pair_parts(n, d->h, !dx_b && !res);
     float* partial = (float*)ws;
     float* bstats = partial + (size_t)n * parts * 3 * c;
     float* tot = bstats + (size_t)n * c * 2;

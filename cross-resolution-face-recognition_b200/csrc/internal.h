@@ -159,7 +159,7 @@ struct crfr_rowconv_fuse {
   const void* db; int db_ld;      // second gradient of the normalised tensor, or NULL
   const void* res; int res_ld;    // residual input of the normalisation, or NULL
   const float* stats; const float* gamma; const float* beta; const float* alpha; int relu;
-  float* partial;                 // out: [n][crfr_rowconv_pair_parts(n, h)][3][64]
+  float* partial;                 // out: [n][crfr_rowconv_pair_parts(n, h, !db && !res)][3][64]
 };
 // optional transform producer (forward only): the convolution's input is act(gamma * (y - mean) * rstd + beta (+ res)),
 // computed on the fly from the raw map y; out (nullable) also receives the activated map
@@ -169,7 +169,7 @@ struct crfr_rowconv_xform {
   const float* stats; const float* gamma; const float* beta; const float* alpha; int relu;
   void* out; int out_ld;
 };
-int crfr_rowconv_pair_parts(int n, int h);
+int crfr_rowconv_pair_parts(int n, int h, int plain = 0);   // partial slots per image of the fused pass (plain: no db / res)
 int crfr_rowconv_pair(const void* src, int src_ld, int n, int h, const void* w_packed, int flip, const float* bias,
                       void* dst, int dst_ld, float* stats, float eps, void* ws, size_t ws_bytes, cudaStream_t st,
                       const crfr_rowconv_fuse* fuse = nullptr, const crfr_rowconv_xform* xf = nullptr);

@@ -52,14 +52,15 @@ constexpr int kWeightBytes = 3 * kKxBytes;
 //   FUSE = 0: 2 groups of 8 warps; warp (quadrant q, half hf) owns 32 pixels x 32 channels: 104 registers, 113 us
 //   FUSE = 1: 3 groups of 4 warps; warp q owns 32 pixels x 64 channels: 152 registers for the extra maps and sums
 // Group g takes the output rows with orow % kGroups == g.
-// Kernel variants V: 0 = plain, 1 = fused dgrad epilogue (FUSE above), 2 = forward with a TRANSFORM producer: 8 warps read
+// Kernel variants V: 0 = plain, 1 = fused dgrad epilogue (FUSE above; 3 = the same for a normalisation without residual and
+// without a second gradient, whose epilogue fits the 16-warp half-row layout), 2 = forward with a TRANSFORM producer: 8 warps read
 // the raw map the preceding normalisation would have read, apply out = act(gamma * (y - mean) * rstd + beta (+ res)) in
 // registers and write the activated row straight into the shared-memory ring (and, optionally, to global memory for the
 // weight gradient): the separate normalisation pass over 2-3 maps disappears.  Whole-row epilogue, 2 groups.
 template <int V>
 struct Cfg {
   static constexpr int kGroups = V == 1 ? 3 : 2;
-  static constexpr int kRowWarps = V == 0 ? 8 : 4;                    // warps that share one output row
+  static constexpr int kRowWarps = (V == 0 || V == 3) ? 8 : 4;        // warps that share one output row
   static constexpr int kXformWarps = V == 2 ? 8 : 0;                  // two teams of 4, alternate input rows
   static constexpr int kEpiThreads = 32 * kRowWarps * kGroups;
   static constexpr int kThreads = 128 + kEpiThreads + 32 * kXformWarps;   // 640 / 512 / 640
@@ -201,6 +202,8 @@ __device__ __forceinline__ uint4 ldg_stream(const bf16* p) {
   return v;
 }
 
+__device__ __forceinline__ uint32_t uw(const uint4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
+
 // 12 pair MMAs of one input row into one destination window: 3 kx shifts x 4 K steps.  The descriptors differ only in
 // their low word (start address), so the issue loop is two 32-bit adds and one UTCHMMA per MMA: the issuing warp is the
 // one serial resource of the kernel (230 instructions per row in the first version = 1 300 of 2 200 cycles per row).
@@ -242,8 +245,10 @@ struct EpiCtx {
 
 // FUSE = 0: forward / dgrad, optional InstanceNorm statistics of the stored values.  2 groups of 8 warps; warp
 // (quadrant q, half hf) owns the 32 pixels of TMEM lane quadrant q and 32 of the 64 channels.
+template <bool FP>   // FP: fused first pass of the normalisation backward, plain form (no second gradient, no residual)
 __device__ __forceinline__ void epilogue_half(const PairParams& p, const EpiCtx& cx) {
   constexpr int kGroups = Cfg<0>::kGroups;
+  constexpr int NQ = FP ? 3 : 2;
   const int warp = cx.warp, lane = cx.lane, cid = cx.cid, ncl = cx.ncl;
   const uint32_t tmem = cx.tmem, rank = cx.rank;
   const int ew = warp - 4, gi = ew >> 3, hf = (ew >> 2) & 1;
@@ -254,11 +259,16 @@ __device__ __forceinline__ void epilogue_half(const PairParams& p, const EpiCtx&
   const int ch0 = hf * 32 + cg * 8;
   const bool has_bias = p.bias != nullptr;
   const int bar_stat = 1 + gi;
-  float* sSt = cx.sStat + gi * 768;         // [4 quadrants][2][64]
+  float* sSt = cx.sStat + gi * 768;         // [4 quadrants][NQ][64]
   const uint32_t remote_acc_empty0 = map_to_rank(&cx.acc_empty[0], 0);   // rank 0's barrier array (own one for rank 0)
   float2 as[4], aq[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) as[k] = aq[k] = make_float2(0.f, 0.f);
+  // FP: coefficients of this lane's 8 channels for the current image (z = sc * y + sh, slope al for z <= 0), third sum
+  float2 sc[4], sh[4], al[4], ad[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) sc[k] = sh[k] = al[k] = ad[k] = make_float2(0.f, 0.f);
+  const bool f_act = FP && (p.frelu || p.falpha != nullptr);
   const bool prof = CRFR_PAIR_PROF && (p.dbg & 32) != 0 && rank == 0 && ew == 0;
   long long e_wait = 0, e_tmem = 0, e_pack = 0, e_stat = 0, e_start = clock64(), t0 = 0;
   int orow = 0;
@@ -269,12 +279,30 @@ __device__ __forceinline__ void epilogue_half(const PairParams& p, const EpiCtx&
     const int seg = (int)min((long long)(p.h - y0), cx.r_end - r);
     const int iy0 = max(y0 - 1, 0), iy1 = min(y0 + seg, p.h - 1);
     const int n = 2 * pr + (int)rank;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (!FP) break;
+      float t[6];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int ch = ch0 + 2 * k + e;
+        const float mu = p.fstats[2 * (n * kC + ch)], rs = p.fstats[2 * (n * kC + ch) + 1];
+        t[e] = (p.fgamma ? p.fgamma[ch] : 1.f) * rs;
+        t[2 + e] = (p.fbeta ? p.fbeta[ch] : 0.f) - mu * t[e];
+        t[4 + e] = p.frelu ? 0.f : (p.falpha ? p.falpha[ch] : 1.f);
+      }
+      sc[k] = make_float2(t[0], t[1]);
+      sh[k] = make_float2(t[2], t[3]);
+      al[k] = make_float2(t[4], t[5]);
+    }
     for (int y = y0; y < y0 + seg; ++y, ++orow) {
       if (orow % kGroups != gi) continue;
       const int slot = orow & (kAccSlots - 1);
       const int g = gbase + (min(y + 1, iy1) - iy0);       // the input row whose MMAs complete this output row
       // this lane's 4 pixels of the row: pixel q * 32 + pg * 4 + i, channels ch0 .. ch0 + 7
       const long long pix0 = ((long long)n * p.h + y) * kW + (q * 32 + pg * 4);
+      if (FP && hf == 0)   // pull the lines of y this row reads into L2 while the warp waits for the MMAs
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.fy + (((long long)n * p.h + y) * kW + (q * 32 + lane)) * p.fy_ld));
       if (prof) t0 = clock64();
       mbar_wait(&cx.done[g & (kDone - 1)], (g / kDone) & 1);
       if (prof) { const long long t1 = clock64(); e_wait += t1 - t0; t0 = t1; }
@@ -299,6 +327,12 @@ __device__ __forceinline__ void epilogue_half(const PairParams& p, const EpiCtx&
                                   __uint_as_float(v[2 * k + 1]) + (has_bias ? cx.sBias[hf * 32 + 2 * k + 1] : 0.f));
         w[k] = *reinterpret_cast<const uint32_t*>(&lo);
       }
+      uint4 Y[4];
+      if (FP) {   // issued here (the accumulator registers are free again): the transpose below hides their L2 latency
+        const bf16* yp = p.fy + pix0 * p.fy_ld + ch0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) Y[i] = ldg_stream(yp + (long long)i * p.fy_ld);
+      }
       // 4 x 4 chunk transpose inside each group of 4 lanes: afterwards w[4 i .. 4 i + 3] = chunk cg of pixel 4 pg + i
 #pragma unroll
       for (int s = 2; s >= 1; s >>= 1) {
@@ -315,6 +349,29 @@ __device__ __forceinline__ void epilogue_half(const PairParams& p, const EpiCtx&
           }
         }
       }
+      if (FP) {
+        // first pass of the normalisation backward on the rounded gradient, exactly as norm_stream.cu's reduce pass:
+        // z = sc * y + sh; z <= 0: ad += D * z, D *= al; dz = bf16(D) replaces the dgrad output; as += dz; aq += dz * y
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float2 gd = bf2(w[4 * i + k]);
+            const float2 f = bf2(uw(Y[i], k));
+            if (f_act) {
+              const float2 z = __ffma2_rn(f, sc[k], sh[k]);
+              if (!(z.x > 0.f)) { ad[k].x = fmaf(gd.x, z.x, ad[k].x); gd.x *= al[k].x; }
+              if (!(z.y > 0.f)) { ad[k].y = fmaf(gd.y, z.y, ad[k].y); gd.y *= al[k].y; }
+            }
+            const __nv_bfloat162 pb = __floats2bfloat162_rn(gd.x, gd.y);
+            const uint32_t wd = *reinterpret_cast<const uint32_t*>(&pb);
+            w[4 * i + k] = wd;
+            const float2 d = bf2(wd);
+            as[k] = __fadd2_rn(as[k], d);
+            aq[k] = __ffma2_rn(d, f, aq[k]);
+          }
+        }
+      }
       if (!(p.dbg & 8)) {
         bf16* line = p.dst + pix0 * p.dst_ld + ch0;
 #pragma unroll
@@ -322,7 +379,7 @@ __device__ __forceinline__ void epilogue_half(const PairParams& p, const EpiCtx&
           *reinterpret_cast<uint4*>(line + (long long)i * p.dst_ld) = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
       }
       if (prof) { const long long t1 = clock64(); e_pack += t1 - t0; t0 = t1; }
-      if (p.partial && !(p.dbg & 16)) {
+      if (!FP && p.partial && !(p.dbg & 16)) {
         // per-channel sums of the stored (rounded) values: this lane's 8 channels over its 4 pixels, packed fp32x2
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -336,7 +393,7 @@ __device__ __forceinline__ void epilogue_half(const PairParams& p, const EpiCtx&
       }
       if (prof) e_stat += clock64() - t0;
     }
-    if (p.partial) {
+    if (FP || p.partial) {
       // end of this CTA's rows of image n: fold the group's pixel lanes in fixed order (8 lanes by shuffle, the 4
       // quadrant warps through shared memory) and publish the group's partial in its own slot - also when it is all zero
 #pragma unroll
@@ -345,28 +402,49 @@ __device__ __forceinline__ void epilogue_half(const PairParams& p, const EpiCtx&
         for (int k = 0; k < 4; ++k) {
           as[k].x += __shfl_xor_sync(0xffffffffu, as[k].x, o);  as[k].y += __shfl_xor_sync(0xffffffffu, as[k].y, o);
           aq[k].x += __shfl_xor_sync(0xffffffffu, aq[k].x, o);  aq[k].y += __shfl_xor_sync(0xffffffffu, aq[k].y, o);
+          if (FP) { ad[k].x += __shfl_xor_sync(0xffffffffu, ad[k].x, o);  ad[k].y += __shfl_xor_sync(0xffffffffu, ad[k].y, o); }
         }
       }
       named_bar_sync(bar_stat, 256);   // previous use of the scratch is over
       if (lane < 4) {
-        float* d0 = sSt + (q * 2 + 0) * kC + ch0;
-        float* d1 = sSt + (q * 2 + 1) * kC + ch0;
+        float* d0 = sSt + (q * NQ + 0) * kC + ch0;
+        float* d1 = sSt + (q * NQ + 1) * kC + ch0;
+        float* d2 = sSt + (q * NQ + 2) * kC + ch0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           d0[2 * k] = as[k].x; d0[2 * k + 1] = as[k].y;
           d1[2 * k] = aq[k].x; d1[2 * k + 1] = aq[k].y;
+          if (FP) { d2[2 * k] = ad[k].x; d2[2 * k + 1] = ad[k].y; }
         }
       }
       named_bar_sync(bar_stat, 256);
       const int b0 = first_cluster_of_row((long long)pr * p.h, p.total_rows, ncl);
       const int part = cid - b0;
-      float* dst = p.partial + ((long long)n * p.parts + kGroups * part + gi) * 2 * kC;
-      if (et < 2 * kC) dst[et] = (sSt[et] + sSt[128 + et]) + (sSt[256 + et] + sSt[384 + et]);
-      if (y0 + seg == p.h && gi == 0)   // last cluster of this image: the unused slots must read as zero
-        for (int z = kGroups * (part + 1); z < p.parts; ++z)
-          if (et < 2 * kC) p.partial[((long long)n * p.parts + z) * 2 * kC + et] = 0.f;
+      if (FP) {
+        float* dst = p.partial3 + ((long long)n * p.parts + kGroups * part + gi) * 3 * kC;
+        if (et < kC) {
+          float t[3];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) as[k] = aq[k] = make_float2(0.f, 0.f);
+          for (int j = 0; j < 3; ++j)
+            t[j] = (sSt[j * kC + et] + sSt[(3 + j) * kC + et]) + (sSt[(6 + j) * kC + et] + sSt[(9 + j) * kC + et]);
+          // centre and scale: sum(dz * xhat) = rstd * (sum(dz * y) - mean * sum(dz))
+          const float mu = p.fstats[2 * (n * kC + et)], rs = p.fstats[2 * (n * kC + et) + 1];
+          dst[et] = t[0];
+          dst[kC + et] = (t[1] - mu * t[0]) * rs;
+          dst[2 * kC + et] = t[2];
+        }
+        if (y0 + seg == p.h && gi == 0)   // last cluster of this image: the unused slots must read as zero
+          for (int z = kGroups * (part + 1); z < p.parts; ++z)
+            for (int j = et; j < 3 * kC; j += 256) p.partial3[((long long)n * p.parts + z) * 3 * kC + j] = 0.f;
+      } else {
+        float* dst = p.partial + ((long long)n * p.parts + kGroups * part + gi) * 2 * kC;
+        if (et < 2 * kC) dst[et] = (sSt[et] + sSt[128 + et]) + (sSt[256 + et] + sSt[384 + et]);
+        if (y0 + seg == p.h && gi == 0)   // last cluster of this image: the unused slots must read as zero
+          for (int z = kGroups * (part + 1); z < p.parts; ++z)
+            if (et < 2 * kC) p.partial[((long long)n * p.parts + z) * 2 * kC + et] = 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) as[k] = aq[k] = ad[k] = make_float2(0.f, 0.f);
     }
     gbase += iy1 - iy0 + 1;
     r += seg;
@@ -610,7 +688,6 @@ constexpr int kXfAhead = 8;   // even: a team prefetches the rows it will transf
 __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
-__device__ __forceinline__ uint32_t uw(const uint4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
 __device__ __forceinline__ void xform_produce(const PairParams& p, uint8_t* sRing, uint64_t* full, uint64_t* done,
                                               long long r_begin, long long r_end, uint32_t rank, int tw, int lane) {
   const int team = tw >> 2, tt = (tw & 3) * 32 + lane;
@@ -892,7 +969,7 @@ rowconv_pair_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
     const long long r_begin = (long long)p.total_rows * cid / ncl;
     const long long r_end = (long long)p.total_rows * (cid + 1) / ncl;
     const EpiCtx cx = {tmem, done, acc_empty, sStat, sBias, r_begin, r_end, cid, ncl, rank, warp, lane};
-    if (FUSE == 0) epilogue_half(p, cx);
+    if (FUSE == 0 || FUSE == 3) epilogue_half<FUSE == 3>(p, cx);
     else epilogue_row<FUSE>(p, cx);
   }
   tc_fence_before();
@@ -927,7 +1004,9 @@ size_t crfr_rowconv_pair_ws_bytes(int n, int h) {
   return sizeof(float) * (size_t)n * parts_for(n / 2, h, Cfg<0>::kGroups) * 2 * kC + 256;
 }
 
-int crfr_rowconv_pair_parts(int n, int h) { return crfr_rowconv_pair_supported(n, h) ? parts_for(n / 2, h, Cfg<1>::kGroups) : 0; }
+int crfr_rowconv_pair_parts(int n, int h, int plain) {
+  return crfr_rowconv_pair_supported(n, h) ? parts_for(n / 2, h, plain ? Cfg<3>::kGroups : Cfg<1>::kGroups) : 0;
+}
 
 // Same contract as crfr_rowconv (rowconv.cu); n must be even.  fuse (dgrad only, see PairParams): the epilogue stores
 // dz = (dgrad (+ db)) * act'(z) instead of the dgrad output and writes the partial sums of the normalisation backward's
@@ -966,7 +1045,8 @@ int crfr_rowconv_pair(const void* src, int src_ld, int n, int h, const void* w_p
     unsigned int box[2] = {64, 32};
     CRFR_TRY(crfr_tmap_encode_bf16(&tmW, w_packed, 2, dims, strides, box, "weights"));
   }
-  static std::atomic<unsigned long long> attr0{0}, attr1{0}, attr2{0};
+  static std::atomic<unsigned long long> attr0{0}, attr1{0}, attr2{0}, attr3{0};
+  CRFR_CUDA((cudaError_t)crfr_smem_attr(rowconv_pair_kernel<3>, kSmemBytes, attr3));
   CRFR_CUDA((cudaError_t)crfr_smem_attr(rowconv_pair_kernel<0>, kSmemBytes, attr0));
   CRFR_CUDA((cudaError_t)crfr_smem_attr(rowconv_pair_kernel<1>, kSmemBytes, attr1));
   CRFR_CUDA((cudaError_t)crfr_smem_attr(rowconv_pair_kernel<2>, kSmemBytes, attr2));
@@ -995,8 +1075,13 @@ int crfr_rowconv_pair(const void* src, int src_ld, int n, int h, const void* w_p
     p.fres = (const bf16*)fuse->res; p.fres_ld = fuse->res_ld;
     p.fstats = fuse->stats; p.fgamma = fuse->gamma; p.fbeta = fuse->beta; p.falpha = fuse->alpha; p.frelu = fuse->relu;
     p.partial3 = fuse->partial;
-    p.parts = parts_for(n / 2, h, Cfg<1>::kGroups);
-    CRFR_CUDA(crfr_launch_pdl(rowconv_pair_kernel<1>, dim3(2 * clusters_for(p.total_rows)), dim3(Cfg<1>::kThreads), kSmemBytes, st, tmX, tmW, p));
+    if (!fuse->db && !fuse->res) {   // plain form: 16-warp half-row epilogue
+      p.parts = parts_for(n / 2, h, Cfg<3>::kGroups);
+      CRFR_CUDA(crfr_launch_pdl(rowconv_pair_kernel<3>, dim3(2 * clusters_for(p.total_rows)), dim3(Cfg<3>::kThreads), kSmemBytes, st, tmX, tmW, p));
+    } else {
+      p.parts = parts_for(n / 2, h, Cfg<1>::kGroups);
+      CRFR_CUDA(crfr_launch_pdl(rowconv_pair_kernel<1>, dim3(2 * clusters_for(p.total_rows)), dim3(Cfg<1>::kThreads), kSmemBytes, st, tmX, tmW, p));
+    }
   } else if (xf) {
     p.xy = (const bf16*)xf->y; p.xy_ld = xf->y_ld;
     p.xres = (const bf16*)xf->res; p.xres_ld = xf->res_ld;
