@@ -83,8 +83,10 @@ int crfr_norm_bwd_reduce_stream(const void* da, int da_ld, const void* db, int d
                                 const float* stats, const float* gamma, const float* beta, const float* alpha, int relu,
                                 const void* res, int res_ld, void* dz, int dz_ld, int n, int hw, int c, float* partial,
                                 cudaStream_t st);
+// (bstats / tot NULL: the apply pass folds the first pass' partial sums [n][parts][3][c] itself, no separate fold launch)
 int crfr_norm_bwd_apply_stream(const void* dsrc, int dsrc_ld, int recompute, const void* y, int y_ld, const float* stats,
-                               const float* bstats, const float* tot, const float* gamma, const float* beta,
+                               const float* partial, int parts, const float* bstats, const float* tot,
+                               const float* gamma, const float* beta,
                                const float* alpha, int relu, void* dy, int dy_ld, float* dgamma, float* dbeta,
                                float* dalpha, int n, int hw, int c, cudaStream_t st);
 

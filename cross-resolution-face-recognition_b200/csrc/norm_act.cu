@@ -549,12 +549,18 @@ int crfr_norm_bwd_finish(const float* partial, int chunks, const void* dsrc, int
                          int y_ld, const float* stats, const float* gamma, const float* beta, const float* alpha, int relu,
                          void* dy, int dy_ld, float* dgamma, float* dbeta, float* dalpha, int n, int hw, int c,
                          float* bstats, float* tot, int use_stream, cudaStream_t st) {
-  CRFR_CUDA(crfr_launch_pdl(bwd_fold_kernel, dim3(n, c / 8), dim3(kThreads), 0, st, partial, chunks, c, 1.f / (float)hw, bstats, tot));
-  CRFR_COUNT_LAUNCH();
-  CRFR_LAUNCH_CHECK();
+  // the TMA-fed apply pass folds the partial sums itself where an image has few partial slots (InstanceNorm); with one
+  // statistic group over the whole batch (BatchNorm: hundreds of slots) the fold stays a kernel of its own
+  const bool fold_inside = use_stream && chunks <= 16;
+  if (!fold_inside) {
+    CRFR_CUDA(crfr_launch_pdl(bwd_fold_kernel, dim3(n, c / 8), dim3(kThreads), 0, st, partial, chunks, c, 1.f / (float)hw, bstats, tot));
+    CRFR_COUNT_LAUNCH();
+    CRFR_LAUNCH_CHECK();
+  }
   if (use_stream)
-    return crfr_norm_bwd_apply_stream(dsrc, dsrc_ld, recompute, y, y_ld, stats, bstats, tot, gamma, beta, alpha, relu, dy,
-                                      dy_ld, dgamma, dbeta, dalpha, n, hw, c, st);
+    return crfr_norm_bwd_apply_stream(dsrc, dsrc_ld, recompute, y, y_ld, stats, partial, chunks, fold_inside ? nullptr : bstats,
+                                      fold_inside ? nullptr : tot, gamma, beta, alpha, relu, dy, dy_ld, dgamma, dbeta, dalpha, n,
+                                      hw, c, st);
   ChunkPlan pl = plan_chunks(n, hw);
   norm_act_bwd_apply_kernel<<<dim3(pl.chunks, n), kThreads, 0, st>>>(
       recompute ? nullptr : (const bf16*)dsrc, dsrc_ld, (const bf16*)y, y_ld, stats, bstats, gamma, (bf16*)dy, dy_ld, hw, c,

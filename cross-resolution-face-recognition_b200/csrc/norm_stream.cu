@@ -51,7 +51,8 @@ struct StreamArgs {
   long long total;                  // n x hw pixels
   int relu, has_b, has_res, recompute;
   const float* stats; const float* gamma; const float* beta; const float* alpha;
-  const float* bstats; const float* tot;
+  const float* bstats; const float* tot;   // apply: folded sums (register-kernel contract), or NULL: fold `partial` here
+  float inv_hw;
   bf16* out; int out_ld;            // reduce: dz (may be null); apply: dy
   float* partial;                   // reduce: [n][parts][3][c]
   float* dgamma; float* dbeta; float* dalpha;
@@ -322,18 +323,20 @@ norm_bwd_apply_stream_kernel(const __grid_constant__ Maps maps, const __grid_con
     produce(maps, a, u, P);
     return;
   }
-  // CTA 0 also folds the per-image totals into the parameter gradients, in fixed order (deterministic)
-  if (blockIdx.x == 0 && (a.dgamma || a.dbeta || a.dalpha)) {
-    for (int ch = threadIdx.x; ch < c; ch += kConsumers) {
-      float t0 = 0.f, t1 = 0.f, t2 = 0.f;
-      for (int i = 0; i < a.nimg; ++i) {
-        t0 += a.tot[(i * 3 + 0) * c + ch];
-        t1 += a.tot[(i * 3 + 1) * c + ch];
-        t2 += a.tot[(i * 3 + 2) * c + ch];
-      }
-      if (a.dbeta) a.dbeta[ch] += t0;
-      if (a.dgamma) a.dgamma[ch] += t1;
-      if (a.dalpha) a.dalpha[ch] += t2;
+  // The parameter gradients: 3 c sums over the images (folded totals) or over (image, partial slot), one warp each, spread
+  // over the grid; lanes stride over the entries and fold by butterfly - a fixed order (deterministic)
+  if (a.dgamma || a.dbeta || a.dalpha) {
+    const int wl = threadIdx.x & 31, entries = a.tot ? a.nimg : a.nimg * a.parts;
+    const float* src = a.tot ? a.tot : a.partial;
+    for (int sidx = blockIdx.x * (kConsumers / 32) + (threadIdx.x >> 5); sidx < 3 * c; sidx += gridDim.x * (kConsumers / 32)) {
+      const int qq = sidx / c, ch = sidx - qq * c;
+      float* dst = qq == 0 ? a.dbeta : (qq == 1 ? a.dgamma : a.dalpha);
+      if (!dst) continue;
+      float t = 0.f;
+      for (int e = wl; e < entries; e += 32) t += src[((long long)e * 3 + qq) * c + ch];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+      if (wl == 0) dst[ch] += t;
     }
   }
   const int cg = threadIdx.x % groups, lane = threadIdx.x / groups;
@@ -357,7 +360,16 @@ norm_bwd_apply_stream_kernel(const __grid_constant__ Maps maps, const __grid_con
       for (int e = 0; e < 2; ++e) {
         const int ch = cg * 8 + 2 * i + e;
         const float mu = a.stats[2 * (img * c + ch)], rs = a.stats[2 * (img * c + ch) + 1];
-        const float m1 = a.bstats[2 * (img * c + ch)], m2 = a.bstats[2 * (img * c + ch) + 1];
+        float m1 = 0.f, m2 = 0.f;   // mean dz, mean dz * xhat of (image, channel)
+        if (a.bstats) {             // folded by bwd_fold_kernel (many partial slots per image: BatchNorm)
+          m1 = a.bstats[2 * (img * c + ch)]; m2 = a.bstats[2 * (img * c + ch) + 1];
+        } else {                    // the few partial slots of an image, in fixed order
+          for (int k = 0; k < a.parts; ++k) {
+            m1 += a.partial[((long long)(img * a.parts + k) * 3 + 0) * c + ch];
+            m2 += a.partial[((long long)(img * a.parts + k) * 3 + 1) * c + ch];
+          }
+          m1 *= a.inv_hw; m2 *= a.inv_hw;
+        }
         const float gr = (a.gamma ? a.gamma[ch] : 1.f) * rs;
         t[e] = gr;
         t[2 + e] = -gr * m2 * rs;
@@ -562,7 +574,8 @@ int crfr_norm_bwd_reduce_stream(const void* da, int da_ld, const void* db, int d
 }
 
 int crfr_norm_bwd_apply_stream(const void* dsrc, int dsrc_ld, int recompute, const void* y, int y_ld, const float* stats,
-                               const float* bstats, const float* tot, const float* gamma, const float* beta,
+                               const float* partial, int parts, const float* bstats, const float* tot,
+                               const float* gamma, const float* beta,
                                const float* alpha, int relu, void* dy, int dy_ld, float* dgamma, float* dbeta,
                                float* dalpha, int n, int hw, int c, cudaStream_t st) {
   Maps maps;
@@ -580,6 +593,7 @@ int crfr_norm_bwd_apply_stream(const void* dsrc, int dsrc_ld, int recompute, con
   a.hw = hw; a.c = c; a.nimg = n; a.total = npix;
   a.relu = relu; a.recompute = recompute;
   a.stats = stats; a.gamma = gamma; a.beta = beta; a.alpha = alpha;
+  a.partial = const_cast<float*>(partial); a.parts = parts; a.inv_hw = 1.f / (float)hw;
   a.bstats = bstats; a.tot = tot;
   a.out = (bf16*)dy; a.out_ld = dy_ld;
   a.dgamma = dgamma; a.dbeta = dbeta; a.dalpha = dalpha;

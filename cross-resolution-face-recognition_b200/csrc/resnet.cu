@@ -108,6 +108,10 @@ struct Net {
   void* scratch = nullptr;
   size_t scratch_bytes = 0;
   Tensor feat[4], emb;
+  // weight packing: a dry run of the program (exec = false) collects every pack job here, the entry point issues them as
+  // one batch, and the real run (packs_done) only re-derives the same arena offsets (as in fsrnet.cu)
+  std::vector<crfr_pack_job>* collect = nullptr;
+  bool packs_done = false;
   bf16* wp = nullptr;    // packed linear weights (forward)
   bf16* wpt = nullptr;   // transposed (backward)
   int pcur = 0, bncur = 0;
@@ -160,8 +164,9 @@ struct Net {
     op.cin_pad = x.c < 8 ? 4 : x.c;
     const int T = k * k;
     void* wpk = alloc((size_t)T * cout * op.cin_pad * sizeof(bf16));
+    if (collect && ok()) collect->push_back({params[w_idx], wpk, T, cout, x.c, op.cin_pad, (long long)x.c * T, T, 0, 0});
     if (run()) {
-      check(crfr_pack_weight(params[w_idx], wpk, T, cout, x.c, op.cin_pad, (long long)x.c * T, T, 1, st));
+      if (!packs_done) check(crfr_pack_weight(params[w_idx], wpk, T, cout, x.c, op.cin_pad, (long long)x.c * T, T, 1, st));
       check(crfr_conv_fwd(engine, &d, x.p, wpk, op.cin_pad, nullptr, y.p, nullptr, nullptr, io->eps, scratch,
                           scratch_bytes, st));
     }
@@ -431,8 +436,10 @@ struct Net {
             bf16* dx = (bf16*)alloc((size_t)x.n * x.h * x.w * x.ld * sizeof(bf16));
             const int T = d.k * d.k;
             void* wt = alloc((size_t)T * d.cin * d.cout * sizeof(bf16));
+            if (collect && ok()) collect->push_back({params[op.w_idx], wt, T, d.cin, d.cout, d.cout, T, (long long)d.cin * T, 0, 0});
             if (run()) {
-              check(crfr_pack_weight(params[op.w_idx], wt, T, d.cin, d.cout, d.cout, T, (long long)d.cin * T, 1, st));
+              if (!packs_done)
+                check(crfr_pack_weight(params[op.w_idx], wt, T, d.cin, d.cout, d.cout, T, (long long)d.cin * T, 1, st));
               check(crfr_conv_dgrad(engine, &d, dy.p, wt, d.cout, dx, scratch, scratch_bytes, st));
             }
             add_slot(x, dx, x.ld);
@@ -572,55 +579,75 @@ extern "C" int crfr_kd_train_step(int engine, const float* const* teacher_params
   io_eval.eps = io_train.eps = kio->eps;
   io_eval.training = 0;
   io_train.training = 1;
+  // The program of one step over three networks; real = false: dry run (arena offsets and weight-pack jobs only)
+  auto program = [&](Net& T, Net& S, Net& A, bool real) -> int {
+    if (kio->teacher_ir50) T.forward_ir50();
+    else T.forward();
+    if (!T.ok()) return T.err;
+    S.forward();
+    if (!S.ok()) return S.err;
+    A.forward();
+    if (!A.ok()) return A.err;
+
+    float* parts = (float*)(base + lay.teacher + 2 * lay.train);   // [6] loss terms, then the reduction scratch
+    void* lws = parts + 64;
+    const size_t lws_bytes = lay.scratch - 64 * sizeof(float);
+    const bool to_student = kio->assistant_grad_to_student != 0;
+    auto grad_buf = [](Net& net, const Tensor& t) {
+      bf16* g = (bf16*)net.alloc((size_t)t.n * t.h * t.w * t.ld * sizeof(bf16));
+      net.add_slot(t, g, t.ld);
+      return g;
+    };
+    // student loss: MSE(s_emb, t_emb.detach())
+    {
+      const long long numel = (long long)S.emb.n * S.emb.c;
+      bf16* d_s = grad_buf(S, S.emb);
+      if (real)
+        CRFR_TRY(crfr_loss_kd(S.emb.p, nullptr, T.emb.p, numel, 0, 1.f, parts + 0, d_s, nullptr, nullptr, lws, lws_bytes, stream));
+    }
+    // assistant loss: sum_k MSE(t_k - s_k, a_k) over the four stage features and the embedding
+    for (int k = 0; k < 5; ++k) {
+      const Tensor& t = k < 4 ? T.feat[k] : T.emb;
+      const Tensor& s_ = k < 4 ? S.feat[k] : S.emb;
+      const Tensor& a = k < 4 ? A.feat[k] : A.emb;
+      const long long numel = (long long)t.n * t.h * t.w * t.c;
+      bf16* d_s = to_student ? grad_buf(S, s_) : nullptr;
+      bf16* d_a = grad_buf(A, a);
+      if (real)
+        CRFR_TRY(crfr_loss_kd(t.p, s_.p, a.p, numel, 0, 1.f, parts + 1 + k, nullptr, d_s, d_a, lws, lws_bytes, stream));
+    }
+    if (!S.ok()) return S.err;
+    if (!A.ok()) return A.err;
+    if (real) {
+      kd_total_kernel<<<1, 1, 0, st>>>(parts, losses);
+      CRFR_COUNT_LAUNCH();
+      CRFR_LAUNCH_CHECK();
+    }
+    S.backward();
+    if (!S.ok()) return S.err;
+    if (real && kio->events[0]) CRFR_CUDA(cudaEventRecord((cudaEvent_t)kio->events[0], st));   // student gradients are final
+    A.backward();
+    if (real && A.ok() && kio->events[1]) CRFR_CUDA(cudaEventRecord((cudaEvent_t)kio->events[1], st));
+    return A.err;
+  };
+  {   // all weight packs of the step (three networks, both directions: ~180) as three launches
+    std::vector<crfr_pack_job> jobs;
+    Net T, S, A;
+    init_net(T, engine, teacher_params, nullptr, teacher_buffers, &io_eval, base, lay.teacher, st, false);
+    init_net(S, engine, student_params, student_grads, student_buffers, &io_train, base + lay.teacher, lay.train, st, false);
+    init_net(A, engine, assistant_params, assistant_grads, assistant_buffers, &io_train, base + lay.teacher + lay.train,
+             lay.train, st, false);
+    T.collect = S.collect = A.collect = &jobs;
+    CRFR_TRY(program(T, S, A, false));
+    CRFR_TRY(crfr_pack_weight_batch(jobs.data(), (int)jobs.size(), st));
+  }
   Net T, S, A;
   init_net(T, engine, teacher_params, nullptr, teacher_buffers, &io_eval, base, lay.teacher, st, true);
   init_net(S, engine, student_params, student_grads, student_buffers, &io_train, base + lay.teacher, lay.train, st, true);
   init_net(A, engine, assistant_params, assistant_grads, assistant_buffers, &io_train, base + lay.teacher + lay.train,
            lay.train, st, true);
-  if (kio->teacher_ir50) T.forward_ir50();
-  else T.forward();
-  if (!T.ok()) return T.err;
-  S.forward();
-  if (!S.ok()) return S.err;
-  A.forward();
-  if (!A.ok()) return A.err;
-
-  float* parts = (float*)(base + lay.teacher + 2 * lay.train);   // [6] loss terms, then the reduction scratch
-  void* lws = parts + 64;
-  const size_t lws_bytes = lay.scratch - 64 * sizeof(float);
-  const bool to_student = kio->assistant_grad_to_student != 0;
-  auto grad_buf = [](Net& net, const Tensor& t) {
-    bf16* g = (bf16*)net.alloc((size_t)t.n * t.h * t.w * t.ld * sizeof(bf16));
-    net.add_slot(t, g, t.ld);
-    return g;
-  };
-  // student loss: MSE(s_emb, t_emb.detach())
-  {
-    const long long numel = (long long)S.emb.n * S.emb.c;
-    bf16* d_s = grad_buf(S, S.emb);
-    CRFR_TRY(crfr_loss_kd(S.emb.p, nullptr, T.emb.p, numel, 0, 1.f, parts + 0, d_s, nullptr, nullptr, lws, lws_bytes, stream));
-  }
-  // assistant loss: sum_k MSE(t_k - s_k, a_k) over the four stage features and the embedding
-  for (int k = 0; k < 5; ++k) {
-    const Tensor& t = k < 4 ? T.feat[k] : T.emb;
-    const Tensor& s_ = k < 4 ? S.feat[k] : S.emb;
-    const Tensor& a = k < 4 ? A.feat[k] : A.emb;
-    const long long numel = (long long)t.n * t.h * t.w * t.c;
-    bf16* d_s = to_student ? grad_buf(S, s_) : nullptr;
-    bf16* d_a = grad_buf(A, a);
-    CRFR_TRY(crfr_loss_kd(t.p, s_.p, a.p, numel, 0, 1.f, parts + 1 + k, nullptr, d_s, d_a, lws, lws_bytes, stream));
-  }
-  if (!S.ok()) return S.err;
-  if (!A.ok()) return A.err;
-  kd_total_kernel<<<1, 1, 0, st>>>(parts, losses);
-  CRFR_COUNT_LAUNCH();
-  CRFR_LAUNCH_CHECK();
-  S.backward();
-  if (!S.ok()) return S.err;
-  if (kio->events[0]) CRFR_CUDA(cudaEventRecord((cudaEvent_t)kio->events[0], st));   // student gradients are final
-  A.backward();
-  if (A.ok() && kio->events[1]) CRFR_CUDA(cudaEventRecord((cudaEvent_t)kio->events[1], st));
-  return A.err;
+  T.packs_done = S.packs_done = A.packs_done = true;
+  return program(T, S, A, true);
 }
 
 extern "C" size_t crfr_ir50_workspace_bytes(int batch, int size) {
