@@ -145,11 +145,11 @@ def run_reference(args):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one rowconv_pair_kernel launch over 128 images from the committed
-# `ncu --set full` capture of this round (profiles/r2_rowconv_pair_ncu.txt): 273.3 MB + 217.0 MB (algorithmic: 268.4 MB in
+# `ncu --set full` capture of this round (profiles/r2_rowconv_pair_final_ncu.txt): 273.3 MB + 224.7 MB (algorithmic: 268.4 MB in
 # + 268.4 MB out; part of the output is still dirty in the 126 MB L2 when the kernel ends).  A counter cannot be read
 # inside an un-profiled run, so the figure is labelled with its source (`traffic_source`).
-ROWCONV_TRAFFIC_BYTES_PER_IMAGE = (273.32e6 + 217.04e6) / 128
-ROWCONV_TRAFFIC_SOURCE = "ncu --set full capture profiles/r2_rowconv_pair_ncu.txt (round 2, rowconv_pair_kernel, 128 images)"
+ROWCONV_TRAFFIC_BYTES_PER_IMAGE = (273.30e6 + 224.68e6) / 128
+ROWCONV_TRAFFIC_SOURCE = "ncu --set full capture profiles/r2_rowconv_pair_final_ncu.txt (round 2 final, rowconv_pair_kernel<0>, 128 images)"
 
 
 def time_matcher(torch, ops, dist, world, rank, probes=10000, gallery=1000000, dim=512, k=5, reps=3):
@@ -278,31 +278,35 @@ def time_dominant_kernel(torch, ops, L, chunk):
     return flops / (ms * 1e-3) / 1e12, ms, flops
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of the two passes over 128 images from the committed `ncu --set full`
-# capture (profiles/r1_norm_stream_ncu_full.txt): reduce 1078.0 + 255.1 MB, apply 538.7 + 235.3 MB (algorithmic: 8 maps
-# of 268.4 MB; the tail of each output map is still dirty in L2 when its kernel ends)
-NORM_BWD_TRAFFIC_BYTES_PER_IMAGE = (1078.0e6 + 255.1e6 + 538.7e6 + 235.3e6) / 128
+# dram__bytes_read.sum + dram__bytes_write.sum over 128 images from the committed `ncu --set full` captures: the row-streaming
+# dgrad kernel with the fused first pass (profiles/r2_rowconv_pair_final_ncu.txt, variant 1: 1079.1 + 236.2 MB) and the apply
+# pass (profiles/r1_norm_stream_ncu_full.txt, kernel unchanged: 538.7 + 235.3 MB); algorithmic: 8 maps of 268.4 MB (the tail of
+# each output map is still dirty in L2 when its kernel ends)
+NORM_BWD_TRAFFIC_BYTES_PER_IMAGE = (1079.1e6 + 236.2e6 + 538.7e6 + 235.3e6) / 128
 
 
-def time_norm_bwd(torch, ops, chunk):
-    """CUDA-event timing of the dominant HBM-bound op: the InstanceNorm + PReLU + residual backward of a block output
-    (64 x 128 x 128, second gradient summed in): reduce pass dout_a, dout_b, y, res in, dz out; apply pass dz, y in,
-    dy out = 8 maps of chunk x 2 MiB; rotating buffers > L2."""
+def time_norm_bwd(torch, ops, L, chunk):
+    """CUDA-event timing of the dominant HBM-bound op of the step: the backward across conv(PReLU(InstanceNorm(y) + res))
+    of a residual block (64 x 128 x 128, second gradient summed in) as crfr_conv_dgrad_norm_bwd - the row-streaming dgrad
+    kernel with the first pass of the normalisation backward in its epilogue (dout, db, y, res in, dz out: 5 maps) and the
+    apply pass (dz, y in, dy out: 3 maps) = 8 maps of chunk x 2 MiB; rotating buffers > L2."""
     g = torch.Generator(device="cuda").manual_seed(5)
     c, h, sets = 64, 128, 3
     mk = lambda: torch.randn(chunk, h, h, c, generator=g, device="cuda").to(torch.bfloat16)
     ys, das, dbs, rs = ([mk() for _ in range(sets)] for _ in range(4))
     gamma, beta, alpha = (torch.rand(c, device="cuda") + 0.5 for _ in range(3))
+    wt = ops.pack_conv_weight(torch.randn(c, c, 3, 3, generator=g, device="cuda") * 0.05, for_dgrad=True)
     stats = ops.norm_stats(ys[0])
+    run = lambda k: ops.conv_dgrad_norm_bwd(das[k], wt, ys[k], stats, c, c, 3, 1, 1, gamma, beta, alpha, res=rs[k], dx_b=dbs[k],
+                                            engine=L.ENGINE_TCGEN05)
     for i in range(2):
-        ops.norm_act_bwd(das[i], ys[i], stats, gamma, beta, alpha, res=rs[i], dout_b=dbs[i])
+        run(i)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = 12
     e0.record()
     for i in range(reps):
-        k = i % sets
-        ops.norm_act_bwd(das[k], ys[k], stats, gamma, beta, alpha, res=rs[k], dout_b=dbs[k])
+        run(i % sets)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
@@ -468,13 +472,14 @@ def run_ours(args):
                              "traffic": ROWCONV_TRAFFIC_BYTES_PER_IMAGE * args.chunk,
                              "traffic_source": ROWCONV_TRAFFIC_SOURCE, "ms_per_launch": k_ms,
                              "flops_per_launch": k_flops, "peak_source": how}}
-        n_gbs, n_ms, n_bytes = time_norm_bwd(torch, ops, args.chunk)
-        line["roofline_hbm"] = {"bound": "hbm", "kernel": "norm_bwd_reduce_stream_kernel + bwd_fold_kernel + "
-                                                          "norm_bwd_apply_stream_kernel (InstanceNorm + PReLU + residual "
-                                                          "backward, 64 x 128 x 128, %d images)" % args.chunk,
+        n_gbs, n_ms, n_bytes = time_norm_bwd(torch, ops, L, args.chunk)
+        line["roofline_hbm"] = {"bound": "hbm", "kernel": "rowconv_pair_kernel<1> (3x3 dgrad + fused first pass of the InstanceNorm "
+                                                          "+ PReLU + residual backward) + norm_bwd_apply_stream_kernel, "
+                                                          "64 x 128 x 128, %d images" % args.chunk,
                                 "achieved": n_gbs, "peak": hbm, "unit": "GB/s", "frac": n_gbs / hbm,
                                 "traffic": NORM_BWD_TRAFFIC_BYTES_PER_IMAGE * args.chunk,
-                                "traffic_source": "ncu --set full capture profiles/r1_norm_stream_ncu_full.txt (kernels unchanged)",
+                                "traffic_source": "ncu --set full captures profiles/r2_rowconv_pair_final_ncu.txt (variant 1) + "
+                                                  "profiles/r1_norm_stream_ncu_full.txt (apply pass, kernel unchanged)",
                                 "ms_per_op": n_ms, "bytes_per_op": n_bytes, "peak_source": how}
         line.update(extras)
         if not args.no_cpu_baseline:
