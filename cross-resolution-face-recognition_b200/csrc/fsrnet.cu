@@ -172,6 +172,7 @@ struct Net {
   int section = -1;
   const crfr_fsrnet_section_io* sio = nullptr;
   bool want_dx = false;       // backward: the gradient w.r.t. the section input is requested
+  int fuse_bwd = -1;          // -1: option fuse_norm_bwd; 0 / 1: forced (the workspace sizing runs take the larger layout)
   Tensor sec_in, sec_feat;    // the section's bf16 input (NHWC) and its bf16 feature output
 
   void* alloc(size_t bytes) {
@@ -582,17 +583,25 @@ struct Net {
           Slot dy = slots[op.out.id][0];
           crfr_conv_desc d = op.cd;
           d.out_ld = dy.ld;
+          // The bias of a convolution whose output is instance-normalised cancels in the normalisation: its gradient is
+          // identically zero (the reference's autograd returns float noise of ~1e-9 relative for it).  The column sum over
+          // the bf16 gradient map (42 us per 128-image layer at 128 x 128, and the one float-atomic kernel of the step) is
+          // skipped for these layers: their bias gradient stays exactly zero.
+          const bool null_bias = op.b_idx >= 0 && i + 1 < (int)tape.size() && tape[i + 1].kind == OP_NORM &&
+                                 tape[i + 1].a.id == op.out.id && tape[i + 1].stats != nullptr;
+          float* dbias = null_bias ? nullptr : grad(op.b_idx);
           // plain tcgen05 weight gradients go to the helper stream, behind this layer's dgrad (see SideStream)
           const bool forked = side && scratch2 && engine != CRFR_ENGINE_DIRECT && crfr_lowered_recipe(&d) == 0 &&
                               !d.transposed && crfr_tc_supported(2, d.h, d.w, d.cin, d.cout, d.k, d.stride, d.pad);
           if (!forked && run())
-            check(crfr_conv_wgrad(engine, &d, op.a.p, dy.p, grad(op.w_idx), grad(op.b_idx), scratch, scratch_bytes, st));
+            check(crfr_conv_wgrad(engine, &d, op.a.p, dy.p, grad(op.w_idx), dbias, scratch, scratch_bytes, st));
           // The convolution's input is the output of the normalisation recorded just before it (every other consumer of
           // that tensor comes later in the tape, so its remaining gradient slots are complete): dgrad + the whole
           // normalisation backward as one operation - for the row-streaming shapes the first pass of the normalisation
           // backward runs inside the dgrad epilogue and the dgrad output never reaches memory.
           Op* nop = (i > 0 && tape[i - 1].kind == OP_NORM && tape[i - 1].out.id == op.a.id) ? &tape[i - 1] : nullptr;
-          if (op.x_needs_grad && nop && !d.transposed && engine != CRFR_ENGINE_DIRECT && crfr_opt(CRFR_OPT_FUSE_NORM_BWD) &&
+          if (op.x_needs_grad && nop && !d.transposed && engine != CRFR_ENGINE_DIRECT &&
+              (fuse_bwd < 0 ? crfr_opt(CRFR_OPT_FUSE_NORM_BWD) : fuse_bwd) &&
               crfr_lowered_recipe(&d) == 0 && crfr_rowconv_supported(d.h, d.w, d.cin, d.cout, d.k, d.stride, d.pad) &&
               crfr_rowconv_pair_supported(d.n, d.h) && op.a.c == nop->a.c) {
             const Tensor& x = op.a;
@@ -632,7 +641,7 @@ struct Net {
           if (forked && run()) {
             check(cudaEventRecord(side->fork, st) == cudaSuccess ? CRFR_OK : CRFR_ECUDA);
             check(cudaStreamWaitEvent(side->st, side->fork, 0) == cudaSuccess ? CRFR_OK : CRFR_ECUDA);
-            check(crfr_conv_wgrad(engine, &d, op.a.p, dy.p, grad(op.w_idx), grad(op.b_idx), scratch2, scratch2_bytes,
+            check(crfr_conv_wgrad(engine, &d, op.a.p, dy.p, grad(op.w_idx), dbias, scratch2, scratch2_bytes,
                                   side->st));
             side_dirty = true;
           }
@@ -795,14 +804,20 @@ extern "C" size_t crfr_fsrnet_workspace_bytes(int batch, int size, int training)
   if (batch <= 0 || size < 32 || size % 16) return 0;
   crfr_fsrnet_io io = {};
   io.batch = batch; io.size = size;
-  Net net;
-  init_net(net, CRFR_ENGINE_AUTO, nullptr, nullptr, &io, nullptr, ~(size_t)0 >> 2, nullptr, false, training != 0);
-  net.forward();
-  if (training) {
-    alloc_out_grads(net, true, true, true);
-    net.backward();
+  size_t need = 0;
+  for (int fuse = 0; fuse < 2; ++fuse) {   // the backward's arena layout depends on the fused / unfused boundary operation:
+    Net net;                               // a workspace of this size serves either setting of the option
+    init_net(net, CRFR_ENGINE_AUTO, nullptr, nullptr, &io, nullptr, ~(size_t)0 >> 2, nullptr, false, training != 0);
+    net.fuse_bwd = fuse;
+    net.forward();
+    if (training) {
+      alloc_out_grads(net, true, true, true);
+      net.backward();
+    }
+    if (net.off > need) need = net.off;
+    if (!training) break;
   }
-  return net.off + 65536;
+  return need + 65536;
 }
 
 // Layout of the saved forward tensors in the workspace (a dry run: nothing is launched).  Parity tests read the stored
@@ -901,23 +916,27 @@ extern "C" size_t crfr_fsrnet_section_workspace_bytes(int section, int batch, in
   if (section < 0 || section > 3 || batch <= 0 || size < 32 || size % 16) return 0;
   crfr_fsrnet_section_io sio = {};
   sio.section = section; sio.batch = batch; sio.size = size;
-  Net net;
-  init_section(net, CRFR_ENGINE_AUTO, nullptr, nullptr, &sio, nullptr, ~(size_t)0 >> 2, nullptr, false, training != 0);
-  net.want_dx = true;
-  net.forward();
-  if (training) {
-    const int Q = size / 4;
-    alloc_out_grads(net, false, section == CRFR_FSRNET_COARSE || section == CRFR_FSRNET_DECODER,
-                    section == CRFR_FSRNET_PRIOR);
-    if (section != CRFR_FSRNET_DECODER) {   // gradient of the feature output, converted to bf16 NHWC
-      net.add_slot(net.sec_feat, (bf16*)net.alloc((size_t)batch * net.sec_feat.h * net.sec_feat.w * net.sec_feat.c * sizeof(bf16)),
-                   net.sec_feat.c);
+  size_t need = 0;
+  for (int fuse = 0; fuse < 2; ++fuse) {   // either setting of option fuse_norm_bwd (see crfr_fsrnet_workspace_bytes)
+    Net net;
+    init_section(net, CRFR_ENGINE_AUTO, nullptr, nullptr, &sio, nullptr, ~(size_t)0 >> 2, nullptr, false, training != 0);
+    net.want_dx = true;
+    net.fuse_bwd = fuse;
+    net.forward();
+    if (training) {
+      alloc_out_grads(net, false, section == CRFR_FSRNET_COARSE || section == CRFR_FSRNET_DECODER,
+                      section == CRFR_FSRNET_PRIOR);
+      if (section != CRFR_FSRNET_DECODER) {   // gradient of the feature output, converted to bf16 NHWC
+        net.add_slot(net.sec_feat, (bf16*)net.alloc((size_t)batch * net.sec_feat.h * net.sec_feat.w * net.sec_feat.c * sizeof(bf16)),
+                     net.sec_feat.c);
+      }
+      net.backward();
+      if (net.has_grad(net.sec_in)) net.squash(net.sec_in, 1);
     }
-    (void)Q;
-    net.backward();
-    if (net.has_grad(net.sec_in)) net.squash(net.sec_in, 1);
+    if (net.off > need) need = net.off;
+    if (!training) break;
   }
-  return net.off + 65536;
+  return need + 65536;
 }
 
 extern "C" int crfr_fsrnet_section_forward(int engine, const float* const* host_params, const crfr_fsrnet_section_io* io,
