@@ -111,4 +111,12 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 __device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+// (mean, rstd) from the sums of x and x^2 over hw samples.  Explicitly rounded operations: the kernels that finalise
+// statistics (stats_finalize_kernel, the forward pass of norm_stream.cu) must agree bit for bit, whatever the compiler
+// would contract into an FMA in each of them.
+__device__ __forceinline__ void crfr_mean_rstd(float sum, float sumsq, float inv_hw, float eps, float& mean, float& rstd) {
+  mean = __fmul_rn(sum, inv_hw);
+  const float var = fmaxf(__fsub_rn(__fmul_rn(sumsq, inv_hw), __fmul_rn(mean, mean)), 0.f);
+  rstd = rsqrtf(__fadd_rn(var, eps));
+}
 #endif

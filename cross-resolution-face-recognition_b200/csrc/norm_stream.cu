@@ -53,6 +53,9 @@ struct StreamArgs {
   const float* stats; const float* gamma; const float* beta; const float* alpha;
   const float* bstats; const float* tot;   // apply: folded sums (register-kernel contract), or NULL: fold `partial` here
   float inv_hw;
+  // forward: statistics still to be finalised from a producer's partial sums [n][fparts][2][c] (NULL: `stats` is final);
+  // the CTA that owns an image's first pixel also writes (mean, rstd) to stats_out for the backward pass
+  const float* fpartial; int fparts; float eps; float* stats_out;
   bf16* out; int out_ld;            // reduce: dz (may be null); apply: dy
   float* partial;                   // reduce: [n][parts][3][c]
   float* dgamma; float* dbeta; float* dalpha;
@@ -450,7 +453,21 @@ norm_fwd_stream_kernel(const __grid_constant__ Maps maps, const __grid_constant_
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int ch = cg * 8 + 2 * i + e;
-        const float mu = a.stats[2 * (img * c + ch)], rs = a.stats[2 * (img * c + ch) + 1];
+        float mu, rs;
+        if (a.fpartial) {   // finalise here, with the arithmetic and summation order of stats_finalize_kernel (norm_act.cu)
+          float ts = 0.f, tq = 0.f;
+          for (int k = 0; k < a.fparts; ++k) {
+            ts += a.fpartial[((long long)(img * a.fparts + k) * 2 + 0) * c + ch];
+            tq += a.fpartial[((long long)(img * a.fparts + k) * 2 + 1) * c + ch];
+          }
+          crfr_mean_rstd(ts, tq, a.inv_hw, a.eps, mu, rs);
+          if (off == 0 && lane == 0) {
+            a.stats_out[2 * (img * c + ch)] = mu;
+            a.stats_out[2 * (img * c + ch) + 1] = rs;
+          }
+        } else {
+          mu = a.stats[2 * (img * c + ch)]; rs = a.stats[2 * (img * c + ch) + 1];
+        }
         t[e] = (a.gamma ? a.gamma[ch] : 1.f) * rs;
         t[2 + e] = (a.beta ? a.beta[ch] : 0.f) - mu * t[e];
         t[4 + e] = a.relu ? 0.f : (a.alpha ? a.alpha[ch] : 1.f);
@@ -606,7 +623,7 @@ int crfr_norm_bwd_apply_stream(const void* dsrc, int dsrc_ld, int recompute, con
 
 int crfr_norm_fwd_stream(const void* y, int y_ld, const float* stats, const float* gamma, const float* beta,
                          const float* alpha, int relu, const void* res, int res_ld, void* out, int out_ld, int n, int hw,
-                         int c, cudaStream_t st) {
+                         int c, cudaStream_t st, const float* fpartial, int fparts, float eps) {
   Maps maps;
   StreamArgs a = {};
   const int P = 2 * kTileBytes / (2 * c);
@@ -624,6 +641,7 @@ int crfr_norm_fwd_stream(const void* y, int y_ld, const float* stats, const floa
   a.relu = relu; a.has_res = res != nullptr;
   a.stats = stats; a.gamma = gamma; a.beta = beta; a.alpha = alpha;
   a.out = (bf16*)out; a.out_ld = out_ld;
+  a.fpartial = fpartial; a.fparts = fparts; a.eps = eps; a.stats_out = const_cast<float*>(stats); a.inv_hw = 1.f / (float)hw;
   CRFR_TRY(set_attrs());
   CRFR_CUDA(crfr_launch_pdl(norm_fwd_stream_kernel, dim3(grid_for(npix, c)), dim3(kThreads), kSmemBytes, st, maps, a));
   CRFR_COUNT_LAUNCH();
