@@ -90,24 +90,9 @@ int crfr_norm_bwd_apply_stream(const void* dsrc, int dsrc_ld, int recompute, con
                                const float* alpha, int relu, void* dy, int dy_ld, float* dgamma, float* dbeta,
                                float* dalpha, int n, int hw, int c, cudaStream_t st);
 
-// fpartial != NULL: `stats` is still to be finalised from a producer's partial sums [n][fparts][2][c]; the kernel does it on
-// the fly (bit-identical to stats_finalize_kernel) and WRITES `stats` for the backward pass
 int crfr_norm_fwd_stream(const void* y, int y_ld, const float* stats, const float* gamma, const float* beta,
                          const float* alpha, int relu, const void* res, int res_ld, void* out, int out_ld, int n, int hw,
-                         int c, cudaStream_t st, const float* fpartial = nullptr, int fparts = 0, float eps = 0.f);
-
-// Deferred finalisation of fused statistics: while a record is armed (by a network program that runs the normalisation
-// right after the convolution), crfr_norm_finalize stores its arguments there instead of launching stats_finalize_kernel,
-// and crfr_norm_act_fwd_deferred lets the TMA-fed forward pass finalise on the fly (one tiny launch per layer fewer).
-struct crfr_norm_defer {
-  const float* partial; int n, chunks, hw, c; float eps; float* stats;
-  bool valid;
-};
-void crfr_norm_defer_arm(crfr_norm_defer* rec);   // nullptr: disarm
-int crfr_norm_defer_flush(crfr_norm_defer* rec, cudaStream_t st);   // launches the pending finalisation, if any
-int crfr_norm_act_fwd_deferred(crfr_norm_defer* rec, const void* y, int y_ld, const float* stats, const float* gamma,
-                               const float* beta, const float* alpha, int relu, const void* res, int res_ld, void* out,
-                               int out_ld, int n, int hw, int c, cudaStream_t st);
+                         int c, cudaStream_t st);
 
 // losses.cu: MSE*97 loss with the fp32 per-channel sums of its gradient (bias gradient of the producing convolution),
 // and the same sums for an explicit fp32 NCHW gradient

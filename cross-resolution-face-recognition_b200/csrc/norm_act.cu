@@ -423,17 +423,8 @@ size_t crfr_norm_ws_bytes(int n, int hw, int c) {
 }
 
 // Finalise (mean, rstd) from partials laid out [n][chunks][2][c]; shared with the conv epilogue statistics.
-namespace {
-thread_local crfr_norm_defer* g_defer = nullptr;
-}
-void crfr_norm_defer_arm(crfr_norm_defer* rec) { g_defer = rec; }
-
 int crfr_norm_finalize(const float* partial, int n, int chunks, int hw, int c, float eps, float* stats,
                        cudaStream_t st) {
-  if (g_defer && chunks <= 32) {   // (<= 32 slots: the in-kernel sum reproduces stats_finalize_kernel's order exactly)
-    *g_defer = {partial, n, chunks, hw, c, eps, stats, true};
-    return CRFR_OK;
-  }
   CRFR_CUDA(crfr_launch_pdl(stats_finalize_kernel, dim3(n, c / 8), dim3(kThreads), 0, st, partial, chunks, c, 1.f / (float)hw, eps, stats));
   CRFR_COUNT_LAUNCH();
   CRFR_LAUNCH_CHECK();
@@ -506,31 +497,6 @@ extern "C" int crfr_norm_act_fwd(const void* y, int y_ld, const float* stats, co
   CRFR_COUNT_LAUNCH();
   CRFR_LAUNCH_CHECK();
   return CRFR_OK;
-}
-
-int crfr_norm_defer_flush(crfr_norm_defer* rec, cudaStream_t st) {
-  if (!rec || !rec->valid) return CRFR_OK;
-  rec->valid = false;
-  crfr_norm_defer* armed = g_defer;
-  g_defer = nullptr;
-  const int rc = crfr_norm_finalize(rec->partial, rec->n, rec->chunks, rec->hw, rec->c, rec->eps, rec->stats, st);
-  g_defer = armed;
-  return rc;
-}
-
-int crfr_norm_act_fwd_deferred(crfr_norm_defer* rec, const void* y, int y_ld, const float* stats, const float* gamma,
-                               const float* beta, const float* alpha, int relu, const void* res, int res_ld, void* out,
-                               int out_ld, int n, int hw, int c, cudaStream_t st) {
-  const void* views[3] = {y, res, out};
-  const int lds[3] = {y_ld, res_ld, out_ld};
-  if (rec && rec->valid && rec->stats == stats && rec->n == n && rec->hw == hw && rec->c == c && y && out &&
-      crfr_opt(CRFR_OPT_NORM_FWD_STREAM) && crfr_norm_stream_supported(c, (long long)n * hw, views, lds, 3)) {
-    rec->valid = false;
-    return crfr_norm_fwd_stream(y, y_ld, stats, gamma, beta, alpha, relu, res, res_ld, out, out_ld, n, hw, c, st, rec->partial,
-                                rec->chunks, rec->eps);
-  }
-  CRFR_TRY(crfr_norm_defer_flush(rec, st));
-  return crfr_norm_act_fwd(y, y_ld, stats, gamma, beta, alpha, relu, res, res_ld, out, out_ld, n, hw, c, (void*)st);
 }
 
 extern "C" int crfr_norm_act_bwd(const void* dout_a, int da_ld, const void* dout_b, int db_ld, const void* y,

@@ -53,9 +53,6 @@ struct StreamArgs {
   const float* stats; const float* gamma; const float* beta; const float* alpha;
   const float* bstats; const float* tot;   // apply: folded sums (register-kernel contract), or NULL: fold `partial` here
   float inv_hw;
-  // forward: statistics still to be finalised from a producer's partial sums [n][fparts][2][c] (NULL: `stats` is final);
-  // the CTA that owns an image's first pixel also writes (mean, rstd) to stats_out for the backward pass
-  const float* fpartial; int fparts; float eps; float* stats_out;
   bf16* out; int out_ld;            // reduce: dz (may be null); apply: dy
   float* partial;                   // reduce: [n][parts][3][c]
   float* dgamma; float* dbeta; float* dalpha;
@@ -355,6 +352,28 @@ norm_bwd_apply_stream_kernel(const __grid_constant__ Maps maps, const __grid_con
     const int img = r / a.hw, off = r - img * a.hw;
     const int seg = min(a.hw - off, u.r_end - r);
     const int nst = (seg + P - 1) / P;
+    // mean dz, mean dz * xhat of this thread's 8 channels of the image
+    float m1[8], m2[8];
+    if (a.bstats) {               // folded by bwd_fold_kernel (many partial slots per image: BatchNorm)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        m1[j] = a.bstats[2 * (img * c + cg * 8 + j)];
+        m2[j] = a.bstats[2 * (img * c + cg * 8 + j) + 1];
+      }
+    } else {                      // the few partial slots of an image in fixed order; slot loop outermost: 16 independent loads
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m1[j] = m2[j] = 0.f;
+      const float* ps = a.partial + (long long)img * a.parts * 3 * c + cg * 8;
+#pragma unroll 2
+      for (int k = 0; k < a.parts; ++k, ps += 3 * c) {
+        const float4 u0 = *reinterpret_cast<const float4*>(ps), u1 = *reinterpret_cast<const float4*>(ps + 4);
+        const float4 v0 = *reinterpret_cast<const float4*>(ps + c), v1 = *reinterpret_cast<const float4*>(ps + c + 4);
+        m1[0] += u0.x; m1[1] += u0.y; m1[2] += u0.z; m1[3] += u0.w; m1[4] += u1.x; m1[5] += u1.y; m1[6] += u1.z; m1[7] += u1.w;
+        m2[0] += v0.x; m2[1] += v0.y; m2[2] += v0.z; m2[3] += v0.w; m2[4] += v1.x; m2[5] += v1.y; m2[6] += v1.z; m2[7] += v1.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { m1[j] *= a.inv_hw; m2[j] *= a.inv_hw; }
+    }
     float2 ca[4], cb[4], cc[4], sh[4], al[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -363,20 +382,10 @@ norm_bwd_apply_stream_kernel(const __grid_constant__ Maps maps, const __grid_con
       for (int e = 0; e < 2; ++e) {
         const int ch = cg * 8 + 2 * i + e;
         const float mu = a.stats[2 * (img * c + ch)], rs = a.stats[2 * (img * c + ch) + 1];
-        float m1 = 0.f, m2 = 0.f;   // mean dz, mean dz * xhat of (image, channel)
-        if (a.bstats) {             // folded by bwd_fold_kernel (many partial slots per image: BatchNorm)
-          m1 = a.bstats[2 * (img * c + ch)]; m2 = a.bstats[2 * (img * c + ch) + 1];
-        } else {                    // the few partial slots of an image, in fixed order
-          for (int k = 0; k < a.parts; ++k) {
-            m1 += a.partial[((long long)(img * a.parts + k) * 3 + 0) * c + ch];
-            m2 += a.partial[((long long)(img * a.parts + k) * 3 + 1) * c + ch];
-          }
-          m1 *= a.inv_hw; m2 *= a.inv_hw;
-        }
         const float gr = (a.gamma ? a.gamma[ch] : 1.f) * rs;
         t[e] = gr;
-        t[2 + e] = -gr * m2 * rs;
-        t[4 + e] = -gr * m1 - t[2 + e] * mu;
+        t[2 + e] = -gr * m2[2 * i + e] * rs;
+        t[4 + e] = -gr * m1[2 * i + e] - t[2 + e] * mu;
         t[6 + e] = (a.beta ? a.beta[ch] : 0.f) - mu * gr;
         t[8 + e] = a.relu ? 0.f : (a.alpha ? a.alpha[ch] : 1.f);
       }
@@ -453,21 +462,7 @@ norm_fwd_stream_kernel(const __grid_constant__ Maps maps, const __grid_constant_
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int ch = cg * 8 + 2 * i + e;
-        float mu, rs;
-        if (a.fpartial) {   // finalise here, with the arithmetic and summation order of stats_finalize_kernel (norm_act.cu)
-          float ts = 0.f, tq = 0.f;
-          for (int k = 0; k < a.fparts; ++k) {
-            ts += a.fpartial[((long long)(img * a.fparts + k) * 2 + 0) * c + ch];
-            tq += a.fpartial[((long long)(img * a.fparts + k) * 2 + 1) * c + ch];
-          }
-          crfr_mean_rstd(ts, tq, a.inv_hw, a.eps, mu, rs);
-          if (off == 0 && lane == 0) {
-            a.stats_out[2 * (img * c + ch)] = mu;
-            a.stats_out[2 * (img * c + ch) + 1] = rs;
-          }
-        } else {
-          mu = a.stats[2 * (img * c + ch)]; rs = a.stats[2 * (img * c + ch) + 1];
-        }
+        const float mu = a.stats[2 * (img * c + ch)], rs = a.stats[2 * (img * c + ch) + 1];
         t[e] = (a.gamma ? a.gamma[ch] : 1.f) * rs;
         t[2 + e] = (a.beta ? a.beta[ch] : 0.f) - mu * t[e];
         t[4 + e] = a.relu ? 0.f : (a.alpha ? a.alpha[ch] : 1.f);
@@ -623,7 +618,7 @@ int crfr_norm_bwd_apply_stream(const void* dsrc, int dsrc_ld, int recompute, con
 
 int crfr_norm_fwd_stream(const void* y, int y_ld, const float* stats, const float* gamma, const float* beta,
                          const float* alpha, int relu, const void* res, int res_ld, void* out, int out_ld, int n, int hw,
-                         int c, cudaStream_t st, const float* fpartial, int fparts, float eps) {
+                         int c, cudaStream_t st) {
   Maps maps;
   StreamArgs a = {};
   const int P = 2 * kTileBytes / (2 * c);
@@ -641,7 +636,6 @@ int crfr_norm_fwd_stream(const void* y, int y_ld, const float* stats, const floa
   a.relu = relu; a.has_res = res != nullptr;
   a.stats = stats; a.gamma = gamma; a.beta = beta; a.alpha = alpha;
   a.out = (bf16*)out; a.out_ld = out_ld;
-  a.fpartial = fpartial; a.fparts = fparts; a.eps = eps; a.stats_out = const_cast<float*>(stats); a.inv_hw = 1.f / (float)hw;
   CRFR_TRY(set_attrs());
   CRFR_CUDA(crfr_launch_pdl(norm_fwd_stream_kernel, dim3(grid_for(npix, c)), dim3(kThreads), kSmemBytes, st, maps, a));
   CRFR_COUNT_LAUNCH();
