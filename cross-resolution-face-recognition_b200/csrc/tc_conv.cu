@@ -94,12 +94,15 @@ template <int N>
 struct ConvCfg {
   static constexpr int kBTileBytes = N * 128;
   static constexpr int kStageBytes = kATileBytes + kBTileBytes;
-  static constexpr int kStages = (N <= 64) ? 4 : 3;
+  // stages: the K loops are short (9-72 steps per tile) and every step is a TMA round trip to L2 (~1 us): the ring is as deep
+  // as the 227 KB of shared memory allow beside the staging tile (24 / 32 / 48 KB per stage)
+  static constexpr int kStages = (N <= 64) ? 8 : (N <= 128) ? 6 : 3;
   static constexpr int kTmemCols = (N <= 32) ? 32 : (N <= 64) ? 64 : (N <= 128) ? 128 : 256;
   static constexpr int kOutTiles = (N + 63) / 64;               // 64-channel sub-tiles staged for the TMA store
   static constexpr int kOutBytes = kOutTiles * kATileBytes;
   static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static_assert(N % 32 == 0 && N <= 256 && 2 * kTmemCols <= 512, "tile width");
+  static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
 
 // Persistent: the grid is (CTAs, column tiles); a CTA walks pixel tiles blockIdx.x, blockIdx.x + gridDim.x, ... so
@@ -326,7 +329,7 @@ template <int N, int TAPS>
 struct WgCfg {
   static constexpr int kDyTiles = N / 64;
   static constexpr int kStageBytes = (TAPS + kDyTiles) * kTile16K;
-  static constexpr int kStages = (kStageBytes <= 64 * 1024) ? 3 : 2;
+  static constexpr int kStages = (kStageBytes <= 32 * 1024) ? 6 : (kStageBytes <= 48 * 1024) ? 4 : (kStageBytes <= 64 * 1024) ? 3 : 2;
   static constexpr int kAccs = (TAPS + 1) / 2;                     // accumulators of M = 128 (two taps each)
   static constexpr int kTmemCols = (kAccs * N <= 64) ? 64 : (kAccs * N <= 128) ? 128 : 256;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
