@@ -90,17 +90,25 @@ struct ConvParams {
 constexpr int kConvThreads = 192;  // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
 constexpr int kATileBytes = 128 * 128;
 
-template <int N>
+// R (3x3, 64 input channels, N <= 64): the TMA unit issues one request per 128-byte pixel row of a box, and the generic
+// form asks for 128 rows per (tap, K chunk) step - 1 152 rows and 72 KB of re-streamed weights per pixel tile, which bounds
+// the 64 -> 64 layers at 766 cycles per K step with the tensor pipe 17 % active (ncu: nothing else above 25 % of its peak).
+// R keeps all nine weight tiles resident in shared memory and loads ONE box per kx shift that also holds the two halo
+// rows, (bh + 2) x bw pixels: the three ky taps of a kx are row offsets into the same box (bw % 8 == 0 keeps the offsets on
+// swizzle-atom boundaries).  576 rows per tile instead of 1 152, 3 ring steps of 12 MMAs instead of 9 of 4.
+constexpr int kResidentIters = 9;
+template <int N, bool R = false>
 struct ConvCfg {
   static constexpr int kBTileBytes = N * 128;
-  static constexpr int kStageBytes = kATileBytes + kBTileBytes;
+  static constexpr int kStageBytes = R ? 2 * kATileBytes : kATileBytes + kBTileBytes;   // R: up to 256 pixel rows (box + halo)
   // stages: the K loops are short (9-72 steps per tile) and every step is a TMA round trip to L2 (~1 us): the ring is as deep
   // as the 227 KB of shared memory allow beside the staging tile (24 / 32 / 48 KB per stage)
-  static constexpr int kStages = (N <= 64) ? 8 : (N <= 128) ? 6 : 3;
+  static constexpr int kStages = R ? 4 : (N <= 64) ? 8 : (N <= 128) ? 6 : 3;
+  static constexpr int kResidentBytes = R ? kResidentIters * kBTileBytes : 0;
   static constexpr int kTmemCols = (N <= 32) ? 32 : (N <= 64) ? 64 : (N <= 128) ? 128 : 256;
   static constexpr int kOutTiles = (N + 63) / 64;               // 64-channel sub-tiles staged for the TMA store
   static constexpr int kOutBytes = kOutTiles * kATileBytes;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kOutBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kResidentBytes + kOutBytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static_assert(N % 32 == 0 && N <= 256 && 2 * kTmemCols <= 512, "tile width");
   static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
@@ -108,19 +116,21 @@ struct ConvCfg {
 // Persistent: the grid is (CTAs, column tiles); a CTA walks pixel tiles blockIdx.x, blockIdx.x + gridDim.x, ... so
 // that barrier setup / TMEM allocation are paid once and - with two TMEM accumulators - the epilogue of tile i
 // overlaps the TMA + MMA work of tile i+1 (the layers on this kernel have short K loops: 9-72 steps per tile).
-template <int N>
+template <int N, bool R>
 __global__ void __launch_bounds__(kConvThreads, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmY, ConvParams p) {
-  using Cfg = ConvCfg<N>;
+               const __grid_constant__ CUtensorMap tmY, ConvParams p) {   // R: tmA has the box with the halo rows
+  using Cfg = ConvCfg<N, R>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* sOut = base + Cfg::kStages * Cfg::kStageBytes;
+  uint8_t* sB = base + Cfg::kStages * Cfg::kStageBytes;          // R: resident weight tiles [iters][N][64]
+  uint8_t* sOut = sB + Cfg::kResidentBytes;
   uint64_t* full = (uint64_t*)(sOut + Cfg::kOutBytes);
   uint64_t* empty = full + Cfg::kStages;
   uint64_t* tmem_full = empty + Cfg::kStages;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;         // [2]
-  uint32_t* tmem_slot = (uint32_t*)(tmem_empty + 2);
+  uint64_t* w_full = tmem_empty + 2;            // R: the resident weights have landed
+  uint32_t* tmem_slot = (uint32_t*)(w_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -132,6 +142,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&tmem_full[b], 1);
       mbar_init(&tmem_empty[b], 4);
     }
+    mbar_init(w_full, 1);
     fence_barrier_init();
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
@@ -143,13 +154,18 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  const int iters = p.ntaps * p.kchunks;
+  const int iters = R ? 3 : p.ntaps * p.kchunks;   // ring steps per pixel tile
   const uint32_t a_bytes = (uint32_t)p.rows * 128u;
   const int ncol0 = blockIdx.y * N;
   const int my_tiles = (int)blockIdx.x < p.total_tiles ? (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   if (warp == 0) {
     const bool leader = elect_one();
+    if (R && leader && my_tiles > 0) {
+      mbar_expect_tx(w_full, (uint32_t)kResidentIters * Cfg::kBTileBytes);
+      for (int tap = 0; tap < kResidentIters; ++tap)
+        tma_load_2d(sB + tap * Cfg::kBTileBytes, &tmB, w_full, 0, tap * p.n_total + ncol0);
+    }
     int g = 0;   // running stage index across tiles
     for (int i = 0; i < my_tiles; ++i) {
       int t = blockIdx.x + i * gridDim.x;
@@ -159,11 +175,18 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int it = 0; it < iters; ++it, ++g) {
         const int s = g % Cfg::kStages;
         mbar_wait(&empty[s], ((g / Cfg::kStages) & 1) ^ 1);
+        uint8_t* sa = base + s * Cfg::kStageBytes;
+        if (R) {   // step = kx: the box of rows y0 - 1 .. y0 + bh at the x shift of this kx
+          if (leader) {
+            mbar_expect_tx(&full[s], (uint32_t)((p.bh + 2) * p.bw) * 128u);
+            tma_load_4d(sa, &tmA, &full[s], 0, x0 + p.sign * (it - 1), y0 - 1, n0);
+          }
+          continue;
+        }
         const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
         const int ky = tap / p.ksize, kx = tap - ky * p.ksize;
-        uint8_t* sa = base + s * Cfg::kStageBytes;
         if (leader) {
-          mbar_expect_tx(&full[s], a_bytes + Cfg::kBTileBytes);
+          mbar_expect_tx(&full[s], a_bytes + (uint32_t)Cfg::kBTileBytes);
           tma_load_4d(sa, &tmA, &full[s], kc * 64, x0 + p.sign * (kx - p.pad), y0 + p.sign * (ky - p.pad), n0);
           tma_load_2d(sa + kATileBytes, &tmB, &full[s], kc * 64, tap * p.n_total + ncol0);
         }
@@ -173,6 +196,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool leader = elect_one();
     const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
     const uint64_t desc0 = make_smem_desc_sw128(smem_u32(base), 16, 1024);
+    const uint64_t descB = make_smem_desc_sw128(smem_u32(sB), 16, 1024);
+    if (R && my_tiles > 0) mbar_wait(w_full, 0);
     int g = 0;
     for (int i = 0; i < my_tiles; ++i) {
       const int buf = i & 1;
@@ -184,6 +209,21 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(&full[s], (g / Cfg::kStages) & 1);
         tc_fence_after();
         const uint64_t da = desc0 + (uint64_t)((s * Cfg::kStageBytes) >> 4);
+        if (R) {   // step = kx; tap (ky, kx) reads the box from row (forward: ky, dgrad: 2 - ky) on
+          if (leader) {
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+              const int row = p.sign > 0 ? ky : 2 - ky;
+              const uint64_t dak = da + (uint64_t)((row * p.bw * 128) >> 4);
+              const uint64_t dbk = descB + (uint64_t)(((ky * 3 + it) * Cfg::kBTileBytes) >> 4);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, dak + 2 * k, dbk + 2 * k, idesc, (uint32_t)((it | ky | k) != 0));
+            }
+            umma_commit(&empty[s]);
+          }
+          __syncwarp();
+          continue;
+        }
         const uint64_t db = da + (uint64_t)(kATileBytes >> 4);
         if (leader) {
 #pragma unroll
@@ -293,18 +333,18 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 int conv_sm_count() { return crfr_sm_count(); }
 
-template <int N>
+template <int N, bool R = false>
 int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const ConvParams& p, int tiles,
                 cudaStream_t st) {
-  using Cfg = ConvCfg<N>;
+  using Cfg = ConvCfg<N, R>;
   static std::atomic<unsigned long long> attr_done{0};
-  CRFR_CUDA((cudaError_t)crfr_smem_attr(tc_conv_kernel<N>, Cfg::kSmemBytes, attr_done));
+  CRFR_CUDA((cudaError_t)crfr_smem_attr(tc_conv_kernel<N, R>, Cfg::kSmemBytes, attr_done));
   // persistent over pixel tiles: about one CTA per SM in total (column tiles share the pixel-tile walk)
   const int ncol = p.n_total / N;
   int ctas = (conv_sm_count() + ncol - 1) / ncol;
   if (ctas > tiles) ctas = tiles;
   if (ctas < 1) ctas = 1;
-  tc_conv_kernel<N><<<dim3(ctas, ncol), kConvThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, tmY, p);
+  tc_conv_kernel<N, R><<<dim3(ctas, ncol), kConvThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, tmY, p);
   CRFR_COUNT_LAUNCH();
   CRFR_LAUNCH_CHECK();
   return CRFR_OK;
@@ -553,7 +593,13 @@ int crfr_tc_gemm(const TcGemm& g, cudaStream_t st) {
   }
   switch (tile_n) {
     case 32: return launch_conv<32>(tmA, tmB, tmY, p, tiles, st);
-    case 64: return launch_conv<64>(tmA, tmB, tmY, p, tiles, st);
+    case 64:
+      if (p.ksize == 3 && p.pad == 1 && p.kchunks == 1 && p.bn == 1 && (p.bw & 7) == 0 && (p.bh + 2) * p.bw <= 256) {
+        CUtensorMap tmA2;   // the box with its two halo rows
+        CRFR_TRY(make_act_map(&tmA2, g.src, g.n, g.h, g.w, g.k_total, g.src_ld, t.bw, t.bh + 2, 1));
+        return launch_conv<64, true>(tmA2, tmB, tmY, p, tiles, st);
+      }
+      return launch_conv<64>(tmA, tmB, tmY, p, tiles, st);
     case 96: return launch_conv<96>(tmA, tmB, tmY, p, tiles, st);
     case 128: return launch_conv<128>(tmA, tmB, tmY, p, tiles, st);
     case 192: return launch_conv<192>(tmA, tmB, tmY, p, tiles, st);
