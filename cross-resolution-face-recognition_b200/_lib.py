@@ -117,6 +117,7 @@ SIGNATURES = {
     "crfr_bn_update_running": (ci, [vp, vp, vp, vp, ci, cll, cf, cf, vp]),
     "crfr_bn_running_to_stats": (ci, [vp, vp, ci, cf, vp, vp]),
     "crfr_resnet34_workspace_bytes": (csz, [ci, ci, ci]),
+    "crfr_resnet34_tape": (ci, [ci, ci, ci, C.POINTER(TapeEntry), ci]),
     "crfr_resnet34_forward": (ci, [ci, vp, vp, C.POINTER(ResnetIO), vp, csz, vp]),
     "crfr_kd_workspace_bytes": (csz, [ci, ci]),
     "crfr_kd_workspace_bytes_ex": (csz, [ci, ci, ci]),

@@ -506,6 +506,33 @@ extern "C" size_t crfr_resnet34_workspace_bytes(int batch, int size, int trainin
   return net.off + 65536;
 }
 
+// Layout of the stored forward tensors of the ResNet_34 program in the workspace (a dry run: nothing is launched): one
+// entry per recorded op in program order - kind 0 convolution, 1 BatchNorm (+ residual) (+ ReLU), 7 linear head; out_off /
+// in_off / stats_off are bytes from the workspace base.  The parity tests read the stored bf16 activations through this
+// table and replay them into the CPU oracle (teacher-forced forward / backward checks, tests/test_resnet_forced_gpu.py).
+extern "C" int crfr_resnet34_tape(int batch, int size, int training, crfr_tape_entry* entries, int max_entries) {
+  if (batch <= 0 || size != 112) return -1;
+  crfr_resnet_io io = {};
+  io.batch = batch; io.size = size; io.training = training; io.momentum = 0.1f; io.eps = 1e-5f;
+  Net net;
+  init_net(net, CRFR_ENGINE_AUTO, nullptr, nullptr, nullptr, &io, nullptr, ~(size_t)0 >> 2, nullptr, false);
+  net.forward();
+  const int count = (int)net.tape.size();
+  for (int i = 0; i < count && i < max_entries && entries; ++i) {
+    const Op& op = net.tape[i];
+    crfr_tape_entry& e = entries[i];
+    const Tensor& t = op.out;
+    e.kind = op.kind == OP_CONV ? 0 : (op.kind == OP_BN ? 1 : 7);
+    e.n = t.n; e.h = t.h; e.w = t.w; e.c = t.c; e.ld = t.ld;
+    e.out_off = t.p ? (long long)((uint8_t*)t.p - (uint8_t*)nullptr) : -1;
+    e.in_off = op.a.p ? (long long)((uint8_t*)op.a.p - (uint8_t*)nullptr) : -1;
+    e.stats_off = op.stats ? (long long)((uint8_t*)op.stats - (uint8_t*)nullptr) : -1;
+    e.w_idx = op.w_idx;
+    e.has_res = op.has_res ? 1 : 0;
+  }
+  return count;
+}
+
 extern "C" int crfr_resnet34_forward(int engine, const float* const* host_params, void* const* host_buffers,
                                      const crfr_resnet_io* io, void* ws, size_t ws_bytes, void* stream) {
   CRFR_TRY(check_io(io, "resnet34_forward"));

@@ -347,6 +347,9 @@ typedef struct crfr_resnet_io {
  * order (running_mean fp32, running_var fp32, num_batches_tracked int64 per BatchNorm; NULL table in training mode
  * skips the buffer update). */
 size_t crfr_resnet34_workspace_bytes(int batch, int size, int training);
+/* Layout of the stored forward tensors of the ResNet_34 program (dry run), as crfr_fsrnet_tape: one entry per op in program
+ * order - kind 0 convolution, 1 BatchNorm (+ residual) (+ ReLU), 7 linear head.  For teacher-forced parity tests. */
+int crfr_resnet34_tape(int batch, int size, int training, crfr_tape_entry* entries, int max_entries);
 int crfr_resnet34_forward(int engine, const float* const* host_params, void* const* host_buffers,
                           const crfr_resnet_io* io, void* ws, size_t ws_bytes, void* stream);
 /* grads w.r.t. the embedding and the four stage features (fp32 NCHW, any may be NULL) -> accumulates into

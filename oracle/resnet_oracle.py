@@ -121,11 +121,11 @@ def _bn(pr, sd, p, y, training, relu, res=None, new_buffers=None):
     if res is not None:
         z = z + res
     z = pr.qg(z)
-    return pr.q(torch.relu(z) if relu else z)
+    return pr.st(torch.relu(z) if relu else z)          # a stored activation (ForcedPrecision substitutes it)
 
 
 def _conv(pr, x, w, stride, pad):
-    return pr.qb(F.conv2d(pr.qg(x), pr.q(w), None, stride, pad))
+    return pr.sb(F.conv2d(pr.qg(x), pr.q(w), None, stride, pad))
 
 
 def resnet34_forward(sd, x, training=True, pr=FP32, new_buffers=None):
@@ -148,7 +148,7 @@ def resnet34_forward(sd, x, training=True, pr=FP32, new_buffers=None):
         feats.append(a)
     o = _bn(pr, sd, "bn_o1.", a, training, False, None, new_buffers)
     o = o.reshape(o.shape[0], -1)
-    y = pr.qb(F.linear(pr.qg(o), pr.q(sd["fc.weight"]), sd["fc.bias"]))
+    y = pr.sb(F.linear(pr.qg(o), pr.q(sd["fc.weight"]), sd["fc.bias"]))
     emb = _bn(pr, sd, "bn_o2.", y, training, False, None, new_buffers)
     return (emb,) + tuple(feats)
 
