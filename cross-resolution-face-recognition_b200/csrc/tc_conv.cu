@@ -365,10 +365,15 @@ constexpr int kTile16K = 128 * 128;
 
 // TAPS = 3: one kernel row (ky) of a 3x3 conv per CTA, the three kx taps share the dY tile.  TAPS = 1: plain
 // [cin x cout] = X^T dY product (1x1 convs and the im2col-lowered edge layers).
-template <int N, int TAPS>
+// H (TAPS = 3, haloed box): one kernel COLUMN (kx) per CTA instead, from ONE X box that also holds the two halo rows,
+// (bh + 2) x bw pixels - the three ky taps are row offsets into it (the second M atom of the first MMA is simply bw pixel
+// rows further, LBO = bw x 128 B).  (bh + 2) x bw + 128 N / 64 TMA rows per step instead of 384 + 128 N / 64: the TMA request
+// rate bounds these kernels as it does the forward engine, and the smaller stage buys a deeper ring.
+template <int N, int TAPS, bool H = false>
 struct WgCfg {
   static constexpr int kDyTiles = N / 64;
-  static constexpr int kStageBytes = (TAPS + kDyTiles) * kTile16K;
+  static constexpr int kXBytes = H ? 2 * kTile16K : TAPS * kTile16K;
+  static constexpr int kStageBytes = kXBytes + kDyTiles * kTile16K;
   static constexpr int kStages = (kStageBytes <= 32 * 1024) ? 6 : (kStageBytes <= 48 * 1024) ? 4 : (kStageBytes <= 64 * 1024) ? 3 : 2;
   static constexpr int kAccs = (TAPS + 1) / 2;                     // accumulators of M = 128 (two taps each)
   static constexpr int kTmemCols = (kAccs * N <= 64) ? 64 : (kAccs * N <= 128) ? 128 : 256;
@@ -379,10 +384,10 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <int N, int TAPS>
+template <int N, int TAPS, bool H>
 __global__ void __launch_bounds__(kConvThreads, 1)
 tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY, WgradParams p) {
-  using Cfg = WgCfg<N, TAPS>;
+  using Cfg = WgCfg<N, TAPS, H>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full = (uint64_t*)(base + Cfg::kStages * Cfg::kStageBytes);
@@ -402,7 +407,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     prefetch_tmap(&tmDY);
   }
   if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
-  if (p.rows < 128) {
+  if (p.rows < 128 || H) {
     // pixels are the K dimension: the rows of a 128-row tile that the (smaller) TMA box never writes must read as
     // zero, so clear the whole ring once
     for (int i = threadIdx.x; i < Cfg::kStages * Cfg::kStageBytes / 16; i += kConvThreads)
@@ -414,10 +419,11 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  // TAPS == 3: blockIdx.y = ky + 3 * column tile;  TAPS == 1: blockIdx.y = column tile of dY
+  // TAPS == 3: blockIdx.y = ky (H: kx) + 3 * column tile;  TAPS == 1: blockIdx.y = column tile of dY
   const int ky = TAPS == 3 ? blockIdx.y % 3 : 0, kc = blockIdx.z;
   const int ncol0 = (TAPS == 3 ? blockIdx.y / 3 : blockIdx.y) * N;
-  const uint32_t stage_tx = (uint32_t)(TAPS + Cfg::kDyTiles) * (uint32_t)p.rows * 128u;
+  const uint32_t stage_tx = H ? (uint32_t)((p.bh + 2) * p.bw + Cfg::kDyTiles * p.rows) * 128u
+                              : (uint32_t)(TAPS + Cfg::kDyTiles) * (uint32_t)p.rows * 128u;
   const int first = blockIdx.x, step = gridDim.x;
   const int my_tiles = first < p.total_tiles ? (p.total_tiles - first + step - 1) / step : 0;
 
@@ -433,7 +439,9 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       uint8_t* sb = base + s * Cfg::kStageBytes;
       if (leader) {
         mbar_expect_tx(&full[s], stage_tx);
-        if (TAPS == 3) {
+        if (H) {   // `ky` is this CTA's kx: the box of rows y0 - 1 .. y0 + bh at its x shift
+          tma_load_4d(sb, &tmX, &full[s], kc * 64, x0 + ky - 1, y0 - 1, n0);
+        } else if (TAPS == 3) {
 #pragma unroll
           for (int kx = 0; kx < 3; ++kx)
             tma_load_4d(sb + kx * kTile16K, &tmX, &full[s], kc * 64, x0 + kx - 1, y0 + ky - 1, n0);
@@ -442,7 +450,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         }
 #pragma unroll
         for (int j = 0; j < Cfg::kDyTiles; ++j)
-          tma_load_4d(sb + (TAPS + j) * kTile16K, &tmDY, &full[s], ncol0 + j * 64, x0, y0, n0);
+          tma_load_4d(sb + Cfg::kXBytes + j * kTile16K, &tmDY, &full[s], ncol0 + j * 64, x0, y0, n0);
       }
     }
   } else if (warp == 1) {
@@ -450,14 +458,17 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     const uint32_t idesc = make_idesc_bf16(128, N, 1, 1);
     // M = 128 = two 64-channel atoms LBO (= one 16 KB tile) apart: taps (0,1) in the first MMA; the second atom of
     // the last MMA is whatever tile follows (rows 64..127 of that accumulator are never read)
-    const uint64_t desc0 = make_smem_desc_sw128(smem_u32(base), kTile16K, 1024);
+    // (H: the atoms are the ky = 0 / 1 / 2 views of one box, bw pixel rows apart; dY keeps its 16 KB tiles)
+    const uint32_t x_lbo = H ? (uint32_t)p.bw * 128u : (uint32_t)kTile16K;
+    const uint64_t desc0 = make_smem_desc_sw128(smem_u32(base), x_lbo, 1024);
+    const uint64_t descB = make_smem_desc_sw128(smem_u32(base), kTile16K, 1024);
     for (int i = 0; i < my_tiles; ++i) {
       const int s = i % Cfg::kStages;
       mbar_wait(&full[s], (i / Cfg::kStages) & 1);
       tc_fence_after();
       const uint64_t a01 = desc0 + (uint64_t)((s * Cfg::kStageBytes) >> 4);
-      const uint64_t a2x = a01 + (uint64_t)((2 * kTile16K) >> 4);
-      const uint64_t db = a01 + (uint64_t)((TAPS * kTile16K) >> 4);
+      const uint64_t a2x = a01 + (uint64_t)((2 * x_lbo) >> 4);
+      const uint64_t db = descB + (uint64_t)((s * Cfg::kStageBytes + Cfg::kXBytes) >> 4);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {  // 8 x 16 pixels
         const uint32_t acc = (uint32_t)((i | k) != 0);
@@ -478,9 +489,10 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     const int ci = kc * 64 + (r & 63);
 #pragma unroll
     for (int half = 0; half < Cfg::kAccs; ++half) {
-      const int kx = half == 0 ? (r >> 6) : 2;
+      const int kx = half == 0 ? (r >> 6) : 2;                          // (H: this is the tap's ky, and `ky` its kx)
       const bool live = TAPS == 3 ? (half == 0 || r < 64) : (r < 64);   // warp-uniform (32-row granularity)
-      float* dst = p.G + ((long long)(TAPS == 3 ? ky * 3 + kx : 0) * p.cin + ci) * p.cout + ncol0;
+      const int tap = TAPS == 3 ? (H ? kx * 3 + ky : ky * 3 + kx) : 0;
+      float* dst = p.G + ((long long)tap * p.cin + ci) * p.cout + ncol0;
 #pragma unroll
       for (int c0 = 0; c0 < N; c0 += 32) {
         uint32_t v[32];
@@ -515,13 +527,13 @@ __global__ void wgrad_unpack_kernel(const float* __restrict__ G, float* __restri
   dw[i] += G[((long long)t * cin + ci) * cout + co];
 }
 
-template <int N, int TAPS>
+template <int N, int TAPS, bool H = false>
 int launch_wgrad(const CUtensorMap& tmX, const CUtensorMap& tmDY, const WgradParams& p, int splits, cudaStream_t st) {
-  using Cfg = WgCfg<N, TAPS>;
+  using Cfg = WgCfg<N, TAPS, H>;
   static std::atomic<unsigned long long> attr_done{0};
-  CRFR_CUDA((cudaError_t)crfr_smem_attr(tc_wgrad_kernel<N, TAPS>, Cfg::kSmemBytes, attr_done));
+  CRFR_CUDA((cudaError_t)crfr_smem_attr(tc_wgrad_kernel<N, TAPS, H>, Cfg::kSmemBytes, attr_done));
   const int gy = (TAPS == 3 ? 3 : 1) * (p.cout / N);
-  tc_wgrad_kernel<N, TAPS><<<dim3(splits, gy, p.cin / 64), kConvThreads, Cfg::kSmemBytes, st>>>(tmX, tmDY, p);
+  tc_wgrad_kernel<N, TAPS, H><<<dim3(splits, gy, p.cin / 64), kConvThreads, Cfg::kSmemBytes, st>>>(tmX, tmDY, p);
   CRFR_COUNT_LAUNCH();
   CRFR_LAUNCH_CHECK();
   return CRFR_OK;
@@ -634,6 +646,12 @@ int crfr_tc_wgrad_raw(const TcWgrad& g, cudaStream_t st) {
   if (splits > p.total_tiles) splits = p.total_tiles;
   if (splits < 1) splits = 1;
   if (g.taps3x3) {
+    if (t.bn == 1 && (t.bw & 7) == 0 && (t.bh + 2) * t.bw <= 256 && (g.cout == 64 || g.cout % 128 == 0)) {
+      CUtensorMap tmXh;   // the X box with its two halo rows
+      CRFR_TRY(make_act_map(&tmXh, g.x, g.n, g.h, g.w, g.cin, g.x_ld, t.bw, t.bh + 2, 1));
+      if (g.cout == 64) return launch_wgrad<64, 3, true>(tmXh, tmDY, p, splits, st);
+      return launch_wgrad<128, 3, true>(tmXh, tmDY, p, splits, st);
+    }
     if (g.cout == 64) return launch_wgrad<64, 3>(tmX, tmDY, p, splits, st);
     if (g.cout % 128 == 0) return launch_wgrad<128, 3>(tmX, tmDY, p, splits, st);
     crfr_set_error("tc_wgrad: 3x3 needs cout 64 or a multiple of 128, got %d", g.cout);
