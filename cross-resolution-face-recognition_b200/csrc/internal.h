@@ -23,6 +23,7 @@ enum {
   CRFR_OPT_FUSE_NORM_BWD,    // crfr_conv_dgrad_norm_bwd: first pass of the normalisation backward in the dgrad epilogue
   CRFR_OPT_FUSE_NORM_FWD,    // crfr_norm_act_conv_fwd: normalise + activate inside the convolution's producer warps
   CRFR_OPT_PDL,              // programmatic dependent launch of the persistent kernels (common.cuh)
+  CRFR_OPT_TC_T2,            // tile engine, N = 128: two pixel tiles per weight tile
   CRFR_OPT_PAIR_DEBUG,       // ablation bits for tools/pair_diag.py (results are WRONG when set): 1 no loads, 2 no MMAs,
                              // 4 no pack / store / statistics, 8 no store, 16 no statistics
   CRFR_OPT_COUNT

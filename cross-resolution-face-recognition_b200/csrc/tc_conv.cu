@@ -97,39 +97,46 @@ constexpr int kATileBytes = 128 * 128;
 // rows, (bh + 2) x bw pixels: the three ky taps of a kx are row offsets into the same box (bw % 8 == 0 keeps the offsets on
 // swizzle-atom boundaries).  576 rows per tile instead of 1 152, 3 ring steps of 12 MMAs instead of 9 of 4.
 constexpr int kResidentIters = 9;
-template <int N, bool R = false>
+// MODE 0: generic; 1: R (above); 2: T2 - TWO pixel tiles per weight tile: a ring step loads the activation tiles of two
+// consecutive pixel tiles of the CTA and ONE weight tile, and issues the MMAs of both (four TMEM accumulators: the pair being
+// computed and the pair in the epilogue): 384 instead of 512 TMA rows per two (tap, K chunk) steps at N = 128.
+template <int N, int MODE = 0>
 struct ConvCfg {
+  static constexpr bool R = MODE == 1, T2 = MODE == 2;
   static constexpr int kBTileBytes = N * 128;
-  static constexpr int kStageBytes = R ? 2 * kATileBytes : kATileBytes + kBTileBytes;   // R: up to 256 pixel rows (box + halo)
+  static constexpr int kStageBytes = R ? 2 * kATileBytes : (T2 ? 2 : 1) * kATileBytes + kBTileBytes;   // R: up to 256 pixel rows (box + halo)
   // stages: the K loops are short (9-72 steps per tile) and every step is a TMA round trip to L2 (~1 us): the ring is as deep
   // as the 227 KB of shared memory allow beside the staging tile (24 / 32 / 48 KB per stage)
-  static constexpr int kStages = R ? 4 : (N <= 64) ? 8 : (N <= 128) ? 6 : 3;
+  static constexpr int kStages = (R || T2) ? 4 : (N <= 64) ? 8 : (N <= 128) ? 6 : 3;
+  static constexpr int kAccBufs = T2 ? 4 : 2;
   static constexpr int kResidentBytes = R ? kResidentIters * kBTileBytes : 0;
   static constexpr int kTmemCols = (N <= 32) ? 32 : (N <= 64) ? 64 : (N <= 128) ? 128 : 256;
   static constexpr int kOutTiles = (N + 63) / 64;               // 64-channel sub-tiles staged for the TMA store
   static constexpr int kOutBytes = kOutTiles * kATileBytes;
   static constexpr int kSmemBytes = kStages * kStageBytes + kResidentBytes + kOutBytes + 1024 /*align slack*/ + 256 /*barriers*/;
-  static_assert(N % 32 == 0 && N <= 256 && 2 * kTmemCols <= 512, "tile width");
+  static_assert(N % 32 == 0 && N <= 256 && kAccBufs * kTmemCols <= 512, "tile width");
   static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
 
 // Persistent: the grid is (CTAs, column tiles); a CTA walks pixel tiles blockIdx.x, blockIdx.x + gridDim.x, ... so
 // that barrier setup / TMEM allocation are paid once and - with two TMEM accumulators - the epilogue of tile i
 // overlaps the TMA + MMA work of tile i+1 (the layers on this kernel have short K loops: 9-72 steps per tile).
-template <int N, bool R>
+template <int N, int MODE>
 __global__ void __launch_bounds__(kConvThreads, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmY, ConvParams p) {   // R: tmA has the box with the halo rows
-  using Cfg = ConvCfg<N, R>;
+  using Cfg = ConvCfg<N, MODE>;
+  constexpr bool R = Cfg::R, T2 = Cfg::T2;
+  constexpr int kAB = Cfg::kAccBufs;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sB = base + Cfg::kStages * Cfg::kStageBytes;          // R: resident weight tiles [iters][N][64]
   uint8_t* sOut = sB + Cfg::kResidentBytes;
   uint64_t* full = (uint64_t*)(sOut + Cfg::kOutBytes);
   uint64_t* empty = full + Cfg::kStages;
-  uint64_t* tmem_full = empty + Cfg::kStages;   // [2]
-  uint64_t* tmem_empty = tmem_full + 2;         // [2]
-  uint64_t* w_full = tmem_empty + 2;            // R: the resident weights have landed
+  uint64_t* tmem_full = empty + Cfg::kStages;   // [kAB]
+  uint64_t* tmem_empty = tmem_full + kAB;       // [kAB]
+  uint64_t* w_full = tmem_empty + kAB;          // R: the resident weights have landed
   uint32_t* tmem_slot = (uint32_t*)(w_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -138,7 +145,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < kAB; ++b) {
       mbar_init(&tmem_full[b], 1);
       mbar_init(&tmem_empty[b], 4);
     }
@@ -148,7 +155,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     prefetch_tmap(&tmB);
     prefetch_tmap(&tmY);
   }
-  if (warp == 1) tmem_alloc<2 * Cfg::kTmemCols>(tmem_slot);
+  if (warp == 1) tmem_alloc<kAB * Cfg::kTmemCols>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -167,11 +174,16 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tma_load_2d(sB + tap * Cfg::kBTileBytes, &tmB, w_full, 0, tap * p.n_total + ncol0);
     }
     int g = 0;   // running stage index across tiles
-    for (int i = 0; i < my_tiles; ++i) {
+    for (int i = 0; i < my_tiles; i += T2 ? 2 : 1) {
       int t = blockIdx.x + i * gridDim.x;
       const int tx = t % p.tiles_x; t /= p.tiles_x;
       const int ty = t % p.tiles_y; t /= p.tiles_y;
       const int x0 = tx * p.bw, y0 = ty * p.bh, n0 = t * p.bn;
+      // T2: the second pixel tile of the pair (the first one again where the CTA's tile count is odd: its result is dropped)
+      int t1 = blockIdx.x + (i + 1 < my_tiles ? i + 1 : i) * gridDim.x;
+      const int tx1 = t1 % p.tiles_x; t1 /= p.tiles_x;
+      const int ty1 = t1 % p.tiles_y; t1 /= p.tiles_y;
+      const int x1 = tx1 * p.bw, y1 = ty1 * p.bh, n1 = t1 * p.bn;
       for (int it = 0; it < iters; ++it, ++g) {
         const int s = g % Cfg::kStages;
         mbar_wait(&empty[s], ((g / Cfg::kStages) & 1) ^ 1);
@@ -186,9 +198,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
         const int ky = tap / p.ksize, kx = tap - ky * p.ksize;
         if (leader) {
-          mbar_expect_tx(&full[s], a_bytes + (uint32_t)Cfg::kBTileBytes);
+          mbar_expect_tx(&full[s], (T2 ? 2u : 1u) * a_bytes + (uint32_t)Cfg::kBTileBytes);
           tma_load_4d(sa, &tmA, &full[s], kc * 64, x0 + p.sign * (kx - p.pad), y0 + p.sign * (ky - p.pad), n0);
-          tma_load_2d(sa + kATileBytes, &tmB, &full[s], kc * 64, tap * p.n_total + ncol0);
+          if (T2) tma_load_4d(sa + kATileBytes, &tmA, &full[s], kc * 64, x1 + p.sign * (kx - p.pad), y1 + p.sign * (ky - p.pad), n1);
+          tma_load_2d(sa + (T2 ? 2 : 1) * kATileBytes, &tmB, &full[s], kc * 64, tap * p.n_total + ncol0);
         }
       }
     }
@@ -199,9 +212,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint64_t descB = make_smem_desc_sw128(smem_u32(sB), 16, 1024);
     if (R && my_tiles > 0) mbar_wait(w_full, 0);
     int g = 0;
-    for (int i = 0; i < my_tiles; ++i) {
-      const int buf = i & 1;
-      mbar_wait(&tmem_empty[buf], ((i >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator
+    for (int i = 0; i < my_tiles; i += T2 ? 2 : 1) {
+      // accumulator of tile i: generic i & 1 (use i >> 1); T2: pair j = i / 2 owns buffers 2 (j & 1) + {0, 1} (use j >> 1)
+      const int buf = T2 ? ((i >> 1) & 1) * 2 : (i & 1);
+      const uint32_t use = T2 ? (uint32_t)(i >> 2) : (uint32_t)(i >> 1);
+      mbar_wait(&tmem_empty[buf], (use & 1) ^ 1);   // the epilogue has drained this accumulator
+      if (T2) mbar_wait(&tmem_empty[buf + 1], (use & 1) ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem + buf * Cfg::kTmemCols;
       for (int it = 0; it < iters; ++it, ++g) {
@@ -224,15 +240,24 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           __syncwarp();
           continue;
         }
-        const uint64_t db = da + (uint64_t)(kATileBytes >> 4);
+        const uint64_t db = da + (uint64_t)(((T2 ? 2 : 1) * kATileBytes) >> 4);
         if (leader) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (uint32_t)((it | k) != 0));
+          if (T2) {
+            const uint64_t da1 = da + (uint64_t)(kATileBytes >> 4);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(d_tmem + Cfg::kTmemCols, da1 + 2 * k, db + 2 * k, idesc, (uint32_t)((it | k) != 0));
+          }
           umma_commit(&empty[s]);
         }
         __syncwarp();
       }
-      if (leader) umma_commit(&tmem_full[buf]);
+      if (leader) {
+        umma_commit(&tmem_full[buf]);
+        if (T2) umma_commit(&tmem_full[buf + 1]);
+      }
       __syncwarp();
     }
   } else {
@@ -244,7 +269,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const float* bias = p.bias ? p.bias + ncol0 : nullptr;
     const bool issuer = warp == 2 && lane == 0;
     for (int i = 0; i < my_tiles; ++i) {
-      const int buf = i & 1;
+      const int buf = T2 ? ((i >> 1) & 1) * 2 + (i & 1) : (i & 1);
+      const uint32_t use = T2 ? (uint32_t)(i >> 2) : (uint32_t)(i >> 1);
       int t = blockIdx.x + i * gridDim.x;
       const int tx = t % p.tiles_x; t /= p.tiles_x;
       const int ty = t % p.tiles_y; t /= p.tiles_y;
@@ -253,7 +279,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool valid = r < p.rows && x < p.w && y < p.h && n < p.n;
       const long long pix = ((long long)n * p.h + y) * p.w + x;
       float* dstf = (float*)p.out + pix * p.out_ld + ncol0;
-      mbar_wait(&tmem_full[buf], (i >> 1) & 1);
+      mbar_wait(&tmem_full[buf], use & 1);
       tc_fence_after();
       if (!p.out_f32) {
         // the TMA store of the previous tile must have finished reading the staging buffer
@@ -327,24 +353,24 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<2 * Cfg::kTmemCols>(tmem);
+    tmem_dealloc<kAB * Cfg::kTmemCols>(tmem);
   }
 }
 
 int conv_sm_count() { return crfr_sm_count(); }
 
-template <int N, bool R = false>
+template <int N, int MODE = 0>
 int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY, const ConvParams& p, int tiles,
                 cudaStream_t st) {
-  using Cfg = ConvCfg<N, R>;
+  using Cfg = ConvCfg<N, MODE>;
   static std::atomic<unsigned long long> attr_done{0};
-  CRFR_CUDA((cudaError_t)crfr_smem_attr(tc_conv_kernel<N, R>, Cfg::kSmemBytes, attr_done));
+  CRFR_CUDA((cudaError_t)crfr_smem_attr(tc_conv_kernel<N, MODE>, Cfg::kSmemBytes, attr_done));
   // persistent over pixel tiles: about one CTA per SM in total (column tiles share the pixel-tile walk)
   const int ncol = p.n_total / N;
   int ctas = (conv_sm_count() + ncol - 1) / ncol;
   if (ctas > tiles) ctas = tiles;
   if (ctas < 1) ctas = 1;
-  tc_conv_kernel<N, R><<<dim3(ctas, ncol), kConvThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, tmY, p);
+  tc_conv_kernel<N, MODE><<<dim3(ctas, ncol), kConvThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, tmY, p);
   CRFR_COUNT_LAUNCH();
   CRFR_LAUNCH_CHECK();
   return CRFR_OK;
@@ -609,11 +635,13 @@ int crfr_tc_gemm(const TcGemm& g, cudaStream_t st) {
       if (p.ksize == 3 && p.pad == 1 && p.kchunks == 1 && p.bn == 1 && (p.bw & 7) == 0 && (p.bh + 2) * p.bw <= 256) {
         CUtensorMap tmA2;   // the box with its two halo rows
         CRFR_TRY(make_act_map(&tmA2, g.src, g.n, g.h, g.w, g.k_total, g.src_ld, t.bw, t.bh + 2, 1));
-        return launch_conv<64, true>(tmA2, tmB, tmY, p, tiles, st);
+        return launch_conv<64, 1>(tmA2, tmB, tmY, p, tiles, st);
       }
       return launch_conv<64>(tmA, tmB, tmY, p, tiles, st);
     case 96: return launch_conv<96>(tmA, tmB, tmY, p, tiles, st);
-    case 128: return launch_conv<128>(tmA, tmB, tmY, p, tiles, st);
+    case 128:
+      if (crfr_opt(CRFR_OPT_TC_T2) && tiles >= 4 * conv_sm_count()) return launch_conv<128, 2>(tmA, tmB, tmY, p, tiles, st);
+      return launch_conv<128>(tmA, tmB, tmY, p, tiles, st);
     case 192: return launch_conv<192>(tmA, tmB, tmY, p, tiles, st);
     case 224: return launch_conv<224>(tmA, tmB, tmY, p, tiles, st);
     case 256: return launch_conv<256>(tmA, tmB, tmY, p, tiles, st);

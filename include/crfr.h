@@ -37,6 +37,8 @@ unsigned long long crfr_launch_count(void);
  *   "norm_bwd_impl": crfr_norm_act_bwd as 0 = register-staged reduce + fold + apply kernels, 1 = persistent TMA-fed
  *                    reduce + fold + apply kernels (default where the views are TMA-addressable: channels a multiple
  *                    of 64, 16-byte aligned), -1 = default / environment CRFR_NORM_BWD=regs|stream.
+ *   "tc_t2": tile engine at N = 128 as 0 = one pixel tile per weight tile, 1 = two (default; fewer TMA requests).
+ *   "pdl": programmatic dependent launch of the persistent kernels, 0 (default) / 1.
  *   "fuse_norm_fwd": crfr_norm_act_conv_fwd as 0 = crfr_norm_act_fwd + crfr_conv_fwd (default), 1 = normalisation inside
  *                    the convolution's producer warps where the row-streaming pair kernel runs (identical bits; measured
  *                    SLOWER on B200, 208 us against 193 us per 128-image layer: the SM's instruction issue slots, which the
