@@ -32,7 +32,7 @@ const OptDef kOpts[CRFR_OPT_COUNT] = {
     {"pair_swap", "CRFR_PAIR_SWAP", 0},       {"wgrad_stream", "CRFR_WGRAD_STREAM", 1},
     {"norm_bwd_impl", "CRFR_NORM_BWD", 1},    {"norm_fwd_stream", "CRFR_NORM_FWD_STREAM", 1},
     {"rowwgrad_pair", "CRFR_ROWWGRAD_PAIR", 1}, {"fuse_norm_bwd", "CRFR_FUSE_NORM_BWD", 1},
-    {"fuse_norm_fwd", "CRFR_FUSE_NORM_FWD", 0}, {"pdl", "CRFR_PDL", 0}, {"tc_t2", "CRFR_TC_T2", 1},
+    {"fuse_norm_fwd", "CRFR_FUSE_NORM_FWD", 0}, {"pdl", "CRFR_PDL", 0}, {"tc_t2", "CRFR_TC_T2", 1}, {"bn_fused_stats", "CRFR_BN_FUSED_STATS", 1},
     {"pair_debug", "CRFR_PAIR_DEBUG", 0}};
 std::atomic<int> g_opt[CRFR_OPT_COUNT];
 std::atomic<int> g_opt_init{0};
@@ -156,6 +156,17 @@ extern "C" int crfr_conv_fwd(int engine, const crfr_conv_desc* d, const void* x,
                                 d->cout, cin_pad, bias, y, d->out_ld, y_nchw, st));
   if (stats) CRFR_TRY(crfr_norm_stats(y, d->n, d->oh * d->ow, d->cout, d->out_ld, eps, stats, ws, ws_bytes, stream));
   return CRFR_OK;
+}
+
+int crfr_conv_fwd_bnstats(int engine, const crfr_conv_desc* d, const void* x, const void* w_packed, int cin_pad, void* y,
+                          float* bn_stats, float eps, void* ws, size_t ws_bytes, cudaStream_t st) {
+  const long long count = (long long)d->n * d->oh * d->ow;
+  if (crfr_opt(CRFR_OPT_BN_FUSED_STATS) && engine != CRFR_ENGINE_DIRECT && !d->transposed && cin_pad == d->cin &&
+      crfr_lowered_recipe(d) == 0 && crfr_tc_supported(0, d->h, d->w, d->cin, d->cout, d->k, d->stride, d->pad) &&
+      count < (1ll << 31))
+    return crfr_tc_conv(d, 0, x, w_packed, nullptr, y, bn_stats, eps, ws, ws_bytes, st, 1);
+  CRFR_TRY(crfr_conv_fwd(engine, d, x, w_packed, cin_pad, nullptr, y, nullptr, nullptr, eps, ws, ws_bytes, (void*)st));
+  return crfr_norm_stats(y, 1, (int)count, d->cout, d->out_ld, eps, bn_stats, ws, ws_bytes, (void*)st);
 }
 
 extern "C" int crfr_conv_dgrad(int engine, const crfr_conv_desc* d, const void* dy, const void* w_packed_t,

@@ -24,6 +24,7 @@ enum {
   CRFR_OPT_FUSE_NORM_FWD,    // crfr_norm_act_conv_fwd: normalise + activate inside the convolution's producer warps
   CRFR_OPT_PDL,              // programmatic dependent launch of the persistent kernels (common.cuh)
   CRFR_OPT_TC_T2,            // tile engine, N = 128: two pixel tiles per weight tile
+  CRFR_OPT_BN_FUSED_STATS,   // ResNet program: train-mode BatchNorm statistics from the tile engine's epilogue
   CRFR_OPT_PAIR_DEBUG,       // ablation bits for tools/pair_diag.py (results are WRONG when set): 1 no loads, 2 no MMAs,
                              // 4 no pack / store / statistics, 8 no store, 16 no statistics
   CRFR_OPT_COUNT
@@ -120,6 +121,9 @@ struct TcGemm {           // out[pixel][n] = bias[n] + sum_{tap,k} src[pixel + s
   // optional fused InstanceNorm statistics of the stored bf16 output: partial sums [n][slots][2][n_total] are written
   // to stat_ws when the tiling allows it and *stat_slots is set to the slot count (0: not fused, caller runs a pass)
   float* stat_ws = nullptr; size_t stat_ws_bytes = 0; int* stat_slots = nullptr;
+  // stat_batch: ONE statistic group over the whole batch (BatchNorm): partial sums [1][tiles x 4][2][n_total], any tiling (rows
+  // of a tile that lie outside the tensor are masked out); needs bias == nullptr
+  int stat_batch = 0;
 };
 int crfr_tc_gemm(const TcGemm& g, cudaStream_t st);
 struct TcWgrad {          // G[tap][ci][co] += sum_pixel x[pixel + tap - 1][ci] * dy[pixel][co]   (fp32, caller zeroes G)
@@ -134,7 +138,11 @@ int crfr_tc_wgrad_raw(const TcWgrad& g, cudaStream_t st);
 int crfr_tc_supported(int op, int h, int w, int cin, int cout, int k, int stride, int pad);
 size_t crfr_tc_workspace_bytes(const crfr_conv_desc* d);
 int crfr_tc_conv(const crfr_conv_desc* d, int dgrad, const void* src, const void* w_packed, const float* bias,
-                 void* dst, float* stats, float eps, void* ws, size_t ws_bytes, cudaStream_t st);
+                 void* dst, float* stats, float eps, void* ws, size_t ws_bytes, cudaStream_t st, int batch_stats = 0);
+// conv_api.cu: forward convolution (no bias, bf16 output) + train-mode BatchNorm statistics [cout][2] = (mean, rstd) over
+// the whole batch, from the convolution's epilogue where the tile engine runs the layer (else a separate pass)
+int crfr_conv_fwd_bnstats(int engine, const crfr_conv_desc* d, const void* x, const void* w_packed, int cin_pad, void* y,
+                          float* bn_stats, float eps, void* ws, size_t ws_bytes, cudaStream_t st);
 int crfr_tc_wgrad(const crfr_conv_desc* d, const void* x, const void* dy, float* dw, void* ws, size_t ws_bytes,
                   cudaStream_t st);
 

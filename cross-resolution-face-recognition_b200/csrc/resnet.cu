@@ -25,6 +25,7 @@ struct Tensor {
   bf16* p = nullptr;
   int n = 0, h = 0, w = 0, c = 0, ld = 0;
   int id = -1;
+  float* bn_stats = nullptr;   // train-mode BatchNorm statistics of a convolution output, computed by its epilogue
 };
 struct Slot {
   bf16* p;
@@ -165,10 +166,16 @@ struct Net {
     const int T = k * k;
     void* wpk = alloc((size_t)T * cout * op.cin_pad * sizeof(bf16));
     if (collect && ok()) collect->push_back({params[w_idx], wpk, T, cout, x.c, op.cin_pad, (long long)x.c * T, T, 0, 0});
+    // every convolution of this network feeds a BatchNorm: in training its batch statistics come out of the epilogue
+    float* bn_stats = io->training ? (float*)alloc((size_t)cout * 2 * sizeof(float)) : nullptr;
+    y.bn_stats = bn_stats;
     if (run()) {
       if (!packs_done) check(crfr_pack_weight(params[w_idx], wpk, T, cout, x.c, op.cin_pad, (long long)x.c * T, T, 1, st));
-      check(crfr_conv_fwd(engine, &d, x.p, wpk, op.cin_pad, nullptr, y.p, nullptr, nullptr, io->eps, scratch,
-                          scratch_bytes, st));
+      if (bn_stats)
+        check(crfr_conv_fwd_bnstats(engine, &d, x.p, wpk, op.cin_pad, y.p, bn_stats, io->eps, scratch, scratch_bytes, st));
+      else
+        check(crfr_conv_fwd(engine, &d, x.p, wpk, op.cin_pad, nullptr, y.p, nullptr, nullptr, io->eps, scratch,
+                            scratch_bytes, st));
     }
     op.a = x; op.out = y; op.w_idx = w_idx; op.x_needs_grad = x_needs_grad;
     tape.push_back(op);
@@ -180,13 +187,14 @@ struct Net {
     const int bi = bn_index >= 0 ? bn_index : bncur++;
     const long long count = (long long)y.n * y.h * y.w;
     Tensor out = new_tensor(y.n, y.h, y.w, y.c);
-    float* stats = (float*)alloc((size_t)y.c * 2 * sizeof(float));
+    const bool have_stats = io->training && y.bn_stats;   // computed by the producing convolution's epilogue
+    float* stats = have_stats ? y.bn_stats : (float*)alloc((size_t)y.c * 2 * sizeof(float));
     float* rmean = buffers ? (float*)buffers[3 * bi] : nullptr;
     float* rvar = buffers ? (float*)buffers[3 * bi + 1] : nullptr;
     long long* nbt = buffers ? (long long*)buffers[3 * bi + 2] : nullptr;
     if (run()) {
       if (io->training) {
-        check(crfr_norm_stats(y.p, 1, (int)count, y.c, y.ld, io->eps, stats, scratch, scratch_bytes, st));
+        if (!have_stats) check(crfr_norm_stats(y.p, 1, (int)count, y.c, y.ld, io->eps, stats, scratch, scratch_bytes, st));
         if (rmean && rvar)
           check(crfr_bn_update_running(stats, rmean, rvar, nbt, y.c, count, io->momentum, io->eps, st));
       } else {

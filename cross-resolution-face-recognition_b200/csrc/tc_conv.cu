@@ -268,6 +268,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int ih = rr % p.bh, in = rr / p.bh;
     const float* bias = p.bias ? p.bias + ncol0 : nullptr;
     const bool issuer = warp == 2 && lane == 0;
+    float bsum[Cfg::kOutTiles][4];   // batch statistics (BatchNorm): running sums of this thread's channel pair and row group
+#pragma unroll
+    for (int t2 = 0; t2 < Cfg::kOutTiles; ++t2) bsum[t2][0] = bsum[t2][1] = bsum[t2][2] = bsum[t2][3] = 0.f;
     for (int i = 0; i < my_tiles; ++i) {
       const int buf = T2 ? ((i >> 1) & 1) * 2 + (i & 1) : (i & 1);
       const uint32_t use = T2 ? (uint32_t)(i >> 2) : (uint32_t)(i >> 1);
@@ -325,9 +328,17 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // InstanceNorm statistics of the stored (rounded) values, from the staged tile: thread = (channel pair,
           // 32-row group); a warp reads one 128-byte row per step (conflict free).  Every group lies inside one image;
           // its sums go to a fixed (image, tile, group) slot and are folded in fixed order by crfr_norm_finalize.
+          // Batch mode (gpt < 0, BatchNorm: one group over the whole batch): slot = (pixel tile, group), any tiling; the
+          // rows of the tile that lie outside the tensor hold values that are never stored and are masked out.
           const int et = (warp - 2) * 32 + lane, cp = et & 31, pg = et >> 5;
-          const int img = n0 + (pg * 32) / (p.bw * p.bh);
-          const int slot = (ty * p.tiles_x + tx) * p.gpt + pg % p.gpt;
+          const bool batch = p.gpt < 0;
+          uint32_t vmask = 0xffffffffu;   // bit k: row pg * 32 + k of the tile lies inside the tensor (pg is NOT this warp's
+          if (batch) {                    // TMEM quadrant q: the statistics walk the staged tile, not the accumulator)
+            const int r2 = pg * 32 + lane, rr2 = r2 / p.bw;
+            vmask = __ballot_sync(0xffffffffu, r2 < p.rows && x0 + r2 % p.bw < p.w && y0 + rr2 % p.bh < p.h && n0 + rr2 / p.bh < p.n);
+          }
+          const int img = batch ? 0 : n0 + (pg * 32) / (p.bw * p.bh);
+          const int slot = batch ? 0 : (ty * p.tiles_x + tx) * p.gpt + pg % p.gpt;
           float* dst = p.partial + ((long long)img * p.slots + slot) * 2 * p.n_total + ncol0 + 2 * cp;
           if (img < p.n)
 #pragma unroll
@@ -336,15 +347,29 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 8
             for (int k = 0; k < 32; ++k) {
               const int px = pg * 32 + k;
-              const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(
+              float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(
                   sOut + t2 * kATileBytes + px * 128 + ((((cp >> 2) ^ (px & 7)) << 4) | ((cp & 3) << 2))));
+              if (!((vmask >> k) & 1u)) f = make_float2(0.f, 0.f);
               s0 += f.x; q0 = fmaf(f.x, f.x, q0);
               s1 += f.y; q1 = fmaf(f.y, f.y, q1);
             }
-            *reinterpret_cast<float2*>(dst + t2 * 64) = make_float2(s0, s1);
-            *reinterpret_cast<float2*>(dst + p.n_total + t2 * 64) = make_float2(q0, q1);
+            if (batch) {   // one running sum per (CTA, row group) over all of the CTA's tiles, written once at the end
+              bsum[t2][0] += s0; bsum[t2][1] += s1; bsum[t2][2] += q0; bsum[t2][3] += q1;
+            } else {
+              *reinterpret_cast<float2*>(dst + t2 * 64) = make_float2(s0, s1);
+              *reinterpret_cast<float2*>(dst + p.n_total + t2 * 64) = make_float2(q0, q1);
+            }
           }
         }
+      }
+    }
+    if (p.partial && p.gpt < 0) {   // batch statistics: slot = (CTA, row group)
+      const int et = (warp - 2) * 32 + lane, cp = et & 31, pg = et >> 5;
+      float* dst = p.partial + ((long long)(blockIdx.x * 4 + pg)) * 2 * p.n_total + ncol0 + 2 * cp;
+#pragma unroll
+      for (int t2 = 0; t2 < Cfg::kOutTiles; ++t2) {
+        *reinterpret_cast<float2*>(dst + t2 * 64) = make_float2(bsum[t2][0], bsum[t2][1]);
+        *reinterpret_cast<float2*>(dst + p.n_total + t2 * 64) = make_float2(bsum[t2][2], bsum[t2][3]);
       }
     }
     if (issuer) tma_store_wait_read<0>();
@@ -615,7 +640,15 @@ int crfr_tc_gemm(const TcGemm& g, cudaStream_t st) {
   p.total_tiles = tiles;
   p.partial = nullptr; p.slots = 0; p.gpt = 0;
   if (g.stat_slots) *g.stat_slots = 0;
-  if (g.stat_ws && g.stat_slots && !g.out_f32 && tile_n % 64 == 0 && t.rows == 128 && g.h % t.bh == 0 && g.w % t.bw == 0 &&
+  int batch_ctas = (conv_sm_count() + g.n_total / tile_n - 1) / (g.n_total / tile_n);   // = launch_conv's grid.x
+  if (batch_ctas > tiles) batch_ctas = tiles;
+  if (g.stat_batch && g.stat_ws && g.stat_slots && !g.out_f32 && tile_n % 64 == 0 && !g.bias &&
+      sizeof(float) * (size_t)batch_ctas * 4 * 2 * g.n_total <= g.stat_ws_bytes) {
+    p.partial = g.stat_ws;
+    p.slots = batch_ctas * 4;
+    p.gpt = -1;
+    *g.stat_slots = p.slots;
+  } else if (g.stat_ws && g.stat_slots && !g.out_f32 && tile_n % 64 == 0 && t.rows == 128 && g.h % t.bh == 0 && g.w % t.bw == 0 &&
       (t.bw * t.bh) % 32 == 0) {
     // fused statistics: 128-row tiles of whole image rows whose 32-row groups never straddle an image.  Eligibility
     // must not depend on the batch size (a ragged last tile just skips the images that do not exist): the statistics
@@ -722,8 +755,8 @@ size_t crfr_tc_workspace_bytes(const crfr_conv_desc* d) {
 static int rowconv_enabled() { return crfr_opt(CRFR_OPT_ROWCONV); }
 
 int crfr_tc_conv(const crfr_conv_desc* d, int dgrad, const void* src, const void* w_packed, const float* bias,
-                 void* dst, float* stats, float eps, void* ws, size_t ws_bytes, cudaStream_t st) {
-  if (rowconv_enabled() && crfr_rowconv_supported(d->h, d->w, d->cin, d->cout, d->k, d->stride, d->pad)) {
+                 void* dst, float* stats, float eps, void* ws, size_t ws_bytes, cudaStream_t st, int batch_stats) {
+  if (!batch_stats && rowconv_enabled() && crfr_rowconv_supported(d->h, d->w, d->cin, d->cout, d->k, d->stride, d->pad)) {
     return crfr_rowconv(src, dgrad ? d->out_ld : d->in_ld, d->n, d->h, w_packed, dgrad, bias, dst,
                         dgrad ? d->in_ld : d->out_ld, dgrad ? nullptr : stats, eps, ws, ws_bytes, st);
   }
@@ -742,8 +775,13 @@ int crfr_tc_conv(const crfr_conv_desc* d, int dgrad, const void* src, const void
   g.stat_ws = want_stats ? (float*)ws : nullptr;
   g.stat_ws_bytes = want_stats ? ws_bytes : 0;
   g.stat_slots = &slots;
+  g.stat_batch = batch_stats;
   CRFR_TRY(crfr_tc_gemm(g, st));
-  if (want_stats) {
+  if (want_stats && batch_stats) {   // one group over the whole batch
+    const long long count = (long long)d->n * d->oh * d->ow;
+    if (slots) CRFR_TRY(crfr_norm_finalize((const float*)ws, 1, slots, (int)count, d->cout, eps, stats, st));
+    else CRFR_TRY(crfr_norm_stats(dst, 1, (int)count, d->cout, d->out_ld, eps, stats, ws, ws_bytes, (void*)st));
+  } else if (want_stats) {
     if (slots) CRFR_TRY(crfr_norm_finalize((const float*)ws, d->n, slots, d->oh * d->ow, d->cout, eps, stats, st));
     else CRFR_TRY(crfr_norm_stats(dst, d->n, d->oh * d->ow, d->cout, d->out_ld, eps, stats, ws, ws_bytes, (void*)st));
   }

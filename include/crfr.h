@@ -37,6 +37,8 @@ unsigned long long crfr_launch_count(void);
  *   "norm_bwd_impl": crfr_norm_act_bwd as 0 = register-staged reduce + fold + apply kernels, 1 = persistent TMA-fed
  *                    reduce + fold + apply kernels (default where the views are TMA-addressable: channels a multiple
  *                    of 64, 16-byte aligned), -1 = default / environment CRFR_NORM_BWD=regs|stream.
+ *   "bn_fused_stats": ResNet program, train-mode BatchNorm statistics of the 3x3 stride-1 layers as 1 = from the tile engine's
+ *                    epilogue (default), 0 = a separate pass over the stored output.
  *   "tc_t2": tile engine at N = 128 as 0 = one pixel tile per weight tile, 1 = two (default; fewer TMA requests).
  *   "pdl": programmatic dependent launch of the persistent kernels, 0 (default) / 1.
  *   "fuse_norm_fwd": crfr_norm_act_conv_fwd as 0 = crfr_norm_act_fwd + crfr_conv_fwd (default), 1 = normalisation inside
