@@ -25,6 +25,7 @@ enum {
   CRFR_OPT_PDL,              // programmatic dependent launch of the persistent kernels (common.cuh)
   CRFR_OPT_TC_T2,            // tile engine, N = 128: two pixel tiles per weight tile
   CRFR_OPT_BN_FUSED_STATS,   // ResNet program: train-mode BatchNorm statistics from the tile engine's epilogue
+  CRFR_OPT_MATCHER_CLUSTER,  // cosine_topk: gallery blocks multicast inside clusters of two CTAs
   CRFR_OPT_PAIR_DEBUG,       // ablation bits for tools/pair_diag.py (results are WRONG when set): 1 no loads, 2 no MMAs,
                              // 4 no pack / store / statistics, 8 no store, 16 no statistics
   CRFR_OPT_COUNT

@@ -39,6 +39,31 @@ int make_rows_map(CUtensorMap* m, const void* ptr, long long rows, int dim, int 
   return crfr_tmap_encode_bf16(m, ptr, 2, dims, strides, box, "embedding rows");
 }
 
+// ---- cluster primitives (CL form of the kernel)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose box lands at the same shared-memory offset in every CTA of `mask` and signals the barrier at the same
+// offset in each of them
+__device__ __forceinline__ void tma_load_2d_multicast(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], "
+      "[%2], %5;" ::"r"(smem_u32(dst)),
+      "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+// arrives on the barrier at this shared-memory offset in every CTA of `mask` once the MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask)
+               : "memory");
+}
+
 struct TopK {
   float v[kTopK];
   int i[kTopK];
@@ -76,6 +101,12 @@ struct MatchParams {
   int* out_idx;
 };
 
+// CL: clusters of two CTAs (two probe tiles, the same gallery range).  The TMA unit issues one request per 128-byte row of a
+// box, and a K step of this kernel asks for 256 gallery rows per 4 MMAs of 128 cycles: the request rate, not the tensor pipe,
+// bounded the single-CTA form at 0.62 of the bf16 peak.  In a cluster each CTA fetches HALF of every gallery block and
+// multicasts it into both shared memories (tmG then has a box of 128 rows); a ring stage is free again when both CTAs'
+// MMAs have consumed it (multicast tcgen05.commit on a barrier of count 2).
+template <bool CL>
 __global__ void __launch_bounds__(kThreads, 1)
 cosine_topk_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmG, MatchParams mp) {
   extern __shared__ uint8_t smem_raw[];
@@ -93,7 +124,7 @@ cosine_topk_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], CL ? 2 : 1);
     }
     mbar_init(a_full, 1);
     for (int b = 0; b < 2; ++b) {
@@ -107,8 +138,10 @@ cosine_topk_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
   if (warp == 1) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
+  if (CL) cluster_sync_all();   // the peer's barriers are initialised before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  const uint32_t crank = CL ? cluster_ctarank() : 0u;
 
   const int ptile = blockIdx.x, split = blockIdx.y;
   const int blk0 = split * mp.blocks_per_split;
@@ -129,7 +162,11 @@ cosine_topk_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
         mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
         if (leader) {
           mbar_expect_tx(&full[s], kBTile);
-          tma_load_2d(sB + s * kBTile, &tmG, &full[s], kc * 64, (blk0 + b) * kGBlock);
+          if (CL)   // this CTA's half of the block's rows, into both CTAs of the cluster
+            tma_load_2d_multicast(sB + s * kBTile + crank * (kBTile / 2), &tmG, &full[s], kc * 64,
+                                  (blk0 + b) * kGBlock + (int)crank * (kGBlock / 2), (uint16_t)3);
+          else
+            tma_load_2d(sB + s * kBTile, &tmG, &full[s], kc * 64, (blk0 + b) * kGBlock);
         }
       }
   } else if (warp == 1) {
@@ -151,7 +188,10 @@ cosine_topk_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           if (leader) umma_bf16(tmem + buf * kGBlock, da + 2 * k, db + 2 * k, idesc, (uint32_t)((kc | k) != 0));
-        if (leader) umma_commit(&empty[s]);
+        if (leader) {
+          if (CL) umma_commit_multicast(&empty[s], (uint16_t)3);   // frees the stage in both CTAs
+          else umma_commit(&empty[s]);
+        }
         __syncwarp();
       }
       if (leader) umma_commit(&acc_full[buf]);
@@ -204,6 +244,7 @@ cosine_topk_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
+  if (CL) cluster_sync_all();   // nobody leaves while the peer may still multicast into this CTA or arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<512>(tmem);
@@ -416,9 +457,10 @@ extern "C" int crfr_cosine_topk(int engine, const void* probes, const void* gall
     return CRFR_EWORKSPACE;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  const bool cl = crfr_opt(CRFR_OPT_MATCHER_CLUSTER) != 0 && s.tiles >= 2;
   CUtensorMap tmP, tmG;
   CRFR_TRY(make_rows_map(&tmP, probes, p, dim, 128));
-  CRFR_TRY(make_rows_map(&tmG, gallery, g, dim, kGBlock));
+  CRFR_TRY(make_rows_map(&tmG, gallery, g, dim, cl ? kGBlock / 2 : kGBlock));
   MatchParams mp;
   mp.p = p; mp.g = g; mp.kchunks = dim / 64; mp.nblocks = s.nblocks; mp.blocks_per_split = s.blocks_per_split;
   mp.index_base = index_base;
@@ -426,9 +468,24 @@ extern "C" int crfr_cosine_topk(int engine, const void* probes, const void* gall
   mp.out_idx = (int*)((float*)ws + (size_t)s.splits * p * kTopK);
   const int smem = mp.kchunks * kTile + kStages * kBTile + 1024 + 256;
   // the dynamic shared-memory size depends on the embedding width: raise the per-device limit to the hardware maximum once
-  static std::atomic<unsigned long long> attr_done{0};
-  CRFR_CUDA((cudaError_t)crfr_smem_attr(cosine_topk_kernel, 232448, attr_done));
-  cosine_topk_kernel<<<dim3(s.tiles, s.splits), kThreads, smem, st>>>(tmP, tmG, mp);
+  static std::atomic<unsigned long long> attr_done{0}, attr_done_cl{0};
+  CRFR_CUDA((cudaError_t)crfr_smem_attr(cosine_topk_kernel<false>, 232448, attr_done));
+  CRFR_CUDA((cudaError_t)crfr_smem_attr(cosine_topk_kernel<true>, 232448, attr_done_cl));
+  if (cl) {   // clusters of two probe tiles (an odd tile count gets one tile of padding: its probes do not exist, nothing is written)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((s.tiles + 1) & ~1, s.splits);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CRFR_CUDA(cudaLaunchKernelEx(&cfg, cosine_topk_kernel<true>, tmP, tmG, mp));
+  } else {
+    cosine_topk_kernel<false><<<dim3(s.tiles, s.splits), kThreads, smem, st>>>(tmP, tmG, mp);
+  }
   CRFR_COUNT_LAUNCH();
   CRFR_LAUNCH_CHECK();
   topk_merge_kernel<<<crfr_cdiv(p, 128), 128, 0, st>>>(mp.out_val, mp.out_idx, s.splits, p, kTopK, k, top_val, top_idx);

@@ -39,6 +39,7 @@ unsigned long long crfr_launch_count(void);
  *                    of 64, 16-byte aligned), -1 = default / environment CRFR_NORM_BWD=regs|stream.
  *   "bn_fused_stats": ResNet program, train-mode BatchNorm statistics of the 3x3 stride-1 layers as 1 = from the tile engine's
  *                    epilogue (default), 0 = a separate pass over the stored output.
+ *   "matcher_cluster": crfr_cosine_topk as 1 = clusters of two CTAs that multicast the gallery blocks (default), 0 = single CTAs.
  *   "tc_t2": tile engine at N = 128 as 0 = one pixel tile per weight tile, 1 = two (default; fewer TMA requests).
  *   "pdl": programmatic dependent launch of the persistent kernels, 0 (default) / 1.
  *   "fuse_norm_fwd": crfr_norm_act_conv_fwd as 0 = crfr_norm_act_fwd + crfr_conv_fwd (default), 1 = normalisation inside
