@@ -415,10 +415,21 @@ SplitPlan plan_splits(int p, long long g) {
   SplitPlan s;
   s.tiles = (p + 127) / 128;
   s.nblocks = (int)((g + kGBlock - 1) / kGBlock);
-  int want = (148 * 8 + s.tiles - 1) / s.tiles;
-  if (want > s.nblocks) want = s.nblocks;
-  if (want < 1) want = 1;
-  s.blocks_per_split = (s.nblocks + want - 1) / want;
+  // One CTA per SM at a time: the launch runs in waves of `sms` CTAs and costs waves x (blocks per split + the probe-tile load,
+  // about 4 blocks' worth).  Pick the split count that minimises it: 10 k probes x 1 M rows = 79 (80 in clusters) tiles - 15
+  // splits are 1 185 CTAs = 8.007 waves, i.e. NINE waves of 261 blocks; 13 splits are 7 waves of 301 (-10 %).
+  const int sms = crfr_sm_count();
+  const int tiles_eff = s.tiles >= 2 ? ((s.tiles + 1) & ~1) : s.tiles;   // clusters of two probe tiles
+  int best = 1;
+  long long best_cost = -1;
+  for (int want = 1; want <= 64 && want <= s.nblocks; ++want) {
+    const int bps = (s.nblocks + want - 1) / want;
+    const int splits = (s.nblocks + bps - 1) / bps;
+    const long long waves = ((long long)tiles_eff * splits + sms - 1) / sms;
+    const long long cost = waves * (bps + 4);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = want; }
+  }
+  s.blocks_per_split = (s.nblocks + best - 1) / best;
   s.splits = (s.nblocks + s.blocks_per_split - 1) / s.blocks_per_split;
   return s;
 }

@@ -392,7 +392,7 @@ int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
   CRFR_CUDA((cudaError_t)crfr_smem_attr(tc_conv_kernel<N, MODE>, Cfg::kSmemBytes, attr_done));
   // persistent over pixel tiles: about one CTA per SM in total (column tiles share the pixel-tile walk)
   const int ncol = p.n_total / N;
-  int ctas = (conv_sm_count() + ncol - 1) / ncol;
+  int ctas = conv_sm_count() / ncol;   // rounded down: more CTAs than SMs would be a second, nearly empty wave
   if (ctas > tiles) ctas = tiles;
   if (ctas < 1) ctas = 1;
   tc_conv_kernel<N, MODE><<<dim3(ctas, ncol), kConvThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, tmY, p);
@@ -640,8 +640,9 @@ int crfr_tc_gemm(const TcGemm& g, cudaStream_t st) {
   p.total_tiles = tiles;
   p.partial = nullptr; p.slots = 0; p.gpt = 0;
   if (g.stat_slots) *g.stat_slots = 0;
-  int batch_ctas = (conv_sm_count() + g.n_total / tile_n - 1) / (g.n_total / tile_n);   // = launch_conv's grid.x
+  int batch_ctas = conv_sm_count() / (g.n_total / tile_n);   // = launch_conv's grid.x
   if (batch_ctas > tiles) batch_ctas = tiles;
+  if (batch_ctas < 1) batch_ctas = 1;
   if (g.stat_batch && g.stat_ws && g.stat_slots && !g.out_f32 && tile_n % 64 == 0 && !g.bias &&
       sizeof(float) * (size_t)batch_ctas * 4 * 2 * g.n_total <= g.stat_ws_bytes) {
     p.partial = g.stat_ws;
@@ -703,7 +704,11 @@ int crfr_tc_wgrad_raw(const TcWgrad& g, cudaStream_t st) {
   p.rows = t.rows;
   const int tile_n = (g.cout % 128 == 0) ? 128 : 64;
   const int ctas_per_split = (g.taps3x3 ? 3 : 1) * (g.cout / tile_n) * (g.cin / 64);
-  int splits = (148 * 2 + ctas_per_split - 1) / ctas_per_split;
+  // One CTA per SM at a time (160-192 KB of shared memory): the grid runs in waves of `sms` CTAs, so it must not exceed a whole
+  // number of them - 50 splits x 6 CTAs = 300 CTAs on 148 SMs were THREE waves for 2.03 waves of work.  Two waves, rounded DOWN.
+  const int sms = conv_sm_count();
+  int splits = (2 * sms) / ctas_per_split;
+  if (splits < 1) splits = ctas_per_split <= sms ? sms / ctas_per_split : 1;
   if (splits > p.total_tiles) splits = p.total_tiles;
   if (splits < 1) splits = 1;
   if (g.taps3x3) {
