@@ -179,8 +179,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int tx = t % p.tiles_x; t /= p.tiles_x;
       const int ty = t % p.tiles_y; t /= p.tiles_y;
       const int x0 = tx * p.bw, y0 = ty * p.bh, n0 = t * p.bn;
-      // T2: the second pixel tile of the pair (the first one again where the CTA's tile count is odd: its result is dropped)
-      int t1 = blockIdx.x + (i + 1 < my_tiles ? i + 1 : i) * gridDim.x;
+      // T2: the second pixel tile of the pair (absent where the CTA's tile count is odd: that step loads and computes one tile)
+      const bool has2 = T2 && i + 1 < my_tiles;
+      int t1 = blockIdx.x + (has2 ? i + 1 : i) * gridDim.x;
       const int tx1 = t1 % p.tiles_x; t1 /= p.tiles_x;
       const int ty1 = t1 % p.tiles_y; t1 /= p.tiles_y;
       const int x1 = tx1 * p.bw, y1 = ty1 * p.bh, n1 = t1 * p.bn;
@@ -198,9 +199,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int tap = it / p.kchunks, kc = it - tap * p.kchunks;
         const int ky = tap / p.ksize, kx = tap - ky * p.ksize;
         if (leader) {
-          mbar_expect_tx(&full[s], (T2 ? 2u : 1u) * a_bytes + (uint32_t)Cfg::kBTileBytes);
+          mbar_expect_tx(&full[s], (has2 ? 2u : 1u) * a_bytes + (uint32_t)Cfg::kBTileBytes);
           tma_load_4d(sa, &tmA, &full[s], kc * 64, x0 + p.sign * (kx - p.pad), y0 + p.sign * (ky - p.pad), n0);
-          if (T2) tma_load_4d(sa + kATileBytes, &tmA, &full[s], kc * 64, x1 + p.sign * (kx - p.pad), y1 + p.sign * (ky - p.pad), n1);
+          if (has2) tma_load_4d(sa + kATileBytes, &tmA, &full[s], kc * 64, x1 + p.sign * (kx - p.pad), y1 + p.sign * (ky - p.pad), n1);
           tma_load_2d(sa + (T2 ? 2 : 1) * kATileBytes, &tmB, &full[s], kc * 64, tap * p.n_total + ncol0);
         }
       }
@@ -244,7 +245,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (leader) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (uint32_t)((it | k) != 0));
-          if (T2) {
+          if (T2 && i + 1 < my_tiles) {
             const uint64_t da1 = da + (uint64_t)(kATileBytes >> 4);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
