@@ -11,6 +11,19 @@
 //     D1[(kx 0|1) x 64 ci][(ky 2|1|0) x 64 co] += X_q(shift 0|1)^T * [dY_{q-1} | dY_q | dY_{q+1}]      (M=128, N=192)
 //     D2[(kx 2|-) x 64 ci][...]                 += X_q(shift 2|3)^T * [...]                               (upper half unused)
 // 16 MMAs (K = 16 pixels each) per row instead of 48 N = 64 MMAs.  Rows outside the image are TMA zero fill.
+// An M = 64 MMA costs the tensor pipe as much as M = 128, so D2 above runs at half use (the kernel at 75 %).  For an even image
+// height the rows are therefore processed in PAIRS (q, q+1) and the two kx = 2 atoms share one MMA over the FOUR dY rows that
+// the pair touches:
+//     D2[(X_q | X_{q+1}) shift 2 x 64 ci][(dY_{q-1} | dY_q | dY_{q+1} | dY_{q+2}) x 64 co]               (M=128, N=256)
+// (M atoms one X slot apart, N atoms one dY slot apart).  Six of its eight 64 x 64 blocks are wanted - X_q with dY_{q+2} and
+// X_{q+1} with dY_{q-1} are no taps and are dropped by the epilogue - so a pair costs 2 x 192 + 256 = 640 accumulator columns
+// per K step instead of 768: 90 % of the issued MMA work is useful instead of 75 %.  Measured (128 images, incl. the slab
+// reduction): 154 -> 137.5 us.  What bounds the kernel now is the shared-memory read port: an SS-mode MMA streams both operands
+// from shared memory, (128 + N) x 16 x 2 bytes per N / 2 cycles = 107 B/clk at N = 192 and 96 B/clk at N = 256, next to
+// ~20 B/clk of TMA fill (incl. the mirror slots) - of 128 B/clk per SM.  Deeper rings change nothing (6 X slots packed at
+// 130 x 128 bytes - the swizzle is a function of the address, slot bases need only 128-byte alignment: verified - 135.6 us; dY
+// ring 8: 139.9 us; L2 prefetch 2 / 4 / 8 rows ahead: 138.7 / 139.8 / 145.4 us).  Halving the B reads needs cta_group::2, whose
+// shared B would force the four-row N on every atom (75 % useful again): not done.
 // Each CTA streams a contiguous range of rows, keeps its partial dW in TMEM for its whole lifetime and writes one
 // fp32 slab; a second kernel sums the slabs in fixed order (deterministic, no float atomics) and accumulates into
 // the reference-layout gradient dW[co][ci][ky][kx].
@@ -52,6 +65,7 @@ struct WgParams {
   int n, h, total_rows;
   float* slabs;   // [gridDim.x][9][64][64]
   int prefetch;   // rows pulled into L2 ahead of the rings
+  int paired;     // even image height: rows in pairs, the kx = 2 taps of a pair in one M = 128, N = 256 MMA
 };
 
 // One MMA: descriptors that differ only in their low word (start address) from precomputed bases - the issuing warp is the
@@ -104,8 +118,10 @@ rowwgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   pdl_trigger();
   pdl_wait();   // (common.cuh) the prologue overlapped the previous kernel's tail; x / dy are read from here on
 
-  const long long r_begin = (long long)p.total_rows * blockIdx.x / gridDim.x;
-  const long long r_end = (long long)p.total_rows * (blockIdx.x + 1) / gridDim.x;
+  // paired: ranges of whole row pairs (h even: an image boundary is a pair boundary too)
+  const long long units = p.paired ? p.total_rows / 2 : p.total_rows;
+  const long long r_begin = (units * blockIdx.x / gridDim.x) << p.paired;
+  const long long r_end = (units * (blockIdx.x + 1) / gridDim.x) << p.paired;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -178,6 +194,9 @@ rowwgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     const uint64_t dydesc0 = make_smem_desc_sw128(smem_u32(sDY), kDyRowBytes, 1024);
     const uint32_t desc_hi = (uint32_t)(xdesc0 >> 32), x_lo = (uint32_t)xdesc0, dy_lo = (uint32_t)dydesc0;
     const uint32_t idesc = make_idesc_bf16(128, 3 * kC, 1, 1);
+    // paired form: A atoms = the kx = 2 views of two consecutive X slots, B = four dY slots
+    const uint32_t x2_lo = (uint32_t)make_smem_desc_sw128(smem_u32(sX) + 256, kXSlotBytes, 1024);
+    const uint32_t idesc4 = make_idesc_bf16(128, 4 * kC, 1, 1);
     int sx = 0;  uint32_t xph = 0;    // X ring slot of the current row and its parity
     int dp = 0;  uint32_t dph = 0;    // dY ring position of the current row's first dY row (q - 1), and its parity
     int dg = 0;
@@ -185,6 +204,51 @@ rowwgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     while (r < r_end) {
       const int y0 = (int)(r % p.h);
       const int seg = (int)min((long long)(p.h - y0), r_end - r);
+      if (p.paired) {
+        // dp is even here (even ring, even segments): positions dp .. dp + 3 are contiguous through the two mirror slots,
+        // and so are dp + 1 .. dp + 3 for the second row of the pair
+        for (int i = 0; i < seg; i += 2) {
+          int p1 = dp + 1, p2 = dp + 2, p3 = dp + 3;
+          uint32_t ph2 = dph;
+          if (p2 >= kDyRing) { p2 -= kDyRing; p3 -= kDyRing; ph2 ^= 1; }
+          if (i == 0) {
+            mbar_wait(&full_dy[dp], dph);
+            mbar_wait(&full_dy[p1], dph);
+          }
+          mbar_wait(&full_dy[p2], ph2);
+          mbar_wait(&full_x[sx], xph);
+          tc_fence_after();
+          const uint32_t a0 = x_lo + (uint32_t)(sx * (kXSlotBytes >> 4));
+          const uint32_t b0 = dy_lo + (uint32_t)(dp * (kDyRowBytes >> 4));
+          if (leader) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              umma_lo(tmem, a0 + (uint32_t)(k * (2048 >> 4)), b0 + (uint32_t)(k * (2048 >> 4)), desc_hi, idesc);
+          }
+          __syncwarp();
+          mbar_wait(&full_dy[p3], ph2);
+          mbar_wait(&full_x[sx + 1], xph);
+          tc_fence_after();
+          if (leader) {
+            const uint32_t a1 = a0 + (uint32_t)(kXSlotBytes >> 4), b1 = b0 + (uint32_t)(kDyRowBytes >> 4);
+            const uint32_t a2 = x2_lo + (uint32_t)(sx * (kXSlotBytes >> 4));
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              umma_lo(tmem, a1 + (uint32_t)(k * (2048 >> 4)), b1 + (uint32_t)(k * (2048 >> 4)), desc_hi, idesc);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              umma_lo(tmem + 256, a2 + (uint32_t)(k * (2048 >> 4)), b0 + (uint32_t)(k * (2048 >> 4)), desc_hi, idesc4);
+            umma_commit(&done[dg]);          // both rows are released by the pair's last MMA
+            umma_commit(&done[dg + 1]);
+          }
+          __syncwarp();
+          sx += 2;
+          if (sx == kXSlots) { sx = 0; xph ^= 1; }
+          dp += 2;
+          if (dp == kDyRing) { dp = 0; dph ^= 1; }
+          dg = (dg + 2) & (kDone - 1);
+        }
+      } else
       for (int i = 0; i < seg; ++i) {
         // dY rows q-1, q, q+1 = ring positions dp, dp+1, dp+2 (mod kDyRing); the first two were waited for by the previous
         // row of the segment
@@ -230,8 +294,40 @@ rowwgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     mbar_wait(fin, 0);
     tc_fence_after();
     float* slab = p.slabs + (size_t)blockIdx.x * kSlabFloats;
+    if (p.paired) {
+      // D2 lanes 0-63: X_q with dY_{q-1+b} in column block b -> ky = 2 - b (b = 3 is no tap); lanes 64-127: X_{q+1} with the
+      // same dY rows -> ky = 3 - b (b = 0 is no tap).  Both halves belong to the same nine 64 x 64 gradients: the lower
+      // lanes store, the upper lanes add after a barrier (fixed order: deterministic).
+      const bool upper = row >= 64;                 // warp-uniform
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
+      for (int phase = 0; phase < 2; ++phase) {
+        if ((phase == 1) == upper) {
+#pragma unroll
+          for (int c0 = 0; c0 < 256; c0 += 32) {
+            const int b = c0 / 64;
+            const int ky = (upper ? 3 : 2) - b;
+            if (ky < 0 || ky > 2) continue;
+            uint32_t v[32];
+            tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 256 + c0, v);
+            tmem_ld_wait();
+            float* dst = slab + ((size_t)(ky * 3 + 2) * kC + ci) * kC + (c0 & 63);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                     __uint_as_float(v[j + 3]));
+              if (upper) {
+                const float4 t = *reinterpret_cast<const float4*>(dst + j);
+                o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
+              }
+              *reinterpret_cast<float4*>(dst + j) = o;
+            }
+          }
+        }
+        if (phase == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+    }
+#pragma unroll
+    for (int half = 0; half < (p.paired ? 1 : 2); ++half) {
       const int kx = half == 0 ? (row >> 6) : 2;
       const bool live = half == 0 || row < 64;      // warp-uniform
 #pragma unroll
@@ -294,9 +390,10 @@ int encode(CUtensorMap* m, const void* ptr, int n, int h, int ld, int box_w, con
   return crfr_tmap_encode_bf16(m, ptr, 4, dims, strides, box, what);
 }
 
-int grid_for(int total_rows) {
+int grid_for(int total_rows, int h) {
   const int sms = crfr_sm_count();
-  return sms < total_rows ? sms : total_rows;
+  const int units = (h & 1) ? total_rows : total_rows / 2;   // even height: CTAs take whole row pairs
+  return sms < units ? sms : units;
 }
 
 }  // namespace
@@ -305,7 +402,7 @@ int crfr_rowwgrad_supported(int h, int w, int cin, int cout, int k, int stride, 
   return w == kW && cin == kC && cout == kC && k == 3 && stride == 1 && pad == 1 && h >= 1;
 }
 
-size_t crfr_rowwgrad_ws_bytes(int n, int h) { return sizeof(float) * (size_t)grid_for(n * h) * kSlabFloats + 256; }
+size_t crfr_rowwgrad_ws_bytes(int n, int h) { return sizeof(float) * (size_t)grid_for(n * h, h) * kSlabFloats + 256; }
 
 // x, dy: NHWC bf16 [n][h][128][64] views; dw: fp32 [64][64][3][3], accumulated.
 int crfr_rowwgrad(const void* x, int x_ld, const void* dy, int dy_ld, int n, int h, float* dw, void* ws,
@@ -326,7 +423,8 @@ int crfr_rowwgrad(const void* x, int x_ld, const void* dy, int dy_ld, int n, int
   p.n = n; p.h = h; p.total_rows = n * h;
   p.slabs = (float*)ws;
   p.prefetch = kPrefetch;
-  const int grid = grid_for(p.total_rows);
+  p.paired = (h & 1) ? 0 : 1;
+  const int grid = grid_for(p.total_rows, h);
   CRFR_CUDA(crfr_launch_pdl(rowwgrad_kernel, dim3(grid), dim3(kThreads), kSmemBytes, st, tmX, tmDY, p));
   CRFR_COUNT_LAUNCH();
   CRFR_LAUNCH_CHECK();
