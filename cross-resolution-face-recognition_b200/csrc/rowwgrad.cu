@@ -18,15 +18,12 @@
 // (M atoms one X slot apart, N atoms one dY slot apart).  Six of its eight 64 x 64 blocks are wanted - X_q with dY_{q+2} and
 // X_{q+1} with dY_{q-1} are no taps and are dropped by the epilogue - so a pair costs 2 x 192 + 256 = 640 accumulator columns
 // per K step instead of 768: 90 % of the issued MMA work is useful instead of 75 %.  Measured (128 images, incl. the slab
-// reduction): 154 -> 137.5 us.  What bounds the kernel now is the shared-memory read port: an SS-mode MMA streams both operands
-// from shared memory, (128 + N) x 16 x 2 bytes per N / 2 cycles = 107 B/clk at N = 192 and 96 B/clk at N = 256, next to
-// ~20 B/clk of TMA fill (incl. the mirror slots) - of 128 B/clk per SM.  Deeper rings change nothing (6 X slots packed at
-// 130 x 128 bytes - the swizzle is a function of the address, slot bases need only 128-byte alignment: verified - 135.6 us; dY
-// ring 8: 139.9 us; L2 prefetch 2 / 4 / 8 rows ahead: 138.7 / 139.8 / 145.4 us).  Halving the B reads needs cta_group::2, whose
-// shared B would force the four-row N on every atom (75 % useful again): not done.
-// Each CTA streams a contiguous range of rows, keeps its partial dW in TMEM for its whole lifetime and writes one
-// fp32 slab; a second kernel sums the slabs in fixed order (deterministic, no float atomics) and accumulates into
-// the reference-layout gradient dW[co][ci][ky][kx].
+// reduction): 154 -> 137.5 us.  ncu on the pair form (profiles/r2_rowwgrad_pair_ncu.txt, 124 us): tensor pipe 80 % of the active
+// cycles, the tensor core's shared-memory reads - an SS-mode MMA streams (128 + N) x 32 bytes per N / 2 cycles - 59 % of their
+// peak, DRAM 4.4 TB/s: no unit is saturated; the idle fifth is the prologue (TMEM zero fill, first loads), the slab epilogue
+// and ring waits.  Deeper rings change nothing (6 X slots packed at 130 x 128 bytes - the swizzle is a function of the
+// address, slot bases need only 128-byte alignment: verified - 135.6 us; dY ring 8: 139.9 us; L2 prefetch 2 / 4 / 8 rows ahead:
+// 138.7 / 139.8 / 145.4 us).
 //
 // ref: the weight gradients of the nn.Conv2d sites model/FSRnet.py:79,85 (coarse / decoder residual stacks).
 #include <cudaTypedefs.h>
