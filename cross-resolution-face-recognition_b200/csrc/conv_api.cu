@@ -133,8 +133,10 @@ extern "C" int crfr_conv_fwd(int engine, const crfr_conv_desc* d, const void* x,
   if (engine != CRFR_ENGINE_DIRECT) {
     const int r = crfr_lowered_recipe(d);
     if (r == 2 || (r != 0 && y && !y_nchw)) {
-      CRFR_TRY(crfr_lowered_fwd(d, x, w_packed, cin_pad, bias, y, y_nchw, ws, ws_bytes, st));
-      if (stats) CRFR_TRY(crfr_norm_stats(y, d->n, d->oh * d->ow, d->cout, d->out_ld, eps, stats, ws, ws_bytes, stream));
+      int stats_done = 0;
+      CRFR_TRY(crfr_lowered_fwd(d, x, w_packed, cin_pad, bias, y, y_nchw, ws, ws_bytes, st, stats, eps, &stats_done));
+      if (stats && !stats_done)
+        CRFR_TRY(crfr_norm_stats(y, d->n, d->oh * d->ow, d->cout, d->out_ld, eps, stats, ws, ws_bytes, stream));
       return CRFR_OK;
     }
   }

@@ -150,8 +150,11 @@ int crfr_tc_wgrad(const crfr_conv_desc* d, const void* x, const void* dy, float*
 // lowered_conv.cu: edge layers as [gather kernel] + [tcgen05 GEMM]; recipe 0 = not applicable
 int crfr_lowered_recipe(const crfr_conv_desc* d);
 size_t crfr_lowered_ws_bytes(const crfr_conv_desc* d);
+// stats != nullptr: InstanceNorm statistics of the stored output where the GEMM's tiling can produce them in its epilogue;
+// *stats_done says whether it did (0: the caller runs crfr_norm_stats over y)
 int crfr_lowered_fwd(const crfr_conv_desc* d, const void* x, const void* w_packed, int cin_pad, const float* bias,
-                     void* y, float* y_nchw, void* ws, size_t ws_bytes, cudaStream_t st);
+                     void* y, float* y_nchw, void* ws, size_t ws_bytes, cudaStream_t st, float* stats = nullptr,
+                     float eps = 0.f, int* stats_done = nullptr);
 int crfr_lowered_dgrad(const crfr_conv_desc* d, const void* dy, const void* w_packed_t, int cout_pad, void* dx, void* ws,
                        size_t ws_bytes, cudaStream_t st);
 int crfr_lowered_wgrad(const crfr_conv_desc* d, const void* x, const void* dy, float* dw, void* ws, size_t ws_bytes,

@@ -430,6 +430,11 @@ int crfr_lowered_recipe(const crfr_conv_desc* d) {
   return 0;
 }
 
+// partial sums of the fused statistics: [n][slots][2][cout] fp32 with at most one slot per 32 output pixels of an image
+static size_t stat_partial_bytes(const crfr_conv_desc* d) {
+  return sizeof(float) * (size_t)d->n * (size_t)((d->oh * d->ow + 31) / 32) * 2 * (size_t)d->cout;
+}
+
 size_t crfr_lowered_ws_bytes(const crfr_conv_desc* d) {
   const int r = crfr_lowered_recipe(d);
   const size_t big = (size_t)d->n * d->h * d->w, small = (size_t)d->n * d->oh * d->ow;
@@ -448,17 +453,40 @@ size_t crfr_lowered_ws_bytes(const crfr_conv_desc* d) {
     }
     default: return 0;
   }
+  if (r == 1 || r == 3 || r == 5) b += stat_partial_bytes(d) + 1024;
   return b + 16 * 1024;
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------------------
+// the GEMM of recipes 1 / 3 / 5 writes the layer's output: let its epilogue produce the InstanceNorm statistics too
+static int gemm_with_stats(TcGemm& g, const crfr_conv_desc* d, Arena& A, float* stats, float eps, int* stats_done,
+                           cudaStream_t st) {
+  int slots = 0;
+  if (stats && stats_done) {
+    const size_t bytes = stat_partial_bytes(d);
+    if (void* part = A.take(bytes)) {
+      g.stat_ws = (float*)part;
+      g.stat_ws_bytes = bytes;
+      g.stat_slots = &slots;
+    }
+  }
+  CRFR_TRY(crfr_tc_gemm(g, st));
+  if (slots) {
+    CRFR_TRY(crfr_norm_finalize(g.stat_ws, d->n, slots, d->oh * d->ow, d->cout, eps, stats, st));
+    *stats_done = 1;
+  }
+  return CRFR_OK;
+}
+
 int crfr_lowered_fwd(const crfr_conv_desc* d, const void* x, const void* w_packed, int cin_pad, const float* bias,
-                     void* y, float* y_nchw, void* ws, size_t ws_bytes, cudaStream_t st) {
+                     void* y, float* y_nchw, void* ws, size_t ws_bytes, cudaStream_t st, float* stats, float eps,
+                     int* stats_done) {
   const int recipe = crfr_lowered_recipe(d);
   Arena A{(uint8_t*)ws, ws_bytes, 0};
   const int T = d->k * d->k;
+  if (stats_done) *stats_done = 0;
   if (recipe == 1 || recipe == 3) {
     if (!y || y_nchw) {
       crfr_set_error("lowered conv: recipe %d produces the bf16 NHWC output only", recipe);
@@ -471,7 +499,7 @@ int crfr_lowered_fwd(const crfr_conv_desc* d, const void* x, const void* w_packe
     CRFR_TRY(launch_im2col_small((const bf16*)x, d->n, d->h, d->w, d->oh, d->ow, d->k, d->stride, d->pad, 1, P, kp, st));
     LAUNCH(repack_tapmajor_kernel, d->cout * kp, st, (const bf16*)w_packed, T, d->cout, 3, cin_pad, Wg, d->cout, kp);
     TcGemm g{P, d->n, d->oh, d->ow, kp, kp, Wg, 1, 0, 1, d->cout, 0, y, d->out_ld, 0, bias};
-    return crfr_tc_gemm(g, st);
+    return gemm_with_stats(g, d, A, stats, eps, stats_done, st);
   }
   if (recipe == 5) {
     if (!y || y_nchw) {
@@ -491,7 +519,7 @@ int crfr_lowered_fwd(const crfr_conv_desc* d, const void* x, const void* w_packe
       wg = Wg;
     }
     TcGemm g{P, d->n, d->oh, d->ow, kc, kc, wg, 1, 0, 1, d->cout, 0, y, d->out_ld, 0, bias};
-    return crfr_tc_gemm(g, st);
+    return gemm_with_stats(g, d, A, stats, eps, stats_done, st);
   }
   if (recipe == 2) {
     const long long pix = (long long)d->n * d->h * d->w;
