@@ -427,6 +427,7 @@ struct WgCfg {
   static constexpr int kXBytes = H ? 2 * kTile16K : TAPS * kTile16K;
   static constexpr int kStageBytes = kXBytes + kDyTiles * kTile16K;
   static constexpr int kStages = (kStageBytes <= 32 * 1024) ? 6 : (kStageBytes <= 48 * 1024) ? 4 : (kStageBytes <= 64 * 1024) ? 3 : 2;
+  static constexpr bool kSwap = TAPS == 3 && N == 128;             // dY as the M operand, the three tap views along N
   static constexpr int kAccs = (TAPS + 1) / 2;                     // accumulators of M = 128 (two taps each)
   static constexpr int kTmemCols = (kAccs * N <= 64) ? 64 : (kAccs * N <= 128) ? 128 : 256;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
@@ -507,7 +508,11 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     }
   } else if (warp == 1) {
     const bool leader = elect_one();
-    const uint32_t idesc = make_idesc_bf16(128, N, 1, 1);
+    const uint32_t idesc = Cfg::kSwap ? make_idesc_bf16(128, 192, 1, 1) : make_idesc_bf16(128, N, 1, 1);
+    // kSwap (three taps, 128 dY channels): the dY tile is the M operand (128 channels: a full M) and the three tap views of X are
+    // stacked along N - ONE M = 128, N = 192 MMA per K step, every block of it wanted, instead of two M = 128, N = 128 MMAs of
+    // which the second uses half its rows (an M = 64 MMA costs the pipe as much as M = 128): 96 instead of 128 cycles.
+    // Otherwise:
     // M = 128 = two 64-channel atoms LBO (= one 16 KB tile) apart: taps (0,1) in the first MMA; the second atom of
     // the last MMA is whatever tile follows (rows 64..127 of that accumulator are never read)
     // (H: the atoms are the ky = 0 / 1 / 2 views of one box, bw pixel rows apart; dY keeps its 16 KB tiles)
@@ -524,6 +529,10 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 #pragma unroll
       for (int k = 0; k < 8; ++k) {  // 8 x 16 pixels
         const uint32_t acc = (uint32_t)((i | k) != 0);
+        if (Cfg::kSwap) {
+          if (leader) umma_bf16(tmem, db + k * (2048 >> 4), a01 + k * (2048 >> 4), idesc, acc);
+          continue;
+        }
         if (leader) umma_bf16(tmem, a01 + k * (2048 >> 4), db + k * (2048 >> 4), idesc, acc);
         if (TAPS == 3)
           if (leader) umma_bf16(tmem + N, a2x + k * (2048 >> 4), db + k * (2048 >> 4), idesc, acc);
@@ -539,6 +548,22 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     const int ci = kc * 64 + (r & 63);
+    if (Cfg::kSwap) {
+      // D[co = lane][(tap view a) x 64 ci]: a warp's 32 lanes hold 32 consecutive co of one (tap, ci) -> one coalesced
+      // 128-byte reduction per column
+#pragma unroll
+      for (int c0 = 0; c0 < 192; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c0, v);
+        tmem_ld_wait();
+        const int a = c0 / 64;
+        const int tap = H ? a * 3 + ky : ky * 3 + a;
+        float* dst = p.G + ((long long)tap * p.cin + kc * 64 + (c0 & 63)) * p.cout + ncol0 + r;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + (long long)j * p.cout), "f"(__uint_as_float(v[j])) : "memory");
+      }
+    } else
 #pragma unroll
     for (int half = 0; half < Cfg::kAccs; ++half) {
       const int kx = half == 0 ? (r >> 6) : 2;                          // (H: this is the tap's ky, and `ky` its kx)
