@@ -97,18 +97,36 @@ __global__ void __launch_bounds__(kT)
 landmark_kernel(const float* __restrict__ x, const float* __restrict__ t, long long npix, int hw, int c, float gcoef,
                 bf16* __restrict__ dx, int dx_ld, int coff, float* __restrict__ partial) {
   long long i = (long long)blockIdx.x * kT + threadIdx.x;
-  float acc = 0.f;
+  float acc = 0.f, d = 0.f;
   if (i < npix) {
     long long n = i / hw;
     int p = (int)(i - n * hw);
     const float* xs = x + n * (long long)c * hw + p;
     float s = 0.f;
-    for (int ch = 0; ch < c; ++ch) s += xs[(long long)ch * hw];
-    float d = s - t[i];
+#pragma unroll 8
+    for (int ch = 0; ch < c; ++ch) s += xs[(long long)ch * hw];   // same order as written; the loads are independent
+    d = s - t[i];
     acc = d * d;
-    if (dx) {
-      bf16 g = __float2bfloat16_rn(gcoef * d);
-      for (int ch = 0; ch < c; ++ch) dx[i * dx_ld + coff + ch] = g;
+  }
+  if (dx) {
+    // every channel of a pixel gets the same gradient: the warp writes its 32 pixels' rows one after the other, each lane
+    // a 4-byte pair of the row (coalesced), instead of every lane walking its own row with 2-byte stores 2 * dx_ld bytes
+    // apart from its neighbours' (137 us for 128 images)
+    const unsigned short gb = __bfloat16_as_ushort(__float2bfloat16_rn(gcoef * d));
+    const int lane = threadIdx.x & 31;
+    const long long wbase = i - lane;
+    for (int k = 0; k < 32; ++k) {
+      const unsigned short gk = (unsigned short)__shfl_sync(0xffffffffu, (int)gb, k);
+      const long long ik = wbase + k;
+      if (ik >= npix) break;                                    // warp-uniform
+      unsigned short* row = reinterpret_cast<unsigned short*>(dx) + ik * dx_ld + coff;
+      const int head = (int)((ik * dx_ld + coff) & 1);          // the row starts in the middle of a 4-byte word
+      if (head && lane == 0) row[0] = gk;
+      const int pairs = (c - head) >> 1;
+      uint32_t* rw = reinterpret_cast<uint32_t*>(row + head);
+      const uint32_t gg = (uint32_t)gk | ((uint32_t)gk << 16);
+      for (int w = lane; w < pairs; w += 32) rw[w] = gg;
+      if (((c - head) & 1) && lane == 0) row[c - 1] = gk;
     }
   }
   block_partial(acc, partial);

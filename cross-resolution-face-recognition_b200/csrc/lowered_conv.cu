@@ -223,14 +223,18 @@ __global__ void col2im_small_kernel(const float* __restrict__ src, int src_ld, i
   const long long n = q / bh;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   for (int c = 0; c < C; ++c) acc[c] = bias ? bias[c] : 0.f;
-  for (int ky = 0; ky < ks; ++ky) {
+  // only every stride-th tap can hit a source pixel: start at the first one and step by the stride (the 7x7 stride-4 stems
+  // walked all 49 taps with a modulo each to find their 1-4 contributions: 133 us per launch at 128 images)
+  const int ky0 = sgn > 0 ? (Y + pad) % stride : ((pad - Y) % stride + stride) % stride;
+  const int kx0 = sgn > 0 ? (X + pad) % stride : ((pad - X) % stride + stride) % stride;
+  for (int ky = ky0; ky < ks; ky += stride) {
     const int ty = Y + sgn * (pad - ky);
-    if (ty < 0 || ty % stride) continue;
+    if (ty < 0) continue;
     const int sy = ty / stride;
     if (sy >= sh) continue;
-    for (int kx = 0; kx < ks; ++kx) {
+    for (int kx = kx0; kx < ks; kx += stride) {
       const int tx = X + sgn * (pad - kx);
-      if (tx < 0 || tx % stride) continue;
+      if (tx < 0) continue;
       const int sx = tx / stride;
       if (sx >= sw) continue;
       const float* s = src + ((n * sh + sy) * sw + sx) * src_ld + (ky * ks + kx) * C;
