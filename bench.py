@@ -152,7 +152,7 @@ ROWCONV_TRAFFIC_BYTES_PER_IMAGE = (273.30e6 + 224.68e6) / 128
 ROWCONV_TRAFFIC_SOURCE = "ncu --set full capture profiles/r2_rowconv_pair_final_ncu.txt (round 2 final, rowconv_pair_kernel<0>, 128 images)"
 
 
-def time_matcher(torch, ops, dist, world, rank, probes=10000, gallery=1000000, dim=512, k=5, reps=3):
+def time_matcher(torch, ops, dist, world, rank, probes=10000, gallery=1000000, dim=512, k=5, reps=8):
     """Cosine-similarity identification (BASELINE.json configs[3]): 10 k probes x 1 M-entry 512-d gallery, top-5.
     N > 1: the gallery rows are sharded across the ranks, every rank runs the fused GEMM + top-k on its shard, the per-rank
     (score, index) lists are all-gathered over NCCL and merged (crfr_b200.utils.cosine_identify(sharded=True))."""
@@ -167,7 +167,8 @@ def time_matcher(torch, ops, dist, world, rank, probes=10000, gallery=1000000, d
 
     def run():
         return U.cosine_identify(pr, shard, k, normalized=True, index_base=lo, sharded=world > 1)
-    val, idx = run()
+    for _ in range(3):                   # warm-up (the first call also sizes the cached workspace)
+        val, idx = run()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
