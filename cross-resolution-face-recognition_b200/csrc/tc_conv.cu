@@ -427,9 +427,9 @@ struct WgCfg {
   static constexpr int kXBytes = H ? 2 * kTile16K : TAPS * kTile16K;
   static constexpr int kStageBytes = kXBytes + kDyTiles * kTile16K;
   static constexpr int kStages = (kStageBytes <= 32 * 1024) ? 6 : (kStageBytes <= 48 * 1024) ? 4 : (kStageBytes <= 64 * 1024) ? 3 : 2;
-  static constexpr bool kSwap = TAPS == 3 && N == 128;             // dY as the M operand, the three tap views along N
+  static constexpr bool kSwap = TAPS == 3 && (N == 128 || N == 64);   // dY as the M operand, the three tap views along N
   static constexpr int kAccs = (TAPS + 1) / 2;                     // accumulators of M = 128 (two taps each)
-  static constexpr int kTmemCols = (kAccs * N <= 64) ? 64 : (kAccs * N <= 128) ? 128 : 256;
+  static constexpr int kTmemCols = kSwap ? 256 : (kAccs * N <= 64) ? 64 : (kAccs * N <= 128) ? 128 : 256;   // kSwap: 192 columns
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
 };
 
@@ -508,7 +508,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     }
   } else if (warp == 1) {
     const bool leader = elect_one();
-    const uint32_t idesc = Cfg::kSwap ? make_idesc_bf16(128, 192, 1, 1) : make_idesc_bf16(128, N, 1, 1);
+    const uint32_t idesc = Cfg::kSwap ? make_idesc_bf16(N, 192, 1, 1) : make_idesc_bf16(128, N, 1, 1);
     // kSwap (three taps, 128 dY channels): the dY tile is the M operand (128 channels: a full M) and the three tap views of X are
     // stacked along N - ONE M = 128, N = 192 MMA per K step, every block of it wanted, instead of two M = 128, N = 128 MMAs of
     // which the second uses half its rows (an M = 64 MMA costs the pipe as much as M = 128): 96 instead of 128 cycles.
@@ -552,16 +552,23 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       // D[co = lane][(tap view a) x 64 ci]: a warp's 32 lanes hold 32 consecutive co of one (tap, ci) -> one coalesced
       // 128-byte reduction per column
 #pragma unroll
+      // (64 dY channels: an M = 64 accumulator keeps row i in lane 32 * (i / 16) + i % 16 - the upper half of every warp's
+      // lanes holds nothing)
+      const int co = N == 64 ? q * 16 + lane : r;
+      const bool live = N != 64 || lane < 16;
+#pragma unroll
       for (int c0 = 0; c0 < 192; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c0, v);
         tmem_ld_wait();
         const int a = c0 / 64;
         const int tap = H ? a * 3 + ky : ky * 3 + a;
-        float* dst = p.G + ((long long)tap * p.cin + kc * 64 + (c0 & 63)) * p.cout + ncol0 + r;
+        float* dst = p.G + ((long long)tap * p.cin + kc * 64 + (c0 & 63)) * p.cout + ncol0 + co;
+        if (live) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + (long long)j * p.cout), "f"(__uint_as_float(v[j])) : "memory");
+          for (int j = 0; j < 32; ++j)
+            asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + (long long)j * p.cout), "f"(__uint_as_float(v[j])) : "memory");
+        }
       }
     } else
 #pragma unroll
