@@ -120,7 +120,7 @@ landmark_kernel(const float* __restrict__ x, const float* __restrict__ t, long l
       const long long ik = wbase + k;
       if (ik >= npix) break;                                    // warp-uniform
       unsigned short* row = reinterpret_cast<unsigned short*>(dx) + ik * dx_ld + coff;
-      const int head = (int)((ik * dx_ld + coff) & 1);          // the row starts in the middle of a 4-byte word
+      const int head = (int)(((uintptr_t)row >> 1) & 1);        // the row starts in the middle of a 4-byte word
       if (head && lane == 0) row[0] = gk;
       const int pairs = (c - head) >> 1;
       uint32_t* rw = reinterpret_cast<uint32_t*>(row + head);

@@ -456,6 +456,26 @@ def test_losses_against_golden_and_torch(cuda, golden_dir):
     assert float(buf[..., 108:].float().abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("n,h,w,ld,coff", [(1, 3, 5, 104, 0), (3, 7, 9, 112, 11), (2, 8, 8, 100, 2), (5, 5, 7, 99, 1)])
+def test_landmark_gradient_rows_ragged(cuda, n, h, w, ld, coff):
+    """The landmark loss writes each pixel's 97 equal gradients as one row of the heads' gradient buffer, a warp per 32 pixels:
+    pixel counts that are no multiple of the warp, rows that start on odd and even elements, odd row pitches; everything
+    outside the rows stays untouched."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(n * 100 + coff)
+    lm = torch.randn(n, 97, h, w, generator=g)
+    hm = torch.rand(n, h, w, generator=g)
+    lmr = lm.clone().requires_grad_(True)
+    (0.3 * ((lmr.sum(1) - hm) ** 2).mean() * 97.0).backward()
+    buf = torch.full((n, h, w, ld), 7.0, dtype=torch.bfloat16, device="cuda")
+    loss = ops.loss_landmark(lm.cuda(), hm.cuda(), 0.3, buf, coff)
+    ref = (((lm.sum(1) - hm) ** 2).mean() * 97.0).item()
+    assert abs(loss.item() - ref) < F32_TOL * abs(ref)
+    assert rel_err(to_nchw(buf[..., coff:coff + 97]), lmr.grad) < BF16_TOL
+    rest = torch.cat([buf[..., :coff], buf[..., coff + 97:]], -1).float()
+    assert bool((rest == 7.0).all())
+
+
 def test_loss_modules_dropin(cuda):
     """MSELossFunc / MSELoss_Landmark / CrossEntropyLoss2d keep the reference call signature and autograd behaviour."""
     from crfr_b200.loss import CrossEntropyLoss2d, MSELoss_Landmark, MSELossFunc
