@@ -41,6 +41,8 @@ DIRECT_SHAPES = [
     (64, 128, 1, 2, 0, 56),    # layer2.0.downsample.0
     (256, 512, 3, 2, 1, 14),   # layer4.0.conv1
     (256, 512, 1, 2, 0, 14),   # layer4.0.downsample.0
+    (3, 64, 7, 4, 3, 48),      # stems at sizes whose pixel count is no multiple of the gather kernel's 64-pixel blocks
+    (3, 64, 7, 2, 3, 50),
 ]
 
 
