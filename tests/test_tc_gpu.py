@@ -27,6 +27,8 @@ TC_SHAPES = [
     (2, 128, 128, 28),    # layer2
     (3, 256, 256, 14),    # layer3: 126-pixel tiles, ragged last tile
     (5, 512, 512, 7),     # layer4: two images per tile, two 256-wide column tiles
+    (2, 64, 128, 24),     # cin != cout with 128 output channels (weight gradient: dY as the M operand, one K chunk)
+    (3, 128, 64, 12),     # ... and with 64 (M = 64 accumulator, two K chunks)
 ]
 
 
