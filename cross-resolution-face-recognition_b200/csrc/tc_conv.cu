@@ -745,7 +745,7 @@ int crfr_tc_wgrad_raw(const TcWgrad& g, cudaStream_t st) {
   if (splits > p.total_tiles) splits = p.total_tiles;
   if (splits < 1) splits = 1;
   if (g.taps3x3) {
-    if (t.bn == 1 && (t.bw & 7) == 0 && (t.bh + 2) * t.bw <= 256 && (g.cout == 64 || g.cout % 128 == 0)) {
+    if (t.bn == 1 && (t.bh + 2) * t.bw <= 256 && (g.cout == 64 || g.cout % 128 == 0)) {
       CUtensorMap tmXh;   // the X box with its two halo rows
       CRFR_TRY(make_act_map(&tmXh, g.x, g.n, g.h, g.w, g.cin, g.x_ld, t.bw, t.bh + 2, 1));
       if (g.cout == 64) return launch_wgrad<64, 3, true>(tmXh, tmDY, p, splits, st);
