@@ -94,8 +94,9 @@ constexpr int kATileBytes = 128 * 128;
 // form asks for 128 rows per (tap, K chunk) step - 1 152 rows and 72 KB of re-streamed weights per pixel tile, which bounds
 // the 64 -> 64 layers at 766 cycles per K step with the tensor pipe 17 % active (ncu: nothing else above 25 % of its peak).
 // R keeps all nine weight tiles resident in shared memory and loads ONE box per kx shift that also holds the two halo
-// rows, (bh + 2) x bw pixels: the three ky taps of a kx are row offsets into the same box (bw % 8 == 0 keeps the offsets on
-// swizzle-atom boundaries).  576 rows per tile instead of 1 152, 3 ring steps of 12 MMAs instead of 9 of 4.
+// rows, (bh + 2) x bw pixels: the three ky taps of a kx are row offsets into the same box (the launcher asks for bw % 8 == 0, which every
+// shape that reaches this form has; the swizzle is a function of the address, so any 128-byte row offset would do - see the
+// weight-gradient form).  576 rows per tile instead of 1 152, 3 ring steps of 12 MMAs instead of 9 of 4.
 constexpr int kResidentIters = 9;
 // MODE 0: generic; 1: R (above); 2: T2 - TWO pixel tiles per weight tile: a ring step loads the activation tiles of two
 // consecutive pixel tiles of the CTA and ONE weight tile, and issues the MMAs of both (four TMEM accumulators: the pair being
