@@ -32,6 +32,17 @@ def test_library_exports_every_declared_symbol(lib):
     assert lib.crfr_version() >= 100
 
 
+def test_integration_doc_lists_every_entry_point():
+    """INTEGRATION.md's appendix (tools/abi_table.py) names every declared entry point next to the reference interface it
+    stands in for."""
+    header = open(os.path.join(ROOT, "include", "crfr.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(crfr_[a-z0-9_]+)\s*\(", header))
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    listed = set(re.findall(r"^\| `(crfr_[a-z0-9_]+)` \|", doc, flags=re.M))
+    assert listed == declared, (sorted(declared - listed), sorted(listed - declared))
+
+
 def test_struct_layouts_match_header():
     from crfr_b200 import _lib
     assert C.sizeof(_lib.ConvDesc) == 13 * 4
