@@ -222,7 +222,8 @@ __global__ void col2im_small_kernel(const float* __restrict__ src, int src_ld, i
   const int Y = (int)(q % bh);
   const long long n = q / bh;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int c = 0; c < C; ++c) acc[c] = bias ? bias[c] : 0.f;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) acc[c] = (bias && c < C) ? bias[c] : 0.f;   // (C <= 4; static indices keep acc in registers)
   // only every stride-th tap can hit a source pixel: start at the first one and step by the stride (the 7x7 stride-4 stems
   // walked all 49 taps with a modulo each to find their 1-4 contributions: 133 us per launch at 128 images)
   const int ky0 = sgn > 0 ? (Y + pad) % stride : ((pad - Y) % stride + stride) % stride;
@@ -238,13 +239,22 @@ __global__ void col2im_small_kernel(const float* __restrict__ src, int src_ld, i
       const int sx = tx / stride;
       if (sx >= sw) continue;
       const float* s = src + ((n * sh + sy) * sw + sx) * src_ld + (ky * ks + kx) * C;
-      for (int c = 0; c < C; ++c) acc[c] += s[c];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (c < C) acc[c] += s[c];
     }
   }
-  if (y_nchw)
-    for (int c = 0; c < C; ++c) y_nchw[(n * C + c) * ((long long)bh * bw) + (long long)Y * bw + X] = acc[c];
-  if (y)
-    for (int c = 0; c < y_ld; ++c) y[i * y_ld + c] = __float2bfloat16_rn(c < C ? acc[c] : 0.f);
+  if (y_nchw) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (c < C) y_nchw[(n * C + c) * ((long long)bh * bw) + (long long)Y * bw + X] = acc[c];
+  }
+  if (y) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (c < y_ld) y[i * y_ld + c] = __float2bfloat16_rn(c < C ? acc[c] : 0.f);
+    for (int c = 4; c < y_ld; ++c) y[i * y_ld + c] = __float2bfloat16_rn(0.f);
+  }
 }
 
 // The 3x3 / stride 1 / pad 1, three-channel case of col2im (forward of conv_mid / conv_out, FSRnet.py:318,439): a block
